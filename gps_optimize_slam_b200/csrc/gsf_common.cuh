@@ -1,0 +1,273 @@
+// Device-side building blocks shared by every kernel of the GPS/SLAM fusion path.
+// fp64 throughout; quaternions are xyzw (scalar last) with the Hamilton product,
+// exactly as scipy's Rotation (the reference's rotation library) defines them.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define GSF_HD __host__ __device__
+#define GSF_D __device__
+#else
+// Host-only build (tests/hostmath): the scalar math below is compiled with g++ so that the
+// CPU test-suite can check it against numpy/scipy without a GPU.
+#define GSF_HD
+#define GSF_D
+#endif
+
+#define GSF_FULL_MASK 0xffffffffu
+#ifndef __CUDACC__
+#define __forceinline__ inline
+#endif
+
+namespace gsf {
+
+// ----------------------------------------------------------------------------- status codes
+// Per-trajectory status written by the batched kernels (mirrors the reference's
+// None-triples / ValueError / RuntimeError exits, EKFGPSSLAM.py:431, :975, :997, :1003).
+enum : int {
+    ST_OK = 0,
+    ST_TOO_FEW_POINTS = 1,     // < 3 points for Umeyama (:431) / < min_samples for Sim3 (:975,:997)
+    ST_DEGENERATE = 2,         // rank-deficient cross-covariance: rotation not unique
+    ST_BAD_QUATERNION = 4,     // zero-norm SLAM quaternion met (scipy raises ValueError)
+    ST_EMPTY = 8,              // zero-length trajectory
+    ST_RANSAC_OUTLIERS = 16,   // all-points fit leaves residuals >= threshold: the reference's
+                               // unseeded RANSAC could pick a different inlier set here
+};
+
+// EKF / pipeline parameters for one trajectory (or shared by the batch).  Values are the
+// reference's CONFIG entries (EKFGPSSLAM.py:22-71) flattened.
+struct FuseParams {
+    double p0[7];            // ekf.initial_cov_diag
+    double q[7];             // ekf.process_noise_diag (per second)
+    double r[3];             // ekf.meas_noise_diag (used as variances, :686)
+    double gap_threshold;    // time_alignment.max_gps_gap_threshold
+    double max_duration;     // sim3_ransac.max_initial_duration
+    double yaw_rate_thresh;  // rts_decision threshold in rad/s
+    double residual_thresh;  // sim3_ransac.residual_threshold
+    double eval_skip;        // 5.0 s evaluation cut (:1021)
+    int min_samples;         // sim3_ransac.min_samples
+    int sharp_turn_steps;    // rts_decision.default_ekf_transition_steps_on_sharp_turn
+};
+static_assert(sizeof(FuseParams) == 23 * 8, "FuseParams layout is part of the C ABI");
+
+// ----------------------------------------------------------------------------- small math
+struct Quat { double x, y, z, w; };
+
+GSF_HD __forceinline__ double rsqrt_(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+GSF_HD __forceinline__ Quat qmul(const Quat& p, const Quat& q) {
+    // scipy compose_quat(p, q): rotation q applied first, then p.
+    Quat r;
+    r.x = p.w * q.x + q.w * p.x + (p.y * q.z - p.z * q.y);
+    r.y = p.w * q.y + q.w * p.y + (p.z * q.x - p.x * q.z);
+    r.z = p.w * q.z + q.w * p.z + (p.x * q.y - p.y * q.x);
+    r.w = p.w * q.w - p.x * q.x - p.y * q.y - p.z * q.z;
+    return r;
+}
+GSF_HD __forceinline__ Quat qconj(const Quat& q) { return Quat{-q.x, -q.y, -q.z, q.w}; }
+GSF_HD __forceinline__ double qnorm2(const Quat& q) { return q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w; }
+GSF_HD __forceinline__ Quat qscale(const Quat& q, double s) { return Quat{q.x * s, q.y * s, q.z * s, q.w * s}; }
+
+// scipy Rotation.from_quat normalisation (raises on zero norm: caller checks n2 == 0 first).
+GSF_HD __forceinline__ Quat qunit(const Quat& q) { return qscale(q, rsqrt_(qnorm2(q))); }
+
+// ExtendedKalmanFilter.normalize_quaternion (EKFGPSSLAM.py:697-700): identity below 1e-9.
+GSF_HD __forceinline__ Quat qunit_or_identity(const Quat& q) {
+    double n2 = qnorm2(q);
+    if (!(n2 > 1e-18)) return Quat{0.0, 0.0, 0.0, 1.0};
+    return qscale(q, rsqrt_(n2));
+}
+
+// scipy as_matrix (row-major).  Homogeneous of degree 2 in q; q is unit on every call site.
+GSF_HD __forceinline__ void qmat(const Quat& q, double* M) {
+    double x2 = q.x * q.x, y2 = q.y * q.y, z2 = q.z * q.z, w2 = q.w * q.w;
+    double xy = q.x * q.y, zw = q.z * q.w, xz = q.x * q.z, yw = q.y * q.w, yz = q.y * q.z, xw = q.x * q.w;
+    M[0] = x2 - y2 - z2 + w2; M[1] = 2.0 * (xy - zw);     M[2] = 2.0 * (xz + yw);
+    M[3] = 2.0 * (xy + zw);     M[4] = -x2 + y2 - z2 + w2; M[5] = 2.0 * (yz - xw);
+    M[6] = 2.0 * (xz - yw);     M[7] = 2.0 * (yz + xw);    M[8] = -x2 - y2 + z2 + w2;
+}
+GSF_HD __forceinline__ void mat_vec(const double* M, double x, double y, double z, double& ox, double& oy, double& oz) {
+    ox = M[0] * x + M[1] * y + M[2] * z;
+    oy = M[3] * x + M[4] * y + M[5] * z;
+    oz = M[6] * x + M[7] * y + M[8] * z;
+}
+GSF_HD __forceinline__ void matT_vec(const double* M, double x, double y, double z, double& ox, double& oy, double& oz) {
+    ox = M[0] * x + M[3] * y + M[6] * z;
+    oy = M[1] * x + M[4] * y + M[7] * z;
+    oz = M[2] * x + M[5] * y + M[8] * z;
+}
+
+// scipy _from_matrix_orthogonal: pick the largest of (m00, m11, m22, trace), no sign
+// canonicalisation, normalise.
+GSF_HD inline Quat quat_from_matrix(const double* m) {
+    double tr = m[0] + m[4] + m[8];
+    int choice = 0; double best = m[0];
+    if (m[4] > best) { best = m[4]; choice = 1; }
+    if (m[8] > best) { best = m[8]; choice = 2; }
+    if (tr > best) { choice = 3; }
+    Quat q;
+    if (choice == 0)      { q.x = 1.0 - tr + 2.0 * m[0]; q.y = m[3] + m[1]; q.z = m[6] + m[2]; q.w = m[7] - m[5]; }
+    else if (choice == 1) { q.x = m[3] + m[1]; q.y = 1.0 - tr + 2.0 * m[4]; q.z = m[7] + m[5]; q.w = m[2] - m[6]; }
+    else if (choice == 2) { q.x = m[6] + m[2]; q.y = m[7] + m[5]; q.z = 1.0 - tr + 2.0 * m[8]; q.w = m[3] - m[1]; }
+    else                  { q.x = m[7] - m[5]; q.y = m[2] - m[6]; q.z = m[3] - m[1]; q.w = 1.0 + tr; }
+    return qunit(q);
+}
+
+// First angle of scipy as_euler('zyx') (extrinsic z-y-x; i=2, j=1, k=0, sign=-1), including
+// its gimbal-lock cases (_get_angles, eps = 1e-7).  Used by the sharp-turn gate
+// (EKFGPSSLAM.py:819-820).
+GSF_HD inline double yaw_zyx(const Quat& q) {
+    const double PI = 3.141592653589793238462643383279502884;
+    double a = q.w - q.y, b = q.z - q.x, c = q.y + q.w, d = -q.x - q.z;
+    double half_sum = atan2(b, a), half_diff = atan2(d, c);
+    double second = 2.0 * atan2(hypot(c, d), hypot(a, b));
+    double first;
+    if (fabs(second) <= 1e-7) first = 2.0 * half_sum;
+    else if (fabs(second - PI) <= 1e-7) first = -2.0 * half_diff;
+    else first = half_sum - half_diff;
+    // (angle + pi) mod 2pi - pi with Python's sign-of-divisor modulo
+    double m = fmod(first + PI, 2.0 * PI);
+    if (m < 0.0) m += 2.0 * PI;
+    return m - PI;
+}
+
+// ----------------------------------------------------------------------------- 3x3 SVD pieces
+// One-sided (Hestenes) Jacobi on the columns of A (row-major 3x3): A <- A*V with V
+// accumulated, until the columns are mutually orthogonal to working precision.  Gives high
+// relative accuracy for the small singular directions, which decide the roll of a
+// near-collinear track (KITTI-04: sigma = 3.4e6 / 10.7 / 1.45).
+GSF_HD inline void jacobi_rotate(double* A, double* V, int p, int q, bool& rotated) {
+    double ap0 = A[p], ap1 = A[3 + p], ap2 = A[6 + p];
+    double aq0 = A[q], aq1 = A[3 + q], aq2 = A[6 + q];
+    double alpha = ap0 * ap0 + ap1 * ap1 + ap2 * ap2;
+    double beta = aq0 * aq0 + aq1 * aq1 + aq2 * aq2;
+    double gamma = ap0 * aq0 + ap1 * aq1 + ap2 * aq2;
+    if (gamma * gamma <= 1e-31 * alpha * beta || gamma == 0.0) return;   // |cos angle| <= 3.2e-16
+    rotated = true;
+    double d = beta - alpha, g2 = 2.0 * gamma;
+    double hyp = sqrt(d * d + g2 * g2);
+    double t = (d >= 0.0 ? g2 : -g2) / (fabs(d) + hyp);
+    double c = rsqrt_(1.0 + t * t), s = c * t;
+    A[p] = c * ap0 - s * aq0; A[3 + p] = c * ap1 - s * aq1; A[6 + p] = c * ap2 - s * aq2;
+    A[q] = s * ap0 + c * aq0; A[3 + q] = s * ap1 + c * aq1; A[6 + q] = s * ap2 + c * aq2;
+    double vp0 = V[p], vp1 = V[3 + p], vp2 = V[6 + p], vq0 = V[q], vq1 = V[3 + q], vq2 = V[6 + q];
+    V[p] = c * vp0 - s * vq0; V[3 + p] = c * vp1 - s * vq1; V[6 + p] = c * vp2 - s * vq2;
+    V[q] = s * vp0 + c * vq0; V[3 + q] = s * vp1 + c * vq1; V[6 + q] = s * vp2 + c * vq2;
+}
+
+// Umeyama's rotation + scale from the (un-normalised) cross-covariance H = src_c^T dst_c,
+// restating EKFGPSSLAM.py:439-449:  U,S,Vt = svd(H); R = Vt^T U^T; if det(R) < 0 negate the
+// last row of Vt; scale numerator = S1 + S2 + S3*det(R_fixed) = S1+S2+S3 in both branches.
+// With singular pairs (u_i, v_i) sorted by sigma, the det=+1 matrix V diag(1,1,d) U^T equals
+// v1 u1^T + v2 u2^T + (v1 x v2)(u1 x u2)^T, so only the two dominant pairs are needed.
+// Returns false when sigma_2 is numerically zero (collinear points: R not unique).
+GSF_HD inline bool umeyama_rotation(const double* H, double* R, double& sigma_sum, bool& reflected) {
+    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = H[i];
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool rotated = false;
+        jacobi_rotate(A, V, 0, 1, rotated);
+        jacobi_rotate(A, V, 0, 2, rotated);
+        jacobi_rotate(A, V, 1, 2, rotated);
+        if (!rotated) break;
+    }
+    double sg[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sg[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+    int i0 = 0, i1 = 1, i2 = 2;                    // sort descending
+    if (sg[i0] < sg[i1]) { int t = i0; i0 = i1; i1 = t; }
+    if (sg[i0] < sg[i2]) { int t = i0; i0 = i2; i2 = t; }
+    if (sg[i1] < sg[i2]) { int t = i1; i1 = i2; i2 = t; }
+    sigma_sum = sg[i0] + sg[i1] + sg[i2];
+    // det(H) = det(U) det(V) sigma1 sigma2 sigma3 decides the reflection branch.
+    double detH = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
+    reflected = detH < 0.0;
+    bool ok = sg[i1] > 1e-14 * sg[i0] && sg[i0] > 0.0;
+    double u1[3], u2[3], v1[3], v2[3];
+    double r0 = sg[i0] > 0.0 ? 1.0 / sg[i0] : 0.0, r1 = sg[i1] > 0.0 ? 1.0 / sg[i1] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        u1[k] = A[3 * k + i0] * r0; u2[k] = A[3 * k + i1] * r1;
+        v1[k] = V[3 * k + i0];      v2[k] = V[3 * k + i1];
+    }
+    // re-orthonormalise u2 against u1 (no-op to rounding when converged)
+    double dp = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u2[k] -= dp * u1[k];
+    double n2 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
+    if (n2 > 0.0) { double rn = rsqrt_(n2); u2[0] *= rn; u2[1] *= rn; u2[2] *= rn; }
+    double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+    double v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = v1[r] * u1[c] + v2[r] * u2[c] + v3[r] * u3[c];
+    return ok;
+}
+
+// Finish Umeyama (EKFGPSSLAM.py:443-451) from the reduced sums.
+//   n      number of points, mu_s/mu_d centroids, H centred cross-covariance (not / n),
+//   ss     sum |src_c|^2.
+// Outputs R (row-major), t, s; returns status bits.
+GSF_HD inline int umeyama_finish(int n, const double* mu_s, const double* mu_d, const double* H, double ss,
+                                     double* R, double* t, double& s) {
+    double sigma_sum; bool refl;
+    bool ok = umeyama_rotation(H, R, sigma_sum, refl);
+    double var_src = ss / (double)n;
+    if (var_src < 1e-12) s = 1.0;
+    else { s = sigma_sum / ((double)n * var_src); if (s <= 1e-6) s = 1.0; }
+    double rx, ry, rz;
+    mat_vec(R, mu_s[0], mu_s[1], mu_s[2], rx, ry, rz);
+    t[0] = mu_d[0] - s * rx; t[1] = mu_d[1] - s * ry; t[2] = mu_d[2] - s * rz;
+    return ok ? ST_OK : ST_DEGENERATE;
+}
+
+#ifdef __CUDACC__
+// ----------------------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GSF_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GSF_FULL_MASK, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum of K doubles per thread: fixed xor-shuffle tree inside each
+// warp, then warp partials combined in warp order through shared memory.  `scratch` needs
+// K * (blockDim.x / 32) doubles.  Every thread returns with the totals in v[].
+template <int K>
+__device__ inline void block_sum(double* v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    if (nwarp == 1) return;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) scratch[warp * K + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double acc = scratch[k];
+        for (int w = 1; w < nwarp; ++w) acc += scratch[w * K + k];
+        v[k] = acc;
+    }
+}
+
+#endif  // __CUDACC__
+
+GSF_HD __forceinline__ bool row_has_nan(double a, double b, double c) { return isnan(a) || isnan(b) || isnan(c); }
+
+}  // namespace gsf
