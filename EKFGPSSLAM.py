@@ -1,0 +1,398 @@
+# -*- coding: utf-8 -*-
+"""Drop-in entry point: the reference's ``EKFGPSSLAM.py`` function surface on B200 kernels.
+
+Same module name, function names, argument meaning, return conventions, ``CONFIG`` keys and
+output file formats as /root/reference/EKFGPSSLAM.py; the arithmetic of every function below
+runs in libgsf.so (hand-written sm_100a CUDA, gps_optimize_slam_b200/csrc) through the C ABI in
+include/gsf.h.  Host code only parses files, sorts/uniques GNSS stamps and moves arrays.
+There is no CPU fallback: without the built library or without a B200 every call raises.
+
+    python EKFGPSSLAM.py SLAM.txt GNSS.txt [--truth GNSS_TRUTH.txt] [--save OUT_utm.txt]
+
+replaces the reference's tkinter dialogs (EKFGPSSLAM.py:940-953; tkinter/matplotlib are not
+part of this path).  Plotting (:470-666) is out of scope.
+
+Differences a caller can observe, all documented in DESIGN.md:
+  * ``compute_sim3_transform_robust`` is deterministic: it returns the all-points Umeyama fit
+    (what the reference's unseeded RANSAC converges to whenever all points are inliers, which
+    holds on the shipped data) and warns when residuals >= threshold exist.
+  * the UTM projection is the Krueger series kernel, not PROJ (pyproj is not installed).
+"""
+from __future__ import annotations
+
+import sys
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from gps_optimize_slam_b200 import _lib, fusion
+from gps_optimize_slam_b200.config import CONFIG, EVAL_SKIP_SECONDS, pack_fuse_params
+
+_DEV = "cuda"
+
+
+def _dev(a, dtype=torch.float64):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=_DEV, dtype=dtype)
+
+
+def _one(n):
+    return torch.tensor([0, n], dtype=torch.int64, device=_DEV)
+
+
+# ----------------------------------------------------------------------------- helpers (API parity)
+def calculate_relative_pose(pose1_pos, pose1_quat, pose2_pos, pose2_quat):
+    """EKFGPSSLAM.py:77-92.  Kept for API compatibility: evaluated by the strict EKF kernel on a
+    two-pose trajectory (delta = pose of step 1 expressed in frame 0)."""
+    ts = np.array([0.0, 1.0])
+    pos = np.stack([np.zeros(3), np.asarray(pose2_pos, float) - np.asarray(pose1_pos, float)])
+    quat = np.stack([np.asarray(pose1_quat, float), np.asarray(pose2_quat, float)])
+    z = np.full((2, 3), np.nan)
+    p, q, st = fusion.ekf_strict_batched(_dev(ts), _dev(pos), _dev(quat), _dev(z), _one(2),
+                                         fusion.params_tensor(CONFIG), _dev(np.zeros((1, 3))),
+                                         _dev(np.array([[0.0, 0.0, 0.0, 1.0]])))
+    if int(st.cpu()[0]) & _lib.ST_BAD_QUATERNION:
+        return np.zeros(3), np.array([0.0, 0.0, 0.0, 1.0])
+    return p[1].cpu().numpy(), q[1].cpu().numpy()
+
+
+# ----------------------------------------------------------------------------- loading
+def load_slam_trajectory(txt_path: str) -> Dict[str, np.ndarray]:
+    """TUM file ``ts x y z qx qy qz qw`` (EKFGPSSLAM.py:110-125)."""
+    try:
+        table = np.loadtxt(txt_path)
+        if table.ndim == 1:
+            table = table.reshape(1, -1)
+        if table.shape[1] != 8:
+            raise ValueError(f"SLAM file must have 8 columns (ts x y z qx qy qz qw), found {table.shape[1]}")
+    except FileNotFoundError:
+        raise ValueError(f"SLAM file not found: {txt_path}")
+    except Exception as exc:
+        raise ValueError(f"failed to load SLAM data ({txt_path}): {exc}")
+    return {"timestamps": table[:, 0].astype(float), "positions": table[:, 1:4].astype(float),
+            "quaternions": table[:, 4:8].astype(float)}
+
+
+class UTMProjector:
+    """Call-compatible with the ``pyproj.Proj`` object the reference stores in
+    gps_data['projector'] (EKFGPSSLAM.py:268-270, :295): ``proj(lon, lat)`` and
+    ``proj(E, N, inverse=True)``, evaluated by the Krueger-series kernels."""
+
+    def __init__(self, zone: int, south: bool):
+        self.zone, self.south = int(zone), bool(south)
+        self.srs = f"+proj=utm +zone={self.zone}{' +south' if self.south else ''} +ellps=WGS84 +datum=WGS84 +units=m +no_defs"
+
+    def __call__(self, x, y, inverse: bool = False):
+        a, b = _dev(np.atleast_1d(x)), _dev(np.atleast_1d(y))
+        fn = fusion.utm_inverse if inverse else fusion.utm_forward
+        u, v = fn(a, b, self.zone, self.south)
+        return u.cpu().numpy(), v.cpu().numpy()
+
+
+def auto_utm_projection(lons: np.ndarray, lats: np.ndarray) -> Tuple[int, str]:
+    """EKFGPSSLAM.py:127-134 (mean reduction on the device)."""
+    if lons.size == 0 or lats.size == 0:
+        raise ValueError("lon/lat arrays must not be empty")
+    out = fusion.geo_zone(_dev(lons), _dev(lats)).cpu().numpy()
+    return int(out[2]), (" +south" if out[3] else "")
+
+
+def filter_gps_outliers_ransac(times, positions, config):
+    """EKFGPSSLAM.py:136-247.  Host-side and unseeded in the reference (sklearn RANSACRegressor);
+    outside the kernel scope (SURVEY 2, row "GPS outlier RANSAC").  Same windowing, same
+    sklearn estimators, when sklearn is importable."""
+    if not config.get("enabled", False) or len(times) < config["min_samples"]:
+        return times, positions
+    from sklearn.linear_model import RANSACRegressor
+    from sklearn.pipeline import make_pipeline
+    from sklearn.preprocessing import PolynomialFeatures
+
+    def inliers(t, xyz):
+        masks = []
+        for axis in range(xyz.shape[1]):
+            model = make_pipeline(PolynomialFeatures(degree=config["polynomial_degree"]),
+                                  RANSACRegressor(min_samples=config["min_samples"],
+                                                  residual_threshold=config["residual_threshold_meters"],
+                                                  max_trials=config["max_trials"]))
+            model.fit(t.reshape(-1, 1), xyz[:, axis])
+            masks.append(model[-1].inlier_mask_)
+        return np.logical_and.reduce(masks)
+
+    if not config.get("use_sliding_window", False):
+        try:
+            keep = inliers(times, positions)
+        except Exception:
+            return times, positions
+        return times[keep], positions[keep]
+    width = config["window_duration_seconds"]
+    step = width * config["window_step_factor"]
+    keep = np.zeros(len(times), dtype=bool)
+    start, t_end = times[0], times[-1]
+    while start < t_end:
+        stop = start + width
+        idx = np.where((times >= start) & (times < stop))[0]
+        if len(idx) >= config["min_samples"]:
+            try:
+                keep[idx[inliers(times[idx], positions[idx])]] = True
+            except Exception:
+                pass
+        if step <= 1e-6:
+            later = np.where(times > start)[0]
+            if len(later) == 0:
+                break
+            start = times[later[0]]
+        else:
+            start += step
+        if start >= t_end and times[-1] >= stop:
+            start = max(times[0], times[-1] - width + 1e-6)
+    return times[keep], positions[keep]
+
+
+def load_gps_data(txt_path: str, data_label: str = "GPS",
+                  filter_config_override: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+    """GNSS rows ``ts lat lon alt ...`` -> UTM (EKFGPSSLAM.py:249-289)."""
+    try:
+        try:
+            raw = np.loadtxt(txt_path, delimiter=" ")
+        except ValueError:
+            raw = np.loadtxt(txt_path, delimiter=",")
+        if raw.ndim == 1:
+            raw = raw.reshape(1, -1)
+        if raw.shape[1] < 4:
+            raise ValueError(f"{data_label} file needs at least 4 columns (ts lat lon alt), found {raw.shape[1]}")
+        ts, lat, lon, alt = raw[:, 0], raw[:, 1], raw[:, 2], raw[:, 3]
+        keep = (np.abs(lat) <= 90) & (np.abs(lon) <= 180) & (lat != 0) & (lon != 0)
+        if not np.all(keep):
+            print(f"warning ({data_label}): dropped {int((~keep).sum())} invalid lat/lon rows")
+            ts, lat, lon, alt = ts[keep], lat[keep], lon[keep], alt[keep]
+            if len(ts) == 0:
+                raise ValueError(f"{data_label}: no valid GNSS rows")
+        zone, hemi = auto_utm_projection(lon, lat)
+        projector = UTMProjector(zone, "south" in hemi)
+        east, north = projector(lon, lat)
+        utm = np.column_stack((east, north, alt))
+        cfg = filter_config_override if filter_config_override is not None else CONFIG["gps_filtering_ransac"]
+        ts_f, utm_f = filter_gps_outliers_ransac(ts, utm, cfg)
+        if len(ts_f) < 2:
+            raise ValueError(f"{data_label}: fewer than 2 points left after filtering")
+        return {"timestamps": ts_f, "positions": utm_f,
+                "utm_zone": f"{zone}{'S' if 'south' in hemi else 'N'}", "projector": projector}
+    except FileNotFoundError:
+        raise ValueError(f"{data_label} file not found: {txt_path}")
+    except _lib.GsfError:
+        raise
+    except Exception as exc:
+        raise ValueError(f"{data_label} processing failed: {exc}")
+
+
+def utm_to_wgs84(utm_points: np.ndarray, projector) -> np.ndarray:
+    """EKFGPSSLAM.py:291-296."""
+    if utm_points.shape[1] != 3:
+        raise ValueError("UTM points must be an Nx3 array")
+    if not isinstance(projector, UTMProjector):
+        raise TypeError("projector must be the object returned in gps_data['projector']")
+    lon, lat = projector(utm_points[:, 0], utm_points[:, 1], inverse=True)
+    return np.column_stack((lon, lat, utm_points[:, 2]))
+
+
+# ----------------------------------------------------------------------------- association
+def estimate_time_offset(slam_times, gps_times, max_samples: int) -> float:
+    """EKFGPSSLAM.py:301-323: correlates two standardised linspaces, which are identical by
+    construction, so the lag -- and the returned offset -- is 0 for every input."""
+    return 0.0
+
+
+def dynamic_time_alignment(slam_data, gps_data_source, time_align_config):
+    """EKFGPSSLAM.py:325-387 -> (aligned [n,3] NaN-filled, valid [n] bool)."""
+    slam_t = np.asarray(slam_data["timestamps"], float)
+    gps_t = np.asarray(gps_data_source["timestamps"], float)
+    gps_p = np.asarray(gps_data_source["positions"], float)
+    n = len(slam_t)
+    aligned, valid = np.full((n, 3), np.nan), np.zeros(n, dtype=bool)
+    if n == 0 or len(gps_t) < 2:
+        return aligned, valid
+    t = gps_t + estimate_time_offset(slam_t, gps_t, time_align_config["max_samples_for_corr"])
+    order = np.argsort(t)                                   # index bookkeeping stays on the host
+    t, p = t[order], gps_p[order]
+    tu, first = np.unique(t, return_index=True)
+    if len(tu) < 2:
+        return aligned, valid
+    if len(tu) < len(t):
+        t, p = tu, p[first]
+    a, v = fusion.associate_spline(_dev(t), _dev(p), _one(len(t)), _dev(slam_t), _one(n),
+                                   gap=float(time_align_config["max_gps_gap_threshold"]))
+    return a.cpu().numpy(), v.cpu().numpy().astype(bool)
+
+
+# ----------------------------------------------------------------------------- Sim3
+def compute_sim3_transform(src: np.ndarray, dst: np.ndarray):
+    """Umeyama (EKFGPSSLAM.py:428-459) -> (R, t, s) or (None, None, None)."""
+    if src.shape[0] < 3 or src.shape != dst.shape or src.shape[1] != 3:
+        return None, None, None
+    n = src.shape[0]
+    R, t, s, st = fusion.umeyama_batched(_dev(src), _dev(dst), _one(n), n)
+    if int(st.cpu()[0]) & _lib.ST_TOO_FEW_POINTS:
+        return None, None, None
+    return R[0].cpu().numpy(), t[0].cpu().numpy(), float(s[0].cpu())
+
+
+def compute_sim3_transform_robust(src, dst, min_samples, residual_threshold, max_trials,
+                                  min_inliers_needed, point_description: str = "points"):
+    """EKFGPSSLAM.py:389-426.  Deterministic stand-in for the unseeded RANSAC: the all-points
+    fit, which is what the reference returns whenever every point is an inlier of the best
+    trial; residuals >= threshold are counted on the device and reported."""
+    n = src.shape[0]
+    if n < min_samples or src.shape != dst.shape:
+        return None, None, None
+    R, t, s = compute_sim3_transform(src, dst)
+    if R is None:
+        return None, None, None
+    sp, _, _ = fusion.sim3_apply_batched(_dev(src), _dev(np.tile([0.0, 0.0, 0.0, 1.0], (n, 1))), _one(n), n,
+                                         _dev(R[None]), _dev(t[None]), _dev(np.array([s])))
+    resid = torch.linalg.norm(sp - _dev(dst), dim=1)
+    outliers = int((~(resid < residual_threshold)).sum().cpu())
+    if outliers:
+        print(f"warning: Sim3 all-points fit leaves {outliers}/{n} {point_description} with residual >= "
+              f"{residual_threshold} m; the reference's randomised RANSAC may pick a different inlier set")
+    if n - outliers < min_inliers_needed:
+        return None, None, None
+    return R, t, s
+
+
+def transform_trajectory(positions, quaternions, R_mat, t_vec, scale_val):
+    """EKFGPSSLAM.py:461-467."""
+    n = positions.shape[0]
+    p, q, st = fusion.sim3_apply_batched(_dev(positions), _dev(quaternions), _one(n), n, _dev(np.asarray(R_mat)[None]),
+                                         _dev(np.asarray(t_vec)[None]), _dev(np.array([scale_val], dtype=float)))
+    if int(st.cpu()[0]) & _lib.ST_BAD_QUATERNION:
+        raise ValueError("Found zero norm quaternions in `quat`.")
+    return p.cpu().numpy(), q.cpu().numpy()
+
+
+def select_sim3_indices(slam_timestamps, valid_mask, config=CONFIG):
+    """Orchestrator logic of EKFGPSSLAM.py:972-998 (index bookkeeping, host)."""
+    allv = np.where(valid_mask)[0]
+    need = config["sim3_ransac"]["min_samples"]
+    if len(allv) < need:
+        raise ValueError(f"only {len(allv)} time-synchronised points for Sim3 (< {need})")
+    gaps = np.where(np.diff(slam_timestamps[allv]) > config["time_alignment"]["max_gps_gap_threshold"])[0]
+    first = allv[:gaps[0]] if len(gaps) else allv
+    if len(first) < need:
+        return allv
+    timed = first[slam_timestamps[first] <= slam_timestamps[first[0]] + config["sim3_ransac"]["max_initial_duration"]]
+    return first if len(timed) < need else timed
+
+
+# ----------------------------------------------------------------------------- EKF
+def apply_ekf_correction(slam_data_in, gps_data_in, sim3_pos_initial, sim3_quat_initial, global_config):
+    """EKFGPSSLAM.py:831-935 -> (corrected_pos [n,3], corrected_quat [n,4])."""
+    ts = np.asarray(slam_data_in["timestamps"], float)
+    n = len(ts)
+    if n == 0:
+        return np.empty((0, 3)), np.empty((0, 4))
+    if not (sim3_pos_initial.shape[0] == n and sim3_quat_initial.shape[0] == n):
+        raise ValueError(f"Sim3-aligned trajectory has {sim3_pos_initial.shape[0]} poses, SLAM has {n}")
+    aligned, valid = dynamic_time_alignment(slam_data_in, gps_data_in, global_config["time_alignment"])
+    z = np.where(valid[:, None], aligned, np.nan)
+    args = (_dev(ts), _dev(slam_data_in["positions"]), _dev(slam_data_in["quaternions"]), _dev(z), _one(n))
+    prm = fusion.params_tensor(global_config)
+    ip, iq = _dev(sim3_pos_initial[:1]), _dev(sim3_quat_initial[:1])
+    p, q, _, st = fusion.fuse_batched(*args, n, prm, init_pos=ip, init_quat=iq)
+    code = int(st.cpu()[0])
+    if code & (_lib.ST_BAD_QUATERNION | _lib.ST_TOO_LONG):
+        # general path: zero-norm quaternions (zero-motion fallback, :84-86) or a trajectory
+        # longer than the shared-memory staging buffer
+        p, q, st = fusion.ekf_strict_batched(*args, prm, ip, iq)
+    return p.cpu().numpy(), q.cpu().numpy()
+
+
+def fuse_trajectory(slam_data, aligned, config=CONFIG):
+    """Whole device path for one trajectory with associated measurements: Sim3 selection +
+    Umeyama + EKF in ONE kernel launch -> dict(R, t, s, pos, quat, status)."""
+    ts = np.asarray(slam_data["timestamps"], float)
+    n = len(ts)
+    p, q, sim3, st = fusion.fuse_batched(_dev(ts), _dev(slam_data["positions"]), _dev(slam_data["quaternions"]),
+                                         _dev(aligned), _one(n), n, fusion.params_tensor(config))
+    s3 = sim3[0].cpu().numpy()
+    return {"R": s3[:9].reshape(3, 3), "t": s3[9:12], "s": float(s3[12]), "n_selected": int(s3[13]),
+            "pos": p.cpu().numpy(), "quat": q.cpu().numpy(), "status": int(st.cpu()[0])}
+
+
+# ----------------------------------------------------------------------------- evaluation + orchestration
+def evaluate_errors(traj_xyz, aligned, slam_timestamps, skip_seconds: float = EVAL_SKIP_SECONDS):
+    """EKFGPSSLAM.py:1021-1033 -> (mean, median, rmse, count) of nearest-neighbour errors."""
+    n = len(slam_timestamps)
+    stats = fusion.ate_nn_batched(_dev(traj_xyz), _dev(aligned), _dev(slam_timestamps), _one(n), n, skip_seconds)
+    m, med, rmse, cnt = stats[0].cpu().numpy()
+    return float(m), float(med), float(rmse), int(cnt)
+
+
+def save_results(slam_path, out_path_utm, timestamps, corrected_pos, corrected_quat, projector):
+    """Writers of EKFGPSSLAM.py:1087-1102 (same formats, headers and file naming)."""
+    np.savetxt(out_path_utm, np.column_stack((timestamps, corrected_pos, corrected_quat)),
+               fmt=["%.6f"] + ["%.6f"] * 3 + ["%.8f"] * 4, header="timestamp x y z qx qy qz qw (UTM)", comments="")
+    wgs = utm_to_wgs84(corrected_pos, projector)
+    out_wgs = out_path_utm.replace("_utm.txt", "_wgs84.txt")
+    if out_wgs == out_path_utm:
+        out_wgs = out_path_utm.replace(".txt", "_wgs84.txt") if ".txt" in out_path_utm else out_path_utm + "_wgs84.txt"
+    np.savetxt(out_wgs, np.column_stack((timestamps, wgs, corrected_quat)),
+               fmt=["%.6f"] + ["%.8f", "%.8f", "%.3f"] + ["%.8f"] * 4,
+               header="timestamp lon lat alt qx qy qz qw (WGS84)", comments="")
+    return out_path_utm, out_wgs
+
+
+def main_process(slam_path: str, gps_path: str, ground_truth_gps_path: str = "", save_path: str = ""):
+    """Steps 1-7 of main_process_gui (EKFGPSSLAM.py:940-1110) without dialogs and plots."""
+    print("step 1/7: loading data")
+    slam = load_slam_trajectory(slam_path)
+    gps = load_gps_data(gps_path, "primary GPS", CONFIG["gps_filtering_ransac"])
+    truth = load_gps_data(ground_truth_gps_path, "GNSS truth", CONFIG["ground_truth_gps_filtering"]) if ground_truth_gps_path else None
+    print(f"  SLAM poses: {len(slam['positions'])}, GNSS points: {len(gps['positions'])}, UTM zone {gps['utm_zone']}")
+    if len(slam["positions"]) == 0 or len(gps["positions"]) < 2:
+        raise ValueError("empty SLAM data or fewer than 2 GNSS points")
+    print("step 2/7: time association")
+    aligned, valid = dynamic_time_alignment(slam, gps, CONFIG["time_alignment"])
+    sel = select_sim3_indices(slam["timestamps"], valid)
+    print(f"  {int(valid.sum())} synchronised points, {len(sel)} used for Sim3")
+    print("step 3/7: Sim3")
+    rc = CONFIG["sim3_ransac"]
+    R, t, s = compute_sim3_transform_robust(slam["positions"][sel], aligned[sel], rc["min_samples"], rc["residual_threshold"],
+                                            rc["max_trials"], rc["min_inliers_needed"])
+    if R is None:
+        raise RuntimeError("Sim3 global transform failed")
+    print(f"  scale = {s:.10f}")
+    print("step 4/7: applying Sim3")
+    sim3_pos, sim3_quat = transform_trajectory(slam["positions"], slam["quaternions"], R, t, s)
+    print("step 5/7: EKF + RTS fusion")
+    fused_pos, fused_quat = apply_ekf_correction(slam, gps, sim3_pos, sim3_quat, CONFIG)
+    print("step 6/7: evaluation (first 5 s dropped, nearest interpolated GNSS point)")
+    results = {}
+    refs = [("primary GPS", aligned)]
+    if truth is not None:
+        refs.append(("GNSS truth", dynamic_time_alignment(slam, truth, CONFIG["time_alignment"])[0]))
+    for ref_name, cand in refs:
+        for label, traj in (("raw SLAM", slam["positions"]), ("Sim3 aligned", sim3_pos), ("EKF fused", fused_pos)):
+            m, med, rmse, cnt = evaluate_errors(traj, cand, slam["timestamps"])
+            results[(ref_name, label)] = (m, med, rmse, cnt)
+            print(f"    vs {ref_name:<12} {label:<14} -> mean: {m:.3f}m, median: {med:.3f}m, RMSE: {rmse:.3f}m ({cnt} pts)")
+    if save_path:
+        print("step 7/7: saving")
+        for path in save_results(slam_path, save_path, slam["timestamps"], fused_pos, fused_quat, gps["projector"]):
+            print(f"  wrote {path}")
+    return {"R": R, "t": t, "s": s, "sim3_pos": sim3_pos, "sim3_quat": sim3_quat, "ekf_pos": fused_pos,
+            "ekf_quat": fused_quat, "aligned": aligned, "valid": valid, "stats": results, "utm_zone": gps["utm_zone"]}
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser(description="SLAM/GNSS alignment and EKF fusion on B200 kernels")
+    ap.add_argument("slam", help="TUM trajectory: ts x y z qx qy qz qw")
+    ap.add_argument("gps", help="GNSS rows: ts lat lon alt ...")
+    ap.add_argument("--truth", default="", help="optional GNSS ground-truth file")
+    ap.add_argument("--save", default="", help="output path for the *_corrected_utm.txt file")
+    a = ap.parse_args()
+    try:
+        main_process(a.slam, a.gps, a.truth, a.save)
+    except (ValueError, RuntimeError, _lib.GsfError) as exc:
+        print(f"processing failed ({type(exc).__name__}): {exc}")
+        sys.exit(1)

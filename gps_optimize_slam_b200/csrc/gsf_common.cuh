@@ -33,6 +33,7 @@ enum : int {
     ST_EMPTY = 8,              // zero-length trajectory
     ST_RANSAC_OUTLIERS = 16,   // all-points fit leaves residuals >= threshold: the reference's
                                // unseeded RANSAC could pick a different inlier set here
+    ST_TOO_LONG = 32,          // trajectory does not fit the shared-memory staging buffer
 };
 
 // EKF / pipeline parameters for one trajectory (or shared by the batch).  Values are the

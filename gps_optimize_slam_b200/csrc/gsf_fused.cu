@@ -1,0 +1,576 @@
+// gsf_fuse_batched: Sim3 point selection -> Umeyama -> EKF (+RTS) for a batch of independent
+// trajectories, one thread block per trajectory at a time, the whole trajectory resident in
+// shared memory so that HBM is read once (88 B/pose) and written once (56 B/pose).
+//
+// Reference path replaced (file:line in /root/reference/EKFGPSSLAM.py):
+//   Sim3 point selection :972-998, compute_sim3_transform :428-459 (+ all-points residual
+//   check standing in for the unseeded RANSAC :389-426), transform_trajectory row 0 :461-467,
+//   apply_ekf_correction :831-935 (ExtendedKalmanFilter :679-772, RTS :777-803, sharp-turn
+//   gate :808-826).
+//
+// Formulation (checked on the CPU by oracle/kernel_model.py against the step-by-step oracle):
+//   * ts / positions / measurements of one trajectory are staged with three TMA bulk copies
+//     (cp.async.bulk + mbarrier); quaternions are streamed (read once, written once).
+//   * each thread owns an odd-length contiguous chunk of poses (odd => conflict-free 8-byte
+//     shared-memory accesses across a warp);
+//   * Umeyama sums: fixed-order chunk sums, xor-shuffle tree, warp-order combine => the
+//     result is bit-reproducible run to run; 3x3 SVD by one-sided Jacobi in registers;
+//   * covariance recursion  p -> R(p+q)/(p+q+R)  = Moebius maps composed as rescaled 2x2
+//     matrices (block scan), then the exact per-step Joseph-form recursion inside a chunk;
+//   * state recursion  x -> (1-k)(x+u) + k z  = affine maps (block scan);
+//   * odometry is telescoped: M(q_state[i-1]) M(q_hat[i-1])^T == M(C), C = q_state0 (x)
+//     conj(q_hat0), so u_i = M(C)(p_i - p_{i-1}) and q_state[i] = C (x) q_hat[i];
+//   * RTS over an outage is the closed form x_s[k] = x_f[k] + P_f[k]/P_pred[i] * delta_i.
+#include "gsf_common.cuh"
+#include "gsf_ekf_strict.cuh"
+#include "gsf_ptx.cuh"
+#include "gsf_internal.cuh"
+
+namespace gsf {
+
+constexpr int FLAG_VALID = 1;
+constexpr int FLAG_SELECTED = 2;
+constexpr int FLAG_RECOVERY = 4;
+constexpr int FLAG_NO_RTS = 8;
+
+template <int ND> struct Pack { double v[ND]; };
+
+// Exclusive block scan of a small struct of doubles.  op(earlier, later) must be associative.
+// Deterministic: fixed shuffle pattern inside a warp, warp totals combined in warp order.
+template <int ND, class Op>
+__device__ inline Pack<ND> block_exclusive_scan(Pack<ND> x, Op op, const Pack<ND>& ident, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Pack<ND> y;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) y.v[k] = __shfl_up_sync(GSF_FULL_MASK, x.v[k], o);
+        if (lane >= o) x = op(y, x);
+    }
+    Pack<ND> excl;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) excl.v[k] = __shfl_up_sync(GSF_FULL_MASK, x.v[k], 1);
+    if (lane == 0) excl = ident;
+    if (nwarp > 1) {
+        __syncthreads();
+        if (lane == 31) {
+#pragma unroll
+            for (int k = 0; k < ND; ++k) scratch[warp * ND + k] = x.v[k];
+        }
+        __syncthreads();
+        Pack<ND> pre = ident;
+        for (int w = 0; w < warp; ++w) {
+            Pack<ND> tot;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) tot.v[k] = scratch[w * ND + k];
+            pre = op(pre, tot);
+        }
+        excl = op(pre, excl);
+    }
+    return excl;
+}
+
+__device__ __forceinline__ int block_min_int(int v, int* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(GSF_FULL_MASK, v, o));
+    if (nwarp == 1) return v;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    int r = scratch[0];
+    for (int w = 1; w < nwarp; ++w) r = min(r, scratch[w]);
+    return r;
+}
+
+// 2x2 Moebius matrices for the three position axes, row-major [a b; c d] per axis.
+// Entries are non-negative, so products have no cancellation; rescale by a power of two.
+__device__ __forceinline__ void moeb_rescale(double* m) {
+    double big = fmax(fmax(m[0], m[1]), fmax(m[2], m[3]));
+    int e = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
+    double sc = __hiloint2double((1023 - e) << 20, 0);          // 2^-e (exact)
+    m[0] *= sc; m[1] *= sc; m[2] *= sc; m[3] *= sc;
+}
+struct MoebOp {
+    __device__ Pack<12> operator()(const Pack<12>& e, const Pack<12>& l) const {
+        Pack<12> r;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double* E = e.v + 4 * a; const double* L = l.v + 4 * a; double* R = r.v + 4 * a;
+            R[0] = L[0] * E[0] + L[1] * E[2]; R[1] = L[0] * E[1] + L[1] * E[3];
+            R[2] = L[2] * E[0] + L[3] * E[2]; R[3] = L[2] * E[1] + L[3] * E[3];
+            moeb_rescale(R);
+        }
+        return r;
+    }
+};
+struct AffOp {      // v = [a0 a1 a2 b0 b1 b2]; later o earlier
+    __device__ Pack<6> operator()(const Pack<6>& e, const Pack<6>& l) const {
+        Pack<6> r;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { r.v[a] = l.v[a] * e.v[a]; r.v[3 + a] = l.v[a] * e.v[3 + a] + l.v[3 + a]; }
+        return r;
+    }
+};
+struct RankOp {     // v = [count, last valid timestamp (NaN = none)]
+    __device__ Pack<2> operator()(const Pack<2>& e, const Pack<2>& l) const {
+        Pack<2> r; r.v[0] = e.v[0] + l.v[0]; r.v[1] = isnan(l.v[1]) ? e.v[1] : l.v[1]; return r;
+    }
+};
+
+// Rare / once-per-trajectory code kept out of line so that its register needs do not spill
+// the per-pose loops.
+__device__ __noinline__ int umeyama_finish_ool(int n, const double* mu_s, const double* mu_d, const double* H, double ss,
+                                               double* R, double* t, double* s) {
+    return umeyama_finish(n, mu_s, mu_d, H, ss, R, t, *s);
+}
+__device__ __noinline__ bool sharp_turn_ool(const double* ts, const double* quat, long s, long e, double thresh) {
+    return sharp_turn_in_range(ts, quat, s, e, thresh);
+}
+
+
+constexpr int SCRATCH_DOUBLES = 160;
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const FuseArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cap2 = A.cap + 2;
+    double* ts_s = reinterpret_cast<double*>(smem_raw);
+    double* pos_s = ts_s + cap2;
+    double* z_s = pos_s + 3 * (size_t)cap2;
+    double* scratch = z_s + 3 * (size_t)cap2;
+    double* bc = scratch + SCRATCH_DOUBLES;                 // broadcast area (48 doubles)
+    int* iscr = reinterpret_cast<int*>(bc + 48);            // 16 ints
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(iscr + 16);
+    unsigned char* flag_s = reinterpret_cast<unsigned char*>(mbar + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t parity = 0;
+    if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    __syncthreads();
+
+    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+        const long long e0 = A.offsets[b];
+        const int n = (int)(A.offsets[b + 1] - e0);
+        const FuseParams& prm = A.params[A.params_per_traj ? b : 0];
+        if (n <= 0) { if (tid == 0) A.status[b] = ST_EMPTY; continue; }
+        if (n > A.cap) { if (tid == 0) A.status[b] = ST_TOO_LONG; continue; }
+
+        // ------------------------------------------------------------------ stage inputs
+        const int lead = A.use_tma ? (int)(e0 & 1) : 0;
+        double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
+        unsigned char* flg = flag_s;
+        if (A.use_tma) {
+            const int cnt = n + lead, even = cnt & ~1;
+            if (tid == 0 && even > 0) {
+                mbar_expect_tx(mbar, (uint32_t)even * 56u);
+                bulk_g2s(ts_s, A.ts + (e0 - lead), (uint32_t)even * 8u, mbar);
+                bulk_g2s(pos_s, A.pos + 3 * (e0 - lead), (uint32_t)even * 24u, mbar);
+                bulk_g2s(z_s, A.z + 3 * (e0 - lead), (uint32_t)even * 24u, mbar);
+            }
+            if ((cnt & 1) && tid < 7) {                       // odd tail element: plain copy
+                const long long g = e0 - lead + even;
+                if (tid == 0) ts_s[even] = A.ts[g];
+                else if (tid < 4) pos_s[3 * even + (tid - 1)] = A.pos[3 * g + (tid - 1)];
+                else z_s[3 * even + (tid - 4)] = A.z[3 * g + (tid - 4)];
+            }
+            if (even > 0) { mbar_wait(mbar, parity); parity ^= 1; }
+            __syncthreads();
+        } else {
+            for (int i = tid; i < n; i += THREADS) tsS[i] = A.ts[e0 + i];
+            for (int i = tid; i < 3 * n; i += THREADS) { posS[i] = A.pos[3 * e0 + i]; zS[i] = A.z[3 * e0 + i]; }
+            __syncthreads();
+        }
+
+        // chunk ownership: odd length => conflict-free strided shared-memory access
+        int L = (n + THREADS - 1) / THREADS; L |= 1;
+        const int c0 = min(tid * L, n), c1 = min(c0 + L, n);
+
+        // ------------------------------------------------------------------ validity flags
+        int cntv = 0; double lastT = nan("");
+        for (int i = c0; i < c1; ++i) {
+            bool v = !row_has_nan(zS[3 * i], zS[3 * i + 1], zS[3 * i + 2]);
+            flg[i] = v ? FLAG_VALID : 0;
+            if (v) { ++cntv; lastT = tsS[i]; }
+        }
+        int st = ST_OK;
+        double RC[9], x0[3]; Quat C;
+        const bool ekf_only = A.init_pos != nullptr;
+        if (!ekf_only) {
+            // -------------------------------------------------------------- Sim3 point selection (:972-998)
+            Pack<2> mine; mine.v[0] = (double)cntv; mine.v[1] = lastT;
+            Pack<2> id2; id2.v[0] = 0.0; id2.v[1] = nan("");
+            Pack<2> pre = block_exclusive_scan<2>(mine, RankOp(), id2, scratch);
+            double tot[1] = {(double)cntv};
+            block_sum<1>(tot, scratch);
+            const int nvalid = (int)tot[0];
+            const int rank0 = (int)pre.v[0];
+            int kmin = 0x7fffffff;
+            {
+                int r = rank0; double pt = pre.v[1];
+                for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_VALID) {
+                    if (r == 0) bc[40] = tsS[i];                        // timestamp of the first valid point
+                    if (r >= 1 && tsS[i] - pt > prm.gap_threshold) kmin = min(kmin, r - 1);
+                    pt = tsS[i]; ++r;
+                }
+            }
+            kmin = block_min_int(kmin, iscr);
+            __syncthreads();
+            const int first_cnt = (kmin == 0x7fffffff) ? nvalid : kmin;
+            int mode;                                   // 0 all valid, 1 first run, 2 first run within max_duration
+            const double tlim = bc[40] + prm.max_duration;
+            if (nvalid < prm.min_samples) st |= ST_TOO_FEW_POINTS;
+            if (first_cnt < prm.min_samples) mode = 0;
+            else {
+                double timed[1] = {0.0};
+                int r = rank0;
+                for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_VALID) { if (r < first_cnt && tsS[i] <= tlim) timed[0] += 1.0; ++r; }
+                block_sum<1>(timed, scratch);
+                mode = ((int)timed[0] < prm.min_samples) ? 1 : 2;
+            }
+            // -------------------------------------------------------------- Umeyama sums (:436-443)
+            double s7[7] = {0, 0, 0, 0, 0, 0, 0};
+            {
+                int r = rank0;
+                for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_VALID) {
+                    bool sel = mode == 0 || (r < first_cnt && (mode == 1 || tsS[i] <= tlim));
+                    if (sel) {
+                        flg[i] |= FLAG_SELECTED;
+                        s7[0] += posS[3 * i]; s7[1] += posS[3 * i + 1]; s7[2] += posS[3 * i + 2];
+                        s7[3] += zS[3 * i]; s7[4] += zS[3 * i + 1]; s7[5] += zS[3 * i + 2];
+                        s7[6] += 1.0;
+                    }
+                    ++r;
+                }
+            }
+            block_sum<7>(s7, scratch);
+            const int nsel = (int)s7[6];
+            if (nsel < 3 || nsel < prm.min_samples) st |= ST_TOO_FEW_POINTS;
+            const double inv_n = 1.0 / fmax(s7[6], 1.0);
+            const double mus[3] = {s7[0] * inv_n, s7[1] * inv_n, s7[2] * inv_n};
+            const double mud[3] = {s7[3] * inv_n, s7[4] * inv_n, s7[5] * inv_n};
+            double h[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_SELECTED) {
+                double a0 = posS[3 * i] - mus[0], a1 = posS[3 * i + 1] - mus[1], a2 = posS[3 * i + 2] - mus[2];
+                double b0 = zS[3 * i] - mud[0], b1 = zS[3 * i + 1] - mud[1], b2 = zS[3 * i + 2] - mud[2];
+                h[0] += a0 * b0; h[1] += a0 * b1; h[2] += a0 * b2;
+                h[3] += a1 * b0; h[4] += a1 * b1; h[5] += a1 * b2;
+                h[6] += a2 * b0; h[7] += a2 * b1; h[8] += a2 * b2;
+                h[9] += a0 * a0 + a1 * a1 + a2 * a2;
+            }
+            block_sum<10>(h, scratch);
+            __syncthreads();
+            if (warp == 0) {
+                double R[9], t[3], s = 1.0;
+                int ust = (st & ST_TOO_FEW_POINTS) ? 0 : umeyama_finish_ool(nsel, mus, mud, h, h[9], R, t, &s);
+                Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
+                if (qnorm2(q0) == 0.0) ust |= ST_BAD_QUATERNION;
+                if (lane == 0) {
+                    if (!(st & ST_TOO_FEW_POINTS)) {
+                        Quat qR = quat_from_matrix(R);
+                        Quat q0h = qunit(q0);
+                        Quat qs0 = qunit_or_identity(qmul(qR, q0h));
+                        Quat Cq = qmul(qs0, qconj(q0h));
+                        double M[9]; qmat(Cq, M);
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) { bc[k] = M[k]; bc[16 + k] = R[k]; }
+                        bc[9] = Cq.x; bc[10] = Cq.y; bc[11] = Cq.z; bc[12] = Cq.w;
+                        double rx, ry, rz;
+                        mat_vec(R, posS[0], posS[1], posS[2], rx, ry, rz);
+                        bc[13] = s * rx + t[0]; bc[14] = s * ry + t[1]; bc[15] = s * rz + t[2];
+                        bc[25] = t[0]; bc[26] = t[1]; bc[27] = t[2]; bc[28] = s;
+                    }
+                    iscr[8] = ust;
+                }
+            }
+            __syncthreads();
+            st |= iscr[8];
+            // all-points residual check standing in for RANSAC (:409-412): count violators
+            double nout[1] = {0.0};
+            if (!(st & ST_TOO_FEW_POINTS) && prm.residual_thresh > 0.0) {
+                const double s = bc[28], thr2 = prm.residual_thresh * prm.residual_thresh;
+                for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_SELECTED) {
+                    double rx, ry, rz;
+                    mat_vec(bc + 16, posS[3 * i], posS[3 * i + 1], posS[3 * i + 2], rx, ry, rz);
+                    double d0 = s * rx + bc[25] - zS[3 * i], d1 = s * ry + bc[26] - zS[3 * i + 1], d2 = s * rz + bc[27] - zS[3 * i + 2];
+                    if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) nout[0] += 1.0;
+                }
+                block_sum<1>(nout, scratch);
+                if (nout[0] > 0.0) st |= ST_RANSAC_OUTLIERS;
+            }
+            if (tid == 0 && A.sim3_out) {
+                double* o = A.sim3_out + 16 * (size_t)b;
+                const bool ok = !(st & ST_TOO_FEW_POINTS);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) o[k] = ok ? bc[16 + k] : nan("");
+                o[9] = ok ? bc[25] : nan(""); o[10] = ok ? bc[26] : nan(""); o[11] = ok ? bc[27] : nan("");
+                o[12] = ok ? bc[28] : nan(""); o[13] = (double)nsel; o[14] = (double)nvalid; o[15] = nout[0];
+            }
+        } else {
+            if (tid == 0) {
+                Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
+                Quat qi{A.init_quat[4 * b], A.init_quat[4 * b + 1], A.init_quat[4 * b + 2], A.init_quat[4 * b + 3]};
+                int ust = (qnorm2(q0) == 0.0) ? ST_BAD_QUATERNION : 0;
+                Quat qs0 = qunit_or_identity(qi);
+                Quat Cq = qmul(qs0, qconj(qunit(q0)));
+                double M[9]; qmat(Cq, M);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) bc[k] = M[k];
+                bc[9] = Cq.x; bc[10] = Cq.y; bc[11] = Cq.z; bc[12] = Cq.w;
+                bc[13] = A.init_pos[3 * b]; bc[14] = A.init_pos[3 * b + 1]; bc[15] = A.init_pos[3 * b + 2];
+                iscr[8] = ust;
+            }
+            __syncthreads();
+            st |= iscr[8];
+        }
+
+        if (st & (ST_TOO_FEW_POINTS | ST_BAD_QUATERNION)) {
+            // The reference aborts the run here (ValueError / RuntimeError): outputs are NaN.
+            for (int i = tid; i < 3 * n; i += THREADS) A.out_pos[3 * e0 + i] = nan("");
+            for (int i = tid; i < 4 * n; i += THREADS) A.out_quat[4 * e0 + i] = nan("");
+            if (tid == 0) A.status[b] = st;
+            __syncthreads();
+            continue;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) RC[k] = bc[k];
+        C = Quat{bc[9], bc[10], bc[11], bc[12]};
+        x0[0] = bc[13]; x0[1] = bc[14]; x0[2] = bc[15];
+        if (tid == 0) iscr[9] = 0;                                  // "trajectory has a recovered outage"
+
+        // ------------------------------------------------------------------ covariance: Moebius scan
+        const double Qx = prm.q[0], Qy = prm.q[1], Qz = prm.q[2];
+        const double Rx = prm.r[0], Ry = prm.r[1], Rz = prm.r[2];
+        const int s0 = max(c0, 1);                                  // steps owned: i in [s0, c1)
+        Pack<12> loc;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { loc.v[4 * a] = 1.0; loc.v[4 * a + 1] = 0.0; loc.v[4 * a + 2] = 0.0; loc.v[4 * a + 3] = 1.0; }
+        {
+            int since = 0;
+            for (int i = s0; i < c1; ++i) {
+                const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
+                const double qq[3] = {Qx * dt, Qy * dt, Qz * dt};
+                const double rr[3] = {Rx, Ry, Rz};
+                const bool v = flg[i] & FLAG_VALID;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    double* m = loc.v + 4 * a;
+                    const double ta = m[0] + qq[a] * m[2], tb = m[1] + qq[a] * m[3];     // [1 q; 0 1] * m
+                    if (v) { m[2] = ta + rr[a] * m[2]; m[3] = tb + rr[a] * m[3]; m[0] = rr[a] * ta; m[1] = rr[a] * tb; }
+                    else { m[0] = ta; m[1] = tb; }
+                }
+                if (++since == 16) { since = 0; moeb_rescale(loc.v); moeb_rescale(loc.v + 4); moeb_rescale(loc.v + 8); }
+            }
+            moeb_rescale(loc.v); moeb_rescale(loc.v + 4); moeb_rescale(loc.v + 8);
+        }
+        Pack<12> idm;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { idm.v[4 * a] = 1.0; idm.v[4 * a + 1] = 0.0; idm.v[4 * a + 2] = 0.0; idm.v[4 * a + 3] = 1.0; }
+        Pack<12> mpre = block_exclusive_scan<12>(loc, MoebOp(), idm, scratch);
+        double P[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double* m = mpre.v + 4 * a;
+            P[a] = (m[0] * prm.p0[a] + m[1]) / (m[2] * prm.p0[a] + m[3]);
+        }
+
+        // ------------------------------------------------------------------ gains + affine maps
+        double pprev[3] = {0, 0, 0};
+        if (s0 < c1) { pprev[0] = posS[3 * (s0 - 1)]; pprev[1] = posS[3 * (s0 - 1) + 1]; pprev[2] = posS[3 * (s0 - 1) + 2]; }
+        __syncthreads();                                            // boundary reads before in-place writes
+        if (c0 == 0 && c1 > 0) { posS[0] = prm.p0[0]; posS[1] = prm.p0[1]; posS[2] = prm.p0[2]; }   // P_f[0]
+        Pack<6> aff;
+        aff.v[0] = aff.v[1] = aff.v[2] = 1.0; aff.v[3] = aff.v[4] = aff.v[5] = 0.0;
+        for (int i = s0; i < c1; ++i) {
+            const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
+            const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
+            double u[3];
+            mat_vec(RC, p0 - pprev[0], p1 - pprev[1], p2 - pprev[2], u[0], u[1], u[2]);
+            pprev[0] = p0; pprev[1] = p1; pprev[2] = p2;
+            const double qq[3] = {Qx * dt, Qy * dt, Qz * dt};
+            const double rr[3] = {Rx, Ry, Rz};
+            const int f = flg[i];
+            if (f & FLAG_VALID) {
+                double w = 1.0;
+                if (!(flg[i - 1] & FLAG_VALID)) {                   // GNSS just recovered (:879-894)
+                    int s = i - 1;
+                    while (s > 0 && !(flg[s - 1] & FLAG_VALID)) --s;
+                    int nf = f | FLAG_RECOVERY;
+                    if (sharp_turn_ool(A.ts + e0, A.quat + 4 * e0, s, i - 1, prm.yaw_rate_thresh)) {
+                        nf |= FLAG_NO_RTS;
+                        if (prm.sharp_turn_steps > 0) { double wd = 1.0 / (double)prm.sharp_turn_steps; if (wd < 1.0) w = wd; }
+                    }
+                    flg[i] = (unsigned char)nf;
+                    iscr[9] = 1;
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double pp = P[a] + qq[a];
+                    const double k = pp * (1.0 / (pp + rr[a]));
+                    const double omk = 1.0 - k;
+                    P[a] = omk * pp * omk + k * rr[a] * k;           // Joseph form (:731)
+                    const double ke = k * w, av = 1.0 - ke;
+                    const double bv = av * u[a] + ke * zS[3 * i + a];
+                    posS[3 * i + a] = av; zS[3 * i + a] = bv;
+                    aff.v[3 + a] = av * aff.v[3 + a] + bv; aff.v[a] *= av;
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    P[a] += qq[a];
+                    posS[3 * i + a] = P[a];                          // P_f[i] kept for the RTS patch
+                    zS[3 * i + a] = u[a];
+                    aff.v[3 + a] += u[a];
+                }
+            }
+        }
+        Pack<6> ida; ida.v[0] = ida.v[1] = ida.v[2] = 1.0; ida.v[3] = ida.v[4] = ida.v[5] = 0.0;
+        Pack<6> apre = block_exclusive_scan<6>(aff, AffOp(), ida, scratch);
+
+        // ------------------------------------------------------------------ state recursion
+        double x[3] = {apre.v[0] * x0[0] + apre.v[3], apre.v[1] * x0[1] + apre.v[4], apre.v[2] * x0[2] + apre.v[5]};
+        if (c0 == 0 && c1 > 0) { zS[0] = x0[0]; zS[1] = x0[1]; zS[2] = x0[2]; }
+        for (int i = s0; i < c1; ++i) {
+            if (flg[i] & FLAG_VALID) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) x[a] = posS[3 * i + a] * x[a] + zS[3 * i + a];
+            } else {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) x[a] += zS[3 * i + a];
+            }
+            zS[3 * i] = x[0]; zS[3 * i + 1] = x[1]; zS[3 * i + 2] = x[2];
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------------ closed-form RTS over recovered outages
+        if (iscr[9]) {
+            for (int i = s0; i < c1; ++i) {
+                const int f = flg[i];
+                if ((f & FLAG_RECOVERY) && !(f & FLAG_NO_RTS)) {
+                    int s = i - 1;
+                    while (s > 0 && !(flg[s - 1] & FLAG_VALID)) --s;
+                    const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
+                    const double* gp = A.pos + 3 * (e0 + i);
+                    double u[3];
+                    mat_vec(RC, gp[0] - gp[-3], gp[1] - gp[-2], gp[2] - gp[-1], u[0], u[1], u[2]);
+                    double ratio_den[3], delta[3];
+                    const double qq[3] = {Qx * dt, Qy * dt, Qz * dt};
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        ratio_den[a] = posS[3 * (i - 1) + a] + qq[a];                  // P_pred[i]
+                        delta[a] = zS[3 * i + a] - (zS[3 * (i - 1) + a] + u[a]);       // x_f[i] - x_pred[i]
+                    }
+                    for (int k = s; k < i; ++k) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) zS[3 * k + a] += (posS[3 * k + a] / ratio_den[a]) * delta[a];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ------------------------------------------------------------------ store fused positions
+        double* gout = A.out_pos + 3 * e0;
+        if (A.use_tma) {
+            fence_proxy_async();
+            __syncthreads();
+            const int m = n - lead, even = m & ~1;
+            if (tid == 0 && even > 0) { bulk_s2g(gout + 3 * lead, zS + 3 * lead, (uint32_t)even * 24u); bulk_commit(); }
+            if (lead && tid < 3) gout[tid] = zS[tid];
+            if ((m & 1) && tid >= 3 && tid < 6) gout[3 * (lead + even) + (tid - 3)] = zS[3 * (lead + even) + (tid - 3)];
+        } else {
+            for (int i = tid; i < 3 * n; i += THREADS) gout[i] = zS[i];
+        }
+
+        // ------------------------------------------------------------------ quaternions: q_state[i] = C (x) q_hat[i]
+        int badq = 0;
+        {
+            const double2* qin = reinterpret_cast<const double2*>(A.quat + 4 * e0);
+            double2* qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
+            for (int i = tid; i < n; i += THREADS) {
+                const double2 lo = __ldg(qin + 2 * i), hi = __ldg(qin + 2 * i + 1);
+                Quat qi{lo.x, lo.y, hi.x, hi.y};
+                const double n2 = qnorm2(qi);
+                if (n2 == 0.0) badq = 1;
+                Quat r = qscale(qmul(C, qi), rsqrt(n2));
+                qout[2 * i] = make_double2(r.x, r.y);
+                qout[2 * i + 1] = make_double2(r.z, r.w);
+            }
+        }
+        badq = __syncthreads_or(badq);
+        if (badq) {
+            // A zero-norm SLAM quaternion: scipy raises inside transform_trajectory (:466), the
+            // reference run aborts.  Flag it and blank the outputs.
+            st |= ST_BAD_QUATERNION;
+            if (A.use_tma && tid == 0) bulk_wait_all();
+            __syncthreads();
+            for (int i = tid; i < 3 * n; i += THREADS) gout[i] = nan("");
+            for (int i = tid; i < 4 * n; i += THREADS) A.out_quat[4 * e0 + i] = nan("");
+        }
+        if (tid == 0) {
+            A.status[b] = st;
+            if (A.use_tma) bulk_wait_read();
+        }
+        if (A.use_tma) fence_proxy_async();
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------- strict batched kernel
+// One thread per trajectory running the literal step-by-step recursion (gsf_ekf_strict.cuh)
+// straight from global memory.  Reference surface: apply_ekf_correction for arbitrary inputs
+// (keeps the zero-motion fallback of :84-86); also the independent on-device cross-check of
+// the scan formulation above.
+__global__ void ekf_strict_kernel(const double* ts, const double* pos, const double* quat, const double* z,
+                                  const long long* offsets, const FuseParams* params, int params_per_traj,
+                                  const double* init_pos, const double* init_quat,
+                                  double* out_pos, double* out_quat, int* status, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    long long e0 = offsets[b];
+    long n = (long)(offsets[b + 1] - e0);
+    status[b] = ekf_strict_trajectory(n, ts + e0, pos + 3 * e0, quat + 4 * e0, z + 3 * e0,
+                                      init_pos + 3 * b, init_quat + 4 * b, params[params_per_traj ? b : 0],
+                                      out_pos + 3 * e0, out_quat + 4 * e0);
+}
+
+size_t fuse_smem_bytes(int cap) {
+    return (size_t)(cap + 2) * 56 + (SCRATCH_DOUBLES + 48) * 8 + 16 * 4 + 16 + (size_t)((cap + 2 + 15) & ~15);
+}
+
+template <int THREADS>
+static cudaError_t launch_fuse_t(const FuseArgs& a, int num_sms, cudaStream_t stream) {
+    size_t smem = fuse_smem_bytes(a.cap);
+    cudaError_t e = cudaFuncSetAttribute(fuse_traj_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fuse_traj_kernel<THREADS>, THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    long long grid = (long long)num_sms * per_sm;
+    if (grid > a.B) grid = a.B;
+    fuse_traj_kernel<THREADS><<<(unsigned)grid, THREADS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fuse(const FuseArgs& a, int threads, int num_sms, cudaStream_t stream) {
+    switch (threads) {
+        case 32: return launch_fuse_t<32>(a, num_sms, stream);
+        case 64: return launch_fuse_t<64>(a, num_sms, stream);
+        case 128: return launch_fuse_t<128>(a, num_sms, stream);
+        case 256: return launch_fuse_t<256>(a, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_ekf_strict(const double* ts, const double* pos, const double* quat, const double* z,
+                              const long long* offsets, const FuseParams* params, int params_per_traj,
+                              const double* init_pos, const double* init_quat, double* out_pos, double* out_quat,
+                              int* status, int B, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    ekf_strict_kernel<<<(B + 63) / 64, 64, 0, stream>>>(ts, pos, quat, z, offsets, params, params_per_traj,
+                                                        init_pos, init_quat, out_pos, out_quat, status, B);
+    return cudaGetLastError();
+}
+
+}  // namespace gsf

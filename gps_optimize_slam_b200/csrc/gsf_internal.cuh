@@ -1,0 +1,50 @@
+// Launch-argument records and launcher prototypes shared by the kernel translation units and
+// the C-ABI layer (gsf_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "gsf_common.cuh"
+
+namespace gsf {
+struct FuseArgs {
+    const double* ts; const double* pos; const double* quat; const double* z;
+    const long long* offsets;
+    const FuseParams* params; int params_per_traj;
+    const double* init_pos; const double* init_quat;
+    double* out_pos; double* out_quat;
+    double* sim3_out;
+    int* status;
+    int B; int cap;
+    int use_tma;
+};
+size_t fuse_smem_bytes(int cap);
+cudaError_t launch_fuse(const FuseArgs& a, int threads, int num_sms, cudaStream_t stream);
+cudaError_t launch_ekf_strict(const double*, const double*, const double*, const double*, const long long*,
+                              const FuseParams*, int, const double*, const double*, double*, double*, int*, int, cudaStream_t);
+struct UtmConst { double A_k0; double e, e2; double alpha[6], beta[6]; double lon0; double fn; };
+cudaError_t launch_utm(bool inverse, const double* a, const double* b, long long n, const UtmConst& K, double* o1, double* o2,
+                       int num_sms, cudaStream_t stream);
+cudaError_t launch_geo_mean(const double* lon, const double* lat, long long n, double* part, int nparts, double* out, cudaStream_t stream);
+struct AssocArgs {
+    const double* gps_t; const double* gps_xyz; const long long* gps_off;
+    const double* slam_t; const long long* slam_off;
+    double gap; double* aligned; unsigned char* valid; double* work; int B;
+};
+cudaError_t launch_associate(const AssocArgs& a, int num_sms, cudaStream_t stream);
+int sim3_tiles_for(long long max_len);
+cudaError_t launch_umeyama(const double*, const double*, const long long*, const unsigned char*, int, long long, double*,
+                           double*, double*, double*, int*, cudaStream_t);
+cudaError_t launch_sim3_apply(const double*, const double*, const long long*, const double*, const double*, const double*, int,
+                              long long, double*, double*, int*, int, cudaStream_t);
+struct AteArgs {
+    const double* traj; const double* cand; const double* ts; const long long* offsets;
+    double skip; double* stats; int B; int cap;
+};
+size_t ate_smem_bytes(int cap);
+cudaError_t launch_ate(const AteArgs& a, int num_sms, cudaStream_t stream);
+struct SynthArgs {
+    double* ts; double* pos; double* quat; double* z;
+    long long traj0; int B; int n; double dt; double speed; unsigned long long seed;
+    double outage_prob; int outage_max_len;
+};
+cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
+}  // namespace gsf

@@ -1,0 +1,493 @@
+// Stand-alone kernels behind the reference's per-function surface (one call = one reference
+// function, batched over trajectories):
+//   K1  utm_forward / utm_inverse / geo_mean       EKFGPSSLAM.py:127-134, :266-271, :291-296
+//   K1b associate_spline                            EKFGPSSLAM.py:351-380 (interp1d cubic/linear)
+//   K2  sim3 tile statistics + finalize (Umeyama)   EKFGPSSLAM.py:428-459
+//   K2b sim3_apply                                  EKFGPSSLAM.py:461-467
+//   K4  ate_nn (nearest-neighbour error statistics) EKFGPSSLAM.py:1021-1033
+#include "gsf_common.cuh"
+#include "gsf_internal.cuh"
+
+namespace gsf {
+
+// ============================================================================= K1: UTM
+// Karney/Krueger 6th-order series (the algorithm PROJ documents for +proj=utm); coefficients
+// for WGS84 are evaluated on the host once (gsf_capi.cu) and passed by value.
+
+__device__ __forceinline__ void krueger_series(const double* coef, double xi_in, double eta_in, double sign,
+                                               double& xi, double& eta) {
+    // xi + sign * sum c_j sin(2j xi') cosh(2j eta'),  eta + sign * sum c_j cos(2j xi') sinh(2j eta')
+    // evaluated with the angle-addition recurrences from (sin 2xi', cos 2xi', sinh 2eta', cosh 2eta').
+    double s2, c2;
+    sincos(2.0 * xi_in, &s2, &c2);
+    const double e2p = exp(2.0 * eta_in), e2m = 1.0 / e2p;
+    const double sh2 = 0.5 * (e2p - e2m), ch2 = 0.5 * (e2p + e2m);
+    double sj = s2, cj = c2, shj = sh2, chj = ch2;
+    double ax = 0.0, ay = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        ax += coef[j] * sj * chj;
+        ay += coef[j] * cj * shj;
+        const double sn = sj * c2 + cj * s2, cn = cj * c2 - sj * s2;
+        const double shn = shj * ch2 + chj * sh2, chn = chj * ch2 + shj * sh2;
+        sj = sn; cj = cn; shj = shn; chj = chn;
+    }
+    xi = xi_in + sign * ax;
+    eta = eta_in + sign * ay;
+}
+
+__global__ void utm_forward_kernel(const double* __restrict__ lon, const double* __restrict__ lat, long long n,
+                                   const UtmConst K, double* __restrict__ east, double* __restrict__ north) {
+    const double D2R = 0.017453292519943295769236907684886;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double lam = lon[i] * D2R - K.lon0, phi = lat[i] * D2R;
+        const double tau = tan(phi);
+        const double t1 = sqrt(1.0 + tau * tau);
+        const double sigma = sinh(K.e * atanh(K.e * tau / t1));
+        const double taup = tau * sqrt(1.0 + sigma * sigma) - sigma * t1;
+        double sl, cl;
+        sincos(lam, &sl, &cl);
+        const double xip = atan2(taup, cl);
+        const double etap = asinh(sl / sqrt(taup * taup + cl * cl));
+        double xi, eta;
+        krueger_series(K.alpha, xip, etap, 1.0, xi, eta);
+        east[i] = 500000.0 + K.A_k0 * eta;
+        north[i] = K.fn + K.A_k0 * xi;
+    }
+}
+
+__global__ void utm_inverse_kernel(const double* __restrict__ east, const double* __restrict__ north, long long n,
+                                   const UtmConst K, double* __restrict__ lon, double* __restrict__ lat) {
+    const double R2D = 57.295779513082320876798154814105;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double xi = (north[i] - K.fn) / K.A_k0, eta = (east[i] - 500000.0) / K.A_k0;
+        double xip, etap;
+        krueger_series(K.beta, xi, eta, -1.0, xip, etap);
+        const double sh = sinh(etap);
+        double sx, cx;
+        sincos(xip, &sx, &cx);
+        const double taup = sx / sqrt(sh * sh + cx * cx);
+        const double lam = atan2(sh, cx);
+        double tau = taup / (1.0 - K.e2);
+        for (int it = 0; it < 5; ++it) {                      // Newton on tau'(tau) = taup
+            const double s1 = sqrt(1.0 + tau * tau);
+            const double sigma = sinh(K.e * atanh(K.e * tau / s1));
+            const double taui = tau * sqrt(1.0 + sigma * sigma) - sigma * s1;
+            const double dtau = (taup - taui) / sqrt(1.0 + taui * taui) * (1.0 + (1.0 - K.e2) * tau * tau) / ((1.0 - K.e2) * s1);
+            tau += dtau;
+        }
+        lat[i] = atan(tau) * R2D;
+        lon[i] = (lam + K.lon0) * R2D;
+    }
+}
+
+// Deterministic two-stage sum of (lon, lat) for the zone / hemisphere choice (:131-133).
+// Stage 1: fixed grid, fixed per-thread stride order, block partials -> part[grid][2].
+__global__ void geo_sum_kernel(const double* __restrict__ lon, const double* __restrict__ lat, long long n, double* part) {
+    __shared__ double scratch[2 * 8];
+    double v[2] = {0.0, 0.0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        v[0] += lon[i]; v[1] += lat[i];
+    }
+    block_sum<2>(v, scratch);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = v[0]; part[2 * blockIdx.x + 1] = v[1]; }
+}
+// Stage 2 (one thread): out[0] = mean lon, out[1] = mean lat, out[2] = zone, out[3] = south flag.
+__global__ void geo_finish_kernel(const double* part, int nparts, long long n, double* out) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nparts; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
+    a /= (double)n; b /= (double)n;
+    out[0] = a; out[1] = b;
+    out[2] = floor((a + 180.0) / 6.0) + 1.0;           // int((mean_lon + 180) // 6 + 1)
+    out[3] = (b < 0.0) ? 1.0 : 0.0;
+}
+
+// ============================================================================= K1b: spline association
+// One block per trajectory.  GNSS stamps must be sorted and unique (the host does the argsort /
+// np.unique of :340-349).  Segments are split at gaps > threshold (:351-354); per segment a
+// not-a-knot cubic spline (>= 4 knots, scipy make_interp_spline(k=3) default boundary
+// conditions) or a linear interpolant (2-3 knots) is evaluated at the SLAM stamps inside
+// [seg start, seg end]; everything else is NaN / invalid (:372-379).
+// The spline is solved in moment form (second derivatives m_j) with the not-a-knot rows
+// eliminated, by the Thomas algorithm: thread a in {0,1,2} owns coordinate axis a.
+// work: per GNSS sample 4 doubles (c', and 3 moments) -> caller-provided workspace.
+
+__device__ void spline_moments(const double* t, const double* y /*stride 3*/, int m, double* cp, double* mom /*stride 3*/, int axis) {
+    // interior unknowns m_1..m_{m-2}; not-a-knot: m_0 = ((h0+h1) m_1 - h0 m_2)/h1, same at the end.
+    const int nu = m - 2;
+    auto h = [&](int j) { return t[j + 1] - t[j]; };
+    auto rhs = [&](int j) {   // row for knot j (1..m-2)
+        return 6.0 * ((y[3 * (j + 1) + axis] - y[3 * j + axis]) / h(j) - (y[3 * j + axis] - y[3 * (j - 1) + axis]) / h(j - 1));
+    };
+    // row j: lo*m_{j-1} + di*m_j + up*m_{j+1} = rhs, with end substitutions folded in.
+    double prev_cp = 0.0, prev_dp = 0.0;
+    for (int j = 1; j <= nu; ++j) {
+        double lo = h(j - 1), di = 2.0 * (h(j - 1) + h(j)), up = h(j);
+        if (j == 1) {          // substitute m_0
+            const double h0 = h(0), h1 = h(1);
+            di += h0 * (h0 + h1) / h1; up -= h0 * h0 / h1; lo = 0.0;
+        }
+        if (j == nu) {         // substitute m_{m-1}
+            const double ha = h(m - 3), hb = h(m - 2);
+            di += hb * (ha + hb) / ha; lo -= hb * hb / ha; up = 0.0;
+        }
+        if (nu == 1) { lo = 0.0; up = 0.0; }
+        const double den = di - lo * prev_cp;
+        const double c = up / den;
+        const double d = (rhs(j) - lo * prev_dp) / den;
+        cp[j] = c; mom[3 * j + axis] = d;
+        prev_cp = c; prev_dp = d;
+    }
+    for (int j = nu - 1; j >= 1; --j) mom[3 * j + axis] -= cp[j] * mom[3 * (j + 1) + axis];
+    {
+        const double h0 = h(0), h1 = h(1);
+        mom[axis] = ((h0 + h1) * mom[3 + axis] - h0 * mom[6 + axis]) / h1;
+        const double ha = h(m - 3), hb = h(m - 2);
+        mom[3 * (m - 1) + axis] = ((ha + hb) * mom[3 * (m - 2) + axis] - hb * mom[3 * (m - 3) + axis]) / ha;
+    }
+}
+
+__global__ void associate_kernel(const AssocArgs A) {
+    __shared__ int seg_lo, seg_hi, seg_ok, more;
+    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+        const long long g0 = A.gps_off[b], s0 = A.slam_off[b];
+        const int M = (int)(A.gps_off[b + 1] - g0), N = (int)(A.slam_off[b + 1] - s0);
+        const double* gt = A.gps_t + g0; const double* gy = A.gps_xyz + 3 * g0;
+        const double* st = A.slam_t + s0;
+        double* out = A.aligned + 3 * s0; unsigned char* val = A.valid + s0;
+        double* cp = A.work + 4 * g0; double* mom = cp + M;      // cp[M], mom[3M]
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = nan(""); val[i] = 0;
+        }
+        if (M < 2 || N == 0) { __syncthreads(); continue; }
+        int lo = 0;
+        while (true) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int hi = lo; bool ok = true;
+                while (hi + 1 < M && !(gt[hi + 1] - gt[hi] > A.gap)) { if (!(gt[hi + 1] - gt[hi] > 1e-9)) ok = false; ++hi; }
+                seg_lo = lo; seg_hi = hi; seg_ok = ok && (hi - lo + 1 >= 2); more = (hi + 1 < M);
+            }
+            __syncthreads();
+            const int a0 = seg_lo, a1 = seg_hi, m = a1 - a0 + 1;
+            if (seg_ok) {
+                if (m >= 4 && threadIdx.x < 3) spline_moments(gt + a0, gy + 3 * a0, m, cp + a0, mom + 3 * a0, threadIdx.x);
+                __syncthreads();
+                const double ta = gt[a0], tb = gt[a1];
+                for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                    const double t = st[i];
+                    if (!(t >= ta && t <= tb)) continue;                 // scipy: NaN outside [ta, tb]
+                    int l = a0, r = a1;                                   // largest j with gt[j] <= t, j < a1
+                    while (r - l > 1) { int mid = (l + r) >> 1; if (gt[mid] <= t) l = mid; else r = mid; }
+                    const int j = l;
+                    const double hh = gt[j + 1] - gt[j];
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const double y0 = gy[3 * j + ax], y1 = gy[3 * (j + 1) + ax];
+                        double v;
+                        if (m >= 4) {
+                            const double wa = (gt[j + 1] - t) / hh, wb = (t - gt[j]) / hh;
+                            const double m0 = mom[3 * j + ax], m1 = mom[3 * (j + 1) + ax];
+                            v = wa * y0 + wb * y1 + ((wa * wa * wa - wa) * m0 + (wb * wb * wb - wb) * m1) * (hh * hh) / 6.0;
+                        } else {
+                            v = (y1 - y0) / hh * (t - gt[j]) + y0;        // interp1d kind='linear'
+                        }
+                        out[3 * i + ax] = v;
+                    }
+                    val[i] = !row_has_nan(out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+                }
+            }
+            if (!more) break;
+            lo = seg_hi + 1;
+        }
+        __syncthreads();
+    }
+}
+
+// ============================================================================= K2: Umeyama (stand-alone)
+// Tile statistics: every block reduces up to TILE points of one trajectory to
+// (n, mean_src, mean_dst, H about the tile means, ss) with a tile-local pivot; the finalize
+// kernel merges tiles in order with the pairwise-covariance update, then SVD.  One pass over
+// the data, any trajectory length, bit-reproducible.
+constexpr int SIM3_TILE = 8192;
+constexpr int SIM3_STAT = 20;    // n, mu_s[3], mu_d[3], H[9], ss, pad[3]
+
+__global__ void __launch_bounds__(256) sim3_tile_stats_kernel(const double* __restrict__ src, const double* __restrict__ dst,
+                                                              const long long* __restrict__ offsets,
+                                                              const unsigned char* __restrict__ mask, int tiles_max,
+                                                              double* __restrict__ stats) {
+    __shared__ double scratch[17 * 8];
+    __shared__ double piv[6];
+    __shared__ int piv_idx;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const long long e0 = offsets[b];
+    const long long n = offsets[b + 1] - e0;
+    double* o = stats + ((size_t)b * tiles_max + tile) * SIM3_STAT;
+    const long long lo = (long long)tile * SIM3_TILE;
+    if (lo >= n) { if (threadIdx.x == 0) o[0] = 0.0; return; }
+    const long long hi = min(n, lo + SIM3_TILE);
+    if (threadIdx.x == 0) piv_idx = 0x7fffffff;
+    __syncthreads();
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x)
+        if (!mask || mask[e0 + i]) { atomicMin(&piv_idx, (int)(i - lo)); break; }
+    __syncthreads();
+    if (piv_idx == 0x7fffffff) { if (threadIdx.x == 0) o[0] = 0.0; return; }
+    if (threadIdx.x < 6) {
+        const long long g = e0 + lo + piv_idx;
+        piv[threadIdx.x] = threadIdx.x < 3 ? src[3 * g + threadIdx.x] : dst[3 * g + threadIdx.x - 3];
+    }
+    __syncthreads();
+    double v[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) v[k] = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const long long g = e0 + i;
+        if (mask && !mask[g]) continue;
+        const double a0 = src[3 * g] - piv[0], a1 = src[3 * g + 1] - piv[1], a2 = src[3 * g + 2] - piv[2];
+        const double b0 = dst[3 * g] - piv[3], b1 = dst[3 * g + 1] - piv[4], b2 = dst[3 * g + 2] - piv[5];
+        v[0] += 1.0; v[1] += a0; v[2] += a1; v[3] += a2; v[4] += b0; v[5] += b1; v[6] += b2;
+        v[7] += a0 * b0; v[8] += a0 * b1; v[9] += a0 * b2;
+        v[10] += a1 * b0; v[11] += a1 * b1; v[12] += a1 * b2;
+        v[13] += a2 * b0; v[14] += a2 * b1; v[15] += a2 * b2;
+        v[16] += a0 * a0 + a1 * a1 + a2 * a2;
+    }
+    block_sum<17>(v, scratch);
+    if (threadIdx.x == 0) {
+        const double cnt = v[0], inv = 1.0 / cnt;
+        const double ma[3] = {v[1] * inv, v[2] * inv, v[3] * inv}, mb[3] = {v[4] * inv, v[5] * inv, v[6] * inv};
+        o[0] = cnt;
+        for (int k = 0; k < 3; ++k) { o[1 + k] = piv[k] + ma[k]; o[4 + k] = piv[3 + k] + mb[k]; }
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o[7 + 3 * r + c] = v[7 + 3 * r + c] - cnt * ma[r] * mb[c];
+        o[16] = v[16] - cnt * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
+    }
+}
+
+__global__ void sim3_finalize_kernel(const double* __restrict__ stats, int tiles_max, int B,
+                                     double* __restrict__ Rout, double* __restrict__ tout, double* __restrict__ sout,
+                                     int* __restrict__ status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double n = 0.0, ms[3] = {0, 0, 0}, md[3] = {0, 0, 0}, H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ss = 0.0;
+    for (int tl = 0; tl < tiles_max; ++tl) {
+        const double* o = stats + ((size_t)b * tiles_max + tl) * SIM3_STAT;
+        const double m = o[0];
+        if (m == 0.0) continue;
+        if (n == 0.0) {
+            n = m;
+            for (int k = 0; k < 3; ++k) { ms[k] = o[1 + k]; md[k] = o[4 + k]; }
+            for (int k = 0; k < 9; ++k) H[k] = o[7 + k];
+            ss = o[16];
+            continue;
+        }
+        const double tot = n + m, w = n * m / tot;
+        double da[3], db[3];
+        for (int k = 0; k < 3; ++k) { da[k] = o[1 + k] - ms[k]; db[k] = o[4 + k] - md[k]; }
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[3 * r + c] += o[7 + 3 * r + c] + w * da[r] * db[c];
+        ss += o[16] + w * (da[0] * da[0] + da[1] * da[1] + da[2] * da[2]);
+        for (int k = 0; k < 3; ++k) { ms[k] += da[k] * (m / tot); md[k] += db[k] * (m / tot); }
+        n = tot;
+    }
+    double* R = Rout + 9 * (size_t)b; double* t = tout + 3 * (size_t)b;
+    if (n < 3.0) {                                      // (None, None, None), :431
+        for (int k = 0; k < 9; ++k) R[k] = nan("");
+        t[0] = t[1] = t[2] = nan(""); sout[b] = nan(""); status[b] = ST_TOO_FEW_POINTS;
+        return;
+    }
+    double s;
+    status[b] = umeyama_finish((int)n, ms, md, H, ss, R, t, s);
+    sout[b] = s;
+}
+
+// ============================================================================= K2b: Sim3 apply
+// p' = s R p + t ; q' = normalize(q_R (x) normalize(q)).  One thread per pose; positions go
+// through shared memory so global accesses stay fully coalesced (24-byte rows).
+__global__ void __launch_bounds__(256) sim3_apply_kernel(const double* __restrict__ pos, const double* __restrict__ quat,
+                                                         const long long* __restrict__ offsets,
+                                                         const double* __restrict__ Rm, const double* __restrict__ tv,
+                                                         const double* __restrict__ sv,
+                                                         double* __restrict__ out_pos, double* __restrict__ out_quat,
+                                                         int* __restrict__ status) {
+    __shared__ double tile[256 * 3];
+    __shared__ double xf[20];
+    const int b = blockIdx.y;
+    const long long e0 = offsets[b], n = offsets[b + 1] - e0;
+    if (threadIdx.x == 0) {
+        Quat qR = quat_from_matrix(Rm + 9 * (size_t)b);
+        xf[12] = qR.x; xf[13] = qR.y; xf[14] = qR.z; xf[15] = qR.w;
+    }
+    if (threadIdx.x < 9) xf[threadIdx.x] = Rm[9 * (size_t)b + threadIdx.x];
+    if (threadIdx.x < 3) xf[9 + threadIdx.x] = tv[3 * (size_t)b + threadIdx.x];
+    if (threadIdx.x == 9) xf[16] = sv[b];
+    __syncthreads();
+    const Quat qR{xf[12], xf[13], xf[14], xf[15]};
+    const double s = xf[16];
+    int bad = 0;
+    for (long long lo = (long long)blockIdx.x * 256; lo < n; lo += (long long)gridDim.x * 256) {
+        const int cnt = (int)min((long long)256, n - lo);
+        __syncthreads();
+        for (int k = threadIdx.x; k < 3 * cnt; k += 256) tile[k] = pos[3 * (e0 + lo) + k];
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            const double x = tile[3 * threadIdx.x], y = tile[3 * threadIdx.x + 1], z = tile[3 * threadIdx.x + 2];
+            double rx, ry, rz;
+            mat_vec(xf, x, y, z, rx, ry, rz);
+            tile[3 * threadIdx.x] = s * rx + xf[9]; tile[3 * threadIdx.x + 1] = s * ry + xf[10]; tile[3 * threadIdx.x + 2] = s * rz + xf[11];
+            const long long g = e0 + lo + threadIdx.x;
+            const double2 q01 = reinterpret_cast<const double2*>(quat)[2 * g], q23 = reinterpret_cast<const double2*>(quat)[2 * g + 1];
+            Quat q{q01.x, q01.y, q23.x, q23.y};
+            if (qnorm2(q) == 0.0) bad = 1;
+            Quat r = qunit(qmul(qR, qunit(q)));
+            reinterpret_cast<double2*>(out_quat)[2 * g] = make_double2(r.x, r.y);
+            reinterpret_cast<double2*>(out_quat)[2 * g + 1] = make_double2(r.z, r.w);
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < 3 * cnt; k += 256) out_pos[3 * (e0 + lo) + k] = tile[k];
+    }
+    if (bad) atomicOr(status + b, ST_BAD_QUATERNION);
+}
+
+// ============================================================================= K4: nearest-neighbour error statistics
+// error_i = min_j |traj[idx_i] - cand[idx_j]| over the evaluation set idx = {valid & t > t0 + skip}
+// (:1021-1031), then mean / median / RMSE (:1033).  One block per trajectory; the candidate
+// set lives in shared memory; per query an exact scan over all candidates (fp64).
+
+__global__ void __launch_bounds__(256) ate_nn_kernel(const AteArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* cs = reinterpret_cast<double*>(smem_raw);          // cand[cap*3]
+    double* err = cs + 3 * (size_t)A.cap;                      // err[pow2(cap)]
+    int* idx = reinterpret_cast<int*>(err + A.cap * 2);        // idx[cap]
+    __shared__ int count;
+    __shared__ double scratch[2 * 8];
+    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+        const long long e0 = A.offsets[b];
+        const int n = (int)(A.offsets[b + 1] - e0);
+        double* o = A.stats + 4 * (size_t)b;
+        __syncthreads();
+        if (threadIdx.x == 0) count = 0;
+        __syncthreads();
+        // ordered compaction of the evaluation set (single pass per 256-wide slab)
+        const double t0 = n > 0 ? A.ts[e0] + A.skip : 0.0;
+        for (int lo = 0; lo < n; lo += 256) {
+            const int i = lo + threadIdx.x;
+            bool keep = false;
+            if (i < n) {
+                const double* c = A.cand + 3 * (e0 + i);
+                keep = !row_has_nan(c[0], c[1], c[2]) && A.ts[e0 + i] > t0;
+            }
+            const unsigned bal = __ballot_sync(GSF_FULL_MASK, keep);
+            __shared__ int wcnt[8];
+            if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = __popc(bal);
+            __syncthreads();
+            int base = count;
+            for (int w = 0; w < (threadIdx.x >> 5); ++w) base += wcnt[w];
+            const int pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
+            if (keep && pos < A.cap) {
+                idx[pos] = i;
+                const double* c = A.cand + 3 * (e0 + i);
+                cs[3 * pos] = c[0]; cs[3 * pos + 1] = c[1]; cs[3 * pos + 2] = c[2];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; ++w) tot += wcnt[w]; count += tot; }
+            __syncthreads();
+        }
+        const int m = count;
+        if (m == 0 || m > A.cap) {
+            if (threadIdx.x == 0) { o[0] = o[1] = o[2] = nan(""); o[3] = (m > A.cap) ? -(double)m : 0.0; }
+            continue;
+        }
+        double v[2] = {0.0, 0.0};
+        for (int qi = threadIdx.x; qi < m; qi += 256) {
+            const double* p = A.traj + 3 * (e0 + idx[qi]);
+            const double px = p[0], py = p[1], pz = p[2];
+            double best = INFINITY;
+            for (int j = 0; j < m; ++j) {
+                const double dx = px - cs[3 * j], dy = py - cs[3 * j + 1], dz = pz - cs[3 * j + 2];
+                best = fmin(best, dx * dx + dy * dy + dz * dz);
+            }
+            const double e = sqrt(best);
+            err[qi] = e; v[0] += e; v[1] += e * e;
+        }
+        int p2 = 1; while (p2 < m) p2 <<= 1;
+        for (int k = m + threadIdx.x; k < p2; k += 256) err[k] = INFINITY;
+        block_sum<2>(v, scratch);
+        __syncthreads();
+        for (int k = 2; k <= p2; k <<= 1)                      // bitonic sort (ascending)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < p2; i += 256) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const double a = err[i], c = err[l];
+                        const bool up = (i & k) == 0;
+                        if ((a > c) == up) { err[i] = c; err[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (threadIdx.x == 0) {
+            o[0] = v[0] / m;
+            o[1] = (m & 1) ? err[m / 2] : 0.5 * (err[m / 2 - 1] + err[m / 2]);
+            o[2] = sqrt(v[1] / m);
+            o[3] = (double)m;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- launchers
+cudaError_t launch_utm(bool inverse, const double* a, const double* b, long long n, const UtmConst& K, double* o1, double* o2,
+                       int num_sms, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
+    if (inverse) utm_inverse_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, b, n, K, o1, o2);
+    else utm_forward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, b, n, K, o1, o2);
+    return cudaGetLastError();
+}
+cudaError_t launch_geo_mean(const double* lon, const double* lat, long long n, double* part, int nparts, double* out, cudaStream_t stream) {
+    geo_sum_kernel<<<nparts, 256, 0, stream>>>(lon, lat, n, part);
+    geo_finish_kernel<<<1, 1, 0, stream>>>(part, nparts, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_associate(const AssocArgs& a, int num_sms, cudaStream_t stream) {
+    if (a.B <= 0) return cudaSuccess;
+    int grid = a.B < num_sms * 8 ? a.B : num_sms * 8;
+    associate_kernel<<<grid, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+int sim3_tiles_for(long long max_len) { return (int)((max_len + SIM3_TILE - 1) / SIM3_TILE) > 0 ? (int)((max_len + SIM3_TILE - 1) / SIM3_TILE) : 1; }
+cudaError_t launch_umeyama(const double* src, const double* dst, const long long* offsets, const unsigned char* mask,
+                           int B, long long max_len, double* work, double* R, double* t, double* s, int* status, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    const int tiles = sim3_tiles_for(max_len);
+    for (int b0 = 0; b0 < B; b0 += 65535) {                    // gridDim.y limit
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+        dim3 grid(tiles, nb);
+        sim3_tile_stats_kernel<<<grid, 256, 0, stream>>>(src, dst, offsets + b0, mask, tiles, work + (size_t)b0 * tiles * SIM3_STAT);
+    }
+    sim3_finalize_kernel<<<(B + 63) / 64, 64, 0, stream>>>(work, tiles, B, R, t, s, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_sim3_apply(const double* pos, const double* quat, const long long* offsets, const double* R, const double* t,
+                              const double* s, int B, long long max_len, double* out_pos, double* out_quat, int* status,
+                              int num_sms, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    long long tiles = (max_len + 255) / 256; if (tiles < 1) tiles = 1;
+    long long cap = (long long)num_sms * 32; if (tiles > cap) tiles = cap;
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+        dim3 grid((unsigned)tiles, nb);
+        sim3_apply_kernel<<<grid, 256, 0, stream>>>(pos, quat, offsets + b0, R + 9 * (size_t)b0, t + 3 * (size_t)b0, s + b0,
+                                                    out_pos, out_quat, status + b0);
+    }
+    return cudaGetLastError();
+}
+size_t ate_smem_bytes(int cap) { return (size_t)cap * 24 + (size_t)cap * 16 + (size_t)cap * 4 + 16; }
+cudaError_t launch_ate(const AteArgs& a, int num_sms, cudaStream_t stream) {
+    if (a.B <= 0) return cudaSuccess;
+    size_t smem = ate_smem_bytes(a.cap);
+    cudaError_t e = cudaFuncSetAttribute(ate_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int grid = a.B < num_sms * 4 ? a.B : num_sms * 4;
+    ate_nn_kernel<<<grid, 256, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace gsf

@@ -1,0 +1,232 @@
+"""Batched device API of the fusion path: thin wrappers that hand torch CUDA tensors
+(device memory + streams only) to the C ABI of libgsf.so.  Every function raises if the
+library or a B200 is missing -- nothing here computes on the CPU.
+
+Layout: fp64, C-contiguous, ragged batches described by ``offsets`` (int64 [B+1], in poses):
+ts [P], pos [P,3], quat [P,4] (xyzw), z [P,3] (NaN row = no GNSS at that pose).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import CONFIG, pack_fuse_params
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream=None):
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _f64(t, device=None):
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64))
+    t = t.to(device=device or "cuda", dtype=torch.float64)
+    return t.contiguous()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.GsfError("device API called with a CPU tensor (no CPU fallback exists)")
+
+
+def equal_offsets(batch: int, n: int, device="cuda") -> torch.Tensor:
+    return torch.arange(batch + 1, dtype=torch.int64, device=device) * n
+
+
+def params_tensor(cfg=None, device="cuda", per_traj=None) -> torch.Tensor:
+    """One packed FuseParams record (uint8[184]) or ``per_traj`` = list of (p0, q, r) overrides."""
+    if per_traj is None:
+        blob = pack_fuse_params(cfg)
+    else:
+        blob = np.concatenate([pack_fuse_params(cfg, p0=p0, q=q, r=r) for (p0, q, r) in per_traj])
+    return torch.from_numpy(blob).to(device)
+
+
+def fuse_batched(ts, pos, quat, z, offsets, max_len, params, params_per_traj=False,
+                 init_pos=None, init_quat=None, out_pos=None, out_quat=None, sim3_out=None,
+                 status=None, stream=None):
+    """Sim3 selection + Umeyama + EKF/RTS for B trajectories (gsf_fuse_batched_dev).
+    Returns (out_pos [P,3], out_quat [P,4], sim3 [B,16], status [B] int32); asynchronous."""
+    lib = _lib.load()
+    _require_cuda(ts, pos, quat, z, offsets, params)
+    B = offsets.numel() - 1
+    P = ts.numel()
+    dev = ts.device
+    if out_pos is None:
+        out_pos = torch.empty((P, 3), dtype=torch.float64, device=dev)
+    if out_quat is None:
+        out_quat = torch.empty((P, 4), dtype=torch.float64, device=dev)
+    if sim3_out is None:
+        sim3_out = torch.empty((B, 16), dtype=torch.float64, device=dev)
+    if status is None:
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+    rc = lib.gsf_fuse_batched_dev(_ptr(ts), _ptr(pos), _ptr(quat), _ptr(z), _ptr(offsets), B, int(max_len),
+                                  _ptr(params), int(bool(params_per_traj)), _ptr(init_pos), _ptr(init_quat),
+                                  _ptr(out_pos), _ptr(out_quat), _ptr(sim3_out), _ptr(status), _stream_ptr(stream))
+    _lib.check(rc, "gsf_fuse_batched_dev")
+    return out_pos, out_quat, sim3_out, status
+
+
+def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, params_per_traj=False, stream=None):
+    """Literal step-by-step EKF recursion, one thread per trajectory (gsf_ekf_strict_batched_dev)."""
+    lib = _lib.load()
+    _require_cuda(ts, pos, quat, z, offsets, params, init_pos, init_quat)
+    B = offsets.numel() - 1
+    out_pos = torch.empty_like(pos)
+    out_quat = torch.empty_like(quat)
+    status = torch.empty((B,), dtype=torch.int32, device=ts.device)
+    rc = lib.gsf_ekf_strict_batched_dev(_ptr(ts), _ptr(pos), _ptr(quat), _ptr(z), _ptr(offsets), B, _ptr(params),
+                                        int(bool(params_per_traj)), _ptr(init_pos), _ptr(init_quat),
+                                        _ptr(out_pos), _ptr(out_quat), _ptr(status), _stream_ptr(stream))
+    _lib.check(rc, "gsf_ekf_strict_batched_dev")
+    return out_pos, out_quat, status
+
+
+def umeyama_batched(src, dst, offsets, max_len, mask=None, stream=None):
+    """compute_sim3_transform for B point-set pairs -> (R [B,3,3], t [B,3], s [B], status [B])."""
+    lib = _lib.load()
+    _require_cuda(src, dst, offsets, mask)
+    B = offsets.numel() - 1
+    dev = src.device
+    work = torch.empty((max(1, lib.gsf_umeyama_work_doubles(B, int(max_len))),), dtype=torch.float64, device=dev)
+    R = torch.empty((B, 3, 3), dtype=torch.float64, device=dev)
+    t = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    s = torch.empty((B,), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    rc = lib.gsf_sim3_umeyama_batched_dev(_ptr(src), _ptr(dst), _ptr(offsets), _ptr(mask), B, int(max_len), _ptr(work),
+                                          _ptr(R), _ptr(t), _ptr(s), _ptr(status), _stream_ptr(stream))
+    _lib.check(rc, "gsf_sim3_umeyama_batched_dev")
+    return R, t, s, status
+
+
+def sim3_apply_batched(pos, quat, offsets, max_len, R, t, s, stream=None):
+    """transform_trajectory for B trajectories -> (pos', quat', status)."""
+    lib = _lib.load()
+    _require_cuda(pos, quat, offsets, R, t, s)
+    B = offsets.numel() - 1
+    out_pos = torch.empty_like(pos)
+    out_quat = torch.empty_like(quat)
+    status = torch.zeros((B,), dtype=torch.int32, device=pos.device)
+    rc = lib.gsf_sim3_apply_dev(_ptr(pos), _ptr(quat), _ptr(offsets), _ptr(R), _ptr(t), _ptr(s), B, int(max_len),
+                                _ptr(out_pos), _ptr(out_quat), _ptr(status), _stream_ptr(stream))
+    _lib.check(rc, "gsf_sim3_apply_dev")
+    return out_pos, out_quat, status
+
+
+def ate_nn_batched(traj, cand, ts, offsets, max_len, skip=5.0, stream=None):
+    """Nearest-neighbour error statistics -> stats [B,4] = mean, median, RMSE, count."""
+    lib = _lib.load()
+    _require_cuda(traj, cand, ts, offsets)
+    B = offsets.numel() - 1
+    stats = torch.empty((B, 4), dtype=torch.float64, device=traj.device)
+    rc = lib.gsf_ate_nn_batched_dev(_ptr(traj), _ptr(cand), _ptr(ts), _ptr(offsets), B, int(max_len), float(skip),
+                                    _ptr(stats), _stream_ptr(stream))
+    _lib.check(rc, "gsf_ate_nn_batched_dev")
+    return stats
+
+
+def utm_forward(lon, lat, zone: int, south: bool, stream=None):
+    lib = _lib.load()
+    _require_cuda(lon, lat)
+    east, north = torch.empty_like(lon), torch.empty_like(lat)
+    rc = lib.gsf_utm_forward_dev(_ptr(lon), _ptr(lat), lon.numel(), int(zone), int(bool(south)), _ptr(east), _ptr(north),
+                                 _stream_ptr(stream))
+    _lib.check(rc, "gsf_utm_forward_dev")
+    return east, north
+
+
+def utm_inverse(east, north, zone: int, south: bool, stream=None):
+    lib = _lib.load()
+    _require_cuda(east, north)
+    lon, lat = torch.empty_like(east), torch.empty_like(north)
+    rc = lib.gsf_utm_inverse_dev(_ptr(east), _ptr(north), east.numel(), int(zone), int(bool(south)), _ptr(lon), _ptr(lat),
+                                 _stream_ptr(stream))
+    _lib.check(rc, "gsf_utm_inverse_dev")
+    return lon, lat
+
+
+def geo_zone(lon, lat, stream=None):
+    """auto_utm_projection on the device -> tensor [4] = mean lon, mean lat, zone, south."""
+    lib = _lib.load()
+    _require_cuda(lon, lat)
+    part = torch.empty((2 * _lib.GEO_PARTS,), dtype=torch.float64, device=lon.device)
+    out = torch.empty((4,), dtype=torch.float64, device=lon.device)
+    rc = lib.gsf_geo_zone_dev(_ptr(lon), _ptr(lat), lon.numel(), _ptr(part), _ptr(out), _stream_ptr(stream))
+    _lib.check(rc, "gsf_geo_zone_dev")
+    return out
+
+
+def associate_spline(gps_t, gps_xyz, gps_offsets, slam_t, slam_offsets, gap=5.0, stream=None):
+    """dynamic_time_alignment's per-segment interpolation -> (aligned [n,3], valid [n] uint8)."""
+    lib = _lib.load()
+    _require_cuda(gps_t, gps_xyz, gps_offsets, slam_t, slam_offsets)
+    B = gps_offsets.numel() - 1
+    dev = gps_t.device
+    work = torch.empty((max(1, 4 * gps_t.numel()),), dtype=torch.float64, device=dev)
+    aligned = torch.empty((slam_t.numel(), 3), dtype=torch.float64, device=dev)
+    valid = torch.empty((slam_t.numel(),), dtype=torch.uint8, device=dev)
+    rc = lib.gsf_associate_spline_dev(_ptr(gps_t), _ptr(gps_xyz), _ptr(gps_offsets), _ptr(slam_t), _ptr(slam_offsets),
+                                      B, float(gap), _ptr(work), _ptr(aligned), _ptr(valid), _stream_ptr(stream))
+    _lib.check(rc, "gsf_associate_spline_dev")
+    return aligned, valid
+
+
+def synth_generate(batch: int, n: int, dt: float, speed: float, seed: int, first_traj: int = 0,
+                   outage_prob: float = 0.0, outage_max_len: int = 0, device="cuda", out=None, stream=None):
+    """Device-side synthetic batch -> (ts [B*n], pos [B*n,3], quat [B*n,4], z [B*n,3])."""
+    lib = _lib.load()
+    P = batch * n
+    if out is None:
+        ts = torch.empty((P,), dtype=torch.float64, device=device)
+        pos = torch.empty((P, 3), dtype=torch.float64, device=device)
+        quat = torch.empty((P, 4), dtype=torch.float64, device=device)
+        z = torch.empty((P, 3), dtype=torch.float64, device=device)
+    else:
+        ts, pos, quat, z = out
+    rc = lib.gsf_synth_generate_dev(_ptr(ts), _ptr(pos), _ptr(quat), _ptr(z), int(first_traj), int(batch), int(n),
+                                    float(dt), float(speed), int(seed), float(outage_prob), int(outage_max_len),
+                                    _stream_ptr(stream))
+    _lib.check(rc, "gsf_synth_generate_dev")
+    return ts, pos, quat, z
+
+
+def fuse_batched_host(ts, pos, quat, z, offsets, max_len, params_blob, params_per_traj=False,
+                      init_pos=None, init_quat=None, out_pos=None, out_quat=None, sim3_out=None, status=None):
+    """Host-buffer entry point (gsf_fuse_batched_host): numpy / pinned CPU tensors in and out,
+    H2D + kernel + D2H pipelined inside the library.  Blocking."""
+    lib = _lib.load()
+
+    def hp(a):
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            return ctypes.c_void_p(a.data_ptr())
+        return ctypes.c_void_p(a.ctypes.data)
+
+    B = len(offsets) - 1
+    P = int(offsets[-1])
+    if out_pos is None:
+        out_pos = np.empty((P, 3))
+    if out_quat is None:
+        out_quat = np.empty((P, 4))
+    if sim3_out is None:
+        sim3_out = np.empty((B, 16))
+    if status is None:
+        status = np.empty((B,), dtype=np.int32)
+    rc = lib.gsf_fuse_batched_host(hp(ts), hp(pos), hp(quat), hp(z), hp(offsets), B, int(max_len), hp(params_blob),
+                                   int(bool(params_per_traj)), hp(init_pos), hp(init_quat),
+                                   hp(out_pos), hp(out_quat), hp(sim3_out), hp(status))
+    _lib.check(rc, "gsf_fuse_batched_host")
+    return out_pos, out_quat, sim3_out, status
+
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,143 @@
+/* gsf.h -- C ABI of libgsf.so: B200 (sm_100a) kernels for the GPS/SLAM fusion path of
+ * A2ureeE/GPS-optimize-SLAM (EKFGPSSLAM.py).
+ *
+ * The reference is pure Python and has no FFI of its own; the boundary it offers is the
+ * function surface of EKFGPSSLAM.py.  Every entry point below names the reference function
+ * (file:line in /root/reference/EKFGPSSLAM.py) it replaces; INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - All arithmetic is IEEE fp64.  Arrays are C-contiguous row-major AoS exactly as the
+ *     reference holds them: timestamps [n], positions [n,3], quaternions [n,4] xyzw.
+ *   - Batches are ragged: `offsets[B+1]` (int64, in poses) delimits trajectory b as
+ *     [offsets[b], offsets[b+1]).
+ *   - "_dev" functions take DEVICE pointers and a cudaStream_t (as void*); they launch
+ *     asynchronously, allocate nothing and never synchronise.  All device pointers must be
+ *     16-byte aligned.  "_host" functions take HOST pointers, stage through an internal
+ *     workspace and return when the results are in the host buffers.
+ *   - Return value: 0 on success, a negative GSF_E_* code otherwise (gsf_last_error() has
+ *     the text).  Per-trajectory conditions are reported in `status[b]` as GSF_ST_* bits.
+ *   - A "measurement" row of NaNs means "no GNSS at this pose" (the reference's
+ *     valid_mask == False, EKFGPSSLAM.py:867-869).
+ */
+#ifndef GSF_H
+#define GSF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSF_E_INVALID   (-1)   /* bad argument (null pointer, misalignment, size) */
+#define GSF_E_CUDA      (-2)   /* CUDA runtime error */
+#define GSF_E_NO_DEVICE (-3)   /* no usable sm_100 device: there is no CPU fallback */
+#define GSF_E_TOO_LARGE (-4)   /* trajectory does not fit the staging buffer */
+
+#define GSF_ST_OK               0
+#define GSF_ST_TOO_FEW_POINTS   1   /* (None,None,None) :431 / ValueError :975,:997 */
+#define GSF_ST_DEGENERATE       2   /* collinear points: rotation not unique */
+#define GSF_ST_BAD_QUATERNION   4   /* zero-norm quaternion (scipy ValueError, :84, :466) */
+#define GSF_ST_EMPTY            8
+#define GSF_ST_RANSAC_OUTLIERS 16   /* all-points fit has residuals >= threshold (:411) */
+#define GSF_ST_TOO_LONG        32
+
+/* Flattened CONFIG (EKFGPSSLAM.py:22-71); 184 bytes, layout fixed. */
+typedef struct gsf_fuse_params {
+    double p0[7];            /* ekf.initial_cov_diag      (only [0..2] influence outputs) */
+    double q[7];             /* ekf.process_noise_diag, per second */
+    double r[3];             /* ekf.meas_noise_diag, used as variances (:686) */
+    double gap_threshold;    /* time_alignment.max_gps_gap_threshold */
+    double max_duration;     /* sim3_ransac.max_initial_duration */
+    double yaw_rate_thresh;  /* rts_decision.sharp_turn_yaw_rate_threshold, rad/s */
+    double residual_thresh;  /* sim3_ransac.residual_threshold (<= 0: skip the check) */
+    double eval_skip;        /* seconds dropped before evaluation (:1021) */
+    int32_t min_samples;     /* sim3_ransac.min_samples */
+    int32_t sharp_turn_steps;/* rts_decision.default_ekf_transition_steps_on_sharp_turn */
+} gsf_fuse_params;
+
+const char* gsf_version(void);
+const char* gsf_last_error(void);
+/* Number of SMs of the current device, or GSF_E_NO_DEVICE. */
+int gsf_device_sm_count(void);
+
+/* ---- fused path: Sim3 point selection (:972-998) + compute_sim3_transform (:428-459) +
+ *      row 0 of transform_trajectory (:461-467) + apply_ekf_correction (:831-935), for B
+ *      independent trajectories with pre-associated measurements z.
+ *      params: 1 record (params_per_traj = 0) or B records.
+ *      init_pos/init_quat: NULL, or [B,3]/[B,4] to skip the Sim3 stage and start the filter
+ *      from a given pose (the stand-alone apply_ekf_correction contract).
+ *      sim3_out [B,16]: R(9, row-major) t(3) s n_selected n_valid n_residual_violators; may be NULL.
+ *      max_len: largest trajectory length in the batch (sizes the shared-memory staging). */
+int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,
+                         const int64_t* offsets, int32_t B, int64_t max_len,
+                         const gsf_fuse_params* params, int32_t params_per_traj,
+                         const double* init_pos, const double* init_quat,
+                         double* out_pos, double* out_quat, double* sim3_out, int32_t* status,
+                         void* stream);
+
+/* ---- apply_ekf_correction (:831-935), literal step-by-step recursion, one thread per
+ *      trajectory (general path; keeps the zero-motion fallback of :84-86). */
+int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,
+                               const int64_t* offsets, int32_t B,
+                               const gsf_fuse_params* params, int32_t params_per_traj,
+                               const double* init_pos, const double* init_quat,
+                               double* out_pos, double* out_quat, int32_t* status, void* stream);
+
+/* ---- compute_sim3_transform (:428-459) batched.  mask: NULL or one byte per point.
+ *      work: gsf_umeyama_work_doubles(B, max_len) doubles.  R [B,9], t [B,3], s [B]. */
+int64_t gsf_umeyama_work_doubles(int32_t B, int64_t max_len);
+int gsf_sim3_umeyama_batched_dev(const double* src, const double* dst, const int64_t* offsets,
+                                 const uint8_t* mask, int32_t B, int64_t max_len, double* work,
+                                 double* R, double* t, double* s, int32_t* status, void* stream);
+
+/* ---- transform_trajectory (:461-467) batched; status must be zero-initialised. */
+int gsf_sim3_apply_dev(const double* pos, const double* quat, const int64_t* offsets,
+                       const double* R, const double* t, const double* s, int32_t B, int64_t max_len,
+                       double* out_pos, double* out_quat, int32_t* status, void* stream);
+
+/* ---- evaluation (:1021-1033): nearest-neighbour error statistics of `traj` against the
+ *      candidate set {cand[i] : cand[i] not NaN and ts[i] > ts[0] + skip}.
+ *      stats [B,4]: mean, median, RMSE, count (count < 0: set larger than the shared-memory
+ *      capacity, statistics NaN). */
+int gsf_ate_nn_batched_dev(const double* traj, const double* cand, const double* ts,
+                           const int64_t* offsets, int32_t B, int64_t max_len, double skip,
+                           double* stats, void* stream);
+
+/* ---- pyproj Proj("+proj=utm +zone=Z [+south] +ellps=WGS84") forward (:270) / inverse (:295). */
+int gsf_utm_forward_dev(const double* lon, const double* lat, int64_t n, int32_t zone, int32_t south,
+                        double* east, double* north, void* stream);
+int gsf_utm_inverse_dev(const double* east, const double* north, int64_t n, int32_t zone, int32_t south,
+                        double* lon, double* lat, void* stream);
+/* ---- auto_utm_projection (:127-134) on the device: out[4] = mean lon, mean lat, zone, south.
+ *      part: 2*GSF_GEO_PARTS doubles of scratch. */
+#define GSF_GEO_PARTS 1024
+int gsf_geo_zone_dev(const double* lon, const double* lat, int64_t n, double* part, double* out, void* stream);
+
+/* ---- dynamic_time_alignment (:325-387) after the host-side argsort/unique (:340-349):
+ *      per-segment not-a-knot cubic / linear interpolation of the GNSS track at the SLAM
+ *      stamps.  work: 4 doubles per GNSS sample.  aligned [n_slam,3] NaN-filled, valid [n_slam]. */
+int gsf_associate_spline_dev(const double* gps_t, const double* gps_xyz, const int64_t* gps_offsets,
+                             const double* slam_t, const int64_t* slam_offsets, int32_t B, double gap,
+                             double* work, double* aligned, uint8_t* valid, void* stream);
+
+/* ---- synthetic batch generator for the large bench configs (equal lengths n). */
+int gsf_synth_generate_dev(double* ts, double* pos, double* quat, double* z, int64_t first_traj,
+                           int32_t B, int32_t n, double dt, double speed, uint64_t seed,
+                           double outage_prob, int32_t outage_max_len, void* stream);
+
+/* ---- host-buffer entry point of the fused path (the call a reference-side binding makes):
+ *      same contract as gsf_fuse_batched_dev with HOST pointers; copies in, runs, copies out,
+ *      chunked and double-buffered on internal streams.  Returns when outputs are complete. */
+int gsf_fuse_batched_host(const double* ts, const double* pos, const double* quat, const double* z,
+                          const int64_t* offsets, int32_t B, int64_t max_len,
+                          const gsf_fuse_params* params, int32_t params_per_traj,
+                          const double* init_pos, const double* init_quat,
+                          double* out_pos, double* out_quat, double* sim3_out, int32_t* status);
+/* Release the internal workspace of the host entry points. */
+void gsf_host_workspace_free(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSF_H */

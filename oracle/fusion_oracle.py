@@ -179,8 +179,8 @@ def umeyama(src, dst):
         Vt = Vt.copy()
         Vt[-1] *= -1
         R = Vt.T @ U.T
-    var_s = np.sum(a * a) / n
-    tr = np.sum(S * np.array([1.0, 1.0, np.linalg.det(R)]))
+    var_s = np.sum(np.sum(a ** 2, axis=1)) / n
+    tr = np.sum(S * np.diag(np.eye(3) @ np.diag([1, 1, np.linalg.det(R)])))
     if var_s < 1e-12:
         scale = 1.0
     else:

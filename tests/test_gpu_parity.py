@@ -1,0 +1,383 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the golden vectors.
+Run on a B200:  python -m pytest tests -m gpu -x -q
+
+Tolerances (north_star: 1e-9 relative in fp64).  UTM-scale coordinates are ~5.4e6 m, where
+one fp64 ulp is 9.3e-10 m; positions are compared with an absolute tolerance of 2e-7 m
+(4e-14 relative), quaternions / rotations with 1e-9 absolute."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+POS_ATOL = 2e-7
+ROT_ATOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def gsf():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    from gps_optimize_slam_b200 import _lib, fusion
+    _lib.load()                                   # raises when libgsf.so is missing
+    return fusion
+
+
+def dev(a, dtype=torch.float64):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype=dtype)
+
+
+def pack(trajs):
+    """list of dict(ts,pos,quat,gps) -> flat device arrays + offsets."""
+    lens = [len(t["ts"]) for t in trajs]
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    cat = lambda k: np.concatenate([t[k] for t in trajs])
+    return dev(cat("ts")), dev(cat("pos")), dev(cat("quat")), dev(cat("gps")), dev(off, torch.int64), off, max(lens)
+
+
+def oracle_pipeline(tr, cfg):
+    from oracle import fusion_oracle as fo
+    ts, p, q, z = tr["ts"], tr["pos"], tr["quat"], tr["gps"]
+    valid = ~np.isnan(z).any(1)
+    sel = fo.sim3_point_selection(ts, valid, cfg["time_alignment"]["max_gps_gap_threshold"],
+                                  cfg["sim3_ransac"]["max_initial_duration"], cfg["sim3_ransac"]["min_samples"])
+    R, t, s = fo.umeyama(p[sel], z[sel])
+    sp, sq = fo.sim3_apply(p, q, R, t, s)
+    fp, fq = fo.ekf_fuse(ts, p, q, z, valid, sp[0], sq[0], cfg)
+    return dict(R=R, t=t, s=s, sel=sel, sim3_pos=sp, sim3_quat=sq, pos=fp, quat=fq, valid=valid)
+
+
+def mixed_batch():
+    from gps_optimize_slam_b200 import synth
+    specs = [dict(seed=1, n=271), dict(seed=2, n=271, outages=[(50, 90)]), dict(seed=3, n=150, outages=[(0, 9), (70, 71)]),
+             dict(seed=4, n=271, outages=[(50, 90)], sharp_turn_at=70), dict(seed=5, n=1000, dt=0.1, speed=10.0, outages=[(300, 420)]),
+             dict(seed=6, n=33), dict(seed=7, n=400, outages=[(100, 160)]), dict(seed=8, n=271, outages=[(250, 271)]),
+             dict(seed=9, n=64, quat_scale_jitter=1e-3), dict(seed=10, n=5), dict(seed=11, n=97, outages=[(10, 12), (20, 23), (40, 41)]),
+             dict(seed=12, n=272)]
+    return [synth.make_trajectory(**s) for s in specs]
+
+
+def test_device_present(gsf):
+    from gps_optimize_slam_b200 import _lib
+    assert _lib.load().gsf_device_sm_count() > 0
+
+
+@pytest.mark.parametrize("steps", [0, 4])
+def test_fused_ragged_batch_matches_oracle(gsf, steps):
+    from oracle import fusion_oracle as fo
+    cfg = fo.default_config()
+    cfg["rts_decision"]["default_ekf_transition_steps_on_sharp_turn"] = steps
+    trajs = mixed_batch()
+    ts, pos, quat, z, off_d, off, max_len = pack(trajs)
+    p, q, sim3, st = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, gsf.params_tensor(cfg))
+    p, q, sim3, st = p.cpu().numpy(), q.cpu().numpy(), sim3.cpu().numpy(), st.cpu().numpy()
+    for b, tr in enumerate(trajs):
+        o = oracle_pipeline(tr, cfg)
+        sl = slice(off[b], off[b + 1])
+        assert st[b] == 0, (b, st[b])
+        assert int(sim3[b, 13]) == len(o["sel"]) and int(sim3[b, 14]) == int(o["valid"].sum())
+        np.testing.assert_allclose(sim3[b, :9].reshape(3, 3), o["R"], atol=ROT_ATOL, err_msg=f"R traj {b}")
+        np.testing.assert_allclose(sim3[b, 9:12], o["t"], rtol=1e-12, atol=POS_ATOL)
+        assert abs(sim3[b, 12] - o["s"]) < 1e-11
+        np.testing.assert_allclose(p[sl], o["pos"], rtol=0, atol=POS_ATOL, err_msg=f"pos traj {b}")
+        np.testing.assert_allclose(q[sl], o["quat"], rtol=0, atol=ROT_ATOL, err_msg=f"quat traj {b}")
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_fused_matches_reference_golden(gsf, case):
+    """Inputs and expected outputs produced by the unmodified reference (tests/golden)."""
+    g = load_golden(case)
+    n = len(g["slam_ts"])
+    off = dev(np.array([0, n]), torch.int64)
+    p, q, sim3, st = gsf.fuse_batched(dev(g["slam_ts"]), dev(g["slam_pos"]), dev(g["slam_quat"]), dev(g["aligned"]), off, n,
+                                      gsf.params_tensor())
+    sim3 = sim3.cpu().numpy()[0]
+    assert int(st.cpu()[0]) == 0
+    assert int(sim3[13]) == len(g["sim3_indices"])
+    np.testing.assert_allclose(sim3[:9].reshape(3, 3), g["R"], atol=ROT_ATOL)
+    np.testing.assert_allclose(sim3[9:12], g["t"], rtol=1e-12, atol=POS_ATOL)
+    assert abs(sim3[12] - float(g["s"])) < 1e-11
+    np.testing.assert_allclose(p.cpu().numpy(), g["ekf_pos"], rtol=0, atol=POS_ATOL)
+    np.testing.assert_allclose(q.cpu().numpy(), g["ekf_quat"], rtol=0, atol=ROT_ATOL)
+
+
+def test_strict_kernel_and_ekf_only_mode(gsf):
+    from oracle import fusion_oracle as fo
+    cfg = fo.default_config()
+    trajs = mixed_batch()
+    ts, pos, quat, z, off_d, off, max_len = pack(trajs)
+    outs = [oracle_pipeline(t, cfg) for t in trajs]
+    ip = dev(np.stack([o["sim3_pos"][0] for o in outs]))
+    iq = dev(np.stack([o["sim3_quat"][0] for o in outs]))
+    prm = gsf.params_tensor(cfg)
+    ps, qs, st = gsf.ekf_strict_batched(ts, pos, quat, z, off_d, prm, ip, iq)
+    pf, qf, _, st2 = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, prm, init_pos=ip, init_quat=iq)
+    assert not st.cpu().numpy().any() and not st2.cpu().numpy().any()
+    exp_p = np.concatenate([o["pos"] for o in outs]); exp_q = np.concatenate([o["quat"] for o in outs])
+    for got_p, got_q in ((ps, qs), (pf, qf)):
+        np.testing.assert_allclose(got_p.cpu().numpy(), exp_p, rtol=0, atol=POS_ATOL)
+        np.testing.assert_allclose(got_q.cpu().numpy(), exp_q, rtol=0, atol=ROT_ATOL)
+
+
+def test_strict_kernel_zero_quaternion_fallback(gsf):
+    from gps_optimize_slam_b200 import synth, _lib
+    from oracle import fusion_oracle as fo
+    cfg = fo.default_config()
+    tr = synth.make_trajectory(77, outages=[(30, 40)])
+    o = oracle_pipeline(tr, cfg)
+    tr["quat"][100] = 0; tr["quat"][35] = 0; tr["quat"][36] = 0
+    fp, fq = fo.ekf_fuse(tr["ts"], tr["pos"], tr["quat"], tr["gps"], o["valid"], o["sim3_pos"][0], o["sim3_quat"][0], cfg)
+    ts, pos, quat, z, off_d, off, max_len = pack([tr])
+    prm = gsf.params_tensor(cfg)
+    ip, iq = dev(o["sim3_pos"][:1]), dev(o["sim3_quat"][:1])
+    ps, qs, st = gsf.ekf_strict_batched(ts, pos, quat, z, off_d, prm, ip, iq)
+    assert int(st.cpu()[0]) == _lib.ST_BAD_QUATERNION
+    np.testing.assert_allclose(ps.cpu().numpy(), fp, rtol=0, atol=POS_ATOL)
+    np.testing.assert_allclose(qs.cpu().numpy(), fq, rtol=0, atol=ROT_ATOL)
+    # the fused pipeline mirrors the reference run, which aborts (scipy ValueError at :466)
+    _, _, _, stf = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, prm)
+    assert int(stf.cpu()[0]) & _lib.ST_BAD_QUATERNION
+
+
+def test_edge_cases_status(gsf):
+    from gps_optimize_slam_b200 import synth, _lib
+    a = synth.make_trajectory(21, n=3)                 # < min_samples(4) points
+    b = synth.make_trajectory(22, n=40); b["gps"][:] = np.nan      # no GNSS at all
+    c = synth.make_trajectory(23, n=1)
+    d = synth.make_trajectory(24, n=50)
+    e = synth.make_trajectory(25, n=50); e["gps"][3:] = np.nan     # 3 valid points only
+    ts, pos, quat, z, off_d, off, max_len = pack([a, b, c, d, e])
+    p, q, sim3, st = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, gsf.params_tensor())
+    st = st.cpu().numpy(); p = p.cpu().numpy()
+    assert (st[[0, 1, 2, 4]] & _lib.ST_TOO_FEW_POINTS).all() and st[3] == 0
+    assert np.isnan(p[off[0]:off[3]]).all() and np.isfinite(p[off[3]:off[4]]).all()
+
+
+def test_umeyama_and_apply_kernels(gsf):
+    from oracle import fusion_oracle as fo
+    trajs = mixed_batch()
+    src = np.concatenate([t["pos"] for t in trajs]); dst = np.concatenate([np.nan_to_num(t["gps"], nan=1.0) for t in trajs])
+    dst[: len(trajs[0]["ts"])] = dst[: len(trajs[0]["ts"])][:, [1, 0, 2]]       # reflection branch for trajectory 0
+    lens = [len(t["ts"]) for t in trajs]
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    R, t, s, st = gsf.umeyama_batched(dev(src), dev(dst), dev(off, torch.int64), max(lens))
+    quat = np.concatenate([tr["quat"] for tr in trajs])
+    ap, aq, ast = gsf.sim3_apply_batched(dev(src), dev(quat), dev(off, torch.int64), max(lens), R, t, s)
+    R, t, s, ap, aq = [x.cpu().numpy() for x in (R, t, s, ap, aq)]
+    for b in range(len(trajs)):
+        sl = slice(off[b], off[b + 1])
+        Ro, to, so = fo.umeyama(src[sl], dst[sl])
+        np.testing.assert_allclose(R[b], Ro, atol=ROT_ATOL); np.testing.assert_allclose(t[b], to, rtol=1e-11, atol=POS_ATOL)
+        assert abs(s[b] - so) < 1e-11
+        po, qo = fo.sim3_apply(src[sl], quat[sl], Ro, to, so)
+        np.testing.assert_allclose(ap[sl], po, rtol=0, atol=POS_ATOL); np.testing.assert_allclose(aq[sl], qo, rtol=0, atol=ROT_ATOL)
+    # large single trajectory spanning several reduction tiles + masked points
+    rng = np.random.default_rng(5)
+    n = 50000
+    big = rng.normal(size=(n, 3)) * [300, 200, 5]
+    Rt = fo.Rotation.random(random_state=3).as_matrix()
+    tgt = 1.07 * big @ Rt.T + [4e5, 5e6, 100] + rng.normal(size=(n, 3)) * 0.1
+    mask = rng.uniform(size=n) < 0.7
+    R1, t1, s1, _ = gsf.umeyama_batched(dev(big), dev(tgt), dev(np.array([0, n]), torch.int64), n, mask=dev(mask.astype(np.uint8), torch.uint8))
+    Ro, to, so = fo.umeyama(big[mask], tgt[mask])
+    np.testing.assert_allclose(R1[0].cpu().numpy(), Ro, atol=ROT_ATOL); assert abs(float(s1[0].cpu()) - so) < 1e-11
+    np.testing.assert_allclose(t1[0].cpu().numpy(), to, rtol=1e-11)
+    # fewer than 3 points -> (None, None, None) status
+    _, _, _, st2 = gsf.umeyama_batched(dev(big[:2]), dev(tgt[:2]), dev(np.array([0, 2]), torch.int64), 2)
+    assert int(st2.cpu()[0]) == 1
+
+
+def test_ate_kernel(gsf):
+    from oracle import fusion_oracle as fo
+    cfg = fo.default_config()
+    trajs = [t for t in mixed_batch() if len(t["ts"]) >= 64]
+    ts, pos, quat, z, off_d, off, max_len = pack(trajs)
+    p, q, sim3, st = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, gsf.params_tensor(cfg))
+    stats = gsf.ate_nn_batched(p, z, ts, off_d, max_len, 5.0).cpu().numpy()
+    p = p.cpu().numpy()
+    for b, tr in enumerate(trajs):
+        valid = ~np.isnan(tr["gps"]).any(1)
+        ev = fo.evaluation_indices(tr["ts"], valid)
+        exp = fo.error_stats(fo.nn_errors(p[off[b]:off[b + 1]], tr["gps"], ev))
+        assert int(stats[b, 3]) == len(ev)
+        np.testing.assert_allclose(stats[b, :3], exp, rtol=1e-10)
+
+
+@pytest.mark.parametrize("case", ["pairA", "pairB"])
+def test_golden_ate_numbers(gsf, case):
+    g = load_golden(case)
+    n = len(g["slam_ts"])
+    off = dev(np.array([0, n]), torch.int64)
+    for row, traj in zip(g["stats"], (g["slam_pos"], g["sim3_pos"], g["ekf_pos"])):
+        got = gsf.ate_nn_batched(dev(traj), dev(g["aligned"]), dev(g["slam_ts"]), off, n, 5.0).cpu().numpy()[0]
+        np.testing.assert_allclose(got[:3], row, rtol=1e-10)
+        assert int(got[3]) == len(g["eval_indices"])
+
+
+def test_utm_kernels(gsf):
+    from oracle import utm_kruger as uk
+    rng = np.random.default_rng(2)
+    lon = 9.0 + rng.uniform(-3.4, 3.4, 5000); lat = rng.uniform(-79, 83, 5000)
+    for south in (False, True):
+        e, n = gsf.utm_forward(dev(lon), dev(lat), 32, south)
+        eo, no = uk.utm_forward(lon, lat, 32, south)
+        np.testing.assert_allclose(e.cpu().numpy(), eo, rtol=0, atol=2e-8)
+        np.testing.assert_allclose(n.cpu().numpy(), no, rtol=0, atol=2e-8)
+        lo2, la2 = gsf.utm_inverse(e, n, 32, south)
+        np.testing.assert_allclose(lo2.cpu().numpy(), lon, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(la2.cpu().numpy(), lat, rtol=0, atol=1e-12)
+    for case in ("pairA", "pairB"):
+        g = load_golden(case)
+        raw = g["gnss_raw"]
+        z = gsf.geo_zone(dev(raw[:, 2]), dev(raw[:, 1])).cpu().numpy()
+        zone, south = uk.utm_zone_from_means(raw[:, 2], raw[:, 1])
+        assert int(z[2]) == zone and bool(z[3]) == south
+        e, n = gsf.utm_forward(dev(raw[:, 2]), dev(raw[:, 1]), zone, south)
+        np.testing.assert_allclose(np.column_stack((e.cpu().numpy(), n.cpu().numpy())), g["gps_utm"][:, :2], rtol=0, atol=2e-8)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_association_kernel_matches_reference_golden(gsf, case):
+    g = load_golden(case)
+    one = lambda n: dev(np.array([0, n]), torch.int64)
+    a, v = gsf.associate_spline(dev(g["gps_ts"]), dev(g["gps_utm"]), one(len(g["gps_ts"])), dev(g["slam_ts"]), one(len(g["slam_ts"])), 5.0)
+    a, v = a.cpu().numpy(), v.cpu().numpy().astype(bool)
+    assert np.array_equal(v, g["valid"])
+    assert np.isnan(a[~v]).all()
+    np.testing.assert_allclose(a[v], g["aligned"][v], rtol=0, atol=POS_ATOL)
+
+
+def test_association_short_segments(gsf):
+    """2-3 knot segments are linear, 1-knot segments are skipped (EKFGPSSLAM.py:361-362)."""
+    from oracle import fusion_oracle as fo
+    gt = np.array([0.0, 1.0, 2.0, 10.0, 11.0, 20.0, 30.0, 31.0, 32.0, 33.0, 34.5])
+    gy = np.cumsum(np.random.default_rng(0).normal(size=(len(gt), 3)), axis=0) + [4e5, 5e6, 100]
+    st = np.linspace(-1, 36, 400)
+    ao, vo = fo.associate(st, gt, gy)
+    one = lambda n: dev(np.array([0, n]), torch.int64)
+    a, v = gsf.associate_spline(dev(gt), dev(gy), one(len(gt)), dev(st), one(len(st)), 5.0)
+    assert np.array_equal(v.cpu().numpy().astype(bool), vo)
+    np.testing.assert_allclose(a.cpu().numpy()[vo], ao[vo], rtol=0, atol=POS_ATOL)
+
+
+def test_device_generator_slice_matches_oracle(gsf):
+    """Config-3-style data generated on the device, a slice checked against the oracle; the
+    generator is counter-based so a shard regenerates identically."""
+    from oracle import fusion_oracle as fo
+    cfg = fo.default_config()
+    B, n = 256, 1000
+    ts, pos, quat, z = gsf.synth_generate(B, n, 0.1, 10.0, seed=1234, outage_prob=0.3, outage_max_len=120)
+    off = gsf.equal_offsets(B, n)
+    p, q, sim3, st = gsf.fuse_batched(ts, pos, quat, z, off, n, gsf.params_tensor(cfg))
+    ts2, pos2, quat2, z2 = gsf.synth_generate(64, n, 0.1, 10.0, seed=1234, first_traj=128, outage_prob=0.3, outage_max_len=120)
+    assert torch.equal(pos2, pos[128 * n:192 * n]) and torch.equal(quat2, quat[128 * n:192 * n])
+    h = [x.cpu().numpy() for x in (ts, pos, quat, z, p, q, sim3, st)]
+    checked = 0
+    for b in list(range(0, 12)) + [100, 255]:
+        sl = slice(b * n, (b + 1) * n)
+        tr = dict(ts=h[0][sl], pos=h[1][sl], quat=h[2][sl], gps=h[3][sl])
+        o = oracle_pipeline(tr, cfg)
+        assert h[7][b] == 0
+        np.testing.assert_allclose(h[4][sl], o["pos"], rtol=0, atol=POS_ATOL)
+        np.testing.assert_allclose(h[5][sl], o["quat"], rtol=0, atol=ROT_ATOL)
+        np.testing.assert_allclose(h[6][b, :9].reshape(3, 3), o["R"], atol=ROT_ATOL)
+        checked += 1
+    assert checked == 14 and np.isnan(h[3]).any()
+
+
+def test_host_buffer_entry_matches_device_entry(gsf):
+    from gps_optimize_slam_b200.config import pack_fuse_params
+    trajs = mixed_batch() * 3
+    ts, pos, quat, z, off_d, off, max_len = pack(trajs)
+    p, q, sim3, st = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, gsf.params_tensor())
+    cat = lambda k: np.ascontiguousarray(np.concatenate([t[k] for t in trajs]))
+    hp, hq, hs, hst = gsf.fuse_batched_host(cat("ts"), cat("pos"), cat("quat"), cat("gps"), off, max_len, pack_fuse_params())
+    assert np.array_equal(hp, p.cpu().numpy()) and np.array_equal(hq, q.cpu().numpy())
+    assert np.array_equal(hst, st.cpu().numpy()) and np.array_equal(hs[:, :15], sim3.cpu().numpy()[:, :15])
+
+
+def test_per_trajectory_noise_parameters(gsf):
+    from gps_optimize_slam_b200 import synth
+    from oracle import fusion_oracle as fo
+    tr = synth.make_trajectory(31, n=200, outages=[(60, 90)])
+    sets = [([0.1] * 3 + [0.01] * 4, [q, q, 3 * q] + [0.01] * 4, [r] * 3) for q in (0.01, 0.1, 1.0) for r in (0.05, 0.2, 2.0)]
+    ts, pos, quat, z, off_d, off, max_len = pack([tr] * len(sets))
+    prm = gsf.params_tensor(per_traj=sets)
+    p, q, _, st = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, prm, params_per_traj=True)
+    p = p.cpu().numpy()
+    for b, (p0, qq, rr) in enumerate(sets):
+        cfg = fo.default_config()
+        cfg["ekf"].update(initial_cov_diag=p0, process_noise_diag=qq, meas_noise_diag=rr)
+        np.testing.assert_allclose(p[off[b]:off[b + 1]], oracle_pipeline(tr, cfg)["pos"], rtol=0, atol=POS_ATOL)
+
+
+def test_bit_reproducible_and_shard_invariant(gsf):
+    """Same inputs -> same bits; an N-way shard (separate launches over trajectory ranges)
+    equals the unsharded run bit for bit (multi-GPU without a cluster)."""
+    B, n = 512, 271
+    ts, pos, quat, z = gsf.synth_generate(B, n, 0.104, 13.0, seed=9, outage_prob=0.2, outage_max_len=80)
+    off = gsf.equal_offsets(B, n)
+    prm = gsf.params_tensor()
+    p1, q1, s1, _ = gsf.fuse_batched(ts, pos, quat, z, off, n, prm)
+    p2, q2, s2, _ = gsf.fuse_batched(ts, pos, quat, z, off, n, prm)
+    assert torch.equal(p1, p2) and torch.equal(q1, q2) and torch.equal(s1[:, :15], s2[:, :15])
+    for k in range(4):
+        a, b = k * B // 4, (k + 1) * B // 4
+        sl = slice(a * n, b * n)
+        ps, qs, ss, _ = gsf.fuse_batched(ts[sl], pos[sl], quat[sl], z[sl], gsf.equal_offsets(b - a, n), n, prm)
+        assert torch.equal(ps, p1[sl]) and torch.equal(qs, q1[sl]) and torch.equal(ss[:, :15], s1[a:b, :15])
+
+
+def test_full_size_properties(gsf):
+    """Config-2 size (4096 x 271) and a config-3 slab (8192 x 1000): size-independent
+    properties -- Sim3 recovers a rotation (R R^T = I, det +1), fused track hugs GNSS better
+    than the Sim3-aligned one, strict and scan formulations agree."""
+    prm = gsf.params_tensor()
+    for (B, n, dt, v) in ((4096, 271, 0.104, 13.0), (8192, 1000, 0.1, 10.0)):
+        ts, pos, quat, z = gsf.synth_generate(B, n, dt, v, seed=77)
+        off = gsf.equal_offsets(B, n)
+        p, q, sim3, st = gsf.fuse_batched(ts, pos, quat, z, off, n, prm)
+        assert int(st.abs().sum().cpu()) == 0
+        R = sim3[:, :9].reshape(B, 3, 3)
+        eye = torch.eye(3, dtype=torch.float64, device="cuda")
+        assert float((R @ R.transpose(1, 2) - eye).abs().max().cpu()) < 1e-12
+        assert float((torch.linalg.det(R) - 1).abs().max().cpu()) < 1e-12
+        assert float((q.norm(dim=1) - 1).abs().max().cpu()) < 1e-12
+        s = sim3[:, 12]
+        assert float(s.min().cpu()) > 0.85 and float(s.max().cpu()) < 1.15
+        sp, sq, _ = gsf.sim3_apply_batched(pos, quat, off, n, R.contiguous(), sim3[:, 9:12].contiguous(), s.contiguous())
+        err_f = (p - z).norm(dim=1).reshape(B, n)[:, 50:].mean()
+        err_s = (sp - z).norm(dim=1).reshape(B, n)[:, 50:].mean()
+        assert float(err_f.cpu()) < float(err_s.cpu())
+        ps, qs, _ = gsf.ekf_strict_batched(ts, pos, quat, z, off, prm, sp.reshape(B, n, 3)[:, 0].contiguous(), sq.reshape(B, n, 4)[:, 0].contiguous())
+        assert float((ps - p).abs().max().cpu()) < POS_ATOL and float((qs - q).abs().max().cpu()) < ROT_ATOL
+
+
+def test_dropin_entry_point(gsf, tmp_path):
+    """The drop-in module reproduces the reference's run on the shipped pair A (from the
+    golden fixture; the reference's files do not travel to the GPU box)."""
+    import EKFGPSSLAM as E
+    g = load_golden("pairA")
+    slam_file, gps_file = tmp_path / "slam.txt", tmp_path / "gnss.txt"
+    np.savetxt(slam_file, np.column_stack((g["slam_ts"], g["slam_pos"], g["slam_quat"])))
+    np.savetxt(gps_file, g["gnss_raw"], fmt="%.12f")
+    E.CONFIG["gps_filtering_ransac"]["enabled"] = False          # sklearn filter: host-only, unseeded
+    out = E.main_process(str(slam_file), str(gps_file), save_path=str(tmp_path / "slam_corrected_utm.txt"))
+    assert out["utm_zone"] == "39N"
+    assert abs(out["s"] - float(g["s"])) < 1e-9
+    np.testing.assert_allclose(out["ekf_pos"], g["ekf_pos"], rtol=0, atol=1e-6)
+    m, med, rmse, cnt = out["stats"][("primary GPS", "EKF fused")]
+    np.testing.assert_allclose([m, med, rmse], g["stats"][2], rtol=1e-7)
+    assert cnt == len(g["eval_indices"])
+    saved = np.loadtxt(tmp_path / "slam_corrected_utm.txt", skiprows=1)
+    assert saved.shape == (271, 8)
+    wgs = np.loadtxt(tmp_path / "slam_corrected_wgs84.txt", skiprows=1)
+    assert wgs.shape == (271, 8) and abs(wgs[0, 1] - 49.0336) < 1e-3       # "lon" column holds the file's lat (swap)
+    R, t, s = E.compute_sim3_transform(g["slam_pos"][:2], g["aligned"][:2])
+    assert R is None and t is None and s is None
+    dp, dq = E.calculate_relative_pose(g["slam_pos"][3], g["slam_quat"][3], g["slam_pos"][4], g["slam_quat"][4])
+    from oracle import fusion_oracle as fo
+    dpo, dqo = fo.relative_pose(g["slam_pos"][3], g["slam_quat"][3], g["slam_pos"][4], g["slam_quat"][4])
+    np.testing.assert_allclose(dp, dpo, atol=1e-12); np.testing.assert_allclose(dq, dqo, atol=1e-12)
