@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--trajectories", type=int, default=0, help="override the total trajectory count (debug)")
     ap.add_argument("--e2e-trajectories", type=int, default=0, help="host-buffer sample per rank (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--with-ate", action="store_true", help="also run the NN-ATE kernel + NCCL gather after timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -249,34 +250,36 @@ def main():
             pass
 
     # ---- end to end through the host-buffer C-ABI entry (pinned host buffers, H2D + kernel + D2H per step)
-    Be = args.e2e_trajectories or max(1, min(B_res, (1 << 24) // n))          # ~16.7M poses = 2.4 GB of traffic per step
-    hts, hpos, hquat, hz = [x[: Be * n].cpu().pin_memory() for x in (ts, pos, quat, z)]
-    hop = torch.empty((Be * n, 3), dtype=torch.float64).pin_memory(); hoq = torch.empty((Be * n, 4), dtype=torch.float64).pin_memory()
-    hs3 = torch.empty((Be, 16), dtype=torch.float64).pin_memory(); hst = torch.empty((Be,), dtype=torch.int32).pin_memory()
-    hoff = (torch.arange(Be + 1, dtype=torch.int64) * n).pin_memory()
-    blob = pack_fuse_params()
+    e2e = None
+    if not args.no_e2e:
+        Be = args.e2e_trajectories or max(1, min(B_res, (1 << 24) // n))          # ~16.7M poses = 2.4 GB of traffic per step
+        hts, hpos, hquat, hz = [x[: Be * n].cpu().pin_memory() for x in (ts, pos, quat, z)]
+        hop = torch.empty((Be * n, 3), dtype=torch.float64).pin_memory(); hoq = torch.empty((Be * n, 4), dtype=torch.float64).pin_memory()
+        hs3 = torch.empty((Be, 16), dtype=torch.float64).pin_memory(); hst = torch.empty((Be,), dtype=torch.int32).pin_memory()
+        hoff = (torch.arange(Be + 1, dtype=torch.int64) * n).pin_memory()
+        blob = pack_fuse_params()
 
-    def e2e_step():
-        fusion.fuse_batched_host(hts, hpos, hquat, hz, hoff, n, blob, out_pos=hop, out_quat=hoq, sim3_out=hs3, status=hst)
+        def e2e_step():
+            fusion.fuse_batched_host(hts, hpos, hquat, hz, hoff, n, blob, out_pos=hop, out_quat=hoq, sim3_out=hs3, status=hst)
 
-    e2e_steps = max(3, min(args.steps, 5))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.cpu())
-    e2e_ok = bool(torch.equal(hop, out_pos[: Be * n].cpu())) if passes == 1 else True
-    e2e = {"value": world * Be * (n - 1) * e2e_steps / e2e_s, "unit": "pose-updates/s",
-           "h2d_bytes_per_step": Be * n * 88 + (Be + 1) * 8 + 184, "d2h_bytes_per_step": Be * n * 56 + Be * 132,
-           "sample": f"{Be} trajectories x {n} poses per rank per step, pinned host buffers, {e2e_steps} steps",
-           "matches_device_path": e2e_ok}
+        e2e_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.cpu())
+        e2e_ok = bool(torch.equal(hop, out_pos[: Be * n].cpu())) if passes == 1 else True
+        e2e = {"value": world * Be * (n - 1) * e2e_steps / e2e_s, "unit": "pose-updates/s",
+               "h2d_bytes_per_step": Be * n * 88 + (Be + 1) * 8 + 184, "d2h_bytes_per_step": Be * n * 56 + Be * 132,
+               "sample": f"{Be} trajectories x {n} poses per rank per step, pinned host buffers, {e2e_steps} steps",
+               "matches_device_path": e2e_ok}
 
     # ---- ATE statistics: per-rank NN-ATE kernel on a slab + NCCL gather (outside the timed region)
     ate = None

@@ -38,6 +38,7 @@ DeviceInfo& device_info() {
     }
     return d;
 }
+long long* g_phase_clock = nullptr;     // debug hook, see gsf_debug_phase_clock
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // WGS84 constants of the Krueger series (same numbers as oracle/utm_kruger.py).
@@ -67,12 +68,14 @@ gsf::UtmConst utm_const(int zone, int south) {
 // Threads per trajectory for the fused kernel: enough blocks per SM to keep ~16 warps
 // resident given the shared-memory footprint of one trajectory.
 int pick_threads(int cap, int max_smem) {
+    // Every thread owns an odd-length chunk of poses; scans and reductions cost per thread, so
+    // use the fewest threads that still give ~12 resident warps per SM for the shared-memory
+    // footprint of one trajectory (chunk length stays around 9 poses).
     const size_t smem = gsf::fuse_smem_bytes(cap);
-    int blocks = (int)((size_t)(227 * 1024) / (smem + 1024));
+    int blocks = (int)((size_t)max_smem / (smem + 1024));
     if (blocks < 1) blocks = 1;
     int threads = 32;
-    while (threads < 256 && blocks * threads < 512) threads <<= 1;
-    (void)max_smem;
+    while (threads < 256 && (blocks * threads < 384 || threads * 9 < cap)) threads <<= 1;
     return threads;
 }
 
@@ -114,6 +117,7 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
     a.out_pos = out_pos; a.out_quat = out_quat; a.sim3_out = sim3_out; a.status = status;
     a.B = B; a.cap = cap;
     a.use_tma = aligned16(ts) && aligned16(pos) && aligned16(z) && aligned16(out_pos);
+    a.phase_clock = g_phase_clock;
     cudaError_t e = gsf::launch_fuse(a, pick_threads(cap, d.max_smem), d.sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev");
     return 0;
@@ -253,6 +257,10 @@ int gsf_synth_generate_dev(double* ts, double* pos, double* quat, double* z, int
     if (e != cudaSuccess) return cuda_fail(e, "gsf_synth_generate_dev");
     return 0;
 }
+
+// Debug hook (not part of include/gsf.h): device buffer of 16 int64 receiving clock64() stamps
+// of block 0 at the phase boundaries of one trajectory; NULL switches it off.
+void gsf_debug_phase_clock(long long* dev_buf) { g_phase_clock = dev_buf; }
 
 // ----------------------------------------------------------------------------- host-buffer pipeline
 namespace {

@@ -28,6 +28,8 @@
 
 namespace gsf {
 
+#define GSF_STAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && tid == 0 && b == (int)gridDim.x * 2) A.phase_clock[k] = clock64(); } while (0)
+
 constexpr int FLAG_VALID = 1;
 constexpr int FLAG_SELECTED = 2;
 constexpr int FLAG_RECOVERY = 4;
@@ -52,20 +54,42 @@ __device__ inline Pack<ND> block_exclusive_scan(Pack<ND> x, Op op, const Pack<ND
     for (int k = 0; k < ND; ++k) excl.v[k] = __shfl_up_sync(GSF_FULL_MASK, x.v[k], 1);
     if (lane == 0) excl = ident;
     if (nwarp > 1) {
+        // second level: warp 0 scans the warp totals (<= 8 of them) with shuffles
         __syncthreads();
         if (lane == 31) {
 #pragma unroll
             for (int k = 0; k < ND; ++k) scratch[warp * ND + k] = x.v[k];
         }
         __syncthreads();
-        Pack<ND> pre = ident;
-        for (int w = 0; w < warp; ++w) {
-            Pack<ND> tot;
+        if (warp == 0) {
+            Pack<ND> tot = ident;
+            if (lane < nwarp) {
 #pragma unroll
-            for (int k = 0; k < ND; ++k) tot.v[k] = scratch[w * ND + k];
-            pre = op(pre, tot);
+                for (int k = 0; k < ND; ++k) tot.v[k] = scratch[lane * ND + k];
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                Pack<ND> y;
+#pragma unroll
+                for (int k = 0; k < ND; ++k) y.v[k] = __shfl_up_sync(GSF_FULL_MASK, tot.v[k], o);
+                if (lane >= o) tot = op(y, tot);
+            }
+            Pack<ND> pre;                                   // exclusive prefix of warp `lane`
+#pragma unroll
+            for (int k = 0; k < ND; ++k) pre.v[k] = __shfl_up_sync(GSF_FULL_MASK, tot.v[k], 1);
+            if (lane == 0) pre = ident;
+            if (lane < nwarp) {
+#pragma unroll
+                for (int k = 0; k < ND; ++k) scratch[(8 + lane) * ND + k] = pre.v[k];
+            }
         }
-        excl = op(pre, excl);
+        __syncthreads();
+        if (warp > 0) {
+            Pack<ND> pre;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) pre.v[k] = scratch[(8 + warp) * ND + k];
+            excl = op(pre, excl);
+        }
     }
     return excl;
 }
@@ -129,12 +153,16 @@ __device__ __noinline__ bool sharp_turn_ool(const double* ts, const double* quat
 }
 
 
-constexpr int SCRATCH_DOUBLES = 160;
+constexpr int SCRATCH_DOUBLES = 200;     // block scan: 2 x 8 warps x 12 doubles
+
+// Resident blocks per SM the register budget is sized for: 16 warps for the small blocks,
+// 3 x 128 threads (170 registers) for ~1000-pose trajectories, 1 x 256 for longer ones.
+constexpr int fuse_min_blocks(int threads) { return threads <= 64 ? 512 / threads : (threads == 128 ? 3 : 1); }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const FuseArgs A) {
+__global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_kernel(const FuseArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int cap2 = A.cap + 2;
+    const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
     double* ts_s = reinterpret_cast<double*>(smem_raw);
     double* pos_s = ts_s + cap2;
     double* z_s = pos_s + 3 * (size_t)cap2;
@@ -156,12 +184,23 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
         if (n <= 0) { if (tid == 0) A.status[b] = ST_EMPTY; continue; }
         if (n > A.cap) { if (tid == 0) A.status[b] = ST_TOO_LONG; continue; }
 
+        GSF_STAMP(0);
         // ------------------------------------------------------------------ stage inputs
         const int lead = A.use_tma ? (int)(e0 & 1) : 0;
         double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
         unsigned char* flg = flag_s;
         if (A.use_tma) {
             const int cnt = n + lead, even = cnt & ~1;
+            if (tid == 32 % THREADS && b + (int)gridDim.x < A.B) {        // warm L2 for this block's next trajectory
+                const long long f0 = A.offsets[b + gridDim.x] & ~1ll;
+                const long long fn = (A.offsets[b + gridDim.x + 1] - f0) & ~1ll;
+                if (fn > 0) {
+                    bulk_prefetch_l2(A.ts + f0, (uint32_t)fn * 8u);
+                    bulk_prefetch_l2(A.pos + 3 * f0, (uint32_t)fn * 24u);
+                    bulk_prefetch_l2(A.z + 3 * f0, (uint32_t)fn * 24u);
+                    bulk_prefetch_l2(A.quat + 4 * f0, (uint32_t)fn * 32u);
+                }
+            }
             if (tid == 0 && even > 0) {
                 mbar_expect_tx(mbar, (uint32_t)even * 56u);
                 bulk_g2s(ts_s, A.ts + (e0 - lead), (uint32_t)even * 8u, mbar);
@@ -182,6 +221,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             __syncthreads();
         }
 
+        GSF_STAMP(1);
         // chunk ownership: odd length => conflict-free strided shared-memory access
         int L = (n + THREADS - 1) / THREADS; L |= 1;
         const int c0 = min(tid * L, n), c1 = min(c0 + L, n);
@@ -194,7 +234,6 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             if (v) { ++cntv; lastT = tsS[i]; }
         }
         int st = ST_OK;
-        double RC[9], x0[3]; Quat C;
         const bool ekf_only = A.init_pos != nullptr;
         if (!ekf_only) {
             // -------------------------------------------------------------- Sim3 point selection (:972-998)
@@ -228,6 +267,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
                 block_sum<1>(timed, scratch);
                 mode = ((int)timed[0] < prm.min_samples) ? 1 : 2;
             }
+            GSF_STAMP(2);
             // -------------------------------------------------------------- Umeyama sums (:436-443)
             double s7[7] = {0, 0, 0, 0, 0, 0, 0};
             {
@@ -260,9 +300,13 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             }
             block_sum<10>(h, scratch);
             __syncthreads();
+            GSF_STAMP(3);
             if (warp == 0) {
-                double R[9], t[3], s = 1.0;
-                int ust = (st & ST_TOO_FEW_POINTS) ? 0 : umeyama_finish_ool(nsel, mus, mud, h, h[9], R, t, &s);
+                // copies whose address escapes into the out-of-line SVD: keeps h[]/mus[]/mud[] in registers above
+                double R[9], t[3], s = 1.0, hh[9], ms_[3] = {mus[0], mus[1], mus[2]}, md_[3] = {mud[0], mud[1], mud[2]};
+#pragma unroll
+                for (int k = 0; k < 9; ++k) hh[k] = h[k];
+                int ust = (st & ST_TOO_FEW_POINTS) ? 0 : umeyama_finish_ool(nsel, ms_, md_, hh, h[9], R, t, &s);
                 Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
                 if (qnorm2(q0) == 0.0) ust |= ST_BAD_QUATERNION;
                 if (lane == 0) {
@@ -285,6 +329,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             }
             __syncthreads();
             st |= iscr[8];
+            GSF_STAMP(4);
             // all-points residual check standing in for RANSAC (:409-412): count violators
             double nout[1] = {0.0};
             if (!(st & ST_TOO_FEW_POINTS) && prm.residual_thresh > 0.0) {
@@ -332,15 +377,10 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             __syncthreads();
             continue;
         }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) RC[k] = bc[k];
-        C = Quat{bc[9], bc[10], bc[11], bc[12]};
-        x0[0] = bc[13]; x0[1] = bc[14]; x0[2] = bc[15];
         if (tid == 0) iscr[9] = 0;                                  // "trajectory has a recovered outage"
 
+        GSF_STAMP(5);
         // ------------------------------------------------------------------ covariance: Moebius scan
-        const double Qx = prm.q[0], Qy = prm.q[1], Qz = prm.q[2];
-        const double Rx = prm.r[0], Ry = prm.r[1], Rz = prm.r[2];
         const int s0 = max(c0, 1);                                  // steps owned: i in [s0, c1)
         Pack<12> loc;
 #pragma unroll
@@ -349,8 +389,8 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             int since = 0;
             for (int i = s0; i < c1; ++i) {
                 const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
-                const double qq[3] = {Qx * dt, Qy * dt, Qz * dt};
-                const double rr[3] = {Rx, Ry, Rz};
+                const double qq[3] = {prm.q[0] * dt, prm.q[1] * dt, prm.q[2] * dt};
+                const double rr[3] = {prm.r[0], prm.r[1], prm.r[2]};
                 const bool v = flg[i] & FLAG_VALID;
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
@@ -374,6 +414,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             P[a] = (m[0] * prm.p0[a] + m[1]) / (m[2] * prm.p0[a] + m[3]);
         }
 
+        GSF_STAMP(6);
         // ------------------------------------------------------------------ gains + affine maps
         double pprev[3] = {0, 0, 0};
         if (s0 < c1) { pprev[0] = posS[3 * (s0 - 1)]; pprev[1] = posS[3 * (s0 - 1) + 1]; pprev[2] = posS[3 * (s0 - 1) + 2]; }
@@ -381,14 +422,17 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
         if (c0 == 0 && c1 > 0) { posS[0] = prm.p0[0]; posS[1] = prm.p0[1]; posS[2] = prm.p0[2]; }   // P_f[0]
         Pack<6> aff;
         aff.v[0] = aff.v[1] = aff.v[2] = 1.0; aff.v[3] = aff.v[4] = aff.v[5] = 0.0;
+        double RC[9];                                               // M(C), read where it is used (register pressure)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) RC[k] = bc[k];
         for (int i = s0; i < c1; ++i) {
             const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
             const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
             double u[3];
             mat_vec(RC, p0 - pprev[0], p1 - pprev[1], p2 - pprev[2], u[0], u[1], u[2]);
             pprev[0] = p0; pprev[1] = p1; pprev[2] = p2;
-            const double qq[3] = {Qx * dt, Qy * dt, Qz * dt};
-            const double rr[3] = {Rx, Ry, Rz};
+            const double qq[3] = {prm.q[0] * dt, prm.q[1] * dt, prm.q[2] * dt};
+            const double rr[3] = {prm.r[0], prm.r[1], prm.r[2]};
             const int f = flg[i];
             if (f & FLAG_VALID) {
                 double w = 1.0;
@@ -427,9 +471,10 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
         Pack<6> ida; ida.v[0] = ida.v[1] = ida.v[2] = 1.0; ida.v[3] = ida.v[4] = ida.v[5] = 0.0;
         Pack<6> apre = block_exclusive_scan<6>(aff, AffOp(), ida, scratch);
 
+        GSF_STAMP(7);
         // ------------------------------------------------------------------ state recursion
-        double x[3] = {apre.v[0] * x0[0] + apre.v[3], apre.v[1] * x0[1] + apre.v[4], apre.v[2] * x0[2] + apre.v[5]};
-        if (c0 == 0 && c1 > 0) { zS[0] = x0[0]; zS[1] = x0[1]; zS[2] = x0[2]; }
+        double x[3] = {apre.v[0] * bc[13] + apre.v[3], apre.v[1] * bc[14] + apre.v[4], apre.v[2] * bc[15] + apre.v[5]};
+        if (c0 == 0 && c1 > 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
         for (int i = s0; i < c1; ++i) {
             if (flg[i] & FLAG_VALID) {
 #pragma unroll
@@ -442,6 +487,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
         }
         __syncthreads();
 
+        GSF_STAMP(8);
         // ------------------------------------------------------------------ closed-form RTS over recovered outages
         if (iscr[9]) {
             for (int i = s0; i < c1; ++i) {
@@ -452,9 +498,9 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
                     const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
                     const double* gp = A.pos + 3 * (e0 + i);
                     double u[3];
-                    mat_vec(RC, gp[0] - gp[-3], gp[1] - gp[-2], gp[2] - gp[-1], u[0], u[1], u[2]);
+                    mat_vec(bc, gp[0] - gp[-3], gp[1] - gp[-2], gp[2] - gp[-1], u[0], u[1], u[2]);
                     double ratio_den[3], delta[3];
-                    const double qq[3] = {Qx * dt, Qy * dt, Qz * dt};
+                    const double qq[3] = {prm.q[0] * dt, prm.q[1] * dt, prm.q[2] * dt};
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
                         ratio_den[a] = posS[3 * (i - 1) + a] + qq[a];                  // P_pred[i]
@@ -469,6 +515,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             __syncthreads();
         }
 
+        GSF_STAMP(9);
         // ------------------------------------------------------------------ store fused positions
         double* gout = A.out_pos + 3 * e0;
         if (A.use_tma) {
@@ -482,22 +529,36 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
             for (int i = tid; i < 3 * n; i += THREADS) gout[i] = zS[i];
         }
 
+        GSF_STAMP(10);
         // ------------------------------------------------------------------ quaternions: q_state[i] = C (x) q_hat[i]
         int badq = 0;
         {
-            const double2* qin = reinterpret_cast<const double2*>(A.quat + 4 * e0);
-            double2* qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
-            for (int i = tid; i < n; i += THREADS) {
-                const double2 lo = __ldg(qin + 2 * i), hi = __ldg(qin + 2 * i + 1);
-                Quat qi{lo.x, lo.y, hi.x, hi.y};
-                const double n2 = qnorm2(qi);
-                if (n2 == 0.0) badq = 1;
-                Quat r = qscale(qmul(C, qi), rsqrt(n2));
-                qout[2 * i] = make_double2(r.x, r.y);
-                qout[2 * i + 1] = make_double2(r.z, r.w);
+            const Quat C{bc[9], bc[10], bc[11], bc[12]};
+            const double2* __restrict__ qin = reinterpret_cast<const double2*>(A.quat + 4 * e0);
+            double2* __restrict__ qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
+            for (int i0 = tid; i0 < n; i0 += 4 * THREADS) {
+                double2 lo[4], hi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * THREADS;
+                    if (i < n) { lo[u] = __ldg(qin + 2 * i); hi[u] = __ldg(qin + 2 * i + 1); }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * THREADS;
+                    if (i < n) {
+                        Quat qi{lo[u].x, lo[u].y, hi[u].x, hi[u].y};
+                        const double n2 = qnorm2(qi);
+                        if (n2 == 0.0) badq = 1;
+                        Quat r = qscale(qmul(C, qi), rsqrt(n2));
+                        qout[2 * i] = make_double2(r.x, r.y);
+                        qout[2 * i + 1] = make_double2(r.z, r.w);
+                    }
+                }
             }
         }
         badq = __syncthreads_or(badq);
+        GSF_STAMP(11);
         if (badq) {
             // A zero-norm SLAM quaternion: scipy raises inside transform_trajectory (:466), the
             // reference run aborts.  Flag it and blank the outputs.
@@ -513,6 +574,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) fuse_traj_kernel(const
         }
         if (A.use_tma) fence_proxy_async();
         __syncthreads();
+        GSF_STAMP(12);
     }
 }
 
@@ -535,13 +597,16 @@ __global__ void ekf_strict_kernel(const double* ts, const double* pos, const dou
 }
 
 size_t fuse_smem_bytes(int cap) {
-    return (size_t)(cap + 2) * 56 + (SCRATCH_DOUBLES + 48) * 8 + 16 * 4 + 16 + (size_t)((cap + 2 + 15) & ~15);
+    const size_t cap2 = (size_t)((cap + 3) & ~1);
+    return cap2 * 56 + (SCRATCH_DOUBLES + 48) * 8 + 16 * 4 + 16 + ((cap2 + 15) & ~(size_t)15);
 }
 
 template <int THREADS>
 static cudaError_t launch_fuse_t(const FuseArgs& a, int num_sms, cudaStream_t stream) {
     size_t smem = fuse_smem_bytes(a.cap);
     cudaError_t e = cudaFuncSetAttribute(fuse_traj_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fuse_traj_kernel<THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fuse_traj_kernel<THREADS>, THREADS, smem);

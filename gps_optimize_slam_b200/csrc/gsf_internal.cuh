@@ -15,6 +15,7 @@ struct FuseArgs {
     int* status;
     int B; int cap;
     int use_tma;
+    long long* phase_clock;   // debug: per-phase clock64() of block 0 (NULL = off)
 };
 size_t fuse_smem_bytes(int cap);
 cudaError_t launch_fuse(const FuseArgs& a, int threads, int num_sms, cudaStream_t stream);

@@ -164,13 +164,16 @@ def test_umeyama_and_apply_kernels(gsf):
     off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
     R, t, s, st = gsf.umeyama_batched(dev(src), dev(dst), dev(off, torch.int64), max(lens))
     quat = np.concatenate([tr["quat"] for tr in trajs])
-    ap, aq, ast = gsf.sim3_apply_batched(dev(src), dev(quat), dev(off, torch.int64), max(lens), R, t, s)
+    # the apply kernel is checked with the oracle's own transforms (same R on both sides)
+    fits = [fo.umeyama(src[off[b]:off[b + 1]], dst[off[b]:off[b + 1]]) for b in range(len(trajs))]
+    ap, aq, ast = gsf.sim3_apply_batched(dev(src), dev(quat), dev(off, torch.int64), max(lens), dev(np.stack([f[0] for f in fits])),
+                                         dev(np.stack([f[1] for f in fits])), dev(np.array([f[2] for f in fits])))
     R, t, s, ap, aq = [x.cpu().numpy() for x in (R, t, s, ap, aq)]
     for b in range(len(trajs)):
         sl = slice(off[b], off[b + 1])
-        Ro, to, so = fo.umeyama(src[sl], dst[sl])
+        Ro, to, so = fits[b]
         np.testing.assert_allclose(R[b], Ro, atol=ROT_ATOL); np.testing.assert_allclose(t[b], to, rtol=1e-11, atol=POS_ATOL)
-        assert abs(s[b] - so) < 1e-11
+        assert abs(s[b] - so) < 1e-11 * max(1.0, abs(so))
         po, qo = fo.sim3_apply(src[sl], quat[sl], Ro, to, so)
         np.testing.assert_allclose(ap[sl], po, rtol=0, atol=POS_ATOL); np.testing.assert_allclose(aq[sl], qo, rtol=0, atol=ROT_ATOL)
     # large single trajectory spanning several reduction tiles + masked points

@@ -1,0 +1,20 @@
+"""Debug: per-phase cycle counts of one trajectory inside fuse_traj_kernel (block 0)."""
+import ctypes, sys, torch
+sys.path.insert(0, ".")
+from gps_optimize_slam_b200 import _lib, fusion
+lib = _lib.load()
+B, n = int(sys.argv[1]), int(sys.argv[2])
+ts, pos, quat, z = fusion.synth_generate(B, n, 0.1, 10.0, seed=1)
+off = fusion.equal_offsets(B, n); prm = fusion.params_tensor()
+buf = torch.zeros(16, dtype=torch.int64, device="cuda")
+lib.gsf_debug_phase_clock.argtypes = [ctypes.c_void_p]; lib.gsf_debug_phase_clock.restype = None
+lib.gsf_debug_phase_clock(ctypes.c_void_p(buf.data_ptr()))
+for _ in range(3):
+    fusion.fuse_batched(ts, pos, quat, z, off, n, prm)
+torch.cuda.synchronize()
+c = buf.cpu().tolist()
+names = ["load", "flags", "selection", "sums", "svd+bcast", "residual", "moebius+scan", "gains+scan", "final", "rts", "store-issue", "quat", "tail"]
+print("n", n, "total cycles", c[12] - c[0])
+for k, nm in enumerate(names[:12]):
+    print(f"  {nm:14s} {c[k+1]-c[k]:8d}")
+lib.gsf_debug_phase_clock(None)
