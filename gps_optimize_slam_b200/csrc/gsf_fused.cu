@@ -10,17 +10,23 @@
 //
 // Formulation (checked on the CPU by oracle/kernel_model.py against the step-by-step oracle):
 //   * ts / positions / measurements of one trajectory are staged with three TMA bulk copies
-//     (cp.async.bulk + mbarrier); quaternions are streamed (read once, written once).
-//   * each thread owns an odd-length contiguous chunk of poses (odd => conflict-free 8-byte
+//     (cp.async.bulk + mbarrier); the next trajectory's copies are issued as soon as the
+//     fused positions of the current one have left shared memory, and overlap the streaming
+//     quaternion pass; the trajectory after that is prefetched into L2.
+//   * each thread owns a contiguous chunk of LCH poses (LCH odd => conflict-free 8-byte
 //     shared-memory accesses across a warp);
-//   * Umeyama sums: fixed-order chunk sums, xor-shuffle tree, warp-order combine => the
-//     result is bit-reproducible run to run; 3x3 SVD by one-sided Jacobi in registers;
-//   * covariance recursion  p -> R(p+q)/(p+q+R)  = Moebius maps composed as rescaled 2x2
-//     matrices (block scan), then the exact per-step Joseph-form recursion inside a chunk;
-//   * state recursion  x -> (1-k)(x+u) + k z  = affine maps (block scan);
+//   * pass 1  validity flags + pivot-shifted Umeyama sums in one sweep (fast path: every pose
+//     has GNSS, no time gap, inside the Sim3 window; otherwise the general selection path);
+//     fixed-order chunk sums, xor-shuffle tree, warp-order combine => bit-reproducible;
+//   * pass 2  covariance recursion p -> R(p+q)/(p+q+R) as Moebius maps, composed as rescaled
+//     2x2 matrices (warp shuffle scan + warp-order combine), while warp 0 runs the 3x3
+//     one-sided-Jacobi SVD;
+//   * pass 3  exact per-step Joseph-form gains inside a chunk + affine state maps
+//     x -> (1-k)(x+u) + k z (scan), residual check against the Sim3 fit;
+//   * pass 4  state recursion, closed-form RTS over recovered outages
+//     x_s[k] = x_f[k] + P_f[k]/P_pred[i] * delta_i;
 //   * odometry is telescoped: M(q_state[i-1]) M(q_hat[i-1])^T == M(C), C = q_state0 (x)
-//     conj(q_hat0), so u_i = M(C)(p_i - p_{i-1}) and q_state[i] = C (x) q_hat[i];
-//   * RTS over an outage is the closed form x_s[k] = x_f[k] + P_f[k]/P_pred[i] * delta_i.
+//     conj(q_hat0), so u_i = M(C)(p_i - p_{i-1}) and q_state[i] = C (x) q_hat[i].
 #include "gsf_common.cuh"
 #include "gsf_ekf_strict.cuh"
 #include "gsf_ptx.cuh"
@@ -28,17 +34,70 @@
 
 namespace gsf {
 
-#define GSF_STAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && tid == 0 && b == (int)gridDim.x * 2) A.phase_clock[k] = clock64(); } while (0)
+#define GSF_STAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && tid == 0 && it == 2) A.phase_clock[k] = clock64(); } while (0)
 
 constexpr int FLAG_VALID = 1;
 constexpr int FLAG_SELECTED = 2;
 constexpr int FLAG_RECOVERY = 4;
 constexpr int FLAG_NO_RTS = 8;
 
-template <int ND> struct Pack { double v[ND]; };
+// ----------------------------------------------------------------------------- scan operators
+// 2x2 Moebius matrices for the three position axes, row-major [a b; c d] per axis.  Entries
+// are non-negative (no cancellation); rescaled by a power of two so products never under- or
+// overflow however long the trajectory is.
+struct Moeb3 { double m[12]; };
+struct Aff3 { double a[3], b[3]; };                     // x -> a x + b per axis
 
-// Exclusive block scan of a small struct of doubles.  op(earlier, later) must be associative.
-// Deterministic: fixed shuffle pattern inside a warp, warp totals combined in warp order.
+__device__ __forceinline__ void moeb_rescale(double* m) {
+    const double big = fmax(fmax(m[0], m[1]), fmax(m[2], m[3]));
+    const int e = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
+    const double sc = __hiloint2double((1023 - e) << 20, 0);       // 2^-e, exact
+    m[0] *= sc; m[1] *= sc; m[2] *= sc; m[3] *= sc;
+}
+__device__ __forceinline__ void moeb_identity(Moeb3& x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { x.m[4 * a] = 1.0; x.m[4 * a + 1] = 0.0; x.m[4 * a + 2] = 0.0; x.m[4 * a + 3] = 1.0; }
+}
+// r = later o earlier
+__device__ __forceinline__ Moeb3 moeb_compose(const Moeb3& e, const Moeb3& l) {
+    Moeb3 r;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double* E = e.m + 4 * a; const double* L = l.m + 4 * a; double* R = r.m + 4 * a;
+        R[0] = L[0] * E[0] + L[1] * E[2]; R[1] = L[0] * E[1] + L[1] * E[3];
+        R[2] = L[2] * E[0] + L[3] * E[2]; R[3] = L[2] * E[1] + L[3] * E[3];
+        moeb_rescale(R);
+    }
+    return r;
+}
+__device__ __forceinline__ Aff3 aff_compose(const Aff3& e, const Aff3& l) {
+    Aff3 r;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { r.a[a] = l.a[a] * e.a[a]; r.b[a] = l.a[a] * e.b[a] + l.b[a]; }
+    return r;
+}
+// Inclusive warp scans (fixed shuffle pattern => deterministic).
+__device__ __forceinline__ void moeb_warp_scan(Moeb3& x, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Moeb3 y;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) y.m[k] = __shfl_up_sync(GSF_FULL_MASK, x.m[k], o);
+        if (lane >= o) x = moeb_compose(y, x);
+    }
+}
+__device__ __forceinline__ void aff_warp_scan(Aff3& x, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Aff3 y;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { y.a[k] = __shfl_up_sync(GSF_FULL_MASK, x.a[k], o); y.b[k] = __shfl_up_sync(GSF_FULL_MASK, x.b[k], o); }
+        if (lane >= o) x = aff_compose(y, x);
+    }
+}
+
+template <int ND> struct Pack { double v[ND]; };
+// Exclusive block scan used by the (rare) general selection path.
 template <int ND, class Op>
 __device__ inline Pack<ND> block_exclusive_scan(Pack<ND> x, Op op, const Pack<ND>& ident, double* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -54,46 +113,29 @@ __device__ inline Pack<ND> block_exclusive_scan(Pack<ND> x, Op op, const Pack<ND
     for (int k = 0; k < ND; ++k) excl.v[k] = __shfl_up_sync(GSF_FULL_MASK, x.v[k], 1);
     if (lane == 0) excl = ident;
     if (nwarp > 1) {
-        // second level: warp 0 scans the warp totals (<= 8 of them) with shuffles
         __syncthreads();
         if (lane == 31) {
 #pragma unroll
             for (int k = 0; k < ND; ++k) scratch[warp * ND + k] = x.v[k];
         }
         __syncthreads();
-        if (warp == 0) {
-            Pack<ND> tot = ident;
-            if (lane < nwarp) {
+        Pack<ND> pre = ident;
+        for (int w = 0; w < warp; ++w) {
+            Pack<ND> tot;
 #pragma unroll
-                for (int k = 0; k < ND; ++k) tot.v[k] = scratch[lane * ND + k];
-            }
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                Pack<ND> y;
-#pragma unroll
-                for (int k = 0; k < ND; ++k) y.v[k] = __shfl_up_sync(GSF_FULL_MASK, tot.v[k], o);
-                if (lane >= o) tot = op(y, tot);
-            }
-            Pack<ND> pre;                                   // exclusive prefix of warp `lane`
-#pragma unroll
-            for (int k = 0; k < ND; ++k) pre.v[k] = __shfl_up_sync(GSF_FULL_MASK, tot.v[k], 1);
-            if (lane == 0) pre = ident;
-            if (lane < nwarp) {
-#pragma unroll
-                for (int k = 0; k < ND; ++k) scratch[(8 + lane) * ND + k] = pre.v[k];
-            }
+            for (int k = 0; k < ND; ++k) tot.v[k] = scratch[w * ND + k];
+            pre = op(pre, tot);
         }
+        excl = op(pre, excl);
         __syncthreads();
-        if (warp > 0) {
-            Pack<ND> pre;
-#pragma unroll
-            for (int k = 0; k < ND; ++k) pre.v[k] = scratch[(8 + warp) * ND + k];
-            excl = op(pre, excl);
-        }
     }
     return excl;
 }
-
+struct RankOp {     // v = [count, last valid timestamp (NaN = none)]
+    __device__ Pack<2> operator()(const Pack<2>& e, const Pack<2>& l) const {
+        Pack<2> r; r.v[0] = e.v[0] + l.v[0]; r.v[1] = isnan(l.v[1]) ? e.v[1] : l.v[1]; return r;
+    }
+};
 __device__ __forceinline__ int block_min_int(int v, int* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
 #pragma unroll
@@ -104,43 +146,9 @@ __device__ __forceinline__ int block_min_int(int v, int* scratch) {
     __syncthreads();
     int r = scratch[0];
     for (int w = 1; w < nwarp; ++w) r = min(r, scratch[w]);
+    __syncthreads();
     return r;
 }
-
-// 2x2 Moebius matrices for the three position axes, row-major [a b; c d] per axis.
-// Entries are non-negative, so products have no cancellation; rescale by a power of two.
-__device__ __forceinline__ void moeb_rescale(double* m) {
-    double big = fmax(fmax(m[0], m[1]), fmax(m[2], m[3]));
-    int e = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
-    double sc = __hiloint2double((1023 - e) << 20, 0);          // 2^-e (exact)
-    m[0] *= sc; m[1] *= sc; m[2] *= sc; m[3] *= sc;
-}
-struct MoebOp {
-    __device__ Pack<12> operator()(const Pack<12>& e, const Pack<12>& l) const {
-        Pack<12> r;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const double* E = e.v + 4 * a; const double* L = l.v + 4 * a; double* R = r.v + 4 * a;
-            R[0] = L[0] * E[0] + L[1] * E[2]; R[1] = L[0] * E[1] + L[1] * E[3];
-            R[2] = L[2] * E[0] + L[3] * E[2]; R[3] = L[2] * E[1] + L[3] * E[3];
-            moeb_rescale(R);
-        }
-        return r;
-    }
-};
-struct AffOp {      // v = [a0 a1 a2 b0 b1 b2]; later o earlier
-    __device__ Pack<6> operator()(const Pack<6>& e, const Pack<6>& l) const {
-        Pack<6> r;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { r.v[a] = l.v[a] * e.v[a]; r.v[3 + a] = l.v[a] * e.v[3 + a] + l.v[3 + a]; }
-        return r;
-    }
-};
-struct RankOp {     // v = [count, last valid timestamp (NaN = none)]
-    __device__ Pack<2> operator()(const Pack<2>& e, const Pack<2>& l) const {
-        Pack<2> r; r.v[0] = e.v[0] + l.v[0]; r.v[1] = isnan(l.v[1]) ? e.v[1] : l.v[1]; return r;
-    }
-};
 
 // Rare / once-per-trajectory code kept out of line so that its register needs do not spill
 // the per-pose loops.
@@ -152,61 +160,87 @@ __device__ __noinline__ bool sharp_turn_ool(const double* ts, const double* quat
     return sharp_turn_in_range(ts, quat, s, e, thresh);
 }
 
+// ----------------------------------------------------------------------------- shared-memory map
+constexpr int SM_SUMS = 0;          // 8 warps x 18 partial sums          (144)
+constexpr int SM_MOEB = 144;        // 8 warps x 12 Moebius warp totals   (96)
+constexpr int SM_AFF = 240;         // 8 warps x 6 affine warp totals     (48)
+constexpr int SM_BC = 288;          // M(C) 0-8, C 9-12, x0 13-15, t 16-18, s 19, R 20-28 (32)
+constexpr int SM_PRM = 320;         // FuseParams as 23 doubles           (24)
+constexpr int SM_GEN = 344;         // general path: n, mu_s, mu_d, H, ss, t_first (24); its scans reuse SM_SUMS
+constexpr int SM_DOUBLES = 400;
+// ints: 0-7 block_min scratch, 8 status bits, 9 has-recovery, 10 residual violators,
+//       11 general-path flag, 12 selection count, 13 valid count
 
-constexpr int SCRATCH_DOUBLES = 200;     // block scan: 2 x 8 warps x 12 doubles
+// one thread: TMA bulk copies of trajectory b (even element count from an even start) and L2
+// prefetch of the trajectory this block handles after it.
+__device__ __forceinline__ void issue_trajectory_load(const FuseArgs& A, int b, double* ts_s, double* pos_s, double* z_s, uint64_t* mbar) {
+    const long long e0 = A.offsets[b];
+    const int n = (int)(A.offsets[b + 1] - e0);
+    if (n <= 0 || n > A.cap) return;
+    const int lead = (int)(e0 & 1);
+    const int even = (n + lead) & ~1;
+    if (even > 0) {
+        mbar_expect_tx(mbar, (uint32_t)even * 56u);
+        bulk_g2s(ts_s, A.ts + (e0 - lead), (uint32_t)even * 8u, mbar);
+        bulk_g2s(pos_s, A.pos + 3 * (e0 - lead), (uint32_t)even * 24u, mbar);
+        bulk_g2s(z_s, A.z + 3 * (e0 - lead), (uint32_t)even * 24u, mbar);
+    }
+    const int nb = b + (int)gridDim.x;
+    if (nb < A.B) {
+        const long long f0 = A.offsets[nb] & ~1ll;
+        const long long fn = (A.offsets[nb + 1] - f0) & ~1ll;
+        if (fn > 0 && fn <= A.cap) {
+            bulk_prefetch_l2(A.ts + f0, (uint32_t)fn * 8u);
+            bulk_prefetch_l2(A.pos + 3 * f0, (uint32_t)fn * 24u);
+            bulk_prefetch_l2(A.z + 3 * f0, (uint32_t)fn * 24u);
+            bulk_prefetch_l2(A.quat + 4 * f0, (uint32_t)fn * 32u);
+        }
+    }
+}
 
-// Resident blocks per SM the register budget is sized for: 16 warps for the small blocks,
-// 3 x 128 threads (170 registers) for ~1000-pose trajectories, 1 x 256 for longer ones.
-constexpr int fuse_min_blocks(int threads) { return threads <= 64 ? 512 / threads : (threads == 128 ? 3 : 1); }
+// Resident blocks per SM the register budget is sized for.
+constexpr int fuse_min_blocks(int threads) { return threads <= 32 ? 14 : (threads == 64 ? 7 : (threads == 128 ? 3 : 1)); }
 
-template <int THREADS>
+template <int THREADS, int LCH>
 __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_kernel(const FuseArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NW = THREADS / 32;
     const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
     double* ts_s = reinterpret_cast<double*>(smem_raw);
     double* pos_s = ts_s + cap2;
     double* z_s = pos_s + 3 * (size_t)cap2;
-    double* scratch = z_s + 3 * (size_t)cap2;
-    double* bc = scratch + SCRATCH_DOUBLES;                 // broadcast area (48 doubles)
-    int* iscr = reinterpret_cast<int*>(bc + 48);            // 16 ints
+    double* sd = z_s + 3 * (size_t)cap2;                    // SM_DOUBLES scratch doubles
+    int* iscr = reinterpret_cast<int*>(sd + SM_DOUBLES);    // 16 ints
     uint64_t* mbar = reinterpret_cast<uint64_t*>(iscr + 16);
-    unsigned char* flag_s = reinterpret_cast<unsigned char*>(mbar + 2);
+    unsigned char* flg = reinterpret_cast<unsigned char*>(mbar + 2);
+    double* bc = sd + SM_BC;
+    const double* prm_s = sd + SM_PRM;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t parity = 0;
     if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     __syncthreads();
+    if (A.use_tma && tid == 0 && (int)blockIdx.x < A.B) issue_trajectory_load(A, blockIdx.x, ts_s, pos_s, z_s, mbar);
 
-    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+    int it = 0;
+    for (int b = blockIdx.x; b < A.B; b += gridDim.x, ++it) {
         const long long e0 = A.offsets[b];
         const int n = (int)(A.offsets[b + 1] - e0);
-        const FuseParams& prm = A.params[A.params_per_traj ? b : 0];
-        if (n <= 0) { if (tid == 0) A.status[b] = ST_EMPTY; continue; }
-        if (n > A.cap) { if (tid == 0) A.status[b] = ST_TOO_LONG; continue; }
-
+        if (n <= 0 || n > A.cap) {
+            if (tid == 0) {
+                A.status[b] = n <= 0 ? ST_EMPTY : ST_TOO_LONG;
+                if (A.use_tma && b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar);
+            }
+            continue;
+        }
         GSF_STAMP(0);
         // ------------------------------------------------------------------ stage inputs
         const int lead = A.use_tma ? (int)(e0 & 1) : 0;
         double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
-        unsigned char* flg = flag_s;
+        if (tid < 23) sd[SM_PRM + tid] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[tid];
+        if (tid == 32 % THREADS) { iscr[9] = 0; iscr[10] = 0; iscr[11] = 0; }
         if (A.use_tma) {
             const int cnt = n + lead, even = cnt & ~1;
-            if (tid == 32 % THREADS && b + (int)gridDim.x < A.B) {        // warm L2 for this block's next trajectory
-                const long long f0 = A.offsets[b + gridDim.x] & ~1ll;
-                const long long fn = (A.offsets[b + gridDim.x + 1] - f0) & ~1ll;
-                if (fn > 0) {
-                    bulk_prefetch_l2(A.ts + f0, (uint32_t)fn * 8u);
-                    bulk_prefetch_l2(A.pos + 3 * f0, (uint32_t)fn * 24u);
-                    bulk_prefetch_l2(A.z + 3 * f0, (uint32_t)fn * 24u);
-                    bulk_prefetch_l2(A.quat + 4 * f0, (uint32_t)fn * 32u);
-                }
-            }
-            if (tid == 0 && even > 0) {
-                mbar_expect_tx(mbar, (uint32_t)even * 56u);
-                bulk_g2s(ts_s, A.ts + (e0 - lead), (uint32_t)even * 8u, mbar);
-                bulk_g2s(pos_s, A.pos + 3 * (e0 - lead), (uint32_t)even * 24u, mbar);
-                bulk_g2s(z_s, A.z + 3 * (e0 - lead), (uint32_t)even * 24u, mbar);
-            }
             if ((cnt & 1) && tid < 7) {                       // odd tail element: plain copy
                 const long long g = e0 - lead + even;
                 if (tid == 0) ts_s[even] = A.ts[g];
@@ -214,41 +248,81 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 else z_s[3 * even + (tid - 4)] = A.z[3 * g + (tid - 4)];
             }
             if (even > 0) { mbar_wait(mbar, parity); parity ^= 1; }
-            __syncthreads();
         } else {
             for (int i = tid; i < n; i += THREADS) tsS[i] = A.ts[e0 + i];
             for (int i = tid; i < 3 * n; i += THREADS) { posS[i] = A.pos[3 * e0 + i]; zS[i] = A.z[3 * e0 + i]; }
-            __syncthreads();
         }
-
+        __syncthreads();
         GSF_STAMP(1);
-        // chunk ownership: odd length => conflict-free strided shared-memory access
-        int L = (n + THREADS - 1) / THREADS; L |= 1;
-        const int c0 = min(tid * L, n), c1 = min(c0 + L, n);
 
-        // ------------------------------------------------------------------ validity flags
-        int cntv = 0; double lastT = nan("");
-        for (int i = c0; i < c1; ++i) {
-            bool v = !row_has_nan(zS[3 * i], zS[3 * i + 1], zS[3 * i + 2]);
-            flg[i] = v ? FLAG_VALID : 0;
-            if (v) { ++cntv; lastT = tsS[i]; }
-        }
-        int st = ST_OK;
+        const FuseParams& prm = *reinterpret_cast<const FuseParams*>(prm_s);
         const bool ekf_only = A.init_pos != nullptr;
-        if (!ekf_only) {
-            // -------------------------------------------------------------- Sim3 point selection (:972-998)
+        const int c0 = min(tid * LCH, n), c1 = min(c0 + LCH, n);
+        const int s0 = max(c0, 1);                          // steps owned: i in [s0, c1)
+
+        // ------------------------------------------------------------------ pass 1: flags + pivot-shifted Umeyama sums
+        double pprev0 = 0.0, pprev1 = 0.0, pprev2 = 0.0;    // position of pose s0-1 (read before any in-place write)
+        if (c0 < n) { const int ip = max(c0 - 1, 0); pprev0 = posS[3 * ip]; pprev1 = posS[3 * ip + 1]; pprev2 = posS[3 * ip + 2]; }
+        {
+            double v[17];
+#pragma unroll
+            for (int k = 0; k < 17; ++k) v[k] = 0.0;
+            const double ps0 = posS[0], ps1 = posS[1], ps2 = posS[2];
+            const double pz0 = zS[0], pz1 = zS[1], pz2 = zS[2];
+            const double t_first = tsS[0], t_lim = t_first + prm.max_duration, gap = prm.gap_threshold;
+            int viol = row_has_nan(pz0, pz1, pz2) ? 1 : 0;
+            double tp = (c0 > 0 && c0 < n) ? tsS[c0 - 1] : t_first;
+#pragma unroll
+            for (int j = 0; j < LCH; ++j) {
+                const int i = c0 + j;
+                if (i < c1) {
+                    const double z0 = zS[3 * i], z1 = zS[3 * i + 1], z2 = zS[3 * i + 2];
+                    const double t = tsS[i];
+                    const bool valid = !row_has_nan(z0, z1, z2);
+                    flg[i] = valid ? FLAG_VALID : 0;
+                    if (!valid || t - tp > gap || t > t_lim) viol = 1;
+                    tp = t;
+                    if (valid && !ekf_only) {
+                        const double a0 = posS[3 * i] - ps0, a1 = posS[3 * i + 1] - ps1, a2 = posS[3 * i + 2] - ps2;
+                        const double b0 = z0 - pz0, b1 = z1 - pz1, b2 = z2 - pz2;
+                        v[0] += 1.0; v[1] += a0; v[2] += a1; v[3] += a2; v[4] += b0; v[5] += b1; v[6] += b2;
+                        v[7] += a0 * b0; v[8] += a0 * b1; v[9] += a0 * b2;
+                        v[10] += a1 * b0; v[11] += a1 * b1; v[12] += a1 * b2;
+                        v[13] += a2 * b0; v[14] += a2 * b1; v[15] += a2 * b2;
+                        v[16] += a0 * a0 + a1 * a1 + a2 * a2;
+                    }
+                }
+            }
+            if (!ekf_only) {
+#pragma unroll
+                for (int k = 0; k < 17; ++k) v[k] = warp_sum(v[k]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 17; ++k) sd[SM_SUMS + warp * 18 + k] = v[k];
+                }
+                if (viol) iscr[11] = 1;
+            }
+        }
+        __syncthreads();
+        GSF_STAMP(2);
+        int st = ST_OK;
+
+        // ------------------------------------------------------------------ general Sim3 point selection (:972-998), rare
+        if (!ekf_only && iscr[11]) {
+            int cntv = 0; double lastT = nan("");
+            for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_VALID) { ++cntv; lastT = tsS[i]; }
             Pack<2> mine; mine.v[0] = (double)cntv; mine.v[1] = lastT;
             Pack<2> id2; id2.v[0] = 0.0; id2.v[1] = nan("");
-            Pack<2> pre = block_exclusive_scan<2>(mine, RankOp(), id2, scratch);
+            Pack<2> pre = block_exclusive_scan<2>(mine, RankOp(), id2, sd + SM_SUMS);
             double tot[1] = {(double)cntv};
-            block_sum<1>(tot, scratch);
+            block_sum<1>(tot, sd + SM_SUMS);
             const int nvalid = (int)tot[0];
             const int rank0 = (int)pre.v[0];
             int kmin = 0x7fffffff;
             {
                 int r = rank0; double pt = pre.v[1];
                 for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_VALID) {
-                    if (r == 0) bc[40] = tsS[i];                        // timestamp of the first valid point
+                    if (r == 0) sd[SM_GEN + 23] = tsS[i];               // timestamp of the first valid point
                     if (r >= 1 && tsS[i] - pt > prm.gap_threshold) kmin = min(kmin, r - 1);
                     pt = tsS[i]; ++r;
                 }
@@ -257,23 +331,20 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             __syncthreads();
             const int first_cnt = (kmin == 0x7fffffff) ? nvalid : kmin;
             int mode;                                   // 0 all valid, 1 first run, 2 first run within max_duration
-            const double tlim = bc[40] + prm.max_duration;
-            if (nvalid < prm.min_samples) st |= ST_TOO_FEW_POINTS;
+            const double tlim = sd[SM_GEN + 23] + prm.max_duration;
             if (first_cnt < prm.min_samples) mode = 0;
             else {
                 double timed[1] = {0.0};
                 int r = rank0;
                 for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_VALID) { if (r < first_cnt && tsS[i] <= tlim) timed[0] += 1.0; ++r; }
-                block_sum<1>(timed, scratch);
+                block_sum<1>(timed, sd + SM_SUMS);
                 mode = ((int)timed[0] < prm.min_samples) ? 1 : 2;
             }
-            GSF_STAMP(2);
-            // -------------------------------------------------------------- Umeyama sums (:436-443)
             double s7[7] = {0, 0, 0, 0, 0, 0, 0};
             {
                 int r = rank0;
                 for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_VALID) {
-                    bool sel = mode == 0 || (r < first_cnt && (mode == 1 || tsS[i] <= tlim));
+                    const bool sel = mode == 0 || (r < first_cnt && (mode == 1 || tsS[i] <= tlim));
                     if (sel) {
                         flg[i] |= FLAG_SELECTED;
                         s7[0] += posS[3 * i]; s7[1] += posS[3 * i + 1]; s7[2] += posS[3 * i + 2];
@@ -283,81 +354,117 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     ++r;
                 }
             }
-            block_sum<7>(s7, scratch);
-            const int nsel = (int)s7[6];
-            if (nsel < 3 || nsel < prm.min_samples) st |= ST_TOO_FEW_POINTS;
+            block_sum<7>(s7, sd + SM_SUMS);
             const double inv_n = 1.0 / fmax(s7[6], 1.0);
-            const double mus[3] = {s7[0] * inv_n, s7[1] * inv_n, s7[2] * inv_n};
-            const double mud[3] = {s7[3] * inv_n, s7[4] * inv_n, s7[5] * inv_n};
+            const double m0 = s7[0] * inv_n, m1 = s7[1] * inv_n, m2 = s7[2] * inv_n;
+            const double d0 = s7[3] * inv_n, d1 = s7[4] * inv_n, d2 = s7[5] * inv_n;
             double h[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_SELECTED) {
-                double a0 = posS[3 * i] - mus[0], a1 = posS[3 * i + 1] - mus[1], a2 = posS[3 * i + 2] - mus[2];
-                double b0 = zS[3 * i] - mud[0], b1 = zS[3 * i + 1] - mud[1], b2 = zS[3 * i + 2] - mud[2];
+                const double a0 = posS[3 * i] - m0, a1 = posS[3 * i + 1] - m1, a2 = posS[3 * i + 2] - m2;
+                const double b0 = zS[3 * i] - d0, b1 = zS[3 * i + 1] - d1, b2 = zS[3 * i + 2] - d2;
                 h[0] += a0 * b0; h[1] += a0 * b1; h[2] += a0 * b2;
                 h[3] += a1 * b0; h[4] += a1 * b1; h[5] += a1 * b2;
                 h[6] += a2 * b0; h[7] += a2 * b1; h[8] += a2 * b2;
                 h[9] += a0 * a0 + a1 * a1 + a2 * a2;
             }
-            block_sum<10>(h, scratch);
+            block_sum<10>(h, sd + SM_SUMS);
             __syncthreads();
-            GSF_STAMP(3);
-            if (warp == 0) {
-                // copies whose address escapes into the out-of-line SVD: keeps h[]/mus[]/mud[] in registers above
-                double R[9], t[3], s = 1.0, hh[9], ms_[3] = {mus[0], mus[1], mus[2]}, md_[3] = {mud[0], mud[1], mud[2]};
+            if (tid == 0) {
+                double* g = sd + SM_GEN;
+                g[0] = s7[6]; g[1] = m0; g[2] = m1; g[3] = m2; g[4] = d0; g[5] = d1; g[6] = d2;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) hh[k] = h[k];
-                int ust = (st & ST_TOO_FEW_POINTS) ? 0 : umeyama_finish_ool(nsel, ms_, md_, hh, h[9], R, t, &s);
-                Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
+                for (int k = 0; k < 10; ++k) g[7 + k] = h[k];
+                iscr[13] = nvalid;
+            }
+            __syncthreads();
+        }
+
+        // ------------------------------------------------------------------ pass 2: Moebius chunk maps (all warps) + SVD (warp 0)
+        Moeb3 mex;                                          // exclusive prefix inside the warp
+        {
+            Moeb3 loc;
+            moeb_identity(loc);
+            int since = 0;
+            for (int i = s0; i < c1; ++i) {
+                const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
+                const bool v = flg[i] & FLAG_VALID;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    double* m = loc.m + 4 * a;
+                    const double qa = prm.q[a] * dt, ra = prm.r[a];
+                    const double ta = m[0] + qa * m[2], tb = m[1] + qa * m[3];        // [1 q; 0 1] * m
+                    if (v) { m[2] = ta + ra * m[2]; m[3] = tb + ra * m[3]; m[0] = ra * ta; m[1] = ra * tb; }
+                    else { m[0] = ta; m[1] = tb; }
+                }
+                if (++since == 16) { since = 0; moeb_rescale(loc.m); moeb_rescale(loc.m + 4); moeb_rescale(loc.m + 8); }
+            }
+            moeb_rescale(loc.m); moeb_rescale(loc.m + 4); moeb_rescale(loc.m + 8);
+            moeb_warp_scan(loc, lane);
+            if (lane == 31) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) sd[SM_MOEB + warp * 12 + k] = loc.m[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) mex.m[k] = __shfl_up_sync(GSF_FULL_MASK, loc.m[k], 1);
+            if (lane == 0) moeb_identity(mex);
+        }
+        if (warp == 0) {
+            int ust = 0;
+            if (!ekf_only) {
+                double n_sel, ms_[3], md_[3], hh[9], ss;
+                if (iscr[11]) {                             // general path: centred sums are ready
+                    const double* g = sd + SM_GEN;
+                    n_sel = g[0];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { ms_[k] = g[1 + k]; md_[k] = g[4 + k]; }
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) hh[k] = g[7 + k];
+                    ss = g[16];
+                } else {                                    // fast path: combine warp partials in warp order, un-shift the pivot
+                    double v[17];
+#pragma unroll
+                    for (int k = 0; k < 17; ++k) { v[k] = sd[SM_SUMS + k]; for (int w = 1; w < NW; ++w) v[k] += sd[SM_SUMS + w * 18 + k]; }
+                    n_sel = v[0];
+                    const double inv = 1.0 / fmax(n_sel, 1.0);
+                    const double ma[3] = {v[1] * inv, v[2] * inv, v[3] * inv}, mb[3] = {v[4] * inv, v[5] * inv, v[6] * inv};
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { ms_[k] = posS[k] + ma[k]; md_[k] = zS[k] + mb[k]; }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) hh[3 * r + c] = v[7 + 3 * r + c] - n_sel * ma[r] * mb[c];
+                    ss = v[16] - n_sel * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
+                }
+                const int nsel = (int)n_sel;
+                double R[9], t[3], s = 1.0;
+                if (nsel < 3 || nsel < prm.min_samples) ust |= ST_TOO_FEW_POINTS;
+                else ust |= umeyama_finish_ool(nsel, ms_, md_, hh, ss, R, t, &s);
+                const Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
                 if (qnorm2(q0) == 0.0) ust |= ST_BAD_QUATERNION;
                 if (lane == 0) {
-                    if (!(st & ST_TOO_FEW_POINTS)) {
-                        Quat qR = quat_from_matrix(R);
-                        Quat q0h = qunit(q0);
-                        Quat qs0 = qunit_or_identity(qmul(qR, q0h));
-                        Quat Cq = qmul(qs0, qconj(q0h));
+                    if (!(ust & ST_TOO_FEW_POINTS)) {
+                        const Quat qR = quat_from_matrix(R);
+                        const Quat q0h = qunit(q0);
+                        const Quat qs0 = qunit_or_identity(qmul(qR, q0h));
+                        const Quat Cq = qmul(qs0, qconj(q0h));
                         double M[9]; qmat(Cq, M);
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) { bc[k] = M[k]; bc[16 + k] = R[k]; }
+                        for (int k = 0; k < 9; ++k) { bc[k] = M[k]; bc[20 + k] = R[k]; }
                         bc[9] = Cq.x; bc[10] = Cq.y; bc[11] = Cq.z; bc[12] = Cq.w;
                         double rx, ry, rz;
                         mat_vec(R, posS[0], posS[1], posS[2], rx, ry, rz);
                         bc[13] = s * rx + t[0]; bc[14] = s * ry + t[1]; bc[15] = s * rz + t[2];
-                        bc[25] = t[0]; bc[26] = t[1]; bc[27] = t[2]; bc[28] = s;
+                        bc[16] = t[0]; bc[17] = t[1]; bc[18] = t[2]; bc[19] = s;
                     }
-                    iscr[8] = ust;
+                    iscr[8] = ust; iscr[12] = nsel;
+                    if (!iscr[11]) iscr[13] = nsel;
                 }
-            }
-            __syncthreads();
-            st |= iscr[8];
-            GSF_STAMP(4);
-            // all-points residual check standing in for RANSAC (:409-412): count violators
-            double nout[1] = {0.0};
-            if (!(st & ST_TOO_FEW_POINTS) && prm.residual_thresh > 0.0) {
-                const double s = bc[28], thr2 = prm.residual_thresh * prm.residual_thresh;
-                for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_SELECTED) {
-                    double rx, ry, rz;
-                    mat_vec(bc + 16, posS[3 * i], posS[3 * i + 1], posS[3 * i + 2], rx, ry, rz);
-                    double d0 = s * rx + bc[25] - zS[3 * i], d1 = s * ry + bc[26] - zS[3 * i + 1], d2 = s * rz + bc[27] - zS[3 * i + 2];
-                    if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) nout[0] += 1.0;
-                }
-                block_sum<1>(nout, scratch);
-                if (nout[0] > 0.0) st |= ST_RANSAC_OUTLIERS;
-            }
-            if (tid == 0 && A.sim3_out) {
-                double* o = A.sim3_out + 16 * (size_t)b;
-                const bool ok = !(st & ST_TOO_FEW_POINTS);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) o[k] = ok ? bc[16 + k] : nan("");
-                o[9] = ok ? bc[25] : nan(""); o[10] = ok ? bc[26] : nan(""); o[11] = ok ? bc[27] : nan("");
-                o[12] = ok ? bc[28] : nan(""); o[13] = (double)nsel; o[14] = (double)nvalid; o[15] = nout[0];
-            }
-        } else {
-            if (tid == 0) {
-                Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
-                Quat qi{A.init_quat[4 * b], A.init_quat[4 * b + 1], A.init_quat[4 * b + 2], A.init_quat[4 * b + 3]};
-                int ust = (qnorm2(q0) == 0.0) ? ST_BAD_QUATERNION : 0;
-                Quat qs0 = qunit_or_identity(qi);
-                Quat Cq = qmul(qs0, qconj(qunit(q0)));
+            } else if (lane == 0) {
+                const Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
+                const Quat qi{A.init_quat[4 * b], A.init_quat[4 * b + 1], A.init_quat[4 * b + 2], A.init_quat[4 * b + 3]};
+                ust = (qnorm2(q0) == 0.0) ? ST_BAD_QUATERNION : 0;
+                const Quat qs0 = qunit_or_identity(qi);
+                const Quat Cq = qmul(qs0, qconj(qunit(q0)));
                 double M[9]; qmat(Cq, M);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) bc[k] = M[k];
@@ -365,131 +472,166 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 bc[13] = A.init_pos[3 * b]; bc[14] = A.init_pos[3 * b + 1]; bc[15] = A.init_pos[3 * b + 2];
                 iscr[8] = ust;
             }
-            __syncthreads();
-            st |= iscr[8];
         }
-
+        __syncthreads();
+        GSF_STAMP(3);
+        st |= iscr[8];
         if (st & (ST_TOO_FEW_POINTS | ST_BAD_QUATERNION)) {
             // The reference aborts the run here (ValueError / RuntimeError): outputs are NaN.
             for (int i = tid; i < 3 * n; i += THREADS) A.out_pos[3 * e0 + i] = nan("");
             for (int i = tid; i < 4 * n; i += THREADS) A.out_quat[4 * e0 + i] = nan("");
-            if (tid == 0) A.status[b] = st;
+            if (tid == 0) {
+                A.status[b] = st;
+                if (A.sim3_out) {
+                    double* o = A.sim3_out + 16 * (size_t)b;
+                    for (int k = 0; k < 13; ++k) o[k] = nan("");
+                    o[13] = (double)iscr[12]; o[14] = (double)iscr[13]; o[15] = 0.0;
+                }
+                if (A.use_tma && b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar);
+            }
             __syncthreads();
             continue;
         }
-        if (tid == 0) iscr[9] = 0;                                  // "trajectory has a recovered outage"
 
-        GSF_STAMP(5);
-        // ------------------------------------------------------------------ covariance: Moebius scan
-        const int s0 = max(c0, 1);                                  // steps owned: i in [s0, c1)
-        Pack<12> loc;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { loc.v[4 * a] = 1.0; loc.v[4 * a + 1] = 0.0; loc.v[4 * a + 2] = 0.0; loc.v[4 * a + 3] = 1.0; }
+        // ------------------------------------------------------------------ pass 3: gains, affine maps, residual check
+        Aff3 aex;                                           // exclusive affine prefix inside the warp
         {
-            int since = 0;
+            Moeb3 pre = mex;
+            if (NW > 1 && warp > 0) {
+                Moeb3 acc;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) acc.m[k] = sd[SM_MOEB + k];
+                for (int w = 1; w < warp; ++w) {
+                    Moeb3 nx;
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) nx.m[k] = sd[SM_MOEB + w * 12 + k];
+                    acc = moeb_compose(acc, nx);
+                }
+                pre = moeb_compose(acc, mex);
+            }
+            double P[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double* m = pre.m + 4 * a;
+                P[a] = (m[0] * prm.p0[a] + m[1]) / (m[2] * prm.p0[a] + m[3]);
+            }
+        // (pose 0's own position was consumed in pass 1 as pivot and is re-read from global below)
+            double RC[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) RC[k] = bc[k];
+            const double sc = bc[19], t0 = bc[16], t1 = bc[17], t2 = bc[18];
+            const double thr2 = (ekf_only || !(prm.residual_thresh > 0.0)) ? -1.0 : prm.residual_thresh * prm.residual_thresh;
+            const bool general = iscr[11] != 0;
+            int nviol = 0;
+            Aff3 aff;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { aff.a[a] = 1.0; aff.b[a] = 0.0; }
+            if (c0 == 0 && c1 > 0) {
+                if (thr2 > 0.0 && (flg[0] & FLAG_VALID) && (!general || (flg[0] & FLAG_SELECTED))) {
+                    double rx, ry, rz;
+                    mat_vec(RC, posS[0], posS[1], posS[2], rx, ry, rz);
+                    const double d0 = sc * rx + t0 - zS[0], d1 = sc * ry + t1 - zS[1], d2 = sc * rz + t2 - zS[2];
+                    if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+                }
+            }
             for (int i = s0; i < c1; ++i) {
                 const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
-                const double qq[3] = {prm.q[0] * dt, prm.q[1] * dt, prm.q[2] * dt};
-                const double rr[3] = {prm.r[0], prm.r[1], prm.r[2]};
-                const bool v = flg[i] & FLAG_VALID;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    double* m = loc.v + 4 * a;
-                    const double ta = m[0] + qq[a] * m[2], tb = m[1] + qq[a] * m[3];     // [1 q; 0 1] * m
-                    if (v) { m[2] = ta + rr[a] * m[2]; m[3] = tb + rr[a] * m[3]; m[0] = rr[a] * ta; m[1] = rr[a] * tb; }
-                    else { m[0] = ta; m[1] = tb; }
-                }
-                if (++since == 16) { since = 0; moeb_rescale(loc.v); moeb_rescale(loc.v + 4); moeb_rescale(loc.v + 8); }
-            }
-            moeb_rescale(loc.v); moeb_rescale(loc.v + 4); moeb_rescale(loc.v + 8);
-        }
-        Pack<12> idm;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { idm.v[4 * a] = 1.0; idm.v[4 * a + 1] = 0.0; idm.v[4 * a + 2] = 0.0; idm.v[4 * a + 3] = 1.0; }
-        Pack<12> mpre = block_exclusive_scan<12>(loc, MoebOp(), idm, scratch);
-        double P[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const double* m = mpre.v + 4 * a;
-            P[a] = (m[0] * prm.p0[a] + m[1]) / (m[2] * prm.p0[a] + m[3]);
-        }
-
-        GSF_STAMP(6);
-        // ------------------------------------------------------------------ gains + affine maps
-        double pprev[3] = {0, 0, 0};
-        if (s0 < c1) { pprev[0] = posS[3 * (s0 - 1)]; pprev[1] = posS[3 * (s0 - 1) + 1]; pprev[2] = posS[3 * (s0 - 1) + 2]; }
-        __syncthreads();                                            // boundary reads before in-place writes
-        if (c0 == 0 && c1 > 0) { posS[0] = prm.p0[0]; posS[1] = prm.p0[1]; posS[2] = prm.p0[2]; }   // P_f[0]
-        Pack<6> aff;
-        aff.v[0] = aff.v[1] = aff.v[2] = 1.0; aff.v[3] = aff.v[4] = aff.v[5] = 0.0;
-        double RC[9];                                               // M(C), read where it is used (register pressure)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) RC[k] = bc[k];
-        for (int i = s0; i < c1; ++i) {
-            const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
-            const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
-            double u[3];
-            mat_vec(RC, p0 - pprev[0], p1 - pprev[1], p2 - pprev[2], u[0], u[1], u[2]);
-            pprev[0] = p0; pprev[1] = p1; pprev[2] = p2;
-            const double qq[3] = {prm.q[0] * dt, prm.q[1] * dt, prm.q[2] * dt};
-            const double rr[3] = {prm.r[0], prm.r[1], prm.r[2]};
-            const int f = flg[i];
-            if (f & FLAG_VALID) {
-                double w = 1.0;
-                if (!(flg[i - 1] & FLAG_VALID)) {                   // GNSS just recovered (:879-894)
-                    int s = i - 1;
-                    while (s > 0 && !(flg[s - 1] & FLAG_VALID)) --s;
-                    int nf = f | FLAG_RECOVERY;
-                    if (sharp_turn_ool(A.ts + e0, A.quat + 4 * e0, s, i - 1, prm.yaw_rate_thresh)) {
-                        nf |= FLAG_NO_RTS;
-                        if (prm.sharp_turn_steps > 0) { double wd = 1.0 / (double)prm.sharp_turn_steps; if (wd < 1.0) w = wd; }
+                const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
+                double u[3];
+                mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u[0], u[1], u[2]);
+                pprev0 = p0; pprev1 = p1; pprev2 = p2;
+                const int f = flg[i];
+                if (f & FLAG_VALID) {
+                    const double zz[3] = {zS[3 * i], zS[3 * i + 1], zS[3 * i + 2]};
+                    if (thr2 > 0.0 && (!general || (f & FLAG_SELECTED))) {
+                        double rx, ry, rz;
+                        mat_vec(RC, p0, p1, p2, rx, ry, rz);
+                        const double d0 = sc * rx + t0 - zz[0], d1 = sc * ry + t1 - zz[1], d2 = sc * rz + t2 - zz[2];
+                        if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
                     }
-                    flg[i] = (unsigned char)nf;
-                    iscr[9] = 1;
-                }
+                    double w = 1.0;
+                    if (!(flg[i - 1] & FLAG_VALID)) {                   // GNSS just recovered (:879-894)
+                        int s = i - 1;
+                        while (s > 0 && !(flg[s - 1] & FLAG_VALID)) --s;
+                        int nf = f | FLAG_RECOVERY;
+                        if (sharp_turn_ool(A.ts + e0, A.quat + 4 * e0, s, i - 1, prm.yaw_rate_thresh)) {
+                            nf |= FLAG_NO_RTS;
+                            if (prm.sharp_turn_steps > 0) { const double wd = 1.0 / (double)prm.sharp_turn_steps; if (wd < 1.0) w = wd; }
+                        }
+                        flg[i] = (unsigned char)nf;
+                        iscr[9] = 1;
+                    }
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const double pp = P[a] + qq[a];
-                    const double k = pp * (1.0 / (pp + rr[a]));
-                    const double omk = 1.0 - k;
-                    P[a] = omk * pp * omk + k * rr[a] * k;           // Joseph form (:731)
-                    const double ke = k * w, av = 1.0 - ke;
-                    const double bv = av * u[a] + ke * zS[3 * i + a];
-                    posS[3 * i + a] = av; zS[3 * i + a] = bv;
-                    aff.v[3 + a] = av * aff.v[3 + a] + bv; aff.v[a] *= av;
-                }
-            } else {
+                    for (int a = 0; a < 3; ++a) {
+                        const double ra = prm.r[a];
+                        const double pp = P[a] + prm.q[a] * dt;
+                        const double k = pp * (1.0 / (pp + ra));
+                        const double omk = 1.0 - k;
+                        P[a] = omk * pp * omk + k * ra * k;             // Joseph form (:731)
+                        const double ke = k * w, av = 1.0 - ke;
+                        const double bv = av * u[a] + ke * zz[a];
+                        posS[3 * i + a] = av; zS[3 * i + a] = bv;
+                        aff.b[a] = av * aff.b[a] + bv; aff.a[a] *= av;
+                    }
+                } else {
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    P[a] += qq[a];
-                    posS[3 * i + a] = P[a];                          // P_f[i] kept for the RTS patch
-                    zS[3 * i + a] = u[a];
-                    aff.v[3 + a] += u[a];
+                    for (int a = 0; a < 3; ++a) {
+                        P[a] += prm.q[a] * dt;
+                        posS[3 * i + a] = P[a];                          // P_f[i] kept for the RTS patch
+                        zS[3 * i + a] = u[a];
+                        aff.b[a] += u[a];
+                    }
                 }
             }
-        }
-        Pack<6> ida; ida.v[0] = ida.v[1] = ida.v[2] = 1.0; ida.v[3] = ida.v[4] = ida.v[5] = 0.0;
-        Pack<6> apre = block_exclusive_scan<6>(aff, AffOp(), ida, scratch);
-
-        GSF_STAMP(7);
-        // ------------------------------------------------------------------ state recursion
-        double x[3] = {apre.v[0] * bc[13] + apre.v[3], apre.v[1] * bc[14] + apre.v[4], apre.v[2] * bc[15] + apre.v[5]};
-        if (c0 == 0 && c1 > 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
-        for (int i = s0; i < c1; ++i) {
-            if (flg[i] & FLAG_VALID) {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) x[a] = posS[3 * i + a] * x[a] + zS[3 * i + a];
-            } else {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) x[a] += zS[3 * i + a];
+            if (c0 == 0 && c1 > 0) { posS[0] = prm.p0[0]; posS[1] = prm.p0[1]; posS[2] = prm.p0[2]; }   // P_f[0] for the RTS patch
+            if (thr2 > 0.0) {
+                nviol = warp_sum_i(nviol);
+                if (lane == 0 && nviol) atomicAdd(iscr + 10, nviol);
             }
-            zS[3 * i] = x[0]; zS[3 * i + 1] = x[1]; zS[3 * i + 2] = x[2];
+            aff_warp_scan(aff, lane);
+            if (lane == 31) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sd[SM_AFF + warp * 6 + k] = aff.a[k]; sd[SM_AFF + warp * 6 + 3 + k] = aff.b[k]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { aex.a[k] = __shfl_up_sync(GSF_FULL_MASK, aff.a[k], 1); aex.b[k] = __shfl_up_sync(GSF_FULL_MASK, aff.b[k], 1); }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { aex.a[k] = 1.0; aex.b[k] = 0.0; }
+            }
         }
         __syncthreads();
+        GSF_STAMP(4);
 
-        GSF_STAMP(8);
-        // ------------------------------------------------------------------ closed-form RTS over recovered outages
+        // ------------------------------------------------------------------ pass 4: state recursion
+        {
+            Aff3 pre = aex;
+            if (NW > 1 && warp > 0) {
+                Aff3 acc;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { acc.a[k] = sd[SM_AFF + k]; acc.b[k] = sd[SM_AFF + 3 + k]; }
+                for (int w = 1; w < warp; ++w) {
+                    Aff3 nx;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { nx.a[k] = sd[SM_AFF + w * 6 + k]; nx.b[k] = sd[SM_AFF + w * 6 + 3 + k]; }
+                    acc = aff_compose(acc, nx);
+                }
+                pre = aff_compose(acc, aex);
+            }
+            double x0 = pre.a[0] * bc[13] + pre.b[0], x1 = pre.a[1] * bc[14] + pre.b[1], x2 = pre.a[2] * bc[15] + pre.b[2];
+            if (c0 == 0 && c1 > 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
+            for (int i = s0; i < c1; ++i) {
+                if (flg[i] & FLAG_VALID) {
+                    x0 = posS[3 * i] * x0 + zS[3 * i]; x1 = posS[3 * i + 1] * x1 + zS[3 * i + 1]; x2 = posS[3 * i + 2] * x2 + zS[3 * i + 2];
+                } else {
+                    x0 += zS[3 * i]; x1 += zS[3 * i + 1]; x2 += zS[3 * i + 2];
+                }
+                zS[3 * i] = x0; zS[3 * i + 1] = x1; zS[3 * i + 2] = x2;
+            }
+        }
+        // ------------------------------------------------------------------ closed-form RTS over recovered outages (rare)
         if (iscr[9]) {
+            __syncthreads();
             for (int i = s0; i < c1; ++i) {
                 const int f = flg[i];
                 if ((f & FLAG_RECOVERY) && !(f & FLAG_NO_RTS)) {
@@ -500,10 +642,9 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     double u[3];
                     mat_vec(bc, gp[0] - gp[-3], gp[1] - gp[-2], gp[2] - gp[-1], u[0], u[1], u[2]);
                     double ratio_den[3], delta[3];
-                    const double qq[3] = {prm.q[0] * dt, prm.q[1] * dt, prm.q[2] * dt};
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        ratio_den[a] = posS[3 * (i - 1) + a] + qq[a];                  // P_pred[i]
+                        ratio_den[a] = posS[3 * (i - 1) + a] + prm.q[a] * dt;         // P_pred[i]
                         delta[a] = zS[3 * i + a] - (zS[3 * (i - 1) + a] + u[a]);       // x_f[i] - x_pred[i]
                     }
                     for (int k = s; k < i; ++k) {
@@ -512,25 +653,50 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     }
                 }
             }
-            __syncthreads();
         }
+        if (A.use_tma) fence_proxy_async();
+        __syncthreads();
+        GSF_STAMP(5);
 
-        GSF_STAMP(9);
-        // ------------------------------------------------------------------ store fused positions
+        // ------------------------------------------------------------------ store fused positions, start the next load
         double* gout = A.out_pos + 3 * e0;
+        if (iscr[10]) st |= ST_RANSAC_OUTLIERS;
         if (A.use_tma) {
-            fence_proxy_async();
-            __syncthreads();
-            const int m = n - lead, even = m & ~1;
-            if (tid == 0 && even > 0) { bulk_s2g(gout + 3 * lead, zS + 3 * lead, (uint32_t)even * 24u); bulk_commit(); }
-            if (lead && tid < 3) gout[tid] = zS[tid];
-            if ((m & 1) && tid >= 3 && tid < 6) gout[3 * (lead + even) + (tid - 3)] = zS[3 * (lead + even) + (tid - 3)];
+            if (tid == 0) {
+                const int m = n - lead, even = m & ~1;
+                if (even > 0) { bulk_s2g(gout + 3 * lead, zS + 3 * lead, (uint32_t)even * 24u); bulk_commit(); }
+                if (lead) { gout[0] = zS[0]; gout[1] = zS[1]; gout[2] = zS[2]; }
+                if (m & 1) {
+                    const int q = 3 * (lead + even);
+                    gout[q] = zS[q]; gout[q + 1] = zS[q + 1]; gout[q + 2] = zS[q + 2];
+                }
+                A.status[b] = st;
+                if (A.sim3_out && !ekf_only) {
+                    double* o = A.sim3_out + 16 * (size_t)b;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
+                    o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
+                    o[13] = (double)iscr[12]; o[14] = (double)iscr[13]; o[15] = (double)iscr[10];
+                }
+                bulk_wait_read();                                   // shared memory is free again
+                fence_proxy_async();
+                if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar);
+            }
         } else {
             for (int i = tid; i < 3 * n; i += THREADS) gout[i] = zS[i];
+            if (tid == 0) {
+                A.status[b] = st;
+                if (A.sim3_out && !ekf_only) {
+                    double* o = A.sim3_out + 16 * (size_t)b;
+                    for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
+                    o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
+                    o[13] = (double)iscr[12]; o[14] = (double)iscr[13]; o[15] = (double)iscr[10];
+                }
+            }
         }
 
-        GSF_STAMP(10);
         // ------------------------------------------------------------------ quaternions: q_state[i] = C (x) q_hat[i]
+        // (streamed global -> global while the next trajectory's bulk copies are in flight)
         int badq = 0;
         {
             const Quat C{bc[9], bc[10], bc[11], bc[12]};
@@ -547,10 +713,10 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 for (int u = 0; u < 4; ++u) {
                     const int i = i0 + u * THREADS;
                     if (i < n) {
-                        Quat qi{lo[u].x, lo[u].y, hi[u].x, hi[u].y};
+                        const Quat qi{lo[u].x, lo[u].y, hi[u].x, hi[u].y};
                         const double n2 = qnorm2(qi);
                         if (n2 == 0.0) badq = 1;
-                        Quat r = qscale(qmul(C, qi), rsqrt(n2));
+                        const Quat r = qscale(qmul(C, qi), rsqrt(n2));
                         qout[2 * i] = make_double2(r.x, r.y);
                         qout[2 * i + 1] = make_double2(r.z, r.w);
                     }
@@ -558,23 +724,17 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             }
         }
         badq = __syncthreads_or(badq);
-        GSF_STAMP(11);
+        GSF_STAMP(6);
         if (badq) {
             // A zero-norm SLAM quaternion: scipy raises inside transform_trajectory (:466), the
             // reference run aborts.  Flag it and blank the outputs.
-            st |= ST_BAD_QUATERNION;
             if (A.use_tma && tid == 0) bulk_wait_all();
             __syncthreads();
             for (int i = tid; i < 3 * n; i += THREADS) gout[i] = nan("");
             for (int i = tid; i < 4 * n; i += THREADS) A.out_quat[4 * e0 + i] = nan("");
+            if (tid == 0) A.status[b] = st | ST_BAD_QUATERNION;
+            __syncthreads();
         }
-        if (tid == 0) {
-            A.status[b] = st;
-            if (A.use_tma) bulk_wait_read();
-        }
-        if (A.use_tma) fence_proxy_async();
-        __syncthreads();
-        GSF_STAMP(12);
     }
 }
 
@@ -598,34 +758,43 @@ __global__ void ekf_strict_kernel(const double* ts, const double* pos, const dou
 
 size_t fuse_smem_bytes(int cap) {
     const size_t cap2 = (size_t)((cap + 3) & ~1);
-    return cap2 * 56 + (SCRATCH_DOUBLES + 48) * 8 + 16 * 4 + 16 + ((cap2 + 15) & ~(size_t)15);
+    return cap2 * 56 + SM_DOUBLES * 8 + 16 * 4 + 16 + ((cap2 + 15) & ~(size_t)15);
 }
 
-template <int THREADS>
+template <int THREADS, int LCH>
 static cudaError_t launch_fuse_t(const FuseArgs& a, int num_sms, cudaStream_t stream) {
-    size_t smem = fuse_smem_bytes(a.cap);
-    cudaError_t e = cudaFuncSetAttribute(fuse_traj_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = fuse_smem_bytes(a.cap);
+    auto kern = fuse_traj_kernel<THREADS, LCH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fuse_traj_kernel<THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fuse_traj_kernel<THREADS>, THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     long long grid = (long long)num_sms * per_sm;
     if (grid > a.B) grid = a.B;
-    fuse_traj_kernel<THREADS><<<(unsigned)grid, THREADS, smem, stream>>>(a);
+    kern<<<(unsigned)grid, THREADS, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
+// threads x chunk must cover the longest trajectory; chunk lengths are odd.
 cudaError_t launch_fuse(const FuseArgs& a, int threads, int num_sms, cudaStream_t stream) {
-    switch (threads) {
-        case 32: return launch_fuse_t<32>(a, num_sms, stream);
-        case 64: return launch_fuse_t<64>(a, num_sms, stream);
-        case 128: return launch_fuse_t<128>(a, num_sms, stream);
-        case 256: return launch_fuse_t<256>(a, num_sms, stream);
-        default: return cudaErrorInvalidValue;
+    const int need = (a.cap + threads - 1) / threads;
+    if (need <= 9) {
+        switch (threads) {
+            case 32: return launch_fuse_t<32, 9>(a, num_sms, stream);
+            case 64: return launch_fuse_t<64, 9>(a, num_sms, stream);
+            case 128: return launch_fuse_t<128, 9>(a, num_sms, stream);
+            case 256: return launch_fuse_t<256, 9>(a, num_sms, stream);
+        }
+    } else if (need <= 17 && threads == 256) {
+        return launch_fuse_t<256, 17>(a, num_sms, stream);
+    } else if (need <= 33 && threads == 256) {
+        return launch_fuse_t<256, 33>(a, num_sms, stream);
     }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_ekf_strict(const double* ts, const double* pos, const double* quat, const double* z,

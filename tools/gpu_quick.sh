@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick perf + parity loop
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -x > gpurun_out/q_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/q_pytest.log | cut -c1-200
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/q_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/q_pytest.log | cut -c1-200
 for wl in "--trajectories 65536" "--workload config2"; do
 timeout 600 python bench.py --steps 5 --warmup 3 $wl --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "
 import sys,json

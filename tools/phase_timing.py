@@ -13,8 +13,8 @@ for _ in range(3):
     fusion.fuse_batched(ts, pos, quat, z, off, n, prm)
 torch.cuda.synchronize()
 c = buf.cpu().tolist()
-names = ["load", "flags", "selection", "sums", "svd+bcast", "residual", "moebius+scan", "gains+scan", "final", "rts", "store-issue", "quat", "tail"]
-print("n", n, "total cycles", c[12] - c[0])
-for k, nm in enumerate(names[:12]):
-    print(f"  {nm:14s} {c[k+1]-c[k]:8d}")
+names = ["load-wait", "pass1 flags+sums", "general-sel + pass2 moebius + SVD", "pass3 gains", "pass4 final+rts", "store+next load+quat"]
+print("n", n, "total cycles", c[6] - c[0])
+for k, nm in enumerate(names):
+    print(f"  {nm:36s} {c[k+1]-c[k]:8d}")
 lib.gsf_debug_phase_clock(None)
