@@ -36,6 +36,17 @@ namespace gsf {
 
 #define GSF_STAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && tid == 0 && it == 2) A.phase_clock[k] = clock64(); } while (0)
 
+// 1/x for finite positive x: hardware seed (rel. error 2^-23) + two Newton steps -> <= 1 ulp.
+// 5 instructions instead of the ~10 of the IEEE division sequence; parity budget is 1e-9.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 constexpr int FLAG_VALID = 1;
 constexpr int FLAG_SELECTED = 2;
 constexpr int FLAG_RECOVERY = 4;
@@ -171,8 +182,8 @@ constexpr int SM_DOUBLES = 400;
 // ints: 0-7 block_min scratch, 8 status bits, 9 has-recovery, 10 residual violators,
 //       11 general-path flag, 12 selection count, 13 valid count
 
-// one thread: TMA bulk copies of trajectory b (even element count from an even start) and L2
-// prefetch of the trajectory this block handles after it.
+// one thread: TMA bulk copies of trajectory b (even element count from an even start) and an L2
+// prefetch of its quaternions.
 __device__ __forceinline__ void issue_trajectory_load(const FuseArgs& A, int b, double* ts_s, double* pos_s, double* z_s, uint64_t* mbar) {
     const long long e0 = A.offsets[b];
     const int n = (int)(A.offsets[b + 1] - e0);
@@ -185,17 +196,9 @@ __device__ __forceinline__ void issue_trajectory_load(const FuseArgs& A, int b, 
         bulk_g2s(pos_s, A.pos + 3 * (e0 - lead), (uint32_t)even * 24u, mbar);
         bulk_g2s(z_s, A.z + 3 * (e0 - lead), (uint32_t)even * 24u, mbar);
     }
-    const int nb = b + (int)gridDim.x;
-    if (nb < A.B) {
-        const long long f0 = A.offsets[nb] & ~1ll;
-        const long long fn = (A.offsets[nb + 1] - f0) & ~1ll;
-        if (fn > 0 && fn <= A.cap) {
-            bulk_prefetch_l2(A.ts + f0, (uint32_t)fn * 8u);
-            bulk_prefetch_l2(A.pos + 3 * f0, (uint32_t)fn * 24u);
-            bulk_prefetch_l2(A.z + 3 * f0, (uint32_t)fn * 24u);
-            bulk_prefetch_l2(A.quat + 4 * f0, (uint32_t)fn * 32u);
-        }
-    }
+    // its quaternions are streamed later (global -> global): warm L2 now so that pass hits L2
+    const long long qn = ((long long)n * 32) & ~15ll;
+    if (qn > 0) bulk_prefetch_l2(A.quat + 4 * e0, (uint32_t)qn);
 }
 
 // Resident blocks per SM the register budget is sized for.
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
         const int lead = A.use_tma ? (int)(e0 & 1) : 0;
         double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
         if (tid < 23) sd[SM_PRM + tid] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[tid];
-        if (tid == 32 % THREADS) { iscr[9] = 0; iscr[10] = 0; iscr[11] = 0; }
+        if (tid == 32 % THREADS) { iscr[9] = 0; iscr[10] = 0; iscr[11] = 0; iscr[14] = 0; }
         if (A.use_tma) {
             const int cnt = n + lead, even = cnt & ~1;
             if ((cnt & 1) && tid < 7) {                       // odd tail element: plain copy
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             const double ps0 = posS[0], ps1 = posS[1], ps2 = posS[2];
             const double pz0 = zS[0], pz1 = zS[1], pz2 = zS[2];
             const double t_first = tsS[0], t_lim = t_first + prm.max_duration, gap = prm.gap_threshold;
-            int viol = row_has_nan(pz0, pz1, pz2) ? 1 : 0;
+            int viol = row_has_nan(pz0, pz1, pz2) ? 1 : 0, inval = 0;
             double tp = (c0 > 0 && c0 < n) ? tsS[c0 - 1] : t_first;
 #pragma unroll
             for (int j = 0; j < LCH; ++j) {
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     const double t = tsS[i];
                     const bool valid = !row_has_nan(z0, z1, z2);
                     flg[i] = valid ? FLAG_VALID : 0;
+                    if (!valid) inval = 1;
                     if (!valid || t - tp > gap || t > t_lim) viol = 1;
                     tp = t;
                     if (valid && !ekf_only) {
@@ -302,11 +306,26 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 }
                 if (viol) iscr[11] = 1;
             }
+            if (inval) iscr[14] = 1;
         }
         __syncthreads();
         GSF_STAMP(2);
         int st = ST_OK;
 
+        // ------------------------------------------------------------------ GNSS recoveries (:879-894), rare: sharp-turn gate
+        if (iscr[14]) {
+            for (int i = s0; i < c1; ++i) {
+                const int f = flg[i];
+                if ((f & FLAG_VALID) && !(flg[i - 1] & FLAG_VALID)) {
+                    int s = i - 1;
+                    while (s > 0 && !(flg[s - 1] & FLAG_VALID)) --s;
+                    int nf = f | FLAG_RECOVERY;
+                    if (sharp_turn_ool(A.ts + e0, A.quat + 4 * e0, s, i - 1, prm.yaw_rate_thresh)) nf |= FLAG_NO_RTS;
+                    flg[i] = (unsigned char)nf;             // bit 0 is unchanged: concurrent neighbour reads stay valid
+                    iscr[9] = 1;
+                }
+            }
+        }
         // ------------------------------------------------------------------ general Sim3 point selection (:972-998), rare
         if (!ekf_only && iscr[11]) {
             int cntv = 0; double lastT = nan("");
@@ -408,6 +427,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             for (int k = 0; k < 12; ++k) mex.m[k] = __shfl_up_sync(GSF_FULL_MASK, loc.m[k], 1);
             if (lane == 0) moeb_identity(mex);
         }
+        GSF_STAMP(7);
         if (warp == 0) {
             int ust = 0;
             if (!ekf_only) {
@@ -437,8 +457,10 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 }
                 const int nsel = (int)n_sel;
                 double R[9], t[3], s = 1.0;
+                GSF_STAMP(8);
                 if (nsel < 3 || nsel < prm.min_samples) ust |= ST_TOO_FEW_POINTS;
                 else ust |= umeyama_finish_ool(nsel, ms_, md_, hh, ss, R, t, &s);
+                GSF_STAMP(9);
                 const Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
                 if (qnorm2(q0) == 0.0) ust |= ST_BAD_QUATERNION;
                 if (lane == 0) {
@@ -522,6 +544,8 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             const double sc = bc[19], t0 = bc[16], t1 = bc[17], t2 = bc[18];
             const double thr2 = (ekf_only || !(prm.residual_thresh > 0.0)) ? -1.0 : prm.residual_thresh * prm.residual_thresh;
             const bool general = iscr[11] != 0;
+            double w_sharp = 1.0;
+            if (prm.sharp_turn_steps > 0) { const double wd = 1.0 / (double)prm.sharp_turn_steps; if (wd < 1.0) w_sharp = wd; }
             int nviol = 0;
             Aff3 aff;
 #pragma unroll
@@ -534,6 +558,14 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
                 }
             }
+            // y = s * M(C) * p(s0-1) + t, advanced by s*u each step: the Sim3 image used by the residual check
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+            if (thr2 > 0.0 && s0 < c1) {
+                mat_vec(RC, pprev0, pprev1, pprev2, y0, y1, y2);
+                y0 = sc * y0 + t0; y1 = sc * y1 + t1; y2 = sc * y2 + t2;
+            }
+            const double q0 = prm.q[0], q1 = prm.q[1], q2 = prm.q[2], r0 = prm.r[0], r1 = prm.r[1], r2 = prm.r[2];
+#pragma unroll 3
             for (int i = s0; i < c1; ++i) {
                 const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
                 const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
@@ -541,42 +573,38 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u[0], u[1], u[2]);
                 pprev0 = p0; pprev1 = p1; pprev2 = p2;
                 const int f = flg[i];
+                const double qq[3] = {q0 * dt, q1 * dt, q2 * dt};
                 if (f & FLAG_VALID) {
                     const double zz[3] = {zS[3 * i], zS[3 * i + 1], zS[3 * i + 2]};
-                    if (thr2 > 0.0 && (!general || (f & FLAG_SELECTED))) {
-                        double rx, ry, rz;
-                        mat_vec(RC, p0, p1, p2, rx, ry, rz);
-                        const double d0 = sc * rx + t0 - zz[0], d1 = sc * ry + t1 - zz[1], d2 = sc * rz + t2 - zz[2];
-                        if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+                    if (thr2 > 0.0) {
+                        y0 = fma(sc, u[0], y0); y1 = fma(sc, u[1], y1); y2 = fma(sc, u[2], y2);
+                        const double d0 = y0 - zz[0], d1 = y1 - zz[1], d2 = y2 - zz[2];
+                        if ((!general || (f & FLAG_SELECTED)) && !(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
                     }
-                    double w = 1.0;
-                    if (!(flg[i - 1] & FLAG_VALID)) {                   // GNSS just recovered (:879-894)
-                        int s = i - 1;
-                        while (s > 0 && !(flg[s - 1] & FLAG_VALID)) --s;
-                        int nf = f | FLAG_RECOVERY;
-                        if (sharp_turn_ool(A.ts + e0, A.quat + 4 * e0, s, i - 1, prm.yaw_rate_thresh)) {
-                            nf |= FLAG_NO_RTS;
-                            if (prm.sharp_turn_steps > 0) { const double wd = 1.0 / (double)prm.sharp_turn_steps; if (wd < 1.0) w = wd; }
-                        }
-                        flg[i] = (unsigned char)nf;
-                        iscr[9] = 1;
+                    const double rr[3] = {r0, r1, r2};
+                    double kk[3], om[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const double pp = P[a] + qq[a];
+                        kk[a] = pp * fast_rcp(pp + rr[a]);
+                        om[a] = 1.0 - kk[a];
+                        P[a] = om[a] * pp * om[a] + kk[a] * rr[a] * kk[a];      // Joseph form (:731)
+                    }
+                    if (f & FLAG_NO_RTS) {                   // blended update at a sharp-turn recovery (:754-767)
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) { kk[a] *= w_sharp; om[a] = 1.0 - kk[a]; }
                     }
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        const double ra = prm.r[a];
-                        const double pp = P[a] + prm.q[a] * dt;
-                        const double k = pp * (1.0 / (pp + ra));
-                        const double omk = 1.0 - k;
-                        P[a] = omk * pp * omk + k * ra * k;             // Joseph form (:731)
-                        const double ke = k * w, av = 1.0 - ke;
-                        const double bv = av * u[a] + ke * zz[a];
-                        posS[3 * i + a] = av; zS[3 * i + a] = bv;
-                        aff.b[a] = av * aff.b[a] + bv; aff.a[a] *= av;
+                        const double bv = om[a] * u[a] + kk[a] * zz[a];
+                        posS[3 * i + a] = om[a]; zS[3 * i + a] = bv;
+                        aff.b[a] = om[a] * aff.b[a] + bv; aff.a[a] *= om[a];
                     }
                 } else {
+                    if (thr2 > 0.0) { y0 = fma(sc, u[0], y0); y1 = fma(sc, u[1], y1); y2 = fma(sc, u[2], y2); }
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        P[a] += prm.q[a] * dt;
+                        P[a] += qq[a];
                         posS[3 * i + a] = P[a];                          // P_f[i] kept for the RTS patch
                         zS[3 * i + a] = u[a];
                         aff.b[a] += u[a];
@@ -658,7 +686,10 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
         __syncthreads();
         GSF_STAMP(5);
 
-        // ------------------------------------------------------------------ store fused positions, start the next load
+        // ------------------------------------------------------------------ store fused positions; stream the quaternions
+        // q_state[i] = C (x) q_hat[i], global -> global in rounds of 4 poses per thread.  Thread 0
+        // issues the bulk store first, and after the first round (when the store has drained out of
+        // shared memory) the next trajectory's bulk loads, which then overlap the remaining rounds.
         double* gout = A.out_pos + 3 * e0;
         if (iscr[10]) st |= ST_RANSAC_OUTLIERS;
         if (A.use_tma) {
@@ -670,39 +701,27 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     const int q = 3 * (lead + even);
                     gout[q] = zS[q]; gout[q + 1] = zS[q + 1]; gout[q + 2] = zS[q + 2];
                 }
-                A.status[b] = st;
-                if (A.sim3_out && !ekf_only) {
-                    double* o = A.sim3_out + 16 * (size_t)b;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
-                    o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
-                    o[13] = (double)iscr[12]; o[14] = (double)iscr[13]; o[15] = (double)iscr[10];
-                }
-                bulk_wait_read();                                   // shared memory is free again
-                fence_proxy_async();
-                if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar);
             }
         } else {
             for (int i = tid; i < 3 * n; i += THREADS) gout[i] = zS[i];
-            if (tid == 0) {
-                A.status[b] = st;
-                if (A.sim3_out && !ekf_only) {
-                    double* o = A.sim3_out + 16 * (size_t)b;
-                    for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
-                    o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
-                    o[13] = (double)iscr[12]; o[14] = (double)iscr[13]; o[15] = (double)iscr[10];
-                }
+        }
+        if (tid == 0) {
+            A.status[b] = st;
+            if (A.sim3_out && !ekf_only) {
+                double* o = A.sim3_out + 16 * (size_t)b;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
+                o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
+                o[13] = (double)iscr[12]; o[14] = (double)iscr[13]; o[15] = (double)iscr[10];
             }
         }
-
-        // ------------------------------------------------------------------ quaternions: q_state[i] = C (x) q_hat[i]
-        // (streamed global -> global while the next trajectory's bulk copies are in flight)
         int badq = 0;
         {
             const Quat C{bc[9], bc[10], bc[11], bc[12]};
             const double2* __restrict__ qin = reinterpret_cast<const double2*>(A.quat + 4 * e0);
             double2* __restrict__ qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
-            for (int i0 = tid; i0 < n; i0 += 4 * THREADS) {
+            bool next_issued = false;
+            for (int i0 = tid; i0 < n || !next_issued; i0 += 4 * THREADS) {
                 double2 lo[4], hi[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -719,6 +738,14 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                         const Quat r = qscale(qmul(C, qi), rsqrt(n2));
                         qout[2 * i] = make_double2(r.x, r.y);
                         qout[2 * i + 1] = make_double2(r.z, r.w);
+                    }
+                }
+                if (!next_issued) {
+                    next_issued = true;
+                    if (A.use_tma && tid == 0) {
+                        bulk_wait_read();                           // shared memory is free again
+                        fence_proxy_async();
+                        if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar);
                     }
                 }
             }

@@ -17,4 +17,5 @@ names = ["load-wait", "pass1 flags+sums", "general-sel + pass2 moebius + SVD", "
 print("n", n, "total cycles", c[6] - c[0])
 for k, nm in enumerate(names):
     print(f"  {nm:36s} {c[k+1]-c[k]:8d}")
+print("  [pass2 detail] moebius+scan", c[7]-c[2], " sums-combine", c[8]-c[7], " svd call", c[9]-c[8], " bcast+sync", c[3]-c[9])
 lib.gsf_debug_phase_clock(None)
