@@ -1,6 +1,7 @@
 // C ABI of libgsf.so (declared in include/gsf.h): argument checks, launch configuration and
 // the host-buffer pipeline.  No torch types, no hidden device allocation in the *_dev calls.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -76,6 +77,8 @@ int pick_threads(int cap, int max_smem) {
     if (blocks < 1) blocks = 1;
     int threads = 32;
     while (threads < 256 && (blocks * threads < 384 || threads * 9 < cap)) threads <<= 1;
+    const char* force = getenv("GSF_FUSE_THREADS");            // tuning hook
+    if (force && atoi(force) > 0) threads = atoi(force);
     return threads;
 }
 

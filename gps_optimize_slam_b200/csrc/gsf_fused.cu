@@ -34,6 +34,11 @@
 
 namespace gsf {
 
+// 1: quaternion rounds beyond the first run in the shadow of the next trajectory's SVD (measured slower: the
+// next load is exposed and the SVD warp competes with them); 0: all rounds right after the store.
+#ifndef GSF_DEFER_QUAT
+#define GSF_DEFER_QUAT 0
+#endif
 #define GSF_STAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && tid == 0 && it == 2) A.phase_clock[k] = clock64(); } while (0)
 
 // 1/x for finite positive x: hardware seed (rel. error 2^-23) + two Newton steps -> <= 1 ulp.
@@ -69,11 +74,13 @@ __device__ __forceinline__ void moeb_identity(Moeb3& x) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) { x.m[4 * a] = 1.0; x.m[4 * a + 1] = 0.0; x.m[4 * a + 2] = 0.0; x.m[4 * a + 3] = 1.0; }
 }
-// r = later o earlier
+// r = later o earlier.  NAX == 2: only axes 0 and 2 are carried (axis 1 is a copy of axis 0).
+template <int NAX>
 __device__ __forceinline__ Moeb3 moeb_compose(const Moeb3& e, const Moeb3& l) {
     Moeb3 r;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
+        if (NAX == 2 && a == 1) continue;
         const double* E = e.m + 4 * a; const double* L = l.m + 4 * a; double* R = r.m + 4 * a;
         R[0] = L[0] * E[0] + L[1] * E[2]; R[1] = L[0] * E[1] + L[1] * E[3];
         R[2] = L[2] * E[0] + L[3] * E[2]; R[3] = L[2] * E[1] + L[3] * E[3];
@@ -88,14 +95,56 @@ __device__ __forceinline__ Aff3 aff_compose(const Aff3& e, const Aff3& l) {
     return r;
 }
 // Inclusive warp scans (fixed shuffle pattern => deterministic).
+template <int NAX>
 __device__ __forceinline__ void moeb_warp_scan(Moeb3& x, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         Moeb3 y;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) y.m[k] = __shfl_up_sync(GSF_FULL_MASK, x.m[k], o);
-        if (lane >= o) x = moeb_compose(y, x);
+        for (int k = 0; k < 12; ++k) {
+            if (NAX == 2 && k >= 4 && k < 8) continue;
+            y.m[k] = __shfl_up_sync(GSF_FULL_MASK, x.m[k], o);
+        }
+        if (lane >= o) x = moeb_compose<NAX>(y, x);
     }
+}
+// Chunk composite of the covariance maps of steps [s0, c1) and its warp scan.  Returns the
+// warp-exclusive prefix; the warp total goes to `wtot` (lane 31).
+template <int NAX>
+__device__ __forceinline__ Moeb3 moebius_chunk_scan(const double* tsS, const unsigned char* flg, const FuseParams& prm,
+                                                    int s0, int c1, int lane, double* wtot) {
+    Moeb3 loc;
+    moeb_identity(loc);
+    int since = 0;
+    for (int i = s0; i < c1; ++i) {
+        const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
+        const bool v = flg[i] & FLAG_VALID;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (NAX == 2 && a == 1) continue;
+            double* m = loc.m + 4 * a;
+            const double qa = prm.q[a] * dt, ra = prm.r[a];
+            const double ta = m[0] + qa * m[2], tb = m[1] + qa * m[3];        // [1 q; 0 1] * m
+            if (v) { m[2] = ta + ra * m[2]; m[3] = tb + ra * m[3]; m[0] = ra * ta; m[1] = ra * tb; }
+            else { m[0] = ta; m[1] = tb; }
+        }
+        if (++since == 16) {
+            since = 0;
+            moeb_rescale(loc.m); if (NAX == 3) moeb_rescale(loc.m + 4); moeb_rescale(loc.m + 8);
+        }
+    }
+    moeb_rescale(loc.m); if (NAX == 3) moeb_rescale(loc.m + 4); moeb_rescale(loc.m + 8);
+    moeb_warp_scan<NAX>(loc, lane);
+    if (NAX == 2) { loc.m[4] = loc.m[0]; loc.m[5] = loc.m[1]; loc.m[6] = loc.m[2]; loc.m[7] = loc.m[3]; }
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) wtot[k] = loc.m[k];
+    }
+    Moeb3 mex;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) mex.m[k] = __shfl_up_sync(GSF_FULL_MASK, loc.m[k], 1);
+    if (lane == 0) moeb_identity(mex);
+    return mex;
 }
 __device__ __forceinline__ void aff_warp_scan(Aff3& x, int lane) {
 #pragma unroll
@@ -201,8 +250,38 @@ __device__ __forceinline__ void issue_trajectory_load(const FuseArgs& A, int b, 
     if (qn > 0) bulk_prefetch_l2(A.quat + 4 * e0, (uint32_t)qn);
 }
 
+// Streaming quaternion pass: q_state[i] = C (x) q_hat[i] for poses first, first+stride, ... < n,
+// 4 poses in flight per thread.  Returns 1 if a zero-norm quaternion was met.
+__device__ __forceinline__ int quat_rounds(const double* __restrict__ quat_in, double* __restrict__ quat_out, const Quat& C,
+                                           int first, int stride, int n) {
+    const double2* __restrict__ qin = reinterpret_cast<const double2*>(quat_in);
+    double2* __restrict__ qout = reinterpret_cast<double2*>(quat_out);
+    int bad = 0;
+    for (int i0 = first; i0 < n; i0 += 4 * stride) {
+        double2 lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * stride;
+            if (i < n) { lo[u] = __ldg(qin + 2 * i); hi[u] = __ldg(qin + 2 * i + 1); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * stride;
+            if (i < n) {
+                const Quat qi{lo[u].x, lo[u].y, hi[u].x, hi[u].y};
+                const double n2 = qnorm2(qi);
+                if (n2 == 0.0) bad = 1;                     // scipy raises here (:466); output row becomes NaN
+                const Quat r = qscale(qmul(C, qi), rsqrt(n2));
+                qout[2 * i] = make_double2(r.x, r.y);
+                qout[2 * i + 1] = make_double2(r.z, r.w);
+            }
+        }
+    }
+    return bad;
+}
+
 // Resident blocks per SM the register budget is sized for.
-constexpr int fuse_min_blocks(int threads) { return threads <= 32 ? 14 : (threads == 64 ? 7 : (threads == 128 ? 3 : 1)); }
+constexpr int fuse_min_blocks(int threads) { return threads <= 32 ? 14 : (threads == 64 ? 7 : (threads <= 160 ? 3 : 1)); }
 
 template <int THREADS, int LCH>
 __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_kernel(const FuseArgs A) {
@@ -224,6 +303,10 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
     if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     __syncthreads();
     if (A.use_tma && tid == 0 && (int)blockIdx.x < A.B) issue_trajectory_load(A, blockIdx.x, ts_s, pos_s, z_s, mbar);
+
+    // quaternion rounds of the previous trajectory still to do (they run in the shadow of the next SVD)
+    long long dq_e0 = 0; int dq_n = 0, dq_b = -1; Quat dq_C{0.0, 0.0, 0.0, 1.0};
+    constexpr int DQ_T = NW > 1 ? THREADS - 32 : THREADS;      // threads that take part in the deferred rounds
 
     int it = 0;
     for (int b = blockIdx.x; b < A.B; b += gridDim.x, ++it) {
@@ -398,34 +481,16 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             __syncthreads();
         }
 
-        // ------------------------------------------------------------------ pass 2: Moebius chunk maps (all warps) + SVD (warp 0)
+        // ------------------------------------------------------------------ pass 2: SVD (warp 0) | Moebius maps + deferred quaternions
+        const bool xy_same = prm.p0[0] == prm.p0[1] && prm.q[0] == prm.q[1] && prm.r[0] == prm.r[1];
         Moeb3 mex;                                          // exclusive prefix inside the warp
-        {
-            Moeb3 loc;
-            moeb_identity(loc);
-            int since = 0;
-            for (int i = s0; i < c1; ++i) {
-                const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
-                const bool v = flg[i] & FLAG_VALID;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    double* m = loc.m + 4 * a;
-                    const double qa = prm.q[a] * dt, ra = prm.r[a];
-                    const double ta = m[0] + qa * m[2], tb = m[1] + qa * m[3];        // [1 q; 0 1] * m
-                    if (v) { m[2] = ta + ra * m[2]; m[3] = tb + ra * m[3]; m[0] = ra * ta; m[1] = ra * tb; }
-                    else { m[0] = ta; m[1] = tb; }
-                }
-                if (++since == 16) { since = 0; moeb_rescale(loc.m); moeb_rescale(loc.m + 4); moeb_rescale(loc.m + 8); }
+        if (NW > 1 && warp != 0) {
+            mex = xy_same ? moebius_chunk_scan<2>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12)
+                          : moebius_chunk_scan<3>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12);
+            if (dq_n > 4 * THREADS) {
+                const int bad = quat_rounds(A.quat + 4 * dq_e0, A.out_quat + 4 * dq_e0, dq_C, 4 * THREADS + tid - 32, DQ_T, dq_n);
+                if (bad) atomicOr(A.status + dq_b, ST_BAD_QUATERNION);
             }
-            moeb_rescale(loc.m); moeb_rescale(loc.m + 4); moeb_rescale(loc.m + 8);
-            moeb_warp_scan(loc, lane);
-            if (lane == 31) {
-#pragma unroll
-                for (int k = 0; k < 12; ++k) sd[SM_MOEB + warp * 12 + k] = loc.m[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 12; ++k) mex.m[k] = __shfl_up_sync(GSF_FULL_MASK, loc.m[k], 1);
-            if (lane == 0) moeb_identity(mex);
         }
         GSF_STAMP(7);
         if (warp == 0) {
@@ -495,6 +560,11 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 iscr[8] = ust;
             }
         }
+        if (NW == 1 || warp == 0) {
+            mex = xy_same ? moebius_chunk_scan<2>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12)
+                          : moebius_chunk_scan<3>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12);
+        }
+        dq_n = 0;
         __syncthreads();
         GSF_STAMP(3);
         st |= iscr[8];
@@ -527,9 +597,9 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     Moeb3 nx;
 #pragma unroll
                     for (int k = 0; k < 12; ++k) nx.m[k] = sd[SM_MOEB + w * 12 + k];
-                    acc = moeb_compose(acc, nx);
+                    acc = moeb_compose<3>(acc, nx);
                 }
-                pre = moeb_compose(acc, mex);
+                pre = moeb_compose<3>(acc, mex);
             }
             double P[3];
 #pragma unroll
@@ -585,6 +655,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     double kk[3], om[3];
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
+                        if (a == 1 && xy_same) { kk[1] = kk[0]; om[1] = om[0]; P[1] = P[0]; continue; }
                         const double pp = P[a] + qq[a];
                         kk[a] = pp * fast_rcp(pp + rr[a]);
                         om[a] = 1.0 - kk[a];
@@ -715,53 +786,26 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 o[13] = (double)iscr[12]; o[14] = (double)iscr[13]; o[15] = (double)iscr[10];
             }
         }
-        int badq = 0;
         {
             const Quat C{bc[9], bc[10], bc[11], bc[12]};
-            const double2* __restrict__ qin = reinterpret_cast<const double2*>(A.quat + 4 * e0);
-            double2* __restrict__ qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
-            bool next_issued = false;
-            for (int i0 = tid; i0 < n || !next_issued; i0 += 4 * THREADS) {
-                double2 lo[4], hi[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * THREADS;
-                    if (i < n) { lo[u] = __ldg(qin + 2 * i); hi[u] = __ldg(qin + 2 * i + 1); }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * THREADS;
-                    if (i < n) {
-                        const Quat qi{lo[u].x, lo[u].y, hi[u].x, hi[u].y};
-                        const double n2 = qnorm2(qi);
-                        if (n2 == 0.0) badq = 1;
-                        const Quat r = qscale(qmul(C, qi), rsqrt(n2));
-                        qout[2 * i] = make_double2(r.x, r.y);
-                        qout[2 * i + 1] = make_double2(r.z, r.w);
-                    }
-                }
-                if (!next_issued) {
-                    next_issued = true;
-                    if (A.use_tma && tid == 0) {
-                        bulk_wait_read();                           // shared memory is free again
-                        fence_proxy_async();
-                        if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar);
-                    }
-                }
+            // first round (4 poses per thread) now, while the bulk store drains ...
+            const int n_now = (NW > 1 && GSF_DEFER_QUAT) ? min(n, 4 * THREADS) : n;
+            int bad = quat_rounds(A.quat + 4 * e0, A.out_quat + 4 * e0, C, tid, THREADS, n_now);
+            if (A.use_tma && tid == 0) {
+                bulk_wait_read();                                   // shared memory is free again
+                fence_proxy_async();
+                if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar);
             }
+            // ... the remaining rounds run in the shadow of the next trajectory's SVD (or after the loop)
+            dq_e0 = e0; dq_n = (NW > 1 && GSF_DEFER_QUAT) ? n : 0; dq_b = b; dq_C = C;
+            __syncthreads();                                        // status[b] is written; scratch may be reused
+            if (bad) atomicOr(A.status + b, ST_BAD_QUATERNION);
         }
-        badq = __syncthreads_or(badq);
         GSF_STAMP(6);
-        if (badq) {
-            // A zero-norm SLAM quaternion: scipy raises inside transform_trajectory (:466), the
-            // reference run aborts.  Flag it and blank the outputs.
-            if (A.use_tma && tid == 0) bulk_wait_all();
-            __syncthreads();
-            for (int i = tid; i < 3 * n; i += THREADS) gout[i] = nan("");
-            for (int i = tid; i < 4 * n; i += THREADS) A.out_quat[4 * e0 + i] = nan("");
-            if (tid == 0) A.status[b] = st | ST_BAD_QUATERNION;
-            __syncthreads();
-        }
+    }
+    if (dq_n > 4 * THREADS) {                                       // flush: last trajectory of this block
+        const int bad = quat_rounds(A.quat + 4 * dq_e0, A.out_quat + 4 * dq_e0, dq_C, 4 * THREADS + tid, THREADS, dq_n);
+        if (bad) atomicOr(A.status + dq_b, ST_BAD_QUATERNION);
     }
 }
 
@@ -809,6 +853,7 @@ static cudaError_t launch_fuse_t(const FuseArgs& a, int num_sms, cudaStream_t st
 // threads x chunk must cover the longest trajectory; chunk lengths are odd.
 cudaError_t launch_fuse(const FuseArgs& a, int threads, int num_sms, cudaStream_t stream) {
     const int need = (a.cap + threads - 1) / threads;
+    if (threads == 160) return need <= 7 ? launch_fuse_t<160, 7>(a, num_sms, stream) : cudaErrorInvalidValue;
     if (need <= 9) {
         switch (threads) {
             case 32: return launch_fuse_t<32, 9>(a, num_sms, stream);
