@@ -152,7 +152,8 @@ def main():
     ap.add_argument("--e2e-trajectories", type=int, default=0, help="host-buffer sample per rank (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
-    ap.add_argument("--with-ate", action="store_true", help="also run the NN-ATE kernel + NCCL gather after timing")
+    ap.add_argument("--with-ate", action="store_true", help="also run the NN-ATE kernel at N=1 (always on for N>1, with the NCCL gather)")
+    ap.add_argument("--ate-trajectories", type=int, default=65536, help="trajectories per rank scored by the NN-ATE kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = dict(WORKLOADS[args.workload])
@@ -169,7 +170,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gps_optimize_slam_b200 import _lib, fusion
+    from gps_optimize_slam_b200 import _lib, fusion, sharding
     from gps_optimize_slam_b200.config import pack_fuse_params
 
     if not torch.cuda.is_available():
@@ -181,7 +182,7 @@ def main():
     _lib.load()
 
     B_total, n = wl["B"], wl["n"]
-    lo, hi = rank * B_total // world, (rank + 1) * B_total // world
+    lo, hi = sharding.shard_range(B_total, rank, world)
     B = hi - lo
     free, _total = torch.cuda.mem_get_info(dev)
     need = B * n * BYTES_PER_POSE + B * 256
@@ -222,10 +223,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) / passes for k in range(args.steps)]
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.cpu())
+    elapsed_ms = sharding.max_over_ranks(elapsed_ms, dev)
     bad = int((status != 0).sum().cpu())
 
     poses_per_step_rank = B_res * passes * n
@@ -241,11 +239,12 @@ def main():
                 "traffic": None, "peak_source": peak_src, "kernel": "fuse_traj_kernel",
                 "algorithmic_bytes_per_launch": B_res * n * BYTES_PER_POSE, "launch_ms": launch_ms}
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
+    if os.path.exists(tr_path):          # DRAM bytes per trajectory from the committed ncu --set full capture, scaled to this launch
         try:
             tj = json.load(open(tr_path))
-            if tj.get("workload") == args.workload and tj.get("trajectories_per_launch") == B_res:
-                roofline["traffic"] = tj["dram_bytes_per_launch"]
+            if tj.get("workload") == args.workload and tj.get("poses_per_trajectory") == n:
+                roofline["traffic"] = tj["dram_bytes_per_trajectory"] * B_res
+                roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass
 
@@ -271,31 +270,34 @@ def main():
             e2e_step()
         torch.cuda.synchronize(dev)
         e2e_s = time.perf_counter() - t0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.cpu())
+        e2e_s = sharding.max_over_ranks(e2e_s, dev)
         e2e_ok = bool(torch.equal(hop, out_pos[: Be * n].cpu())) if passes == 1 else True
         e2e = {"value": world * Be * (n - 1) * e2e_steps / e2e_s, "unit": "pose-updates/s",
                "h2d_bytes_per_step": Be * n * 88 + (Be + 1) * 8 + 184, "d2h_bytes_per_step": Be * n * 56 + Be * 132,
                "sample": f"{Be} trajectories x {n} poses per rank per step, pinned host buffers, {e2e_steps} steps",
                "matches_device_path": e2e_ok}
 
-    # ---- ATE statistics: per-rank NN-ATE kernel on a slab + NCCL gather (outside the timed region)
+    # ---- ATE statistics (EKFGPSSLAM.py:1021-1033): per-rank NN-ATE kernel on a bounded slab of the
+    #      fused output, then the only collective of the path: gather of the per-trajectory stats
+    #      (NCCL all_gather over NVLink).  Outside the timed region; the exact O(n^2) nearest-neighbour
+    #      kernel is FP64-bound (about 20x the fused kernel per trajectory at n = 1000).
     ate = None
-    if args.with_ate:
-        Ba = min(B_res, 4096)
+    if args.with_ate or world > 1:
+        Ba = min(B_res, args.ate_trajectories)
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         stats = fusion.ate_nn_batched(out_pos[: Ba * n], z[: Ba * n], ts[: Ba * n], off[: Ba + 1], n, 5.0)
         torch.cuda.synchronize(dev)
         ate_s = time.perf_counter() - t0
-        if world > 1:
-            gathered = [torch.empty_like(stats) for _ in range(world)]
-            dist.all_gather(gathered, stats)
-            stats = torch.cat(gathered)
-        s = stats.cpu()
-        ate = {"trajectories": int(s.shape[0]), "mean_rmse_m": float(s[:, 2].mean()), "mean_median_m": float(s[:, 1].mean()),
-               "seconds_per_rank": ate_s, "gathered_with": "nccl all_gather" if world > 1 else "single rank"}
+        t0 = time.perf_counter()
+        table = sharding.gather_stats(stats, total_rows=Ba * world if world > 1 else None)
+        torch.cuda.synchronize(dev)
+        gather_s = time.perf_counter() - t0
+        s_ = table.cpu()
+        ate = {"trajectories": int(s_.shape[0]), "per_rank": Ba, "mean_rmse_m": float(s_[:, 2].mean()),
+               "mean_median_m": float(s_[:, 1].mean()), "mean_of_means_m": float(s_[:, 0].mean()),
+               "kernel_seconds_per_rank": ate_s, "gather_seconds": gather_s,
+               "gathered_with": "nccl all_gather" if world > 1 else "single rank (no collective)"}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample
     cpu = None
