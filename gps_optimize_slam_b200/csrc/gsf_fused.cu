@@ -97,7 +97,7 @@ __device__ __forceinline__ Aff3 aff_compose(const Aff3& e, const Aff3& l) {
 // Inclusive warp scans (fixed shuffle pattern => deterministic).
 template <int NAX>
 __device__ __forceinline__ void moeb_warp_scan(Moeb3& x, int lane) {
-#pragma unroll
+#pragma unroll 1
     for (int o = 1; o < 32; o <<= 1) {
         Moeb3 y;
 #pragma unroll
@@ -147,7 +147,7 @@ __device__ __forceinline__ Moeb3 moebius_chunk_scan(const double* tsS, const uns
     return mex;
 }
 __device__ __forceinline__ void aff_warp_scan(Aff3& x, int lane) {
-#pragma unroll
+#pragma unroll 1
     for (int o = 1; o < 32; o <<= 1) {
         Aff3 y;
 #pragma unroll
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             const double t_first = tsS[0], t_lim = t_first + prm.max_duration, gap = prm.gap_threshold;
             int viol = row_has_nan(pz0, pz1, pz2) ? 1 : 0, inval = 0;
             double tp = (c0 > 0 && c0 < n) ? tsS[c0 - 1] : t_first;
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < LCH; ++j) {
                 const int i = c0 + j;
                 if (i < c1) {
@@ -484,14 +484,6 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
         // ------------------------------------------------------------------ pass 2: SVD (warp 0) | Moebius maps + deferred quaternions
         const bool xy_same = prm.p0[0] == prm.p0[1] && prm.q[0] == prm.q[1] && prm.r[0] == prm.r[1];
         Moeb3 mex;                                          // exclusive prefix inside the warp
-        if (NW > 1 && warp != 0) {
-            mex = xy_same ? moebius_chunk_scan<2>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12)
-                          : moebius_chunk_scan<3>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12);
-            if (dq_n > 4 * THREADS) {
-                const int bad = quat_rounds(A.quat + 4 * dq_e0, A.out_quat + 4 * dq_e0, dq_C, 4 * THREADS + tid - 32, DQ_T, dq_n);
-                if (bad) atomicOr(A.status + dq_b, ST_BAD_QUATERNION);
-            }
-        }
         GSF_STAMP(7);
         if (warp == 0) {
             int ust = 0;
@@ -560,11 +552,8 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 iscr[8] = ust;
             }
         }
-        if (NW == 1 || warp == 0) {
-            mex = xy_same ? moebius_chunk_scan<2>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12)
-                          : moebius_chunk_scan<3>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12);
-        }
-        dq_n = 0;
+        mex = xy_same ? moebius_chunk_scan<2>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12)
+                      : moebius_chunk_scan<3>(tsS, flg, prm, s0, c1, lane, sd + SM_MOEB + warp * 12);
         __syncthreads();
         GSF_STAMP(3);
         st |= iscr[8];
@@ -635,7 +624,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 y0 = sc * y0 + t0; y1 = sc * y1 + t1; y2 = sc * y2 + t2;
             }
             const double q0 = prm.q[0], q1 = prm.q[1], q2 = prm.q[2], r0 = prm.r[0], r1 = prm.r[1], r2 = prm.r[2];
-#pragma unroll 3
+#pragma unroll 1
             for (int i = s0; i < c1; ++i) {
                 const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
                 const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
