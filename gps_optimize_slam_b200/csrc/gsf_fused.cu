@@ -381,8 +381,12 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 }
             }
             if (!ekf_only) {
+                // xor-shuffle tree with the stage loop rolled (code size), the 17 sums unrolled
+#pragma unroll 1
+                for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                for (int k = 0; k < 17; ++k) v[k] = warp_sum(v[k]);
+                    for (int k = 0; k < 17; ++k) v[k] += __shfl_xor_sync(GSF_FULL_MASK, v[k], o);
+                }
                 if (lane == 0) {
 #pragma unroll
                     for (int k = 0; k < 17; ++k) sd[SM_SUMS + warp * 18 + k] = v[k];
