@@ -121,7 +121,22 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
     a.B = B; a.cap = cap;
     a.use_tma = aligned16(ts) && aligned16(pos) && aligned16(z) && aligned16(out_pos);
     a.phase_clock = g_phase_clock;
-    cudaError_t e = gsf::launch_fuse(a, pick_threads(cap, d.max_smem), d.sms, (cudaStream_t)stream);
+    a.only_deferred = 0; a.defer_count = nullptr;
+    // Fast kernel first (all-valid trajectories); whatever it defers goes through the general kernel
+    // behind it on the same stream.  GSF_FUSE_IMPL=general forces the general kernel for everything.
+    const char* impl = getenv("GSF_FUSE_IMPL");
+    const bool want_fast = !(impl && strcmp(impl, "general") == 0);
+    cudaError_t e;
+    if (want_fast && a.use_tma && !init_pos && gsf::fast_fuse_supported(cap, d.max_smem)) {
+        e = gsf::defer_counter(&a.defer_count);
+        if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter)");
+        e = cudaMemsetAsync(a.defer_count, 0, sizeof(int), (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter reset)");
+        e = gsf::launch_fuse_fast(a, d.sms, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (fast kernel)");
+        a.only_deferred = 1;
+    }
+    e = gsf::launch_fuse(a, pick_threads(cap, d.max_smem), d.sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev");
     return 0;
 }

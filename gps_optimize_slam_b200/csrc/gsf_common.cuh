@@ -34,6 +34,7 @@ enum : int {
     ST_RANSAC_OUTLIERS = 16,   // all-points fit leaves residuals >= threshold: the reference's
                                // unseeded RANSAC could pick a different inlier set here
     ST_TOO_LONG = 32,          // trajectory does not fit the shared-memory staging buffer
+    ST_DEFERRED = 1 << 30,     // internal: left by the fast kernel for the general kernel (never returned)
 };
 
 // EKF / pipeline parameters for one trajectory (or shared by the batch).  Values are the

@@ -1,0 +1,571 @@
+// gsf_fuse_batched, fast kernel: the same fused Sim3 -> EKF path as gsf_fused.cu for the common case
+// (every pose has a GNSS measurement, no GNSS time gap, trajectory inside the Sim3 window), organised as
+// a warp-specialised pipeline so that nothing serial sits on the critical path of the pose loops.
+//
+// Reference path replaced (file:line in /root/reference/EKFGPSSLAM.py): Sim3 point selection :972-998
+// (here: "all points", verified on the fly), compute_sim3_transform :428-459, transform_trajectory row 0
+// :461-467, apply_ekf_correction :831-935 with ExtendedKalmanFilter :679-772.  Trajectories that need
+// the general machinery (invalid rows -> outages/RTS :875-928, time gaps, Sim3 window, too few points,
+// zero quaternion) are detected by the look-ahead warps, marked ST_DEFERRED and processed by the general
+// kernel (gsf_fused.cu) launched behind this one on the same stream.
+//
+// One block = CT compute threads + two look-ahead warps, persistent over trajectories b, b+grid, ...:
+//   * warp A (sums)  streams positions + measurements of trajectory j+1/j+2 straight from HBM with
+//     128-bit loads (the later TMA load of the same bytes hits L2), accumulates the 16 pivot-shifted
+//     Umeyama sums in a fixed order (lane-strided pose pairs, transposing butterfly) -> bit-reproducible;
+//   * warp B (scan + SVD) reads the timestamps, checks gap/window, composes the covariance recursion
+//     p -> R(p+q)/(p+q+R) per compute-thread chunk as 2x2 Moebius matrices (one warp scan over 32 lanes
+//     x CT/32 chunks) and publishes the covariance every compute thread starts from; then finishes
+//     Umeyama (one-sided Jacobi SVD) and publishes R, t, s, C = q_state0 (x) conj(q_hat0), M(C);
+//   * compute warps (trajectory j, resident in shared memory via three TMA bulk copies): exact per-step
+//     Joseph-form gains + affine state maps (pass B), affine scan, state recursion (pass C), bulk store,
+//     streaming quaternion pass, next TMA load.  No Moebius scan, no reduction, no SVD wait.
+//   Hand-offs are mbarriers (aux_ready / aux_free / sums_ready, two slots); the compute warps
+//   synchronise among themselves with a named barrier.
+#include <cstdlib>
+#include <atomic>
+#include "gsf_fuse_shared.cuh"
+
+namespace gsf {
+
+// ----------------------------------------------------------------------------- Moebius maps, NAX axes
+template <int NAX> struct MoebN { double m[4 * NAX]; };      // per axis row-major [a b; c d]
+
+template <int NAX>
+__device__ __forceinline__ void moebn_identity(MoebN<NAX>& x) {
+#pragma unroll
+    for (int a = 0; a < NAX; ++a) { x.m[4 * a] = 1.0; x.m[4 * a + 1] = 0.0; x.m[4 * a + 2] = 0.0; x.m[4 * a + 3] = 1.0; }
+}
+template <int NAX>
+__device__ __forceinline__ void moebn_rescale(MoebN<NAX>& x) {
+#pragma unroll
+    for (int a = 0; a < NAX; ++a) moeb_rescale(x.m + 4 * a);
+}
+// r = later o earlier
+template <int NAX>
+__device__ __forceinline__ MoebN<NAX> moebn_compose(const MoebN<NAX>& e, const MoebN<NAX>& l) {
+    MoebN<NAX> r;
+#pragma unroll
+    for (int a = 0; a < NAX; ++a) {
+        const double* E = e.m + 4 * a; const double* L = l.m + 4 * a; double* R = r.m + 4 * a;
+        R[0] = L[0] * E[0] + L[1] * E[2]; R[1] = L[0] * E[1] + L[1] * E[3];
+        R[2] = L[2] * E[0] + L[3] * E[2]; R[3] = L[2] * E[1] + L[3] * E[3];
+        moeb_rescale(R);
+    }
+    return r;
+}
+// one predict + update step with a valid measurement: [r r*q; 1 q+r] applied on the left
+template <int NAX>
+__device__ __forceinline__ void moebn_step(MoebN<NAX>& x, const double* qv, const double* rv, double dt) {
+#pragma unroll
+    for (int a = 0; a < NAX; ++a) {
+        double* m = x.m + 4 * a;
+        const double qa = qv[a] * dt, ra = rv[a];
+        const double ta = m[0] + qa * m[2], tb = m[1] + qa * m[3];
+        m[2] = ta + ra * m[2]; m[3] = tb + ra * m[3]; m[0] = ra * ta; m[1] = ra * tb;
+    }
+}
+template <int NAX>
+__device__ __forceinline__ double moebn_apply(const MoebN<NAX>& x, int a, double p) {
+    const double* m = x.m + 4 * a;
+    return (m[0] * p + m[1]) / (m[2] * p + m[3]);
+}
+
+// ----------------------------------------------------------------------------- shared-memory map (doubles after the staging buffers)
+constexpr int FS_BC = 0;            // 2 slots x 48: M(C) 0-8, C 9-12, x0 13-15, t 16-18, s 19, R 20-28, verdict 30, status 31
+constexpr int FS_SUMS = 96;         // 2 slots x 24: 16 sums, pivots 16-21
+constexpr int FS_AFF = 144;         // 4 warps x 6 affine warp totals
+constexpr int FS_PRM = 168;         // FuseParams as 23 doubles (24)
+constexpr int FS_INT = 192;         // 4 ints: 0 residual violators
+constexpr int FS_MBAR = 194;        // 7 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2]
+constexpr int FS_PST = 202;         // 2 slots x CT x 3 start covariances
+constexpr int MB_FULL = 0, MB_SUMS = 1, MB_AUXRDY = 3, MB_AUXFREE = 5;
+
+__host__ __device__ constexpr size_t fast_smem_bytes(int cap, int ct) {
+    return (size_t)((cap + 3) & ~1) * 56 + (size_t)(FS_PST + 6 * ct) * 8;
+}
+
+// 16 accumulators x 32 lanes -> lane L (bit 0 clear) ends with the warp total of value idx(L):
+// fixed exchange pattern (halve the value set at each of the first four stages), 16 shuffles of doubles.
+__device__ __forceinline__ double butterfly16(double* v, int lane) {
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+        const int o = 16 >> st, half = 8 >> st;
+        const bool up = lane & o;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const double send = up ? v[k] : v[k + half];
+            const double keep = up ? v[k + half] : v[k];
+            v[k] = keep + __shfl_xor_sync(GSF_FULL_MASK, send, o);
+        }
+    }
+    return v[0] + __shfl_xor_sync(GSF_FULL_MASK, v[0], 1);
+}
+__device__ __forceinline__ int butterfly16_index(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
+__device__ __forceinline__ void umeyama_accumulate(double* v, double p0, double p1, double p2, double z0, double z1, double z2,
+                                                   double ps0, double ps1, double ps2, double pz0, double pz1, double pz2) {
+    const double a0 = p0 - ps0, a1 = p1 - ps1, a2 = p2 - ps2;
+    const double b0 = z0 - pz0, b1 = z1 - pz1, b2 = z2 - pz2;
+    v[0] += a0; v[1] += a1; v[2] += a2; v[3] += b0; v[4] += b1; v[5] += b2;
+    v[6] += a0 * b0; v[7] += a0 * b1; v[8] += a0 * b2;
+    v[9] += a1 * b0; v[10] += a1 * b1; v[11] += a1 * b2;
+    v[12] += a2 * b0; v[13] += a2 * b1; v[14] += a2 * b2;
+    v[15] += a0 * a0 + a1 * a1 + a2 * a2;
+}
+
+// Warp B, part 1: covariance the compute thread t starts from, for every t, and the gap / window check.
+template <int NAX, int CT, int LCH>
+__device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, int n, const FuseParams* __restrict__ gp, int lane,
+                                              double* __restrict__ pst) {
+    constexpr int CPL = CT / 32;                            // compute-thread chunks per lane
+    double qv[NAX], rv[NAX], p0v[NAX];
+#pragma unroll
+    for (int a = 0; a < NAX; ++a) { const int ax = (NAX == 2 && a == 1) ? 2 : a; qv[a] = gp->q[ax]; rv[a] = gp->r[ax]; p0v[a] = gp->p0[ax]; }
+    const double gap = gp->gap_threshold, t_lim = gts[0] + gp->max_duration;
+    int viol = 0;
+    MoebN<NAX> incl[CPL - 1 > 0 ? CPL - 1 : 1];
+    MoebN<NAX> cur;
+    moebn_identity(cur);
+    const int first = max(lane * CPL * LCH, 1);
+    double tp = first < n ? gts[first - 1] : 0.0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const int t = lane * CPL + k;
+        const int c0 = min(t * LCH, n), c1 = min(c0 + LCH, n), s0 = max(c0, 1);
+#pragma unroll 1
+        for (int i = s0; i < c1; ++i) {
+            const double ti = gts[i];
+            const double raw = ti - tp;
+            if (raw > gap || ti > t_lim) viol = 1;
+            moebn_step(cur, qv, rv, fmax(1e-6, raw));
+            tp = ti;
+        }
+        moebn_rescale(cur);
+        if (k < CPL - 1) incl[k] = cur;
+    }
+    // inclusive warp scan of the lane totals, then the exclusive prefix of this lane
+    MoebN<NAX> tot = cur;
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {
+        MoebN<NAX> y;
+#pragma unroll
+        for (int k = 0; k < 4 * NAX; ++k) y.m[k] = __shfl_up_sync(GSF_FULL_MASK, tot.m[k], o);
+        if (lane >= o) tot = moebn_compose(y, tot);
+    }
+    MoebN<NAX> ex;
+#pragma unroll
+    for (int k = 0; k < 4 * NAX; ++k) ex.m[k] = __shfl_up_sync(GSF_FULL_MASK, tot.m[k], 1);
+    if (lane == 0) moebn_identity(ex);
+    double pl[NAX];
+#pragma unroll
+    for (int a = 0; a < NAX; ++a) pl[a] = moebn_apply(ex, a, p0v[a]);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const int t = lane * CPL + k;
+        double pk[NAX];
+#pragma unroll
+        for (int a = 0; a < NAX; ++a) pk[a] = k == 0 ? pl[a] : moebn_apply(incl[k > 0 ? k - 1 : 0], a, pl[a]);
+        if (NAX == 2) { pst[3 * t] = pk[0]; pst[3 * t + 1] = pk[0]; pst[3 * t + 2] = pk[1]; }
+        else { pst[3 * t] = pk[0]; pst[3 * t + 1] = pk[1]; pst[3 * t + 2] = pk[NAX - 1]; }
+    }
+    return __any_sync(GSF_FULL_MASK, viol);
+}
+
+constexpr int fast_min_blocks(int ct) { return ct <= 32 ? 5 : (ct == 64 ? 4 : 3); }
+
+template <int CT, int LCH>
+__global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel(const FuseArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NW = CT / 32;
+    const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
+    double* ts_s = reinterpret_cast<double*>(smem_raw);
+    double* pos_s = ts_s + cap2;
+    double* z_s = pos_s + 3 * (size_t)cap2;
+    double* sd = z_s + 3 * (size_t)cap2;
+    int* iscr = reinterpret_cast<int*>(sd + FS_INT);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) mbar_init(mbar + k, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp < NW) {
+        // ====================================================================== compute warps
+        uint32_t par_full = 0;
+        if (tid == 0 && (int)blockIdx.x < A.B) issue_trajectory_load(A, blockIdx.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+        int j = 0;
+        for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+            const long long e0 = A.offsets[b];
+            const int n = (int)(A.offsets[b + 1] - e0);
+            if (n <= 0 || n > A.cap) {
+                if (tid == 0) {
+                    A.status[b] = n <= 0 ? ST_EMPTY : ST_TOO_LONG;
+                    if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+                }
+                continue;
+            }
+            const int slot = j & 1;
+            const uint32_t kpar = (uint32_t)(j >> 1) & 1u;
+            ++j;
+            double* bc = sd + FS_BC + 48 * slot;
+            const double* pst = sd + FS_PST + 3 * CT * slot;
+            const int lead = (int)(e0 & 1);
+            double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
+            if (tid < 23) sd[FS_PRM + tid] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[tid];
+            if (tid == 32 % CT) iscr[0] = 0;
+            {
+                const int cnt = n + lead, even = cnt & ~1;
+                if ((cnt & 1) && tid < 7) {                   // odd tail element: plain copy
+                    const long long g = e0 - lead + even;
+                    if (tid == 0) ts_s[even] = A.ts[g];
+                    else if (tid < 4) pos_s[3 * even + (tid - 1)] = A.pos[3 * g + (tid - 1)];
+                    else z_s[3 * even + (tid - 4)] = A.z[3 * g + (tid - 4)];
+                }
+                if (even > 0) { mbar_wait(mbar + MB_FULL, par_full); par_full ^= 1; }
+            }
+            mbar_wait(mbar + MB_AUXRDY + slot, kpar);
+            named_sync(1, CT);
+            if (bc[30] != 0.0) {
+                // needs the general machinery: leave it to the general kernel
+                if (tid == 0) {
+                    A.status[b] = ST_DEFERRED;
+                    atomicAdd(A.defer_count, 1);
+                    if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+                }
+                named_sync(1, CT);                           // every thread has read the verdict
+                if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
+                continue;
+            }
+
+            const FuseParams& prm = *reinterpret_cast<const FuseParams*>(sd + FS_PRM);
+            const bool xy_same = prm.p0[0] == prm.p0[1] && prm.q[0] == prm.q[1] && prm.r[0] == prm.r[1];
+            const int c0 = min(tid * LCH, n), c1 = min(c0 + LCH, n);
+            const int s0 = max(c0, 1);                      // steps owned: i in [s0, c1)
+            int st = (int)bc[31];
+
+            // ------------------------------------------------------------------ pass B: gains, affine maps, residual check
+            double RC[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) RC[k] = bc[k];
+            const double sc = bc[19], t0 = bc[16], t1 = bc[17], t2 = bc[18];
+            const double thr2 = !(prm.residual_thresh > 0.0) ? -1.0 : prm.residual_thresh * prm.residual_thresh;
+            double pprev0 = 0.0, pprev1 = 0.0, pprev2 = 0.0, tprev = 0.0;
+            if (c0 < n) { const int ip = max(c0 - 1, 0); pprev0 = posS[3 * ip]; pprev1 = posS[3 * ip + 1]; pprev2 = posS[3 * ip + 2]; tprev = tsS[ip]; }
+            int nviol = 0;
+            if (c0 == 0 && thr2 > 0.0) {
+                double rx, ry, rz;
+                mat_vec(RC, posS[0], posS[1], posS[2], rx, ry, rz);
+                const double d0 = sc * rx + t0 - zS[0], d1 = sc * ry + t1 - zS[1], d2 = sc * rz + t2 - zS[2];
+                if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+            }
+            named_sync(1, CT);                               // neighbours' boundary poses are read before being overwritten
+            Aff3 aff;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { aff.a[a] = 1.0; aff.b[a] = 0.0; }
+            {
+                double P[3] = {pst[3 * tid], pst[3 * tid + 1], pst[3 * tid + 2]};
+                // y = s * M(C) * p(s0-1) + t, advanced by s*u each step: the Sim3 image used by the residual check
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                if (thr2 > 0.0 && s0 < c1) {
+                    mat_vec(RC, pprev0, pprev1, pprev2, y0, y1, y2);
+                    y0 = sc * y0 + t0; y1 = sc * y1 + t1; y2 = sc * y2 + t2;
+                }
+                const double q0 = prm.q[0], q1 = prm.q[1], q2 = prm.q[2], r0 = prm.r[0], r1 = prm.r[1], r2 = prm.r[2];
+#pragma unroll 1
+                for (int i = s0; i < c1; ++i) {
+                    const double ti = tsS[i];
+                    const double dt = fmax(1e-6, ti - tprev);
+                    tprev = ti;
+                    const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
+                    double u[3];
+                    mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u[0], u[1], u[2]);
+                    pprev0 = p0; pprev1 = p1; pprev2 = p2;
+                    const double zz[3] = {zS[3 * i], zS[3 * i + 1], zS[3 * i + 2]};
+                    if (thr2 > 0.0) {
+                        y0 = fma(sc, u[0], y0); y1 = fma(sc, u[1], y1); y2 = fma(sc, u[2], y2);
+                        const double d0 = y0 - zz[0], d1 = y1 - zz[1], d2 = y2 - zz[2];
+                        if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+                    }
+                    const double qq[3] = {q0 * dt, q1 * dt, q2 * dt};
+                    const double rr[3] = {r0, r1, r2};
+                    double kk[3], om[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        if (a == 1 && xy_same) { kk[1] = kk[0]; om[1] = om[0]; P[1] = P[0]; continue; }
+                        const double pp = P[a] + qq[a];
+                        kk[a] = pp * fast_rcp(pp + rr[a]);
+                        om[a] = 1.0 - kk[a];
+                        P[a] = om[a] * pp * om[a] + kk[a] * rr[a] * kk[a];      // Joseph form (:731)
+                    }
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const double bv = om[a] * u[a] + kk[a] * zz[a];
+                        posS[3 * i + a] = om[a]; zS[3 * i + a] = bv;
+                        aff.b[a] = om[a] * aff.b[a] + bv; aff.a[a] *= om[a];
+                    }
+                }
+            }
+            if (thr2 > 0.0) {
+                nviol = warp_sum_i(nviol);
+                if (lane == 0 && nviol) atomicAdd(iscr, nviol);
+            }
+            Aff3 aex;                                       // exclusive affine prefix inside the warp
+            aff_warp_scan(aff, lane);
+            if (NW > 1 && lane == 31) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sd[FS_AFF + warp * 6 + k] = aff.a[k]; sd[FS_AFF + warp * 6 + 3 + k] = aff.b[k]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { aex.a[k] = __shfl_up_sync(GSF_FULL_MASK, aff.a[k], 1); aex.b[k] = __shfl_up_sync(GSF_FULL_MASK, aff.b[k], 1); }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { aex.a[k] = 1.0; aex.b[k] = 0.0; }
+            }
+            named_sync(1, CT);
+
+            // ------------------------------------------------------------------ pass C: state recursion
+            {
+                Aff3 pre = aex;
+                if (NW > 1 && warp > 0) {
+                    Aff3 acc;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { acc.a[k] = sd[FS_AFF + k]; acc.b[k] = sd[FS_AFF + 3 + k]; }
+                    for (int w = 1; w < warp; ++w) {
+                        Aff3 nx;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { nx.a[k] = sd[FS_AFF + w * 6 + k]; nx.b[k] = sd[FS_AFF + w * 6 + 3 + k]; }
+                        acc = aff_compose(acc, nx);
+                    }
+                    pre = aff_compose(acc, aex);
+                }
+                double x0 = pre.a[0] * bc[13] + pre.b[0], x1 = pre.a[1] * bc[14] + pre.b[1], x2 = pre.a[2] * bc[15] + pre.b[2];
+                if (c0 == 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
+#pragma unroll 1
+                for (int i = s0; i < c1; ++i) {
+                    x0 = posS[3 * i] * x0 + zS[3 * i]; x1 = posS[3 * i + 1] * x1 + zS[3 * i + 1]; x2 = posS[3 * i + 2] * x2 + zS[3 * i + 2];
+                    zS[3 * i] = x0; zS[3 * i + 1] = x1; zS[3 * i + 2] = x2;
+                }
+            }
+            fence_proxy_async();
+            named_sync(1, CT);
+
+            // ------------------------------------------------------------------ store fused positions; stream the quaternions
+            double* gout = A.out_pos + 3 * e0;
+            const int viol_total = iscr[0];
+            if (viol_total) st |= ST_RANSAC_OUTLIERS;
+            if (tid == 0) {
+                const int m = n - lead, even = m & ~1;
+                if (even > 0) { bulk_s2g(gout + 3 * lead, zS + 3 * lead, (uint32_t)even * 24u); bulk_commit(); }
+                if (lead) { gout[0] = zS[0]; gout[1] = zS[1]; gout[2] = zS[2]; }
+                if (m & 1) {
+                    const int q = 3 * (lead + even);
+                    gout[q] = zS[q]; gout[q + 1] = zS[q + 1]; gout[q + 2] = zS[q + 2];
+                }
+                A.status[b] = st;
+                if (A.sim3_out) {
+                    double* o = A.sim3_out + 16 * (size_t)b;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
+                    o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
+                    o[13] = (double)n; o[14] = (double)n; o[15] = (double)viol_total;
+                }
+            }
+            {
+                const Quat C{bc[9], bc[10], bc[11], bc[12]};
+                const int bad = quat_rounds(A.quat + 4 * e0, A.out_quat + 4 * e0, C, tid, CT, n);
+                if (tid == 0) {
+                    bulk_wait_read();                               // shared memory is free again
+                    fence_proxy_async();
+                    if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+                }
+                named_sync(1, CT);                                  // status[b] is written; slot and scratch may be reused
+                if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
+                if (bad) atomicOr(A.status + b, ST_BAD_QUATERNION);
+            }
+        }
+    } else if (warp == NW) {
+        // ====================================================================== warp A: Umeyama sums, one to two trajectories ahead
+        int j = 0;
+        for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+            const long long e0 = A.offsets[b];
+            const int n = (int)(A.offsets[b + 1] - e0);
+            if (n <= 0 || n > A.cap) continue;
+            const int slot = j & 1, k = j >> 1;
+            ++j;
+            if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
+            const double* __restrict__ gp = A.pos + 3 * e0;
+            const double* __restrict__ gz = A.z + 3 * e0;
+            const double ps0 = gp[0], ps1 = gp[1], ps2 = gp[2], pz0 = gz[0], pz1 = gz[1], pz2 = gz[2];
+            double v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = 0.0;
+            const int npairs = (n + 1) >> 1;
+            if (!(e0 & 1)) {
+                const double2* __restrict__ gp2 = reinterpret_cast<const double2*>(gp);
+                const double2* __restrict__ gz2 = reinterpret_cast<const double2*>(gz);
+#pragma unroll 1
+                for (int p = lane; p < npairs; p += 64) {
+                    // two pose pairs per round: 12 128-bit loads in flight
+                    double2 a[2][3], c[2][3];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int pp = p + 32 * h;
+                        if (2 * pp + 1 < n) {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) { a[h][q] = __ldg(gp2 + 3 * pp + q); c[h][q] = __ldg(gz2 + 3 * pp + q); }
+                        } else if (2 * pp < n) {                    // last pose of an odd-length trajectory
+                            a[h][0] = make_double2(gp[6 * pp], gp[6 * pp + 1]); a[h][1] = make_double2(gp[6 * pp + 2], 0.0);
+                            c[h][0] = make_double2(gz[6 * pp], gz[6 * pp + 1]); c[h][1] = make_double2(gz[6 * pp + 2], 0.0);
+                            a[h][2] = make_double2(0.0, 0.0); c[h][2] = make_double2(0.0, 0.0);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int pp = p + 32 * h;
+                        if (2 * pp < n) umeyama_accumulate(v, a[h][0].x, a[h][0].y, a[h][1].x, c[h][0].x, c[h][0].y, c[h][1].x, ps0, ps1, ps2, pz0, pz1, pz2);
+                        if (2 * pp + 1 < n) umeyama_accumulate(v, a[h][1].y, a[h][2].x, a[h][2].y, c[h][1].y, c[h][2].x, c[h][2].y, ps0, ps1, ps2, pz0, pz1, pz2);
+                    }
+                }
+            } else {
+                // odd pose offset: rows are only 8-byte aligned; same pose order, 64-bit loads
+#pragma unroll 1
+                for (int p = lane; p < npairs; p += 32) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int i = 2 * p + h;
+                        if (i < n) umeyama_accumulate(v, gp[3 * i], gp[3 * i + 1], gp[3 * i + 2], gz[3 * i], gz[3 * i + 1], gz[3 * i + 2], ps0, ps1, ps2, pz0, pz1, pz2);
+                    }
+                }
+            }
+            const double total = butterfly16(v, lane);
+            double* sums = sd + FS_SUMS + 24 * slot;
+            if (!(lane & 1)) sums[butterfly16_index(lane)] = total;
+            if (lane == 1) { sums[16] = ps0; sums[17] = ps1; sums[18] = ps2; sums[19] = pz0; sums[20] = pz1; sums[21] = pz2; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mbar + MB_SUMS + slot);
+        }
+    } else {
+        // ====================================================================== warp B: covariance start values, gap/window check, Umeyama finish
+        int j = 0;
+        for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+            const long long e0 = A.offsets[b];
+            const int n = (int)(A.offsets[b + 1] - e0);
+            if (n <= 0 || n > A.cap) continue;
+            const int slot = j & 1, k = j >> 1;
+            ++j;
+            if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
+            const FuseParams* __restrict__ gprm = A.params + (A.params_per_traj ? b : 0);
+            const bool xy_same = gprm->p0[0] == gprm->p0[1] && gprm->q[0] == gprm->q[1] && gprm->r[0] == gprm->r[1];
+            double* pst = sd + FS_PST + 3 * CT * slot;
+            int general = xy_same ? cov_start_scan<2, CT, LCH>(A.ts + e0, n, gprm, lane, pst)
+                                  : cov_start_scan<3, CT, LCH>(A.ts + e0, n, gprm, lane, pst);
+            mbar_wait(mbar + MB_SUMS + slot, (uint32_t)k & 1u);
+            const double* sums = sd + FS_SUMS + 24 * slot;
+            double v[16], chk = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { v[q] = sums[q]; chk += v[q]; }
+            if (!(fabs(chk) <= 1.7976931348623157e308)) general = 1;       // NaN row (no GNSS) or non-finite input
+            if (n < 3 || n < gprm->min_samples) general = 1;
+            const Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
+            if (qnorm2(q0) == 0.0) general = 1;
+            int ust = 0;
+            double* bc = sd + FS_BC + 48 * slot;
+            if (!general) {
+                const double nn = (double)n, inv = 1.0 / nn;
+                const double ma[3] = {v[0] * inv, v[1] * inv, v[2] * inv}, mb[3] = {v[3] * inv, v[4] * inv, v[5] * inv};
+                double ms_[3], md_[3], hh[9];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { ms_[q] = sums[16 + q] + ma[q]; md_[q] = sums[19 + q] + mb[q]; }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) hh[3 * r + c] = v[6 + 3 * r + c] - nn * ma[r] * mb[c];
+                const double ss = v[15] - nn * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
+                double R[9], t[3], s = 1.0;
+                ust = umeyama_finish_ool(n, ms_, md_, hh, ss, R, t, &s);
+                if (lane == 0) {
+                    const Quat qR = quat_from_matrix(R);
+                    const Quat q0h = qunit(q0);
+                    const Quat qs0 = qunit_or_identity(qmul(qR, q0h));
+                    const Quat Cq = qmul(qs0, qconj(q0h));
+                    double M[9]; qmat(Cq, M);
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { bc[q] = M[q]; bc[20 + q] = R[q]; }
+                    bc[9] = Cq.x; bc[10] = Cq.y; bc[11] = Cq.z; bc[12] = Cq.w;
+                    double rx, ry, rz;
+                    mat_vec(R, sums[16], sums[17], sums[18], rx, ry, rz);
+                    bc[13] = s * rx + t[0]; bc[14] = s * ry + t[1]; bc[15] = s * rz + t[2];
+                    bc[16] = t[0]; bc[17] = t[1]; bc[18] = t[2]; bc[19] = s;
+                }
+            }
+            if (lane == 0) { bc[30] = general ? 1.0 : 0.0; bc[31] = (double)ust; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mbar + MB_AUXRDY + slot);
+        }
+    }
+}
+
+// Deferred-trajectory counters (one per in-flight call, recycled round-robin): module-level device
+// memory, so the *_dev entry point needs no workspace argument and allocates nothing.
+__device__ int g_defer_count[64];
+cudaError_t defer_counter(int** out) {
+    static std::atomic<unsigned> ticket{0};
+    int* base = nullptr;
+    cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_defer_count);
+    if (e != cudaSuccess) return e;
+    *out = base + (ticket.fetch_add(1) & 63u);
+    return cudaSuccess;
+}
+
+template <int CT, int LCH>
+static cudaError_t launch_fast_t(const FuseArgs& a, int num_sms, cudaStream_t stream) {
+    const size_t smem = fast_smem_bytes(a.cap, CT);
+    auto kern = fuse_fast_kernel<CT, LCH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CT + 64, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    long long grid = (long long)num_sms * per_sm;
+    if (grid > a.B) grid = a.B;
+    kern<<<(unsigned)grid, CT + 64, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// Compute threads x chunk length per instantiation (chunk lengths odd: conflict-free 8-byte shared accesses).
+static int fast_variant(int cap) {
+    const char* force = getenv("GSF_FAST_CT");                     // tuning hook
+    const int f = force ? atoi(force) : 0;
+    if (f == 128 && cap <= 128 * 9) return 128;
+    if (f == 96 && cap <= 96 * 11) return 96;
+    if (f == 64 && cap <= 64 * 9) return 64;
+    if (f == 32 && cap <= 32 * 9) return 32;
+    if (cap <= 32 * 9) return 32;
+    if (cap <= 64 * 9) return 64;
+    if (cap <= 96 * 11) return 96;
+    if (cap <= 128 * 9) return 128;
+    return 0;
+}
+bool fast_fuse_supported(int cap, int max_smem) {
+    const int ct = fast_variant(cap);
+    return ct > 0 && fast_smem_bytes(cap, ct) <= (size_t)max_smem;
+}
+cudaError_t launch_fuse_fast(const FuseArgs& a, int num_sms, cudaStream_t stream) {
+    switch (fast_variant(a.cap)) {
+        case 32: return launch_fast_t<32, 9>(a, num_sms, stream);
+        case 64: return launch_fast_t<64, 9>(a, num_sms, stream);
+        case 96: return launch_fast_t<96, 11>(a, num_sms, stream);
+        case 128: return launch_fast_t<128, 9>(a, num_sms, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace gsf

@@ -16,9 +16,15 @@ struct FuseArgs {
     int B; int cap;
     int use_tma;
     long long* phase_clock;   // debug: per-phase clock64() of block 0 (NULL = off)
+    int only_deferred;        // general kernel: process only trajectories whose status is ST_DEFERRED
+    int* defer_count;         // fast kernel: += deferred trajectories; general kernel (only_deferred): exit when 0
 };
 size_t fuse_smem_bytes(int cap);
 cudaError_t launch_fuse(const FuseArgs& a, int threads, int num_sms, cudaStream_t stream);
+// Warp-specialised fast kernel (gsf_fast.cu); fast_fuse_supported: an instantiation covers `cap`.
+bool fast_fuse_supported(int cap, int max_smem);
+cudaError_t launch_fuse_fast(const FuseArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t defer_counter(int** out);
 cudaError_t launch_ekf_strict(const double*, const double*, const double*, const double*, const long long*,
                               const FuseParams*, int, const double*, const double*, double*, double*, int*, int, cudaStream_t);
 struct UtmConst { double A_k0; double e, e2; double alpha[6], beta[6]; double lon0; double fn; };
