@@ -28,6 +28,8 @@
 
 namespace gsf {
 
+#define GSF_FSTAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW) && j == 4) A.phase_clock[k] = clock64(); } while (0)
+
 // ----------------------------------------------------------------------------- Moebius maps, NAX axes
 template <int NAX> struct MoebN { double m[4 * NAX]; };      // per axis row-major [a b; c d]
 
@@ -77,12 +79,12 @@ constexpr int FS_SUMS = 96;         // 2 slots x 24: 16 sums, pivots 16-21
 constexpr int FS_AFF = 144;         // 4 warps x 6 affine warp totals
 constexpr int FS_PRM = 168;         // FuseParams as 23 doubles (24)
 constexpr int FS_INT = 192;         // 4 ints: 0 residual violators
-constexpr int FS_MBAR = 194;        // 7 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2]
-constexpr int FS_PST = 202;         // 2 slots x CT x 3 start covariances
-constexpr int MB_FULL = 0, MB_SUMS = 1, MB_AUXRDY = 3, MB_AUXFREE = 5;
+constexpr int FS_MBAR = 194;        // 8 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2], ts_b
+constexpr int FS_PST = 202;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
+constexpr int MB_FULL = 0, MB_SUMS = 1, MB_AUXRDY = 3, MB_AUXFREE = 5, MB_TSB = 7;
 
 __host__ __device__ constexpr size_t fast_smem_bytes(int cap, int ct) {
-    return (size_t)((cap + 3) & ~1) * 56 + (size_t)(FS_PST + 6 * ct) * 8;
+    return (size_t)((cap + 3) & ~1) * 64 + (size_t)(FS_PST + 6 * ct) * 8;
 }
 
 // 16 accumulators x 32 lanes -> lane L (bit 0 clear) ends with the warp total of value idx(L):
@@ -172,342 +174,518 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
     return __any_sync(GSF_FULL_MASK, viol);
 }
 
+// one thread: TMA bulk copies of trajectory b (second and last touch of these bytes: evict_first) and an L2
+// prefetch of its quaternions (kept until the streaming quaternion pass: evict_last).
+__device__ __forceinline__ void issue_trajectory_load_hint(const FuseArgs& A, int b, double* ts_s, double* pos_s, double* z_s, uint64_t* mbar) {
+    const long long e0 = A.offsets[b];
+    const int n = (int)(A.offsets[b + 1] - e0);
+    if (n <= 0 || n > A.cap) return;
+    const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
+    const int lead = (int)(e0 & 1);
+    const int even = (n + lead) & ~1;
+    if (even > 0) {
+        mbar_expect_tx(mbar, (uint32_t)even * 56u);
+        bulk_g2s_hint(ts_s, A.ts + (e0 - lead), (uint32_t)even * 8u, mbar, pf);
+        bulk_g2s_hint(pos_s, A.pos + 3 * (e0 - lead), (uint32_t)even * 24u, mbar, pf);
+        bulk_g2s_hint(z_s, A.z + 3 * (e0 - lead), (uint32_t)even * 24u, mbar, pf);
+    }
+    const long long qn = ((long long)n * 32) & ~15ll;
+    if (qn > 0) bulk_prefetch_l2_hint(A.quat + 4 * e0, (uint32_t)qn, pl);
+}
+// Streaming quaternion pass with evict_first loads and stores (see quat_rounds).
+__device__ __forceinline__ int quat_rounds_hint(const double* __restrict__ quat_in, double* __restrict__ quat_out, const Quat& C,
+                                                int first, int stride, int n) {
+    const double2* __restrict__ qin = reinterpret_cast<const double2*>(quat_in);
+    double2* __restrict__ qout = reinterpret_cast<double2*>(quat_out);
+    const uint64_t pf = l2_policy_evict_first();
+    int bad = 0;
+    for (int i0 = first; i0 < n; i0 += 4 * stride) {
+        double2 lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * stride;
+            if (i < n) { lo[u] = ldg2_hint(qin + 2 * i, pf); hi[u] = ldg2_hint(qin + 2 * i + 1, pf); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * stride;
+            if (i < n) {
+                const Quat qi{lo[u].x, lo[u].y, hi[u].x, hi[u].y};
+                const double n2 = qnorm2(qi);
+                if (n2 == 0.0) bad = 1;                     // scipy raises here (:466); output row becomes NaN
+                const Quat r = qscale(qmul(C, qi), rsqrt(n2));
+                stg2_hint(qout + 2 * i, make_double2(r.x, r.y), pf);
+                stg2_hint(qout + 2 * i + 1, make_double2(r.z, r.w), pf);
+            }
+        }
+    }
+    return bad;
+}
+
+// next trajectory of this block (after b) with a length the kernel handles, or B
+__device__ __forceinline__ int next_valid_traj(const FuseArgs& A, int b) {
+    for (b += gridDim.x; b < A.B; b += gridDim.x) {
+        const int n = (int)(A.offsets[b + 1] - A.offsets[b]);
+        if (n > 0 && n <= A.cap) break;
+    }
+    return b;
+}
+// warp B, lane 0: bulk copy of the timestamps of trajectory b into warp B's private buffer
+__device__ __forceinline__ void issue_ts_load(const FuseArgs& A, int b, double* tsb, uint64_t* bar) {
+    const long long e0 = A.offsets[b];
+    const int n = (int)(A.offsets[b + 1] - e0);
+    const int lead = (int)(e0 & 1), even = (n + lead) & ~1;
+    mbar_expect_tx(bar, (uint32_t)even * 8u);
+    bulk_g2s_hint(tsb, A.ts + (e0 - lead), (uint32_t)even * 8u, bar, l2_policy_evict_last());
+}
+// L2 prefetch of positions + measurements of trajectory b (warp A streams them one trajectory later)
+__device__ __forceinline__ void prefetch_pos_z(const FuseArgs& A, int b) {
+    const long long e0 = A.offsets[b];
+    const int n = (int)(A.offsets[b + 1] - e0);
+    const long long lead = e0 & 1;
+    const uint32_t bytes = (uint32_t)(((long long)n + lead) * 24) & ~15u;
+    const uint64_t pl = l2_policy_evict_last();
+    if (bytes) { bulk_prefetch_l2_hint(A.pos + 3 * (e0 - lead), bytes, pl); bulk_prefetch_l2_hint(A.z + 3 * (e0 - lead), bytes, pl); }
+}
+
 constexpr int fast_min_blocks(int ct) { return ct <= 32 ? 5 : (ct == 64 ? 4 : 3); }
 
+// Pass B1 of the compute warps, steps [s0, c1) of one thread: telescoped odometry u_i = M(C)(p_i - p_{i-1})
+// written over p_i, and the residual of the Sim3 image y_i = s M(C) p_i + t against the measurement
+// (y advanced by s*u each step).  No loop-carried chain besides p_{i-1} and y.
+__device__ __forceinline__ int pass_b1_odometry(double* __restrict__ posS, const double* __restrict__ zS, const double* __restrict__ bc,
+                                                int s0, int c1, double thr2, double pprev0, double pprev1, double pprev2) {
+    double RC[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) RC[k] = bc[k];
+    const double sc = bc[19];
+    int nviol = 0;
+    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+    if (thr2 > 0.0 && s0 < c1) {
+        mat_vec(RC, pprev0, pprev1, pprev2, y0, y1, y2);
+        y0 = sc * y0 + bc[16]; y1 = sc * y1 + bc[17]; y2 = sc * y2 + bc[18];
+    }
+#pragma unroll 1
+    for (int i = s0; i < c1; ++i) {
+        const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
+        double u0, u1, u2;
+        mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u0, u1, u2);
+        pprev0 = p0; pprev1 = p1; pprev2 = p2;
+        posS[3 * i] = u0; posS[3 * i + 1] = u1; posS[3 * i + 2] = u2;
+        if (thr2 > 0.0) {
+            y0 = fma(sc, u0, y0); y1 = fma(sc, u1, y1); y2 = fma(sc, u2, y2);
+            const double d0 = y0 - zS[3 * i], d1 = y1 - zS[3 * i + 1], d2 = y2 - zS[3 * i + 2];
+            if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+        }
+    }
+    return nviol;
+}
+// Pass B2: exact per-step Joseph-form gains (:722-731) from the start covariance, affine map
+// x -> om x + (om u + k z) per axis.  Overwrites u (in pos) with om and z with om u + k z.
+// XY: x and y share P0/Q/R (the shipped CONFIG), so the y gain is the x gain.
+template <bool XY>
+__device__ __forceinline__ void pass_b2_gains(const double* __restrict__ tsS, double* __restrict__ posS, double* __restrict__ zS,
+                                              const FuseParams& prm, const double* __restrict__ pst, int s0, int c1, double tprev, Aff3& aff) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { aff.a[a] = 1.0; aff.b[a] = 0.0; }
+    double Px = pst[0], Py = pst[1], Pz = pst[2];
+    const double qx = prm.q[0], qy = prm.q[1], qz = prm.q[2], rx = prm.r[0], ry = prm.r[1], rz = prm.r[2];
+#pragma unroll 1
+    for (int i = s0; i < c1; ++i) {
+        const double ti = tsS[i];
+        const double dt = fmax(1e-6, ti - tprev);
+        tprev = ti;
+        const double u0 = posS[3 * i], u1 = posS[3 * i + 1], u2 = posS[3 * i + 2];
+        const double z0 = zS[3 * i], z1 = zS[3 * i + 1], z2 = zS[3 * i + 2];
+        double kx, ky, kz, ox, oy, oz;
+        {
+            const double pp = Px + qx * dt;
+            kx = pp * fast_rcp(pp + rx); ox = 1.0 - kx;
+            Px = ox * pp * ox + kx * rx * kx;                        // Joseph form (:731)
+        }
+        if (XY) { ky = kx; oy = ox; }
+        else {
+            const double pp = Py + qy * dt;
+            ky = pp * fast_rcp(pp + ry); oy = 1.0 - ky;
+            Py = oy * pp * oy + ky * ry * ky;
+        }
+        {
+            const double pp = Pz + qz * dt;
+            kz = pp * fast_rcp(pp + rz); oz = 1.0 - kz;
+            Pz = oz * pp * oz + kz * rz * kz;
+        }
+        const double b0 = ox * u0 + kx * z0, b1 = oy * u1 + ky * z1, b2 = oz * u2 + kz * z2;
+        posS[3 * i] = ox; posS[3 * i + 1] = oy; posS[3 * i + 2] = oz;
+        zS[3 * i] = b0; zS[3 * i + 1] = b1; zS[3 * i + 2] = b2;
+        aff.b[0] = ox * aff.b[0] + b0; aff.b[1] = oy * aff.b[1] + b1; aff.b[2] = oz * aff.b[2] + b2;
+        aff.a[0] *= ox; aff.a[1] *= oy; aff.a[2] *= oz;
+    }
+}
+
+// ====================================================================== compute warps
 template <int CT, int LCH>
-__global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel(const FuseArgs A) {
+__device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
+    // (pointers are derived from the shared array here so that the accesses compile to LDS/STS, not generic loads)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
+    double* const ts_s = reinterpret_cast<double*>(smem_raw);
+    double* const pos_s = ts_s + cap2;
+    double* const z_s = pos_s + 3 * (size_t)cap2;
+    double* const sd = z_s + 3 * (size_t)cap2;
+    int* const iscr = reinterpret_cast<int*>(sd + FS_INT);
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = CT / 32;
+    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
+
+    uint32_t par_full = 0;
+    if (tid == 0 && (int)blockIdx.x < A.B) issue_trajectory_load_hint(A, blockIdx.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+    int j = 0;
+    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+        const long long e0 = A.offsets[b];
+        const int n = (int)(A.offsets[b + 1] - e0);
+        if (n <= 0 || n > A.cap) {
+            if (tid == 0) {
+                A.status[b] = n <= 0 ? ST_EMPTY : ST_TOO_LONG;
+                if (b + (int)gridDim.x < A.B) issue_trajectory_load_hint(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+            }
+            continue;
+        }
+        const int slot = j & 1;
+        const uint32_t kpar = (uint32_t)(j >> 1) & 1u;
+        ++j;
+        GSF_FSTAMP(0);
+        double* bc = sd + FS_BC + 48 * slot;
+        const double* pst = sd + FS_PST + 3 * CT * slot;
+        const int lead = (int)(e0 & 1);
+        double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
+        if (tid < 23) sd[FS_PRM + tid] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[tid];
+        if (tid == 32 % CT) iscr[0] = 0;
+        {
+            const int cnt = n + lead, even = cnt & ~1;
+            if ((cnt & 1) && tid < 7) {                   // odd tail element: plain copy
+                const long long g = e0 - lead + even;
+                if (tid == 0) ts_s[even] = A.ts[g];
+                else if (tid < 4) pos_s[3 * even + (tid - 1)] = A.pos[3 * g + (tid - 1)];
+                else z_s[3 * even + (tid - 4)] = A.z[3 * g + (tid - 4)];
+            }
+            if (even > 0) { mbar_wait(mbar + MB_FULL, par_full); par_full ^= 1; }
+        }
+        GSF_FSTAMP(1);
+        mbar_wait(mbar + MB_AUXRDY + slot, kpar);
+        GSF_FSTAMP(2);
+        named_sync(1, CT);
+        if (bc[30] != 0.0) {
+            // needs the general machinery: leave it to the general kernel
+            if (tid == 0) {
+                A.status[b] = ST_DEFERRED;
+                atomicAdd(A.defer_count, 1);
+                if (b + (int)gridDim.x < A.B) issue_trajectory_load_hint(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+            }
+            named_sync(1, CT);                           // every thread has read the verdict
+            if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
+            continue;
+        }
+
+        const FuseParams& prm = *reinterpret_cast<const FuseParams*>(sd + FS_PRM);
+        const bool xy_same = prm.p0[0] == prm.p0[1] && prm.q[0] == prm.q[1] && prm.r[0] == prm.r[1];
+        const int c0 = min(tid * LCH, n), c1 = min(c0 + LCH, n);
+        const int s0 = max(c0, 1);                      // steps owned: i in [s0, c1)
+        int st = (int)bc[31];
+
+        // ------------------------------------------------------------------ pass B: gains, affine maps, residual check
+        const double thr2 = !(prm.residual_thresh > 0.0) ? -1.0 : prm.residual_thresh * prm.residual_thresh;
+        double pprev0 = 0.0, pprev1 = 0.0, pprev2 = 0.0, tprev = 0.0;
+        if (c0 < n) { const int ip = max(c0 - 1, 0); pprev0 = posS[3 * ip]; pprev1 = posS[3 * ip + 1]; pprev2 = posS[3 * ip + 2]; tprev = tsS[ip]; }
+        int nviol = 0;
+        if (c0 == 0 && thr2 > 0.0) {                      // pose 0 against its Sim3 image
+            double rx, ry, rz;
+            mat_vec(bc, posS[0], posS[1], posS[2], rx, ry, rz);
+            const double d0 = bc[19] * rx + bc[16] - zS[0], d1 = bc[19] * ry + bc[17] - zS[1], d2 = bc[19] * rz + bc[18] - zS[2];
+            if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+        }
+        named_sync(1, CT);                               // neighbours' boundary poses are read before being overwritten
+        nviol += pass_b1_odometry(posS, zS, bc, s0, c1, thr2, pprev0, pprev1, pprev2);
+        Aff3 aff;
+        if (xy_same) pass_b2_gains<true>(tsS, posS, zS, prm, pst + 3 * tid, s0, c1, tprev, aff);
+        else pass_b2_gains<false>(tsS, posS, zS, prm, pst + 3 * tid, s0, c1, tprev, aff);
+        if (thr2 > 0.0) {
+            nviol = warp_sum_i(nviol);
+            if (lane == 0 && nviol) atomicAdd(iscr, nviol);
+        }
+        Aff3 aex;                                       // exclusive affine prefix inside the warp
+        aff_warp_scan(aff, lane);
+        if (NW > 1 && lane == 31) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sd[FS_AFF + warp * 6 + k] = aff.a[k]; sd[FS_AFF + warp * 6 + 3 + k] = aff.b[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { aex.a[k] = __shfl_up_sync(GSF_FULL_MASK, aff.a[k], 1); aex.b[k] = __shfl_up_sync(GSF_FULL_MASK, aff.b[k], 1); }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { aex.a[k] = 1.0; aex.b[k] = 0.0; }
+        }
+        named_sync(1, CT);
+        GSF_FSTAMP(3);
+
+        // ------------------------------------------------------------------ pass C: state recursion
+        {
+            Aff3 pre = aex;
+            if (NW > 1 && warp > 0) {
+                Aff3 acc;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { acc.a[k] = sd[FS_AFF + k]; acc.b[k] = sd[FS_AFF + 3 + k]; }
+                for (int w = 1; w < warp; ++w) {
+                    Aff3 nx;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { nx.a[k] = sd[FS_AFF + w * 6 + k]; nx.b[k] = sd[FS_AFF + w * 6 + 3 + k]; }
+                    acc = aff_compose(acc, nx);
+                }
+                pre = aff_compose(acc, aex);
+            }
+            double x0 = pre.a[0] * bc[13] + pre.b[0], x1 = pre.a[1] * bc[14] + pre.b[1], x2 = pre.a[2] * bc[15] + pre.b[2];
+            if (c0 == 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
+#pragma unroll 1
+            for (int i = s0; i < c1; ++i) {
+                x0 = posS[3 * i] * x0 + zS[3 * i]; x1 = posS[3 * i + 1] * x1 + zS[3 * i + 1]; x2 = posS[3 * i + 2] * x2 + zS[3 * i + 2];
+                zS[3 * i] = x0; zS[3 * i + 1] = x1; zS[3 * i + 2] = x2;
+            }
+        }
+        fence_proxy_async();
+        named_sync(1, CT);
+        GSF_FSTAMP(4);
+
+        // ------------------------------------------------------------------ store fused positions; stream the quaternions
+        double* gout = A.out_pos + 3 * e0;
+        const int viol_total = iscr[0];
+        if (viol_total) st |= ST_RANSAC_OUTLIERS;
+        if (tid == 0) {
+            const int m = n - lead, even = m & ~1;
+            if (even > 0) { bulk_s2g_hint(gout + 3 * lead, zS + 3 * lead, (uint32_t)even * 24u, l2_policy_evict_first()); bulk_commit(); }
+            if (lead) { gout[0] = zS[0]; gout[1] = zS[1]; gout[2] = zS[2]; }
+            if (m & 1) {
+                const int q = 3 * (lead + even);
+                gout[q] = zS[q]; gout[q + 1] = zS[q + 1]; gout[q + 2] = zS[q + 2];
+            }
+            A.status[b] = st;
+            if (A.sim3_out) {
+                double* o = A.sim3_out + 16 * (size_t)b;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
+                o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
+                o[13] = (double)n; o[14] = (double)n; o[15] = (double)viol_total;
+            }
+        }
+        {
+            const Quat C{bc[9], bc[10], bc[11], bc[12]};
+            const int bad = quat_rounds_hint(A.quat + 4 * e0, A.out_quat + 4 * e0, C, tid, CT, n);
+            GSF_FSTAMP(5);
+            if (tid == 0) {
+                bulk_wait_read();                               // shared memory is free again
+                fence_proxy_async();
+                if (b + (int)gridDim.x < A.B) issue_trajectory_load_hint(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+            }
+            named_sync(1, CT);                                  // status[b] is written; slot and scratch may be reused
+            if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
+            if (bad) atomicOr(A.status + b, ST_BAD_QUATERNION);
+            GSF_FSTAMP(6);
+        }
+    }
+}
+
+template <int CT, int LCH>
+__device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
+    // (pointers are derived from the shared array here so that the accesses compile to LDS/STS, not generic loads)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
+    double* const ts_s = reinterpret_cast<double*>(smem_raw);
+    double* const pos_s = ts_s + cap2;
+    double* const z_s = pos_s + 3 * (size_t)cap2;
+    double* const sd = z_s + 3 * (size_t)cap2;
+    int* const iscr = reinterpret_cast<int*>(sd + FS_INT);
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = CT / 32;
+    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
+
+    // ====================================================================== warp A: Umeyama sums, one to two trajectories ahead
+    int j = 0;
+    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+        const long long e0 = A.offsets[b];
+        const int n = (int)(A.offsets[b + 1] - e0);
+        if (n <= 0 || n > A.cap) continue;
+        const int slot = j & 1, k = j >> 1;
+        ++j;
+        GSF_FSTAMP(16);
+        if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
+        GSF_FSTAMP(17);
+        if (lane == 0) { const int bn = next_valid_traj(A, b); if (bn < A.B) prefetch_pos_z(A, bn); }
+        const double* __restrict__ gp = A.pos + 3 * e0;
+        const double* __restrict__ gz = A.z + 3 * e0;
+        const double ps0 = gp[0], ps1 = gp[1], ps2 = gp[2], pz0 = gz[0], pz1 = gz[1], pz2 = gz[2];
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = 0.0;
+        const int npairs = (n + 1) >> 1;
+        const uint64_t pl = l2_policy_evict_last();
+        if (!(e0 & 1)) {
+            const double2* __restrict__ gp2 = reinterpret_cast<const double2*>(gp);
+            const double2* __restrict__ gz2 = reinterpret_cast<const double2*>(gz);
+#pragma unroll 1
+            for (int p = lane; p < npairs; p += 64) {
+                // two pose pairs per round: 12 128-bit loads in flight
+                double2 a[2][3], c[2][3];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pp = p + 32 * h;
+                    if (2 * pp + 1 < n) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { a[h][q] = ldg2_hint(gp2 + 3 * pp + q, pl); c[h][q] = ldg2_hint(gz2 + 3 * pp + q, pl); }
+                    } else if (2 * pp < n) {                    // last pose of an odd-length trajectory
+                        a[h][0] = make_double2(gp[6 * pp], gp[6 * pp + 1]); a[h][1] = make_double2(gp[6 * pp + 2], 0.0);
+                        c[h][0] = make_double2(gz[6 * pp], gz[6 * pp + 1]); c[h][1] = make_double2(gz[6 * pp + 2], 0.0);
+                        a[h][2] = make_double2(0.0, 0.0); c[h][2] = make_double2(0.0, 0.0);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pp = p + 32 * h;
+                    if (2 * pp < n) umeyama_accumulate(v, a[h][0].x, a[h][0].y, a[h][1].x, c[h][0].x, c[h][0].y, c[h][1].x, ps0, ps1, ps2, pz0, pz1, pz2);
+                    if (2 * pp + 1 < n) umeyama_accumulate(v, a[h][1].y, a[h][2].x, a[h][2].y, c[h][1].y, c[h][2].x, c[h][2].y, ps0, ps1, ps2, pz0, pz1, pz2);
+                }
+            }
+        } else {
+            // odd pose offset: rows are only 8-byte aligned; same pose order, 64-bit loads
+#pragma unroll 1
+            for (int p = lane; p < npairs; p += 32) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = 2 * p + h;
+                    if (i < n) umeyama_accumulate(v, gp[3 * i], gp[3 * i + 1], gp[3 * i + 2], gz[3 * i], gz[3 * i + 1], gz[3 * i + 2], ps0, ps1, ps2, pz0, pz1, pz2);
+                }
+            }
+        }
+        GSF_FSTAMP(18);
+        const double total = butterfly16(v, lane);
+        double* sums = sd + FS_SUMS + 24 * slot;
+        if (!(lane & 1)) sums[butterfly16_index(lane)] = total;
+        if (lane == 1) { sums[16] = ps0; sums[17] = ps1; sums[18] = ps2; sums[19] = pz0; sums[20] = pz1; sums[21] = pz2; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mbar + MB_SUMS + slot);
+        GSF_FSTAMP(19);
+    }
+}
+
+template <int CT, int LCH>
+__device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
+    // (pointers are derived from the shared array here so that the accesses compile to LDS/STS, not generic loads)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
+    double* const ts_s = reinterpret_cast<double*>(smem_raw);
+    double* const pos_s = ts_s + cap2;
+    double* const z_s = pos_s + 3 * (size_t)cap2;
+    double* const sd = z_s + 3 * (size_t)cap2;
+    int* const iscr = reinterpret_cast<int*>(sd + FS_INT);
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = CT / 32;
+    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
+
+    // ====================================================================== warp B: covariance start values, gap/window check, Umeyama finish
+    double* tsb = sd + FS_PST + 6 * CT;
+    uint32_t par_ts = 0;
+    {
+        int b0 = (int)blockIdx.x - (int)gridDim.x;
+        b0 = next_valid_traj(A, b0);
+        if (lane == 0 && b0 < A.B) issue_ts_load(A, b0, tsb, mbar + MB_TSB);
+    }
+    int j = 0;
+    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+        const long long e0 = A.offsets[b];
+        const int n = (int)(A.offsets[b + 1] - e0);
+        if (n <= 0 || n > A.cap) continue;
+        const int slot = j & 1, k = j >> 1;
+        ++j;
+        GSF_FSTAMP(24);
+        if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
+        GSF_FSTAMP(25);
+        const FuseParams* __restrict__ gprm = A.params + (A.params_per_traj ? b : 0);
+        const bool xy_same = gprm->p0[0] == gprm->p0[1] && gprm->q[0] == gprm->q[1] && gprm->r[0] == gprm->r[1];
+        double* pst = sd + FS_PST + 3 * CT * slot;
+        {
+            const int lead = (int)(e0 & 1), cnt = n + lead, even = cnt & ~1;
+            if ((cnt & 1) && lane == 0) tsb[even] = A.ts[e0 - lead + even];      // odd tail element: plain copy
+            mbar_wait(mbar + MB_TSB, par_ts); par_ts ^= 1;
+            __syncwarp();
+        }
+        int general = xy_same ? cov_start_scan<2, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst)
+                              : cov_start_scan<3, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst);
+        __syncwarp();
+        if (lane == 0) { const int bn = next_valid_traj(A, b); if (bn < A.B) issue_ts_load(A, bn, tsb, mbar + MB_TSB); }
+        GSF_FSTAMP(26);
+        mbar_wait(mbar + MB_SUMS + slot, (uint32_t)k & 1u);
+        GSF_FSTAMP(27);
+        const double* sums = sd + FS_SUMS + 24 * slot;
+        double v[16], chk = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { v[q] = sums[q]; chk += v[q]; }
+        if (!(fabs(chk) <= 1.7976931348623157e308)) general = 1;       // NaN row (no GNSS) or non-finite input
+        if (n < 3 || n < gprm->min_samples) general = 1;
+        const Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
+        if (qnorm2(q0) == 0.0) general = 1;
+        int ust = 0;
+        double* bc = sd + FS_BC + 48 * slot;
+        if (!general) {
+            const double nn = (double)n, inv = 1.0 / nn;
+            const double ma[3] = {v[0] * inv, v[1] * inv, v[2] * inv}, mb[3] = {v[3] * inv, v[4] * inv, v[5] * inv};
+            double ms_[3], md_[3], hh[9];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { ms_[q] = sums[16 + q] + ma[q]; md_[q] = sums[19 + q] + mb[q]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) hh[3 * r + c] = v[6 + 3 * r + c] - nn * ma[r] * mb[c];
+            const double ss = v[15] - nn * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
+            double R[9], t[3], s = 1.0;
+            ust = umeyama_finish_ool(n, ms_, md_, hh, ss, R, t, &s);
+            if (lane == 0) {
+                const Quat qR = quat_from_matrix(R);
+                const Quat q0h = qunit(q0);
+                const Quat qs0 = qunit_or_identity(qmul(qR, q0h));
+                const Quat Cq = qmul(qs0, qconj(q0h));
+                double M[9]; qmat(Cq, M);
+#pragma unroll
+                for (int q = 0; q < 9; ++q) { bc[q] = M[q]; bc[20 + q] = R[q]; }
+                bc[9] = Cq.x; bc[10] = Cq.y; bc[11] = Cq.z; bc[12] = Cq.w;
+                double rx, ry, rz;
+                mat_vec(R, sums[16], sums[17], sums[18], rx, ry, rz);
+                bc[13] = s * rx + t[0]; bc[14] = s * ry + t[1]; bc[15] = s * rz + t[2];
+                bc[16] = t[0]; bc[17] = t[1]; bc[18] = t[2]; bc[19] = s;
+            }
+        }
+        if (lane == 0) { bc[30] = general ? 1.0 : 0.0; bc[31] = (double)ust; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mbar + MB_AUXRDY + slot);
+        GSF_FSTAMP(28);
+    }
+}
+
+template <int CT, int LCH>
+__global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel(const __grid_constant__ FuseArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NW = CT / 32;
-    const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
-    double* ts_s = reinterpret_cast<double*>(smem_raw);
-    double* pos_s = ts_s + cap2;
-    double* z_s = pos_s + 3 * (size_t)cap2;
-    double* sd = z_s + 3 * (size_t)cap2;
-    int* iscr = reinterpret_cast<int*>(sd + FS_INT);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
+    const int cap2 = (A.cap + 3) & ~1;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smem_raw) + 7 * (size_t)cap2 + FS_MBAR);
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) mbar_init(mbar + k, 1);
+        for (int k = 0; k < 8; ++k) mbar_init(mbar + k, 1);
         fence_mbar_init();
     }
     __syncthreads();
-
-    if (warp < NW) {
-        // ====================================================================== compute warps
-        uint32_t par_full = 0;
-        if (tid == 0 && (int)blockIdx.x < A.B) issue_trajectory_load(A, blockIdx.x, ts_s, pos_s, z_s, mbar + MB_FULL);
-        int j = 0;
-        for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-            const long long e0 = A.offsets[b];
-            const int n = (int)(A.offsets[b + 1] - e0);
-            if (n <= 0 || n > A.cap) {
-                if (tid == 0) {
-                    A.status[b] = n <= 0 ? ST_EMPTY : ST_TOO_LONG;
-                    if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
-                }
-                continue;
-            }
-            const int slot = j & 1;
-            const uint32_t kpar = (uint32_t)(j >> 1) & 1u;
-            ++j;
-            double* bc = sd + FS_BC + 48 * slot;
-            const double* pst = sd + FS_PST + 3 * CT * slot;
-            const int lead = (int)(e0 & 1);
-            double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
-            if (tid < 23) sd[FS_PRM + tid] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[tid];
-            if (tid == 32 % CT) iscr[0] = 0;
-            {
-                const int cnt = n + lead, even = cnt & ~1;
-                if ((cnt & 1) && tid < 7) {                   // odd tail element: plain copy
-                    const long long g = e0 - lead + even;
-                    if (tid == 0) ts_s[even] = A.ts[g];
-                    else if (tid < 4) pos_s[3 * even + (tid - 1)] = A.pos[3 * g + (tid - 1)];
-                    else z_s[3 * even + (tid - 4)] = A.z[3 * g + (tid - 4)];
-                }
-                if (even > 0) { mbar_wait(mbar + MB_FULL, par_full); par_full ^= 1; }
-            }
-            mbar_wait(mbar + MB_AUXRDY + slot, kpar);
-            named_sync(1, CT);
-            if (bc[30] != 0.0) {
-                // needs the general machinery: leave it to the general kernel
-                if (tid == 0) {
-                    A.status[b] = ST_DEFERRED;
-                    atomicAdd(A.defer_count, 1);
-                    if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
-                }
-                named_sync(1, CT);                           // every thread has read the verdict
-                if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
-                continue;
-            }
-
-            const FuseParams& prm = *reinterpret_cast<const FuseParams*>(sd + FS_PRM);
-            const bool xy_same = prm.p0[0] == prm.p0[1] && prm.q[0] == prm.q[1] && prm.r[0] == prm.r[1];
-            const int c0 = min(tid * LCH, n), c1 = min(c0 + LCH, n);
-            const int s0 = max(c0, 1);                      // steps owned: i in [s0, c1)
-            int st = (int)bc[31];
-
-            // ------------------------------------------------------------------ pass B: gains, affine maps, residual check
-            double RC[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) RC[k] = bc[k];
-            const double sc = bc[19], t0 = bc[16], t1 = bc[17], t2 = bc[18];
-            const double thr2 = !(prm.residual_thresh > 0.0) ? -1.0 : prm.residual_thresh * prm.residual_thresh;
-            double pprev0 = 0.0, pprev1 = 0.0, pprev2 = 0.0, tprev = 0.0;
-            if (c0 < n) { const int ip = max(c0 - 1, 0); pprev0 = posS[3 * ip]; pprev1 = posS[3 * ip + 1]; pprev2 = posS[3 * ip + 2]; tprev = tsS[ip]; }
-            int nviol = 0;
-            if (c0 == 0 && thr2 > 0.0) {
-                double rx, ry, rz;
-                mat_vec(RC, posS[0], posS[1], posS[2], rx, ry, rz);
-                const double d0 = sc * rx + t0 - zS[0], d1 = sc * ry + t1 - zS[1], d2 = sc * rz + t2 - zS[2];
-                if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
-            }
-            named_sync(1, CT);                               // neighbours' boundary poses are read before being overwritten
-            Aff3 aff;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { aff.a[a] = 1.0; aff.b[a] = 0.0; }
-            {
-                double P[3] = {pst[3 * tid], pst[3 * tid + 1], pst[3 * tid + 2]};
-                // y = s * M(C) * p(s0-1) + t, advanced by s*u each step: the Sim3 image used by the residual check
-                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-                if (thr2 > 0.0 && s0 < c1) {
-                    mat_vec(RC, pprev0, pprev1, pprev2, y0, y1, y2);
-                    y0 = sc * y0 + t0; y1 = sc * y1 + t1; y2 = sc * y2 + t2;
-                }
-                const double q0 = prm.q[0], q1 = prm.q[1], q2 = prm.q[2], r0 = prm.r[0], r1 = prm.r[1], r2 = prm.r[2];
-#pragma unroll 1
-                for (int i = s0; i < c1; ++i) {
-                    const double ti = tsS[i];
-                    const double dt = fmax(1e-6, ti - tprev);
-                    tprev = ti;
-                    const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
-                    double u[3];
-                    mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u[0], u[1], u[2]);
-                    pprev0 = p0; pprev1 = p1; pprev2 = p2;
-                    const double zz[3] = {zS[3 * i], zS[3 * i + 1], zS[3 * i + 2]};
-                    if (thr2 > 0.0) {
-                        y0 = fma(sc, u[0], y0); y1 = fma(sc, u[1], y1); y2 = fma(sc, u[2], y2);
-                        const double d0 = y0 - zz[0], d1 = y1 - zz[1], d2 = y2 - zz[2];
-                        if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
-                    }
-                    const double qq[3] = {q0 * dt, q1 * dt, q2 * dt};
-                    const double rr[3] = {r0, r1, r2};
-                    double kk[3], om[3];
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        if (a == 1 && xy_same) { kk[1] = kk[0]; om[1] = om[0]; P[1] = P[0]; continue; }
-                        const double pp = P[a] + qq[a];
-                        kk[a] = pp * fast_rcp(pp + rr[a]);
-                        om[a] = 1.0 - kk[a];
-                        P[a] = om[a] * pp * om[a] + kk[a] * rr[a] * kk[a];      // Joseph form (:731)
-                    }
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const double bv = om[a] * u[a] + kk[a] * zz[a];
-                        posS[3 * i + a] = om[a]; zS[3 * i + a] = bv;
-                        aff.b[a] = om[a] * aff.b[a] + bv; aff.a[a] *= om[a];
-                    }
-                }
-            }
-            if (thr2 > 0.0) {
-                nviol = warp_sum_i(nviol);
-                if (lane == 0 && nviol) atomicAdd(iscr, nviol);
-            }
-            Aff3 aex;                                       // exclusive affine prefix inside the warp
-            aff_warp_scan(aff, lane);
-            if (NW > 1 && lane == 31) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { sd[FS_AFF + warp * 6 + k] = aff.a[k]; sd[FS_AFF + warp * 6 + 3 + k] = aff.b[k]; }
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { aex.a[k] = __shfl_up_sync(GSF_FULL_MASK, aff.a[k], 1); aex.b[k] = __shfl_up_sync(GSF_FULL_MASK, aff.b[k], 1); }
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { aex.a[k] = 1.0; aex.b[k] = 0.0; }
-            }
-            named_sync(1, CT);
-
-            // ------------------------------------------------------------------ pass C: state recursion
-            {
-                Aff3 pre = aex;
-                if (NW > 1 && warp > 0) {
-                    Aff3 acc;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { acc.a[k] = sd[FS_AFF + k]; acc.b[k] = sd[FS_AFF + 3 + k]; }
-                    for (int w = 1; w < warp; ++w) {
-                        Aff3 nx;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { nx.a[k] = sd[FS_AFF + w * 6 + k]; nx.b[k] = sd[FS_AFF + w * 6 + 3 + k]; }
-                        acc = aff_compose(acc, nx);
-                    }
-                    pre = aff_compose(acc, aex);
-                }
-                double x0 = pre.a[0] * bc[13] + pre.b[0], x1 = pre.a[1] * bc[14] + pre.b[1], x2 = pre.a[2] * bc[15] + pre.b[2];
-                if (c0 == 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
-#pragma unroll 1
-                for (int i = s0; i < c1; ++i) {
-                    x0 = posS[3 * i] * x0 + zS[3 * i]; x1 = posS[3 * i + 1] * x1 + zS[3 * i + 1]; x2 = posS[3 * i + 2] * x2 + zS[3 * i + 2];
-                    zS[3 * i] = x0; zS[3 * i + 1] = x1; zS[3 * i + 2] = x2;
-                }
-            }
-            fence_proxy_async();
-            named_sync(1, CT);
-
-            // ------------------------------------------------------------------ store fused positions; stream the quaternions
-            double* gout = A.out_pos + 3 * e0;
-            const int viol_total = iscr[0];
-            if (viol_total) st |= ST_RANSAC_OUTLIERS;
-            if (tid == 0) {
-                const int m = n - lead, even = m & ~1;
-                if (even > 0) { bulk_s2g(gout + 3 * lead, zS + 3 * lead, (uint32_t)even * 24u); bulk_commit(); }
-                if (lead) { gout[0] = zS[0]; gout[1] = zS[1]; gout[2] = zS[2]; }
-                if (m & 1) {
-                    const int q = 3 * (lead + even);
-                    gout[q] = zS[q]; gout[q + 1] = zS[q + 1]; gout[q + 2] = zS[q + 2];
-                }
-                A.status[b] = st;
-                if (A.sim3_out) {
-                    double* o = A.sim3_out + 16 * (size_t)b;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
-                    o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
-                    o[13] = (double)n; o[14] = (double)n; o[15] = (double)viol_total;
-                }
-            }
-            {
-                const Quat C{bc[9], bc[10], bc[11], bc[12]};
-                const int bad = quat_rounds(A.quat + 4 * e0, A.out_quat + 4 * e0, C, tid, CT, n);
-                if (tid == 0) {
-                    bulk_wait_read();                               // shared memory is free again
-                    fence_proxy_async();
-                    if (b + (int)gridDim.x < A.B) issue_trajectory_load(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
-                }
-                named_sync(1, CT);                                  // status[b] is written; slot and scratch may be reused
-                if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
-                if (bad) atomicOr(A.status + b, ST_BAD_QUATERNION);
-            }
-        }
-    } else if (warp == NW) {
-        // ====================================================================== warp A: Umeyama sums, one to two trajectories ahead
-        int j = 0;
-        for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-            const long long e0 = A.offsets[b];
-            const int n = (int)(A.offsets[b + 1] - e0);
-            if (n <= 0 || n > A.cap) continue;
-            const int slot = j & 1, k = j >> 1;
-            ++j;
-            if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
-            const double* __restrict__ gp = A.pos + 3 * e0;
-            const double* __restrict__ gz = A.z + 3 * e0;
-            const double ps0 = gp[0], ps1 = gp[1], ps2 = gp[2], pz0 = gz[0], pz1 = gz[1], pz2 = gz[2];
-            double v[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = 0.0;
-            const int npairs = (n + 1) >> 1;
-            if (!(e0 & 1)) {
-                const double2* __restrict__ gp2 = reinterpret_cast<const double2*>(gp);
-                const double2* __restrict__ gz2 = reinterpret_cast<const double2*>(gz);
-#pragma unroll 1
-                for (int p = lane; p < npairs; p += 64) {
-                    // two pose pairs per round: 12 128-bit loads in flight
-                    double2 a[2][3], c[2][3];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int pp = p + 32 * h;
-                        if (2 * pp + 1 < n) {
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) { a[h][q] = __ldg(gp2 + 3 * pp + q); c[h][q] = __ldg(gz2 + 3 * pp + q); }
-                        } else if (2 * pp < n) {                    // last pose of an odd-length trajectory
-                            a[h][0] = make_double2(gp[6 * pp], gp[6 * pp + 1]); a[h][1] = make_double2(gp[6 * pp + 2], 0.0);
-                            c[h][0] = make_double2(gz[6 * pp], gz[6 * pp + 1]); c[h][1] = make_double2(gz[6 * pp + 2], 0.0);
-                            a[h][2] = make_double2(0.0, 0.0); c[h][2] = make_double2(0.0, 0.0);
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int pp = p + 32 * h;
-                        if (2 * pp < n) umeyama_accumulate(v, a[h][0].x, a[h][0].y, a[h][1].x, c[h][0].x, c[h][0].y, c[h][1].x, ps0, ps1, ps2, pz0, pz1, pz2);
-                        if (2 * pp + 1 < n) umeyama_accumulate(v, a[h][1].y, a[h][2].x, a[h][2].y, c[h][1].y, c[h][2].x, c[h][2].y, ps0, ps1, ps2, pz0, pz1, pz2);
-                    }
-                }
-            } else {
-                // odd pose offset: rows are only 8-byte aligned; same pose order, 64-bit loads
-#pragma unroll 1
-                for (int p = lane; p < npairs; p += 32) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int i = 2 * p + h;
-                        if (i < n) umeyama_accumulate(v, gp[3 * i], gp[3 * i + 1], gp[3 * i + 2], gz[3 * i], gz[3 * i + 1], gz[3 * i + 2], ps0, ps1, ps2, pz0, pz1, pz2);
-                    }
-                }
-            }
-            const double total = butterfly16(v, lane);
-            double* sums = sd + FS_SUMS + 24 * slot;
-            if (!(lane & 1)) sums[butterfly16_index(lane)] = total;
-            if (lane == 1) { sums[16] = ps0; sums[17] = ps1; sums[18] = ps2; sums[19] = pz0; sums[20] = pz1; sums[21] = pz2; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(mbar + MB_SUMS + slot);
-        }
-    } else {
-        // ====================================================================== warp B: covariance start values, gap/window check, Umeyama finish
-        int j = 0;
-        for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-            const long long e0 = A.offsets[b];
-            const int n = (int)(A.offsets[b + 1] - e0);
-            if (n <= 0 || n > A.cap) continue;
-            const int slot = j & 1, k = j >> 1;
-            ++j;
-            if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
-            const FuseParams* __restrict__ gprm = A.params + (A.params_per_traj ? b : 0);
-            const bool xy_same = gprm->p0[0] == gprm->p0[1] && gprm->q[0] == gprm->q[1] && gprm->r[0] == gprm->r[1];
-            double* pst = sd + FS_PST + 3 * CT * slot;
-            int general = xy_same ? cov_start_scan<2, CT, LCH>(A.ts + e0, n, gprm, lane, pst)
-                                  : cov_start_scan<3, CT, LCH>(A.ts + e0, n, gprm, lane, pst);
-            mbar_wait(mbar + MB_SUMS + slot, (uint32_t)k & 1u);
-            const double* sums = sd + FS_SUMS + 24 * slot;
-            double v[16], chk = 0.0;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) { v[q] = sums[q]; chk += v[q]; }
-            if (!(fabs(chk) <= 1.7976931348623157e308)) general = 1;       // NaN row (no GNSS) or non-finite input
-            if (n < 3 || n < gprm->min_samples) general = 1;
-            const Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
-            if (qnorm2(q0) == 0.0) general = 1;
-            int ust = 0;
-            double* bc = sd + FS_BC + 48 * slot;
-            if (!general) {
-                const double nn = (double)n, inv = 1.0 / nn;
-                const double ma[3] = {v[0] * inv, v[1] * inv, v[2] * inv}, mb[3] = {v[3] * inv, v[4] * inv, v[5] * inv};
-                double ms_[3], md_[3], hh[9];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) { ms_[q] = sums[16 + q] + ma[q]; md_[q] = sums[19 + q] + mb[q]; }
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) hh[3 * r + c] = v[6 + 3 * r + c] - nn * ma[r] * mb[c];
-                const double ss = v[15] - nn * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
-                double R[9], t[3], s = 1.0;
-                ust = umeyama_finish_ool(n, ms_, md_, hh, ss, R, t, &s);
-                if (lane == 0) {
-                    const Quat qR = quat_from_matrix(R);
-                    const Quat q0h = qunit(q0);
-                    const Quat qs0 = qunit_or_identity(qmul(qR, q0h));
-                    const Quat Cq = qmul(qs0, qconj(q0h));
-                    double M[9]; qmat(Cq, M);
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) { bc[q] = M[q]; bc[20 + q] = R[q]; }
-                    bc[9] = Cq.x; bc[10] = Cq.y; bc[11] = Cq.z; bc[12] = Cq.w;
-                    double rx, ry, rz;
-                    mat_vec(R, sums[16], sums[17], sums[18], rx, ry, rz);
-                    bc[13] = s * rx + t[0]; bc[14] = s * ry + t[1]; bc[15] = s * rz + t[2];
-                    bc[16] = t[0]; bc[17] = t[1]; bc[18] = t[2]; bc[19] = s;
-                }
-            }
-            if (lane == 0) { bc[30] = general ? 1.0 : 0.0; bc[31] = (double)ust; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(mbar + MB_AUXRDY + slot);
-        }
-    }
+    if (warp < NW) fast_compute_role<CT, LCH>(A);
+    else if (warp == NW) fast_sums_role<CT, LCH>(A);
+    else fast_scan_svd_role<CT, LCH>(A);
 }
 
 // Deferred-trajectory counters (one per in-flight call, recycled round-robin): module-level device
