@@ -6,8 +6,9 @@ pts/s at 1/2/4/8 B200; % HBM roofline").
 
 Workload (default ``config3``): 2^20 synthetic trajectories x 1000 poses (BASELINE.json
 configs[2]), generated on the device, resident in HBM, sharded by trajectory across the N
-ranks (strong scaling: total work fixed).  One step = ONE launch of gsf_fuse_batched_dev over
-the rank's shard: Sim3 point selection + Umeyama + all-points residual check + EKF/RTS for
+ranks (strong scaling: total work fixed).  One step = ONE call of gsf_fuse_batched_dev over
+the rank's shard (two kernel launches: the warp-specialised fast kernel, then the general
+kernel over whatever the fast one deferred): Sim3 point selection + Umeyama + all-points residual check + EKF/RTS for
 every trajectory (N-1 pose updates and N Sim3-aligned points per trajectory).
 Prints one JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
 """
@@ -236,7 +237,8 @@ def main():
     launch_ms = statistics.mean(per_launch_ms)
     achieved = B_res * n * BYTES_PER_POSE / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "fuse_traj_kernel",
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "fuse_fast_kernel (+ the general fuse_traj_kernel pass over deferred trajectories: none in this workload)",
                 "algorithmic_bytes_per_launch": B_res * n * BYTES_PER_POSE, "launch_ms": launch_ms}
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):          # DRAM bytes per trajectory from the committed ncu --set full capture, scaled to this launch
@@ -324,7 +326,7 @@ def main():
                        "sim3": "selection + Umeyama + residual check inside the same kernel", "nonzero_status": bad},
             "sim3_aligned_points_per_s": sim3_pts,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * passes, "ate": ate,
+            "gpu_launches": 2 * args.steps * passes, "ate": ate,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -28,6 +28,9 @@
 
 namespace gsf {
 
+#ifndef GSF_QUAT_U
+#define GSF_QUAT_U 6
+#endif
 #define GSF_FSTAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW) && j == 4) A.phase_clock[k] = clock64(); } while (0)
 
 // ----------------------------------------------------------------------------- Moebius maps, NAX axes
@@ -131,6 +134,7 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
     moebn_identity(cur);
     const int first = max(lane * CPL * LCH, 1);
     double tp = first < n ? gts[first - 1] : 0.0;
+    // (rolled step loop: straight-line code measured slower here -- instruction fetch, not the 2x2 chain, bounds it)
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
         const int t = lane * CPL + k;
@@ -176,9 +180,7 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
 
 // one thread: TMA bulk copies of trajectory b (second and last touch of these bytes: evict_first) and an L2
 // prefetch of its quaternions (kept until the streaming quaternion pass: evict_last).
-__device__ __forceinline__ void issue_trajectory_load_hint(const FuseArgs& A, int b, double* ts_s, double* pos_s, double* z_s, uint64_t* mbar) {
-    const long long e0 = A.offsets[b];
-    const int n = (int)(A.offsets[b + 1] - e0);
+__device__ __forceinline__ void issue_trajectory_load_hint(const FuseArgs& A, long long e0, int n, double* ts_s, double* pos_s, double* z_s, uint64_t* mbar) {
     if (n <= 0 || n > A.cap) return;
     const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
     const int lead = (int)(e0 & 1);
@@ -192,22 +194,25 @@ __device__ __forceinline__ void issue_trajectory_load_hint(const FuseArgs& A, in
     const long long qn = ((long long)n * 32) & ~15ll;
     if (qn > 0) bulk_prefetch_l2_hint(A.quat + 4 * e0, (uint32_t)qn, pl);
 }
-// Streaming quaternion pass with evict_first loads and stores (see quat_rounds).
+// Streaming quaternion pass q_state[i] = C (x) q_hat[i] (see quat_rounds) with evict_first loads and
+// stores, U poses in flight per thread.
+template <int U>
 __device__ __forceinline__ int quat_rounds_hint(const double* __restrict__ quat_in, double* __restrict__ quat_out, const Quat& C,
                                                 int first, int stride, int n) {
     const double2* __restrict__ qin = reinterpret_cast<const double2*>(quat_in);
     double2* __restrict__ qout = reinterpret_cast<double2*>(quat_out);
     const uint64_t pf = l2_policy_evict_first();
     int bad = 0;
-    for (int i0 = first; i0 < n; i0 += 4 * stride) {
-        double2 lo[4], hi[4];
+#pragma unroll 1
+    for (int i0 = first; i0 < n; i0 += U * stride) {
+        double2 lo[U], hi[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int i = i0 + u * stride;
             if (i < n) { lo[u] = ldg2_hint(qin + 2 * i, pf); hi[u] = ldg2_hint(qin + 2 * i + 1, pf); }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int i = i0 + u * stride;
             if (i < n) {
                 const Quat qi{lo[u].x, lo[u].y, hi[u].x, hi[u].y};
@@ -339,15 +344,21 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
     uint32_t par_full = 0;
-    if (tid == 0 && (int)blockIdx.x < A.B) issue_trajectory_load_hint(A, blockIdx.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+    // offsets of the next trajectory are fetched one iteration ahead (their latency would otherwise stall every warp)
+    long long o0 = 0, o1 = 0;
+    if ((int)blockIdx.x < A.B) { o0 = A.offsets[blockIdx.x]; o1 = A.offsets[blockIdx.x + 1]; }
+    if (tid == 0 && (int)blockIdx.x < A.B) issue_trajectory_load_hint(A, o0, (int)(o1 - o0), ts_s, pos_s, z_s, mbar + MB_FULL);
     int j = 0;
     for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        const long long e0 = A.offsets[b];
-        const int n = (int)(A.offsets[b + 1] - e0);
+        const long long e0 = o0;
+        const int n = (int)(o1 - o0);
+        const bool has_next = b + (int)gridDim.x < A.B;
+        if (has_next) { o0 = A.offsets[b + gridDim.x]; o1 = A.offsets[b + gridDim.x + 1]; }
+        const int n_next = (int)(o1 - o0);
         if (n <= 0 || n > A.cap) {
             if (tid == 0) {
                 A.status[b] = n <= 0 ? ST_EMPTY : ST_TOO_LONG;
-                if (b + (int)gridDim.x < A.B) issue_trajectory_load_hint(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+                if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
             }
             continue;
         }
@@ -380,7 +391,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
             if (tid == 0) {
                 A.status[b] = ST_DEFERRED;
                 atomicAdd(A.defer_count, 1);
-                if (b + (int)gridDim.x < A.B) issue_trajectory_load_hint(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+                if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
             }
             named_sync(1, CT);                           // every thread has read the verdict
             if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
@@ -478,12 +489,12 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
         }
         {
             const Quat C{bc[9], bc[10], bc[11], bc[12]};
-            const int bad = quat_rounds_hint(A.quat + 4 * e0, A.out_quat + 4 * e0, C, tid, CT, n);
+            const int bad = quat_rounds_hint<GSF_QUAT_U>(A.quat + 4 * e0, A.out_quat + 4 * e0, C, tid, CT, n);
             GSF_FSTAMP(5);
             if (tid == 0) {
                 bulk_wait_read();                               // shared memory is free again
                 fence_proxy_async();
-                if (b + (int)gridDim.x < A.B) issue_trajectory_load_hint(A, b + gridDim.x, ts_s, pos_s, z_s, mbar + MB_FULL);
+                if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
             }
             named_sync(1, CT);                                  // status[b] is written; slot and scratch may be reused
             if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
@@ -510,9 +521,12 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
 
     // ====================================================================== warp A: Umeyama sums, one to two trajectories ahead
     int j = 0;
+    long long o0 = 0, o1 = 0;
+    if ((int)blockIdx.x < A.B) { o0 = A.offsets[blockIdx.x]; o1 = A.offsets[blockIdx.x + 1]; }
     for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        const long long e0 = A.offsets[b];
-        const int n = (int)(A.offsets[b + 1] - e0);
+        const long long e0 = o0;
+        const int n = (int)(o1 - o0);
+        if (b + (int)gridDim.x < A.B) { o0 = A.offsets[b + gridDim.x]; o1 = A.offsets[b + gridDim.x + 1]; }
         if (n <= 0 || n > A.cap) continue;
         const int slot = j & 1, k = j >> 1;
         ++j;
@@ -526,17 +540,18 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
         double v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = 0.0;
+        constexpr int NP = 2;                               // pose pairs in flight per lane
         const int npairs = (n + 1) >> 1;
         const uint64_t pl = l2_policy_evict_last();
         if (!(e0 & 1)) {
             const double2* __restrict__ gp2 = reinterpret_cast<const double2*>(gp);
             const double2* __restrict__ gz2 = reinterpret_cast<const double2*>(gz);
 #pragma unroll 1
-            for (int p = lane; p < npairs; p += 64) {
-                // two pose pairs per round: 12 128-bit loads in flight
-                double2 a[2][3], c[2][3];
+            for (int p = lane; p < npairs; p += 32 * NP) {
+                // NP pose pairs per round: 6 NP 128-bit loads in flight
+                double2 a[NP][3], c[NP][3];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < NP; ++h) {
                     const int pp = p + 32 * h;
                     if (2 * pp + 1 < n) {
 #pragma unroll
@@ -548,7 +563,7 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
                     }
                 }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < NP; ++h) {
                     const int pp = p + 32 * h;
                     if (2 * pp < n) umeyama_accumulate(v, a[h][0].x, a[h][0].y, a[h][1].x, c[h][0].x, c[h][0].y, c[h][1].x, ps0, ps1, ps2, pz0, pz1, pz2);
                     if (2 * pp + 1 < n) umeyama_accumulate(v, a[h][1].y, a[h][2].x, a[h][2].y, c[h][1].y, c[h][2].x, c[h][2].y, ps0, ps1, ps2, pz0, pz1, pz2);
@@ -600,9 +615,12 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
         if (lane == 0 && b0 < A.B) issue_ts_load(A, b0, tsb, mbar + MB_TSB);
     }
     int j = 0;
+    long long o0 = 0, o1 = 0;
+    if ((int)blockIdx.x < A.B) { o0 = A.offsets[blockIdx.x]; o1 = A.offsets[blockIdx.x + 1]; }
     for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        const long long e0 = A.offsets[b];
-        const int n = (int)(A.offsets[b + 1] - e0);
+        const long long e0 = o0;
+        const int n = (int)(o1 - o0);
+        if (b + (int)gridDim.x < A.B) { o0 = A.offsets[b + gridDim.x]; o1 = A.offsets[b + gridDim.x + 1]; }
         if (n <= 0 || n > A.cap) continue;
         const int slot = j & 1, k = j >> 1;
         ++j;
