@@ -178,11 +178,10 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
     return __any_sync(GSF_FULL_MASK, viol);
 }
 
-// one thread: TMA bulk copies of trajectory b (second and last touch of these bytes: evict_first) and an L2
-// prefetch of its quaternions (kept until the streaming quaternion pass: evict_last).
+// one thread: TMA bulk copies of a trajectory (second and last touch of these bytes: evict_first)
 __device__ __forceinline__ void issue_trajectory_load_hint(const FuseArgs& A, long long e0, int n, double* ts_s, double* pos_s, double* z_s, uint64_t* mbar) {
     if (n <= 0 || n > A.cap) return;
-    const uint64_t pf = l2_policy_evict_first(), pl = l2_policy_evict_last();
+    const uint64_t pf = l2_policy_evict_first();
     const int lead = (int)(e0 & 1);
     const int even = (n + lead) & ~1;
     if (even > 0) {
@@ -191,8 +190,6 @@ __device__ __forceinline__ void issue_trajectory_load_hint(const FuseArgs& A, lo
         bulk_g2s_hint(pos_s, A.pos + 3 * (e0 - lead), (uint32_t)even * 24u, mbar, pf);
         bulk_g2s_hint(z_s, A.z + 3 * (e0 - lead), (uint32_t)even * 24u, mbar, pf);
     }
-    const long long qn = ((long long)n * 32) & ~15ll;
-    if (qn > 0) bulk_prefetch_l2_hint(A.quat + 4 * e0, (uint32_t)qn, pl);
 }
 // Streaming quaternion pass q_state[i] = C (x) q_hat[i] (see quat_rounds) with evict_first loads and
 // stores, U poses in flight per thread.
@@ -243,10 +240,8 @@ __device__ __forceinline__ void issue_ts_load(const FuseArgs& A, int b, double* 
     mbar_expect_tx(bar, (uint32_t)even * 8u);
     bulk_g2s_hint(tsb, A.ts + (e0 - lead), (uint32_t)even * 8u, bar, l2_policy_evict_last());
 }
-// L2 prefetch of positions + measurements of trajectory b (warp A streams them one trajectory later)
-__device__ __forceinline__ void prefetch_pos_z(const FuseArgs& A, int b) {
-    const long long e0 = A.offsets[b];
-    const int n = (int)(A.offsets[b + 1] - e0);
+// L2 prefetch of positions + measurements of a trajectory (issued by warp A right before it streams them)
+__device__ __forceinline__ void prefetch_pos_z(const FuseArgs& A, long long e0, int n) {
     const long long lead = e0 & 1;
     const uint32_t bytes = (uint32_t)(((long long)n + lead) * 24) & ~15u;
     const uint64_t pl = l2_policy_evict_last();
@@ -398,6 +393,8 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
             continue;
         }
 
+        // quaternions of this trajectory into L2 now; the streaming pass reads them ~10k cycles later
+        if (tid == 0) { const long long qn = ((long long)n * 32) & ~15ll; bulk_prefetch_l2_hint(A.quat + 4 * e0, (uint32_t)qn, l2_policy_evict_last()); }
         const FuseParams& prm = *reinterpret_cast<const FuseParams*>(sd + FS_PRM);
         const bool xy_same = prm.p0[0] == prm.p0[1] && prm.q[0] == prm.q[1] && prm.r[0] == prm.r[1];
         const int c0 = min(tid * LCH, n), c1 = min(c0 + LCH, n);
@@ -533,7 +530,7 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
         GSF_FSTAMP(16);
         if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
         GSF_FSTAMP(17);
-        if (lane == 0) { const int bn = next_valid_traj(A, b); if (bn < A.B) prefetch_pos_z(A, bn); }
+        if (lane == 0) prefetch_pos_z(A, e0, n);          // whole trajectory into L2 now: rounds after the first hit L2
         const double* __restrict__ gp = A.pos + 3 * e0;
         const double* __restrict__ gz = A.z + 3 * e0;
         const double ps0 = gp[0], ps1 = gp[1], ps2 = gp[2], pz0 = gz[0], pz1 = gz[1], pz2 = gz[2];
