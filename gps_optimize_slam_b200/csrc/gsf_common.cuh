@@ -155,29 +155,28 @@ GSF_HD inline double yaw_zyx(const Quat& q) {
     return m - PI;
 }
 
-// ----------------------------------------------------------------------------- 3x3 SVD pieces
-// One-sided (Hestenes) Jacobi on the columns of A (row-major 3x3): A <- A*V with V
-// accumulated, until the columns are mutually orthogonal to working precision.  Gives high
+// One-sided (Hestenes) Jacobi SVD of a 3x3 matrix, columns kept in registers: high
 // relative accuracy for the small singular directions, which decide the roll of a
 // near-collinear track (KITTI-04: sigma = 3.4e6 / 10.7 / 1.45).
-GSF_HD inline void jacobi_rotate(double* A, double* V, int p, int q, bool& rotated) {
-    double ap0 = A[p], ap1 = A[3 + p], ap2 = A[6 + p];
-    double aq0 = A[q], aq1 = A[3 + q], aq2 = A[6 + q];
-    double alpha = ap0 * ap0 + ap1 * ap1 + ap2 * ap2;
-    double beta = aq0 * aq0 + aq1 * aq1 + aq2 * aq2;
-    double gamma = ap0 * aq0 + ap1 * aq1 + ap2 * aq2;
-    if (gamma * gamma <= 1e-31 * alpha * beta || gamma == 0.0) return;   // |cos angle| <= 3.2e-16
-    rotated = true;
-    double d = beta - alpha, g2 = 2.0 * gamma;
+// One rotation of the column pair held in (a0, a1) / (v0, v1); returns true if it rotated.
+GSF_HD __forceinline__ bool jacobi_rotate_pair(double* a0, double* a1, double* v0, double* v1) {
+    const double alpha = a0[0] * a0[0] + a0[1] * a0[1] + a0[2] * a0[2];
+    const double beta = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+    const double gamma = a0[0] * a1[0] + a0[1] * a1[1] + a0[2] * a1[2];
+    if (gamma * gamma <= 1e-31 * alpha * beta || gamma == 0.0) return false;   // |cos angle| <= 3.2e-16
+    const double d = beta - alpha, g2 = 2.0 * gamma;
     const double w = d * d + g2 * g2;                 // > 0: gamma != 0 here
-    double hyp = w * rsqrt_(w);
-    double t = (d >= 0.0 ? g2 : -g2) * rcp_(fabs(d) + hyp);
-    double c = rsqrt_(1.0 + t * t), s = c * t;
-    A[p] = c * ap0 - s * aq0; A[3 + p] = c * ap1 - s * aq1; A[6 + p] = c * ap2 - s * aq2;
-    A[q] = s * ap0 + c * aq0; A[3 + q] = s * ap1 + c * aq1; A[6 + q] = s * ap2 + c * aq2;
-    double vp0 = V[p], vp1 = V[3 + p], vp2 = V[6 + p], vq0 = V[q], vq1 = V[3 + q], vq2 = V[6 + q];
-    V[p] = c * vp0 - s * vq0; V[3 + p] = c * vp1 - s * vq1; V[6 + p] = c * vp2 - s * vq2;
-    V[q] = s * vp0 + c * vq0; V[3 + q] = s * vp1 + c * vq1; V[6 + q] = s * vp2 + c * vq2;
+    const double hyp = w * rsqrt_(w);
+    const double t = (d >= 0.0 ? g2 : -g2) * rcp_(fabs(d) + hyp);
+    const double c = rsqrt_(1.0 + t * t), sn = c * t;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double x = a0[r], y = a1[r];
+        a0[r] = c * x - sn * y; a1[r] = sn * x + c * y;
+        const double vx = v0[r], vy = v1[r];
+        v0[r] = c * vx - sn * vy; v1[r] = sn * vx + c * vy;
+    }
+    return true;
 }
 
 // Umeyama's rotation + scale from the (un-normalised) cross-covariance H = src_c^T dst_c,
@@ -187,16 +186,35 @@ GSF_HD inline void jacobi_rotate(double* A, double* V, int p, int q, bool& rotat
 // v1 u1^T + v2 u2^T + (v1 x v2)(u1 x u2)^T, so only the two dominant pairs are needed.
 // Returns false when sigma_2 is numerically zero (collinear points: R not unique).
 GSF_HD inline bool umeyama_rotation(const double* H, double* R, double& sigma_sum, bool& reflected) {
-    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    // column-major copies: ca[j] = column j of the working matrix, cv[j] = column j of V
+    double ca[3][3], cv[3][3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) A[i] = H[i];
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { ca[j][r] = H[3 * r + j]; cv[j][r] = (r == j) ? 1.0 : 0.0; }
+    // Cyclic sweeps with ONE rotation body: rotate the pair in slots (0,1), then shift the columns
+    // (0,1,2) <- (1,2,0); three steps visit the pairs (0,1), (1,2), (2,0) and restore the order.
+    // (One body instead of three inlined copies: the instruction footprint matters on the device.)
     for (int sweep = 0; sweep < 30; ++sweep) {
         bool rotated = false;
-        jacobi_rotate(A, V, 0, 1, rotated);
-        jacobi_rotate(A, V, 0, 2, rotated);
-        jacobi_rotate(A, V, 1, 2, rotated);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+        for (int k = 0; k < 3; ++k) {
+            if (jacobi_rotate_pair(ca[0], ca[1], cv[0], cv[1])) rotated = true;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double ta = ca[0][r]; ca[0][r] = ca[1][r]; ca[1][r] = ca[2][r]; ca[2][r] = ta;
+                const double tv = cv[0][r]; cv[0][r] = cv[1][r]; cv[1][r] = cv[2][r]; cv[2][r] = tv;
+            }
+        }
         if (!rotated) break;
     }
+    double A[9], V[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { A[3 * r + j] = ca[j][r]; V[3 * r + j] = cv[j][r]; }
     double sg[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) sg[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);

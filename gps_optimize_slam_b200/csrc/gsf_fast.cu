@@ -31,7 +31,7 @@ namespace gsf {
 #ifndef GSF_QUAT_U
 #define GSF_QUAT_U 6
 #endif
-#define GSF_FSTAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW) && j == 4) A.phase_clock[k] = clock64(); } while (0)
+#define GSF_FSTAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW) && j == 100) A.phase_clock[k] = clock64(); } while (0)
 
 // ----------------------------------------------------------------------------- Moebius maps, NAX axes
 template <int NAX> struct MoebN { double m[4 * NAX]; };      // per axis row-major [a b; c d]
@@ -73,17 +73,18 @@ __device__ __forceinline__ void moebn_step(MoebN<NAX>& x, const double* qv, cons
 template <int NAX>
 __device__ __forceinline__ double moebn_apply(const MoebN<NAX>& x, int a, double p) {
     const double* m = x.m + 4 * a;
-    return (m[0] * p + m[1]) / (m[2] * p + m[3]);
+    return (m[0] * p + m[1]) * rcp_(m[2] * p + m[3]);      // positive normal denominator (entries >= 0, rescaled)
 }
 
 // ----------------------------------------------------------------------------- shared-memory map (doubles after the staging buffers)
 constexpr int FS_BC = 0;            // 2 slots x 48: M(C) 0-8, C 9-12, x0 13-15, t 16-18, s 19, R 20-28, verdict 30, status 31
 constexpr int FS_SUMS = 96;         // 2 slots x 24: 16 sums, pivots 16-21
 constexpr int FS_AFF = 144;         // 4 warps x 6 affine warp totals
-constexpr int FS_PRM = 168;         // FuseParams as 23 doubles (24)
+constexpr int FS_PRM = 168;         // FuseParams as 23 doubles (24): compute warps' copy
 constexpr int FS_INT = 192;         // 4 ints: 0 residual violators
 constexpr int FS_MBAR = 194;        // 8 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2], ts_b
-constexpr int FS_PST = 202;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
+constexpr int FS_PRMB = 202;        // FuseParams, warp B's copy (24)
+constexpr int FS_PST = 226;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
 constexpr int MB_FULL = 0, MB_SUMS = 1, MB_AUXRDY = 3, MB_AUXFREE = 5, MB_TSB = 7;
 
 __host__ __device__ constexpr size_t fast_smem_bytes(int cap, int ct) {
@@ -122,7 +123,7 @@ __device__ __forceinline__ void umeyama_accumulate(double* v, double p0, double 
 // Warp B, part 1: covariance the compute thread t starts from, for every t, and the gap / window check.
 template <int NAX, int CT, int LCH>
 __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, int n, const FuseParams* __restrict__ gp, int lane,
-                                              double* __restrict__ pst) {
+                                              double* __restrict__ pst, long long* clk) {
     constexpr int CPL = CT / 32;                            // compute-thread chunks per lane
     double qv[NAX], rv[NAX], p0v[NAX];
 #pragma unroll
@@ -150,6 +151,7 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
         moebn_rescale(cur);
         if (k < CPL - 1) incl[k] = cur;
     }
+    if (clk) clk[29] = clock64();
     // inclusive warp scan of the lane totals, then the exclusive prefix of this lane
     MoebN<NAX> tot = cur;
 #pragma unroll 1
@@ -163,6 +165,7 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
 #pragma unroll
     for (int k = 0; k < 4 * NAX; ++k) ex.m[k] = __shfl_up_sync(GSF_FULL_MASK, tot.m[k], 1);
     if (lane == 0) moebn_identity(ex);
+    if (clk) clk[30] = clock64();
     double pl[NAX];
 #pragma unroll
     for (int a = 0; a < NAX; ++a) pl[a] = moebn_apply(ex, a, p0v[a]);
@@ -621,10 +624,20 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
         if (n <= 0 || n > A.cap) continue;
         const int slot = j & 1, k = j >> 1;
         ++j;
+        // the few global scalars this warp needs (first quaternion, parameters) are pulled into L1 one trajectory ahead
+        if (lane == 0 && b + (int)gridDim.x < A.B) {
+            prefetch_l1(A.quat + 4 * o0);
+            if (A.params_per_traj) { prefetch_l1(A.params + b + gridDim.x); prefetch_l1(reinterpret_cast<const char*>(A.params + b + gridDim.x) + 128); }
+        }
         GSF_FSTAMP(24);
         if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
         GSF_FSTAMP(25);
-        const FuseParams* __restrict__ gprm = A.params + (A.params_per_traj ? b : 0);
+        // parameters: this warp's shared-memory copy (a batch-wide record is fetched once)
+        if (A.params_per_traj || k + slot == 0) {
+            if (lane < 23) sd[FS_PRMB + lane] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[lane];
+            __syncwarp();
+        }
+        const FuseParams* __restrict__ gprm = reinterpret_cast<const FuseParams*>(sd + FS_PRMB);
         const bool xy_same = gprm->p0[0] == gprm->p0[1] && gprm->q[0] == gprm->q[1] && gprm->r[0] == gprm->r[1];
         double* pst = sd + FS_PST + 3 * CT * slot;
         {
@@ -633,8 +646,10 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
             mbar_wait(mbar + MB_TSB, par_ts); par_ts ^= 1;
             __syncwarp();
         }
-        int general = xy_same ? cov_start_scan<2, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst)
-                              : cov_start_scan<3, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst);
+        long long* clk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && j == 100) ? A.phase_clock : nullptr;
+        if (clk) clk[31] = clock64();
+        int general = xy_same ? cov_start_scan<2, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst, clk)
+                              : cov_start_scan<3, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst, clk);
         __syncwarp();
         if (lane == 0) { const int bn = next_valid_traj(A, b); if (bn < A.B) issue_ts_load(A, bn, tsb, mbar + MB_TSB); }
         GSF_FSTAMP(26);

@@ -49,6 +49,8 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // ---- L2 eviction-priority policies (createpolicy) and hinted accesses.  evict_last keeps the look-ahead
 // data (read by a helper warp now, by the TMA load a trajectory later) resident; evict_first marks the
 // streaming traffic (quaternions, outputs, second touches) as the first victims.

@@ -19,4 +19,5 @@ print("compute (traj j=3): start %d | load landed +%d | aux ready +%d | passB+sc
     rel(0), c[1]-c[0], c[2]-c[1], c[3]-c[2], c[4]-c[3], c[5]-c[4], c[6]-c[5], c[6]-c[0]))
 print("warp A  (traj j=3): start %d | wait free +%d | stream sums +%d | butterfly+publish +%d" % (rel(16), c[17]-c[16], c[18]-c[17], c[19]-c[18]))
 print("warp B  (traj j=3): start %d | wait free +%d | cov scan +%d | wait sums +%d | SVD+publish +%d" % (rel(24), c[25]-c[24], c[26]-c[25], c[27]-c[26], c[28]-c[27]))
+print("warp B scan detail: ts wait %d | step loops %d | warp scan %d | eval+publish %d" % (c[31]-c[25], c[29]-c[31], c[30]-c[29], c[26]-c[30]))
 lib.gsf_debug_phase_clock(None)
