@@ -13,9 +13,10 @@ replaces the reference's tkinter dialogs (EKFGPSSLAM.py:940-953; tkinter/matplot
 part of this path).  Plotting (:470-666) is out of scope.
 
 Differences a caller can observe, all documented in DESIGN.md:
-  * ``compute_sim3_transform_robust`` is deterministic: it returns the all-points Umeyama fit
-    (what the reference's unseeded RANSAC converges to whenever all points are inliers, which
-    holds on the shipped data) and warns when residuals >= threshold exist.
+  * ``compute_sim3_transform_robust`` runs the reference's RANSAC on the device; the sample
+    indices are drawn on the host from numpy's global RNG exactly as the reference draws them,
+    so a seeded run evaluates the same trials (the batched fused path keeps the all-points fit
+    + residual flag, which is what RANSAC returns whenever every point is an inlier).
   * the UTM projection is the Krueger series kernel, not PROJ (pyproj is not installed).
 """
 from __future__ import annotations
@@ -238,25 +239,23 @@ def compute_sim3_transform(src: np.ndarray, dst: np.ndarray):
 
 def compute_sim3_transform_robust(src, dst, min_samples, residual_threshold, max_trials,
                                   min_inliers_needed, point_description: str = "points"):
-    """EKFGPSSLAM.py:389-426.  Deterministic stand-in for the unseeded RANSAC: the all-points
-    fit, which is what the reference returns whenever every point is an inlier of the best
-    trial; residuals >= threshold are counted on the device and reported."""
+    """EKFGPSSLAM.py:389-426 on the device.  The sample indices are drawn here exactly as the
+    reference draws them -- np.random.choice(n, min_samples, replace=False) once per trial from
+    numpy's global RNG (:408) -- and handed to gsf_sim3_ransac_dev, which runs every trial
+    (sample fit, residuals of all points, inlier count), keeps the first strictly-best one and
+    refits on its inliers.  With the same np.random.seed the reference evaluates the same trials."""
+    src = np.asarray(src, dtype=np.float64); dst = np.asarray(dst, dtype=np.float64)
     n = src.shape[0]
     if n < min_samples or src.shape != dst.shape:
         return None, None, None
-    R, t, s = compute_sim3_transform(src, dst)
-    if R is None:
+    samples = np.stack([np.random.choice(n, min_samples, replace=False) for _ in range(int(max_trials))]).astype(np.int32)
+    R, t, s, mask, info, st = fusion.sim3_ransac(_dev(src), _dev(dst), torch.from_numpy(samples).to("cuda"),
+                                                 residual_threshold, min_inliers_needed)
+    info = info.cpu().numpy()
+    print(f"  Sim3 RANSAC: best inlier count {int(info[0])}/{n} {point_description} (trial {int(info[1])} of {int(max_trials)})")
+    if int(info[2]) == 0 or (int(st.cpu()[0]) & _lib.ST_TOO_FEW_POINTS):
         return None, None, None
-    sp, _, _ = fusion.sim3_apply_batched(_dev(src), _dev(np.tile([0.0, 0.0, 0.0, 1.0], (n, 1))), _one(n), n,
-                                         _dev(R[None]), _dev(t[None]), _dev(np.array([s])))
-    resid = torch.linalg.norm(sp - _dev(dst), dim=1)
-    outliers = int((~(resid < residual_threshold)).sum().cpu())
-    if outliers:
-        print(f"warning: Sim3 all-points fit leaves {outliers}/{n} {point_description} with residual >= "
-              f"{residual_threshold} m; the reference's randomised RANSAC may pick a different inlier set")
-    if n - outliers < min_inliers_needed:
-        return None, None, None
-    return R, t, s
+    return R.cpu().numpy(), t.cpu().numpy(), float(s.cpu()[0])
 
 
 def transform_trajectory(positions, quaternions, R_mat, t_vec, scale_val):

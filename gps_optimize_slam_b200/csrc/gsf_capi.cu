@@ -176,6 +176,23 @@ int gsf_sim3_umeyama_batched_dev(const double* src, const double* dst, const int
     return 0;
 }
 
+int64_t gsf_sim3_ransac_work_doubles(int32_t trials, int64_t n) {
+    return gsf::sim3_ransac_work_doubles(trials < 0 ? 0 : trials, n < 0 ? 0 : n);
+}
+int gsf_sim3_ransac_dev(const double* src, const double* dst, int64_t n, const int32_t* samples,
+                        int32_t trials, int32_t min_samples, double residual_threshold, int32_t min_inliers,
+                        double* work, uint8_t* inlier_mask, double* R, double* t, double* s,
+                        int32_t* info, int32_t* status, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (n <= 0 || trials <= 0 || min_samples <= 0 || !src || !dst || !samples || !work || !inlier_mask || !R || !t || !s || !info || !status)
+        return fail(GSF_E_INVALID, "gsf_sim3_ransac_dev: null pointer or non-positive size");
+    cudaError_t e = gsf::launch_sim3_ransac(src, dst, n, samples, min_samples, trials, residual_threshold, min_inliers, work,
+                                            inlier_mask, R, t, s, info, status, d.sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_sim3_ransac_dev");
+    return 0;
+}
+
 int gsf_sim3_apply_dev(const double* pos, const double* quat, const int64_t* offsets,
                        const double* R, const double* t, const double* s, int32_t B, int64_t max_len,
                        double* out_pos, double* out_quat, int32_t* status, void* stream) {

@@ -91,6 +91,30 @@ def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, p
     return out_pos, out_quat, status
 
 
+def sim3_ransac(src, dst, samples, residual_threshold, min_inliers, stream=None):
+    """compute_sim3_transform_robust with host-supplied sample indices (gsf_sim3_ransac_dev).
+    src/dst [n,3] device fp64, samples [trials, m] device int32.
+    Returns (R [3,3], t [3], s [1], inlier_mask [n] uint8, info [3] int32, status [1] int32); asynchronous."""
+    lib = _lib.load()
+    _require_cuda(src, dst, samples)
+    n = src.shape[0]
+    trials, m = samples.shape
+    dev = src.device
+    work = torch.empty((max(1, lib.gsf_sim3_ransac_work_doubles(int(trials), int(n))),), dtype=torch.float64, device=dev)
+    mask = torch.empty((n,), dtype=torch.uint8, device=dev)
+    R = torch.empty((3, 3), dtype=torch.float64, device=dev)
+    t = torch.empty((3,), dtype=torch.float64, device=dev)
+    s = torch.empty((1,), dtype=torch.float64, device=dev)
+    info = torch.empty((3,), dtype=torch.int32, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    samples = samples.to(torch.int32).contiguous()
+    rc = lib.gsf_sim3_ransac_dev(_ptr(src), _ptr(dst), int(n), _ptr(samples), int(trials), int(m), float(residual_threshold),
+                                 int(min_inliers), _ptr(work), _ptr(mask), _ptr(R), _ptr(t), _ptr(s), _ptr(info), _ptr(status),
+                                 _stream_ptr(stream))
+    _lib.check(rc, "gsf_sim3_ransac_dev")
+    return R, t, s, mask, info, status
+
+
 def umeyama_batched(src, dst, offsets, max_len, mask=None, stream=None):
     """compute_sim3_transform for B point-set pairs -> (R [B,3,3], t [B,3], s [B], status [B])."""
     lib = _lib.load()

@@ -91,6 +91,20 @@ int gsf_sim3_umeyama_batched_dev(const double* src, const double* dst, const int
                                  const uint8_t* mask, int32_t B, int64_t max_len, double* work,
                                  double* R, double* t, double* s, int32_t* status, void* stream);
 
+/* ---- compute_sim3_transform_robust (:389-426) with HOST-SUPPLIED sample indices: `samples`
+ *      [trials, min_samples] int32 (device) holds what the reference draws with
+ *      np.random.choice(n, min_samples, replace=False) in each trial (:408), so a seeded reference
+ *      run and this call evaluate the same trials.  Per trial: Umeyama on the sample, residual
+ *      norms of all n points, inlier count; first strictly-best trial wins (:416); final fit on
+ *      its inliers (:422-423).  inlier_mask [n]; info[3] = max_inliers, winning trial, usable flag
+ *      (max_inliers >= min_inliers, :419); R [9], t [3], s [1]; status[1] = GSF_ST_TOO_FEW_POINTS
+ *      when the reference returns (None, None, None).  work: gsf_sim3_ransac_work_doubles(). */
+int64_t gsf_sim3_ransac_work_doubles(int32_t trials, int64_t n);
+int gsf_sim3_ransac_dev(const double* src, const double* dst, int64_t n, const int32_t* samples,
+                        int32_t trials, int32_t min_samples, double residual_threshold, int32_t min_inliers,
+                        double* work, uint8_t* inlier_mask, double* R, double* t, double* s,
+                        int32_t* info, int32_t* status, void* stream);
+
 /* ---- transform_trajectory (:461-467) batched; status must be zero-initialised. */
 int gsf_sim3_apply_dev(const double* pos, const double* quat, const int64_t* offsets,
                        const double* R, const double* t, const double* s, int32_t B, int64_t max_len,

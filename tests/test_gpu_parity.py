@@ -192,6 +192,37 @@ def test_umeyama_and_apply_kernels(gsf):
     assert int(st2.cpu()[0]) == 1
 
 
+@pytest.mark.parametrize("case", ["ransac_outliers", "ransac_collinear", "ransac_hopeless"])
+def test_sim3_ransac_matches_seeded_reference(gsf, case):
+    """gsf_sim3_ransac_dev with the sample indices of a seeded reference run against that run's
+    result (tests/golden/ransac_*.npz from the unmodified reference), then the drop-in function,
+    which draws the indices itself from numpy's global RNG."""
+    from gps_optimize_slam_b200 import _lib
+    g = load_golden(case)
+    src, dst, smp = g["src"], g["dst"], g["samples"]
+    R, t, s, mask, info, st = gsf.sim3_ransac(dev(src), dev(dst), dev(smp, torch.int32), float(g["thr"]), int(g["min_inliers"]))
+    info = info.cpu().numpy(); mask = mask.cpu().numpy().astype(bool)
+    if not bool(g["ok"]):
+        assert info[2] == 0 and not mask.any() and int(st.cpu()[0]) & _lib.ST_TOO_FEW_POINTS
+    else:
+        assert info[2] == 1 and info[0] == mask.sum()
+        assert not (mask & g["outliers"]).any()                  # no gross outlier survives
+        np.testing.assert_allclose(R.cpu().numpy(), g["R"], rtol=0, atol=ROT_ATOL)
+        np.testing.assert_allclose(t.cpu().numpy(), g["t"], rtol=1e-11, atol=POS_ATOL)
+        assert abs(float(s.cpu()[0]) - float(g["s"])) < 1e-11
+    import EKFGPSSLAM as drop
+    np.random.seed(int(g["seed"]))
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = drop.compute_sim3_transform_robust(src, dst, smp.shape[1], float(g["thr"]), len(smp), int(g["min_inliers"]))
+    if not bool(g["ok"]):
+        assert out == (None, None, None)
+    else:
+        np.testing.assert_allclose(out[0], g["R"], rtol=0, atol=ROT_ATOL)
+        np.testing.assert_allclose(out[1], g["t"], rtol=1e-11, atol=POS_ATOL)
+        assert abs(out[2] - float(g["s"])) < 1e-11
+
+
 def test_ate_kernel(gsf):
     from oracle import fusion_oracle as fo
     cfg = fo.default_config()

@@ -74,3 +74,21 @@ def test_loader_and_projection_on_raw_rows():
         assert f"{zone}{'S' if south else 'N'}" == str(g["utm_zone"])
         e, n = uk.utm_forward(lon[keep], lat[keep], zone, south)
         np.testing.assert_allclose(np.column_stack((e, n, alt[keep])), g["gps_utm"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("case", ["ransac_outliers", "ransac_collinear", "ransac_hopeless"])
+def test_sim3_ransac_matches_seeded_reference(case):
+    """oracle.sim3_ransac against the unmodified reference's seeded compute_sim3_transform_robust
+    (oracle/make_golden_ransac.py), including the sample indices the global RNG produces."""
+    g = load_golden(case)
+    np.random.seed(int(g["seed"]))
+    draws = np.stack([np.random.choice(len(g["src"]), g["samples"].shape[1], replace=False) for _ in range(len(g["samples"]))])
+    assert np.array_equal(draws, g["samples"])
+    np.random.seed(int(g["seed"]))
+    R, t, s = fo.sim3_ransac(g["src"], g["dst"], g["samples"].shape[1], float(g["thr"]), len(g["samples"]), int(g["min_inliers"]))
+    if not bool(g["ok"]):
+        assert R is None
+        return
+    np.testing.assert_allclose(R, g["R"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(t, g["t"], rtol=1e-15)
+    assert abs(s - float(g["s"])) <= 1e-15
