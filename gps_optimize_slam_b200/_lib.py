@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libgsf.so")
 
 GSF_E_INVALID, GSF_E_CUDA, GSF_E_NO_DEVICE, GSF_E_TOO_LARGE = -1, -2, -3, -4
 ST_OK, ST_TOO_FEW_POINTS, ST_DEGENERATE, ST_BAD_QUATERNION = 0, 1, 2, 4
-ST_EMPTY, ST_RANSAC_OUTLIERS, ST_TOO_LONG = 8, 16, 32
+ST_EMPTY, ST_RANSAC_OUTLIERS, ST_TOO_LONG, ST_GRID_NEEDS_ALL_VALID = 8, 16, 32, 64
 GEO_PARTS = 1024
 
 # name -> (restype, argtypes); the CPU test-suite checks that every symbol declared in
@@ -22,6 +22,8 @@ SIGNATURES = {
     "gsf_device_sm_count": (c_int32, []),
     "gsf_fuse_batched_dev": (c_int32, [c_void_p] * 5 + [c_int32, c_int64, c_void_p, c_int32] + [c_void_p] * 7),
     "gsf_ekf_strict_batched_dev": (c_int32, [c_void_p] * 5 + [c_int32, c_void_p, c_int32] + [c_void_p] * 6),
+    "gsf_hypothesis_grid_work_doubles": (c_int64, [c_int64, c_int32]),
+    "gsf_ekf_hypothesis_grid_dev": (c_int32, [c_void_p] * 4 + [c_int64, c_void_p, c_int32] + [c_void_p] * 5),
     "gsf_umeyama_work_doubles": (c_int64, [c_int32, c_int64]),
     "gsf_sim3_umeyama_batched_dev": (c_int32, [c_void_p] * 4 + [c_int32, c_int64] + [c_void_p] * 6),
     "gsf_sim3_ransac_work_doubles": (c_int64, [c_int32, c_int64]),

@@ -141,6 +141,24 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
     return 0;
 }
 
+int64_t gsf_hypothesis_grid_work_doubles(int64_t n, int32_t H) {
+    return gsf::grid_work_doubles(n < 0 ? 0 : n, H < 0 ? 0 : H);
+}
+int gsf_ekf_hypothesis_grid_dev(const double* ts, const double* pos, const double* quat, const double* z, int64_t n,
+                                const gsf_fuse_params* params, int32_t H, double* work, double* stats,
+                                double* sim3_out, int32_t* status, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (n < 2 || H <= 0 || !ts || !pos || !quat || !z || !params || !work || !stats || !status)
+        return fail(GSF_E_INVALID, "gsf_ekf_hypothesis_grid_dev: null pointer or bad size");
+    if (!aligned16(work)) return fail(GSF_E_INVALID, "gsf_ekf_hypothesis_grid_dev: work must be 16-byte aligned");
+    cudaError_t e = gsf::launch_hypothesis_grid(ts, pos, quat, z, n, reinterpret_cast<const gsf::FuseParams*>(params), H, work, stats,
+                                                sim3_out, status, d.max_smem, d.sms, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(GSF_E_TOO_LARGE, "gsf_ekf_hypothesis_grid_dev: trajectory too long for the shared-memory candidate set"); }
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_ekf_hypothesis_grid_dev");
+    return 0;
+}
+
 int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,
                                const int64_t* offsets, int32_t B,
                                const gsf_fuse_params* params, int32_t params_per_traj,

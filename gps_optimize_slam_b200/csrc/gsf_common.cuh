@@ -34,6 +34,7 @@ enum : int {
     ST_RANSAC_OUTLIERS = 16,   // all-points fit leaves residuals >= threshold: the reference's
                                // unseeded RANSAC could pick a different inlier set here
     ST_TOO_LONG = 32,          // trajectory does not fit the shared-memory staging buffer
+    ST_GRID_NEEDS_ALL_VALID = 64,  // hypothesis grid: the trajectory has poses without GNSS (outage/RTS unsupported there)
     ST_DEFERRED = 1 << 30,     // internal: left by the fast kernel for the general kernel (never returned)
 };
 

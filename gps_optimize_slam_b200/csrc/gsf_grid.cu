@@ -1,0 +1,306 @@
+// gsf_ekf_hypothesis_grid: ONE trajectory, H hypotheses of the EKF noise parameters (P0, Q, R diagonals);
+// per hypothesis the EKF of apply_ekf_correction (EKFGPSSLAM.py:831-935, ExtendedKalmanFilter :679-772) is
+// run from the Sim3-aligned pose 0 and scored with the nearest-neighbour error statistics of :1021-1033
+// (mean / median / RMSE).  BASELINE.json config 5 (KITTI-00 length x 262 144 noise-grid hypotheses).
+//
+// Everything that does not depend on the hypothesis is computed once (prep kernels): Sim3 selection
+// (:972-998), Umeyama (:428-459, tiled kernels of gsf_kernels.cu), C = q_state0 (x) conj(q_hat0), the
+// telescoped odometry u_i = M(C)(p_i - p_{i-1}) (see gsf_fused.cu), the step records {dt, u, z} and the
+// candidate set sorted by x with every evaluation pose's own rank in it.
+// The grid kernel maps one THREAD to one hypothesis: state (x, P per axis) and the nine noise values stay
+// in registers, the shared step records are staged through shared memory with TMA bulk copies
+// (double-buffered tiles, mbarrier), the candidate set is resident in shared memory.  The nearest
+// neighbour is found exactly by scanning outwards in the x-sorted candidate order from the pose's own
+// measurement until the 1-D gap alone exceeds the best distance (the pose's own measurement is always a
+// candidate, so the first bound is its innovation).  Errors go to a [poses, hypotheses] table (coalesced);
+// a second kernel sorts each hypothesis' column for the median.  FP64-pipe bound; no tensor cores.
+// Restriction (status GSF_ST_GRID_NEEDS_ALL_VALID otherwise): every pose has a GNSS measurement, i.e. no
+// outage / RTS segments (those need per-hypothesis history; use gsf_fuse_batched_dev with per-trajectory
+// parameters for such data).
+#include "gsf_common.cuh"
+#include "gsf_ptx.cuh"
+#include "gsf_internal.cuh"
+
+namespace gsf {
+
+constexpr int GRID_REC = 8;          // doubles per step record: dt, u(3), z(3), own rank (or -1: not evaluated)
+constexpr int GRID_TILE = 128;       // step records per shared-memory tile (8 KB)
+constexpr int GRID_THREADS = 256;    // hypotheses per block
+constexpr int GRID_FATAL = ST_TOO_FEW_POINTS | ST_BAD_QUATERNION | ST_GRID_NEEDS_ALL_VALID;
+
+// ----------------------------------------------------------------------------- prep 1: validity, Sim3 selection mask
+__global__ void __launch_bounds__(1024) grid_prep_select_kernel(const double* __restrict__ ts, const double* __restrict__ z, int n,
+                                                                const FuseParams* __restrict__ prm, unsigned char* __restrict__ mask,
+                                                                long long* __restrict__ offsets2, int* __restrict__ status) {
+    __shared__ int s_invalid, s_gap0, s_timed;
+    if (threadIdx.x == 0) { s_invalid = 0; s_gap0 = 0x7fffffff; s_timed = 0; }
+    __syncthreads();
+    const double gap = prm->gap_threshold;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        if (row_has_nan(z[3 * i], z[3 * i + 1], z[3 * i + 2])) s_invalid = 1;
+        if (i + 1 < n && ts[i + 1] - ts[i] > gap) atomicMin(&s_gap0, i);      // np.where(np.diff(ts[allv]) > gap)[0][0]
+    }
+    __syncthreads();
+    // :977-998 with every pose valid: first = allv[:gaps[0]] (the reference's slice end is the gap index itself)
+    const int first_cnt = s_gap0 == 0x7fffffff ? n : s_gap0;
+    const double tlim = ts[0] + prm->max_duration;
+    int mode = 0;                                           // 0: all, 1: first run, 2: first run within max_duration
+    if (first_cnt >= prm->min_samples) {
+        int c = 0;
+        for (int i = threadIdx.x; i < first_cnt; i += 1024) c += ts[i] <= tlim ? 1 : 0;
+        atomicAdd(&s_timed, c);
+        __syncthreads();
+        mode = s_timed < prm->min_samples ? 1 : 2;
+    }
+    for (int i = threadIdx.x; i < n; i += 1024)
+        mask[i] = (mode == 0 || (i < first_cnt && (mode == 1 || ts[i] <= tlim))) ? 1 : 0;
+    if (threadIdx.x == 0) {
+        const int nsel = mode == 0 ? n : (mode == 1 ? first_cnt : s_timed);
+        int st = s_invalid ? ST_GRID_NEEDS_ALL_VALID : 0;
+        if (nsel < 3 || nsel < prm->min_samples) st |= ST_TOO_FEW_POINTS;       // ValueError :975 / :997
+        offsets2[0] = 0; offsets2[1] = n; status[0] = st;
+    }
+}
+
+// ----------------------------------------------------------------------------- prep 2: step records + x-sorted candidates
+// One block.  rec[i] = {dt_i, u_i, z_i, rank_i}; cand[k] = k-th evaluation measurement in x order;
+// hdr = {x0(3), n_eval}.
+__global__ void __launch_bounds__(1024) grid_prep_records_kernel(const double* __restrict__ ts, const double* __restrict__ pos,
+                                                                 const double* __restrict__ quat, const double* __restrict__ z, int n,
+                                                                 const FuseParams* __restrict__ prm, const double* __restrict__ R,
+                                                                 const double* __restrict__ t, const double* __restrict__ s,
+                                                                 double* __restrict__ rec, double* __restrict__ cand, double* __restrict__ hdr,
+                                                                 int* __restrict__ status, int cap_pow2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* key = reinterpret_cast<double*>(smem_raw);      // [cap_pow2] x of the evaluation measurements
+    int* idx = reinterpret_cast<int*>(key + cap_pow2);      // [cap_pow2] pose index
+    __shared__ double MC[9];
+    __shared__ int s_count;
+    if (threadIdx.x == 0) {
+        s_count = 0;
+        const Quat q0{quat[0], quat[1], quat[2], quat[3]};
+        int st = status[0] | status[1];                     // selection status | Umeyama status
+        if (qnorm2(q0) == 0.0) st |= ST_BAD_QUATERNION;
+        const Quat qR = quat_from_matrix(R);
+        const Quat q0h = qunit(q0);
+        const Quat qs0 = qunit_or_identity(qmul(qR, q0h));
+        const Quat Cq = qmul(qs0, qconj(q0h));
+        qmat(Cq, MC);
+        double rx, ry, rz;
+        mat_vec(R, pos[0], pos[1], pos[2], rx, ry, rz);
+        hdr[0] = s[0] * rx + t[0]; hdr[1] = s[0] * ry + t[1]; hdr[2] = s[0] * rz + t[2];
+        hdr[5] = Cq.x; hdr[6] = Cq.y; hdr[7] = Cq.z; hdr[8] = Cq.w;
+        status[0] = st;
+    }
+    __syncthreads();
+    const double t_eval = ts[0] + prm->eval_skip;
+    // ordered compaction of the evaluation set (ts > ts[0] + skip; every pose is valid here), in slabs of 1024
+    for (int lo = 0; lo < n; lo += 1024) {
+        const int i = lo + threadIdx.x;
+        const bool keep = i < n && ts[i] > t_eval;
+        const unsigned bal = __ballot_sync(GSF_FULL_MASK, keep);
+        __shared__ int wcnt[32];
+        if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = __popc(bal);
+        __syncthreads();
+        int base = s_count;
+        for (int w = 0; w < (threadIdx.x >> 5); ++w) base += wcnt[w];
+        const int p = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
+        if (keep && p < cap_pow2) { key[p] = z[3 * i]; idx[p] = i; }
+        __syncthreads();
+        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += wcnt[w]; s_count += tot; }
+        __syncthreads();
+    }
+    const int m = min(s_count, cap_pow2);
+    for (int k = m + threadIdx.x; k < cap_pow2; k += 1024) { key[k] = INFINITY; idx[k] = 0x7fffffff; }
+    __syncthreads();
+    // bitonic sort by (x, pose index): ties keep pose order -> deterministic
+    for (int k = 2; k <= cap_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < cap_pow2; i += 1024) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const double a = key[i], c = key[l];
+                    const int ia = idx[i], ic = idx[l];
+                    const bool up = (i & k) == 0;
+                    const bool gt = a > c || (a == c && ia > ic);
+                    if (gt == up) { key[i] = c; key[l] = a; idx[i] = ic; idx[l] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    // step records; rank defaults to -1
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        double* r = rec + (size_t)GRID_REC * i;
+        if (i == 0) { r[0] = 0.0; r[1] = r[2] = r[3] = 0.0; }
+        else {
+            r[0] = fmax(1e-6, ts[i] - ts[i - 1]);
+            mat_vec(MC, pos[3 * i] - pos[3 * i - 3], pos[3 * i + 1] - pos[3 * i - 2], pos[3 * i + 2] - pos[3 * i - 1], r[1], r[2], r[3]);
+        }
+        r[4] = z[3 * i]; r[5] = z[3 * i + 1]; r[6] = z[3 * i + 2]; r[7] = -1.0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += 1024) {
+        const int i = idx[k];
+        cand[3 * k] = z[3 * i]; cand[3 * k + 1] = z[3 * i + 1]; cand[3 * k + 2] = z[3 * i + 2];
+        rec[(size_t)GRID_REC * i + 7] = (double)k;
+    }
+    if (threadIdx.x == 0) { hdr[3] = (double)m; hdr[4] = (double)s_count; }
+}
+
+// ----------------------------------------------------------------------------- the grid kernel: one thread per hypothesis
+__global__ void __launch_bounds__(GRID_THREADS) ekf_grid_kernel(const double* __restrict__ rec, const double* __restrict__ cand,
+                                                                const double* __restrict__ hdr, int n, const FuseParams* __restrict__ params,
+                                                                int H, double* __restrict__ err, double* __restrict__ stats,
+                                                                const int* __restrict__ status) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tile = reinterpret_cast<double*>(smem_raw);                 // 2 x GRID_TILE x GRID_REC
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + 2 * GRID_TILE * GRID_REC);
+    double* cs = reinterpret_cast<double*>(mbar + 2);                   // candidates [m,3]
+    const int m = (int)hdr[3];
+    const int h = blockIdx.x * GRID_THREADS + threadIdx.x;
+    const bool live = h < H;
+    if ((status[0] & GRID_FATAL) || (int)hdr[4] != m) {                  // prerequisites failed / candidate set too large
+        if (live) { stats[4 * (size_t)h] = stats[4 * (size_t)h + 1] = stats[4 * (size_t)h + 2] = nan(""); stats[4 * (size_t)h + 3] = 0.0; }
+        return;
+    }
+    if (threadIdx.x == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); fence_mbar_init(); }
+    for (int k = threadIdx.x; k < 3 * m; k += GRID_THREADS) cs[k] = cand[k];
+    __syncthreads();
+    const int ntiles = (n + GRID_TILE - 1) / GRID_TILE;
+    auto issue = [&](int tl) {
+        const int cnt = min(GRID_TILE, n - tl * GRID_TILE);
+        const uint32_t bytes = (uint32_t)cnt * GRID_REC * 8u;
+        mbar_expect_tx(mbar + (tl & 1), bytes);
+        bulk_g2s(tile + (size_t)(tl & 1) * GRID_TILE * GRID_REC, rec + (size_t)tl * GRID_TILE * GRID_REC, bytes, mbar + (tl & 1));
+    };
+    if (threadIdx.x == 0) { issue(0); if (ntiles > 1) issue(1); }
+
+    const FuseParams* pr = params + (live ? h : 0);
+    const double p0x = pr->p0[0], p0y = pr->p0[1], p0z = pr->p0[2];
+    const double qx = pr->q[0], qy = pr->q[1], qz = pr->q[2], rx = pr->r[0], ry = pr->r[1], rz = pr->r[2];
+    double x0 = hdr[0], x1 = hdr[1], x2 = hdr[2];
+    double Px = p0x, Py = p0y, Pz = p0z;
+    double se = 0.0, se2 = 0.0;
+    int ne = 0;
+    for (int tl = 0; tl < ntiles; ++tl) {
+        mbar_wait(mbar + (tl & 1), (uint32_t)(tl >> 1) & 1u);
+        const double* T = tile + (size_t)(tl & 1) * GRID_TILE * GRID_REC;
+        const int cnt = min(GRID_TILE, n - tl * GRID_TILE);
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const double* r = T + GRID_REC * k;
+            const int i = tl * GRID_TILE + k;
+            if (i > 0) {
+                const double dt = r[0];
+                {   const double pp = Px + qx * dt, kk = pp / (pp + rx), om = 1.0 - kk;
+                    Px = om * pp * om + kk * rx * kk; x0 = om * (x0 + r[1]) + kk * r[4]; }
+                {   const double pp = Py + qy * dt, kk = pp / (pp + ry), om = 1.0 - kk;
+                    Py = om * pp * om + kk * ry * kk; x1 = om * (x1 + r[2]) + kk * r[5]; }
+                {   const double pp = Pz + qz * dt, kk = pp / (pp + rz), om = 1.0 - kk;
+                    Pz = om * pp * om + kk * rz * kk; x2 = om * (x2 + r[3]) + kk * r[6]; }
+            }
+            const int rank = (int)r[7];
+            if (rank >= 0) {
+                // exact nearest neighbour: own measurement first, then outwards in x order while the 1-D gap can still win
+                double dx = x0 - cs[3 * rank], dy = x1 - cs[3 * rank + 1], dz = x2 - cs[3 * rank + 2];
+                double best = dx * dx + dy * dy + dz * dz;
+                for (int c = rank - 1; c >= 0; --c) {
+                    dx = x0 - cs[3 * c];
+                    if (dx > 0.0 && dx * dx >= best) break;
+                    dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
+                    best = fmin(best, dx * dx + dy * dy + dz * dz);
+                }
+                for (int c = rank + 1; c < m; ++c) {
+                    dx = cs[3 * c] - x0;
+                    if (dx > 0.0 && dx * dx >= best) break;
+                    dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
+                    best = fmin(best, dx * dx + dy * dy + dz * dz);
+                }
+                const double e = sqrt(best);
+                if (live) err[(size_t)ne * H + h] = e;
+                se += e; se2 += e * e; ++ne;
+            }
+        }
+        __syncthreads();                                                // every thread is done with this tile buffer
+        if (threadIdx.x == 0 && tl + 2 < ntiles) issue(tl + 2);
+    }
+    if (live) {
+        double* o = stats + 4 * (size_t)h;
+        o[0] = ne ? se / ne : nan(""); o[2] = ne ? sqrt(se2 / ne) : nan(""); o[3] = (double)ne;
+        if (!ne) o[1] = nan("");
+    }
+}
+
+// ----------------------------------------------------------------------------- median of each hypothesis' error column
+__global__ void __launch_bounds__(256) grid_median_kernel(const double* __restrict__ err, const double* __restrict__ hdr, int H,
+                                                          double* __restrict__ stats, const int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* v = reinterpret_cast<double*>(smem_raw);
+    const int m = (int)hdr[3];
+    if ((status[0] & GRID_FATAL) || (int)hdr[4] != m || m == 0) return;
+    int p2 = 1; while (p2 < m) p2 <<= 1;
+    for (int h = blockIdx.x; h < H; h += gridDim.x) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < p2; k += 256) v[k] = k < m ? err[(size_t)k * H + h] : INFINITY;
+        __syncthreads();
+        for (int k = 2; k <= p2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < p2; i += 256) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const double a = v[i], c = v[l];
+                        const bool up = (i & k) == 0;
+                        if ((a > c) == up) { v[i] = c; v[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (threadIdx.x == 0) stats[4 * (size_t)h + 1] = (m & 1) ? v[m / 2] : 0.5 * (v[m / 2 - 1] + v[m / 2]);
+    }
+}
+
+static int pow2_at_least(long long n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+// work layout (doubles): hdr[16] | R[9] t[3] s[1] pad[3] | offsets2 (2 long long) | status (4 ints = 2 doubles) |
+//                        rec[8 n] | cand[3 n] | umeyama tiles | mask (n bytes, padded) | err [n x H]
+long long grid_work_doubles(long long n, int H) {
+    return 16 + 16 + 2 + 2 + 8 * n + 3 * n + (long long)sim3_tiles_for(n) * 20 + (n + 7) / 8 + n * (long long)H;
+}
+cudaError_t launch_hypothesis_grid(const double* ts, const double* pos, const double* quat, const double* z, long long n,
+                                   const FuseParams* params, int H, double* work, double* stats, double* sim3_out, int* status_out,
+                                   int max_smem, int num_sms, cudaStream_t stream) {
+    double* hdr = work;
+    double* R = work + 16; double* t = R + 9; double* s = t + 3;
+    long long* offsets2 = reinterpret_cast<long long*>(work + 32);
+    int* st = reinterpret_cast<int*>(work + 34);
+    double* rec = work + 36;
+    double* cand = rec + 8 * n;
+    double* uwork = cand + 3 * n;
+    unsigned char* mask = reinterpret_cast<unsigned char*>(uwork + (size_t)sim3_tiles_for(n) * 20);
+    double* err = reinterpret_cast<double*>(mask) + (n + 7) / 8;
+    const int cap2 = pow2_at_least(n);
+    const size_t smem_prep = (size_t)cap2 * 12;
+    const size_t smem_grid = (size_t)2 * GRID_TILE * GRID_REC * 8 + 16 + (size_t)n * 24;
+    const size_t smem_med = (size_t)cap2 * 8;
+    if (smem_prep > (size_t)max_smem || smem_grid > (size_t)max_smem || smem_med > (size_t)max_smem) return cudaErrorInvalidValue;
+    grid_prep_select_kernel<<<1, 1024, 0, stream>>>(ts, z, (int)n, params, mask, offsets2, st);
+    cudaError_t e = launch_umeyama(pos, z, offsets2, mask, 1, n, uwork, R, t, s, st + 1, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(grid_prep_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
+    if (e != cudaSuccess) return e;
+    grid_prep_records_kernel<<<1, 1024, smem_prep, stream>>>(ts, pos, quat, z, (int)n, params, R, t, s, rec, cand, hdr, st, cap2);
+    e = cudaFuncSetAttribute(ekf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_grid);
+    if (e != cudaSuccess) return e;
+    ekf_grid_kernel<<<(H + GRID_THREADS - 1) / GRID_THREADS, GRID_THREADS, smem_grid, stream>>>(rec, cand, hdr, (int)n, params, H, err, stats, st);
+    e = cudaFuncSetAttribute(grid_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_med);
+    if (e != cudaSuccess) return e;
+    const int mg = H < num_sms * 8 ? H : num_sms * 8;
+    grid_median_kernel<<<mg, 256, smem_med, stream>>>(err, hdr, H, stats, st);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (sim3_out) { e = cudaMemcpyAsync(sim3_out, R, 13 * sizeof(double), cudaMemcpyDeviceToDevice, stream); if (e != cudaSuccess) return e; }
+    if (status_out) e = cudaMemcpyAsync(status_out, st, sizeof(int), cudaMemcpyDeviceToDevice, stream);
+    return e;
+}
+
+}  // namespace gsf

@@ -27,6 +27,9 @@ cudaError_t launch_fuse_fast(const FuseArgs& a, int num_sms, cudaStream_t stream
 cudaError_t defer_counter(int** out);
 cudaError_t launch_ekf_strict(const double*, const double*, const double*, const double*, const long long*,
                               const FuseParams*, int, const double*, const double*, double*, double*, int*, int, cudaStream_t);
+long long grid_work_doubles(long long n, int H);
+cudaError_t launch_hypothesis_grid(const double*, const double*, const double*, const double*, long long, const FuseParams*, int,
+                                   double*, double*, double*, int*, int, int, cudaStream_t);
 struct UtmConst { double A_k0; double e, e2; double alpha[6], beta[6]; double lon0; double fn; };
 cudaError_t launch_utm(bool inverse, const double* a, const double* b, long long n, const UtmConst& K, double* o1, double* o2,
                        int num_sms, cudaStream_t stream);

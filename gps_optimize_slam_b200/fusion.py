@@ -76,6 +76,25 @@ def fuse_batched(ts, pos, quat, z, offsets, max_len, params, params_per_traj=Fal
     return out_pos, out_quat, sim3_out, status
 
 
+def hypothesis_grid(ts, pos, quat, z, params, stream=None):
+    """One trajectory x H noise-parameter hypotheses -> ATE statistics (gsf_ekf_hypothesis_grid_dev).
+    ts [n], pos [n,3], quat [n,4], z [n,3] (all valid); params: uint8 [H*184] packed FuseParams records.
+    Returns (stats [H,4] = mean, median, RMSE, count; sim3 [13]; status [1]); asynchronous."""
+    lib = _lib.load()
+    _require_cuda(ts, pos, quat, z, params)
+    n = ts.numel()
+    H = params.numel() // 184
+    dev = ts.device
+    work = torch.empty((lib.gsf_hypothesis_grid_work_doubles(int(n), int(H)),), dtype=torch.float64, device=dev)
+    stats = torch.empty((H, 4), dtype=torch.float64, device=dev)
+    sim3 = torch.empty((13,), dtype=torch.float64, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    rc = lib.gsf_ekf_hypothesis_grid_dev(_ptr(ts), _ptr(pos), _ptr(quat), _ptr(z), int(n), _ptr(params), int(H), _ptr(work),
+                                         _ptr(stats), _ptr(sim3), _ptr(status), _stream_ptr(stream))
+    _lib.check(rc, "gsf_ekf_hypothesis_grid_dev")
+    return stats, sim3, status
+
+
 def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, params_per_traj=False, stream=None):
     """Literal step-by-step EKF recursion, one thread per trajectory (gsf_ekf_strict_batched_dev)."""
     lib = _lib.load()

@@ -41,6 +41,7 @@ extern "C" {
 #define GSF_ST_EMPTY            8
 #define GSF_ST_RANSAC_OUTLIERS 16   /* all-points fit has residuals >= threshold (:411) */
 #define GSF_ST_TOO_LONG        32
+#define GSF_ST_GRID_NEEDS_ALL_VALID 64 /* hypothesis grid: a pose without GNSS (use gsf_fuse_batched_dev) */
 
 /* Flattened CONFIG (EKFGPSSLAM.py:22-71); 184 bytes, layout fixed. */
 typedef struct gsf_fuse_params {
@@ -75,6 +76,17 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
                          const double* init_pos, const double* init_quat,
                          double* out_pos, double* out_quat, double* sim3_out, int32_t* status,
                          void* stream);
+
+/* ---- noise-parameter hypothesis grid (BASELINE config 5): ONE trajectory, H parameter records; per
+ *      hypothesis the EKF of apply_ekf_correction (:831-935) from the Sim3-aligned pose 0 (Sim3 selection
+ *      :972-998 and Umeyama :428-459 run once, with params[0]'s gap / window / min_samples), scored with
+ *      the evaluation of :1021-1033.  Every pose must carry a GNSS measurement (else status =
+ *      GSF_ST_GRID_NEEDS_ALL_VALID and NaN statistics).  stats [H,4]: mean, median, RMSE, count.
+ *      sim3_out [13]: R(9) t(3) s, or NULL.  status [1].  work: gsf_hypothesis_grid_work_doubles(). */
+int64_t gsf_hypothesis_grid_work_doubles(int64_t n, int32_t H);
+int gsf_ekf_hypothesis_grid_dev(const double* ts, const double* pos, const double* quat, const double* z, int64_t n,
+                                const gsf_fuse_params* params, int32_t H, double* work, double* stats,
+                                double* sim3_out, int32_t* status, void* stream);
 
 /* ---- apply_ekf_correction (:831-935), literal step-by-step recursion, one thread per
  *      trajectory (general path; keeps the zero-motion fallback of :84-86). */

@@ -347,6 +347,45 @@ def test_per_trajectory_noise_parameters(gsf):
         np.testing.assert_allclose(p[off[b]:off[b + 1]], oracle_pipeline(tr, cfg)["pos"], rtol=0, atol=POS_ATOL)
 
 
+@pytest.mark.parametrize("n,dt", [(300, 0.104), (2200, 0.104)])
+def test_hypothesis_grid_matches_oracle(gsf, n, dt):
+    """gsf_ekf_hypothesis_grid_dev (one trajectory x H noise sets -> ATE statistics) against the oracle run
+    hypothesis by hypothesis; n = 2200 spans 229 s, so the 180 s Sim3 window (:985-998) is exercised, and a
+    closed loop makes the pruned nearest-neighbour search meet candidates from another lap."""
+    from gps_optimize_slam_b200 import synth
+    from gps_optimize_slam_b200.config import pack_fuse_params
+    from oracle import fusion_oracle as fo
+    tr = synth.make_trajectory(41, n=n, dt=dt, speed=9.0)
+    if n > 1000:                                   # second lap over the first one: NN candidates from another time
+        half = n // 2
+        tr["gps"][half:] = tr["gps"][:n - half] + np.random.default_rng(3).normal(0, 0.2, (n - half, 3))
+    rng = np.random.default_rng(9)
+    sets = [([0.1] * 3 + [0.01] * 4, [0.1, 0.1, 0.7] + [0.01] * 4, [0.2] * 3)]
+    for _ in range(40 if n <= 1000 else 9):
+        qv = 10 ** rng.uniform(-3, 1, 3); rv = 10 ** rng.uniform(-2, 1, 3); pv = 10 ** rng.uniform(-2, 0, 3)
+        sets.append((list(pv) + [0.01] * 4, list(qv) + [0.01] * 4, list(rv)))
+    blob = np.concatenate([pack_fuse_params(None, p0=a, q=b, r=c) for (a, b, c) in sets])
+    stats, sim3, st = gsf.hypothesis_grid(dev(tr["ts"]), dev(tr["pos"]), dev(tr["quat"]), dev(tr["gps"]), dev(blob, torch.uint8))
+    assert int(st.cpu()[0]) == 0
+    stats = stats.cpu().numpy()
+    valid = np.ones(n, dtype=bool)
+    ev = fo.evaluation_indices(tr["ts"], valid)
+    for h, (p0, qq, rr) in enumerate(sets):
+        cfg = fo.default_config()
+        cfg["ekf"].update(initial_cov_diag=p0, process_noise_diag=qq, meas_noise_diag=rr)
+        o = oracle_pipeline(tr, cfg)
+        want = fo.error_stats(fo.nn_errors(o["pos"], tr["gps"], ev))
+        # errors are differences of UTM-scale coordinates (one ulp = 9.3e-10 m): same absolute budget as positions
+        np.testing.assert_allclose(stats[h, :3], want, rtol=0, atol=POS_ATOL)
+        assert stats[h, 3] == len(ev)
+    np.testing.assert_allclose(sim3.cpu().numpy()[:9].reshape(3, 3), o["R"], atol=ROT_ATOL)
+    # a pose without GNSS is refused (outage / RTS needs per-hypothesis history)
+    bad = tr["gps"].copy(); bad[50] = np.nan
+    stats2, _, st2 = gsf.hypothesis_grid(dev(tr["ts"]), dev(tr["pos"]), dev(tr["quat"]), dev(bad), dev(blob, torch.uint8))
+    from gps_optimize_slam_b200 import _lib
+    assert int(st2.cpu()[0]) & _lib.ST_GRID_NEEDS_ALL_VALID and np.isnan(stats2.cpu().numpy()[:, :3]).all()
+
+
 def test_bit_reproducible_and_shard_invariant(gsf):
     """Same inputs -> same bits; an N-way shard (separate launches over trajectory ranges)
     equals the unsharded run bit for bit (multi-GPU without a cluster)."""
