@@ -142,13 +142,53 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def main_extra(args):
+    """config4 (single long trajectory) and config5 (noise-grid hypotheses): bench_workloads.py."""
+    import bench_workloads as bw
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank == 0:
+            from gps_optimize_slam_b200 import synth
+            if args.workload == "config5":
+                tr = synth.make_loop_trajectory(2026, n=args.poses or 4541)
+                cpu = bw.cpu_baseline_config5(tr, synth.noise_grid(args.grid_k), os.cpu_count() or 1)
+            else:
+                import numpy as np
+                m = 2_000_000
+                i = np.arange(m, dtype=np.float64)
+                rows = np.column_stack([i * 0.1, 49.0 + 4e-9 * i + 1e-4 * np.sin(i * 1e-4), 8.4 + 6e-9 * i + 1e-4 * np.cos(i * 7e-5), 112.0 + np.sin(i * 1e-3)])
+                pos = np.random.default_rng(4).normal(size=(m, 3)).cumsum(0)
+                quat = np.column_stack([np.zeros(m), np.zeros(m), np.sin(i * 1e-5), np.cos(i * 1e-5)])
+                cpu = bw.cpu_baseline_config4(rows, pos, quat)
+            print(json.dumps({"impl": "reference", "metric": args.workload, "value": cpu["value"], "unit": cpu["unit"], "n_gpus": args.gpus,
+                              "steps": 1, "warmup": 1, "higher_is_better": True, "cpu_baseline": cpu, "dtype": "f64", "data": "synthetic",
+                              "config": {"workload": args.workload, "sample": cpu["sample"]},
+                              "e2e": {"value": cpu["value"], "unit": cpu["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    from gps_optimize_slam_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a B200: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.load()
+    (bw.run_config5 if args.workload == "config5" else bw.run_config4)(args, rank, local_rank, world, ClockSampler, read_peak)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + ["config4", "config5"])
+    ap.add_argument("--poses", type=int, default=0, help="config4 / config5: override the trajectory length")
+    ap.add_argument("--grid-k", type=int, default=64, help="config5: hypotheses = k^3")
     ap.add_argument("--trajectories", type=int, default=0, help="override the total trajectory count (debug)")
     ap.add_argument("--e2e-trajectories", type=int, default=0, help="host-buffer sample per rank (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -157,6 +197,8 @@ def main():
     ap.add_argument("--ate-trajectories", type=int, default=65536, help="trajectories per rank scored by the NN-ATE kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload in ("config4", "config5"):
+        return main_extra(args)
     wl = dict(WORKLOADS[args.workload])
     if args.trajectories:
         wl["B"] = args.trajectories

@@ -1,0 +1,254 @@
+"""bench.py workloads beyond the default (part of the benchmark, not of the product package: the CPU baselines import oracle/)
+
+Workloads beyond the default (BASELINE.json configs[3] and configs[4]).
+
+config4  single long trajectory (default 1e8 poses): fused GNSS ingest (validity mask, zone from the
+         masked means, UTM forward) + Sim3 Umeyama reduction over all points + transform_trajectory.
+         One step = the three stages back to back on one GPU; per-stage times from CUDA events.
+config5  one KITTI-00-length closed-loop trajectory x 64^3 EKF noise-grid hypotheses, hypotheses sharded
+         across the ranks, one gsf_ekf_hypothesis_grid_dev call per step, then the only collective of the
+         path: NCCL all_gather of the per-hypothesis ATE statistics.
+Both print the bench contract's JSON line (rank 0)."""
+from __future__ import annotations
+
+import json
+import os
+import statistics
+import time
+
+import numpy as np
+
+
+def _events(torch, k):
+    return [torch.cuda.Event(enable_timing=True) for _ in range(k)]
+
+
+def run_config5(args, rank, local_rank, world, ClockSampler, read_peak):
+    import torch
+    import torch.distributed as dist
+    from gps_optimize_slam_b200 import fusion, sharding, synth
+    from gps_optimize_slam_b200.config import pack_noise_grid
+
+    dev = torch.device("cuda", local_rank)
+    n = args.poses or 4541
+    k = args.grid_k
+    H_total = k ** 3
+    lo, hi = sharding.shard_range(H_total, rank, world)
+    tr = synth.make_loop_trajectory(2026, n=n)
+    grid = synth.noise_grid(k)
+    blob_h = torch.from_numpy(pack_noise_grid(grid[lo:hi])).pin_memory()
+    host = [torch.from_numpy(np.ascontiguousarray(tr[key])).pin_memory() for key in ("ts", "pos", "quat", "gps")]
+    ts, pos, quat, z = [h.to(dev) for h in host]
+    blob = blob_h.to(dev)
+    H = hi - lo
+
+    def step():
+        return fusion.hypothesis_grid(ts, pos, quat, z, blob)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        stats, sim3, st = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = _events(torch, args.steps + 1)
+    ev[0].record()
+    for i in range(args.steps):
+        stats, sim3, st = step()
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sharding.max_over_ranks(ev[0].elapsed_time(ev[-1]), dev) / args.steps
+    value = H_total * (n - 1) / (ms * 1e-3)
+
+    # the collective: gather [H/G, 4] statistics from every rank (NCCL all_gather over NVLink)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    table = sharding.gather_stats(stats, total_rows=H_total if world > 1 else None)
+    torch.cuda.synchronize(dev)
+    gather_s = time.perf_counter() - t0
+    best = int(torch.argmin(table[:, 2]).item())
+
+    # end to end: trajectory + parameter records from pinned host memory, statistics back to the host
+    def e2e_step():
+        d = [h.to(dev, non_blocking=True) for h in host]
+        b = blob_h.to(dev, non_blocking=True)
+        s_, _, _ = fusion.hypothesis_grid(d[0], d[1], d[2], d[3], b)
+        return s_.cpu()
+
+    e2e_step(); barrier()
+    t0 = time.perf_counter()
+    e_steps = max(2, min(args.steps, 3))
+    for _ in range(e_steps):
+        e2e_step()
+    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev) / e_steps
+    e2e = {"value": H_total * (n - 1) / e2e_s, "unit": "pose-updates/s",
+           "h2d_bytes_per_step": int(n * 88 + H * 184), "d2h_bytes_per_step": int(H * 32),
+           "sample": f"{H} hypotheses x {n} poses per rank per step, pinned host buffers, {e_steps} steps"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_config5(tr, grid, os.cpu_count() or 1)
+
+    # FP64 accounting: per pose-update 3 axes x (predict 2, gain 1 div + 1, update 4, Joseph 7) = 45 flops,
+    # per evaluated pose the own-measurement distance (8) + sqrt; neighbours visited by the pruned search add
+    # ~8 flops each (data dependent, not counted): a lower bound on the executed fp64 work.
+    flops = H * (n - 1) * 45.0 + H * float(table[0, 3].item()) * 9.0
+    peak_tf = 148 * 64 * 2 * 1.965e9 / 1e12
+    roofline = {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": flops / (ms * 1e-3) / 1e12 / peak_tf, "traffic": None,
+                "peak_source": "nominal: 148 SMs x 64 FP64 FMA/clk x 1.965 GHz (the path is FP64-pipe bound, not HBM / tensor)",
+                "kernel": "ekf_grid_kernel (+ prep kernels, grid_median_kernel)", "launch_ms": ms,
+                "algorithmic_flops_per_launch": flops}
+    if rank == 0:
+        line = {"metric": "EKF pose-updates/s (noise-grid hypotheses, ATE statistics only)", "value": value, "unit": "pose-updates/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"config5: {n}-pose closed-loop trajectory x {H_total} EKF Q/R noise-grid hypotheses ({k}^3)",
+                           "hypotheses_per_gpu": H, "parallelism": f"hypothesis-sharded x{world}; all_gather of [H/G,4] ATE statistics",
+                           "l2": "inputs are one 400 KB trajectory (L2 resident by design); the path is FP64-bound",
+                           "gather": "nccl all_gather" if world > 1 else "single rank (no collective)", "gather_seconds": gather_s,
+                           "best_hypothesis": {"index": best, "q_xy": float(grid[best, 0]), "q_z": float(grid[best, 1]), "r": float(grid[best, 2]),
+                                               "rmse_m": float(table[best, 2].item())},
+                           "status": int(st.cpu()[0])},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 6 * args.steps}
+        print(json.dumps(line), flush=True)
+
+
+def _cpu5_worker(job):
+    from oracle import fusion_oracle as fo
+    tr, sets = job
+    ts, p, q, z = tr["ts"], tr["pos"], tr["quat"], tr["gps"]
+    valid = np.ones(len(ts), dtype=bool)
+    sel = fo.sim3_point_selection(ts, valid)
+    R, t, s = fo.umeyama(p[sel], z[sel])
+    sp, sq = fo.sim3_apply(p, q, R, t, s)
+    ev = fo.evaluation_indices(ts, valid)
+    t0 = time.perf_counter()
+    for (qxy, qz, r) in sets:
+        cfg = fo.default_config()
+        cfg["ekf"].update(process_noise_diag=[qxy, qxy, qz, 0.01, 0.01, 0.01, 0.01], meas_noise_diag=[r, r, r])
+        fp, _ = fo.ekf_fuse(ts, p, q, z, valid, sp[0], sq[0], cfg)
+        fo.error_stats(fo.nn_errors(fp, z, ev))
+    return len(sets) * (len(ts) - 1), time.perf_counter() - t0
+
+
+def cpu_baseline_config5(tr, grid, cores, per_core=2):
+    """Oracle port, one hypothesis at a time (what a user of the reference would loop over), on all host cores."""
+    import multiprocessing as mp
+    rng = np.random.default_rng(0)
+    pick = grid[rng.choice(len(grid), cores * per_core, replace=False)]
+    jobs = [(tr, [tuple(x) for x in pick[i::cores]]) for i in range(cores)]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu5_worker, [(tr, [tuple(pick[0])])] * cores)          # warm
+        t0 = time.perf_counter()
+        res = pool.map(_cpu5_worker, jobs)
+        dt = time.perf_counter() - t0
+    updates = sum(r[0] for r in res)
+    return {"value": updates / dt, "unit": "pose-updates/s", "cores": cores, "kind": "port",
+            "sample": f"{len(pick)} hypotheses x {len(tr['ts'])} poses (EKF + exact NN-ATE each), {cores} processes"}
+
+
+def run_config4(args, rank, local_rank, world, ClockSampler, read_peak):
+    """Replicas only: the single long trajectory is specified for one GPU."""
+    import torch
+    from gps_optimize_slam_b200 import fusion
+
+    if rank != 0:
+        return
+    dev = torch.device("cuda", local_rank)
+    n = args.poses or 100_000_000
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    # GNSS rows (ts, lat, lon, alt) of a long drive inside one UTM zone; SLAM positions = the ENU track in a
+    # Sim3-related frame + noise; quaternions about z.  GNSS stamps = SLAM stamps (association = identity, stated).
+    i = torch.arange(n, dtype=torch.float64, device=dev)
+    rows = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    rows[:, 0] = i * 0.1
+    rows[:, 1] = 49.0 + 4e-9 * i + 1e-4 * torch.sin(i * 1e-4)
+    rows[:, 2] = 8.4 + 6e-9 * i + 1e-4 * torch.cos(i * 7e-5)
+    rows[:, 3] = 112.0 + torch.sin(i * 1e-3)
+    _, enu, zone = fusion.gnss_rows_to_utm(rows, want_ts=False)
+    s_gt, a = 1.07, 0.6
+    Rg = torch.tensor([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]], dtype=torch.float64, device=dev)
+    pos = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    CH = 1 << 24
+    t_gt = enu[0].clone()
+    for a0 in range(0, n, CH):
+        sl = slice(a0, min(n, a0 + CH))
+        pos[sl] = ((enu[sl] - t_gt) / s_gt) @ Rg + 0.05 * torch.randn((sl.stop - sl.start, 3), dtype=torch.float64, device=dev, generator=g)
+    quat = torch.zeros((n, 4), dtype=torch.float64, device=dev)
+    quat[:, 2] = torch.sin(i * 1e-5); quat[:, 3] = torch.cos(i * 1e-5)
+    del i
+    off = torch.tensor([0, n], dtype=torch.int64, device=dev)
+    torch.cuda.synchronize(dev)
+
+    def step(ev=None):
+        _, z, zone_ = fusion.gnss_rows_to_utm(rows, want_ts=False)
+        if ev: ev[1].record()
+        R, t, s, st = fusion.umeyama_batched(pos, z, off, n)
+        if ev: ev[2].record()
+        p2, q2, st2 = fusion.sim3_apply_batched(pos, quat, off, n, R, t, s)
+        if ev: ev[3].record()
+        return R, t, s, st
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank); sampler.start()
+    stage = [[], [], []]
+    t_all = []
+    for _ in range(args.steps):
+        ev = _events(torch, 4)
+        ev[0].record()
+        R, t, s, st = step(ev)
+        torch.cuda.synchronize(dev)
+        for k in range(3):
+            stage[k].append(ev[k].elapsed_time(ev[k + 1]))
+        t_all.append(ev[0].elapsed_time(ev[3]))
+    clocks = sampler.stop()
+    ms = statistics.mean(t_all)
+    ms_ingest, ms_reduce, ms_apply = [statistics.mean(x) for x in stage]
+    peak, peak_src = read_peak()
+    scale_err = abs(float(s.cpu()[0]) - s_gt)
+    roofline = {"bound": "hbm", "achieved": n * 48 / (ms_reduce * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": n * 48 / (ms_reduce * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "sim3_tile_stats_kernel (Umeyama reduction, 48 B/point)", "launch_ms": ms_reduce,
+                "algorithmic_bytes_per_launch": n * 48,
+                "other_stages": {"gnss_rows_project_kernel (64 B/pt incl. the zone pass; transcendental-bound)":
+                                 {"ms": ms_ingest, "GB/s": n * 88 / (ms_ingest * 1e-3) / 1e9},
+                                 "sim3_apply_kernel (112 B/pt)": {"ms": ms_apply, "GB/s": n * 112 / (ms_apply * 1e-3) / 1e9}}}
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline_config4(rows[:2_000_000].cpu().numpy(), pos[:2_000_000].cpu().numpy(), quat[:2_000_000].cpu().numpy())
+    line = {"metric": "Sim3 aligned pts/s (GNSS ingest + Umeyama reduction + transform, single trajectory)", "value": n / (ms * 1e-3),
+            "unit": "pts/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config4: single {n}-pose trajectory: ENU conversion + Sim3 alignment",
+                       "stages_ms": {"gnss_ingest_utm": ms_ingest, "umeyama_reduce": ms_reduce, "transform_apply": ms_apply},
+                       "reduce_pts_per_s": n / (ms_reduce * 1e-3), "apply_pts_per_s": n / (ms_apply * 1e-3),
+                       "ingest_pts_per_s": n / (ms_ingest * 1e-3), "parallelism": "single GPU (replicas only)",
+                       "l2": "arrays of 0.8-3.2 GB each: far beyond L2, no flush needed",
+                       "recovered_scale_error": scale_err, "status": int(st.cpu()[0]), "zone": int(zone.cpu()[2])},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": 7 * args.steps}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_config4(rows, pos, quat):
+    """The same three stages with the oracle (numpy/scipy) on one core, 2e6-point sample."""
+    from oracle import fusion_oracle as fo
+    from oracle import utm_kruger as uk
+    t0 = time.perf_counter()
+    keep = uk.gnss_validity_mask(rows[:, 1], rows[:, 2])
+    zone, south = uk.utm_zone_from_means(rows[keep, 2], rows[keep, 1])
+    e, nn = uk.utm_forward(rows[keep, 2], rows[keep, 1], zone, south)
+    z = np.column_stack((e, nn, rows[keep, 3]))
+    R, t, s = fo.umeyama(pos[keep], z)
+    fo.sim3_apply(pos, quat, R, t, s)
+    dt = time.perf_counter() - t0
+    return {"value": len(rows) / dt, "unit": "pts/s", "cores": 1, "kind": "port",
+            "sample": f"first {len(rows)} points of the same trajectory, numpy/scipy oracle, single process"}

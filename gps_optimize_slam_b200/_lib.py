@@ -32,6 +32,7 @@ SIGNATURES = {
     "gsf_ate_nn_batched_dev": (c_int32, [c_void_p] * 4 + [c_int32, c_int64, c_double, c_void_p, c_void_p]),
     "gsf_utm_forward_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "gsf_utm_inverse_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gsf_gnss_rows_to_utm_dev": (c_int32, [c_void_p, c_int64] + [c_void_p] * 5),
     "gsf_geo_zone_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gsf_associate_spline_dev": (c_int32, [c_void_p] * 5 + [c_int32, c_double] + [c_void_p] * 4),
     "gsf_synth_generate_dev": (c_int32, [c_void_p] * 4 + [c_int64, c_int32, c_int32, c_double, c_double, c_uint64,

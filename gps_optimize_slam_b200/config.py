@@ -78,3 +78,14 @@ def pack_fuse_params(cfg=None, *, p0=None, q=None, r=None) -> np.ndarray:
         int(rc["min_samples"]), int(rts["default_ekf_transition_steps_on_sharp_turn"]))
     assert len(blob) == FUSE_PARAMS_BYTES
     return np.frombuffer(blob, dtype=np.uint8).copy()
+
+
+def pack_noise_grid(grid: np.ndarray, cfg=None) -> np.ndarray:
+    """Vectorised pack of [H,3] = (q_xy, q_z, r) hypotheses into H FuseParams records (uint8 [H*184])."""
+    base = np.frombuffer(pack_fuse_params(cfg).tobytes(), dtype=np.dtype([("d", "<f8", 22), ("i", "<i4", 2)]))
+    rec = np.repeat(base, len(grid))
+    d = rec["d"]
+    d[:, 7] = grid[:, 0]; d[:, 8] = grid[:, 0]; d[:, 9] = grid[:, 1]          # q x, y, z
+    d[:, 14] = grid[:, 2]; d[:, 15] = grid[:, 2]; d[:, 16] = grid[:, 2]       # r x, y, z
+    rec["d"] = d
+    return np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()

@@ -269,6 +269,17 @@ int gsf_utm_inverse_dev(const double* east, const double* north, int64_t n, int3
     if (e != cudaSuccess) return cuda_fail(e, "gsf_utm_inverse_dev");
     return 0;
 }
+int gsf_gnss_rows_to_utm_dev(const double* rows, int64_t n, double* part, double* zone_out,
+                             double* out_ts, double* out_xyz, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (n <= 0 || !rows || !part || !zone_out || !out_xyz) return fail(GSF_E_INVALID, "gsf_gnss_rows_to_utm_dev: bad argument");
+    if (!aligned16(rows)) return fail(GSF_E_INVALID, "gsf_gnss_rows_to_utm_dev: rows must be 16-byte aligned");
+    int nparts = (int)std::min<int64_t>(GSF_GEO_PARTS, (n + 255) / 256);
+    cudaError_t e = gsf::launch_gnss_rows(rows, n, utm_const(31, 0), part, nparts, zone_out, out_ts, out_xyz, d.sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_gnss_rows_to_utm_dev");
+    return 0;
+}
 int gsf_geo_zone_dev(const double* lon, const double* lat, int64_t n, double* part, double* out, void* stream) {
     DeviceInfo& d = device_info();
     if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");

@@ -33,6 +33,8 @@ cudaError_t launch_hypothesis_grid(const double*, const double*, const double*, 
 struct UtmConst { double A_k0; double e, e2; double alpha[6], beta[6]; double lon0; double fn; };
 cudaError_t launch_utm(bool inverse, const double* a, const double* b, long long n, const UtmConst& K, double* o1, double* o2,
                        int num_sms, cudaStream_t stream);
+cudaError_t launch_gnss_rows(const double* rows, long long n, const UtmConst& K, double* part, int nparts, double* zone_out,
+                             double* out_ts, double* out_xyz, int num_sms, cudaStream_t stream);
 cudaError_t launch_geo_mean(const double* lon, const double* lat, long long n, double* part, int nparts, double* out, cudaStream_t stream);
 struct AssocArgs {
     const double* gps_t; const double* gps_xyz; const long long* gps_off;

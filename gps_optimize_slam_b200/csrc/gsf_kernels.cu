@@ -36,23 +36,75 @@ __device__ __forceinline__ void krueger_series(const double* coef, double xi_in,
     eta = eta_in + sign * ay;
 }
 
+// forward projection of one point (lam = lon - lon0, phi in radians) -> (xi, eta) scaled later by A k0
+__device__ __forceinline__ void utm_forward_point(const UtmConst& K, double lam, double phi, double& xi, double& eta) {
+    const double tau = tan(phi);
+    const double t1 = sqrt(1.0 + tau * tau);
+    const double sigma = sinh(K.e * atanh(K.e * tau / t1));
+    const double taup = tau * sqrt(1.0 + sigma * sigma) - sigma * t1;
+    double sl, cl;
+    sincos(lam, &sl, &cl);
+    const double xip = atan2(taup, cl);
+    const double etap = asinh(sl / sqrt(taup * taup + cl * cl));
+    krueger_series(K.alpha, xip, etap, 1.0, xi, eta);
+}
+
 __global__ void utm_forward_kernel(const double* __restrict__ lon, const double* __restrict__ lat, long long n,
                                    const UtmConst K, double* __restrict__ east, double* __restrict__ north) {
     const double D2R = 0.017453292519943295769236907684886;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double lam = lon[i] * D2R - K.lon0, phi = lat[i] * D2R;
-        const double tau = tan(phi);
-        const double t1 = sqrt(1.0 + tau * tau);
-        const double sigma = sinh(K.e * atanh(K.e * tau / t1));
-        const double taup = tau * sqrt(1.0 + sigma * sigma) - sigma * t1;
-        double sl, cl;
-        sincos(lam, &sl, &cl);
-        const double xip = atan2(taup, cl);
-        const double etap = asinh(sl / sqrt(taup * taup + cl * cl));
         double xi, eta;
-        krueger_series(K.alpha, xip, etap, 1.0, xi, eta);
+        utm_forward_point(K, lon[i] * D2R - K.lon0, lat[i] * D2R, xi, eta);
         east[i] = 500000.0 + K.A_k0 * eta;
         north[i] = K.fn + K.A_k0 * xi;
+    }
+}
+
+// ---- fused GNSS-row ingest (load_gps_data :258-271 + auto_utm_projection :127-134): rows [n,4] = ts, lat, lon, alt
+// in the loader's column order.  Row validity (:259): |lat| <= 90, |lon| <= 180, lat != 0, lon != 0.
+__device__ __forceinline__ bool gnss_row_valid(double lat, double lon) {
+    return fabs(lat) <= 90.0 && fabs(lon) <= 180.0 && lat != 0.0 && lon != 0.0;
+}
+// Stage 1 of the masked means: fixed grid, fixed stride order -> part[grid][3] = sum lon, sum lat, count.
+__global__ void gnss_rows_sum_kernel(const double* __restrict__ rows, long long n, double* __restrict__ part) {
+    __shared__ double scratch[3 * 8];
+    const double2* __restrict__ r2 = reinterpret_cast<const double2*>(rows);
+    double v[3] = {0.0, 0.0, 0.0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 a = __ldg(r2 + 2 * i), b = __ldg(r2 + 2 * i + 1);       // (ts, lat), (lon, alt)
+        if (gnss_row_valid(a.y, b.x)) { v[0] += b.x; v[1] += a.y; v[2] += 1.0; }
+    }
+    block_sum<3>(v, scratch);
+    if (threadIdx.x == 0) { part[3 * blockIdx.x] = v[0]; part[3 * blockIdx.x + 1] = v[1]; part[3 * blockIdx.x + 2] = v[2]; }
+}
+// Stage 2 (one thread): out = mean lon, mean lat, zone, south flag, valid count.
+__global__ void gnss_rows_zone_kernel(const double* part, int nparts, double* out) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = 0; i < nparts; ++i) { a += part[3 * i]; b += part[3 * i + 1]; c += part[3 * i + 2]; }
+    a /= c; b /= c;
+    out[0] = a; out[1] = b;
+    out[2] = floor((a + 180.0) / 6.0) + 1.0;           // int((mean_lon + 180) // 6 + 1)
+    out[3] = (b < 0.0) ? 1.0 : 0.0;
+    out[4] = c;
+}
+// Projection: one thread per row, two 128-bit loads; zone / hemisphere are read from device memory (no host
+// round trip).  Invalid rows become NaN measurements ("no GNSS at this stamp").
+__global__ void __launch_bounds__(256) gnss_rows_project_kernel(const double* __restrict__ rows, long long n, UtmConst K,
+                                                                const double* __restrict__ zone_dev, double* __restrict__ out_ts,
+                                                                double* __restrict__ out_xyz) {
+    const double D2R = 0.017453292519943295769236907684886;
+    const double lon0 = (6.0 * zone_dev[2] - 183.0) * D2R, fn = zone_dev[3] != 0.0 ? 10000000.0 : 0.0;
+    const double2* __restrict__ r2 = reinterpret_cast<const double2*>(rows);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 a = __ldg(r2 + 2 * i), b = __ldg(r2 + 2 * i + 1);       // (ts, lat), (lon, alt)
+        double e = nan(""), nn = nan(""), up = nan("");
+        if (gnss_row_valid(a.y, b.x)) {
+            double xi, eta;
+            utm_forward_point(K, b.x * D2R - lon0, a.y * D2R, xi, eta);
+            e = 500000.0 + K.A_k0 * eta; nn = fn + K.A_k0 * xi; up = b.y;
+        }
+        if (out_ts) out_ts[i] = a.x;
+        out_xyz[3 * i] = e; out_xyz[3 * i + 1] = nn; out_xyz[3 * i + 2] = up;
     }
 }
 
@@ -439,6 +491,16 @@ cudaError_t launch_utm(bool inverse, const double* a, const double* b, long long
     if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
     if (inverse) utm_inverse_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, b, n, K, o1, o2);
     else utm_forward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, b, n, K, o1, o2);
+    return cudaGetLastError();
+}
+cudaError_t launch_gnss_rows(const double* rows, long long n, const UtmConst& K, double* part, int nparts, double* zone_out,
+                             double* out_ts, double* out_xyz, int num_sms, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    gnss_rows_sum_kernel<<<nparts, 256, 0, stream>>>(rows, n, part);
+    gnss_rows_zone_kernel<<<1, 1, 0, stream>>>(part, nparts, zone_out);
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+    gnss_rows_project_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rows, n, K, zone_out, out_ts, out_xyz);
     return cudaGetLastError();
 }
 cudaError_t launch_geo_mean(const double* lon, const double* lat, long long n, double* part, int nparts, double* out, cudaStream_t stream) {

@@ -76,6 +76,23 @@ def fuse_batched(ts, pos, quat, z, offsets, max_len, params, params_per_traj=Fal
     return out_pos, out_quat, sim3_out, status
 
 
+def gnss_rows_to_utm(rows, want_ts=True, stream=None):
+    """Fused GNSS ingest (gsf_gnss_rows_to_utm_dev): rows [n,4] = ts, lat, lon, alt ->
+    (ts [n] or None, xyz [n,3] = E, N, alt with NaN rows where the validity mask fails,
+    zone [5] = mean lon, mean lat, zone, south, valid count); asynchronous, zone stays on the device."""
+    lib = _lib.load()
+    _require_cuda(rows)
+    n = rows.shape[0]
+    dev = rows.device
+    part = torch.empty((3 * _lib.GEO_PARTS,), dtype=torch.float64, device=dev)
+    zone = torch.empty((5,), dtype=torch.float64, device=dev)
+    ts = torch.empty((n,), dtype=torch.float64, device=dev) if want_ts else None
+    xyz = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    rc = lib.gsf_gnss_rows_to_utm_dev(_ptr(rows), int(n), _ptr(part), _ptr(zone), _ptr(ts), _ptr(xyz), _stream_ptr(stream))
+    _lib.check(rc, "gsf_gnss_rows_to_utm_dev")
+    return ts, xyz, zone
+
+
 def hypothesis_grid(ts, pos, quat, z, params, stream=None):
     """One trajectory x H noise-parameter hypotheses -> ATE statistics (gsf_ekf_hypothesis_grid_dev).
     ts [n], pos [n,3], quat [n,4], z [n,3] (all valid); params: uint8 [H*184] packed FuseParams records.

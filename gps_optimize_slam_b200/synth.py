@@ -70,3 +70,32 @@ def make_batch(seed0: int, batch: int, n: int, **kw):
     items = [make_trajectory(seed0 + b, n, **kw) for b in range(batch)]
     return (np.stack([i["ts"] for i in items]), np.stack([i["pos"] for i in items]),
             np.stack([i["quat"] for i in items]), np.stack([i["gps"] for i in items]))
+
+
+def make_loop_trajectory(seed: int, n: int = 4541, dt: float = 0.104, speed: float = 10.0):
+    """Closed-loop track of KITTI-00 length (BASELINE config 5; no KITTI-00 data ships): one lap of a
+    wobbly circle, every pose with GNSS.  Same Sim3 / drift / noise model as make_trajectory."""
+    rng = np.random.default_rng(seed)
+    ts = np.arange(n) * dt
+    lap = 2.0 * np.pi * np.arange(n) / n
+    yaw = lap + 0.15 * np.sin(5 * lap) + rng.uniform(-np.pi, np.pi)
+    vel = speed * np.stack([np.cos(yaw), np.sin(yaw), 0.02 * np.sin(0.05 * np.arange(n))], axis=1)
+    world = WORLD_ORIGIN + np.cumsum(vel * dt, axis=0)
+    world_q = _quat_z(yaw)
+    s_gt, a_gt = rng.uniform(0.9, 1.1), rng.uniform(-np.pi, np.pi)
+    ca, sa = np.cos(a_gt), np.sin(a_gt)
+    Rg = np.array([[ca, -sa, 0], [sa, ca, 0], [0, 0, 1.0]])
+    slam_true = ((world - world[0]) / s_gt) @ Rg
+    drift_p = np.cumsum(rng.normal(0, 0.02, (n, 3)) * np.array([1, 1, 0.2]), axis=0)
+    drift_yaw = np.cumsum(rng.normal(0, np.deg2rad(0.2), n))
+    slam_q = _qmul(_quat_z(np.full(n, -a_gt) + drift_yaw), world_q)
+    gps = world + rng.normal(0, 0.3, (n, 3))
+    return {"ts": ts, "pos": slam_true + drift_p, "quat": slam_q, "gps": gps}
+
+
+def noise_grid(k: int = 64):
+    """BASELINE config 5: k^3 log-spaced hypotheses over (Q_xy in [1e-3, 1e1], Q_z in [1e-3, 1e1],
+    R in [1e-2, 1e1]), Q_quat and P0 fixed.  Returns float64 [k^3, 3] = q_xy, q_z, r."""
+    qxy = np.logspace(-3, 1, k); qz = np.logspace(-3, 1, k); r = np.logspace(-2, 1, k)
+    g = np.stack(np.meshgrid(qxy, qz, r, indexing="ij"), axis=-1).reshape(-1, 3)
+    return g

@@ -140,6 +140,15 @@ int gsf_utm_inverse_dev(const double* east, const double* north, int64_t n, int3
 #define GSF_GEO_PARTS 1024
 int gsf_geo_zone_dev(const double* lon, const double* lat, int64_t n, double* part, double* out, void* stream);
 
+/* ---- fused GNSS ingest: the projection part of load_gps_data (:258-271) with auto_utm_projection
+ *      (:127-134).  rows [n,4] = timestamp, lat, lon, alt in the loader's column order (:258), 16-byte
+ *      aligned.  Rows failing the validity mask (:259) do not enter the zone means and come out as NaN
+ *      measurements.  zone_out[5] = mean lon, mean lat, zone, south flag, valid rows (device; the
+ *      projection reads the zone from there: no host round trip).  part: 3*GSF_GEO_PARTS doubles.
+ *      out_ts [n] (may be NULL), out_xyz [n,3] = easting, northing, altitude. */
+int gsf_gnss_rows_to_utm_dev(const double* rows, int64_t n, double* part, double* zone_out,
+                             double* out_ts, double* out_xyz, void* stream);
+
 /* ---- dynamic_time_alignment (:325-387) after the host-side argsort/unique (:340-349):
  *      per-segment not-a-knot cubic / linear interpolation of the GNSS track at the SLAM
  *      stamps.  work: 4 doubles per GNSS sample.  aligned [n_slam,3] NaN-filled, valid [n_slam]. */

@@ -272,6 +272,32 @@ def test_utm_kernels(gsf):
         np.testing.assert_allclose(np.column_stack((e.cpu().numpy(), n.cpu().numpy())), g["gps_utm"][:, :2], rtol=0, atol=2e-8)
 
 
+def test_fused_gnss_ingest_matches_loader_and_oracle(gsf):
+    """gsf_gnss_rows_to_utm_dev against the shipped GNSS files as the reference's loader sees them
+    (golden gps_utm) and against the oracle on rows with invalid entries / a southern-hemisphere track."""
+    from oracle import utm_kruger as uk
+    for case in ("pairA", "pairB"):
+        g = load_golden(case)
+        ts, xyz, zone = gsf.gnss_rows_to_utm(dev(g["gnss_raw"]))
+        keep = uk.gnss_validity_mask(g["gnss_raw"][:, 1], g["gnss_raw"][:, 2])
+        z = zone.cpu().numpy()
+        assert f"{int(z[2])}{'S' if z[3] else 'N'}" == str(g["utm_zone"]) and int(z[4]) == keep.sum()
+        np.testing.assert_allclose(xyz.cpu().numpy()[keep], g["gps_utm"], rtol=0, atol=1e-8)
+        np.testing.assert_array_equal(ts.cpu().numpy(), g["gnss_raw"][:, 0])
+    rng = np.random.default_rng(17)
+    n = 100003
+    rows = np.column_stack([np.arange(n) * 0.1, -33.9 + rng.normal(0, 0.05, n), 151.2 + rng.normal(0, 0.05, n), 30 + rng.normal(0, 2, n)])
+    rows[5, 1] = 0.0; rows[77, 2] = 0.0; rows[500, 1] = 91.0; rows[900, 2] = -181.0
+    keep = uk.gnss_validity_mask(rows[:, 1], rows[:, 2])
+    zone_o, south_o = uk.utm_zone_from_means(rows[keep, 2], rows[keep, 1])
+    e, nn = uk.utm_forward(rows[keep, 2], rows[keep, 1], zone_o, south_o)
+    _, xyz, zone = gsf.gnss_rows_to_utm(dev(rows), want_ts=False)
+    xyz = xyz.cpu().numpy(); z = zone.cpu().numpy()
+    assert int(z[2]) == zone_o and bool(z[3]) == south_o and south_o
+    assert np.isnan(xyz[~keep]).all()
+    np.testing.assert_allclose(xyz[keep], np.column_stack((e, nn, rows[keep, 3])), rtol=0, atol=1e-8)
+
+
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_association_kernel_matches_reference_golden(gsf, case):
     g = load_golden(case)
