@@ -262,10 +262,27 @@ __global__ void associate_kernel(const AssocArgs A) {
 // the data, any trajectory length, bit-reproducible.
 constexpr int SIM3_TILE = 8192;
 constexpr int SIM3_STAT = 20;    // n, mu_s[3], mu_d[3], H[9], ss, pad[3]
+// Tile length as a function of the longest trajectory only (so results do not depend on the device): 8192
+// points up to 8M-point trajectories, beyond that at most 1024 tiles per trajectory.
+__host__ __device__ inline long long sim3_tile_len(long long max_len) {
+    if (max_len <= (long long)SIM3_TILE * 1024) return SIM3_TILE;
+    const long long t = (max_len + 1023) / 1024;
+    return (t + 511) / 512 * 512;
+}
+
+__device__ __forceinline__ void sim3_accumulate(double* v, const double* piv, double s0, double s1, double s2, double d0, double d1, double d2) {
+    const double a0 = s0 - piv[0], a1 = s1 - piv[1], a2 = s2 - piv[2];
+    const double b0 = d0 - piv[3], b1 = d1 - piv[4], b2 = d2 - piv[5];
+    v[0] += 1.0; v[1] += a0; v[2] += a1; v[3] += a2; v[4] += b0; v[5] += b1; v[6] += b2;
+    v[7] += a0 * b0; v[8] += a0 * b1; v[9] += a0 * b2;
+    v[10] += a1 * b0; v[11] += a1 * b1; v[12] += a1 * b2;
+    v[13] += a2 * b0; v[14] += a2 * b1; v[15] += a2 * b2;
+    v[16] += a0 * a0 + a1 * a1 + a2 * a2;
+}
 
 __global__ void __launch_bounds__(256) sim3_tile_stats_kernel(const double* __restrict__ src, const double* __restrict__ dst,
                                                               const long long* __restrict__ offsets,
-                                                              const unsigned char* __restrict__ mask, int tiles_max,
+                                                              const unsigned char* __restrict__ mask, int tiles_max, long long tile_len,
                                                               double* __restrict__ stats) {
     __shared__ double scratch[17 * 8];
     __shared__ double piv[6];
@@ -274,9 +291,9 @@ __global__ void __launch_bounds__(256) sim3_tile_stats_kernel(const double* __re
     const long long e0 = offsets[b];
     const long long n = offsets[b + 1] - e0;
     double* o = stats + ((size_t)b * tiles_max + tile) * SIM3_STAT;
-    const long long lo = (long long)tile * SIM3_TILE;
+    const long long lo = (long long)tile * tile_len;
     if (lo >= n) { if (threadIdx.x == 0) o[0] = 0.0; return; }
-    const long long hi = min(n, lo + SIM3_TILE);
+    const long long hi = min(n, lo + tile_len);
     if (threadIdx.x == 0) piv_idx = 0x7fffffff;
     __syncthreads();
     for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x)
@@ -291,61 +308,91 @@ __global__ void __launch_bounds__(256) sim3_tile_stats_kernel(const double* __re
     double v[17];
 #pragma unroll
     for (int k = 0; k < 17; ++k) v[k] = 0.0;
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const long long g = e0 + i;
-        if (mask && !mask[g]) continue;
-        const double a0 = src[3 * g] - piv[0], a1 = src[3 * g + 1] - piv[1], a2 = src[3 * g + 2] - piv[2];
-        const double b0 = dst[3 * g] - piv[3], b1 = dst[3 * g + 1] - piv[4], b2 = dst[3 * g + 2] - piv[5];
-        v[0] += 1.0; v[1] += a0; v[2] += a1; v[3] += a2; v[4] += b0; v[5] += b1; v[6] += b2;
-        v[7] += a0 * b0; v[8] += a0 * b1; v[9] += a0 * b2;
-        v[10] += a1 * b0; v[11] += a1 * b1; v[12] += a1 * b2;
-        v[13] += a2 * b0; v[14] += a2 * b1; v[15] += a2 * b2;
-        v[16] += a0 * a0 + a1 * a1 + a2 * a2;
+    // Point pairs (2p, 2p+1) of the tile, pairs strided over the threads: the same summation order whether the
+    // rows are 16-byte aligned (three 128-bit loads per array and pair) or not (64-bit loads).
+    const long long g0 = e0 + lo, cnt = hi - lo, npairs = (cnt + 1) >> 1;
+    const bool vec = !(g0 & 1) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(src + 3 * g0);
+    const double2* __restrict__ d2 = reinterpret_cast<const double2*>(dst + 3 * g0);
+    for (long long p = threadIdx.x; p < npairs; p += 256) {
+        const long long i = 2 * p;
+        const bool two = i + 1 < cnt;
+        const bool m0 = !mask || mask[g0 + i], m1 = two && (!mask || mask[g0 + i + 1]);
+        if (vec && two) {
+            const double2 a0 = __ldg(s2 + 3 * p), a1 = __ldg(s2 + 3 * p + 1), a2 = __ldg(s2 + 3 * p + 2);
+            const double2 b0 = __ldg(d2 + 3 * p), b1 = __ldg(d2 + 3 * p + 1), b2 = __ldg(d2 + 3 * p + 2);
+            if (m0) sim3_accumulate(v, piv, a0.x, a0.y, a1.x, b0.x, b0.y, b1.x);
+            if (m1) sim3_accumulate(v, piv, a1.y, a2.x, a2.y, b1.y, b2.x, b2.y);
+        } else {
+            const long long g = g0 + i;
+            if (m0) sim3_accumulate(v, piv, src[3 * g], src[3 * g + 1], src[3 * g + 2], dst[3 * g], dst[3 * g + 1], dst[3 * g + 2]);
+            if (m1) sim3_accumulate(v, piv, src[3 * g + 3], src[3 * g + 4], src[3 * g + 5], dst[3 * g + 3], dst[3 * g + 4], dst[3 * g + 5]);
+        }
     }
     block_sum<17>(v, scratch);
     if (threadIdx.x == 0) {
-        const double cnt = v[0], inv = 1.0 / cnt;
+        const double cnt_v = v[0], inv = 1.0 / cnt_v;
         const double ma[3] = {v[1] * inv, v[2] * inv, v[3] * inv}, mb[3] = {v[4] * inv, v[5] * inv, v[6] * inv};
-        o[0] = cnt;
+        o[0] = cnt_v;
         for (int k = 0; k < 3; ++k) { o[1 + k] = piv[k] + ma[k]; o[4 + k] = piv[3 + k] + mb[k]; }
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o[7 + 3 * r + c] = v[7 + 3 * r + c] - cnt * ma[r] * mb[c];
-        o[16] = v[16] - cnt * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o[7 + 3 * r + c] = v[7 + 3 * r + c] - cnt_v * ma[r] * mb[c];
+        o[16] = v[16] - cnt_v * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
     }
 }
 
-__global__ void sim3_finalize_kernel(const double* __restrict__ stats, int tiles_max, int B,
-                                     double* __restrict__ Rout, double* __restrict__ tout, double* __restrict__ sout,
-                                     int* __restrict__ status) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    double n = 0.0, ms[3] = {0, 0, 0}, md[3] = {0, 0, 0}, H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ss = 0.0;
-    for (int tl = 0; tl < tiles_max; ++tl) {
-        const double* o = stats + ((size_t)b * tiles_max + tl) * SIM3_STAT;
-        const double m = o[0];
-        if (m == 0.0) continue;
-        if (n == 0.0) {
-            n = m;
-            for (int k = 0; k < 3; ++k) { ms[k] = o[1 + k]; md[k] = o[4 + k]; }
-            for (int k = 0; k < 9; ++k) H[k] = o[7 + k];
-            ss = o[16];
-            continue;
-        }
-        const double tot = n + m, w = n * m / tot;
-        double da[3], db[3];
-        for (int k = 0; k < 3; ++k) { da[k] = o[1 + k] - ms[k]; db[k] = o[4 + k] - md[k]; }
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) H[3 * r + c] += o[7 + 3 * r + c] + w * da[r] * db[c];
-        ss += o[16] + w * (da[0] * da[0] + da[1] * da[1] + da[2] * da[2]);
-        for (int k = 0; k < 3; ++k) { ms[k] += da[k] * (m / tot); md[k] += db[k] * (m / tot); }
-        n = tot;
+// Pairwise-covariance merge of two (n, means, centred H, ss) records, `a` before `b` in point order.
+__device__ __forceinline__ void sim3_merge(double* a, const double* b) {
+    const double m = b[0];
+    if (m == 0.0) return;
+    if (a[0] == 0.0) {
+#pragma unroll
+        for (int k = 0; k < 17; ++k) a[k] = b[k];
+        return;
     }
+    const double n = a[0], tot = n + m, w = n * m / tot;
+    double da[3], db[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { da[k] = b[1 + k] - a[1 + k]; db[k] = b[4 + k] - a[4 + k]; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[7 + 3 * r + c] += b[7 + 3 * r + c] + w * da[r] * db[c];
+    a[16] += b[16] + w * (da[0] * da[0] + da[1] * da[1] + da[2] * da[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a[1 + k] += da[k] * (m / tot); a[4 + k] += db[k] * (m / tot); }
+    a[0] = tot;
+}
+
+// One warp per trajectory: every lane merges a contiguous run of tiles in tile order, then the lanes are merged
+// by a fixed in-order tree (lane L absorbs lane L + o for o = 1, 2, 4, ...) -> deterministic; lane 0 finishes.
+__global__ void __launch_bounds__(128) sim3_finalize_kernel(const double* __restrict__ stats, int tiles_max, int B,
+                                                            double* __restrict__ Rout, double* __restrict__ tout, double* __restrict__ sout,
+                                                            int* __restrict__ status) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    double acc[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) acc[k] = 0.0;
+    const int per = (tiles_max + 31) / 32;
+    for (int tl = lane * per; tl < min(tiles_max, (lane + 1) * per); ++tl) sim3_merge(acc, stats + ((size_t)b * tiles_max + tl) * SIM3_STAT);
+    if (tiles_max > 1) {
+#pragma unroll 1
+        for (int o = 1; o < 32; o <<= 1) {
+            double other[17];
+#pragma unroll
+            for (int k = 0; k < 17; ++k) other[k] = __shfl_down_sync(GSF_FULL_MASK, acc[k], o);
+            if ((lane & (2 * o - 1)) == 0) sim3_merge(acc, other);
+        }
+    }
+    if (lane != 0) return;
     double* R = Rout + 9 * (size_t)b; double* t = tout + 3 * (size_t)b;
-    if (n < 3.0) {                                      // (None, None, None), :431
+    if (acc[0] < 3.0) {                                 // (None, None, None), :431
         for (int k = 0; k < 9; ++k) R[k] = nan("");
         t[0] = t[1] = t[2] = nan(""); sout[b] = nan(""); status[b] = ST_TOO_FEW_POINTS;
         return;
     }
     double s;
-    status[b] = umeyama_finish((int)n, ms, md, H, ss, R, t, s);
+    status[b] = umeyama_finish((int)acc[0], acc + 1, acc + 4, acc + 7, acc[16], R, t, s);
     sout[b] = s;
 }
 
@@ -514,7 +561,7 @@ cudaError_t launch_associate(const AssocArgs& a, int num_sms, cudaStream_t strea
     associate_kernel<<<grid, 128, 0, stream>>>(a);
     return cudaGetLastError();
 }
-int sim3_tiles_for(long long max_len) { return (int)((max_len + SIM3_TILE - 1) / SIM3_TILE) > 0 ? (int)((max_len + SIM3_TILE - 1) / SIM3_TILE) : 1; }
+int sim3_tiles_for(long long max_len) { const long long tl = sim3_tile_len(max_len); const long long t = (max_len + tl - 1) / tl; return t > 0 ? (int)t : 1; }
 cudaError_t launch_umeyama(const double* src, const double* dst, const long long* offsets, const unsigned char* mask,
                            int B, long long max_len, double* work, double* R, double* t, double* s, int* status, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
@@ -522,9 +569,9 @@ cudaError_t launch_umeyama(const double* src, const double* dst, const long long
     for (int b0 = 0; b0 < B; b0 += 65535) {                    // gridDim.y limit
         const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
         dim3 grid(tiles, nb);
-        sim3_tile_stats_kernel<<<grid, 256, 0, stream>>>(src, dst, offsets + b0, mask, tiles, work + (size_t)b0 * tiles * SIM3_STAT);
+        sim3_tile_stats_kernel<<<grid, 256, 0, stream>>>(src, dst, offsets + b0, mask, tiles, sim3_tile_len(max_len), work + (size_t)b0 * tiles * SIM3_STAT);
     }
-    sim3_finalize_kernel<<<(B + 63) / 64, 64, 0, stream>>>(work, tiles, B, R, t, s, status);
+    sim3_finalize_kernel<<<(B + 3) / 4, 128, 0, stream>>>(work, tiles, B, R, t, s, status);
     return cudaGetLastError();
 }
 cudaError_t launch_sim3_apply(const double* pos, const double* quat, const long long* offsets, const double* R, const double* t,
