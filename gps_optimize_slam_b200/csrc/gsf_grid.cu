@@ -13,7 +13,7 @@
 // neighbour is found exactly by scanning outwards in the x-sorted candidate order from the pose's own
 // measurement until the 1-D gap alone exceeds the best distance (the pose's own measurement is always a
 // candidate, so the first bound is its innovation).  Errors go to a [poses, hypotheses] table (coalesced);
-// a second kernel sorts each hypothesis' column for the median.  FP64-pipe bound; no tensor cores.
+// a second kernel radix-selects the median of each hypothesis' column.  FP64-pipe bound; no tensor cores.
 // Restriction (status GSF_ST_GRID_NEEDS_ALL_VALID otherwise): every pose has a GNSS measurement, i.e. no
 // outage / RTS segments (those need per-hypothesis history; use gsf_fuse_batched_dev with per-trajectory
 // parameters for such data).
@@ -232,30 +232,107 @@ __global__ void __launch_bounds__(GRID_THREADS) ekf_grid_kernel(const double* __
 }
 
 // ----------------------------------------------------------------------------- median of each hypothesis' error column
+// Exact order statistics by radix selection on the bit patterns (errors are >= 0, so the IEEE patterns order like
+// unsigned integers): 8-bit digits from the top, per pass a 256-bin histogram of the digit among the elements that
+// still match the selected prefix, then the bin holding the wanted rank.  One block handles FOUR adjacent hypotheses
+// (one 32-byte sector of a table row) and both middle ranks (np.median of an even count averages them) at once:
+// hist[4][2][256].  Passes whose digit is identical for the whole column (sign / exponent bytes, typically) are
+// skipped through the column's min / max keys.
+constexpr int MED_Q = 4;
 __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restrict__ err, const double* __restrict__ hdr, int H,
                                                           double* __restrict__ stats, const int* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* v = reinterpret_cast<double*>(smem_raw);
+    __shared__ unsigned int hist[MED_Q][2][256];
+    __shared__ unsigned long long prefix[MED_Q][2], kmin[MED_Q], kmax[MED_Q];
+    __shared__ unsigned int rank[MED_Q][2];
     const int m = (int)hdr[3];
     if ((status[0] & GRID_FATAL) || (int)hdr[4] != m || m == 0) return;
-    int p2 = 1; while (p2 < m) p2 <<= 1;
-    for (int h = blockIdx.x; h < H; h += gridDim.x) {
+    const int nquads = (H + MED_Q - 1) / MED_Q;
+    const int tid = threadIdx.x;
+    for (int quad = blockIdx.x; quad < nquads; quad += gridDim.x) {
+        const int h0 = quad * MED_Q;
+        const int nq = min(MED_Q, H - h0);
+        const bool vec = nq == MED_Q && (H % MED_Q) == 0;                 // rows of the quad are 32-byte aligned
         __syncthreads();
-        for (int k = threadIdx.x; k < p2; k += 256) v[k] = k < m ? err[(size_t)k * H + h] : INFINITY;
+        if (tid < MED_Q) { kmin[tid] = ~0ull; kmax[tid] = 0ull; rank[tid][0] = (unsigned)((m - 1) / 2); rank[tid][1] = (unsigned)(m / 2); prefix[tid][0] = prefix[tid][1] = 0ull; }
         __syncthreads();
-        for (int k = 2; k <= p2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = threadIdx.x; i < p2; i += 256) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const double a = v[i], c = v[l];
-                        const bool up = (i & k) == 0;
-                        if ((a > c) == up) { v[i] = c; v[l] = a; }
-                    }
-                }
-                __syncthreads();
+        auto load_row = [&](int r, unsigned long long* k) {
+            const double* p = err + (size_t)r * H + h0;
+            if (vec) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+                k[0] = (unsigned long long)__double_as_longlong(a.x); k[1] = (unsigned long long)__double_as_longlong(a.y);
+                k[2] = (unsigned long long)__double_as_longlong(b.x); k[3] = (unsigned long long)__double_as_longlong(b.y);
+            } else {
+#pragma unroll
+                for (int q = 0; q < MED_Q; ++q) k[q] = q < nq ? (unsigned long long)__double_as_longlong(p[q]) : 0ull;
             }
-        if (threadIdx.x == 0) stats[4 * (size_t)h + 1] = (m & 1) ? v[m / 2] : 0.5 * (v[m / 2 - 1] + v[m / 2]);
+        };
+        // column min / max keys
+        {
+            unsigned long long lo[MED_Q], hi[MED_Q];
+#pragma unroll
+            for (int q = 0; q < MED_Q; ++q) { lo[q] = ~0ull; hi[q] = 0ull; }
+            for (int r = tid; r < m; r += 256) {
+                unsigned long long k[MED_Q];
+                load_row(r, k);
+#pragma unroll
+                for (int q = 0; q < MED_Q; ++q) { lo[q] = min(lo[q], k[q]); hi[q] = max(hi[q], k[q]); }
+            }
+#pragma unroll
+            for (int q = 0; q < MED_Q; ++q) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { lo[q] = min(lo[q], __shfl_xor_sync(GSF_FULL_MASK, lo[q], o)); hi[q] = max(hi[q], __shfl_xor_sync(GSF_FULL_MASK, hi[q], o)); }
+                if ((tid & 31) == 0) { atomicMin(&kmin[q], lo[q]); atomicMax(&kmax[q], hi[q]); }
+            }
+        }
+        __syncthreads();
+        // first digit position (from the top) where any column of the quad varies
+        int first = 8;
+        for (int q = 0; q < nq; ++q) {
+            const unsigned long long x = kmin[q] ^ kmax[q];
+            const int d = x ? (__clzll((long long)x) >> 3) : 8;
+            first = min(first, d);
+        }
+        if (tid < MED_Q) {                                                  // bytes above `first` are common to the whole column
+            const unsigned long long keep = first == 0 ? 0ull : (~0ull << (64 - 8 * first));
+            prefix[tid][0] = prefix[tid][1] = kmin[tid] & keep;
+        }
+        __syncthreads();
+        for (int d = first; d < 8; ++d) {
+            const int shift = 56 - 8 * d;
+            for (int k = tid; k < MED_Q * 2 * 256; k += 256) (&hist[0][0][0])[k] = 0u;
+            __syncthreads();
+            const unsigned long long himask = d == 0 ? 0ull : (~0ull << (64 - 8 * d));
+            unsigned long long pf[MED_Q][2];
+#pragma unroll
+            for (int q = 0; q < MED_Q; ++q) { pf[q][0] = prefix[q][0]; pf[q][1] = prefix[q][1]; }
+            for (int r = tid; r < m; r += 256) {
+                unsigned long long k[MED_Q];
+                load_row(r, k);
+#pragma unroll
+                for (int q = 0; q < MED_Q; ++q) {
+                    const unsigned dig = (unsigned)(k[q] >> shift) & 255u;
+                    const unsigned long long top = k[q] & himask;
+                    if (top == pf[q][0]) atomicAdd(&hist[q][0][dig], 1u);
+                    if (top == pf[q][1]) atomicAdd(&hist[q][1][dig], 1u);
+                }
+            }
+            __syncthreads();
+            if (tid < MED_Q * 2) {                                          // one thread per (hypothesis, rank): find the bin
+                const int q = tid >> 1, w = tid & 1;
+                unsigned r = rank[q][w], acc = 0;
+                int bin = 0;
+                for (; bin < 255; ++bin) { const unsigned c = hist[q][w][bin]; if (acc + c > r) break; acc += c; }
+                rank[q][w] = r - acc;
+                prefix[q][w] |= (unsigned long long)bin << shift;
+            }
+            __syncthreads();
+        }
+        if (tid < nq) {
+            const int h = h0 + tid;
+            double* o = stats + 4 * (size_t)h;
+            const double a = __longlong_as_double((long long)prefix[tid][0]), b = __longlong_as_double((long long)prefix[tid][1]);
+            o[1] = (o[0] != o[0]) ? nan("") : ((m & 1) ? a : 0.5 * (a + b));     // a NaN error (NaN mean) -> NaN median, like np.median
+        }
     }
 }
 
@@ -264,7 +341,7 @@ static int pow2_at_least(long long n) { int p = 1; while (p < n) p <<= 1; return
 // work layout (doubles): hdr[16] | R[9] t[3] s[1] pad[3] | offsets2 (2 long long) | status (4 ints = 2 doubles) |
 //                        rec[8 n] | cand[3 n] | umeyama tiles | mask (n bytes, padded) | err [n x H]
 long long grid_work_doubles(long long n, int H) {
-    return 16 + 16 + 2 + 2 + 8 * n + 3 * n + (long long)sim3_tiles_for(n) * 20 + (n + 7) / 8 + n * (long long)H;
+    return 16 + 16 + 2 + 2 + 8 * n + 3 * n + (long long)sim3_tiles_for(n) * 20 + (n + 7) / 8 + 4 + n * (long long)H;
 }
 cudaError_t launch_hypothesis_grid(const double* ts, const double* pos, const double* quat, const double* z, long long n,
                                    const FuseParams* params, int H, double* work, double* stats, double* sim3_out, int* status_out,
@@ -278,11 +355,11 @@ cudaError_t launch_hypothesis_grid(const double* ts, const double* pos, const do
     double* uwork = cand + 3 * n;
     unsigned char* mask = reinterpret_cast<unsigned char*>(uwork + (size_t)sim3_tiles_for(n) * 20);
     double* err = reinterpret_cast<double*>(mask) + (n + 7) / 8;
+    err = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(err) + 31) & ~(uintptr_t)31);      // 32-byte rows for the median kernel
     const int cap2 = pow2_at_least(n);
     const size_t smem_prep = (size_t)cap2 * 12;
     const size_t smem_grid = (size_t)2 * GRID_TILE * GRID_REC * 8 + 16 + (size_t)n * 24;
-    const size_t smem_med = (size_t)cap2 * 8;
-    if (smem_prep > (size_t)max_smem || smem_grid > (size_t)max_smem || smem_med > (size_t)max_smem) return cudaErrorInvalidValue;
+    if (smem_prep > (size_t)max_smem || smem_grid > (size_t)max_smem || false) return cudaErrorInvalidValue;
     grid_prep_select_kernel<<<1, 1024, 0, stream>>>(ts, z, (int)n, params, mask, offsets2, st);
     cudaError_t e = launch_umeyama(pos, z, offsets2, mask, 1, n, uwork, R, t, s, st + 1, stream);
     if (e != cudaSuccess) return e;
@@ -292,10 +369,9 @@ cudaError_t launch_hypothesis_grid(const double* ts, const double* pos, const do
     e = cudaFuncSetAttribute(ekf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_grid);
     if (e != cudaSuccess) return e;
     ekf_grid_kernel<<<(H + GRID_THREADS - 1) / GRID_THREADS, GRID_THREADS, smem_grid, stream>>>(rec, cand, hdr, (int)n, params, H, err, stats, st);
-    e = cudaFuncSetAttribute(grid_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_med);
-    if (e != cudaSuccess) return e;
-    const int mg = H < num_sms * 8 ? H : num_sms * 8;
-    grid_median_kernel<<<mg, 256, smem_med, stream>>>(err, hdr, H, stats, st);
+    const int nquads = (H + MED_Q - 1) / MED_Q;
+    const int mg = nquads < num_sms * 8 ? nquads : num_sms * 8;
+    grid_median_kernel<<<mg, 256, 0, stream>>>(err, hdr, H, stats, st);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (sim3_out) { e = cudaMemcpyAsync(sim3_out, R, 13 * sizeof(double), cudaMemcpyDeviceToDevice, stream); if (e != cudaSuccess) return e; }
