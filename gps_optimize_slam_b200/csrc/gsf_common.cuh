@@ -165,11 +165,16 @@ GSF_HD __forceinline__ bool jacobi_rotate_pair(double* a0, double* a1, double* v
     const double beta = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
     const double gamma = a0[0] * a1[0] + a0[1] * a1[1] + a0[2] * a1[2];
     if (gamma * gamma <= 1e-31 * alpha * beta || gamma == 0.0) return false;   // |cos angle| <= 3.2e-16
+    // rotation by theta in [-pi/4, pi/4] with tan(2 theta) = g2 / d:  cos(2 theta) = |d| / hyp, sin(2 theta) = sign(d) g2 / hyp,
+    // c = sqrt((1 + cos 2theta) / 2), s = sin(2 theta) / (2 c)  -- two reciprocal square roots, no division
+    // (dependent chain 23 operations instead of 30 for the tangent form; c^2 + s^2 = 1 to rounding either way)
     const double d = beta - alpha, g2 = 2.0 * gamma;
     const double w = d * d + g2 * g2;                 // > 0: gamma != 0 here
-    const double hyp = w * rsqrt_(w);
-    const double t = (d >= 0.0 ? g2 : -g2) * rcp_(fabs(d) + hyp);
-    const double c = rsqrt_(1.0 + t * t), sn = c * t;
+    const double rw = rsqrt_(w);
+    const double c2 = fabs(d) * rw, s2 = (d >= 0.0 ? g2 : -g2) * rw;
+    const double cc = 0.5 + 0.5 * c2;                 // in [0.5, 1]
+    const double rc = rsqrt_(cc);
+    const double c = cc * rc, sn = 0.5 * s2 * rc;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const double x = a0[r], y = a1[r];

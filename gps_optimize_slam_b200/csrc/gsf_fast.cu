@@ -20,8 +20,8 @@
 //   * compute warps (trajectory j, resident in shared memory via three TMA bulk copies): exact per-step
 //     Joseph-form gains + affine state maps (pass B), affine scan, state recursion (pass C), bulk store,
 //     streaming quaternion pass, next TMA load.  No Moebius scan, no reduction, no SVD wait.
-//   Hand-offs are mbarriers (aux_ready / aux_free / sums_ready, two slots); the compute warps
-//   synchronise among themselves with a named barrier.
+//   Hand-offs are hardware named barriers (aux_ready / aux_free / sums_ready, two slots: bar.arrive on the
+//   signalling side, bar.sync on the waiting side); mbarriers only for the TMA completions.
 #include <cstdlib>
 #include <atomic>
 #include "gsf_fuse_shared.cuh"
@@ -85,7 +85,13 @@ constexpr int FS_INT = 192;         // 4 ints: 0 residual violators
 constexpr int FS_MBAR = 194;        // 8 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2], ts_b
 constexpr int FS_PRMB = 202;        // FuseParams, warp B's copy (24)
 constexpr int FS_PST = 226;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
-constexpr int MB_FULL = 0, MB_SUMS = 1, MB_AUXRDY = 3, MB_AUXFREE = 5, MB_TSB = 7;
+constexpr int MB_FULL = 0, MB_TSB = 7;
+// Role hand-offs use hardware named barriers (bar.sync on the waiting side, bar.arrive on the signalling side): a
+// parked warp costs no issue slots (warps polling an mbarrier slowed the serial SVD of the warp they were waiting
+// for).  Barrier ids (two slots each): 1 compute-internal, 2-3 aux_ready, 4-5 / 6-7 aux_free for the sums / scan
+// warp, 8-9 sums_ready.  mbarriers remain for the TMA completions only (MB_FULL, MB_TSB; polled by one lane with
+// nanosleep back-off).
+constexpr int NB_AUXRDY = 2, NB_FREE_A = 4, NB_FREE_B = 6, NB_SUMS = 8;
 
 __host__ __device__ constexpr size_t fast_smem_bytes(int cap, int ct) {
     return (size_t)((cap + 3) & ~1) * 64 + (size_t)(FS_PST + 6 * ct) * 8;
@@ -236,9 +242,7 @@ __device__ __forceinline__ int next_valid_traj(const FuseArgs& A, int b) {
     return b;
 }
 // warp B, lane 0: bulk copy of the timestamps of trajectory b into warp B's private buffer
-__device__ __forceinline__ void issue_ts_load(const FuseArgs& A, int b, double* tsb, uint64_t* bar) {
-    const long long e0 = A.offsets[b];
-    const int n = (int)(A.offsets[b + 1] - e0);
+__device__ __forceinline__ void issue_ts_load(const FuseArgs& A, long long e0, int n, double* tsb, uint64_t* bar) {
     const int lead = (int)(e0 & 1), even = (n + lead) & ~1;
     mbar_expect_tx(bar, (uint32_t)even * 8u);
     bulk_g2s_hint(tsb, A.ts + (e0 - lead), (uint32_t)even * 8u, bar, l2_policy_evict_last());
@@ -342,6 +346,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
     uint32_t par_full = 0;
+    const long long blk_t0 = clock64();
     // offsets of the next trajectory are fetched one iteration ahead (their latency would otherwise stall every warp)
     long long o0 = 0, o1 = 0;
     if ((int)blockIdx.x < A.B) { o0 = A.offsets[blockIdx.x]; o1 = A.offsets[blockIdx.x + 1]; }
@@ -361,7 +366,6 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
             continue;
         }
         const int slot = j & 1;
-        const uint32_t kpar = (uint32_t)(j >> 1) & 1u;
         ++j;
         GSF_FSTAMP(0);
         double* bc = sd + FS_BC + 48 * slot;
@@ -378,10 +382,11 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
                 else if (tid < 4) pos_s[3 * even + (tid - 1)] = A.pos[3 * g + (tid - 1)];
                 else z_s[3 * even + (tid - 4)] = A.z[3 * g + (tid - 4)];
             }
-            if (even > 0) { mbar_wait(mbar + MB_FULL, par_full); par_full ^= 1; }
+            if (even > 0) { mbar_wait_polite(mbar + MB_FULL, par_full); par_full ^= 1; }
         }
         GSF_FSTAMP(1);
-        mbar_wait(mbar + MB_AUXRDY + slot, kpar);
+        named_sync(NB_AUXRDY + slot, CT + 32);             // look-ahead results of this trajectory are published
+        __threadfence_block();
         GSF_FSTAMP(2);
         named_sync(1, CT);
         if (bc[30] != 0.0) {
@@ -392,7 +397,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
                 if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
             }
             named_sync(1, CT);                           // every thread has read the verdict
-            if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
+            named_arrive(NB_FREE_A + slot, CT + 32); named_arrive(NB_FREE_B + slot, CT + 32);
             continue;
         }
 
@@ -497,10 +502,15 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
                 if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
             }
             named_sync(1, CT);                                  // status[b] is written; slot and scratch may be reused
-            if (tid == 0) mbar_arrive(mbar + MB_AUXFREE + slot);
+            named_arrive(NB_FREE_A + slot, CT + 32); named_arrive(NB_FREE_B + slot, CT + 32);
             if (bad) atomicOr(A.status + b, ST_BAD_QUATERNION);
             GSF_FSTAMP(6);
         }
+    }
+    if (A.phase_clock && tid == 0 && blockIdx.x % 37 == 0 && blockIdx.x / 37 < 12) {      // debug: per-block totals
+        long long* o = A.phase_clock + 64 + 4 * (blockIdx.x / 37);
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        o[0] = clock64() - blk_t0; o[1] = j; o[2] = smid; o[3] = blk_t0;
     }
 }
 
@@ -531,7 +541,7 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
         const int slot = j & 1, k = j >> 1;
         ++j;
         GSF_FSTAMP(16);
-        if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
+        if (k > 0) named_sync(NB_FREE_A + slot, CT + 32);
         GSF_FSTAMP(17);
         if (lane == 0) prefetch_pos_z(A, e0, n);          // whole trajectory into L2 now: rounds after the first hit L2
         const double* __restrict__ gp = A.pos + 3 * e0;
@@ -585,8 +595,8 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
         double* sums = sd + FS_SUMS + 24 * slot;
         if (!(lane & 1)) sums[butterfly16_index(lane)] = total;
         if (lane == 1) { sums[16] = ps0; sums[17] = ps1; sums[18] = ps2; sums[19] = pz0; sums[20] = pz1; sums[21] = pz2; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(mbar + MB_SUMS + slot);
+        __threadfence_block();
+        named_arrive(NB_SUMS + slot, 64);
         GSF_FSTAMP(19);
     }
 }
@@ -612,7 +622,7 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
     {
         int b0 = (int)blockIdx.x - (int)gridDim.x;
         b0 = next_valid_traj(A, b0);
-        if (lane == 0 && b0 < A.B) issue_ts_load(A, b0, tsb, mbar + MB_TSB);
+        if (lane == 0 && b0 < A.B) issue_ts_load(A, A.offsets[b0], (int)(A.offsets[b0 + 1] - A.offsets[b0]), tsb, mbar + MB_TSB);
     }
     int j = 0;
     long long o0 = 0, o1 = 0;
@@ -630,7 +640,7 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
             if (A.params_per_traj) { prefetch_l1(A.params + b + gridDim.x); prefetch_l1(reinterpret_cast<const char*>(A.params + b + gridDim.x) + 128); }
         }
         GSF_FSTAMP(24);
-        if (k > 0) mbar_wait(mbar + MB_AUXFREE + slot, (uint32_t)(k - 1) & 1u);
+        if (k > 0) named_sync(NB_FREE_B + slot, CT + 32);
         GSF_FSTAMP(25);
         // parameters: this warp's shared-memory copy (a batch-wide record is fetched once)
         if (A.params_per_traj || k + slot == 0) {
@@ -643,7 +653,7 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
         {
             const int lead = (int)(e0 & 1), cnt = n + lead, even = cnt & ~1;
             if ((cnt & 1) && lane == 0) tsb[even] = A.ts[e0 - lead + even];      // odd tail element: plain copy
-            mbar_wait(mbar + MB_TSB, par_ts); par_ts ^= 1;
+            mbar_wait_polite(mbar + MB_TSB, par_ts); par_ts ^= 1;
             __syncwarp();
         }
         long long* clk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && j == 100) ? A.phase_clock : nullptr;
@@ -651,9 +661,14 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
         int general = xy_same ? cov_start_scan<2, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst, clk)
                               : cov_start_scan<3, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst, clk);
         __syncwarp();
-        if (lane == 0) { const int bn = next_valid_traj(A, b); if (bn < A.B) issue_ts_load(A, bn, tsb, mbar + MB_TSB); }
+        if (lane == 0) {                                    // next trajectory's timestamps (its offsets are already in registers)
+            const int nn = (int)(o1 - o0);
+            if (b + (int)gridDim.x < A.B && nn > 0 && nn <= A.cap) issue_ts_load(A, o0, nn, tsb, mbar + MB_TSB);
+            else { const int bn = next_valid_traj(A, b); if (bn < A.B) issue_ts_load(A, A.offsets[bn], (int)(A.offsets[bn + 1] - A.offsets[bn]), tsb, mbar + MB_TSB); }
+        }
         GSF_FSTAMP(26);
-        mbar_wait(mbar + MB_SUMS + slot, (uint32_t)k & 1u);
+        named_sync(NB_SUMS + slot, 64);
+        __threadfence_block();
         GSF_FSTAMP(27);
         const double* sums = sd + FS_SUMS + 24 * slot;
         double v[16], chk = 0.0;
@@ -694,8 +709,8 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
             }
         }
         if (lane == 0) { bc[30] = general ? 1.0 : 0.0; bc[31] = (double)ust; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(mbar + MB_AUXRDY + slot);
+        __threadfence_block();
+        named_arrive(NB_AUXRDY + slot, CT + 32);
         GSF_FSTAMP(28);
     }
 }

@@ -18,6 +18,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Named barrier over `count` threads of the block (ids 1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -29,6 +30,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra GSF_WAIT;\n"
         "GSF_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Polite wait for the warp-specialised kernel: one lane polls (try_wait, then nanosleep back-off), the rest of the
+// warp parks at __syncwarp, so waiting warps do not take issue slots from the warp they are waiting for
+// (measured: the producer's serial SVD ran 3x slower while 3 consumer warps spun on the barrier).
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        unsigned ns = 32;
+        while (!mbar_try(bar, parity)) { __nanosleep(ns); if (ns < 256) ns <<= 1; }
+    }
+    __syncwarp();
 }
 // global -> shared bulk copy completing on an mbarrier (16-byte aligned addresses and size)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
