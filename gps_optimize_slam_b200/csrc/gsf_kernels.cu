@@ -14,14 +14,10 @@ namespace gsf {
 // Karney/Krueger 6th-order series (the algorithm PROJ documents for +proj=utm); coefficients
 // for WGS84 are evaluated on the host once (gsf_capi.cu) and passed by value.
 
-__device__ __forceinline__ void krueger_series(const double* coef, double xi_in, double eta_in, double sign,
-                                               double& xi, double& eta) {
-    // xi + sign * sum c_j sin(2j xi') cosh(2j eta'),  eta + sign * sum c_j cos(2j xi') sinh(2j eta')
-    // evaluated with the angle-addition recurrences from (sin 2xi', cos 2xi', sinh 2eta', cosh 2eta').
-    double s2, c2;
-    sincos(2.0 * xi_in, &s2, &c2);
-    const double e2p = exp(2.0 * eta_in), e2m = 1.0 / e2p;
-    const double sh2 = 0.5 * (e2p - e2m), ch2 = 0.5 * (e2p + e2m);
+// xi + sign * sum c_j sin(2j xi') cosh(2j eta'),  eta + sign * sum c_j cos(2j xi') sinh(2j eta'), evaluated with the
+// angle-addition recurrences from (sin 2xi', cos 2xi', sinh 2eta', cosh 2eta').
+__device__ __forceinline__ void krueger_series_sc(const double* coef, double xi_in, double eta_in, double sign,
+                                                  double s2, double c2, double sh2, double ch2, double& xi, double& eta) {
     double sj = s2, cj = c2, shj = sh2, chj = ch2;
     double ax = 0.0, ay = 0.0;
 #pragma unroll
@@ -35,18 +31,43 @@ __device__ __forceinline__ void krueger_series(const double* coef, double xi_in,
     xi = xi_in + sign * ax;
     eta = eta_in + sign * ay;
 }
+__device__ __forceinline__ void krueger_series(const double* coef, double xi_in, double eta_in, double sign,
+                                               double& xi, double& eta) {
+    double s2, c2;
+    sincos(2.0 * xi_in, &s2, &c2);
+    const double e2p = exp(2.0 * eta_in), e2m = 1.0 / e2p;
+    krueger_series_sc(coef, xi_in, eta_in, sign, s2, c2, 0.5 * (e2p - e2m), 0.5 * (e2p + e2m), xi, eta);
+}
 
-// forward projection of one point (lam = lon - lon0, phi in radians) -> (xi, eta) scaled later by A k0
+// forward projection of one point (lam = lon - lon0, phi in radians) -> (xi, eta) scaled later by A k0.
+// Four transcendental calls per point (sincos phi, sincos lam, atan2, asinh): sigma = sinh(e atanh(e sin phi)) has a
+// tiny argument (e sin phi <= 0.082), so both functions are short odd series (truncation < 1e-17 relative); the
+// double-angle terms of the series follow algebraically from tau', cos lam and sin lam (no sincos(2 xi') / exp(2 eta')).
 __device__ __forceinline__ void utm_forward_point(const UtmConst& K, double lam, double phi, double& xi, double& eta) {
-    const double tau = tan(phi);
-    const double t1 = sqrt(1.0 + tau * tau);
-    const double sigma = sinh(K.e * atanh(K.e * tau / t1));
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    const double rcp_c = 1.0 / cp;
+    const double tau = sp * rcp_c, t1 = fabs(rcp_c);                    // tan phi, sqrt(1 + tan^2 phi)
+    const double x = K.e * sp, x2 = x * x;                             // e tau / t1 = e sin phi
+    // atanh(x) = x (1 + x^2/3 + x^4/5 + ... + x^16/17)
+    double at = 1.0 / 17.0;
+    at = fma(at, x2, 1.0 / 15.0); at = fma(at, x2, 1.0 / 13.0); at = fma(at, x2, 1.0 / 11.0); at = fma(at, x2, 1.0 / 9.0);
+    at = fma(at, x2, 1.0 / 7.0); at = fma(at, x2, 1.0 / 5.0); at = fma(at, x2, 1.0 / 3.0); at = fma(at, x2, 1.0);
+    const double y = K.e * x * at, y2 = y * y;                         // |y| <= 0.0068
+    // sinh(y) = y (1 + y^2/6 + y^4/120 + y^6/5040 + y^8/362880)
+    double sg = 1.0 / 362880.0;
+    sg = fma(sg, y2, 1.0 / 5040.0); sg = fma(sg, y2, 1.0 / 120.0); sg = fma(sg, y2, 1.0 / 6.0); sg = fma(sg, y2, 1.0);
+    const double sigma = y * sg;
     const double taup = tau * sqrt(1.0 + sigma * sigma) - sigma * t1;
     double sl, cl;
     sincos(lam, &sl, &cl);
+    const double h2 = taup * taup + cl * cl, rh2 = 1.0 / h2, rh = sqrt(rh2);
     const double xip = atan2(taup, cl);
-    const double etap = asinh(sl / sqrt(taup * taup + cl * cl));
-    krueger_series(K.alpha, xip, etap, 1.0, xi, eta);
+    const double v = sl * rh;                                           // sinh(eta')
+    const double etap = asinh(v);
+    const double s2 = 2.0 * taup * cl * rh2, c2 = (cl * cl - taup * taup) * rh2;
+    const double sh2 = 2.0 * v * sqrt(1.0 + v * v), ch2 = 1.0 + 2.0 * v * v;
+    krueger_series_sc(K.alpha, xip, etap, 1.0, s2, c2, sh2, ch2, xi, eta);
 }
 
 __global__ void utm_forward_kernel(const double* __restrict__ lon, const double* __restrict__ lat, long long n,
