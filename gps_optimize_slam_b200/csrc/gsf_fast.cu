@@ -28,6 +28,9 @@
 
 namespace gsf {
 
+constexpr int PASS_UNROLL = 2;      // per-pose loops of the compute warps: two steps per iteration (overlaps one step's
+                                    // stores / affine update with the next step's gain chain; full unrolling measured slower)
+
 #ifndef GSF_QUAT_U
 #define GSF_QUAT_U 6
 #endif
@@ -139,22 +142,34 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
     MoebN<NAX> incl[CPL - 1 > 0 ? CPL - 1 : 1];
     MoebN<NAX> cur;
     moebn_identity(cur);
-    const int first = max(lane * CPL * LCH, 1);
-    double tp = first < n ? gts[first - 1] : 0.0;
-    // (rolled step loop: straight-line code measured slower here -- instruction fetch, not the 2x2 chain, bounds it)
+    // The lane's CPL chunks are independent 2x2 product chains: advance them together, one step each per
+    // iteration (CPL-way instruction-level parallelism; the loop stays rolled), then compose them in order.
+    MoebN<NAX> ch[CPL];
+    double tpk[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
-        const int t = lane * CPL + k;
-        const int c0 = min(t * LCH, n), c1 = min(c0 + LCH, n), s0 = max(c0, 1);
+        moebn_identity(ch[k]);
+        const int c0 = min((lane * CPL + k) * LCH, n);
+        tpk[k] = c0 >= 1 && c0 < n ? gts[c0 - 1] : (n > 0 ? gts[0] : 0.0);
+    }
 #pragma unroll 1
-        for (int i = s0; i < c1; ++i) {
-            const double ti = gts[i];
-            const double raw = ti - tp;
-            if (raw > gap || ti > t_lim) viol = 1;
-            moebn_step(cur, qv, rv, fmax(1e-6, raw));
-            tp = ti;
+    for (int m = 0; m < LCH; ++m) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const int i = (lane * CPL + k) * LCH + m;
+            if (i >= 1 && i < n) {
+                const double ti = gts[i];
+                const double raw = ti - tpk[k];
+                if (raw > gap || ti > t_lim) viol = 1;
+                moebn_step(ch[k], qv, rv, fmax(1e-6, raw));
+                tpk[k] = ti;
+            }
         }
-        moebn_rescale(cur);
+    }
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        moebn_rescale(ch[k]);
+        cur = k == 0 ? ch[0] : moebn_compose(cur, ch[k]);   // inclusive prefix inside the lane
         if (k < CPL - 1) incl[k] = cur;
     }
     if (clk) clk[29] = clock64();
@@ -272,7 +287,7 @@ __device__ __forceinline__ int pass_b1_odometry(double* __restrict__ posS, const
         mat_vec(RC, pprev0, pprev1, pprev2, y0, y1, y2);
         y0 = sc * y0 + bc[16]; y1 = sc * y1 + bc[17]; y2 = sc * y2 + bc[18];
     }
-#pragma unroll 1
+#pragma unroll PASS_UNROLL
     for (int i = s0; i < c1; ++i) {
         const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
         double u0, u1, u2;
@@ -297,7 +312,7 @@ __device__ __forceinline__ void pass_b2_gains(const double* __restrict__ tsS, do
     for (int a = 0; a < 3; ++a) { aff.a[a] = 1.0; aff.b[a] = 0.0; }
     double Px = pst[0], Py = pst[1], Pz = pst[2];
     const double qx = prm.q[0], qy = prm.q[1], qz = prm.q[2], rx = prm.r[0], ry = prm.r[1], rz = prm.r[2];
-#pragma unroll 1
+#pragma unroll PASS_UNROLL
     for (int i = s0; i < c1; ++i) {
         const double ti = tsS[i];
         const double dt = fmax(1e-6, ti - tprev);
@@ -461,7 +476,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
             }
             double x0 = pre.a[0] * bc[13] + pre.b[0], x1 = pre.a[1] * bc[14] + pre.b[1], x2 = pre.a[2] * bc[15] + pre.b[2];
             if (c0 == 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
-#pragma unroll 1
+#pragma unroll PASS_UNROLL
             for (int i = s0; i < c1; ++i) {
                 x0 = posS[3 * i] * x0 + zS[3 * i]; x1 = posS[3 * i + 1] * x1 + zS[3 * i + 1]; x2 = posS[3 * i + 2] * x2 + zS[3 * i + 2];
                 zS[3 * i] = x0; zS[3 * i + 1] = x1; zS[3 * i + 2] = x2;
