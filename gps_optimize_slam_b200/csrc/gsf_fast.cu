@@ -88,7 +88,7 @@ constexpr int FS_INT = 192;         // 4 ints: 0 residual violators
 constexpr int FS_MBAR = 194;        // 8 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2], ts_b
 constexpr int FS_PRMB = 202;        // FuseParams, warp B's copy (24)
 constexpr int FS_PST = 226;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
-constexpr int MB_FULL = 0, MB_TSB = 7;
+constexpr int MB_FULL = 0, MB_QUAT = 1, MB_TSB = 7;
 // Role hand-offs use hardware named barriers (bar.sync on the waiting side, bar.arrive on the signalling side): a
 // parked warp costs no issue slots (warps polling an mbarrier slowed the serial SVD of the warp they were waiting
 // for).  Barrier ids (two slots each): 1 compute-internal, 2-3 aux_ready, 4-5 / 6-7 aux_free for the sums / scan
@@ -360,7 +360,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
     constexpr int NW = CT / 32;
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
-    uint32_t par_full = 0;
+    uint32_t par_full = 0, par_quat = 0;
     const long long blk_t0 = clock64();
     // offsets of the next trajectory are fetched one iteration ahead (their latency would otherwise stall every warp)
     long long o0 = 0, o1 = 0;
@@ -508,15 +508,39 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
             }
         }
         {
-            const Quat C{bc[9], bc[10], bc[11], bc[12]};
-            const int bad = quat_rounds_hint<GSF_QUAT_U>(A.quat + 4 * e0, A.out_quat + 4 * e0, C, tid, CT, n);
-            GSF_FSTAMP(5);
+            // Quaternions q_state[i] = C (x) q_hat[i]: the timestamp + position buffers (32 B/pose) are dead after
+            // pass C, so the whole quaternion array comes in with ONE TMA bulk copy (it was prefetched into L2 at the
+            // start of the trajectory) and the per-pose loop is ~60 instructions -- the unrolled global->global
+            // version was ~600, which thrashes the ~8 KB per-partition instruction cache (tools/micro/icache_roles.cu).
+            double* qs = ts_s;                                  // [n,4] over ts_s + pos_s
             if (tid == 0) {
-                bulk_wait_read();                               // shared memory is free again
+                mbar_expect_tx(mbar + MB_QUAT, (uint32_t)n * 32u);
+                bulk_g2s_hint(qs, A.quat + 4 * e0, (uint32_t)n * 32u, mbar + MB_QUAT, l2_policy_evict_first());
+            }
+            const Quat C{bc[9], bc[10], bc[11], bc[12]};
+            const uint64_t pf = l2_policy_evict_first();
+            double2* __restrict__ qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
+            const double2* __restrict__ q2 = reinterpret_cast<const double2*>(qs);
+            mbar_wait_polite(mbar + MB_QUAT, par_quat); par_quat ^= 1;
+            int bad = 0;
+#pragma unroll 1
+            for (int i = tid; i < n; i += CT) {
+                const double2 lo = q2[2 * i], hi = q2[2 * i + 1];
+                const Quat qi{lo.x, lo.y, hi.x, hi.y};
+                const double n2 = qnorm2(qi);
+                if (n2 == 0.0) bad = 1;                         // scipy raises here (:466); output row becomes NaN
+                const Quat r = qscale(qmul(C, qi), rsqrt(n2));
+                stg2_hint(qout + 2 * i, make_double2(r.x, r.y), pf);
+                stg2_hint(qout + 2 * i + 1, make_double2(r.z, r.w), pf);
+            }
+            GSF_FSTAMP(5);
+            fence_proxy_async();                                // generic reads of the buffer before the next TMA writes
+            named_sync(1, CT);                                  // status[b] is written; every thread is done with the buffers
+            if (tid == 0) {
+                bulk_wait_read();                               // the position store has left shared memory
                 fence_proxy_async();
                 if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
             }
-            named_sync(1, CT);                                  // status[b] is written; slot and scratch may be reused
             named_arrive(NB_FREE_A + slot, CT + 32); named_arrive(NB_FREE_B + slot, CT + 32);
             if (bad) atomicOr(A.status + b, ST_BAD_QUATERNION);
             GSF_FSTAMP(6);
