@@ -82,12 +82,12 @@ __device__ __forceinline__ double moebn_apply(const MoebN<NAX>& x, int a, double
 // ----------------------------------------------------------------------------- shared-memory map (doubles after the staging buffers)
 constexpr int FS_BC = 0;            // 2 slots x 48: M(C) 0-8, C 9-12, x0 13-15, t 16-18, s 19, R 20-28, verdict 30, status 31
 constexpr int FS_SUMS = 96;         // 2 slots x 24: 16 sums, pivots 16-21
-constexpr int FS_AFF = 144;         // 4 warps x 6 affine warp totals
-constexpr int FS_PRM = 168;         // FuseParams as 23 doubles (24): compute warps' copy
-constexpr int FS_INT = 192;         // 4 ints: 0 residual violators
-constexpr int FS_MBAR = 194;        // 8 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2], ts_b
-constexpr int FS_PRMB = 202;        // FuseParams, warp B's copy (24)
-constexpr int FS_PST = 226;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
+constexpr int FS_AFF = 144;         // up to 8 warps x 6 affine warp totals (48)
+constexpr int FS_PRM = 192;         // FuseParams as 23 doubles (24): compute warps' copy
+constexpr int FS_INT = 216;         // 4 ints: 0 residual violators
+constexpr int FS_MBAR = 218;        // 8 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2], ts_b
+constexpr int FS_PRMB = 226;        // FuseParams, warp B's copy (24)
+constexpr int FS_PST = 250;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
 constexpr int MB_FULL = 0, MB_QUAT = 1, MB_TSB = 7;
 // Role hand-offs use hardware named barriers (bar.sync on the waiting side, bar.arrive on the signalling side): a
 // parked warp costs no issue slots (warps polling an mbarrier slowed the serial SVD of the warp they were waiting
@@ -270,7 +270,7 @@ __device__ __forceinline__ void prefetch_pos_z(const FuseArgs& A, long long e0, 
     if (bytes) { bulk_prefetch_l2_hint(A.pos + 3 * (e0 - lead), bytes, pl); bulk_prefetch_l2_hint(A.z + 3 * (e0 - lead), bytes, pl); }
 }
 
-constexpr int fast_min_blocks(int ct) { return ct <= 32 ? 5 : (ct == 64 ? 4 : 3); }
+constexpr int fast_min_blocks(int ct) { return ct <= 32 ? 5 : (ct == 64 ? 3 : (ct <= 128 ? 3 : 2)); }
 
 // Pass B1 of the compute warps, steps [s0, c1) of one thread: telescoped odometry u_i = M(C)(p_i - p_{i-1})
 // written over p_i, and the residual of the Sim3 image y_i = s M(C) p_i + t against the measurement
@@ -803,29 +803,33 @@ static cudaError_t launch_fast_t(const FuseArgs& a, int num_sms, cudaStream_t st
 }
 
 // Compute threads x chunk length per instantiation (chunk lengths odd: conflict-free 8-byte shared accesses).
+// Variant id = compute threads * 100 + chunk length.
 static int fast_variant(int cap) {
     const char* force = getenv("GSF_FAST_CT");                     // tuning hook
     const int f = force ? atoi(force) : 0;
-    if (f == 128 && cap <= 128 * 9) return 128;
-    if (f == 96 && cap <= 96 * 11) return 96;
-    if (f == 64 && cap <= 64 * 9) return 64;
-    if (f == 32 && cap <= 32 * 9) return 32;
-    if (cap <= 32 * 9) return 32;
-    if (cap <= 64 * 9) return 64;
-    if (cap <= 96 * 11) return 96;
-    if (cap <= 128 * 9) return 128;
+    if (f == 128 && cap <= 128 * 9) return 12809;
+    if (f == 96 && cap <= 96 * 11) return 9611;
+    if (f == 64 && cap <= 64 * 9) return 6409;
+    if (f == 64 && cap <= 64 * 17) return 6417;
+    if (f == 32 && cap <= 32 * 9) return 3209;
+    if (cap <= 32 * 9) return 3209;
+    if (cap <= 64 * 9) return 6409;
+    if (cap <= 96 * 11) return 9611;
+    if (cap <= 128 * 9) return 12809;
     return 0;
 }
+static int variant_ct(int v) { return v / 100; }
 bool fast_fuse_supported(int cap, int max_smem) {
-    const int ct = fast_variant(cap);
-    return ct > 0 && fast_smem_bytes(cap, ct) <= (size_t)max_smem;
+    const int v = fast_variant(cap);
+    return v > 0 && fast_smem_bytes(cap, variant_ct(v)) <= (size_t)max_smem;
 }
 cudaError_t launch_fuse_fast(const FuseArgs& a, int num_sms, cudaStream_t stream) {
     switch (fast_variant(a.cap)) {
-        case 32: return launch_fast_t<32, 9>(a, num_sms, stream);
-        case 64: return launch_fast_t<64, 9>(a, num_sms, stream);
-        case 96: return launch_fast_t<96, 11>(a, num_sms, stream);
-        case 128: return launch_fast_t<128, 9>(a, num_sms, stream);
+        case 3209: return launch_fast_t<32, 9>(a, num_sms, stream);
+        case 6409: return launch_fast_t<64, 9>(a, num_sms, stream);
+        case 6417: return launch_fast_t<64, 17>(a, num_sms, stream);
+        case 9611: return launch_fast_t<96, 11>(a, num_sms, stream);
+        case 12809: return launch_fast_t<128, 9>(a, num_sms, stream);
     }
     return cudaErrorInvalidValue;
 }
