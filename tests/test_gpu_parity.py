@@ -373,6 +373,40 @@ def test_per_trajectory_noise_parameters(gsf):
         np.testing.assert_allclose(p[off[b]:off[b + 1]], oracle_pipeline(tr, cfg)["pos"], rtol=0, atol=POS_ATOL)
 
 
+def test_fast_kernel_per_trajectory_parameters_all_axes_distinct(gsf):
+    """All-valid trajectories (fast warp-specialised kernel) with one parameter record per trajectory, x / y / z
+    noise all different (three-axis covariance scan), ragged lengths with odd offsets; also checks that the fast and
+    the general kernel (GSF_FUSE_IMPL=general) agree."""
+    import os
+    from gps_optimize_slam_b200 import synth
+    from oracle import fusion_oracle as fo
+    rng = np.random.default_rng(77)
+    lens = [271, 1000, 333, 64, 999, 1001, 577]
+    trajs = [synth.make_trajectory(200 + k, n=n, dt=0.1, speed=10.0) for k, n in enumerate(lens)]
+    sets = []
+    for _ in lens:
+        qv = 10 ** rng.uniform(-2, 0.5, 3); rv = 10 ** rng.uniform(-1.5, 0.5, 3); pv = 10 ** rng.uniform(-2, 0, 3)
+        sets.append((list(pv) + [0.01] * 4, list(qv) + [0.01] * 4, list(rv)))
+    sets[1] = ([0.1] * 3 + [0.01] * 4, [0.1, 0.1, 0.7] + [0.01] * 4, [0.2] * 3)        # shipped CONFIG: x = y
+    ts, pos, quat, z, off_d, off, max_len = pack(trajs)
+    prm = gsf.params_tensor(per_traj=sets)
+    p, q, sim3, st = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, prm, params_per_traj=True)
+    assert (st.cpu().numpy() == 0).all()
+    os.environ["GSF_FUSE_IMPL"] = "general"
+    try:
+        pg, qg, _, stg = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, prm, params_per_traj=True)
+    finally:
+        del os.environ["GSF_FUSE_IMPL"]
+    p, q, pg, qg = [x.cpu().numpy() for x in (p, q, pg, qg)]
+    np.testing.assert_allclose(p, pg, rtol=0, atol=POS_ATOL); np.testing.assert_allclose(q, qg, rtol=0, atol=ROT_ATOL)
+    for b, (p0, qq, rr) in enumerate(sets):
+        cfg = fo.default_config()
+        cfg["ekf"].update(initial_cov_diag=p0, process_noise_diag=qq, meas_noise_diag=rr)
+        o = oracle_pipeline(trajs[b], cfg)
+        np.testing.assert_allclose(p[off[b]:off[b + 1]], o["pos"], rtol=0, atol=POS_ATOL)
+        np.testing.assert_allclose(q[off[b]:off[b + 1]], o["quat"], rtol=0, atol=ROT_ATOL)
+
+
 @pytest.mark.parametrize("n,dt", [(300, 0.104), (2200, 0.104)])
 def test_hypothesis_grid_matches_oracle(gsf, n, dt):
     """gsf_ekf_hypothesis_grid_dev (one trajectory x H noise sets -> ATE statistics) against the oracle run
