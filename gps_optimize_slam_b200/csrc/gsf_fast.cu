@@ -62,6 +62,19 @@ __device__ __forceinline__ MoebN<NAX> moebn_compose(const MoebN<NAX>& e, const M
     }
     return r;
 }
+// r = later o earlier, no rescale (callers rescale every other scan stage: entries are >= 0 and every operand was
+// normalised to a maximum in [1, 2) at most two products ago, so neither overflow nor harmful underflow can occur)
+template <int NAX>
+__device__ __forceinline__ MoebN<NAX> moebn_compose_raw(const MoebN<NAX>& e, const MoebN<NAX>& l) {
+    MoebN<NAX> r;
+#pragma unroll
+    for (int a = 0; a < NAX; ++a) {
+        const double* E = e.m + 4 * a; const double* L = l.m + 4 * a; double* R = r.m + 4 * a;
+        R[0] = L[0] * E[0] + L[1] * E[2]; R[1] = L[0] * E[1] + L[1] * E[3];
+        R[2] = L[2] * E[0] + L[3] * E[2]; R[3] = L[2] * E[1] + L[3] * E[3];
+    }
+    return r;
+}
 // one predict + update step with a valid measurement: [r r*q; 1 q+r] applied on the left
 template <int NAX>
 __device__ __forceinline__ void moebn_step(MoebN<NAX>& x, const double* qv, const double* rv, double dt) {
@@ -180,7 +193,8 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
         MoebN<NAX> y;
 #pragma unroll
         for (int k = 0; k < 4 * NAX; ++k) y.m[k] = __shfl_up_sync(GSF_FULL_MASK, tot.m[k], o);
-        if (lane >= o) tot = moebn_compose(y, tot);
+        if (lane >= o) tot = moebn_compose_raw(y, tot);
+        if (o == 2 || o == 8 || o == 16) moebn_rescale(tot);           // every other stage (and the last)
     }
     MoebN<NAX> ex;
 #pragma unroll
