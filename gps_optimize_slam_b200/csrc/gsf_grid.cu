@@ -25,7 +25,9 @@ namespace gsf {
 
 constexpr int GRID_REC = 8;          // doubles per step record: dt, u(3), z(3), own rank (or -1: not evaluated)
 constexpr int GRID_TILE = 128;       // step records per shared-memory tile (8 KB)
-constexpr int GRID_THREADS = 256;    // hypotheses per block
+// Hypotheses per block are a template parameter: the candidate set takes ~110 KB of shared memory, so one block
+// is resident per SM and its thread count IS the occupancy (256 -> 83 ms, 512 -> 66 ms, 1024 -> 62 ms on config 5);
+// small grids use smaller blocks so that every SM gets one.
 constexpr int GRID_FATAL = ST_TOO_FEW_POINTS | ST_BAD_QUATERNION | ST_GRID_NEEDS_ALL_VALID;
 
 // ----------------------------------------------------------------------------- prep 1: validity, Sim3 selection mask
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(1024) grid_prep_records_kernel(const double* _
 }
 
 // ----------------------------------------------------------------------------- the grid kernel: one thread per hypothesis
+template <int GRID_THREADS>
 __global__ void __launch_bounds__(GRID_THREADS) ekf_grid_kernel(const double* __restrict__ rec, const double* __restrict__ cand,
                                                                 const double* __restrict__ hdr, int n, const FuseParams* __restrict__ params,
                                                                 int H, double* __restrict__ err, double* __restrict__ stats,
@@ -192,11 +195,11 @@ __global__ void __launch_bounds__(GRID_THREADS) ekf_grid_kernel(const double* __
             const int i = tl * GRID_TILE + k;
             if (i > 0) {
                 const double dt = r[0];
-                {   const double pp = Px + qx * dt, kk = pp / (pp + rx), om = 1.0 - kk;
+                {   const double pp = Px + qx * dt, kk = pp * rcp_(pp + rx), om = 1.0 - kk;
                     Px = om * pp * om + kk * rx * kk; x0 = om * (x0 + r[1]) + kk * r[4]; }
-                {   const double pp = Py + qy * dt, kk = pp / (pp + ry), om = 1.0 - kk;
+                {   const double pp = Py + qy * dt, kk = pp * rcp_(pp + ry), om = 1.0 - kk;
                     Py = om * pp * om + kk * ry * kk; x1 = om * (x1 + r[2]) + kk * r[5]; }
-                {   const double pp = Pz + qz * dt, kk = pp / (pp + rz), om = 1.0 - kk;
+                {   const double pp = Pz + qz * dt, kk = pp * rcp_(pp + rz), om = 1.0 - kk;
                     Pz = om * pp * om + kk * rz * kk; x2 = om * (x2 + r[3]) + kk * r[6]; }
             }
             const int rank = (int)r[7];
@@ -336,6 +339,14 @@ __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restri
     }
 }
 
+template <int THREADS>
+static cudaError_t launch_grid_t(const double* rec, const double* cand, const double* hdr, int n, const FuseParams* params, int H,
+                                 double* err, double* stats, const int* st, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(ekf_grid_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ekf_grid_kernel<THREADS><<<(H + THREADS - 1) / THREADS, THREADS, smem, stream>>>(rec, cand, hdr, n, params, H, err, stats, st);
+    return cudaGetLastError();
+}
 static int pow2_at_least(long long n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // work layout (doubles): hdr[16] | R[9] t[3] s[1] pad[3] | offsets2 (2 long long) | status (4 ints = 2 doubles) |
@@ -366,9 +377,10 @@ cudaError_t launch_hypothesis_grid(const double* ts, const double* pos, const do
     e = cudaFuncSetAttribute(grid_prep_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
     if (e != cudaSuccess) return e;
     grid_prep_records_kernel<<<1, 1024, smem_prep, stream>>>(ts, pos, quat, z, (int)n, params, R, t, s, rec, cand, hdr, st, cap2);
-    e = cudaFuncSetAttribute(ekf_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_grid);
+    if (H >= num_sms * 1024) e = launch_grid_t<1024>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, stream);
+    else if (H >= num_sms * 512) e = launch_grid_t<512>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, stream);
+    else e = launch_grid_t<256>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, stream);
     if (e != cudaSuccess) return e;
-    ekf_grid_kernel<<<(H + GRID_THREADS - 1) / GRID_THREADS, GRID_THREADS, smem_grid, stream>>>(rec, cand, hdr, (int)n, params, H, err, stats, st);
     const int nquads = (H + MED_Q - 1) / MED_Q;
     const int mg = nquads < num_sms * 8 ? nquads : num_sms * 8;
     grid_median_kernel<<<mg, 256, 0, stream>>>(err, hdr, H, stats, st);
