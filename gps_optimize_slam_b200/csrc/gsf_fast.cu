@@ -284,11 +284,6 @@ __device__ __forceinline__ void prefetch_pos_z(const FuseArgs& A, long long e0, 
     if (bytes) { bulk_prefetch_l2_hint(A.pos + 3 * (e0 - lead), bytes, pl); bulk_prefetch_l2_hint(A.z + 3 * (e0 - lead), bytes, pl); }
 }
 
-// Experimental warp layout (64 compute threads x 17-pose chunks): the two compute warps are warps 0 and 4 of a
-// five-warp block, i.e. hardware warp slots congruent mod 4 = the same SM partition, so they share every fetched
-// instruction line; warps 1 / 2 are the look-ahead warps, warp 3 exits at once.
-__host__ __device__ constexpr bool fast_colocated(int ct, int lch) { return ct == 64 && lch == 17; }
-__host__ __device__ constexpr int fast_block_threads(int ct, int lch) { return fast_colocated(ct, lch) ? 160 : ct + 64; }
 constexpr int fast_min_blocks(int ct) { return ct <= 32 ? 5 : (ct == 64 ? 3 : (ct <= 128 ? 3 : 2)); }
 
 // Pass B1 of the compute warps, steps [s0, c1) of one thread: telescoped odometry u_i = M(C)(p_i - p_{i-1})
@@ -375,8 +370,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
     double* const sd = z_s + 3 * (size_t)cap2;
     int* const iscr = reinterpret_cast<int*>(sd + FS_INT);
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
-    const int tid = fast_colocated(CT, LCH) ? (threadIdx.x < 32 ? (int)threadIdx.x : (int)threadIdx.x - 96) : (int)threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CT / 32;
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
@@ -775,7 +769,7 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
 }
 
 template <int CT, int LCH>
-__global__ void __launch_bounds__(fast_block_threads(CT, LCH), fast_min_blocks(CT)) fuse_fast_kernel(const __grid_constant__ FuseArgs A) {
+__global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel(const __grid_constant__ FuseArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NW = CT / 32;
     const int cap2 = (A.cap + 3) & ~1;
@@ -787,12 +781,6 @@ __global__ void __launch_bounds__(fast_block_threads(CT, LCH), fast_min_blocks(C
         fence_mbar_init();
     }
     __syncthreads();
-    if (fast_colocated(CT, LCH)) {
-        if (warp == 0 || warp == 4) fast_compute_role<CT, LCH>(A);
-        else if (warp == 1) fast_sums_role<CT, LCH>(A);
-        else if (warp == 2) fast_scan_svd_role<CT, LCH>(A);
-        return;
-    }
     if (warp < NW) fast_compute_role<CT, LCH>(A);
     else if (warp == NW) fast_sums_role<CT, LCH>(A);
     else fast_scan_svd_role<CT, LCH>(A);
@@ -819,12 +807,12 @@ static cudaError_t launch_fast_t(const FuseArgs& a, int num_sms, cudaStream_t st
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, fast_block_threads(CT, LCH), smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CT + 64, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     long long grid = (long long)num_sms * per_sm;
     if (grid > a.B) grid = a.B;
-    kern<<<(unsigned)grid, fast_block_threads(CT, LCH), smem, stream>>>(a);
+    kern<<<(unsigned)grid, CT + 64, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
