@@ -39,9 +39,9 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"     // suspend-time hint: the hardware parks the
+        "selp.u32 %0, 1, 0, P1;\n"                                             // thread instead of returning at once
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
