@@ -25,11 +25,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "GSF_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"     // suspend-time hint (the thread is parked, not spinning)
         "@P1 bra GSF_DONE;\n"
         "bra GSF_WAIT;\n"
         "GSF_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // Polite wait for the warp-specialised kernel: one lane polls (try_wait, then nanosleep back-off), the rest of the
 // warp parks at __syncwarp, so waiting warps do not take issue slots from the warp they are waiting for
