@@ -208,37 +208,35 @@ GSF_HD inline bool umeyama_rotation(const double* H, double* R, double& sigma_su
         if (jacobi_rotate_pair(ca[1], ca[2], cv[1], cv[2])) rotated = true;
         if (!rotated) break;
     }
-    double A[9], V[9];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { A[3 * r + j] = ca[j][r]; V[3 * r + j] = cv[j][r]; }
+    // singular values = column norms; the two dominant pairs are picked with warp-uniform branches on the column
+    // registers (no index arithmetic, no select chains)
     double sg[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) sg[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
-    double s_hi = sg[0], s_mid = sg[1], s_lo = sg[2];      // sort descending, carrying the column indices
-    int i0 = 0, i1 = 1, i2 = 2;
-    if (s_hi < s_mid) { double t = s_hi; s_hi = s_mid; s_mid = t; int k = i0; i0 = i1; i1 = k; }
-    if (s_hi < s_lo) { double t = s_hi; s_hi = s_lo; s_lo = t; int k = i0; i0 = i2; i2 = k; }
-    if (s_mid < s_lo) { double t = s_mid; s_mid = s_lo; s_lo = t; int k = i1; i1 = i2; i2 = k; }
-    (void)i2;
-    sigma_sum = s_hi + s_mid + s_lo;
+    for (int j = 0; j < 3; ++j) {
+        const double q = ca[j][0] * ca[j][0] + ca[j][1] * ca[j][1] + ca[j][2] * ca[j][2];
+        sg[j] = q > 0.0 ? q * rsqrt_(q) : 0.0;
+    }
+    sigma_sum = sg[0] + sg[1] + sg[2];
     // det(H) = det(U) det(V) sigma1 sigma2 sigma3 decides the reflection branch.
     double detH = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
     reflected = detH < 0.0;
-    // (selects instead of runtime-indexed arrays: keeps everything in registers on the device)
-#define GSF_SEL3(i, a, b, c) ((i) == 0 ? (a) : ((i) == 1 ? (b) : (c)))
-    bool ok = s_mid > 1e-14 * s_hi && s_hi > 0.0;
-    double u1[3], u2[3], v1[3], v2[3];
-    double r0 = s_hi > 1e-300 ? rcp_(s_hi) : 0.0, r1 = s_mid > 1e-300 ? rcp_(s_mid) : 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        u1[k] = GSF_SEL3(i0, A[3 * k], A[3 * k + 1], A[3 * k + 2]) * r0;
-        u2[k] = GSF_SEL3(i1, A[3 * k], A[3 * k + 1], A[3 * k + 2]) * r1;
-        v1[k] = GSF_SEL3(i0, V[3 * k], V[3 * k + 1], V[3 * k + 2]);
-        v2[k] = GSF_SEL3(i1, V[3 * k], V[3 * k + 1], V[3 * k + 2]);
+    double u1[3], u2[3], v1[3], v2[3], s_hi, s_mid;
+    const int imin = (sg[0] <= sg[1]) ? (sg[0] <= sg[2] ? 0 : 2) : (sg[1] <= sg[2] ? 1 : 2);
+#define GSF_TAKE(a, b)                                                                                     \
+    {                                                                                                      \
+        const bool first = sg[a] >= sg[b];                                                                 \
+        s_hi = first ? sg[a] : sg[b]; s_mid = first ? sg[b] : sg[a];                                       \
+        for (int k = 0; k < 3; ++k) {                                                                      \
+            u1[k] = first ? ca[a][k] : ca[b][k]; u2[k] = first ? ca[b][k] : ca[a][k];                     \
+            v1[k] = first ? cv[a][k] : cv[b][k]; v2[k] = first ? cv[b][k] : cv[a][k];                     \
+        }                                                                                                  \
     }
-#undef GSF_SEL3
+    if (imin == 0) GSF_TAKE(1, 2) else if (imin == 1) GSF_TAKE(0, 2) else GSF_TAKE(0, 1)
+#undef GSF_TAKE
+    bool ok = s_mid > 1e-14 * s_hi && s_hi > 0.0;
+    const double r0 = s_hi > 1e-300 ? rcp_(s_hi) : 0.0, r1 = s_mid > 1e-300 ? rcp_(s_mid) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { u1[k] *= r0; u2[k] *= r1; }
     // re-orthonormalise u2 against u1 (no-op to rounding when converged)
     double dp = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
 #pragma unroll
@@ -262,9 +260,9 @@ GSF_HD inline int umeyama_finish(int n, const double* mu_s, const double* mu_d, 
                                      double* R, double* t, double& s) {
     double sigma_sum; bool refl;
     bool ok = umeyama_rotation(H, R, sigma_sum, refl);
-    double var_src = ss / (double)n;
+    const double var_src = ss * rcp_((double)n);
     if (var_src < 1e-12) s = 1.0;
-    else { s = sigma_sum / ((double)n * var_src); if (s <= 1e-6) s = 1.0; }
+    else { s = sigma_sum * rcp_((double)n * var_src); if (s <= 1e-6) s = 1.0; }
     double rx, ry, rz;
     mat_vec(R, mu_s[0], mu_s[1], mu_s[2], rx, ry, rz);
     t[0] = mu_d[0] - s * rx; t[1] = mu_d[1] - s * ry; t[2] = mu_d[2] - s * rz;
