@@ -57,6 +57,112 @@ def calculate_relative_pose(pose1_pos, pose1_quat, pose2_pos, pose2_quat):
     return p[1].cpu().numpy(), q[1].cpu().numpy()
 
 
+def quaternion_nlerp(q1, q2, weight_q2):
+    """EKFGPSSLAM.py:94-105 (gsf_quat_nlerp_dev)."""
+    out = fusion.quat_nlerp(_dev(np.asarray(q1, float)[None]), _dev(np.asarray(q2, float)[None]), _dev(np.array([float(weight_q2)])))
+    return out[0].cpu().numpy()
+
+
+def is_sharp_turn_in_segment(slam_quaternions_segment, slam_timestamps_segment, yaw_rate_threshold_rad_per_sec) -> bool:
+    """EKFGPSSLAM.py:808-826 (gsf_sharp_turn_dev): max yaw rate over the segment against the threshold; a zero-norm
+    quaternion makes the segment a sharp turn, like the reference's ValueError branch."""
+    n = len(slam_quaternions_segment)
+    if n < 2:
+        return False
+    flags, rate = fusion.sharp_turn(_dev(np.asarray(slam_timestamps_segment, float)), _dev(np.asarray(slam_quaternions_segment, float)),
+                                    _one(n), float(yaw_rate_threshold_rad_per_sec))
+    print(f"  pure-SLAM segment ({n} points): max yaw rate {np.rad2deg(float(rate.cpu()[0])):.2f} deg/s")
+    return bool(int(flags.cpu()[0]))
+
+
+def rts_smoother_segment(states_filt_segment, covs_filt_segment, states_pred_segment, covs_pred_segment):
+    """EKFGPSSLAM.py:777-803 (gsf_rts_segment_dev): lists of 7-vectors / 7x7 matrices in, lists out."""
+    n = len(states_filt_segment)
+    if n == 0:
+        return [], []
+    xs, Ps = fusion.rts_segments(_dev(np.asarray(states_filt_segment, float)), _dev(np.asarray(covs_filt_segment, float)),
+                                 _dev(np.asarray(states_pred_segment, float)), _dev(np.asarray(covs_pred_segment, float)), _one(n))
+    xs, Ps = xs.cpu().numpy(), Ps.cpu().numpy()
+    return [xs[k] for k in range(n)], [Ps[k] for k in range(n)]
+
+
+class ExtendedKalmanFilter:
+    """EKFGPSSLAM.py:679-772, same constructor, attributes and methods; the arithmetic of every call runs in
+    gsf_ekf_step_dev (dense 7x7 covariance).  For whole trajectories use apply_ekf_correction / the batched API:
+    this object costs one kernel launch per step, exactly like the reference costs one numpy round per step."""
+
+    def __init__(self, initial_pos, initial_quat, config_params):
+        initial_pos = np.asarray(initial_pos, float); initial_quat = np.asarray(initial_quat, float)
+        if not (initial_pos.shape == (3,) and initial_quat.shape == (4,)):
+            raise ValueError("EKF init: initial pose has the wrong shape")
+        cfg = config_params
+        self.state = np.concatenate([initial_pos, self.normalize_quaternion(initial_quat)]).astype(float)
+        self.cov = np.diag(cfg["initial_cov_diag"]).astype(float)
+        self.Q_per_sec = np.diag(cfg["process_noise_diag"]).astype(float)
+        self.R = np.diag(cfg["meas_noise_diag"]).astype(float)
+        if self.state.shape != (7,) or self.cov.shape != (7, 7) or self.Q_per_sec.shape != (7, 7) or self.R.shape != (3, 3):
+            raise ValueError("EKF init: state / covariance / noise matrices have the wrong shape")
+        self.gnss_available_prev = None
+        self.gnss_update_weight = 0.0
+        self.original_transition_steps = max(1, int(cfg.get("transition_steps", 10)))
+        self.current_transition_steps = self.original_transition_steps
+        self.weight_delta = 1.0
+        self._last_predicted_state_for_blending = self.state.copy()
+
+    @staticmethod
+    def normalize_quaternion(q):
+        q = np.asarray(q, float)
+        out = fusion.quat_nlerp(_dev(q[None]), _dev(q[None]), _dev(np.array([0.0])))      # nlerp(q, q, 0) = q / |q|
+        nrm2 = float(np.dot(q, q))
+        return out[0].cpu().numpy() if nrm2 > 1e-18 else np.array([0.0, 0.0, 0.0, 1.0])
+
+    def _step(self, mode, state, cov, motion, dt, z, w):
+        dp, dq = motion
+        nan3 = np.full(3, np.nan)
+        o = fusion.ekf_step(mode, _dev(np.asarray(state, float)[None]), _dev(np.asarray(cov, float)[None]), _dev(np.asarray(dp, float)[None]),
+                            _dev(np.asarray(dq, float)[None]), _dev(np.array([float(dt)])), _dev((nan3 if z is None else np.asarray(z, float))[None]),
+                            _dev(np.diag(self.Q_per_sec).copy()), _dev(np.diag(self.R).copy()), _dev(np.array([float(w)])))
+        xs, Ps, xp, Pp, fl = [t.cpu().numpy()[0] for t in o]
+        if int(fl) & 2:
+            raise ValueError("Found zero norm quaternions in `quat`.")          # scipy's message (Rotation.from_quat)
+        return xs, Ps, xp, Pp, int(fl)
+
+    def _predict(self, current_state, current_cov, slam_motion_update, delta_time):
+        _, _, xp, Pp, _ = self._step(1, current_state, current_cov, slam_motion_update, delta_time, None, 1.0)
+        return xp, Pp
+
+    def _update(self, predicted_state, predicted_covariance, gps_pos_meas):
+        gps_pos_meas = np.asarray(gps_pos_meas, float)
+        if gps_pos_meas.shape != (3,) or np.isnan(gps_pos_meas).any():
+            return None, None
+        zero = (np.zeros(3), np.array([0.0, 0.0, 0.0, 1.0]))
+        xs, Ps, _, _, fl = self._step(2, predicted_state, predicted_covariance, zero, 0.0, gps_pos_meas, 1.0)
+        if not (fl & 1):
+            print("warning (EKF update): innovation covariance is singular; update skipped")
+            return None, None
+        return xs, Ps
+
+    def process_step(self, slam_motion_update, gps_measurement, gnss_is_available, delta_time, override_transition_steps=None):
+        eff = override_transition_steps if override_transition_steps is not None else self.current_transition_steps
+        self.weight_delta = 1.0 / eff if eff > 0 else 1.0
+        just_recovered = gnss_is_available and (self.gnss_available_prev == False)   # noqa: E712 (None != False)
+        if gnss_is_available:
+            if just_recovered or eff == 0:
+                self.gnss_update_weight = 1.0 if eff == 0 else self.weight_delta
+            elif self.gnss_update_weight < 1.0:
+                self.gnss_update_weight = min(1.0, self.gnss_update_weight + self.weight_delta)
+        else:
+            self.gnss_update_weight = 0.0
+        use_z = gnss_is_available and gps_measurement is not None
+        blend = self.gnss_update_weight if (self.gnss_update_weight < 1.0 and eff > 0) else 1.0
+        xs, Ps, xp, Pp, fl = self._step(3 if use_z else 1, self.state, self.cov, slam_motion_update, delta_time,
+                                        gps_measurement if use_z else None, blend)
+        self._last_predicted_state_for_blending = xp.copy()
+        self.state, self.cov = xs.copy(), Ps.copy()
+        self.gnss_available_prev = gnss_is_available
+        return self.state, self.cov, xp, Pp
+
+
 # ----------------------------------------------------------------------------- loading
 def load_slam_trajectory(txt_path: str) -> Dict[str, np.ndarray]:
     """TUM file ``ts x y z qx qy qz qw`` (EKFGPSSLAM.py:110-125)."""

@@ -176,6 +176,54 @@ int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double
     return 0;
 }
 
+int gsf_ekf_step_dev(int32_t mode, const double* state, const double* cov, const double* motion_dp, const double* motion_dq,
+                     const double* dt, const double* z, const double* q_diag_per_sec, const double* r_diag,
+                     const double* blend_w, int32_t B, double* out_state, double* out_cov, double* pred_state,
+                     double* pred_cov, int32_t* flags, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (B == 0) return 0;
+    if (B < 0 || !state || !cov || !motion_dp || !motion_dq || !dt || !z || !q_diag_per_sec || !r_diag || !blend_w || !out_state ||
+        !out_cov || !pred_state || !pred_cov || !flags || !(mode & 3))
+        return fail(GSF_E_INVALID, "gsf_ekf_step_dev: null pointer, negative size or empty mode");
+    cudaError_t e = gsf::launch_ekf_step(mode, state, cov, motion_dp, motion_dq, dt, z, q_diag_per_sec, r_diag, blend_w, B, out_state,
+                                         out_cov, pred_state, pred_cov, flags, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_ekf_step_dev");
+    return 0;
+}
+int gsf_rts_segment_dev(const double* x_filt, const double* P_filt, const double* x_pred, const double* P_pred,
+                        const int64_t* offsets, int32_t B, double* x_smooth, double* P_smooth, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (B == 0) return 0;
+    if (B < 0 || !x_filt || !P_filt || !x_pred || !P_pred || !offsets || !x_smooth || !P_smooth)
+        return fail(GSF_E_INVALID, "gsf_rts_segment_dev: null pointer or negative size");
+    cudaError_t e = gsf::launch_rts_segment(x_filt, P_filt, x_pred, P_pred, reinterpret_cast<const long long*>(offsets), B, x_smooth,
+                                            P_smooth, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_rts_segment_dev");
+    return 0;
+}
+int gsf_quat_nlerp_dev(const double* q1, const double* q2, const double* weight_q2, int64_t n, double* out, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (n == 0) return 0;
+    if (n < 0 || !q1 || !q2 || !weight_q2 || !out) return fail(GSF_E_INVALID, "gsf_quat_nlerp_dev: null pointer or negative size");
+    cudaError_t e = gsf::launch_quat_nlerp(q1, q2, weight_q2, n, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_quat_nlerp_dev");
+    return 0;
+}
+int gsf_sharp_turn_dev(const double* ts, const double* quat, const int64_t* offsets, int32_t B, double yaw_rate_threshold,
+                       int32_t* flags, double* max_rate, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (B == 0) return 0;
+    if (B < 0 || !ts || !quat || !offsets || !flags || !max_rate) return fail(GSF_E_INVALID, "gsf_sharp_turn_dev: null pointer or negative size");
+    cudaError_t e = gsf::launch_sharp_turn(ts, quat, reinterpret_cast<const long long*>(offsets), B, yaw_rate_threshold, flags, max_rate,
+                                           (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_sharp_turn_dev");
+    return 0;
+}
+
 int64_t gsf_umeyama_work_doubles(int32_t B, int64_t max_len) {
     return (int64_t)B * gsf::sim3_tiles_for(max_len) * 20;
 }

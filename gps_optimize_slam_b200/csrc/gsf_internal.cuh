@@ -30,6 +30,11 @@ cudaError_t launch_ekf_strict(const double*, const double*, const double*, const
 long long grid_work_doubles(long long n, int H);
 cudaError_t launch_hypothesis_grid(const double*, const double*, const double*, const double*, long long, const FuseParams*, int,
                                    double*, double*, double*, int*, int, int, cudaStream_t);
+cudaError_t launch_ekf_step(int, const double*, const double*, const double*, const double*, const double*, const double*, const double*,
+                            const double*, const double*, int, double*, double*, double*, double*, int*, cudaStream_t);
+cudaError_t launch_rts_segment(const double*, const double*, const double*, const double*, const long long*, int, double*, double*, cudaStream_t);
+cudaError_t launch_quat_nlerp(const double*, const double*, const double*, long long, double*, cudaStream_t);
+cudaError_t launch_sharp_turn(const double*, const double*, const long long*, int, double, int*, double*, cudaStream_t);
 struct UtmConst { double A_k0; double e, e2; double alpha[6], beta[6]; double lon0; double fn; };
 cudaError_t launch_utm(bool inverse, const double* a, const double* b, long long n, const UtmConst& K, double* o1, double* o2,
                        int num_sms, cudaStream_t stream);

@@ -76,6 +76,55 @@ def fuse_batched(ts, pos, quat, z, offsets, max_len, params, params_per_traj=Fal
     return out_pos, out_quat, sim3_out, status
 
 
+def ekf_step(mode, state, cov, motion_dp, motion_dq, dt, z, q_diag, r_diag, blend_w, stream=None):
+    """ExtendedKalmanFilter._predict / ._update / blend for B filters (gsf_ekf_step_dev); device fp64 tensors.
+    Returns (out_state [B,7], out_cov [B,7,7], pred_state [B,7], pred_cov [B,7,7], flags [B] int32)."""
+    lib = _lib.load()
+    _require_cuda(state, cov, motion_dp, motion_dq, dt, z, q_diag, r_diag, blend_w)
+    B = state.shape[0]
+    dev = state.device
+    out_state = torch.empty((B, 7), dtype=torch.float64, device=dev); out_cov = torch.empty((B, 7, 7), dtype=torch.float64, device=dev)
+    pred_state = torch.empty((B, 7), dtype=torch.float64, device=dev); pred_cov = torch.empty((B, 7, 7), dtype=torch.float64, device=dev)
+    flags = torch.empty((B,), dtype=torch.int32, device=dev)
+    rc = lib.gsf_ekf_step_dev(int(mode), _ptr(state), _ptr(cov), _ptr(motion_dp), _ptr(motion_dq), _ptr(dt), _ptr(z), _ptr(q_diag),
+                              _ptr(r_diag), _ptr(blend_w), int(B), _ptr(out_state), _ptr(out_cov), _ptr(pred_state), _ptr(pred_cov),
+                              _ptr(flags), _stream_ptr(stream))
+    _lib.check(rc, "gsf_ekf_step_dev")
+    return out_state, out_cov, pred_state, pred_cov, flags
+
+
+def rts_segments(x_filt, P_filt, x_pred, P_pred, offsets, stream=None):
+    """rts_smoother_segment for B segments (gsf_rts_segment_dev) -> (x_smooth [N,7], P_smooth [N,7,7])."""
+    lib = _lib.load()
+    _require_cuda(x_filt, P_filt, x_pred, P_pred, offsets)
+    xs = torch.empty_like(x_filt); Ps = torch.empty_like(P_filt)
+    rc = lib.gsf_rts_segment_dev(_ptr(x_filt), _ptr(P_filt), _ptr(x_pred), _ptr(P_pred), _ptr(offsets), int(offsets.numel() - 1),
+                                 _ptr(xs), _ptr(Ps), _stream_ptr(stream))
+    _lib.check(rc, "gsf_rts_segment_dev")
+    return xs, Ps
+
+
+def quat_nlerp(q1, q2, w, stream=None):
+    """quaternion_nlerp for n pairs (gsf_quat_nlerp_dev)."""
+    lib = _lib.load()
+    _require_cuda(q1, q2, w)
+    out = torch.empty_like(q1)
+    rc = lib.gsf_quat_nlerp_dev(_ptr(q1), _ptr(q2), _ptr(w), int(q1.shape[0]), _ptr(out), _stream_ptr(stream))
+    _lib.check(rc, "gsf_quat_nlerp_dev")
+    return out
+
+
+def sharp_turn(ts, quat, offsets, thresh, stream=None):
+    """is_sharp_turn_in_segment for B segments (gsf_sharp_turn_dev) -> (flags [B] int32, max yaw rate [B])."""
+    lib = _lib.load()
+    _require_cuda(ts, quat, offsets)
+    B = offsets.numel() - 1
+    flags = torch.empty((B,), dtype=torch.int32, device=ts.device); rate = torch.empty((B,), dtype=torch.float64, device=ts.device)
+    rc = lib.gsf_sharp_turn_dev(_ptr(ts), _ptr(quat), _ptr(offsets), int(B), float(thresh), _ptr(flags), _ptr(rate), _stream_ptr(stream))
+    _lib.check(rc, "gsf_sharp_turn_dev")
+    return flags, rate
+
+
 def gnss_rows_to_utm(rows, want_ts=True, stream=None):
     """Fused GNSS ingest (gsf_gnss_rows_to_utm_dev): rows [n,4] = ts, lat, lon, alt ->
     (ts [n] or None, xyz [n,3] = E, N, alt with NaN rows where the validity mask fails,

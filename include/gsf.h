@@ -96,6 +96,25 @@ int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double
                                const double* init_pos, const double* init_quat,
                                double* out_pos, double* out_quat, int32_t* status, void* stream);
 
+/* ---- per-call surface of the reference's EKF helpers, dense 7x7 covariance as the Python objects hold it, batched
+ *      over B independent filters / segments (API completeness; the throughput path is gsf_fuse_batched_dev).
+ *      gsf_ekf_step_dev: ExtendedKalmanFilter._predict (:702-715) [mode bit 0], ._update (:717-734) [mode bit 1] and
+ *      the blend of process_step (:754-767) [blend_w < 1].  state [B,7], cov [B,49], motion_dp [B,3], motion_dq [B,4],
+ *      dt [B], z [B,3] (NaN row: no update), q_diag_per_sec [7], r_diag [3], blend_w [B].  Outputs: out_state, out_cov,
+ *      pred_state, pred_cov, flags [B] (1 update applied, 2 zero-norm quaternion = scipy ValueError, 4 singular S).
+ *      gsf_rts_segment_dev: rts_smoother_segment (:777-803) over segments [offsets[b], offsets[b+1]).
+ *      gsf_quat_nlerp_dev: quaternion_nlerp (:94-105).  gsf_sharp_turn_dev: is_sharp_turn_in_segment (:808-826),
+ *      flags [B] and the largest yaw rate [B] (rad/s). */
+int gsf_ekf_step_dev(int32_t mode, const double* state, const double* cov, const double* motion_dp, const double* motion_dq,
+                     const double* dt, const double* z, const double* q_diag_per_sec, const double* r_diag,
+                     const double* blend_w, int32_t B, double* out_state, double* out_cov, double* pred_state,
+                     double* pred_cov, int32_t* flags, void* stream);
+int gsf_rts_segment_dev(const double* x_filt, const double* P_filt, const double* x_pred, const double* P_pred,
+                        const int64_t* offsets, int32_t B, double* x_smooth, double* P_smooth, void* stream);
+int gsf_quat_nlerp_dev(const double* q1, const double* q2, const double* weight_q2, int64_t n, double* out, void* stream);
+int gsf_sharp_turn_dev(const double* ts, const double* quat, const int64_t* offsets, int32_t B, double yaw_rate_threshold,
+                       int32_t* flags, double* max_rate, void* stream);
+
 /* ---- compute_sim3_transform (:428-459) batched.  mask: NULL or one byte per point.
  *      work: gsf_umeyama_work_doubles(B, max_len) doubles.  R [B,9], t [B,3], s [B]. */
 int64_t gsf_umeyama_work_doubles(int32_t B, int64_t max_len);

@@ -373,6 +373,70 @@ def test_per_trajectory_noise_parameters(gsf):
         np.testing.assert_allclose(p[off[b]:off[b + 1]], oracle_pipeline(tr, cfg)["pos"], rtol=0, atol=POS_ATOL)
 
 
+def test_dropin_ekf_object_rts_nlerp_sharp_turn(gsf):
+    """The per-call surface of the drop-in (ExtendedKalmanFilter.process_step / _predict / _update,
+    rts_smoother_segment, quaternion_nlerp, is_sharp_turn_in_segment: gsf_ekf_step_dev, gsf_rts_segment_dev,
+    gsf_quat_nlerp_dev, gsf_sharp_turn_dev) against the oracle's dense 7x7 restatement, step by step over a trajectory
+    with an outage, a recovery and blended updates."""
+    import contextlib, io
+    import EKFGPSSLAM as drop
+    from gps_optimize_slam_b200 import synth
+    from oracle import fusion_oracle as fo
+    tr = synth.make_trajectory(91, n=60, outages=[(20, 33)])
+    cfg = fo.default_config()["ekf"]
+    p0, q0 = tr["gps"][0], tr["quat"][0]
+    mine = drop.ExtendedKalmanFilter(p0, q0, cfg)
+    ref = fo.DenseEKF(p0, q0, cfg)
+    hist = {k: [] for k in ("xf", "Pf", "xp", "Pp")}
+    for i in range(1, 60):
+        motion = fo.relative_pose(tr["pos"][i - 1], tr["quat"][i - 1], tr["pos"][i], tr["quat"][i])
+        z = tr["gps"][i]
+        avail = not np.isnan(z).any()
+        steps = 3 if 33 <= i < 40 else 0                       # blended updates right after the recovery
+        a = mine.process_step(motion, z if avail else None, avail, tr["ts"][i] - tr["ts"][i - 1], steps)
+        b = ref.step(motion, z if avail else None, avail, tr["ts"][i] - tr["ts"][i - 1], steps)
+        for got, want, atol in zip(a, b, (POS_ATOL, 1e-12, POS_ATOL, 1e-12)):
+            np.testing.assert_allclose(got, want, rtol=0, atol=atol)
+        assert abs(mine.gnss_update_weight - ref.weight) < 1e-15
+        for k, v in zip(("xf", "Pf", "xp", "Pp"), a):
+            hist[k].append(np.array(v))
+    xp, Pp = mine._predict(ref.x, ref.P, motion, 0.1)
+    xo, Po = ref.predict(motion, 0.1)
+    np.testing.assert_allclose(xp, xo, rtol=0, atol=POS_ATOL); np.testing.assert_allclose(Pp, Po, rtol=0, atol=1e-12)
+    xu, Pu = mine._update(xo, Po, tr["gps"][5])
+    xuo, Puo = ref.update(xo, Po, tr["gps"][5])
+    np.testing.assert_allclose(xu, xuo, rtol=0, atol=POS_ATOL); np.testing.assert_allclose(Pu, Puo, rtol=0, atol=1e-12)
+    assert mine._update(xo, Po, np.array([np.nan, 0.0, 0.0])) == (None, None)
+    # RTS over the outage segment of the recorded history (dense covariances with off-diagonal terms added)
+    sl = slice(18, 34)
+    rng = np.random.default_rng(2)
+    def spd(P):
+        A = rng.normal(size=(7, 7)) * 1e-3
+        return P + A @ A.T
+    Pf = [spd(P) for P in hist["Pf"][sl]]; Pp_ = [spd(P) for P in hist["Pp"][sl]]
+    xs, Ps = drop.rts_smoother_segment(hist["xf"][sl], Pf, hist["xp"][sl], Pp_)
+    want = fo.rts_segment(hist["xf"][sl], Pf, hist["xp"][sl], Pp_)
+    for got, w_ in zip(xs, want):
+        np.testing.assert_allclose(got, w_, rtol=0, atol=POS_ATOL)
+    assert len(Ps) == len(xs) and all(np.allclose(P, P.T) for P in Ps)
+    # nlerp (sign flip, clipping, degenerate antipodal midpoint) and the sharp-turn gate
+    qa = np.array([0.1, -0.2, 0.3, 0.9]); qa /= np.linalg.norm(qa)
+    qb = -np.array([0.12, -0.18, 0.33, 0.88]); qb /= np.linalg.norm(qb)
+    for w in (-0.3, 0.0, 0.25, 0.5, 1.0, 1.7):
+        np.testing.assert_allclose(drop.quaternion_nlerp(qa, qb, w), fo.nlerp(qa, qb, w), rtol=0, atol=1e-15)
+    for w in (0.5, 0.2, 0.9):
+        np.testing.assert_allclose(drop.quaternion_nlerp(qa, -qa * 1.0, w), fo.nlerp(qa, -qa * 1.0, w), rtol=0, atol=1e-15)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for case in (synth.make_trajectory(92, n=40), synth.make_trajectory(93, n=40, sharp_turn_at=20)):
+            for a0, a1 in ((0, 40), (15, 26), (3, 4), (7, 8)):
+                got = drop.is_sharp_turn_in_segment(list(case["quat"][a0:a1]), list(case["ts"][a0:a1]), np.deg2rad(45.0))
+                assert got == fo.sharp_turn(case["quat"][a0:a1], case["ts"][a0:a1], np.deg2rad(45.0))
+        bad = case["quat"][10:20].copy(); bad[4] = 0.0
+        assert drop.is_sharp_turn_in_segment(list(bad), list(case["ts"][10:20]), np.deg2rad(45.0)) is True
+    with pytest.raises(ValueError):
+        mine.process_step((np.zeros(3), np.zeros(4)), None, False, 0.1)
+
+
 def test_fast_kernel_per_trajectory_parameters_all_axes_distinct(gsf):
     """All-valid trajectories (fast warp-specialised kernel) with one parameter record per trajectory, x / y / z
     noise all different (three-axis covariance scan), ragged lengths with odd offsets; also checks that the fast and
