@@ -124,7 +124,7 @@ GSF_HD __forceinline__ void matT_vec(const double* M, double x, double y, double
 
 // scipy _from_matrix_orthogonal: pick the largest of (m00, m11, m22, trace), no sign
 // canonicalisation, normalise.
-GSF_HD inline Quat quat_from_matrix(const double* m) {
+GSF_HD __forceinline__ Quat quat_from_matrix(const double* m) {
     double tr = m[0] + m[4] + m[8];
     int choice = 0; double best = m[0];
     if (m[4] > best) { best = m[4]; choice = 1; }
@@ -191,7 +191,7 @@ GSF_HD __forceinline__ bool jacobi_rotate_pair(double* a0, double* a1, double* v
 // With singular pairs (u_i, v_i) sorted by sigma, the det=+1 matrix V diag(1,1,d) U^T equals
 // v1 u1^T + v2 u2^T + (v1 x v2)(u1 x u2)^T, so only the two dominant pairs are needed.
 // Returns false when sigma_2 is numerically zero (collinear points: R not unique).
-GSF_HD inline bool umeyama_rotation(const double* H, double* R, double& sigma_sum, bool& reflected) {
+GSF_HD __forceinline__ bool umeyama_rotation(const double* H, double* R, double& sigma_sum, bool& reflected) {
     // column-major copies: ca[j] = column j of the working matrix, cv[j] = column j of V
     double ca[3][3], cv[3][3];
 #pragma unroll
@@ -256,7 +256,7 @@ GSF_HD inline bool umeyama_rotation(const double* H, double* R, double& sigma_su
 //   n      number of points, mu_s/mu_d centroids, H centred cross-covariance (not / n),
 //   ss     sum |src_c|^2.
 // Outputs R (row-major), t, s; returns status bits.
-GSF_HD inline int umeyama_finish(int n, const double* mu_s, const double* mu_d, const double* H, double ss,
+GSF_HD __forceinline__ int umeyama_finish(int n, const double* mu_s, const double* mu_d, const double* H, double ss,
                                      double* R, double* t, double& s) {
     double sigma_sum; bool refl;
     bool ok = umeyama_rotation(H, R, sigma_sum, refl);

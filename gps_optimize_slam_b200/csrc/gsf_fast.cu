@@ -75,15 +75,18 @@ __device__ __forceinline__ MoebN<NAX> moebn_compose_raw(const MoebN<NAX>& e, con
     }
     return r;
 }
-// one predict + update step with a valid measurement: [r r*q; 1 q+r] applied on the left
+// one predict + update step with a valid measurement, applied on the left.  The step matrix [r r*q; 1 q+r] is
+// used divided by r (a Moebius map is projective): [1 qa; g g*qa+1] with g = 1/r -- four FMAs per axis, and
+// (qa, g) = (0, 0) is the identity, so steps outside the trajectory are masked by selecting the two scalars
+// instead of branching (the chains of one lane then interleave in one straight-line loop body).
 template <int NAX>
-__device__ __forceinline__ void moebn_step(MoebN<NAX>& x, const double* qv, const double* rv, double dt) {
+__device__ __forceinline__ void moebn_step(MoebN<NAX>& x, const double* qv, const double* gv, double dt, bool valid) {
 #pragma unroll
     for (int a = 0; a < NAX; ++a) {
         double* m = x.m + 4 * a;
-        const double qa = qv[a] * dt, ra = rv[a];
-        const double ta = m[0] + qa * m[2], tb = m[1] + qa * m[3];
-        m[2] = ta + ra * m[2]; m[3] = tb + ra * m[3]; m[0] = ra * ta; m[1] = ra * tb;
+        const double qa = qv[a] * dt, ga = valid ? gv[a] : 0.0;
+        m[0] = fma(qa, m[2], m[0]); m[1] = fma(qa, m[3], m[1]);
+        m[2] = fma(ga, m[0], m[2]); m[3] = fma(ga, m[1], m[3]);
     }
 }
 template <int NAX>
@@ -101,7 +104,7 @@ constexpr int FS_INT = 216;         // 4 ints: 0 residual violators
 constexpr int FS_MBAR = 218;        // 8 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2], ts_b
 constexpr int FS_PRMB = 226;        // FuseParams, warp B's copy (24)
 constexpr int FS_PST = 250;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
-constexpr int MB_FULL = 0, MB_QUAT = 1, MB_TSB = 7;
+constexpr int MB_FULL = 0, MB_QUAT = 1, MB_QUAT0 = 2, MB_TSB = 7;
 // Role hand-offs use hardware named barriers (bar.sync on the waiting side, bar.arrive on the signalling side): a
 // parked warp costs no issue slots (warps polling an mbarrier slowed the serial SVD of the warp they were waiting
 // for).  Barrier ids (two slots each): 1 compute-internal, 2-3 aux_ready, 4-5 / 6-7 aux_free for the sums / scan
@@ -147,16 +150,22 @@ template <int NAX, int CT, int LCH>
 __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, int n, const FuseParams* __restrict__ gp, int lane,
                                               double* __restrict__ pst, long long* clk) {
     constexpr int CPL = CT / 32;                            // compute-thread chunks per lane
-    double qv[NAX], rv[NAX], p0v[NAX];
-#pragma unroll
-    for (int a = 0; a < NAX; ++a) { const int ax = (NAX == 2 && a == 1) ? 2 : a; qv[a] = gp->q[ax]; rv[a] = gp->r[ax]; p0v[a] = gp->p0[ax]; }
-    const double gap = gp->gap_threshold, t_lim = gts[0] + gp->max_duration;
+    double qv[NAX], gv[NAX], p0v[NAX];
     int viol = 0;
+#pragma unroll
+    for (int a = 0; a < NAX; ++a) {
+        const int ax = (NAX == 2 && a == 1) ? 2 : a;
+        qv[a] = gp->q[ax]; p0v[a] = gp->p0[ax];
+        const double ra = gp->r[ax];
+        if (!(ra >= 1e-300 && ra <= 1e300)) viol = 1;        // exact (zero-variance) or non-finite measurement noise: general kernel
+        gv[a] = 1.0 / ra;
+    }
+    const double gap = gp->gap_threshold, t_lim = gts[0] + gp->max_duration;
     MoebN<NAX> incl[CPL - 1 > 0 ? CPL - 1 : 1];
     MoebN<NAX> cur;
     moebn_identity(cur);
     // The lane's CPL chunks are independent 2x2 product chains: advance them together, one step each per
-    // iteration (CPL-way instruction-level parallelism; the loop stays rolled), then compose them in order.
+    // iteration (CPL-way instruction-level parallelism, branch-free; the loop stays rolled), then compose them in order.
     MoebN<NAX> ch[CPL];
     double tpk[CPL];
 #pragma unroll
@@ -170,17 +179,20 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
             const int i = (lane * CPL + k) * LCH + m;
-            if (i >= 1 && i < n) {
-                const double ti = gts[i];
-                const double raw = ti - tpk[k];
-                if (raw > gap || ti > t_lim) viol = 1;
-                moebn_step(ch[k], qv, rv, fmax(1e-6, raw));
-                tpk[k] = ti;
-            }
+            const bool valid = i >= 1 && i < n;
+            const double ti = gts[min(i, n - 1)];
+            const double raw = ti - tpk[k];
+            if (valid && (raw > gap || ti > t_lim)) viol = 1;
+            moebn_step(ch[k], qv, gv, valid ? (raw > 1e-6 ? raw : 1e-6) : 0.0, valid);   // = fmax(1e-6, raw), NaN included
+            tpk[k] = ti;
         }
     }
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
+        double fin = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4 * NAX; ++q) fin += ch[k].m[q];
+        if (!(fin <= 1.7976931348623157e308)) viol = 1;      // q/r ratio beyond the range of a chunk product: general kernel
         moebn_rescale(ch[k]);
         cur = k == 0 ? ch[0] : moebn_compose(cur, ch[k]);   // inclusive prefix inside the lane
         if (k < CPL - 1) incl[k] = cur;
@@ -329,7 +341,8 @@ __device__ __forceinline__ void pass_b2_gains(const double* __restrict__ tsS, do
 #pragma unroll PASS_UNROLL
     for (int i = s0; i < c1; ++i) {
         const double ti = tsS[i];
-        const double dt = fmax(1e-6, ti - tprev);
+        const double raw = ti - tprev;
+        const double dt = raw > 1e-6 ? raw : 1e-6;          // = fmax(1e-6, raw), NaN included
         tprev = ti;
         const double u0 = posS[3 * i], u1 = posS[3 * i + 1], u2 = posS[3 * i + 2];
         const double z0 = zS[3 * i], z1 = zS[3 * i + 1], z2 = zS[3 * i + 2];
@@ -374,7 +387,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
     constexpr int NW = CT / 32;
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
-    uint32_t par_full = 0, par_quat = 0;
+    uint32_t par_full = 0, par_q0 = 0, par_q1 = 0;
     const long long blk_t0 = clock64();
     // offsets of the next trajectory are fetched one iteration ahead (their latency would otherwise stall every warp)
     long long o0 = 0, o1 = 0;
@@ -470,7 +483,15 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { aex.a[k] = 1.0; aex.b[k] = 0.0; }
         }
+        fence_proxy_async();                            // generic reads of the timestamp buffer before the TMA write below
         named_sync(1, CT);
+        // Quaternions, part 1: the timestamp buffer is dead after pass B, so the first nq1 quaternions (32 B each; nq1 a
+        // multiple of 32 poses) land in it while pass C runs; part 2 follows into the position buffer after pass C.
+        const int nq1 = min(n, (cap2 >> 2) & ~31);
+        if (tid == 0) {
+            mbar_expect_tx(mbar + MB_QUAT0, (uint32_t)nq1 * 32u);
+            if (nq1 > 0) bulk_g2s_hint(ts_s, A.quat + 4 * e0, (uint32_t)nq1 * 32u, mbar + MB_QUAT0, l2_policy_evict_first());
+        }
         GSF_FSTAMP(3);
 
         // ------------------------------------------------------------------ pass C: state recursion
@@ -527,26 +548,39 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
             // start of the trajectory) and the per-pose loop is ~60 instructions -- the unrolled global->global
             // version was ~600, which thrashes the ~8 KB per-partition instruction cache (tools/micro/icache_roles.cu).
             double* qs = ts_s;                                  // [n,4] over ts_s + pos_s
-            if (tid == 0) {
-                mbar_expect_tx(mbar + MB_QUAT, (uint32_t)n * 32u);
-                bulk_g2s_hint(qs, A.quat + 4 * e0, (uint32_t)n * 32u, mbar + MB_QUAT, l2_policy_evict_first());
+            if (tid == 0 && n > nq1) {
+                mbar_expect_tx(mbar + MB_QUAT, (uint32_t)(n - nq1) * 32u);
+                bulk_g2s_hint(qs + 4 * nq1, A.quat + 4 * (e0 + nq1), (uint32_t)(n - nq1) * 32u, mbar + MB_QUAT, l2_policy_evict_first());
             }
             const Quat C{bc[9], bc[10], bc[11], bc[12]};
             const uint64_t pf = l2_policy_evict_first();
             double2* __restrict__ qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
             const double2* __restrict__ q2 = reinterpret_cast<const double2*>(qs);
-            mbar_wait_polite(mbar + MB_QUAT, par_quat); par_quat ^= 1;
+            mbar_wait_polite(mbar + MB_QUAT0, par_q0); par_q0 ^= 1;
+            bool second = n <= nq1;                             // part 2 landed (or does not exist)
             int bad = 0;
+            // two poses per iteration (independent chains, branch-free reciprocal square root)
 #pragma unroll 1
-            for (int i = tid; i < n; i += CT) {
-                const double2 lo = q2[2 * i], hi = q2[2 * i + 1];
-                const Quat qi{lo.x, lo.y, hi.x, hi.y};
-                const double n2 = qnorm2(qi);
-                if (n2 == 0.0) bad = 1;                         // scipy raises here (:466); output row becomes NaN
-                const Quat r = qscale(qmul(C, qi), rsqrt(n2));
-                stg2_hint(qout + 2 * i, make_double2(r.x, r.y), pf);
-                stg2_hint(qout + 2 * i + 1, make_double2(r.z, r.w), pf);
+            for (int i0 = tid - lane; i0 < n; i0 += 2 * CT) {   // warp-uniform trip count (the wait below syncs the warp)
+                if (!second && i0 + CT + 31 >= nq1) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; second = true; }
+                const int i = i0 + lane, i1 = i + CT;
+                const bool va = i < n, vb = i1 < n;
+                const int ia = va ? i : 0, ib = vb ? i1 : ia;   // tails re-read a landed pose and store nothing
+                const double2 lo0 = q2[2 * ia], hi0 = q2[2 * ia + 1], lo1 = q2[2 * ib], hi1 = q2[2 * ib + 1];
+                const Quat qa{lo0.x, lo0.y, hi0.x, hi0.y}, qb{lo1.x, lo1.y, hi1.x, hi1.y};
+                const double na = qnorm2(qa), nb = qnorm2(qb);
+                if (na == 0.0 || nb == 0.0) bad = 1;            // scipy raises here (:466); output row becomes NaN
+                const Quat ra = qscale(qmul(C, qa), fast_rsqrt(na)), rb = qscale(qmul(C, qb), fast_rsqrt(nb));
+                if (va) {
+                    stg2_hint(qout + 2 * i, make_double2(ra.x, ra.y), pf);
+                    stg2_hint(qout + 2 * i + 1, make_double2(ra.z, ra.w), pf);
+                }
+                if (vb) {
+                    stg2_hint(qout + 2 * i1, make_double2(rb.x, rb.y), pf);
+                    stg2_hint(qout + 2 * i1 + 1, make_double2(rb.z, rb.w), pf);
+                }
             }
+            if (!second) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; }     // keep every warp's phase in step
             GSF_FSTAMP(5);
             fence_proxy_async();                                // generic reads of the buffer before the next TMA writes
             named_sync(1, CT);                                  // status[b] is written; every thread is done with the buffers
@@ -687,10 +721,11 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
         if (n <= 0 || n > A.cap) continue;
         const int slot = j & 1, k = j >> 1;
         ++j;
-        // the few global scalars this warp needs (first quaternion, parameters) are pulled into L1 one trajectory ahead
-        if (lane == 0 && b + (int)gridDim.x < A.B) {
-            prefetch_l1(A.quat + 4 * o0);
-            if (A.params_per_traj) { prefetch_l1(A.params + b + gridDim.x); prefetch_l1(reinterpret_cast<const char*>(A.params + b + gridDim.x) + 128); }
+        // the global scalars this warp needs are requested here and consumed after the scan: the first quaternion
+        // (lanes 0-3 hold one component each), the next trajectory's offsets (above) and, one trajectory ahead, the parameters
+        const double q0c = A.quat[4 * e0 + (lane & 3)];
+        if (lane == 0 && A.params_per_traj && b + (int)gridDim.x < A.B) {
+            prefetch_l1(A.params + b + gridDim.x); prefetch_l1(reinterpret_cast<const char*>(A.params + b + gridDim.x) + 128);
         }
         GSF_FSTAMP(24);
         if (k > 0) named_sync(NB_FREE_B + slot, CT + 32);
@@ -729,7 +764,8 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
         for (int q = 0; q < 16; ++q) { v[q] = sums[q]; chk += v[q]; }
         if (!(fabs(chk) <= 1.7976931348623157e308)) general = 1;       // NaN row (no GNSS) or non-finite input
         if (n < 3 || n < gprm->min_samples) general = 1;
-        const Quat q0{A.quat[4 * e0], A.quat[4 * e0 + 1], A.quat[4 * e0 + 2], A.quat[4 * e0 + 3]};
+        const Quat q0{__shfl_sync(GSF_FULL_MASK, q0c, 0), __shfl_sync(GSF_FULL_MASK, q0c, 1), __shfl_sync(GSF_FULL_MASK, q0c, 2),
+                      __shfl_sync(GSF_FULL_MASK, q0c, 3)};
         if (qnorm2(q0) == 0.0) general = 1;
         int ust = 0;
         double* bc = sd + FS_BC + 48 * slot;
@@ -745,7 +781,7 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
                 for (int c = 0; c < 3; ++c) hh[3 * r + c] = v[6 + 3 * r + c] - nn * ma[r] * mb[c];
             const double ss = v[15] - nn * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
             double R[9], t[3], s = 1.0;
-            ust = umeyama_finish_ool(n, ms_, md_, hh, ss, R, t, &s);
+            ust = umeyama_finish(n, ms_, md_, hh, ss, R, t, s);
             if (lane == 0) {
                 const Quat qR = quat_from_matrix(R);
                 const Quat q0h = qunit(q0);

@@ -20,6 +20,15 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(r, e, r);
 }
 
+// 1/sqrt(x) for positive normal x: hardware seed + one third-order step (the arithmetic of CUDA's rsqrt() without
+// its special-case branch, so that two chains interleave in one loop body).  x = 0 gives inf (-> NaN downstream).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r * r, 1.0);
+    return fma(fma(e, 0.375, 0.5), r * e, r);
+}
+
 constexpr int FLAG_VALID = 1;
 constexpr int FLAG_SELECTED = 2;
 constexpr int FLAG_RECOVERY = 4;
