@@ -59,6 +59,15 @@ struct Quat { double x, y, z, w; };
 
 GSF_HD __forceinline__ double rsqrt_(double x) {
 #ifdef __CUDA_ARCH__
+    // CUDA's rsqrt() arithmetic (hardware seed + one third-order step) for arguments away from the ends of the
+    // exponent range; the library call keeps the special cases (0, denormal, inf, NaN, |exponent| > 1000)
+    const unsigned ex = ((unsigned)__double2hiint(x) >> 20) - 24u;      // sign bit set -> huge -> library path
+    if (ex < 2000u) {
+        double r;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+        const double e = fma(-x, r * r, 1.0);
+        return fma(fma(e, 0.375, 0.5), r * e, r);
+    }
     return rsqrt(x);
 #else
     return 1.0 / sqrt(x);

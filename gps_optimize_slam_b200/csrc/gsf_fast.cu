@@ -34,7 +34,7 @@ constexpr int PASS_UNROLL = 2;      // per-pose loops of the compute warps: two 
 #ifndef GSF_QUAT_U
 #define GSF_QUAT_U 6
 #endif
-#define GSF_FSTAMP(k) do { if (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW) && j == 100) A.phase_clock[k] = clock64(); } while (0)
+#define GSF_FSTAMP(k) do { if (pclk && j == 100) pclk[k] = clock64(); } while (0)       // pclk: per-role debug pointer, null in production
 
 // ----------------------------------------------------------------------------- Moebius maps, NAX axes
 template <int NAX> struct MoebN { double m[4 * NAX]; };      // per axis row-major [a b; c d]
@@ -385,6 +385,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CT / 32;
+    long long* const pclk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW)) ? A.phase_clock : nullptr;
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
     uint32_t par_full = 0, par_q0 = 0, par_q1 = 0;
@@ -614,6 +615,7 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CT / 32;
+    long long* const pclk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW)) ? A.phase_clock : nullptr;
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
     // ====================================================================== warp A: Umeyama sums, one to two trajectories ahead
@@ -701,6 +703,7 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(sd + FS_MBAR);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CT / 32;
+    long long* const pclk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW)) ? A.phase_clock : nullptr;
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
     // ====================================================================== warp B: covariance start values, gap/window check, Umeyama finish

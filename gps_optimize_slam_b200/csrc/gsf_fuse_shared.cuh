@@ -42,8 +42,9 @@ struct Moeb3 { double m[12]; };
 struct Aff3 { double a[3], b[3]; };                     // x -> a x + b per axis
 
 __device__ __forceinline__ void moeb_rescale(double* m) {
-    const double big = fmax(fmax(m[0], m[1]), fmax(m[2], m[3]));
-    const int e = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
+    // entries are >= 0, so the largest one has the largest high word: three integer maxima instead of three fmax
+    const int hi = max(max(__double2hiint(m[0]), __double2hiint(m[1])), max(__double2hiint(m[2]), __double2hiint(m[3])));
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
     const double sc = __hiloint2double((1023 - e) << 20, 0);       // 2^-e, exact
     m[0] *= sc; m[1] *= sc; m[2] *= sc; m[3] *= sc;
 }
