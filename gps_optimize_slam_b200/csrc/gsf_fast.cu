@@ -192,7 +192,7 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
         double fin = 0.0;
 #pragma unroll
         for (int q = 0; q < 4 * NAX; ++q) fin += ch[k].m[q];
-        if (!(fin <= 1.7976931348623157e308)) viol = 1;      // q/r ratio beyond the range of a chunk product: general kernel
+        if (!(fin <= 1e200)) viol = 1;                       // q/r ratio beyond the range of a chunk product (here and in pass B2): general kernel
         moebn_rescale(ch[k]);
         cur = k == 0 ? ch[0] : moebn_compose(cur, ch[k]);   // inclusive prefix inside the lane
         if (k < CPL - 1) incl[k] = cur;
@@ -328,16 +328,21 @@ __device__ __forceinline__ int pass_b1_odometry(double* __restrict__ posS, const
     }
     return nviol;
 }
-// Pass B2: exact per-step Joseph-form gains (:722-731) from the start covariance, affine map
-// x -> om x + (om u + k z) per axis.  Overwrites u (in pos) with om and z with om u + k z.
+// Pass B2: per-step gains from the start covariance, affine map x -> om x + (om u + k z) per axis.  Overwrites u
+// (in pos) with om and z with om u + k z.  The covariance is carried projectively, P = a / b, with the same step
+// matrix as the scan warp ([1 qa; g g*qa+1], g = 1/r):  a' = a + qa b,  b' = b + g a',  k = g a' / b',  om = b / b'.
+// The recursion (two dependent operations per step) is separated from the reciprocal, which pipelines across
+// steps; k and om keep full relative accuracy.  P' = a'/b' = r pp / (pp + r) equals the reference's Joseph form
+// (:731) up to rounding, and the recursion is contractive, so the difference stays at the 1e-16 level.
 // XY: x and y share P0/Q/R (the shipped CONFIG), so the y gain is the x gain.
 template <bool XY>
 __device__ __forceinline__ void pass_b2_gains(const double* __restrict__ tsS, double* __restrict__ posS, double* __restrict__ zS,
                                               const FuseParams& prm, const double* __restrict__ pst, int s0, int c1, double tprev, Aff3& aff) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) { aff.a[a] = 1.0; aff.b[a] = 0.0; }
-    double Px = pst[0], Py = pst[1], Pz = pst[2];
-    const double qx = prm.q[0], qy = prm.q[1], qz = prm.q[2], rx = prm.r[0], ry = prm.r[1], rz = prm.r[2];
+    double ax = pst[0], ay = pst[1], az = pst[2], bx = 1.0, by = 1.0, bz = 1.0;
+    const double qx = prm.q[0], qy = prm.q[1], qz = prm.q[2];
+    const double gx = fast_rcp(prm.r[0]), gy = XY ? gx : fast_rcp(prm.r[1]), gz = fast_rcp(prm.r[2]);   // r: positive normal (scan warp defers otherwise)
 #pragma unroll PASS_UNROLL
     for (int i = s0; i < c1; ++i) {
         const double ti = tsS[i];
@@ -348,20 +353,20 @@ __device__ __forceinline__ void pass_b2_gains(const double* __restrict__ tsS, do
         const double z0 = zS[3 * i], z1 = zS[3 * i + 1], z2 = zS[3 * i + 2];
         double kx, ky, kz, ox, oy, oz;
         {
-            const double pp = Px + qx * dt;
-            kx = pp * fast_rcp(pp + rx); ox = 1.0 - kx;
-            Px = ox * pp * ox + kx * rx * kx;                        // Joseph form (:731)
+            ax = fma(qx * dt, bx, ax);
+            const double ga = gx * ax, bn = bx + ga, rb = fast_rcp(bn);
+            kx = ga * rb; ox = bx * rb; bx = bn;
         }
         if (XY) { ky = kx; oy = ox; }
         else {
-            const double pp = Py + qy * dt;
-            ky = pp * fast_rcp(pp + ry); oy = 1.0 - ky;
-            Py = oy * pp * oy + ky * ry * ky;
+            ay = fma(qy * dt, by, ay);
+            const double ga = gy * ay, bn = by + ga, rb = fast_rcp(bn);
+            ky = ga * rb; oy = by * rb; by = bn;
         }
         {
-            const double pp = Pz + qz * dt;
-            kz = pp * fast_rcp(pp + rz); oz = 1.0 - kz;
-            Pz = oz * pp * oz + kz * rz * kz;
+            az = fma(qz * dt, bz, az);
+            const double ga = gz * az, bn = bz + ga, rb = fast_rcp(bn);
+            kz = ga * rb; oz = bz * rb; bz = bn;
         }
         const double b0 = ox * u0 + kx * z0, b1 = oy * u1 + ky * z1, b2 = oz * u2 + kz * z2;
         posS[3 * i] = ox; posS[3 * i + 1] = oy; posS[3 * i + 2] = oz;
