@@ -121,7 +121,7 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
     a.B = B; a.cap = cap;
     a.use_tma = aligned16(ts) && aligned16(pos) && aligned16(z) && aligned16(out_pos);
     a.phase_clock = g_phase_clock;
-    a.only_deferred = 0; a.defer_count = nullptr;
+    a.only_deferred = 0; a.defer_count = nullptr; a.work_counter = nullptr;
     // Fast kernel first (all-valid trajectories); whatever it defers goes through the general kernel
     // behind it on the same stream.  GSF_FUSE_IMPL=general forces the general kernel for everything.
     const char* impl = getenv("GSF_FUSE_IMPL");
@@ -130,7 +130,8 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
     if (want_fast && a.use_tma && !init_pos && gsf::fast_fuse_supported(cap, d.max_smem)) {
         e = gsf::defer_counter(&a.defer_count);
         if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter)");
-        e = cudaMemsetAsync(a.defer_count, 0, sizeof(int), (cudaStream_t)stream);
+        a.work_counter = a.defer_count + 1;
+        e = cudaMemsetAsync(a.defer_count, 0, 2 * sizeof(int), (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter reset)");
         e = gsf::launch_fuse_fast(a, d.sms, (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (fast kernel)");

@@ -103,7 +103,8 @@ constexpr int FS_PRM = 192;         // FuseParams as 23 doubles (24): compute wa
 constexpr int FS_INT = 216;         // 4 ints: 0 residual violators
 constexpr int FS_MBAR = 218;        // 8 mbarriers: full, sums_ready[2], aux_ready[2], aux_free[2], ts_b
 constexpr int FS_PRMB = 226;        // FuseParams, warp B's copy (24)
-constexpr int FS_PST = 250;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
+constexpr int FS_RING = 250;        // 4 trajectory references (16 bytes each): the block's work queue, filled by compute thread 0
+constexpr int FS_PST = 258;         // 2 slots x CT x 3 start covariances; then warp B's timestamp buffer (cap2 doubles)
 constexpr int MB_FULL = 0, MB_QUAT = 1, MB_QUAT0 = 2, MB_TSB = 7;
 // Role hand-offs use hardware named barriers (bar.sync on the waiting side, bar.arrive on the signalling side): a
 // parked warp costs no issue slots (warps polling an mbarrier slowed the serial SVD of the warp they were waiting
@@ -274,14 +275,6 @@ __device__ __forceinline__ int quat_rounds_hint(const double* __restrict__ quat_
     return bad;
 }
 
-// next trajectory of this block (after b) with a length the kernel handles, or B
-__device__ __forceinline__ int next_valid_traj(const FuseArgs& A, int b) {
-    for (b += gridDim.x; b < A.B; b += gridDim.x) {
-        const int n = (int)(A.offsets[b + 1] - A.offsets[b]);
-        if (n > 0 && n <= A.cap) break;
-    }
-    return b;
-}
 // warp B, lane 0: bulk copy of the timestamps of trajectory b into warp B's private buffer
 __device__ __forceinline__ void issue_ts_load(const FuseArgs& A, long long e0, int n, double* tsb, uint64_t* bar) {
     const int lead = (int)(e0 & 1), even = (n + lead) & ~1;
@@ -294,6 +287,21 @@ __device__ __forceinline__ void prefetch_pos_z(const FuseArgs& A, long long e0, 
     const uint32_t bytes = (uint32_t)(((long long)n + lead) * 24) & ~15u;
     const uint64_t pl = l2_policy_evict_last();
     if (bytes) { bulk_prefetch_l2_hint(A.pos + 3 * (e0 - lead), bytes, pl); bulk_prefetch_l2_hint(A.z + 3 * (e0 - lead), bytes, pl); }
+}
+
+// Work distribution: trajectories are handed out by a global counter (one atomicAdd per trajectory, issued three
+// trajectories ahead by compute thread 0), not by a static stride, so that all blocks finish within one trajectory
+// of each other whatever their individual pace.  A reference with b >= B ends the block's sequence.
+struct __align__(16) TrajRef { long long e0; int b; int n; };
+__device__ __forceinline__ TrajRef traj_ref_from(const FuseArgs& A, int b) {      // b: value returned by the counter
+    for (;;) {
+        if (b >= A.B) return TrajRef{0, A.B, 0};
+        const long long o0 = A.offsets[b], o1 = A.offsets[b + 1];
+        const long long n = o1 - o0;
+        if (n > 0 && n <= A.cap) return TrajRef{o0, b, (int)n};
+        A.status[b] = n <= 0 ? ST_EMPTY : ST_TOO_LONG;     // not handled by this kernel: take another one
+        b = atomicAdd(A.work_counter, 1);
+    }
 }
 
 constexpr int fast_min_blocks(int ct) { return ct <= 32 ? 5 : (ct == 64 ? 3 : (ct <= 128 ? 3 : 2)); }
@@ -395,24 +403,24 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
 
     uint32_t par_full = 0, par_q0 = 0, par_q1 = 0;
     const long long blk_t0 = clock64();
-    // offsets of the next trajectory are fetched one iteration ahead (their latency would otherwise stall every warp)
-    long long o0 = 0, o1 = 0;
-    if ((int)blockIdx.x < A.B) { o0 = A.offsets[blockIdx.x]; o1 = A.offsets[blockIdx.x + 1]; }
-    if (tid == 0 && (int)blockIdx.x < A.B) issue_trajectory_load_hint(A, o0, (int)(o1 - o0), ts_s, pos_s, z_s, mbar + MB_FULL);
+    // the block's work queue: entries 0-2 were filled before the kernel's first barrier; entry j + 3 is requested at
+    // the start of trajectory j and published at its end (before the slot is handed back to the look-ahead warps)
+    TrajRef* const ring = reinterpret_cast<TrajRef*>(sd + FS_RING);
+    TrajRef cur = ring[0];
+    if (tid == 0 && cur.b < A.B) issue_trajectory_load_hint(A, cur.e0, cur.n, ts_s, pos_s, z_s, mbar + MB_FULL);
     int j = 0;
-    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        const long long e0 = o0;
-        const int n = (int)(o1 - o0);
-        const bool has_next = b + (int)gridDim.x < A.B;
-        if (has_next) { o0 = A.offsets[b + gridDim.x]; o1 = A.offsets[b + gridDim.x + 1]; }
-        const int n_next = (int)(o1 - o0);
-        if (n <= 0 || n > A.cap) {
-            if (tid == 0) {
-                A.status[b] = n <= 0 ? ST_EMPTY : ST_TOO_LONG;
-                if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
-            }
-            continue;
-        }
+    for (;;) {
+        if (cur.b >= A.B) break;
+        const int b = cur.b, n = cur.n;
+        const long long e0 = cur.e0;
+        const TrajRef nxt = ring[(j + 1) & 3];
+        cur = nxt;
+        const bool has_next = nxt.b < A.B;
+        const long long o0 = nxt.e0;
+        const int n_next = nxt.n;
+        int fetched = 0;
+        if (tid == 0) fetched = atomicAdd(A.work_counter, 1);      // trajectory j + 3 (consumed after pass B)
+        TrajRef* const ring_out = ring + ((j + 3) & 3);
         const int slot = j & 1;
         ++j;
         GSF_FSTAMP(0);
@@ -443,6 +451,8 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
                 A.status[b] = ST_DEFERRED;
                 atomicAdd(A.defer_count, 1);
                 if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
+                *ring_out = traj_ref_from(A, fetched);
+                __threadfence_block();
             }
             named_sync(1, CT);                           // every thread has read the verdict
             named_arrive(NB_FREE_A + slot, CT + 32); named_arrive(NB_FREE_B + slot, CT + 32);
@@ -498,6 +508,8 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
             mbar_expect_tx(mbar + MB_QUAT0, (uint32_t)nq1 * 32u);
             if (nq1 > 0) bulk_g2s_hint(ts_s, A.quat + 4 * e0, (uint32_t)nq1 * 32u, mbar + MB_QUAT0, l2_policy_evict_first());
         }
+        TrajRef fref{0, 0, 0};
+        if (tid == 0) fref = traj_ref_from(A, fetched);
         GSF_FSTAMP(3);
 
         // ------------------------------------------------------------------ pass C: state recursion
@@ -594,6 +606,8 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
                 bulk_wait_read();                               // the position store has left shared memory
                 fence_proxy_async();
                 if (has_next) issue_trajectory_load_hint(A, o0, n_next, ts_s, pos_s, z_s, mbar + MB_FULL);
+                *ring_out = fref;
+                __threadfence_block();
             }
             named_arrive(NB_FREE_A + slot, CT + 32); named_arrive(NB_FREE_B + slot, CT + 32);
             if (bad) atomicOr(A.status + b, ST_BAD_QUATERNION);
@@ -624,18 +638,17 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
     // ====================================================================== warp A: Umeyama sums, one to two trajectories ahead
+    const TrajRef* const ring = reinterpret_cast<const TrajRef*>(sd + FS_RING);
     int j = 0;
-    long long o0 = 0, o1 = 0;
-    if ((int)blockIdx.x < A.B) { o0 = A.offsets[blockIdx.x]; o1 = A.offsets[blockIdx.x + 1]; }
-    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        const long long e0 = o0;
-        const int n = (int)(o1 - o0);
-        if (b + (int)gridDim.x < A.B) { o0 = A.offsets[b + gridDim.x]; o1 = A.offsets[b + gridDim.x + 1]; }
-        if (n <= 0 || n > A.cap) continue;
+    for (;;) {
         const int slot = j & 1, k = j >> 1;
-        ++j;
         GSF_FSTAMP(16);
-        if (k > 0) named_sync(NB_FREE_A + slot, CT + 32);
+        if (k > 0) named_sync(NB_FREE_A + slot, CT + 32);     // also publishes the queue entry of this trajectory
+        const TrajRef ref = ring[j & 3];
+        if (ref.b >= A.B) break;
+        const long long e0 = ref.e0;
+        const int n = ref.n;
+        ++j;
         GSF_FSTAMP(17);
         if (lane == 0) prefetch_pos_z(A, e0, n);          // whole trajectory into L2 now: rounds after the first hit L2
         const double* __restrict__ gp = A.pos + 3 * e0;
@@ -714,29 +727,21 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
     // ====================================================================== warp B: covariance start values, gap/window check, Umeyama finish
     double* tsb = sd + FS_PST + 6 * CT;
     uint32_t par_ts = 0;
-    {
-        int b0 = (int)blockIdx.x - (int)gridDim.x;
-        b0 = next_valid_traj(A, b0);
-        if (lane == 0 && b0 < A.B) issue_ts_load(A, A.offsets[b0], (int)(A.offsets[b0 + 1] - A.offsets[b0]), tsb, mbar + MB_TSB);
-    }
+    const TrajRef* const ring = reinterpret_cast<const TrajRef*>(sd + FS_RING);
+    if (lane == 0 && ring[0].b < A.B) issue_ts_load(A, ring[0].e0, ring[0].n, tsb, mbar + MB_TSB);
     int j = 0;
-    long long o0 = 0, o1 = 0;
-    if ((int)blockIdx.x < A.B) { o0 = A.offsets[blockIdx.x]; o1 = A.offsets[blockIdx.x + 1]; }
-    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        const long long e0 = o0;
-        const int n = (int)(o1 - o0);
-        if (b + (int)gridDim.x < A.B) { o0 = A.offsets[b + gridDim.x]; o1 = A.offsets[b + gridDim.x + 1]; }
-        if (n <= 0 || n > A.cap) continue;
+    for (;;) {
         const int slot = j & 1, k = j >> 1;
+        GSF_FSTAMP(24);
+        if (k > 0) named_sync(NB_FREE_B + slot, CT + 32);     // also publishes the queue entries up to trajectory j + 1
+        const TrajRef ref = ring[j & 3];
+        if (ref.b >= A.B) break;
+        const int b = ref.b, n = ref.n;
+        const long long e0 = ref.e0;
         ++j;
         // the global scalars this warp needs are requested here and consumed after the scan: the first quaternion
         // (lanes 0-3 hold one component each), the next trajectory's offsets (above) and, one trajectory ahead, the parameters
         const double q0c = A.quat[4 * e0 + (lane & 3)];
-        if (lane == 0 && A.params_per_traj && b + (int)gridDim.x < A.B) {
-            prefetch_l1(A.params + b + gridDim.x); prefetch_l1(reinterpret_cast<const char*>(A.params + b + gridDim.x) + 128);
-        }
-        GSF_FSTAMP(24);
-        if (k > 0) named_sync(NB_FREE_B + slot, CT + 32);
         GSF_FSTAMP(25);
         // parameters: this warp's shared-memory copy (a batch-wide record is fetched once)
         if (A.params_per_traj || k + slot == 0) {
@@ -757,10 +762,9 @@ __device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
         int general = xy_same ? cov_start_scan<2, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst, clk)
                               : cov_start_scan<3, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst, clk);
         __syncwarp();
-        if (lane == 0) {                                    // next trajectory's timestamps (its offsets are already in registers)
-            const int nn = (int)(o1 - o0);
-            if (b + (int)gridDim.x < A.B && nn > 0 && nn <= A.cap) issue_ts_load(A, o0, nn, tsb, mbar + MB_TSB);
-            else { const int bn = next_valid_traj(A, b); if (bn < A.B) issue_ts_load(A, A.offsets[bn], (int)(A.offsets[bn + 1] - A.offsets[bn]), tsb, mbar + MB_TSB); }
+        if (lane == 0) {                                    // next trajectory's timestamps (its queue entry was published with this slot's release)
+            const TrajRef nx = ring[j & 3];
+            if (nx.b < A.B) issue_ts_load(A, nx.e0, nx.n, tsb, mbar + MB_TSB);
         }
         GSF_FSTAMP(26);
         named_sync(NB_SUMS + slot, 64);
@@ -823,6 +827,12 @@ __global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel
 #pragma unroll
         for (int k = 0; k < 8; ++k) mbar_init(mbar + k, 1);
         fence_mbar_init();
+        TrajRef* ring = reinterpret_cast<TrajRef*>(reinterpret_cast<double*>(smem_raw) + 7 * (size_t)cap2 + FS_RING);
+        int f[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) f[k] = atomicAdd(A.work_counter, 1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ring[k] = traj_ref_from(A, f[k]);
     }
     __syncthreads();
     if (warp < NW) fast_compute_role<CT, LCH>(A);
@@ -832,13 +842,13 @@ __global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel
 
 // Deferred-trajectory counters (one per in-flight call, recycled round-robin): module-level device
 // memory, so the *_dev entry point needs no workspace argument and allocates nothing.
-__device__ int g_defer_count[64];
+__device__ int g_defer_count[128];          // pairs: [deferred count, work counter]
 cudaError_t defer_counter(int** out) {
     static std::atomic<unsigned> ticket{0};
     int* base = nullptr;
     cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_defer_count);
     if (e != cudaSuccess) return e;
-    *out = base + (ticket.fetch_add(1) & 63u);
+    *out = base + 2 * (ticket.fetch_add(1) & 63u);
     return cudaSuccess;
 }
 

@@ -18,6 +18,7 @@ struct FuseArgs {
     long long* phase_clock;   // debug: per-phase clock64() of block 0 (NULL = off)
     int only_deferred;        // general kernel: process only trajectories whose status is ST_DEFERRED
     int* defer_count;         // fast kernel: += deferred trajectories; general kernel (only_deferred): exit when 0
+    int* work_counter;        // fast kernel: next trajectory index to hand out (zeroed before the launch)
 };
 size_t fuse_smem_bytes(int cap);
 cudaError_t launch_fuse(const FuseArgs& a, int threads, int num_sms, cudaStream_t stream);
