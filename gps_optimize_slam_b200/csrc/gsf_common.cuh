@@ -57,6 +57,11 @@ static_assert(sizeof(FuseParams) == 23 * 8, "FuseParams layout is part of the C 
 // ----------------------------------------------------------------------------- small math
 struct Quat { double x, y, z, w; };
 
+#ifdef __CUDACC__
+// library rsqrt kept out of line: its special-case code would otherwise be inlined at every call site of the hot
+// Jacobi chain (instruction-cache footprint)
+static __device__ __noinline__ double rsqrt_lib(double x) { return rsqrt(x); }
+#endif
 GSF_HD __forceinline__ double rsqrt_(double x) {
 #ifdef __CUDA_ARCH__
     // CUDA's rsqrt() arithmetic (hardware seed + one third-order step) for arguments away from the ends of the
@@ -68,7 +73,7 @@ GSF_HD __forceinline__ double rsqrt_(double x) {
         const double e = fma(-x, r * r, 1.0);
         return fma(fma(e, 0.375, 0.5), r * e, r);
     }
-    return rsqrt(x);
+    return rsqrt_lib(x);
 #else
     return 1.0 / sqrt(x);
 #endif

@@ -386,7 +386,7 @@ __device__ __forceinline__ void pass_b2_gains(const double* __restrict__ tsS, do
 
 // ====================================================================== compute warps
 template <int CT, int LCH>
-__device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
+__device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
     // (pointers are derived from the shared array here so that the accesses compile to LDS/STS, not generic loads)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
@@ -622,7 +622,7 @@ __device__ __noinline__ void fast_compute_role(const FuseArgs& A) {
 }
 
 template <int CT, int LCH>
-__device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
+__device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
     // (pointers are derived from the shared array here so that the accesses compile to LDS/STS, not generic loads)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
@@ -709,7 +709,7 @@ __device__ __noinline__ void fast_sums_role(const FuseArgs& A) {
 }
 
 template <int CT, int LCH>
-__device__ __noinline__ void fast_scan_svd_role(const FuseArgs& A) {
+__device__ __forceinline__ void fast_scan_svd_role(const FuseArgs& A) {
     // (pointers are derived from the shared array here so that the accesses compile to LDS/STS, not generic loads)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cap2 = (A.cap + 3) & ~1;                      // even => every sub-buffer stays 16-byte aligned
