@@ -14,6 +14,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgsf.so")
 SOURCES = ["gsf_fused.cu", "gsf_fast.cu", "gsf_kernels.cu", "gsf_ransac.cu", "gsf_grid.cu", "gsf_ekf_api.cu", "gsf_synth.cu", "gsf_capi.cu"]
 EXTRA = os.environ.get("GSF_NVCC_EXTRA", "").split()
+PER_FILE = {}                     # per-source extra flags (tuning hook)
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true"]
 
@@ -44,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *PER_FILE.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

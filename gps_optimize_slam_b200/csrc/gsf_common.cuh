@@ -178,7 +178,10 @@ GSF_HD __forceinline__ bool jacobi_rotate_pair(double* a0, double* a1, double* v
     const double alpha = a0[0] * a0[0] + a0[1] * a0[1] + a0[2] * a0[2];
     const double beta = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
     const double gamma = a0[0] * a1[0] + a0[1] * a1[1] + a0[2] * a1[2];
-    if (gamma * gamma <= 1e-31 * alpha * beta || gamma == 0.0) return false;   // |cos angle| <= 3.2e-16
+#ifndef GSF_JACOBI_TOL2
+#define GSF_JACOBI_TOL2 1e-31
+#endif
+    if (gamma * gamma <= GSF_JACOBI_TOL2 * alpha * beta || gamma == 0.0) return false;   // |cos angle| <= 3.2e-16
     // rotation by theta in [-pi/4, pi/4] with tan(2 theta) = g2 / d:  cos(2 theta) = |d| / hyp, sin(2 theta) = sign(d) g2 / hyp,
     // c = sqrt((1 + cos 2theta) / 2), s = sin(2 theta) / (2 c)  -- two reciprocal square roots, no division
     // (dependent chain 23 operations instead of 30 for the tangent form; c^2 + s^2 = 1 to rounding either way)
@@ -205,9 +208,8 @@ GSF_HD __forceinline__ bool jacobi_rotate_pair(double* a0, double* a1, double* v
 // With singular pairs (u_i, v_i) sorted by sigma, the det=+1 matrix V diag(1,1,d) U^T equals
 // v1 u1^T + v2 u2^T + (v1 x v2)(u1 x u2)^T, so only the two dominant pairs are needed.
 // Returns false when sigma_2 is numerically zero (collinear points: R not unique).
-GSF_HD __forceinline__ bool umeyama_rotation(const double* H, double* R, double& sigma_sum, bool& reflected) {
-    // column-major copies: ca[j] = column j of the working matrix, cv[j] = column j of V
-    double ca[3][3], cv[3][3];
+// Part 1: the Jacobi sweeps.  ca[j] = column j of H V (the scaled left singular vectors), cv[j] = column j of V.
+GSF_HD __forceinline__ void jacobi_sweeps(const double* H, double (&ca)[3][3], double (&cv)[3][3]) {
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
@@ -222,6 +224,14 @@ GSF_HD __forceinline__ bool umeyama_rotation(const double* H, double* R, double&
         if (jacobi_rotate_pair(ca[1], ca[2], cv[1], cv[2])) rotated = true;
         if (!rotated) break;
     }
+}
+GSF_HD __forceinline__ double det3(const double* H) {
+    return H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
+}
+// Part 2: rotation and singular-value sum from the converged columns; det(H) = det(U) det(V) sigma1 sigma2 sigma3
+// decides the reflection branch.
+GSF_HD __forceinline__ bool rotation_from_columns(const double (&ca)[3][3], const double (&cv)[3][3], double detH, double* R,
+                                                  double& sigma_sum, bool& reflected) {
     // singular values = column norms; the two dominant pairs are picked with warp-uniform branches on the column
     // registers (no index arithmetic, no select chains)
     double sg[3];
@@ -231,8 +241,6 @@ GSF_HD __forceinline__ bool umeyama_rotation(const double* H, double* R, double&
         sg[j] = q > 0.0 ? q * rsqrt_(q) : 0.0;
     }
     sigma_sum = sg[0] + sg[1] + sg[2];
-    // det(H) = det(U) det(V) sigma1 sigma2 sigma3 decides the reflection branch.
-    double detH = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
     reflected = detH < 0.0;
     double u1[3], u2[3], v1[3], v2[3], s_hi, s_mid;
     const int imin = (sg[0] <= sg[1]) ? (sg[0] <= sg[2] ? 0 : 2) : (sg[1] <= sg[2] ? 1 : 2);
@@ -265,6 +273,11 @@ GSF_HD __forceinline__ bool umeyama_rotation(const double* H, double* R, double&
         for (int c = 0; c < 3; ++c) R[3 * r + c] = v1[r] * u1[c] + v2[r] * u2[c] + v3[r] * u3[c];
     return ok;
 }
+GSF_HD __forceinline__ bool umeyama_rotation(const double* H, double* R, double& sigma_sum, bool& reflected) {
+    double ca[3][3], cv[3][3];
+    jacobi_sweeps(H, ca, cv);
+    return rotation_from_columns(ca, cv, det3(H), R, sigma_sum, reflected);
+}
 
 // Finish Umeyama (EKFGPSSLAM.py:443-451) from the reduced sums.
 //   n      number of points, mu_s/mu_d centroids, H centred cross-covariance (not / n),
@@ -274,6 +287,20 @@ GSF_HD __forceinline__ int umeyama_finish(int n, const double* mu_s, const doubl
                                      double* R, double* t, double& s) {
     double sigma_sum; bool refl;
     bool ok = umeyama_rotation(H, R, sigma_sum, refl);
+    const double var_src = ss * rcp_((double)n);
+    if (var_src < 1e-12) s = 1.0;
+    else { s = sigma_sum * rcp_((double)n * var_src); if (s <= 1e-6) s = 1.0; }
+    double rx, ry, rz;
+    mat_vec(R, mu_s[0], mu_s[1], mu_s[2], rx, ry, rz);
+    t[0] = mu_d[0] - s * rx; t[1] = mu_d[1] - s * ry; t[2] = mu_d[2] - s * rz;
+    return ok ? ST_OK : ST_DEGENERATE;
+}
+
+// The same from converged Jacobi columns (the fast fused kernel runs the sweeps in another warp).
+GSF_HD __forceinline__ int umeyama_finish_columns(int n, const double* mu_s, const double* mu_d, const double (&ca)[3][3],
+                                                  const double (&cv)[3][3], double detH, double ss, double* R, double* t, double& s) {
+    double sigma_sum; bool refl;
+    bool ok = rotation_from_columns(ca, cv, detH, R, sigma_sum, refl);
     const double var_src = ss * rcp_((double)n);
     if (var_src < 1e-12) s = 1.0;
     else { s = sigma_sum * rcp_((double)n * var_src); if (s <= 1e-6) s = 1.0; }

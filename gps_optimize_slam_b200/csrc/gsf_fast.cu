@@ -28,13 +28,20 @@
 
 namespace gsf {
 
-constexpr int PASS_UNROLL = 2;      // per-pose loops of the compute warps: two steps per iteration (overlaps one step's
-                                    // stores / affine update with the next step's gain chain; full unrolling measured slower)
+#ifndef GSF_PASS_UNROLL
+#define GSF_PASS_UNROLL 1
+#endif
+constexpr int PASS_UNROLL = GSF_PASS_UNROLL;      // per-pose loops of the compute warps stay rolled: with the roles inlined, one step per
+                                    // iteration measured 3 % faster than two and 8 % faster than four (instruction-cache footprint)
 
 #ifndef GSF_QUAT_U
 #define GSF_QUAT_U 6
 #endif
-#define GSF_FSTAMP(k) do { if (pclk && j == 100) pclk[k] = clock64(); } while (0)       // pclk: per-role debug pointer, null in production
+#ifdef GSF_DEBUG_STAMPS                             // tools/phase_timing_fast.py: build with GSF_NVCC_EXTRA=-DGSF_DEBUG_STAMPS
+#define GSF_FSTAMP(k) do { if (pclk && j == 100) pclk[k] = clock64(); } while (0)       // pclk: per-role debug pointer
+#else
+#define GSF_FSTAMP(k) do { } while (0)
+#endif
 
 // ----------------------------------------------------------------------------- Moebius maps, NAX axes
 template <int NAX> struct MoebN { double m[4 * NAX]; };      // per axis row-major [a b; c d]
@@ -306,11 +313,20 @@ __device__ __forceinline__ TrajRef traj_ref_from(const FuseArgs& A, int b) {    
 
 constexpr int fast_min_blocks(int ct) { return ct <= 32 ? 5 : (ct == 64 ? 3 : (ct <= 128 ? 3 : 2)); }
 
-// Pass B1 of the compute warps, steps [s0, c1) of one thread: telescoped odometry u_i = M(C)(p_i - p_{i-1})
-// written over p_i, and the residual of the Sim3 image y_i = s M(C) p_i + t against the measurement
-// (y advanced by s*u each step).  No loop-carried chain besides p_{i-1} and y.
-__device__ __forceinline__ int pass_b1_odometry(double* __restrict__ posS, const double* __restrict__ zS, const double* __restrict__ bc,
-                                                int s0, int c1, double thr2, double pprev0, double pprev1, double pprev2) {
+// Pass B of the compute warps, steps [s0, c1) of one thread, in one loop:
+//  * telescoped odometry u_i = M(C)(p_i - p_{i-1}) and the residual of the Sim3 image y_i = s M(C) p_i + t against
+//    the measurement (y advanced by s*u each step);
+//  * per-step gains from the start covariance and the affine map x -> om x + (om u + k z) per axis; om overwrites
+//    the position row, om u + k z the measurement row.  The covariance is carried projectively, P = a / b, with the
+//    same step matrix as the scan warp ([1 qa; g g*qa+1], g = 1/r):  a' = a + qa b,  b' = b + g a',  k = g a' / b',
+//    om = b / b'.  The recursion (two dependent operations per step) is separated from the reciprocal, which
+//    pipelines across steps; k and om keep full relative accuracy.  P' = a'/b' = r pp / (pp + r) equals the
+//    reference's Joseph form (:731) up to rounding, and the recursion is contractive, so the difference stays at the
+//    1e-16 level.  XY: x and y share P0/Q/R (the shipped CONFIG), so the y gain is the x gain.
+template <bool XY>
+__device__ __forceinline__ int pass_b12(const double* __restrict__ tsS, double* __restrict__ posS, double* __restrict__ zS,
+                                        const double* __restrict__ bc, const FuseParams& prm, const double* __restrict__ pst,
+                                        int s0, int c1, double thr2, double pprev0, double pprev1, double pprev2, double tprev, Aff3& aff) {
     double RC[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) RC[k] = bc[k];
@@ -321,44 +337,27 @@ __device__ __forceinline__ int pass_b1_odometry(double* __restrict__ posS, const
         mat_vec(RC, pprev0, pprev1, pprev2, y0, y1, y2);
         y0 = sc * y0 + bc[16]; y1 = sc * y1 + bc[17]; y2 = sc * y2 + bc[18];
     }
-#pragma unroll PASS_UNROLL
-    for (int i = s0; i < c1; ++i) {
-        const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
-        double u0, u1, u2;
-        mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u0, u1, u2);
-        pprev0 = p0; pprev1 = p1; pprev2 = p2;
-        posS[3 * i] = u0; posS[3 * i + 1] = u1; posS[3 * i + 2] = u2;
-        if (thr2 > 0.0) {
-            y0 = fma(sc, u0, y0); y1 = fma(sc, u1, y1); y2 = fma(sc, u2, y2);
-            const double d0 = y0 - zS[3 * i], d1 = y1 - zS[3 * i + 1], d2 = y2 - zS[3 * i + 2];
-            if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
-        }
-    }
-    return nviol;
-}
-// Pass B2: per-step gains from the start covariance, affine map x -> om x + (om u + k z) per axis.  Overwrites u
-// (in pos) with om and z with om u + k z.  The covariance is carried projectively, P = a / b, with the same step
-// matrix as the scan warp ([1 qa; g g*qa+1], g = 1/r):  a' = a + qa b,  b' = b + g a',  k = g a' / b',  om = b / b'.
-// The recursion (two dependent operations per step) is separated from the reciprocal, which pipelines across
-// steps; k and om keep full relative accuracy.  P' = a'/b' = r pp / (pp + r) equals the reference's Joseph form
-// (:731) up to rounding, and the recursion is contractive, so the difference stays at the 1e-16 level.
-// XY: x and y share P0/Q/R (the shipped CONFIG), so the y gain is the x gain.
-template <bool XY>
-__device__ __forceinline__ void pass_b2_gains(const double* __restrict__ tsS, double* __restrict__ posS, double* __restrict__ zS,
-                                              const FuseParams& prm, const double* __restrict__ pst, int s0, int c1, double tprev, Aff3& aff) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) { aff.a[a] = 1.0; aff.b[a] = 0.0; }
     double ax = pst[0], ay = pst[1], az = pst[2], bx = 1.0, by = 1.0, bz = 1.0;
     const double qx = prm.q[0], qy = prm.q[1], qz = prm.q[2];
-    const double gx = fast_rcp(prm.r[0]), gy = XY ? gx : fast_rcp(prm.r[1]), gz = fast_rcp(prm.r[2]);   // r: positive normal (scan warp defers otherwise)
+    const double gx = fast_rcp(prm.r[0]), gy = XY ? gx : fast_rcp(prm.r[1]), gz = fast_rcp(prm.r[2]);
 #pragma unroll PASS_UNROLL
     for (int i = s0; i < c1; ++i) {
+        const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
+        const double z0 = zS[3 * i], z1 = zS[3 * i + 1], z2 = zS[3 * i + 2];
         const double ti = tsS[i];
+        double u0, u1, u2;
+        mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u0, u1, u2);
+        pprev0 = p0; pprev1 = p1; pprev2 = p2;
+        if (thr2 > 0.0) {
+            y0 = fma(sc, u0, y0); y1 = fma(sc, u1, y1); y2 = fma(sc, u2, y2);
+            const double d0 = y0 - z0, d1 = y1 - z1, d2 = y2 - z2;
+            if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+        }
         const double raw = ti - tprev;
         const double dt = raw > 1e-6 ? raw : 1e-6;          // = fmax(1e-6, raw), NaN included
         tprev = ti;
-        const double u0 = posS[3 * i], u1 = posS[3 * i + 1], u2 = posS[3 * i + 2];
-        const double z0 = zS[3 * i], z1 = zS[3 * i + 1], z2 = zS[3 * i + 2];
         double kx, ky, kz, ox, oy, oz;
         {
             ax = fma(qx * dt, bx, ax);
@@ -382,6 +381,7 @@ __device__ __forceinline__ void pass_b2_gains(const double* __restrict__ tsS, do
         aff.b[0] = ox * aff.b[0] + b0; aff.b[1] = oy * aff.b[1] + b1; aff.b[2] = oz * aff.b[2] + b2;
         aff.a[0] *= ox; aff.a[1] *= oy; aff.a[2] *= oz;
     }
+    return nviol;
 }
 
 // ====================================================================== compute warps
@@ -402,7 +402,9 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
     (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
 
     uint32_t par_full = 0, par_q0 = 0, par_q1 = 0;
+#ifdef GSF_DEBUG_STAMPS
     const long long blk_t0 = clock64();
+#endif
     // the block's work queue: entries 0-2 were filled before the kernel's first barrier; entry j + 3 is requested at
     // the start of trajectory j and published at its end (before the slot is handed back to the look-ahead warps)
     TrajRef* const ring = reinterpret_cast<TrajRef*>(sd + FS_RING);
@@ -479,10 +481,9 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
             if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
         }
         named_sync(1, CT);                               // neighbours' boundary poses are read before being overwritten
-        nviol += pass_b1_odometry(posS, zS, bc, s0, c1, thr2, pprev0, pprev1, pprev2);
         Aff3 aff;
-        if (xy_same) pass_b2_gains<true>(tsS, posS, zS, prm, pst + 3 * tid, s0, c1, tprev, aff);
-        else pass_b2_gains<false>(tsS, posS, zS, prm, pst + 3 * tid, s0, c1, tprev, aff);
+        if (xy_same) nviol += pass_b12<true>(tsS, posS, zS, bc, prm, pst + 3 * tid, s0, c1, thr2, pprev0, pprev1, pprev2, tprev, aff);
+        else nviol += pass_b12<false>(tsS, posS, zS, bc, prm, pst + 3 * tid, s0, c1, thr2, pprev0, pprev1, pprev2, tprev, aff);
         if (thr2 > 0.0) {
             nviol = warp_sum_i(nviol);
             if (lane == 0 && nviol) atomicAdd(iscr, nviol);
@@ -577,25 +578,22 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
             mbar_wait_polite(mbar + MB_QUAT0, par_q0); par_q0 ^= 1;
             bool second = n <= nq1;                             // part 2 landed (or does not exist)
             int bad = 0;
-            // two poses per iteration (independent chains, branch-free reciprocal square root)
+            // one pose per iteration, branch-free reciprocal square root (two interleaved poses per iteration measured
+            // 2 % slower with the roles inlined: instruction-cache footprint again)
 #pragma unroll 1
-            for (int i0 = tid - lane; i0 < n; i0 += 2 * CT) {   // warp-uniform trip count (the wait below syncs the warp)
-                if (!second && i0 + CT + 31 >= nq1) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; second = true; }
-                const int i = i0 + lane, i1 = i + CT;
-                const bool va = i < n, vb = i1 < n;
-                const int ia = va ? i : 0, ib = vb ? i1 : ia;   // tails re-read a landed pose and store nothing
-                const double2 lo0 = q2[2 * ia], hi0 = q2[2 * ia + 1], lo1 = q2[2 * ib], hi1 = q2[2 * ib + 1];
-                const Quat qa{lo0.x, lo0.y, hi0.x, hi0.y}, qb{lo1.x, lo1.y, hi1.x, hi1.y};
-                const double na = qnorm2(qa), nb = qnorm2(qb);
-                if (na == 0.0 || nb == 0.0) bad = 1;            // scipy raises here (:466); output row becomes NaN
-                const Quat ra = qscale(qmul(C, qa), fast_rsqrt(na)), rb = qscale(qmul(C, qb), fast_rsqrt(nb));
+            for (int i0 = tid - lane; i0 < n; i0 += CT) {       // warp-uniform trip count (the wait below syncs the warp)
+                if (!second && i0 + 31 >= nq1) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; second = true; }
+                const int i = i0 + lane;
+                const bool va = i < n;
+                const int ia = va ? i : 0;                      // the tail re-reads a landed pose and stores nothing
+                const double2 lo0 = q2[2 * ia], hi0 = q2[2 * ia + 1];
+                const Quat qa{lo0.x, lo0.y, hi0.x, hi0.y};
+                const double na = qnorm2(qa);
+                if (na == 0.0) bad = 1;                         // scipy raises here (:466); output row becomes NaN
+                const Quat ra = qscale(qmul(C, qa), fast_rsqrt(na));
                 if (va) {
                     stg2_hint(qout + 2 * i, make_double2(ra.x, ra.y), pf);
                     stg2_hint(qout + 2 * i + 1, make_double2(ra.z, ra.w), pf);
-                }
-                if (vb) {
-                    stg2_hint(qout + 2 * i1, make_double2(rb.x, rb.y), pf);
-                    stg2_hint(qout + 2 * i1 + 1, make_double2(rb.z, rb.w), pf);
                 }
             }
             if (!second) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; }     // keep every warp's phase in step
@@ -614,11 +612,13 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
             GSF_FSTAMP(6);
         }
     }
+#ifdef GSF_DEBUG_STAMPS
     if (A.phase_clock && tid == 0 && blockIdx.x % 37 == 0 && blockIdx.x / 37 < 12) {      // debug: per-block totals
         long long* o = A.phase_clock + 64 + 4 * (blockIdx.x / 37);
         unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         o[0] = clock64() - blk_t0; o[1] = j; o[2] = smid; o[3] = blk_t0;
     }
+#endif
 }
 
 template <int CT, int LCH>
@@ -657,7 +657,7 @@ __device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
         double v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = 0.0;
-        constexpr int NP = 2;                               // pose pairs in flight per lane
+        constexpr int NP = CT <= 32 ? 1 : 2;                // pose pairs in flight per lane (short trajectories, 5 blocks per SM: one measured 4 % faster)
         const int npairs = (n + 1) >> 1;
         const uint64_t pl = l2_policy_evict_last();
         if (!(e0 & 1)) {
@@ -757,8 +757,12 @@ __device__ __forceinline__ void fast_scan_svd_role(const FuseArgs& A) {
             mbar_wait_polite(mbar + MB_TSB, par_ts); par_ts ^= 1;
             __syncwarp();
         }
+#ifdef GSF_DEBUG_STAMPS
         long long* clk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && j == 100) ? A.phase_clock : nullptr;
         if (clk) clk[31] = clock64();
+#else
+        long long* const clk = nullptr;
+#endif
         int general = xy_same ? cov_start_scan<2, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst, clk)
                               : cov_start_scan<3, CT, LCH>(tsb + (e0 & 1), n, gprm, lane, pst, clk);
         __syncwarp();
@@ -882,7 +886,7 @@ static int fast_variant(int cap) {
     if (f == 32 && cap <= 32 * 9) return 3209;
     if (cap <= 32 * 9) return 3209;
     if (cap <= 64 * 9) return 6409;
-    if (cap <= 96 * 11) return 9611;
+    if (cap <= 64 * 17) return 6417;                 // two compute warps x 17 poses per thread: 1 % faster than 96 x 11 at 1000 poses
     if (cap <= 128 * 9) return 12809;
     return 0;
 }
