@@ -9,19 +9,26 @@
 // zero quaternion) are detected by the look-ahead warps, marked ST_DEFERRED and processed by the general
 // kernel (gsf_fused.cu) launched behind this one on the same stream.
 //
-// One block = CT compute threads + two look-ahead warps, persistent over trajectories b, b+grid, ...:
+// One block = CT compute threads + two look-ahead warps, persistent; trajectories are handed out by a global
+// counter through a four-entry queue in shared memory (compute thread 0 requests entry j + 3 while trajectory j
+// runs), so that every block ends within one trajectory of the others whatever its pace:
 //   * warp A (sums)  streams positions + measurements of trajectory j+1/j+2 straight from HBM with
 //     128-bit loads (the later TMA load of the same bytes hits L2), accumulates the 16 pivot-shifted
 //     Umeyama sums in a fixed order (lane-strided pose pairs, transposing butterfly) -> bit-reproducible;
 //   * warp B (scan + SVD) reads the timestamps, checks gap/window, composes the covariance recursion
-//     p -> R(p+q)/(p+q+R) per compute-thread chunk as 2x2 Moebius matrices (one warp scan over 32 lanes
-//     x CT/32 chunks) and publishes the covariance every compute thread starts from; then finishes
-//     Umeyama (one-sided Jacobi SVD) and publishes R, t, s, C = q_state0 (x) conj(q_hat0), M(C);
-//   * compute warps (trajectory j, resident in shared memory via three TMA bulk copies): exact per-step
-//     Joseph-form gains + affine state maps (pass B), affine scan, state recursion (pass C), bulk store,
-//     streaming quaternion pass, next TMA load.  No Moebius scan, no reduction, no SVD wait.
+//     p -> R(p+q)/(p+q+R) per compute-thread chunk as 2x2 Moebius matrices [1 qa; g g*qa+1], g = 1/R (branch-free
+//     interleaved chains, one warp scan over 32 lanes x CT/32 chunks) and publishes the covariance every compute
+//     thread starts from; then finishes Umeyama (one-sided Jacobi SVD) and publishes R, t, s,
+//     C = q_state0 (x) conj(q_hat0), M(C);
+//   * compute warps (trajectory j, resident in shared memory via three TMA bulk copies): pass B (telescoped
+//     odometry, residual check, per-step gains from the projectively carried covariance, affine state maps),
+//     affine scan, state recursion (pass C), bulk store, quaternion pass (TMA in two parts over the dead
+//     timestamp + position buffers), next TMA load.  No Moebius scan, no reduction, no SVD wait.
 //   Hand-offs are hardware named barriers (aux_ready / aux_free / sums_ready, two slots: bar.arrive on the
 //   signalling side, bar.sync on the waiting side); mbarriers only for the TMA completions.
+// The kernel is instruction-supply bound (12 resident warps per SM in three roles, ~85 KB of hot code against a
+// 32 KB L1.5 instruction cache): every per-pose loop is rolled, the roles are inlined into the kernel (parameters
+// from the constant bank), debug stamps are compiled out (GSF_DEBUG_STAMPS).  See DESIGN.md section 3.
 #include <cstdlib>
 #include <atomic>
 #include "gsf_fuse_shared.cuh"
