@@ -197,8 +197,8 @@ __device__ __forceinline__ int cov_start_scan(const double* __restrict__ gts, in
             const bool valid = i >= 1 && i < n;
             const double ti = gts[min(i, n - 1)];
             const double raw = ti - tpk[k];
-            if (valid && (raw > gap || ti > t_lim)) viol = 1;
-            moebn_step(ch[k], qv, gv, valid ? (raw > 1e-6 ? raw : 1e-6) : 0.0, valid);   // = fmax(1e-6, raw), NaN included
+            if (valid && (!(raw > 1e-6) || raw > gap || ti > t_lim)) viol = 1;     // dt <= 1e-6 s (the reference clamps, :863) or NaN: general kernel
+            moebn_step(ch[k], qv, gv, valid ? raw : 0.0, valid);
             tpk[k] = ti;
         }
     }
@@ -326,14 +326,14 @@ constexpr int fast_min_blocks(int ct) { return ct <= 32 ? 5 : (ct == 64 ? 3 : (c
 //  * per-step gains from the start covariance and the affine map x -> om x + (om u + k z) per axis; om overwrites
 //    the position row, om u + k z the measurement row.  The covariance is carried projectively, P = a / b, with the
 //    same step matrix as the scan warp ([1 qa; g g*qa+1], g = 1/r):  a' = a + qa b,  b' = b + g a',  k = g a' / b',
-//    om = b / b'.  The recursion (two dependent operations per step) is separated from the reciprocal, which
+//    om = 1 - k (one FMA).  The recursion (two dependent operations per step) is separated from the reciprocal, which
 //    pipelines across steps; k and om keep full relative accuracy.  P' = a'/b' = r pp / (pp + r) equals the
 //    reference's Joseph form (:731) up to rounding, and the recursion is contractive, so the difference stays at the
 //    1e-16 level.  XY: x and y share P0/Q/R (the shipped CONFIG), so the y gain is the x gain.
 template <bool XY>
 __device__ __forceinline__ int pass_b12(const double* __restrict__ tsS, double* __restrict__ posS, double* __restrict__ zS,
                                         const double* __restrict__ bc, const FuseParams& prm, const double* __restrict__ pst,
-                                        int s0, int c1, double thr2, double pprev0, double pprev1, double pprev2, double tprev, Aff3& aff) {
+                                        int s0, int c1, double thr2, double pprev0, double pprev1, double pprev2, Aff3& aff) {
     double RC[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) RC[k] = bc[k];
@@ -348,12 +348,14 @@ __device__ __forceinline__ int pass_b12(const double* __restrict__ tsS, double* 
     for (int a = 0; a < 3; ++a) { aff.a[a] = 1.0; aff.b[a] = 0.0; }
     double ax = pst[0], ay = pst[1], az = pst[2], bx = 1.0, by = 1.0, bz = 1.0;
     const double qx = prm.q[0], qy = prm.q[1], qz = prm.q[2];
-    const double gx = fast_rcp(prm.r[0]), gy = XY ? gx : fast_rcp(prm.r[1]), gz = fast_rcp(prm.r[2]);
+    const double gx = fast_rcp(prm.r[0]), gy = XY ? gx : fast_rcp(prm.r[1]), gz = fast_rcp(prm.r[2]);   // r: positive normal (scan warp defers otherwise)
 #pragma unroll PASS_UNROLL
     for (int i = s0; i < c1; ++i) {
         const double p0 = posS[3 * i], p1 = posS[3 * i + 1], p2 = posS[3 * i + 2];
         const double z0 = zS[3 * i], z1 = zS[3 * i + 1], z2 = zS[3 * i + 2];
-        const double ti = tsS[i];
+        // the reference's max(1e-6, dt) (:863) never binds here: the scan warp defers every trajectory with a
+        // step of 1e-6 s or less (or NaN) to the general kernel
+        const double dt = tsS[i] - tsS[i - 1];
         double u0, u1, u2;
         mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u0, u1, u2);
         pprev0 = p0; pprev1 = p1; pprev2 = p2;
@@ -362,25 +364,29 @@ __device__ __forceinline__ int pass_b12(const double* __restrict__ tsS, double* 
             const double d0 = y0 - z0, d1 = y1 - z1, d2 = y2 - z2;
             if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
         }
-        const double raw = ti - tprev;
-        const double dt = raw > 1e-6 ? raw : 1e-6;          // = fmax(1e-6, raw), NaN included
-        tprev = ti;
+        // in-place recursion (no loop-carried copies): a += qa b; ga = g a; b += ga; k = ga / b; om = 1 - k
         double kx, ky, kz, ox, oy, oz;
         {
             ax = fma(qx * dt, bx, ax);
-            const double ga = gx * ax, bn = bx + ga, rb = fast_rcp(bn);
-            kx = ga * rb; ox = bx * rb; bx = bn;
+            const double ga = gx * ax;
+            bx += ga;
+            const double rb = fast_rcp(bx);
+            kx = ga * rb; ox = fma(-ga, rb, 1.0);
         }
         if (XY) { ky = kx; oy = ox; }
         else {
             ay = fma(qy * dt, by, ay);
-            const double ga = gy * ay, bn = by + ga, rb = fast_rcp(bn);
-            ky = ga * rb; oy = by * rb; by = bn;
+            const double ga = gy * ay;
+            by += ga;
+            const double rb = fast_rcp(by);
+            ky = ga * rb; oy = fma(-ga, rb, 1.0);
         }
         {
             az = fma(qz * dt, bz, az);
-            const double ga = gz * az, bn = bz + ga, rb = fast_rcp(bn);
-            kz = ga * rb; oz = bz * rb; bz = bn;
+            const double ga = gz * az;
+            bz += ga;
+            const double rb = fast_rcp(bz);
+            kz = ga * rb; oz = fma(-ga, rb, 1.0);
         }
         const double b0 = ox * u0 + kx * z0, b1 = oy * u1 + ky * z1, b2 = oz * u2 + kz * z2;
         posS[3 * i] = ox; posS[3 * i + 1] = oy; posS[3 * i + 2] = oz;
@@ -478,8 +484,8 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
 
         // ------------------------------------------------------------------ pass B: gains, affine maps, residual check
         const double thr2 = !(prm.residual_thresh > 0.0) ? -1.0 : prm.residual_thresh * prm.residual_thresh;
-        double pprev0 = 0.0, pprev1 = 0.0, pprev2 = 0.0, tprev = 0.0;
-        if (c0 < n) { const int ip = max(c0 - 1, 0); pprev0 = posS[3 * ip]; pprev1 = posS[3 * ip + 1]; pprev2 = posS[3 * ip + 2]; tprev = tsS[ip]; }
+        double pprev0 = 0.0, pprev1 = 0.0, pprev2 = 0.0;
+        if (c0 < n) { const int ip = max(c0 - 1, 0); pprev0 = posS[3 * ip]; pprev1 = posS[3 * ip + 1]; pprev2 = posS[3 * ip + 2]; }
         int nviol = 0;
         if (c0 == 0 && thr2 > 0.0) {                      // pose 0 against its Sim3 image
             double rx, ry, rz;
@@ -489,8 +495,8 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
         }
         named_sync(1, CT);                               // neighbours' boundary poses are read before being overwritten
         Aff3 aff;
-        if (xy_same) nviol += pass_b12<true>(tsS, posS, zS, bc, prm, pst + 3 * tid, s0, c1, thr2, pprev0, pprev1, pprev2, tprev, aff);
-        else nviol += pass_b12<false>(tsS, posS, zS, bc, prm, pst + 3 * tid, s0, c1, thr2, pprev0, pprev1, pprev2, tprev, aff);
+        if (xy_same) nviol += pass_b12<true>(tsS, posS, zS, bc, prm, pst + 3 * tid, s0, c1, thr2, pprev0, pprev1, pprev2, aff);
+        else nviol += pass_b12<false>(tsS, posS, zS, bc, prm, pst + 3 * tid, s0, c1, thr2, pprev0, pprev1, pprev2, aff);
         if (thr2 > 0.0) {
             nviol = warp_sum_i(nviol);
             if (lane == 0 && nviol) atomicAdd(iscr, nviol);
