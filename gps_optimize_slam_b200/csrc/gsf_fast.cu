@@ -589,27 +589,32 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
             double2* __restrict__ qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
             const double2* __restrict__ q2 = reinterpret_cast<const double2*>(qs);
             mbar_wait_polite(mbar + MB_QUAT0, par_q0); par_q0 ^= 1;
-            bool second = n <= nq1;                             // part 2 landed (or does not exist)
             int bad = 0;
             // one pose per iteration, branch-free reciprocal square root (two interleaved poses per iteration measured
-            // 2 % slower with the roles inlined: instruction-cache footprint again)
+            // 2 % slower with the roles inlined: instruction-cache footprint again).  Two phases over the same loop
+            // body: warp-rows that lie entirely in part 1, then -- after part 2 has landed -- the rest.
+            int i0 = tid - lane;                                // warp-uniform loop variables (the wait below syncs the warp)
+            int stop = min(n, nq1);                             // nq1 is a multiple of 32
 #pragma unroll 1
-            for (int i0 = tid - lane; i0 < n; i0 += CT) {       // warp-uniform trip count (the wait below syncs the warp)
-                if (!second && i0 + 31 >= nq1) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; second = true; }
-                const int i = i0 + lane;
-                const bool va = i < n;
-                const int ia = va ? i : 0;                      // the tail re-reads a landed pose and stores nothing
-                const double2 lo0 = q2[2 * ia], hi0 = q2[2 * ia + 1];
-                const Quat qa{lo0.x, lo0.y, hi0.x, hi0.y};
-                const double na = qnorm2(qa);
-                if (na == 0.0) bad = 1;                         // scipy raises here (:466); output row becomes NaN
-                const Quat ra = qscale(qmul(C, qa), fast_rsqrt(na));
-                if (va) {
-                    stg2_hint(qout + 2 * i, make_double2(ra.x, ra.y), pf);
-                    stg2_hint(qout + 2 * i + 1, make_double2(ra.z, ra.w), pf);
+            for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+                for (; i0 < stop; i0 += CT) {
+                    const int i = i0 + lane;
+                    const bool va = i < n;
+                    const int ia = va ? i : 0;                  // the tail re-reads a landed pose and stores nothing
+                    const double2 lo0 = q2[2 * ia], hi0 = q2[2 * ia + 1];
+                    const Quat qa{lo0.x, lo0.y, hi0.x, hi0.y};
+                    const double na = qnorm2(qa);
+                    if (na == 0.0) bad = 1;                     // scipy raises here (:466); output row becomes NaN
+                    const Quat ra = qscale(qmul(C, qa), fast_rsqrt(na));
+                    if (va) {
+                        stg2_hint(qout + 2 * i, make_double2(ra.x, ra.y), pf);
+                        stg2_hint(qout + 2 * i + 1, make_double2(ra.z, ra.w), pf);
+                    }
                 }
+                if (phase == 0 && n > nq1) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; }
+                stop = n;
             }
-            if (!second) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; }     // keep every warp's phase in step
             GSF_FSTAMP(5);
             fence_proxy_async();                                // generic reads of the buffer before the next TMA writes
             named_sync(1, CT);                                  // status[b] is written; every thread is done with the buffers
