@@ -681,7 +681,6 @@ __device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
         for (int q = 0; q < 16; ++q) v[q] = 0.0;
         constexpr int NP = CT <= 32 ? 1 : 2;                // pose pairs in flight per lane (short trajectories, 5 blocks per SM: one measured 4 % faster)
         const int npairs = (n + 1) >> 1;
-        const uint64_t pl = l2_policy_evict_last();
         if (!(e0 & 1)) {
             const double2* __restrict__ gp2 = reinterpret_cast<const double2*>(gp);
             const double2* __restrict__ gz2 = reinterpret_cast<const double2*>(gz);
@@ -694,7 +693,9 @@ __device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
                     const int pp = p + 32 * h;
                     if (2 * pp + 1 < n) {
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) { a[h][q] = ldg2_hint(gp2 + 3 * pp + q, pl); c[h][q] = ldg2_hint(gz2 + 3 * pp + q, pl); }
+                                                // plain read-only loads: the lines were requested with evict_last by the bulk prefetch above, and a
+                        // per-load cache-policy operand costs two uniform-register moves per load in this loop
+                        for (int q = 0; q < 3; ++q) { a[h][q] = __ldg(gp2 + 3 * pp + q); c[h][q] = __ldg(gz2 + 3 * pp + q); }
                     } else if (2 * pp < n) {                    // last pose of an odd-length trajectory
                         a[h][0] = make_double2(gp[6 * pp], gp[6 * pp + 1]); a[h][1] = make_double2(gp[6 * pp + 2], 0.0);
                         c[h][0] = make_double2(gz[6 * pp], gz[6 * pp + 1]); c[h][1] = make_double2(gz[6 * pp + 2], 0.0);
