@@ -858,11 +858,10 @@ __global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel
         for (int k = 0; k < 8; ++k) mbar_init(mbar + k, 1);
         fence_mbar_init();
         TrajRef* ring = reinterpret_cast<TrajRef*>(reinterpret_cast<double*>(smem_raw) + 7 * (size_t)cap2 + FS_RING);
-        int f[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) f[k] = atomicAdd(A.work_counter, 1);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ring[k] = traj_ref_from(A, f[k]);
+        // one after the other: an entry that skips an unusable trajectory draws a new index, and that index must be
+        // larger than those of the entries before it and smaller than those after it -- the end-of-sequence entry
+        // (b >= B) has to be the last one of a block
+        for (int k = 0; k < 3; ++k) ring[k] = traj_ref_from(A, atomicAdd(A.work_counter, 1));
     }
     __syncthreads();
     if (warp < NW) fast_compute_role<CT, LCH>(A);

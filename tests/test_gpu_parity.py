@@ -471,6 +471,49 @@ def test_fast_kernel_per_trajectory_parameters_all_axes_distinct(gsf):
         np.testing.assert_allclose(q[off[b]:off[b + 1]], o["quat"], rtol=0, atol=ROT_ATOL)
 
 
+def test_fast_kernel_deferral_conditions_and_work_queue(gsf):
+    """Inputs the warp-specialised kernel must hand to the general kernel (ST_DEFERRED internally, never visible to
+    the caller), mixed with trajectories it handles itself and with empty ones the work queue has to skip:
+    repeated / decreasing timestamps (the reference clamps dt to 1e-6 s, :863), a measurement variance so small that
+    the projective covariance recursion leaves its range, and a normal trajectory with extreme but representable
+    noise ratios.  Many more trajectories than thread blocks per SM slot, so the dynamic queue wraps its ring."""
+    import os
+    from gps_optimize_slam_b200 import synth
+    from oracle import fusion_oracle as fo
+    lens = [271, 300, 0, 271, 64, 1000, 0, 333, 271, 500] + [97] * 30
+    trajs = [synth.make_trajectory(500 + k, n=max(n, 1), dt=0.1, speed=10.0) for k, n in enumerate(lens)]
+    for k, n in enumerate(lens):
+        if n == 0:
+            for key in ("ts", "pos", "quat", "gps"):
+                trajs[k][key] = trajs[k][key][:0]
+    trajs[1]["ts"][100] = trajs[1]["ts"][99]                      # dt = 0      -> clamp in the reference
+    trajs[3]["ts"][50] = trajs[3]["ts"][49] - 0.03                # dt < 0      -> clamp in the reference
+    trajs[7]["ts"][10] = trajs[7]["ts"][9] + 5e-7                 # 0 < dt < 1e-6
+    base = ([0.1] * 3 + [0.01] * 4, [0.1, 0.1, 0.7] + [0.01] * 4, [0.2] * 3)
+    sets = [base] * len(lens)
+    sets[4] = ([0.1] * 3 + [0.01] * 4, [50.0, 50.0, 80.0] + [0.01] * 4, [1e-14] * 3)      # q dt / r ~ 5e14 per step
+    sets[8] = ([1e-3] * 3 + [0.01] * 4, [10.0, 10.0, 3.0] + [0.01] * 4, [1e-4, 1e-4, 2e-4])  # large but in range
+    ts, pos, quat, z, off_d, off, max_len = pack(trajs)
+    prm = gsf.params_tensor(per_traj=sets)
+    p, q, sim3, st = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, prm, params_per_traj=True)
+    os.environ["GSF_FUSE_IMPL"] = "general"
+    try:
+        pg, qg, _, stg = gsf.fuse_batched(ts, pos, quat, z, off_d, max_len, prm, params_per_traj=True)
+    finally:
+        del os.environ["GSF_FUSE_IMPL"]
+    st, stg = st.cpu().numpy(), stg.cpu().numpy()
+    np.testing.assert_array_equal(st, stg)
+    assert (st[[k for k, n in enumerate(lens) if n > 0]] == 0).all(), st
+    p, q, pg, qg = [x.cpu().numpy() for x in (p, q, pg, qg)]
+    np.testing.assert_allclose(p, pg, rtol=0, atol=POS_ATOL); np.testing.assert_allclose(q, qg, rtol=0, atol=ROT_ATOL)
+    for b in (0, 1, 3, 4, 5, 7, 8, 12):
+        cfg = fo.default_config()
+        cfg["ekf"].update(initial_cov_diag=sets[b][0], process_noise_diag=sets[b][1], meas_noise_diag=sets[b][2])
+        o = oracle_pipeline(trajs[b], cfg)
+        np.testing.assert_allclose(p[off[b]:off[b + 1]], o["pos"], rtol=0, atol=POS_ATOL)
+        np.testing.assert_allclose(q[off[b]:off[b + 1]], o["quat"], rtol=0, atol=ROT_ATOL)
+
+
 @pytest.mark.parametrize("n,dt", [(300, 0.104), (2200, 0.104)])
 def test_hypothesis_grid_matches_oracle(gsf, n, dt):
     """gsf_ekf_hypothesis_grid_dev (one trajectory x H noise sets -> ATE statistics) against the oracle run
