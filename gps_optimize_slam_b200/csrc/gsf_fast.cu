@@ -443,7 +443,8 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
         const double* pst = sd + FS_PST + 3 * CT * slot;
         const int lead = (int)(e0 & 1);
         double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
-        if (tid < 23) sd[FS_PRM + tid] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[tid];
+        if (tid < 23 && (A.params_per_traj || j == 1))      // a batch-wide record is fetched once
+            sd[FS_PRM + tid] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[tid];
         if (tid == 32 % CT) iscr[0] = 0;
         {
             const int cnt = n + lead, even = cnt & ~1;
@@ -456,10 +457,9 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
             if (even > 0) { mbar_wait_polite(mbar + MB_FULL, par_full); par_full ^= 1; }
         }
         GSF_FSTAMP(1);
-        named_sync(NB_AUXRDY + slot, CT + 32);             // look-ahead results of this trajectory are published
-        __threadfence_block();
+        named_sync(NB_AUXRDY + slot, CT + 32);             // look-ahead results of this trajectory are published (and, as every
+        __threadfence_block();                             // compute thread takes part, the parameter / tail writes above)
         GSF_FSTAMP(2);
-        named_sync(1, CT);
         if (bc[30] != 0.0) {
             // needs the general machinery: leave it to the general kernel
             if (tid == 0) {
