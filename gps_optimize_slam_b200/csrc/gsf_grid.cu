@@ -237,100 +237,103 @@ __global__ void __launch_bounds__(GRID_THREADS) ekf_grid_kernel(const double* __
 // ----------------------------------------------------------------------------- median of each hypothesis' error column
 // Exact order statistics by radix selection on the bit patterns (errors are >= 0, so the IEEE patterns order like
 // unsigned integers): 8-bit digits from the top, per pass a 256-bin histogram of the digit among the elements that
-// still match the selected prefix, then the bin holding the wanted rank.  One block handles FOUR adjacent hypotheses
-// (one 32-byte sector of a table row) and both middle ranks (np.median of an even count averages them) at once:
-// hist[4][2][256].  Passes whose digit is identical for the whole column (sign / exponent bytes, typically) are
-// skipped through the column's min / max keys.
-constexpr int MED_Q = 4;
+// still match the selected prefix, then the bin holding the wanted rank.  One block handles MED_COLS = 32 adjacent
+// hypotheses -- a warp reads 256 contiguous bytes of a table row, eight rows per block and step (the first version
+// took four hypotheses per block, one 32-byte sector per row: 1.9 TB/s) -- and both middle ranks (np.median of an
+// even count averages them) at once.  Histograms: [rank][column][257] (padded: equal digits in the 32 columns of a
+// warp fall into 32 different banks).  Passes whose digit is identical for the whole column (sign / exponent bytes,
+// typically) are skipped through the column's min / max keys; the bin of a rank is found by a warp (8 bins per lane,
+// shuffle scan) instead of a 255-step serial walk.
+constexpr int MED_COLS = 32;
+constexpr int MED_HSTRIDE = 257;
+constexpr size_t MED_SMEM = (size_t)2 * MED_COLS * MED_HSTRIDE * sizeof(unsigned int);
 __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restrict__ err, const double* __restrict__ hdr, int H,
                                                           double* __restrict__ stats, const int* __restrict__ status) {
-    __shared__ unsigned int hist[MED_Q][2][256];
-    __shared__ unsigned long long prefix[MED_Q][2], kmin[MED_Q], kmax[MED_Q];
-    __shared__ unsigned int rank[MED_Q][2];
+    extern __shared__ __align__(128) unsigned char smem_raw[];          // (same declaration as the grid kernel's)
+    unsigned int* const hist = reinterpret_cast<unsigned int*>(smem_raw);      // [(w * MED_COLS + c) * MED_HSTRIDE + digit]
+    __shared__ unsigned long long prefix[MED_COLS][2], kmin[MED_COLS], kmax[MED_COLS];
+    __shared__ unsigned int rank[MED_COLS][2];
+    __shared__ int first_s;
     const int m = (int)hdr[3];
     if ((status[0] & GRID_FATAL) || (int)hdr[4] != m || m == 0) return;
-    const int nquads = (H + MED_Q - 1) / MED_Q;
-    const int tid = threadIdx.x;
-    for (int quad = blockIdx.x; quad < nquads; quad += gridDim.x) {
-        const int h0 = quad * MED_Q;
-        const int nq = min(MED_Q, H - h0);
-        const bool vec = nq == MED_Q && (H % MED_Q) == 0;                 // rows of the quad are 32-byte aligned
+    const int ntiles = (H + MED_COLS - 1) / MED_COLS;
+    const int tid = threadIdx.x, c = tid & 31, rg = tid >> 5;           // column of the tile, row group (0-7)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int h0 = tile * MED_COLS;
+        const bool live = h0 + c < H;
+        const double* __restrict__ col = err + h0 + c;
         __syncthreads();
-        if (tid < MED_Q) { kmin[tid] = ~0ull; kmax[tid] = 0ull; rank[tid][0] = (unsigned)((m - 1) / 2); rank[tid][1] = (unsigned)(m / 2); prefix[tid][0] = prefix[tid][1] = 0ull; }
+        if (tid < MED_COLS) { kmin[tid] = ~0ull; kmax[tid] = 0ull; rank[tid][0] = (unsigned)((m - 1) / 2); rank[tid][1] = (unsigned)(m / 2); prefix[tid][0] = prefix[tid][1] = 0ull; }
         __syncthreads();
-        auto load_row = [&](int r, unsigned long long* k) {
-            const double* p = err + (size_t)r * H + h0;
-            if (vec) {
-                const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-                k[0] = (unsigned long long)__double_as_longlong(a.x); k[1] = (unsigned long long)__double_as_longlong(a.y);
-                k[2] = (unsigned long long)__double_as_longlong(b.x); k[3] = (unsigned long long)__double_as_longlong(b.y);
-            } else {
-#pragma unroll
-                for (int q = 0; q < MED_Q; ++q) k[q] = q < nq ? (unsigned long long)__double_as_longlong(p[q]) : 0ull;
-            }
-        };
         // column min / max keys
-        {
-            unsigned long long lo[MED_Q], hi[MED_Q];
-#pragma unroll
-            for (int q = 0; q < MED_Q; ++q) { lo[q] = ~0ull; hi[q] = 0ull; }
-            for (int r = tid; r < m; r += 256) {
-                unsigned long long k[MED_Q];
-                load_row(r, k);
-#pragma unroll
-                for (int q = 0; q < MED_Q; ++q) { lo[q] = min(lo[q], k[q]); hi[q] = max(hi[q], k[q]); }
+        if (live) {
+            unsigned long long lo = ~0ull, hi = 0ull;
+            for (int r = rg; r < m; r += 8) {
+                const unsigned long long k = (unsigned long long)__double_as_longlong(__ldg(col + (size_t)r * H));
+                lo = min(lo, k); hi = max(hi, k);
             }
-#pragma unroll
-            for (int q = 0; q < MED_Q; ++q) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { lo[q] = min(lo[q], __shfl_xor_sync(GSF_FULL_MASK, lo[q], o)); hi[q] = max(hi[q], __shfl_xor_sync(GSF_FULL_MASK, hi[q], o)); }
-                if ((tid & 31) == 0) { atomicMin(&kmin[q], lo[q]); atomicMax(&kmax[q], hi[q]); }
-            }
+            atomicMin(&kmin[c], lo); atomicMax(&kmax[c], hi);
         }
         __syncthreads();
-        // first digit position (from the top) where any column of the quad varies
-        int first = 8;
-        for (int q = 0; q < nq; ++q) {
-            const unsigned long long x = kmin[q] ^ kmax[q];
-            const int d = x ? (__clzll((long long)x) >> 3) : 8;
-            first = min(first, d);
+        // first digit position (from the top) where any column of the tile varies
+        if (tid < 32) {
+            const unsigned long long x = h0 + tid < H ? (kmin[tid] ^ kmax[tid]) : 0ull;
+            int d = x ? (__clzll((long long)x) >> 3) : 8;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d = min(d, __shfl_xor_sync(GSF_FULL_MASK, d, o));
+            if (tid == 0) first_s = d;
         }
-        if (tid < MED_Q) {                                                  // bytes above `first` are common to the whole column
+        __syncthreads();
+        const int first = first_s;
+        if (tid < MED_COLS) {                                             // bytes above `first` are common to the whole column
             const unsigned long long keep = first == 0 ? 0ull : (~0ull << (64 - 8 * first));
             prefix[tid][0] = prefix[tid][1] = kmin[tid] & keep;
         }
         __syncthreads();
         for (int d = first; d < 8; ++d) {
             const int shift = 56 - 8 * d;
-            for (int k = tid; k < MED_Q * 2 * 256; k += 256) (&hist[0][0][0])[k] = 0u;
+            for (int k = tid; k < 2 * MED_COLS * MED_HSTRIDE; k += 256) hist[k] = 0u;
             __syncthreads();
-            const unsigned long long himask = d == 0 ? 0ull : (~0ull << (64 - 8 * d));
-            unsigned long long pf[MED_Q][2];
-#pragma unroll
-            for (int q = 0; q < MED_Q; ++q) { pf[q][0] = prefix[q][0]; pf[q][1] = prefix[q][1]; }
-            for (int r = tid; r < m; r += 256) {
-                unsigned long long k[MED_Q];
-                load_row(r, k);
-#pragma unroll
-                for (int q = 0; q < MED_Q; ++q) {
-                    const unsigned dig = (unsigned)(k[q] >> shift) & 255u;
-                    const unsigned long long top = k[q] & himask;
-                    if (top == pf[q][0]) atomicAdd(&hist[q][0][dig], 1u);
-                    if (top == pf[q][1]) atomicAdd(&hist[q][1][dig], 1u);
+            if (live) {
+                const unsigned long long himask = d == 0 ? 0ull : (~0ull << (64 - 8 * d));
+                const unsigned long long pf0 = prefix[c][0], pf1 = prefix[c][1];
+                unsigned int* const h0p = hist + (size_t)c * MED_HSTRIDE;
+                unsigned int* const h1p = hist + (size_t)(MED_COLS + c) * MED_HSTRIDE;
+                for (int r = rg; r < m; r += 8) {
+                    const unsigned long long k = (unsigned long long)__double_as_longlong(__ldg(col + (size_t)r * H));
+                    const unsigned dig = (unsigned)(k >> shift) & 255u;
+                    const unsigned long long top = k & himask;
+                    if (top == pf0) atomicAdd(h0p + dig, 1u);
+                    if (top == pf1) atomicAdd(h1p + dig, 1u);
                 }
             }
             __syncthreads();
-            if (tid < MED_Q * 2) {                                          // one thread per (hypothesis, rank): find the bin
-                const int q = tid >> 1, w = tid & 1;
-                unsigned r = rank[q][w], acc = 0;
-                int bin = 0;
-                for (; bin < 255; ++bin) { const unsigned c = hist[q][w][bin]; if (acc + c > r) break; acc += c; }
-                rank[q][w] = r - acc;
-                prefix[q][w] |= (unsigned long long)bin << shift;
+            // one warp per (column, rank) pair, 8 pairs per warp: 8 bins per lane, inclusive shuffle scan, then the lane
+            // whose range holds the rank walks its 8 bins
+            for (int pair = rg; pair < 2 * MED_COLS; pair += 8) {
+                const int q = pair & (MED_COLS - 1), w = pair >> 5;
+                const unsigned int* hp = hist + (size_t)(w * MED_COLS + q) * MED_HSTRIDE + 8 * c;      // c = lane
+                unsigned cnt[8], tot = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { cnt[k] = hp[k]; tot += cnt[k]; }
+                const unsigned r = rank[q][w];                          // read by every lane before the shuffles below, written after them
+                unsigned inc = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(GSF_FULL_MASK, inc, o); if (c >= o) inc += y; }
+                const unsigned exc = inc - tot;
+                // the owning lane: exc <= r < inc; if the rank lies beyond every bin (cannot happen for r < population)
+                // the last lane takes it, like the serial walk that stopped at bin 255
+                const bool mine = (r >= exc && r < inc) || (c == 31 && r >= inc);
+                if (mine) {
+                    unsigned acc = exc; int bin = 0;
+                    for (; bin < 7; ++bin) { if (acc + cnt[bin] > r) break; acc += cnt[bin]; }
+                    rank[q][w] = r - acc;
+                    prefix[q][w] |= (unsigned long long)(8 * c + bin) << shift;
+                }
             }
             __syncthreads();
         }
-        if (tid < nq) {
+        if (tid < MED_COLS && h0 + tid < H) {
             const int h = h0 + tid;
             double* o = stats + 4 * (size_t)h;
             const double a = __longlong_as_double((long long)prefix[tid][0]), b = __longlong_as_double((long long)prefix[tid][1]);
@@ -381,9 +384,11 @@ cudaError_t launch_hypothesis_grid(const double* ts, const double* pos, const do
     else if (H >= num_sms * 512) e = launch_grid_t<512>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, stream);
     else e = launch_grid_t<256>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, stream);
     if (e != cudaSuccess) return e;
-    const int nquads = (H + MED_Q - 1) / MED_Q;
-    const int mg = nquads < num_sms * 8 ? nquads : num_sms * 8;
-    grid_median_kernel<<<mg, 256, 0, stream>>>(err, hdr, H, stats, st);
+    const int ntiles = (H + MED_COLS - 1) / MED_COLS;
+    const int mg = ntiles < num_sms * 3 ? ntiles : num_sms * 3;           // 66 KB of histograms per block: three blocks per SM
+    e = cudaFuncSetAttribute(grid_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MED_SMEM);
+    if (e != cudaSuccess) return e;
+    grid_median_kernel<<<mg, 256, MED_SMEM, stream>>>(err, hdr, H, stats, st);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (sim3_out) { e = cudaMemcpyAsync(sim3_out, R, 13 * sizeof(double), cudaMemcpyDeviceToDevice, stream); if (e != cudaSuccess) return e; }
