@@ -246,13 +246,15 @@ __global__ void __launch_bounds__(GRID_THREADS) ekf_grid_kernel(const double* __
 // shuffle scan) instead of a 255-step serial walk.
 constexpr int MED_COLS = 32;
 constexpr int MED_HSTRIDE = 257;
+constexpr int MED_CAP = 16;           // candidates per (column, rank) below which the selection finishes by gathering them
 constexpr size_t MED_SMEM = (size_t)2 * MED_COLS * MED_HSTRIDE * sizeof(unsigned int);
 __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restrict__ err, const double* __restrict__ hdr, int H,
                                                           double* __restrict__ stats, const int* __restrict__ status) {
     extern __shared__ __align__(128) unsigned char smem_raw[];          // (same declaration as the grid kernel's)
     unsigned int* const hist = reinterpret_cast<unsigned int*>(smem_raw);      // [(w * MED_COLS + c) * MED_HSTRIDE + digit]
     __shared__ unsigned long long prefix[MED_COLS][2], kmin[MED_COLS], kmax[MED_COLS];
-    __shared__ unsigned int rank[MED_COLS][2];
+    __shared__ unsigned int rank[MED_COLS][2], pop[MED_COLS][2], lcount[MED_COLS][2];
+    __shared__ unsigned long long list[MED_COLS][2][MED_CAP];
     __shared__ int first_s;
     const int m = (int)hdr[3];
     if ((status[0] & GRID_FATAL) || (int)hdr[4] != m || m == 0) return;
@@ -328,10 +330,41 @@ __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restri
                     unsigned acc = exc; int bin = 0;
                     for (; bin < 7; ++bin) { if (acc + cnt[bin] > r) break; acc += cnt[bin]; }
                     rank[q][w] = r - acc;
+                    pop[q][w] = cnt[bin];
                     prefix[q][w] |= (unsigned long long)(8 * c + bin) << shift;
                 }
             }
             __syncthreads();
+            // Few candidates left in every column of the tile: one more pass gathers them (instead of up to six more
+            // histogram passes) and the wanted rank is picked among at most MED_CAP keys.
+            bool few = true;
+            if (tid < 2 * MED_COLS && h0 + (tid & 31) < H) few = pop[tid & 31][tid >> 5] <= (unsigned)MED_CAP;
+            if (tid < 2 * MED_COLS) lcount[tid & 31][tid >> 5] = 0u;
+            if (d < 7 && __syncthreads_and(few)) {
+                if (live) {
+                    const unsigned long long mask2 = ~0ull << shift;
+                    const unsigned long long pf0 = prefix[c][0], pf1 = prefix[c][1];
+                    for (int r = rg; r < m; r += 8) {
+                        const unsigned long long k = (unsigned long long)__double_as_longlong(__ldg(col + (size_t)r * H));
+                        const unsigned long long top = k & mask2;
+                        if (top == pf0) { const unsigned sl = atomicAdd(&lcount[c][0], 1u); if (sl < (unsigned)MED_CAP) list[c][0][sl] = k; }
+                        if (top == pf1) { const unsigned sl = atomicAdd(&lcount[c][1], 1u); if (sl < (unsigned)MED_CAP) list[c][1][sl] = k; }
+                    }
+                }
+                __syncthreads();
+                if (tid < 2 * MED_COLS && h0 + (tid & 31) < H) {
+                    const int q = tid & 31, w = tid >> 5;
+                    const unsigned nl = min(lcount[q][w], (unsigned)MED_CAP), r = rank[q][w];
+                    for (unsigned i = 0; i < nl; ++i) {
+                        const unsigned long long x = list[q][w][i];
+                        unsigned less = 0;
+                        for (unsigned j2 = 0; j2 < nl; ++j2) { const unsigned long long y = list[q][w][j2]; less += (y < x || (y == x && j2 < i)) ? 1u : 0u; }
+                        if (less == r) { prefix[q][w] = x; break; }
+                    }
+                }
+                __syncthreads();
+                break;
+            }
         }
         if (tid < MED_COLS && h0 + tid < H) {
             const int h = h0 + tid;
