@@ -160,14 +160,14 @@ __global__ void __launch_bounds__(GRID_THREADS) ekf_grid_kernel(const double* __
     uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + 2 * GRID_TILE * GRID_REC);
     double* cs = reinterpret_cast<double*>(mbar + 2);                   // candidates [m,3]
     const int m = (int)hdr[3];
-    const int h = blockIdx.x * GRID_THREADS + threadIdx.x;
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;               // blockDim.x <= GRID_THREADS (see launch_grid_t)
     const bool live = h < H;
     if ((status[0] & GRID_FATAL) || (int)hdr[4] != m) {                  // prerequisites failed / candidate set too large
         if (live) { stats[4 * (size_t)h] = stats[4 * (size_t)h + 1] = stats[4 * (size_t)h + 2] = nan(""); stats[4 * (size_t)h + 3] = 0.0; }
         return;
     }
     if (threadIdx.x == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); fence_mbar_init(); }
-    for (int k = threadIdx.x; k < 3 * m; k += GRID_THREADS) cs[k] = cand[k];
+    for (int k = threadIdx.x; k < 3 * m; k += blockDim.x) cs[k] = cand[k];
     __syncthreads();
     const int ntiles = (n + GRID_TILE - 1) / GRID_TILE;
     auto issue = [&](int tl) {
@@ -375,12 +375,23 @@ __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restri
     }
 }
 
+// One block per SM (the candidate set fills most of the shared memory): the block size is chosen so that the grid
+// is a whole number of waves -- 262 144 hypotheses on 148 SMs run as 2 x 148 blocks of 896 threads instead of 256
+// blocks of 1024 (1.73 waves that cost 2).
 template <int THREADS>
 static cudaError_t launch_grid_t(const double* rec, const double* cand, const double* hdr, int n, const FuseParams* params, int H,
-                                 double* err, double* stats, const int* st, size_t smem, cudaStream_t stream) {
+                                 double* err, double* stats, const int* st, size_t smem, int num_sms, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(ekf_grid_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    ekf_grid_kernel<THREADS><<<(H + THREADS - 1) / THREADS, THREADS, smem, stream>>>(rec, cand, hdr, n, params, H, err, stats, st);
+    int threads = THREADS;
+    if (num_sms > 0) {
+        const long long waves = ((long long)H + (long long)num_sms * THREADS - 1) / ((long long)num_sms * THREADS);
+        const long long per_block = ((long long)H + waves * num_sms - 1) / (waves * num_sms);
+        threads = (int)((per_block + 31) / 32 * 32);
+        if (threads > THREADS) threads = THREADS;
+        if (threads < 32) threads = 32;
+    }
+    ekf_grid_kernel<THREADS><<<(H + threads - 1) / threads, threads, smem, stream>>>(rec, cand, hdr, n, params, H, err, stats, st);
     return cudaGetLastError();
 }
 static int pow2_at_least(long long n) { int p = 1; while (p < n) p <<= 1; return p; }
@@ -413,9 +424,9 @@ cudaError_t launch_hypothesis_grid(const double* ts, const double* pos, const do
     e = cudaFuncSetAttribute(grid_prep_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
     if (e != cudaSuccess) return e;
     grid_prep_records_kernel<<<1, 1024, smem_prep, stream>>>(ts, pos, quat, z, (int)n, params, R, t, s, rec, cand, hdr, st, cap2);
-    if (H >= num_sms * 1024) e = launch_grid_t<1024>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, stream);
-    else if (H >= num_sms * 512) e = launch_grid_t<512>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, stream);
-    else e = launch_grid_t<256>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, stream);
+    if (H >= num_sms * 1024) e = launch_grid_t<1024>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, num_sms, stream);
+    else if (H >= num_sms * 512) e = launch_grid_t<512>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, num_sms, stream);
+    else e = launch_grid_t<256>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, num_sms, stream);
     if (e != cudaSuccess) return e;
     const int ntiles = (H + MED_COLS - 1) / MED_COLS;
     const int mg = ntiles < num_sms * 3 ? ntiles : num_sms * 3;           // 66 KB of histograms per block: three blocks per SM
