@@ -912,7 +912,8 @@ static int fast_variant(int cap) {
     if (cap <= 32 * 9) return 3209;
     if (cap <= 64 * 9) return 6409;
     if (cap <= 64 * 17) return 6417;                 // two compute warps x 17 poses per thread: 1 % faster than 96 x 11 at 1000 poses
-    if (cap <= 128 * 9) return 12809;
+    // longer trajectories: general kernel (128 x 9 needs three 192-thread blocks per SM = 112 registers per thread and
+    // measured no faster than the general kernel; it stays reachable through GSF_FAST_CT=128 for experiments)
     return 0;
 }
 static int variant_ct(int v) { return v / 100; }
