@@ -69,7 +69,14 @@ int gsf_device_sm_count(void);
  *      init_pos/init_quat: NULL, or [B,3]/[B,4] to skip the Sim3 stage and start the filter
  *      from a given pose (the stand-alone apply_ekf_correction contract).
  *      sim3_out [B,16]: R(9, row-major) t(3) s n_selected n_valid n_residual_violators; may be NULL.
- *      max_len: largest trajectory length in the batch (sizes the shared-memory staging). */
+ *      max_len: largest trajectory length in the batch (sizes the shared-memory staging).
+ *      Dispatch (invisible to the caller, same results to rounding): batches with max_len <= 1088 and no
+ *      init_pos first run the warp-specialised kernel (csrc/gsf_fast.cu); trajectories it does not handle --
+ *      a pose without GNSS (outage / RTS :875-928), a GNSS time gap, a time step <= 1e-6 s (the clamp of :863),
+ *      a trajectory longer than the Sim3 window, fewer than min_samples points, a zero quaternion, a
+ *      measurement-to-process noise ratio outside the range of its projective covariance recursion -- are
+ *      processed by the general kernel (csrc/gsf_fused.cu) launched behind it on the same stream.  No host
+ *      synchronisation, no allocation; GSF_FUSE_IMPL=general forces the general kernel for everything. */
 int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,
                          const int64_t* offsets, int32_t B, int64_t max_len,
                          const gsf_fuse_params* params, int32_t params_per_traj,
