@@ -375,22 +375,24 @@ __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restri
     }
 }
 
-// One block per SM (the candidate set fills most of the shared memory): the block size is chosen so that the grid
-// is a whole number of waves -- 262 144 hypotheses on 148 SMs run as 2 x 148 blocks of 896 threads instead of 256
-// blocks of 1024 (1.73 waves that cost 2).
+// One block per SM (the candidate set fills most of the shared memory) and a block takes about the same time whatever
+// its size (the per-hypothesis recursion is latency-bound): use the fewest waves that blocks of <= 1024 threads allow
+// and size the blocks so that the waves are full -- 262 144 hypotheses on 148 SMs run as 2 x 148 blocks of 896
+// threads (not 256 blocks of 1024: 1.73 waves that cost 2), 131 072 as one wave of 148 x 896.
+static int grid_block_threads(int H, int num_sms) {
+    if (num_sms <= 0) return 256;
+    const long long waves = ((long long)H + (long long)num_sms * 1024 - 1) / ((long long)num_sms * 1024);
+    const long long per_block = ((long long)H + waves * num_sms - 1) / (waves * num_sms);
+    long long threads = (per_block + 31) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    if (threads < 32) threads = 32;
+    return (int)threads;
+}
 template <int THREADS>
 static cudaError_t launch_grid_t(const double* rec, const double* cand, const double* hdr, int n, const FuseParams* params, int H,
-                                 double* err, double* stats, const int* st, size_t smem, int num_sms, cudaStream_t stream) {
+                                 double* err, double* stats, const int* st, size_t smem, int threads, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(ekf_grid_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int threads = THREADS;
-    if (num_sms > 0) {
-        const long long waves = ((long long)H + (long long)num_sms * THREADS - 1) / ((long long)num_sms * THREADS);
-        const long long per_block = ((long long)H + waves * num_sms - 1) / (waves * num_sms);
-        threads = (int)((per_block + 31) / 32 * 32);
-        if (threads > THREADS) threads = THREADS;
-        if (threads < 32) threads = 32;
-    }
     ekf_grid_kernel<THREADS><<<(H + threads - 1) / threads, threads, smem, stream>>>(rec, cand, hdr, n, params, H, err, stats, st);
     return cudaGetLastError();
 }
@@ -424,9 +426,10 @@ cudaError_t launch_hypothesis_grid(const double* ts, const double* pos, const do
     e = cudaFuncSetAttribute(grid_prep_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
     if (e != cudaSuccess) return e;
     grid_prep_records_kernel<<<1, 1024, smem_prep, stream>>>(ts, pos, quat, z, (int)n, params, R, t, s, rec, cand, hdr, st, cap2);
-    if (H >= num_sms * 1024) e = launch_grid_t<1024>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, num_sms, stream);
-    else if (H >= num_sms * 512) e = launch_grid_t<512>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, num_sms, stream);
-    else e = launch_grid_t<256>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, num_sms, stream);
+    const int gthreads = grid_block_threads(H, num_sms);                   // the template bounds the registers per thread
+    if (gthreads > 512) e = launch_grid_t<1024>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, gthreads, stream);
+    else if (gthreads > 256) e = launch_grid_t<512>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, gthreads, stream);
+    else e = launch_grid_t<256>(rec, cand, hdr, (int)n, params, H, err, stats, st, smem_grid, gthreads, stream);
     if (e != cudaSuccess) return e;
     const int ntiles = (H + MED_COLS - 1) / MED_COLS;
     const int mg = ntiles < num_sms * 3 ? ntiles : num_sms * 3;           // 66 KB of histograms per block: three blocks per SM
