@@ -402,11 +402,9 @@ def apply_ekf_correction(slam_data_in, gps_data_in, sim3_pos_initial, sim3_quat_
     args = (_dev(ts), _dev(slam_data_in["positions"]), _dev(slam_data_in["quaternions"]), _dev(z), _one(n))
     prm = fusion.params_tensor(global_config)
     ip, iq = _dev(sim3_pos_initial[:1]), _dev(sim3_quat_initial[:1])
-    p, q, _, st = fusion.fuse_batched(*args, n, prm, init_pos=ip, init_quat=iq)
-    code = int(st.cpu()[0])
-    if code & (_lib.ST_BAD_QUATERNION | _lib.ST_TOO_LONG):
-        # general path: zero-norm quaternions (zero-motion fallback, :84-86) or a trajectory
-        # longer than the shared-memory staging buffer
+    p, q, _, st = fusion.fuse_batched(*args, n, prm, init_pos=ip, init_quat=iq)      # any length (tiled kernel beyond ~4000 poses)
+    if int(st.cpu()[0]) & _lib.ST_BAD_QUATERNION:
+        # zero-norm SLAM quaternions: the literal recursion keeps the reference's zero-motion fallback (:84-86)
         p, q, st = fusion.ekf_strict_batched(*args, prm, ip, iq)
     return p.cpu().numpy(), q.cpu().numpy()
 
@@ -429,6 +427,8 @@ def evaluate_errors(traj_xyz, aligned, slam_timestamps, skip_seconds: float = EV
     n = len(slam_timestamps)
     stats = fusion.ate_nn_batched(_dev(traj_xyz), _dev(aligned), _dev(slam_timestamps), _one(n), n, skip_seconds)
     m, med, rmse, cnt = stats[0].cpu().numpy()
+    if cnt < 0:
+        raise _lib.GsfError(f"evaluate_errors: evaluation set of {int(-cnt)} points exceeds the kernel's staging capacity")
     return float(m), float(med), float(rmse), int(cnt)
 
 

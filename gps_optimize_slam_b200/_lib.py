@@ -33,7 +33,8 @@ SIGNATURES = {
     "gsf_sim3_ransac_work_doubles": (c_int64, [c_int32, c_int64]),
     "gsf_sim3_ransac_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_double, c_int32] + [c_void_p] * 8),
     "gsf_sim3_apply_dev": (c_int32, [c_void_p] * 6 + [c_int32, c_int64] + [c_void_p] * 4),
-    "gsf_ate_nn_batched_dev": (c_int32, [c_void_p] * 4 + [c_int32, c_int64, c_double, c_void_p, c_void_p]),
+    "gsf_ate_work_doubles": (c_int64, [c_int64, c_int64]),
+    "gsf_ate_nn_batched_dev": (c_int32, [c_void_p] * 4 + [c_int32, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     "gsf_utm_forward_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "gsf_utm_inverse_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "gsf_gnss_rows_to_utm_dev": (c_int32, [c_void_p, c_int64] + [c_void_p] * 5),

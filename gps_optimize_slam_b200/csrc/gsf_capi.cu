@@ -108,10 +108,15 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
         return fail(GSF_E_INVALID, "gsf_fuse_batched_dev: init_pos and init_quat must be given together");
     if (!aligned16(quat) || !aligned16(out_quat))
         return fail(GSF_E_INVALID, "gsf_fuse_batched_dev: quaternion arrays must be 16-byte aligned");
-    int cap = (int)std::max<int64_t>(max_len, 2);
-    if (gsf::fuse_smem_bytes(cap) > (size_t)d.max_smem)
-        return fail(GSF_E_TOO_LARGE, "gsf_fuse_batched_dev: trajectory too long for shared-memory staging ("
-                                     + std::to_string(max_len) + " poses); use gsf_ekf_strict_batched_dev");
+    // Trajectories that fit the shared-memory staging (about 4000 poses) run on the shared-memory kernels; longer ones
+    // are left to the tiled kernel launched behind them (any length, like the reference: EKFGPSSLAM.py:831-935).
+    int cap = (int)std::max<int64_t>(std::min<int64_t>(max_len, 1 << 20), 2);
+    bool need_long = max_len > cap;
+    if (gsf::fuse_smem_bytes(cap) > (size_t)d.max_smem) {
+        need_long = true;
+        cap = (int)(((size_t)d.max_smem - 3400) / 57) & ~1;
+        while (cap > 2 && gsf::fuse_smem_bytes(cap) > (size_t)d.max_smem) cap -= 2;
+    }
     gsf::FuseArgs a;
     a.ts = ts; a.pos = pos; a.quat = quat; a.z = z;
     a.offsets = reinterpret_cast<const long long*>(offsets);
@@ -139,6 +144,10 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
     }
     e = gsf::launch_fuse(a, pick_threads(cap, d.max_smem), d.sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev");
+    if (need_long) {
+        e = gsf::launch_fuse_long(a, d.sms, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (long-trajectory kernel)");
+    }
     return 0;
 }
 
@@ -276,9 +285,14 @@ int gsf_sim3_apply_dev(const double* pos, const double* quat, const int64_t* off
     return 0;
 }
 
+int64_t gsf_ate_work_doubles(int64_t total_poses, int64_t max_len) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return 0;
+    return max_len > gsf::ate_smem_capacity(d.max_smem) ? 4 * std::max<int64_t>(total_poses, 0) : 0;
+}
 int gsf_ate_nn_batched_dev(const double* traj, const double* cand, const double* ts,
                            const int64_t* offsets, int32_t B, int64_t max_len, double skip,
-                           double* stats, void* stream) {
+                           double* work, double* stats, void* stream) {
     DeviceInfo& d = device_info();
     if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
     if (B == 0) return 0;
@@ -287,10 +301,12 @@ int gsf_ate_nn_batched_dev(const double* traj, const double* cand, const double*
     gsf::AteArgs a;
     a.traj = traj; a.cand = cand; a.ts = ts; a.offsets = reinterpret_cast<const long long*>(offsets);
     a.skip = skip; a.stats = stats; a.B = B;
-    int cap = (int)std::max<int64_t>(max_len, 32);
-    const int cap_max = (int)((d.max_smem - 1024) / 44);
-    if (cap > cap_max) cap = cap_max;
-    a.cap = cap;
+    const bool big = max_len > gsf::ate_smem_capacity(d.max_smem);
+    if (big && !work)
+        return fail(GSF_E_INVALID, "gsf_ate_nn_batched_dev: trajectories of " + std::to_string(max_len) +
+                                   " poses need the workspace of gsf_ate_work_doubles()");
+    a.cap = big ? 0 : (int)std::max<int64_t>(max_len, 32);
+    a.work = big ? work : nullptr;
     cudaError_t e = gsf::launch_ate(a, d.sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gsf_ate_nn_batched_dev");
     return 0;

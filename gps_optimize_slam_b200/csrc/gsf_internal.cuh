@@ -22,6 +22,8 @@ struct FuseArgs {
 };
 size_t fuse_smem_bytes(int cap);
 cudaError_t launch_fuse(const FuseArgs& a, int threads, int num_sms, cudaStream_t stream);
+// Tiled kernel for trajectories longer than a.cap (gsf_long.cu): any length.
+cudaError_t launch_fuse_long(const FuseArgs& a, int num_sms, cudaStream_t stream);
 // Warp-specialised fast kernel (gsf_fast.cu); fast_fuse_supported: an instantiation covers `cap`.
 bool fast_fuse_supported(int cap, int max_smem);
 cudaError_t launch_fuse_fast(const FuseArgs& a, int num_sms, cudaStream_t stream);
@@ -59,8 +61,10 @@ cudaError_t launch_sim3_apply(const double*, const double*, const long long*, co
 struct AteArgs {
     const double* traj; const double* cand; const double* ts; const long long* offsets;
     double skip; double* stats; int B; int cap;
+    double* work;             // NULL: candidates + errors in shared memory (cap evaluation poses); else 4 doubles per pose in global memory
 };
 size_t ate_smem_bytes(int cap);
+int ate_smem_capacity(int max_smem);
 cudaError_t launch_ate(const AteArgs& a, int num_sms, cudaStream_t stream);
 struct SynthArgs {
     double* ts; double* pos; double* quat; double* z;

@@ -4,7 +4,7 @@
 //   K1b associate_spline                            EKFGPSSLAM.py:351-380 (interp1d cubic/linear)
 //   K2  sim3 tile statistics + finalize (Umeyama)   EKFGPSSLAM.py:428-459
 //   K2b sim3_apply                                  EKFGPSSLAM.py:461-467
-//   K4  ate_nn (nearest-neighbour error statistics) EKFGPSSLAM.py:1021-1033
+//   (K4, the nearest-neighbour error statistics of EKFGPSSLAM.py:1021-1033, lives in gsf_ate.cu)
 #include "gsf_common.cuh"
 #include "gsf_internal.cuh"
 
@@ -465,92 +465,6 @@ __global__ void __launch_bounds__(256) sim3_apply_kernel(const double* __restric
     if (bad) atomicOr(status + b, ST_BAD_QUATERNION);
 }
 
-// ============================================================================= K4: nearest-neighbour error statistics
-// error_i = min_j |traj[idx_i] - cand[idx_j]| over the evaluation set idx = {valid & t > t0 + skip}
-// (:1021-1031), then mean / median / RMSE (:1033).  One block per trajectory; the candidate
-// set lives in shared memory; per query an exact scan over all candidates (fp64).
-
-__global__ void __launch_bounds__(256) ate_nn_kernel(const AteArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* cs = reinterpret_cast<double*>(smem_raw);          // cand[cap*3]
-    double* err = cs + 3 * (size_t)A.cap;                      // err[pow2(cap)]
-    int* idx = reinterpret_cast<int*>(err + A.cap * 2);        // idx[cap]
-    __shared__ int count;
-    __shared__ double scratch[2 * 8];
-    for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
-        const long long e0 = A.offsets[b];
-        const int n = (int)(A.offsets[b + 1] - e0);
-        double* o = A.stats + 4 * (size_t)b;
-        __syncthreads();
-        if (threadIdx.x == 0) count = 0;
-        __syncthreads();
-        // ordered compaction of the evaluation set (single pass per 256-wide slab)
-        const double t0 = n > 0 ? A.ts[e0] + A.skip : 0.0;
-        for (int lo = 0; lo < n; lo += 256) {
-            const int i = lo + threadIdx.x;
-            bool keep = false;
-            if (i < n) {
-                const double* c = A.cand + 3 * (e0 + i);
-                keep = !row_has_nan(c[0], c[1], c[2]) && A.ts[e0 + i] > t0;
-            }
-            const unsigned bal = __ballot_sync(GSF_FULL_MASK, keep);
-            __shared__ int wcnt[8];
-            if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = __popc(bal);
-            __syncthreads();
-            int base = count;
-            for (int w = 0; w < (threadIdx.x >> 5); ++w) base += wcnt[w];
-            const int pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
-            if (keep && pos < A.cap) {
-                idx[pos] = i;
-                const double* c = A.cand + 3 * (e0 + i);
-                cs[3 * pos] = c[0]; cs[3 * pos + 1] = c[1]; cs[3 * pos + 2] = c[2];
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; ++w) tot += wcnt[w]; count += tot; }
-            __syncthreads();
-        }
-        const int m = count;
-        if (m == 0 || m > A.cap) {
-            if (threadIdx.x == 0) { o[0] = o[1] = o[2] = nan(""); o[3] = (m > A.cap) ? -(double)m : 0.0; }
-            continue;
-        }
-        double v[2] = {0.0, 0.0};
-        for (int qi = threadIdx.x; qi < m; qi += 256) {
-            const double* p = A.traj + 3 * (e0 + idx[qi]);
-            const double px = p[0], py = p[1], pz = p[2];
-            double best = INFINITY;
-            for (int j = 0; j < m; ++j) {
-                const double dx = px - cs[3 * j], dy = py - cs[3 * j + 1], dz = pz - cs[3 * j + 2];
-                best = fmin(best, dx * dx + dy * dy + dz * dz);
-            }
-            const double e = sqrt(best);
-            err[qi] = e; v[0] += e; v[1] += e * e;
-        }
-        int p2 = 1; while (p2 < m) p2 <<= 1;
-        for (int k = m + threadIdx.x; k < p2; k += 256) err[k] = INFINITY;
-        block_sum<2>(v, scratch);
-        __syncthreads();
-        for (int k = 2; k <= p2; k <<= 1)                      // bitonic sort (ascending)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = threadIdx.x; i < p2; i += 256) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const double a = err[i], c = err[l];
-                        const bool up = (i & k) == 0;
-                        if ((a > c) == up) { err[i] = c; err[l] = a; }
-                    }
-                }
-                __syncthreads();
-            }
-        if (threadIdx.x == 0) {
-            o[0] = v[0] / m;
-            o[1] = (m & 1) ? err[m / 2] : 0.5 * (err[m / 2 - 1] + err[m / 2]);
-            o[2] = sqrt(v[1] / m);
-            o[3] = (double)m;
-        }
-    }
-}
-
 // ----------------------------------------------------------------------------- launchers
 cudaError_t launch_utm(bool inverse, const double* a, const double* b, long long n, const UtmConst& K, double* o1, double* o2,
                        int num_sms, cudaStream_t stream) {
@@ -609,15 +523,4 @@ cudaError_t launch_sim3_apply(const double* pos, const double* quat, const long 
     }
     return cudaGetLastError();
 }
-size_t ate_smem_bytes(int cap) { return (size_t)cap * 24 + (size_t)cap * 16 + (size_t)cap * 4 + 16; }
-cudaError_t launch_ate(const AteArgs& a, int num_sms, cudaStream_t stream) {
-    if (a.B <= 0) return cudaSuccess;
-    size_t smem = ate_smem_bytes(a.cap);
-    cudaError_t e = cudaFuncSetAttribute(ate_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int grid = a.B < num_sms * 4 ? a.B : num_sms * 4;
-    ate_nn_kernel<<<grid, 256, smem, stream>>>(a);
-    return cudaGetLastError();
-}
-
 }  // namespace gsf

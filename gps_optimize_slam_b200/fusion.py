@@ -237,8 +237,10 @@ def ate_nn_batched(traj, cand, ts, offsets, max_len, skip=5.0, stream=None):
     _require_cuda(traj, cand, ts, offsets)
     B = offsets.numel() - 1
     stats = torch.empty((B, 4), dtype=torch.float64, device=traj.device)
+    nwork = lib.gsf_ate_work_doubles(int(ts.numel()), int(max_len))
+    work = torch.empty((nwork,), dtype=torch.float64, device=traj.device) if nwork > 0 else None
     rc = lib.gsf_ate_nn_batched_dev(_ptr(traj), _ptr(cand), _ptr(ts), _ptr(offsets), B, int(max_len), float(skip),
-                                    _ptr(stats), _stream_ptr(stream))
+                                    _ptr(work), _ptr(stats), _stream_ptr(stream))
     _lib.check(rc, "gsf_ate_nn_batched_dev")
     return stats
 

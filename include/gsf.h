@@ -32,7 +32,7 @@ extern "C" {
 #define GSF_E_INVALID   (-1)   /* bad argument (null pointer, misalignment, size) */
 #define GSF_E_CUDA      (-2)   /* CUDA runtime error */
 #define GSF_E_NO_DEVICE (-3)   /* no usable sm_100 device: there is no CPU fallback */
-#define GSF_E_TOO_LARGE (-4)   /* trajectory does not fit the staging buffer */
+#define GSF_E_TOO_LARGE (-4)   /* a size beyond what an entry point supports (see its comment) */
 
 #define GSF_ST_OK               0
 #define GSF_ST_TOO_FEW_POINTS   1   /* (None,None,None) :431 / ValueError :975,:997 */
@@ -69,7 +69,9 @@ int gsf_device_sm_count(void);
  *      init_pos/init_quat: NULL, or [B,3]/[B,4] to skip the Sim3 stage and start the filter
  *      from a given pose (the stand-alone apply_ekf_correction contract).
  *      sim3_out [B,16]: R(9, row-major) t(3) s n_selected n_valid n_residual_violators; may be NULL.
- *      max_len: largest trajectory length in the batch (sizes the shared-memory staging).
+ *      max_len: largest trajectory length in the batch (sizes the shared-memory staging).  Any length is
+ *      accepted: trajectories beyond the shared-memory staging (about 4000 poses) are streamed through
+ *      shared memory in tiles by a third kernel (csrc/gsf_long.cu) behind the other two.
  *      Dispatch (invisible to the caller, same results to rounding): batches with max_len <= 1088 and no
  *      init_pos first run the warp-specialised kernel (csrc/gsf_fast.cu); trajectories it does not handle --
  *      a pose without GNSS (outage / RTS :875-928), a GNSS time gap, a time step <= 1e-6 s (the clamp of :863),
@@ -149,12 +151,15 @@ int gsf_sim3_apply_dev(const double* pos, const double* quat, const int64_t* off
                        double* out_pos, double* out_quat, int32_t* status, void* stream);
 
 /* ---- evaluation (:1021-1033): nearest-neighbour error statistics of `traj` against the
- *      candidate set {cand[i] : cand[i] not NaN and ts[i] > ts[0] + skip}.
- *      stats [B,4]: mean, median, RMSE, count (count < 0: set larger than the shared-memory
- *      capacity, statistics NaN). */
+ *      candidate set {cand[i] : cand[i] not NaN and ts[i] > ts[0] + skip}, exact (bucketed, pruned search
+ *      instead of the reference's full cdist matrix).  stats [B,4]: mean, median, RMSE, count.
+ *      Any trajectory length: up to ~6900 poses the candidates and errors of a trajectory are held in
+ *      shared memory and `work` may be NULL; beyond that `work` must hold gsf_ate_work_doubles(total
+ *      poses of the batch, max_len) doubles (0 when shared memory suffices). */
+int64_t gsf_ate_work_doubles(int64_t total_poses, int64_t max_len);
 int gsf_ate_nn_batched_dev(const double* traj, const double* cand, const double* ts,
                            const int64_t* offsets, int32_t B, int64_t max_len, double skip,
-                           double* stats, void* stream);
+                           double* work, double* stats, void* stream);
 
 /* ---- pyproj Proj("+proj=utm +zone=Z [+south] +ellps=WGS84") forward (:270) / inverse (:295). */
 int gsf_utm_forward_dev(const double* lon, const double* lat, int64_t n, int32_t zone, int32_t south,

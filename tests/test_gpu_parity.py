@@ -621,3 +621,156 @@ def test_dropin_entry_point(gsf, tmp_path):
     from oracle import fusion_oracle as fo
     dpo, dqo = fo.relative_pose(g["slam_pos"][3], g["slam_quat"][3], g["slam_pos"][4], g["slam_quat"][4])
     np.testing.assert_allclose(dp, dpo, atol=1e-12); np.testing.assert_allclose(dq, dqo, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------- long trajectories (no length limit)
+def _nn_errors_chunked(traj, cand):
+    """cdist(...).min(axis=1) of EKFGPSSLAM.py:1030-1031 in row blocks (the full matrix of a 20 000-pose
+    trajectory would need gigabytes)."""
+    from scipy.spatial import distance
+    return np.concatenate([distance.cdist(traj[a:a + 1024], cand, "euclidean").min(axis=1) for a in range(0, len(traj), 1024)])
+
+
+@pytest.mark.parametrize("n,outages", [(4541, ()), (4541, [(2100, 2400), (4000, 4075)]), (20000, ()),
+                                       (20000, [(0, 80), (2250, 2400), (9000, 9700), (19900, 20000)])])
+def test_long_trajectory_through_dropin_matches_oracle(gsf, n, outages):
+    """Trajectories beyond the shared-memory staging (KITTI-00 length and 20 000 poses, with and without GNSS
+    outages that span tile boundaries, start at pose 0 or run to the end) through the drop-in's
+    apply_ekf_correction / evaluate_errors and through gsf_fuse_batched_dev, against the oracle."""
+    import contextlib, io
+    import EKFGPSSLAM as E
+    from gps_optimize_slam_b200 import synth
+    from oracle import fusion_oracle as fo
+    cfg = fo.default_config()
+    tr = synth.make_trajectory(900 + n // 1000 + len(outages), n=n, dt=0.1, speed=10.0, outages=outages)
+    valid_rows = ~np.isnan(tr["gps"]).any(1)
+    slam = {"timestamps": tr["ts"], "positions": tr["pos"], "quaternions": tr["quat"]}
+    gps = {"timestamps": tr["ts"][valid_rows], "positions": tr["gps"][valid_rows]}
+    # oracle: the reference's own order of steps (association -> selection -> Umeyama -> apply -> EKF -> evaluation)
+    aligned, valid = fo.associate(tr["ts"], gps["timestamps"], gps["positions"])
+    assert np.array_equal(valid, valid_rows)
+    sel = fo.sim3_point_selection(tr["ts"], valid)
+    R, t, s = fo.umeyama(tr["pos"][sel], aligned[sel])
+    sp, sq = fo.sim3_apply(tr["pos"], tr["quat"], R, t, s)
+    fp, fq = fo.ekf_fuse(tr["ts"], tr["pos"], tr["quat"], aligned, valid, sp[0], sq[0], cfg)
+    ev = fo.evaluation_indices(tr["ts"], valid)
+    with contextlib.redirect_stdout(io.StringIO()):
+        got_p, got_q = E.apply_ekf_correction(slam, gps, sp, sq, E.CONFIG)
+        m, med, rmse, cnt = E.evaluate_errors(got_p, aligned, tr["ts"])
+    # the evaluation is checked on the same trajectory bits (one ulp of a UTM coordinate is 9.3e-10 m, i.e. 5e-9 of a 0.2 m error)
+    want = fo.error_stats(_nn_errors_chunked(got_p[ev], aligned[ev]))
+    np.testing.assert_allclose(got_p, fp, rtol=0, atol=POS_ATOL)
+    np.testing.assert_allclose(got_q, fq, rtol=0, atol=ROT_ATOL)
+    assert cnt == len(ev)
+    np.testing.assert_allclose([m, med, rmse], want, rtol=1e-10)
+    # the fused entry point (selection + Umeyama inside), alone and in a batch with short trajectories
+    z = np.where(valid[:, None], aligned, np.nan)
+    long_tr = dict(ts=tr["ts"], pos=tr["pos"], quat=tr["quat"], gps=z)
+    short = [synth.make_trajectory(5, n=1000, dt=0.1, speed=10.0, outages=[(300, 420)]), synth.make_trajectory(1, n=271)]
+    batch = [short[0], long_tr, short[1]]
+    ts_d, pos_d, quat_d, z_d, off_d, off, max_len = pack(batch)
+    p, q, sim3, st = gsf.fuse_batched(ts_d, pos_d, quat_d, z_d, off_d, max_len, gsf.params_tensor(cfg))
+    p, q, sim3, st = p.cpu().numpy(), q.cpu().numpy(), sim3.cpu().numpy(), st.cpu().numpy()
+    assert (st == 0).all(), st
+    sl = slice(off[1], off[2])
+    assert int(sim3[1, 13]) == len(sel) and int(sim3[1, 14]) == int(valid.sum())
+    np.testing.assert_allclose(sim3[1, :9].reshape(3, 3), R, atol=ROT_ATOL)
+    np.testing.assert_allclose(sim3[1, 9:12], t, rtol=1e-12, atol=POS_ATOL)
+    assert abs(sim3[1, 12] - s) < 1e-11
+    np.testing.assert_allclose(p[sl], fp, rtol=0, atol=POS_ATOL)
+    np.testing.assert_allclose(q[sl], fq, rtol=0, atol=ROT_ATOL)
+    for b in (0, 2):
+        o = oracle_pipeline(batch[b], cfg)
+        np.testing.assert_allclose(p[off[b]:off[b + 1]], o["pos"], rtol=0, atol=POS_ATOL)
+    # the long-trajectory kernel is deterministic and agrees with the literal one-thread recursion
+    p2, q2, _, _ = gsf.fuse_batched(ts_d, pos_d, quat_d, z_d, off_d, max_len, gsf.params_tensor(cfg))
+    assert np.array_equal(p2.cpu().numpy(), p) and np.array_equal(q2.cpu().numpy(), q)
+    one = dev(np.array([0, n]), torch.int64)
+    ps, qs, _ = gsf.ekf_strict_batched(dev(tr["ts"]), dev(tr["pos"]), dev(tr["quat"]), dev(z), one, gsf.params_tensor(cfg), dev(sp[:1]), dev(sq[:1]))
+    np.testing.assert_allclose(ps.cpu().numpy(), fp, rtol=0, atol=POS_ATOL)
+
+
+def test_long_trajectory_sharp_turn_and_window_fallbacks(gsf):
+    """Long trajectory whose first gap-free run is too short (selection falls back to all valid points), with a sharp
+    turn inside an outage (RTS skipped, blended update) -- the rare branches of :972-998 and :879-928 in the tiled kernel."""
+    from gps_optimize_slam_b200 import synth
+    from oracle import fusion_oracle as fo
+    for steps in (0, 4):
+        cfg = fo.default_config()
+        cfg["rts_decision"]["default_ekf_transition_steps_on_sharp_turn"] = steps
+        tr = synth.make_trajectory(950, n=6000, dt=0.1, speed=10.0, outages=[(3, 80), (2290, 2420), (5000, 5100)], sharp_turn_at=2350)
+        o = oracle_pipeline(tr, cfg)
+        ts_d, pos_d, quat_d, z_d, off_d, off, max_len = pack([tr])
+        p, q, sim3, st = gsf.fuse_batched(ts_d, pos_d, quat_d, z_d, off_d, max_len, gsf.params_tensor(cfg))
+        assert int(st.cpu()[0]) == 0
+        assert int(sim3.cpu()[0, 13]) == len(o["sel"])
+        np.testing.assert_allclose(sim3.cpu().numpy()[0, :9].reshape(3, 3), o["R"], atol=ROT_ATOL)
+        np.testing.assert_allclose(p.cpu().numpy(), o["pos"], rtol=0, atol=POS_ATOL)
+        np.testing.assert_allclose(q.cpu().numpy(), o["quat"], rtol=0, atol=ROT_ATOL)
+
+
+def test_ate_kernel_any_length_and_far_queries(gsf):
+    """The bucketed nearest-neighbour search against brute force: a 20 000-pose loop (candidates from other laps are
+    nearer than the index-matched one), queries far from every candidate (raw SLAM frame vs UTM: no pruning possible),
+    duplicate errors around the median, a track along y (bins along the other axis), NaN rows and a 1-point set."""
+    from oracle import fusion_oracle as fo
+    rng = np.random.default_rng(12)
+    n = 20000
+    lap = 2 * np.pi * np.arange(n) / 5000.0
+    cand = np.stack([455000 + 300 * np.cos(lap), 5431000 + 900 * np.sin(lap), 100 + 0.01 * np.arange(n) % 7], axis=1) + rng.normal(0, 0.3, (n, 3))
+    cand[rng.uniform(size=n) < 0.1] = np.nan
+    ts = np.arange(n) * 0.1
+    traj = np.where(np.isnan(cand), 0.0, cand) + rng.normal(0, 0.5, (n, 3))
+    far = rng.normal(0, 100.0, (n, 3))
+    dup = np.where(np.isnan(cand), 0.0, cand) + np.array([0.25, 0.0, 0.0])
+    one = dev(np.array([0, n]), torch.int64)
+    valid = ~np.isnan(cand).any(1)
+    ev = fo.evaluation_indices(ts, valid)
+    for t_ in (traj, far, dup):
+        got = gsf.ate_nn_batched(dev(t_), dev(cand), dev(ts), one, n, 5.0).cpu().numpy()[0]
+        want = fo.error_stats(_nn_errors_chunked(t_[ev], cand[ev]))
+        assert int(got[3]) == len(ev)
+        np.testing.assert_allclose(got[:3], want, rtol=1e-10)
+    # ragged batch: shared-memory variant, sizes 1 .. 6000, one trajectory without any evaluation point
+    lens = [1, 60, 61, 1000, 6000, 333]
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    c = cand[: off[-1]].copy(); tr2 = traj[: off[-1]].copy()
+    tsb = np.concatenate([np.arange(k) * 0.1 for k in lens])
+    c[off[3]:off[4], :2] = c[off[3]:off[4], 1::-1] * [1e-3, 1.0]          # a track along y with a tiny x extent
+    got = gsf.ate_nn_batched(dev(tr2), dev(c), dev(tsb), dev(off, torch.int64), max(lens), 5.0).cpu().numpy()
+    for b, k in enumerate(lens):
+        sl = slice(off[b], off[b + 1])
+        v = ~np.isnan(c[sl]).any(1)
+        evb = fo.evaluation_indices(tsb[sl], v)
+        assert int(got[b, 3]) == len(evb)
+        if len(evb):
+            np.testing.assert_allclose(got[b, :3], fo.error_stats(_nn_errors_chunked(tr2[sl][evb], c[sl][evb])), rtol=1e-10)
+        else:
+            assert np.isnan(got[b, :3]).all()
+
+
+def test_dropin_main_process_pair_b(gsf, tmp_path):
+    """Shipped pair B (yolotum04.txt + combined_output.txt: zone 32N, 270/271 valid, RTS over [0, 1]) through the
+    drop-in's main_process against the unmodified reference's outputs (tests/golden/pairB.npz)."""
+    import contextlib, io
+    import EKFGPSSLAM as E
+    g = load_golden("pairB")
+    slam_file, gps_file = tmp_path / "slam.txt", tmp_path / "gnss.txt"
+    np.savetxt(slam_file, np.column_stack((g["slam_ts"], g["slam_pos"], g["slam_quat"])), fmt="%.18e")
+    np.savetxt(gps_file, g["gnss_raw"], fmt="%.18e")
+    E.CONFIG["gps_filtering_ransac"]["enabled"] = False          # sklearn filter: unseeded in the reference, removes nothing here
+    np.random.seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = E.main_process(str(slam_file), str(gps_file))
+    assert out["utm_zone"] == str(g["utm_zone"]) == "32N"
+    assert int(out["valid"].sum()) == int(g["valid"].sum()) == 270
+    np.testing.assert_allclose(out["R"], g["R"], rtol=0, atol=ROT_ATOL)
+    assert abs(out["s"] - float(g["s"])) < 1e-11
+    np.testing.assert_allclose(out["sim3_pos"], g["sim3_pos"], rtol=0, atol=POS_ATOL)
+    np.testing.assert_allclose(out["ekf_pos"], g["ekf_pos"], rtol=0, atol=POS_ATOL)
+    np.testing.assert_allclose(out["ekf_quat"], g["ekf_quat"], rtol=0, atol=ROT_ATOL)
+    for k, label in enumerate(("raw SLAM", "Sim3 aligned", "EKF fused")):
+        m, med, rmse, cnt = out["stats"][("primary GPS", label)]
+        # errors are differences of UTM-scale coordinates computed from trajectories that agree to POS_ATOL: same absolute budget
+        np.testing.assert_allclose([m, med, rmse], g["stats"][k], rtol=0, atol=POS_ATOL)
+        assert cnt == len(g["eval_indices"])
