@@ -7,7 +7,7 @@ import os
 from ctypes import c_char_p, c_double, c_int32, c_int64, c_uint64, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libgsf.so")
+LIB_PATH = os.environ.get("GSF_LIB") or os.path.join(PKG_DIR, "libgsf.so")     # GSF_LIB: tuning hook (A/B builds)
 
 GSF_E_INVALID, GSF_E_CUDA, GSF_E_NO_DEVICE, GSF_E_TOO_LARGE = -1, -2, -3, -4
 ST_OK, ST_TOO_FEW_POINTS, ST_DEGENERATE, ST_BAD_QUATERNION = 0, 1, 2, 4

@@ -11,7 +11,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libgsf.so")
+LIB_PATH = os.environ.get("GSF_LIB_OUT") or os.path.join(PKG_DIR, "libgsf.so")   # GSF_LIB_OUT: A/B builds (with GSF_NVCC_EXTRA)
 SOURCES = ["gsf_fused.cu", "gsf_fast.cu", "gsf_long.cu", "gsf_ate.cu", "gsf_kernels.cu", "gsf_ransac.cu", "gsf_grid.cu", "gsf_ekf_api.cu", "gsf_synth.cu", "gsf_capi.cu"]
 EXTRA = os.environ.get("GSF_NVCC_EXTRA", "").split()
 PER_FILE = {}                     # per-source extra flags (tuning hook)
@@ -40,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = _nvcc()
     objs = []
-    build_dir = os.path.join(PKG_DIR, "build")
+    build_dir = os.path.join(PKG_DIR, "build", os.path.basename(LIB_PATH).replace(".so", ""))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:

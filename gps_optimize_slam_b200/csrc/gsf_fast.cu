@@ -35,19 +35,29 @@
 
 namespace gsf {
 
+#ifndef GSF_PASSC_UNROLL
+#define GSF_PASSC_UNROLL 1
+#endif
+#ifndef GSF_A_EARLY
+#define GSF_A_EARLY 0               // 0: warp A starts trajectory j+2 when trajectory j releases its slot; 1 / 2: when trajectory j has finished pass B / pass C
+#endif
+#ifndef GSF_QUAT2
+#define GSF_QUAT2 0                 // quaternion pass: poses per thread and iteration - 1
+#endif
 #ifndef GSF_PASS_UNROLL
 #define GSF_PASS_UNROLL 1
 #endif
+constexpr int PASSC_UNROLL = GSF_PASSC_UNROLL;
 constexpr int PASS_UNROLL = GSF_PASS_UNROLL;      // per-pose loops of the compute warps stay rolled: with the roles inlined, one step per
                                     // iteration measured 3 % faster than two and 8 % faster than four (instruction-cache footprint)
 
-#ifndef GSF_QUAT_U
-#define GSF_QUAT_U 6
-#endif
+
 #ifdef GSF_DEBUG_STAMPS                             // tools/phase_timing_fast.py: build with GSF_NVCC_EXTRA=-DGSF_DEBUG_STAMPS
-#define GSF_FSTAMP(k) do { if (pclk && j == 100) pclk[k] = clock64(); } while (0)       // pclk: per-role debug pointer
+#define GSF_FSTAMP(k) do { if (pclk) { const long long t_ = clock64(); pclk[k] += t_ - tlast; tlast = t_; } } while (0)   // pclk: per-role debug pointer; cycles since the role's previous stamp, accumulated over the block's trajectories
+#define GSF_FSTAMP_DECL long long tlast = clock64(); (void)tlast
 #else
 #define GSF_FSTAMP(k) do { } while (0)
+#define GSF_FSTAMP_DECL do { } while (0)
 #endif
 
 // ----------------------------------------------------------------------------- Moebius maps, NAX axes
@@ -125,7 +135,7 @@ constexpr int MB_FULL = 0, MB_QUAT = 1, MB_QUAT0 = 2, MB_TSB = 7;
 // for).  Barrier ids (two slots each): 1 compute-internal, 2-3 aux_ready, 4-5 / 6-7 aux_free for the sums / scan
 // warp, 8-9 sums_ready.  mbarriers remain for the TMA completions only (MB_FULL, MB_TSB; polled by one lane with
 // nanosleep back-off).
-constexpr int NB_AUXRDY = 2, NB_FREE_A = 4, NB_FREE_B = 6, NB_SUMS = 8;
+constexpr int NB_AUXRDY = 2, NB_FREE_A = 4, NB_FREE_B = 6, NB_SUMS = 8, NB_MID = 10;
 
 __host__ __device__ constexpr size_t fast_smem_bytes(int cap, int ct) {
     return (size_t)((cap + 3) & ~1) * 64 + (size_t)(FS_PST + 6 * ct) * 8;
@@ -359,10 +369,11 @@ __device__ __forceinline__ int pass_b12(const double* __restrict__ tsS, double* 
         double u0, u1, u2;
         mat_vec(RC, p0 - pprev0, p1 - pprev1, p2 - pprev2, u0, u1, u2);
         pprev0 = p0; pprev1 = p1; pprev2 = p2;
-        if (thr2 > 0.0) {
+        {   // unconditional (the count is dropped below when the check is off): the loop body stays one basic block, so
+            // that consecutive steps can be interleaved by the instruction scheduler
             y0 = fma(sc, u0, y0); y1 = fma(sc, u1, y1); y2 = fma(sc, u2, y2);
             const double d0 = y0 - z0, d1 = y1 - z1, d2 = y2 - z2;
-            if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+            nviol += (d0 * d0 + d1 * d1 + d2 * d2 < thr2) ? 0 : 1;
         }
         // in-place recursion (no loop-carried copies): a += qa b; ga = g a; b += ga; k = ga / b; om = 1 - k
         double kx, ky, kz, ox, oy, oz;
@@ -394,7 +405,7 @@ __device__ __forceinline__ int pass_b12(const double* __restrict__ tsS, double* 
         aff.b[0] = ox * aff.b[0] + b0; aff.b[1] = oy * aff.b[1] + b1; aff.b[2] = oz * aff.b[2] + b2;
         aff.a[0] *= ox; aff.a[1] *= oy; aff.a[2] *= oz;
     }
-    return nviol;
+    return thr2 > 0.0 ? nviol : 0;
 }
 
 // ====================================================================== compute warps
@@ -412,7 +423,8 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CT / 32;
     long long* const pclk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW)) ? A.phase_clock : nullptr;
-    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
+    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW; (void)pclk;
+    GSF_FSTAMP_DECL;
 
     uint32_t par_full = 0, par_q0 = 0, par_q1 = 0;
 #ifdef GSF_DEBUG_STAMPS
@@ -470,6 +482,7 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
                 __threadfence_block();
             }
             named_sync(1, CT);                           // every thread has read the verdict
+            if (GSF_A_EARLY && CT > 32) named_arrive(NB_MID + slot, CT + 32);
             named_arrive(NB_FREE_A + slot, CT + 32); named_arrive(NB_FREE_B + slot, CT + 32);
             continue;
         }
@@ -525,6 +538,7 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
         TrajRef fref{0, 0, 0};
         if (tid == 0) fref = traj_ref_from(A, fetched);
         GSF_FSTAMP(3);
+        if (GSF_A_EARLY == 1 && CT > 32) named_arrive(NB_MID + slot, CT + 32);     // warp A may start on trajectory j + 2
 
         // ------------------------------------------------------------------ pass C: state recursion
         {
@@ -543,7 +557,7 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
             }
             double x0 = pre.a[0] * bc[13] + pre.b[0], x1 = pre.a[1] * bc[14] + pre.b[1], x2 = pre.a[2] * bc[15] + pre.b[2];
             if (c0 == 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
-#pragma unroll PASS_UNROLL
+#pragma unroll PASSC_UNROLL
             for (int i = s0; i < c1; ++i) {
                 x0 = posS[3 * i] * x0 + zS[3 * i]; x1 = posS[3 * i + 1] * x1 + zS[3 * i + 1]; x2 = posS[3 * i + 2] * x2 + zS[3 * i + 2];
                 zS[3 * i] = x0; zS[3 * i + 1] = x1; zS[3 * i + 2] = x2;
@@ -552,6 +566,7 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
         fence_proxy_async();
         named_sync(1, CT);
         GSF_FSTAMP(4);
+        if (GSF_A_EARLY == 2 && CT > 32) named_arrive(NB_MID + slot, CT + 32);
 
         // ------------------------------------------------------------------ store fused positions; stream the quaternions
         double* gout = A.out_pos + 3 * e0;
@@ -594,22 +609,30 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
             // 2 % slower with the roles inlined: instruction-cache footprint again).  Two phases over the same loop
             // body: warp-rows that lie entirely in part 1, then -- after part 2 has landed -- the rest.
             int i0 = tid - lane;                                // warp-uniform loop variables (the wait below syncs the warp)
-            int stop = min(n, nq1);                             // nq1 is a multiple of 32
+            constexpr int QS = (GSF_QUAT2 + 1) * CT;            // poses per block and iteration
+            int stop = min(n, nq1) - (QS - CT);                 // nq1 is a multiple of 32: phase 0 takes the iterations whose rows all lie in part 1
 #pragma unroll 1
             for (int phase = 0; phase < 2; ++phase) {
 #pragma unroll 1
-                for (; i0 < stop; i0 += CT) {
-                    const int i = i0 + lane;
-                    const bool va = i < n;
-                    const int ia = va ? i : 0;                  // the tail re-reads a landed pose and stores nothing
-                    const double2 lo0 = q2[2 * ia], hi0 = q2[2 * ia + 1];
-                    const Quat qa{lo0.x, lo0.y, hi0.x, hi0.y};
-                    const double na = qnorm2(qa);
-                    if (na == 0.0) bad = 1;                     // scipy raises here (:466); output row becomes NaN
-                    const Quat ra = qscale(qmul(C, qa), fast_rsqrt(na));
-                    if (va) {
-                        stg2_hint(qout + 2 * i, make_double2(ra.x, ra.y), pf);
-                        stg2_hint(qout + 2 * i + 1, make_double2(ra.z, ra.w), pf);
+                for (; i0 < stop; i0 += QS) {
+                    Quat rr[GSF_QUAT2 + 1];
+#pragma unroll
+                    for (int u = 0; u <= GSF_QUAT2; ++u) {
+                        const int i = i0 + u * CT + lane;
+                        const int ia = i < n ? i : 0;           // the tail re-reads a landed pose and stores nothing
+                        const double2 lo0 = q2[2 * ia], hi0 = q2[2 * ia + 1];
+                        const Quat qa{lo0.x, lo0.y, hi0.x, hi0.y};
+                        const double na = qnorm2(qa);
+                        if (na == 0.0) bad = 1;                 // scipy raises here (:466); output row becomes NaN
+                        rr[u] = qscale(qmul(C, qa), fast_rsqrt(na));
+                    }
+#pragma unroll
+                    for (int u = 0; u <= GSF_QUAT2; ++u) {
+                        const int i = i0 + u * CT + lane;
+                        if (i < n) {
+                            stg2_hint(qout + 2 * i, make_double2(rr[u].x, rr[u].y), pf);
+                            stg2_hint(qout + 2 * i + 1, make_double2(rr[u].z, rr[u].w), pf);
+                        }
                     }
                 }
                 if (phase == 0 && n > nq1) { mbar_wait_polite(mbar + MB_QUAT, par_q1); par_q1 ^= 1; }
@@ -653,7 +676,8 @@ __device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CT / 32;
     long long* const pclk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW)) ? A.phase_clock : nullptr;
-    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
+    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW; (void)pclk;
+    GSF_FSTAMP_DECL;
 
     // ====================================================================== warp A: Umeyama sums, one to two trajectories ahead
     const TrajRef* const ring = reinterpret_cast<const TrajRef*>(sd + FS_RING);
@@ -665,7 +689,9 @@ __device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
         // slot is only needed for the hand-over below -- which measured 5 % faster at 271 poses; at 1000 poses the
         // extra trajectory of look-ahead falls out of L2 (DRAM reads 5.9 -> 8.3 GB per 65536 trajectories, 3 % slower).
         constexpr bool AHEAD = CT <= 32;
-        if (!AHEAD && k > 0) named_sync(NB_FREE_A + slot, CT + 32);     // also publishes the queue entry of this trajectory
+        constexpr bool EARLY = !AHEAD && GSF_A_EARLY != 0;   // start when trajectory j - 2 is past pass B / C; the slot itself is only needed for the hand-over
+        if (EARLY) { if (k > 0) named_sync(NB_MID + slot, CT + 32); }
+        else if (!AHEAD && k > 0) named_sync(NB_FREE_A + slot, CT + 32);     // also publishes the queue entry of this trajectory
         const TrajRef ref = ring[j & 3];
         if (ref.b >= A.B) break;
         const long long e0 = ref.e0;
@@ -725,7 +751,7 @@ __device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
         double* sums = sd + FS_SUMS + 24 * slot;
         // (AHEAD) the slot is only needed now; this wait also publishes the queue entries up to trajectory j + 2,
         // read at the top of the next iterations
-        if (AHEAD && k > 0) named_sync(NB_FREE_A + slot, CT + 32);
+        if ((AHEAD || EARLY) && k > 0) named_sync(NB_FREE_A + slot, CT + 32);
         if (!(lane & 1)) sums[butterfly16_index(lane)] = total;
         if (lane == 1) { sums[16] = ps0; sums[17] = ps1; sums[18] = ps2; sums[19] = pz0; sums[20] = pz1; sums[21] = pz2; }
         __threadfence_block();
@@ -748,7 +774,8 @@ __device__ __forceinline__ void fast_scan_svd_role(const FuseArgs& A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CT / 32;
     long long* const pclk = (A.phase_clock && blockIdx.x == 0 && lane == 0 && (tid == 0 || warp >= NW)) ? A.phase_clock : nullptr;
-    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW;
+    (void)ts_s; (void)pos_s; (void)z_s; (void)iscr; (void)warp; (void)NW; (void)pclk;
+    GSF_FSTAMP_DECL;
 
     // ====================================================================== warp B: covariance start values, gap/window check, Umeyama finish
     double* tsb = sd + FS_PST + 6 * CT;
@@ -883,7 +910,8 @@ cudaError_t defer_counter(int** out) {
 
 template <int CT, int LCH>
 static cudaError_t launch_fast_t(const FuseArgs& a, int num_sms, cudaStream_t stream) {
-    const size_t smem = fast_smem_bytes(a.cap, CT);
+    size_t smem = fast_smem_bytes(a.cap, CT);
+    if (const char* pad = getenv("GSF_FAST_PAD_SMEM")) smem += (size_t)atoi(pad);      // tuning hook: fewer blocks per SM
     auto kern = fuse_fast_kernel<CT, LCH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -13,12 +13,12 @@ for _ in range(3):
     fusion.fuse_batched(ts, pos, quat, z, off, n, prm)
 torch.cuda.synchronize()
 c = buf.cpu().tolist()
-base = min(x for x in c if x > 0)
-def rel(k): return c[k] - base
-print("compute (traj j=3): start %d | load landed +%d | aux ready +%d | passB+scan +%d | passC +%d | quats +%d | end +%d  (period end-start %d)" % (
-    rel(0), c[1]-c[0], c[2]-c[1], c[3]-c[2], c[4]-c[3], c[5]-c[4], c[6]-c[5], c[6]-c[0]))
-print("warp A  (traj j=3): start %d | wait free +%d | stream sums +%d | butterfly+publish +%d" % (rel(16), c[17]-c[16], c[18]-c[17], c[19]-c[18]))
-print("warp B  (traj j=3): start %d | wait free +%d | cov scan +%d | wait sums +%d | SVD+publish +%d" % (rel(24), c[25]-c[24], c[26]-c[25], c[27]-c[26], c[28]-c[27]))
-print("warp B scan detail: ts wait %d | step loops %d | warp scan %d | eval+publish %d" % (c[31]-c[25], c[29]-c[31], c[30]-c[29], c[26]-c[30]))
+nt = max(1, c[65]) * 3          # trajectories of block 0 over the three calls
+a = lambda k: c[k] / nt
+print("block 0, averages over %d trajectories (cycles)" % nt)
+print("compute: queue %.0f | load wait %.0f | aux wait %.0f | passB+scan %.0f | passC %.0f | quats %.0f | end %.0f | period %.0f" % (
+    a(0), a(1), a(2), a(3), a(4), a(5), a(6), sum(a(k) for k in range(7))))
+print("warp A : top %.0f | wait start %.0f | stream sums %.0f | butterfly+wait slot+publish %.0f | period %.0f" % (a(16), a(17), a(18), a(19), sum(a(k) for k in range(16, 20))))
+print("warp B : top %.0f | wait free %.0f | cov scan %.0f | wait sums %.0f | SVD+publish %.0f | period %.0f" % (a(24), a(25), a(26), a(27), a(28), sum(a(k) for k in range(24, 29))))
 print('per-block totals (block, sm, trajectories, cycles/trajectory):', [(37*k, c[64+4*k+2], c[64+4*k+1], c[64+4*k]//max(1,c[64+4*k+1])) for k in range(12)])
 lib.gsf_debug_phase_clock(None)
