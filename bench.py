@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + ["config4", "config5"])
     ap.add_argument("--poses", type=int, default=0, help="config4 / config5: override the trajectory length")
     ap.add_argument("--grid-k", type=int, default=64, help="config5: hypotheses = k^3")
+    ap.add_argument("--grid-impl", default="factored", choices=["factored", "general"],
+                    help="config5: product-grid entry (scalar tracks + combine kernel) or the per-hypothesis kernel")
     ap.add_argument("--trajectories", type=int, default=0, help="override the total trajectory count (debug)")
     ap.add_argument("--e2e-trajectories", type=int, default=0, help="host-buffer sample per rank (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

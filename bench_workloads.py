@@ -23,100 +23,143 @@ def _events(torch, k):
     return [torch.cuda.Event(enable_timing=True) for _ in range(k)]
 
 
-def run_config5(args, rank, local_rank, world, ClockSampler, read_peak):
+def measure_config5(args, rank, local_rank, world, ClockSampler, with_cpu=False, with_e2e=True, steps=None, warmup=None):
+    """config 5 on the current process group: returns the record (dict) on every rank."""
     import torch
     import torch.distributed as dist
     from gps_optimize_slam_b200 import fusion, sharding, synth
-    from gps_optimize_slam_b200.config import pack_noise_grid
+    from gps_optimize_slam_b200.config import pack_fuse_params, pack_noise_grid
 
     dev = torch.device("cuda", local_rank)
-    n = args.poses or 4541
-    k = args.grid_k
+    n = getattr(args, "poses", 0) or 4541
+    k = getattr(args, "grid_k", 64)
+    impl = getattr(args, "grid_impl", "factored")
+    steps = steps or args.steps
+    warmup = max(3, warmup or args.warmup)
     H_total = k ** 3
     lo, hi = sharding.shard_range(H_total, rank, world)
+    counts = [sharding.shard_range(H_total, r, world)[1] - sharding.shard_range(H_total, r, world)[0] for r in range(world)]
     tr = synth.make_loop_trajectory(2026, n=n)
     grid = synth.noise_grid(k)
-    blob_h = torch.from_numpy(pack_noise_grid(grid[lo:hi])).pin_memory()
+    axes_h = [torch.from_numpy(a).pin_memory() for a in (np.logspace(-3, 1, k), np.logspace(-3, 1, k), np.logspace(-2, 1, k))]
     host = [torch.from_numpy(np.ascontiguousarray(tr[key])).pin_memory() for key in ("ts", "pos", "quat", "gps")]
     ts, pos, quat, z = [h.to(dev) for h in host]
-    blob = blob_h.to(dev)
     H = hi - lo
+    if impl == "factored":
+        base_h = torch.from_numpy(pack_fuse_params()).pin_memory()
+        base = base_h.to(dev)
+        qxy, qz, rr = [a.to(dev) for a in axes_h]
+        need = fusion._lib.load().gsf_noise_grid_work_doubles(n, k, k, k, lo, H)
+        work = torch.empty((need,), dtype=torch.float64, device=dev)
+        stats_buf = torch.empty((H, 4), dtype=torch.float64, device=dev)
 
-    def step():
-        return fusion.hypothesis_grid(ts, pos, quat, z, blob)
+        def step():
+            return fusion.noise_grid(ts, pos, quat, z, base, qxy, qz, rr, h_first=lo, h_count=H, work=work, stats=stats_buf)
+        launches = 6
+    else:
+        blob_h = torch.from_numpy(pack_noise_grid(grid[lo:hi])).pin_memory()
+        blob = blob_h.to(dev)
+
+        def step():
+            return fusion.hypothesis_grid(ts, pos, quat, z, blob)
+        launches = 6
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         stats, sim3, st = step()
+        table = sharding.gather_stats(stats, total_rows=H_total if world > 1 else None, counts=counts)      # warms NCCL too
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = _events(torch, args.steps + 1)
+    ev = _events(torch, 2 * steps + 1)
     ev[0].record()
-    for i in range(args.steps):
+    for i in range(steps):
         stats, sim3, st = step()
-        ev[i + 1].record()
+        ev[2 * i + 1].record()
+        # the collective of the path: [H/G, 4] statistics from every rank (one NCCL all_gather over NVLink), inside the timed step
+        table = sharding.gather_stats(stats, total_rows=H_total if world > 1 else None, counts=counts)
+        ev[2 * i + 2].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms = sharding.max_over_ranks(ev[0].elapsed_time(ev[-1]), dev) / args.steps
+    ms = sharding.max_over_ranks(ev[0].elapsed_time(ev[-1]), dev) / steps
+    kernel_ms = sharding.max_over_ranks(sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)), dev) / steps
+    gather_ms = sharding.max_over_ranks(sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)), dev) / steps
     value = H_total * (n - 1) / (ms * 1e-3)
-
-    # the collective: gather [H/G, 4] statistics from every rank (NCCL all_gather over NVLink)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    table = sharding.gather_stats(stats, total_rows=H_total if world > 1 else None)
-    torch.cuda.synchronize(dev)
-    gather_s = time.perf_counter() - t0
     best = int(torch.argmin(table[:, 2]).item())
+    m_eval = float(table[0, 3].item())
 
-    # end to end: trajectory + parameter records from pinned host memory, statistics back to the host
-    def e2e_step():
-        d = [h.to(dev, non_blocking=True) for h in host]
-        b = blob_h.to(dev, non_blocking=True)
-        s_, _, _ = fusion.hypothesis_grid(d[0], d[1], d[2], d[3], b)
-        return s_.cpu()
+    e2e = None
+    if with_e2e:
+        # end to end: trajectory + grid axes from pinned host memory, statistics back to the host
+        def e2e_step():
+            d = [h.to(dev, non_blocking=True) for h in host]
+            if impl == "factored":
+                ax = [a.to(dev, non_blocking=True) for a in axes_h]
+                s_, _, _ = fusion.noise_grid(d[0], d[1], d[2], d[3], base_h.to(dev, non_blocking=True), ax[0], ax[1], ax[2],
+                                             h_first=lo, h_count=H, work=work, stats=stats_buf)
+            else:
+                s_, _, _ = fusion.hypothesis_grid(d[0], d[1], d[2], d[3], blob_h.to(dev, non_blocking=True))
+            return s_.cpu()
 
-    e2e_step(); barrier()
-    t0 = time.perf_counter()
-    e_steps = max(2, min(args.steps, 3))
-    for _ in range(e_steps):
-        e2e_step()
-    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev) / e_steps
-    e2e = {"value": H_total * (n - 1) / e2e_s, "unit": "pose-updates/s",
-           "h2d_bytes_per_step": int(n * 88 + H * 184), "d2h_bytes_per_step": int(H * 32),
-           "sample": f"{H} hypotheses x {n} poses per rank per step, pinned host buffers, {e_steps} steps"}
+        e2e_step(); barrier()
+        t0 = time.perf_counter()
+        e_steps = max(2, min(steps, 3))
+        for _ in range(e_steps):
+            e2e_step()
+        e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev) / e_steps
+        h2d = int(n * 88 + (184 + 3 * k * 8 if impl == "factored" else H * 184))
+        e2e = {"value": H_total * (n - 1) / e2e_s, "unit": "pose-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(H * 32),
+               "sample": f"{H} hypotheses x {n} poses per rank per step, pinned host buffers, {e_steps} steps"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if with_cpu and rank == 0 and world == 1:
         cpu = cpu_baseline_config5(tr, grid, os.cpu_count() or 1)
 
-    # FP64 accounting: per pose-update 3 axes x (predict 2, gain 1 div + 1, update 4, Joseph 7) = 45 flops,
-    # per evaluated pose the own-measurement distance (8) + sqrt; neighbours visited by the pruned search add
-    # ~8 flops each (data dependent, not counted): a lower bound on the executed fp64 work.
-    flops = H * (n - 1) * 45.0 + H * float(table[0, 3].item()) * 9.0
+    # FP64 accounting (a lower bound on the executed work).  Per-hypothesis kernel: per pose-update 3 axes x (predict 2, gain
+    # 1 div + 1, update 4, Joseph 7) = 45 flops + per evaluated pose the own-measurement distance and the square root (9).
+    # Factored: the 45-flop updates run once per scalar track (2 Kq Kr + Kz Kr tracks x (n - 1) x 15), the evaluation once per
+    # hypothesis and pose; neighbours visited by the pruned search add ~8 flops each (data dependent, not counted).
+    if impl == "factored":
+        flops = (3.0 * k * k) * (n - 1) * 15.0 + H * m_eval * 9.0
+    else:
+        flops = H * (n - 1) * 45.0 + H * m_eval * 9.0
     peak_tf = 148 * 64 * 2 * 1.965e9 / 1e12
-    roofline = {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": flops / (ms * 1e-3) / 1e12 / peak_tf, "traffic": None,
-                "peak_source": "nominal: 148 SMs x 64 FP64 FMA/clk x 1.965 GHz (the path is FP64-pipe bound, not HBM / tensor)",
-                "kernel": "ekf_grid_kernel (+ prep kernels, grid_median_kernel)", "launch_ms": ms,
-                "algorithmic_flops_per_launch": flops}
+    peak_src = "nominal: 148 SMs x 64 FP64 FMA/clk x 1.965 GHz"
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "fp64_peak.json")) as f:
+            pk = json.load(f)
+        peak_tf, peak_src = float(pk["dfma_tflops"]), pk["source"]
+    except Exception:
+        pass
+    roofline = {"bound": "fp64", "achieved": flops / (kernel_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": flops / (kernel_ms * 1e-3) / 1e12 / peak_tf, "traffic": None, "peak_source": peak_src,
+                "kernel": ("grid_combine_kernel (+ prep kernels, grid_tracks_kernel)" if impl == "factored"
+                           else "ekf_grid_kernel (+ prep kernels, grid_median_kernel)"),
+                "launch_ms": kernel_ms, "algorithmic_flops_per_launch": flops,
+                "note": "useful-work lower bound: the factored path removes 63/64 of the filter arithmetic, so its fraction of the FP64 peak says little; ms_per_step is the figure of merit"}
+    return {"metric": "EKF pose-updates/s (noise-grid hypotheses, ATE statistics only)", "value": value, "unit": "pose-updates/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config5: {n}-pose closed-loop trajectory x {H_total} EKF Q/R noise-grid hypotheses ({k}^3)",
+                       "impl": impl, "hypotheses_per_gpu": H,
+                       "parallelism": f"hypothesis-sharded x{world}; all_gather of [H/G,4] ATE statistics inside the timed step",
+                       "l2": "inputs are one 400 KB trajectory (L2 resident by design); the path is FP64 / latency bound",
+                       "gather": "nccl all_gather_into_tensor" if world > 1 else "single rank (no collective)",
+                       "kernel_ms": kernel_ms, "gather_ms": gather_ms, "gather_seconds": gather_ms * 1e-3,
+                       "best_hypothesis": {"index": best, "q_xy": float(grid[best, 0]), "q_z": float(grid[best, 1]), "r": float(grid[best, 2]),
+                                           "rmse_m": float(table[best, 2].item())},
+                       "status": int(st.cpu()[0])},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches * steps}
+
+
+def run_config5(args, rank, local_rank, world, ClockSampler, read_peak):
+    line = measure_config5(args, rank, local_rank, world, ClockSampler, with_cpu=not args.no_cpu_baseline)
     if rank == 0:
-        line = {"metric": "EKF pose-updates/s (noise-grid hypotheses, ATE statistics only)", "value": value, "unit": "pose-updates/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"config5: {n}-pose closed-loop trajectory x {H_total} EKF Q/R noise-grid hypotheses ({k}^3)",
-                           "hypotheses_per_gpu": H, "parallelism": f"hypothesis-sharded x{world}; all_gather of [H/G,4] ATE statistics",
-                           "l2": "inputs are one 400 KB trajectory (L2 resident by design); the path is FP64-bound",
-                           "gather": "nccl all_gather" if world > 1 else "single rank (no collective)", "gather_seconds": gather_s,
-                           "best_hypothesis": {"index": best, "q_xy": float(grid[best, 0]), "q_z": float(grid[best, 1]), "r": float(grid[best, 2]),
-                                               "rmse_m": float(table[best, 2].item())},
-                           "status": int(st.cpu()[0])},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 6 * args.steps}
         print(json.dumps(line), flush=True)
 
 

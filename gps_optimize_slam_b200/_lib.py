@@ -24,6 +24,8 @@ SIGNATURES = {
     "gsf_ekf_strict_batched_dev": (c_int32, [c_void_p] * 5 + [c_int32, c_void_p, c_int32] + [c_void_p] * 6),
     "gsf_hypothesis_grid_work_doubles": (c_int64, [c_int64, c_int32]),
     "gsf_ekf_hypothesis_grid_dev": (c_int32, [c_void_p] * 4 + [c_int64, c_void_p, c_int32] + [c_void_p] * 5),
+    "gsf_noise_grid_work_doubles": (c_int64, [c_int64, c_int32, c_int32, c_int32, c_int64, c_int64]),
+    "gsf_ekf_noise_grid_dev": (c_int32, [c_void_p] * 4 + [c_int64] + [c_void_p] * 4 + [c_int32] * 3 + [c_int64] * 2 + [c_void_p] * 5),
     "gsf_ekf_step_dev": (c_int32, [c_int32] + [c_void_p] * 9 + [c_int32] + [c_void_p] * 6),
     "gsf_rts_segment_dev": (c_int32, [c_void_p] * 5 + [c_int32] + [c_void_p] * 3),
     "gsf_quat_nlerp_dev": (c_int32, [c_void_p] * 3 + [c_int64, c_void_p, c_void_p]),

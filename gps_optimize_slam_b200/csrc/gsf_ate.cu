@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(ATE_T) ate_nn_kernel(const AteArgs A) {
             if (row_has_nan(px, py, pz)) { e = nan(""); S.any_nan = 1; }
             else {
                 double dx = px - cx, dy = py - cy, dz = pz - cz;
-                double best = dx * dx + dy * dy + dz * dz;               // own measurement first
+                double best = dist2_rn(dx, dy, dz);               // own measurement first
                 const double qa = ax ? py : px;
                 int qb = (int)((qa - base) * scale);
                 qb = min(max(qb, 0), ATE_NB - 1);
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(ATE_T) ate_nn_kernel(const AteArgs A) {
                     const int c1 = S.bin[k + 1];
                     for (int c = S.bin[k]; c < c1; ++c) {
                         dx = px - cs[3 * (size_t)c]; dy = py - cs[3 * (size_t)c + 1]; dz = pz - cs[3 * (size_t)c + 2];
-                        best = fmin(best, dx * dx + dy * dy + dz * dz);
+                        best = fmin(best, dist2_rn(dx, dy, dz));
                     }
                 }
                 for (int k = qb + 1; k < ATE_NB; ++k) {
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(ATE_T) ate_nn_kernel(const AteArgs A) {
                     const int c1 = S.bin[k + 1];
                     for (int c = S.bin[k]; c < c1; ++c) {
                         dx = px - cs[3 * (size_t)c]; dy = py - cs[3 * (size_t)c + 1]; dz = pz - cs[3 * (size_t)c + 2];
-                        best = fmin(best, dx * dx + dy * dy + dz * dz);
+                        best = fmin(best, dist2_rn(dx, dy, dz));
                     }
                 }
                 e = sqrt(best);

@@ -169,6 +169,27 @@ int gsf_ekf_hypothesis_grid_dev(const double* ts, const double* pos, const doubl
     return 0;
 }
 
+int64_t gsf_noise_grid_work_doubles(int64_t n, int32_t Kq, int32_t Kz, int32_t Kr, int64_t h_first, int64_t h_count) {
+    if (n < 0 || Kq <= 0 || Kz <= 0 || Kr <= 0 || h_first < 0 || h_count <= 0 || h_first + h_count > (int64_t)Kq * Kz * Kr) return 0;
+    return gsf::noise_grid_work_doubles(n, Kq, Kz, Kr, h_first, h_count);
+}
+int gsf_ekf_noise_grid_dev(const double* ts, const double* pos, const double* quat, const double* z, int64_t n,
+                           const gsf_fuse_params* base, const double* q_xy, const double* q_z, const double* r,
+                           int32_t Kq, int32_t Kz, int32_t Kr, int64_t h_first, int64_t h_count,
+                           double* work, double* stats, double* sim3_out, int32_t* status, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (n < 2 || Kq <= 0 || Kz <= 0 || Kr <= 0 || h_first < 0 || h_count <= 0 || h_first + h_count > (int64_t)Kq * Kz * Kr || !ts || !pos ||
+        !quat || !z || !base || !q_xy || !q_z || !r || !work || !stats || !status)
+        return fail(GSF_E_INVALID, "gsf_ekf_noise_grid_dev: null pointer or bad size");
+    if (!aligned16(work)) return fail(GSF_E_INVALID, "gsf_ekf_noise_grid_dev: work must be 16-byte aligned");
+    cudaError_t e = gsf::launch_noise_grid(ts, pos, quat, z, n, reinterpret_cast<const gsf::FuseParams*>(base), q_xy, q_z, r, Kq, Kz, Kr,
+                                           h_first, h_count, work, stats, sim3_out, status, d.max_smem, d.sms, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(GSF_E_TOO_LARGE, "gsf_ekf_noise_grid_dev: trajectory too long for the shared-memory candidate set"); }
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_ekf_noise_grid_dev");
+    return 0;
+}
+
 int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,
                                const int64_t* offsets, int32_t B,
                                const gsf_fuse_params* params, int32_t params_per_traj,

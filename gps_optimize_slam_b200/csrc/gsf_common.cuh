@@ -347,6 +347,18 @@ __device__ inline void block_sum(double* v, double* scratch) {
 
 #endif  // __CUDACC__
 
+// Squared Euclidean distance with the rounding sequence of scipy's cdist (EKFGPSSLAM.py:1030): every square and every
+// partial sum rounded on its own, (dx^2 + dy^2) + dz^2, no FMA contraction -- so the value does not depend on which of
+// the products a pruning test has already computed, and the nearest-neighbour kernels agree bit for bit.
+GSF_HD __forceinline__ double dist2_rn(double dx, double dy, double dz) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+#else
+    volatile double a = dx * dx, b = dy * dy, c = dz * dz;
+    volatile double ab = a + b;
+    return ab + c;
+#endif
+}
 GSF_HD __forceinline__ bool row_has_nan(double a, double b, double c) { return isnan(a) || isnan(b) || isnan(c); }
 
 }  // namespace gsf

@@ -17,6 +17,8 @@
 // Restriction (status GSF_ST_GRID_NEEDS_ALL_VALID otherwise): every pose has a GNSS measurement, i.e. no
 // outage / RTS segments (those need per-hypothesis history; use gsf_fuse_batched_dev with per-trajectory
 // parameters for such data).
+#include <cstdio>
+#include <cstdlib>
 #include "gsf_common.cuh"
 #include "gsf_ptx.cuh"
 #include "gsf_internal.cuh"
@@ -206,18 +208,18 @@ __global__ void __launch_bounds__(GRID_THREADS) ekf_grid_kernel(const double* __
             if (rank >= 0) {
                 // exact nearest neighbour: own measurement first, then outwards in x order while the 1-D gap can still win
                 double dx = x0 - cs[3 * rank], dy = x1 - cs[3 * rank + 1], dz = x2 - cs[3 * rank + 2];
-                double best = dx * dx + dy * dy + dz * dz;
+                double best = dist2_rn(dx, dy, dz);
                 for (int c = rank - 1; c >= 0; --c) {
                     dx = x0 - cs[3 * c];
                     if (dx > 0.0 && dx * dx >= best) break;
                     dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
-                    best = fmin(best, dx * dx + dy * dy + dz * dz);
+                    best = fmin(best, dist2_rn(dx, dy, dz));
                 }
                 for (int c = rank + 1; c < m; ++c) {
                     dx = cs[3 * c] - x0;
                     if (dx > 0.0 && dx * dx >= best) break;
                     dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
-                    best = fmin(best, dx * dx + dy * dy + dz * dz);
+                    best = fmin(best, dist2_rn(dx, dy, dz));
                 }
                 const double e = sqrt(best);
                 if (live) err[(size_t)ne * H + h] = e;
@@ -373,6 +375,451 @@ __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restri
             o[1] = (o[0] != o[0]) ? nan("") : ((m & 1) ? a : 0.5 * (a + b));     // a NaN error (NaN mean) -> NaN median, like np.median
         }
     }
+}
+
+// ============================================================================= separable noise grid (config 5 proper)
+// The hypotheses of BASELINE config 5 are a PRODUCT grid (q_xy, q_z, r) with P0 and everything else shared.  P0, Q and R
+// are diagonal (EKFGPSSLAM.py:684-686) and H = [I3 0], so the x / y / z components of the filter are three independent
+// scalar filters: the x and y tracks depend on (q_xy, r) only, the z track on (q_z, r) only.  Kq Kr x/y tracks and
+// Kz Kr z tracks (2 x 64^2 + 64^2 = 12 288 scalar filter runs) replace the 3 x 64^3 = 786 432 the per-hypothesis
+// kernel above executes -- same arithmetic per step, so every track is bit-identical to the corresponding component
+// of ekf_grid_kernel -- and a combine kernel scores every (q_xy, q_z, r) triple against the candidate set.
+//   grid_tracks_kernel   one thread per scalar track, the whole recursion in registers; 32 x 32 tiles are transposed
+//                        through shared memory so that the table [track][pose] is written in 256-byte rows;
+//   grid_combine_kernel  one block per hypothesis at a time (threads over poses -- the tracks make the poses of a
+//                        hypothesis independent, so the evaluation is parallel in time): coalesced reads of the three
+//                        track rows (L2-resident by the loop order), exact pruned nearest neighbour in the x-sorted
+//                        candidate set (shared memory), errors kept in shared memory, mean / RMSE by a fixed-order block
+//                        reduction, median by radix selection in shared memory.  No [poses, hypotheses] error table.
+static int pow2_at_least(long long n);
+constexpr int TRK_THREADS = 128;
+__global__ void __launch_bounds__(TRK_THREADS) grid_tracks_kernel(const double* __restrict__ rec, const double* __restrict__ hdr, int n,
+                                                                  const FuseParams* __restrict__ base, const double* __restrict__ qxy,
+                                                                  const double* __restrict__ qz, const double* __restrict__ rr, int Kr,
+                                                                  int iq0, int nq, int iz0, int nz, double* __restrict__ tracks,
+                                                                  long long npad, const int* __restrict__ status) {
+    __shared__ double tile[TRK_THREADS / 32][32][33];
+    if (status[0] & GRID_FATAL) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nxy = nq * Kr, NT = 2 * nxy + nz * Kr;
+    const int t = blockIdx.x * TRK_THREADS + threadIdx.x;
+    const int tw0 = t - lane;                                            // first track of this warp
+    if (tw0 >= NT) return;
+    const bool live = t < NT;
+    const int tt = live ? t : NT - 1;
+    int axis; double q, r;
+    if (tt < 2 * nxy) { axis = tt / nxy; const int rem = tt - axis * nxy; q = qxy[iq0 + rem / Kr]; r = rr[rem % Kr]; }
+    else { axis = 2; const int rem = tt - 2 * nxy; q = qz[iz0 + rem / Kr]; r = rr[rem % Kr]; }
+    double P = base->p0[axis], x = hdr[axis];
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int cnt = min(32, n - i0);
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const int i = i0 + k;
+            if (i > 0) {
+                const double* rc = rec + (size_t)GRID_REC * i;
+                const double dt = rc[0];
+                const double pp = P + q * dt, kk = pp * rcp_(pp + r), om = 1.0 - kk;     // the step of ekf_grid_kernel, verbatim
+                P = om * pp * om + kk * r * kk; x = om * (x + rc[1 + axis]) + kk * rc[4 + axis];
+            }
+            tile[warp][k][lane] = x;
+        }
+        __syncwarp();
+        if (lane < cnt) {
+            for (int tr = 0; tr < 32 && tw0 + tr < NT; ++tr) tracks[(size_t)(tw0 + tr) * npad + i0 + lane] = tile[warp][lane][tr];
+        }
+        __syncwarp();
+    }
+}
+
+// Candidate order for the combine kernel: own[k] = pose of the k-th candidate (x order), hgap[k] = a quarter of the
+// squared distance from candidate k to its nearest other candidate.  Triangle inequality: a query closer than half that
+// distance to its own measurement cannot have another candidate nearer, so the scan is skipped for it.
+__global__ void __launch_bounds__(256) grid_prep_order_kernel(const double* __restrict__ rec, const double* __restrict__ cand,
+                                                              const double* __restrict__ hdr, int n, int* __restrict__ own,
+                                                              double* __restrict__ hgap, const int* __restrict__ status) {
+    if (status[0] & GRID_FATAL) return;
+    const int m = (int)hdr[3];
+    if ((int)hdr[4] != m) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = (int)rec[(size_t)GRID_REC * i + 7];
+        if (r >= 0) own[r] = i;
+    }
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+        const double x0 = cand[3 * k], x1 = cand[3 * k + 1], x2 = cand[3 * k + 2];
+        double best = INFINITY;
+        for (int c = k - 1; c >= 0; --c) {
+            const double dx = x0 - cand[3 * c];
+            if (dx * dx >= best) break;
+            const double dy = x1 - cand[3 * c + 1], dz = x2 - cand[3 * c + 2];
+            best = fmin(best, dist2_rn(dx, dy, dz));
+        }
+        for (int c = k + 1; c < m; ++c) {
+            const double dx = cand[3 * c] - x0;
+            if (dx * dx >= best) break;
+            const double dy = x1 - cand[3 * c + 1], dz = x2 - cand[3 * c + 2];
+            best = fmin(best, dist2_rn(dx, dy, dz));
+        }
+        hgap[k] = best < INFINITY ? 0.25 * best * (1.0 - 1e-12) : 0.0;        // rounding margin; one candidate only: never skip (harmless)
+    }
+}
+// Second scan order for the combine kernel.  The 1-D pruning of an x-sorted scan degenerates where the track runs along y
+// (all the poses of that stretch share nearly the same x): such candidates are scanned in y order instead.  One block:
+// bitonic sort of the candidates' (y, x-rank) pairs -> yperm[j] = x-rank of the j-th candidate in y order; yrank[k] = position of
+// candidate k in that order if its local track direction (from the measurements 4 poses before / after) is closer to the
+// y axis than to the x axis, 0xFFFF otherwise (scan in x order).
+__global__ void __launch_bounds__(1024) grid_prep_ysort_kernel(const double* __restrict__ cand, const double* __restrict__ z,
+                                                               const double* __restrict__ hdr, int n, const int* __restrict__ own,
+                                                               unsigned short* __restrict__ yperm, unsigned short* __restrict__ yrank,
+                                                               const int* __restrict__ status, int cap_pow2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* key = reinterpret_cast<double*>(smem_raw);
+    int* idx = reinterpret_cast<int*>(key + cap_pow2);
+    if (status[0] & GRID_FATAL) return;
+    const int m = (int)hdr[3];
+    if ((int)hdr[4] != m || m > 65535) return;
+    for (int k = threadIdx.x; k < cap_pow2; k += 1024) { key[k] = k < m ? cand[3 * k + 1] : INFINITY; idx[k] = k < m ? k : 0x7fffffff; }
+    __syncthreads();
+    for (int k = 2; k <= cap_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < cap_pow2; i += 1024) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const double a = key[i], c = key[l];
+                    const int ia = idx[i], ic = idx[l];
+                    const bool up = (i & k) == 0;
+                    const bool gt = a > c || (a == c && ia > ic);
+                    if (gt == up) { key[i] = c; key[l] = a; idx[i] = ic; idx[l] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int j = threadIdx.x; j < m; j += 1024) {
+        const int k = idx[j];
+        yperm[j] = (unsigned short)k;
+        const int i = own[k], ia = max(i - 4, 0), ib = min(i + 4, n - 1);
+        const double dx = fabs(z[3 * ib] - z[3 * ia]), dy = fabs(z[3 * ib + 1] - z[3 * ia + 1]);
+        yrank[k] = dy > dx ? (unsigned short)j : (unsigned short)0xFFFF;
+    }
+}
+// One block per track: the row (time order) is re-ordered in place to candidate (x) order through shared memory, so that
+// the combine kernel reads tracks, candidates and errors with the same index.
+__global__ void __launch_bounds__(256) grid_permute_kernel(double* __restrict__ tracks, long long npad, int n, const int* __restrict__ own,
+                                                           const double* __restrict__ hdr, const int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* row = reinterpret_cast<double*>(smem_raw);
+    if (status[0] & GRID_FATAL) return;
+    const int m = (int)hdr[3];
+    if ((int)hdr[4] != m) return;
+    double* g = tracks + (size_t)blockIdx.x * npad;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) row[i] = g[i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += blockDim.x) g[k] = row[own[k]];
+}
+
+constexpr int CMB_THREADS = 1024;
+constexpr int CMB_GROUP = 8;          // q_xy values per loop group: their 2 x 8 x Kr x/y rows stay L2-resident across the q_z loop
+constexpr int CMB_BINS = 1024;        // linear bins of the median selection (one per thread)
+struct CombineArgs {
+    const double* cand; const double* hgap; const double* hdr; const double* tracks; long long npad;
+    const unsigned short* yperm; const unsigned short* yrank;
+    int n, Kz, Kr, iq0, nq, iz0, nz;
+    long long h_first, h_count;
+    double* stats; const int* status;
+};
+struct CmbShared {
+    double red[2][32];
+    unsigned long long redk[2][32];
+    unsigned int hist[CMB_BINS];
+    unsigned int wtot[32];
+    unsigned long long list[64];
+    double fin[2], lo, hi, sel_lo, sel_w, v0, v1;
+    unsigned int rank, lcount, below, cnt, level, done, le_count;
+    unsigned long long above;
+};
+// value of 0-based rank `r` among err[0..m): linear bins between the running bounds, narrowed level by level; the bin index
+// is a monotone function of the value, so order statistics are exact.  Leaves S.v0 (the value) and S.le_count
+// (how many elements are <= it) / S.above (smallest key above it) for the caller.
+__device__ __forceinline__ int cmb_bin(double e, double lo, double scale) {
+    const double t = (e - lo) * scale;
+    return t < (double)(CMB_BINS - 1) ? (t > 0.0 ? (int)t : 0) : CMB_BINS - 1;
+}
+__device__ void cmb_select(CmbShared& S, const double* __restrict__ err, int m, unsigned r, int tid, int lane, int warp) {
+    // level state: elements with value in [lo_cur, hi_cur] by bin chain; here the chain is kept as an explicit value interval
+    // [a, b] of *keys* (bit patterns), which is exact: after choosing a bin we take the min / max keys of its members.
+    unsigned long long ka = __double_as_longlong(S.lo), kb = __double_as_longlong(S.hi);
+    unsigned rank = r;
+    for (int level = 0; level < 12; ++level) {
+        const double a = __longlong_as_double((long long)ka), b = __longlong_as_double((long long)kb);
+        if (ka == kb) { if (tid == 0) S.v0 = a; __syncthreads(); return; }
+        const double scale = (double)CMB_BINS / (b - a);
+        S.hist[tid] = 0u;
+        if (tid == 0) { S.lcount = 0u; }
+        __syncthreads();
+        for (int k = tid; k < m; k += CMB_THREADS) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(err[k]);
+            if (key >= ka && key <= kb) atomicAdd(&S.hist[cmb_bin(err[k], a, scale)], 1u);
+        }
+        __syncthreads();
+        // exclusive scan over the 1024 bins (one per thread)
+        const unsigned c = S.hist[tid];
+        unsigned inc = c;
+#pragma unroll
+        for (int ofs = 1; ofs < 32; ofs <<= 1) { const unsigned y = __shfl_up_sync(GSF_FULL_MASK, inc, ofs); if (lane >= ofs) inc += y; }
+        if (lane == 31) S.wtot[warp] = inc;
+        __syncthreads();
+        unsigned pre = 0;
+        for (int w = 0; w < warp; ++w) pre += S.wtot[w];
+        const unsigned exc = pre + inc - c;
+        if (c > 0 && rank >= exc && rank < exc + c) { S.rank = rank - exc; S.cnt = c; S.level = (unsigned)tid; }
+        __syncthreads();
+        const int bin = (int)S.level;
+        const unsigned cnt = S.cnt;
+        rank = S.rank;
+        if (cnt <= 64u) {
+            // gather the members of the bin and pick the rank by counting
+            for (int k = tid; k < m; k += CMB_THREADS) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(err[k]);
+                if (key >= ka && key <= kb && cmb_bin(err[k], a, scale) == bin) { const unsigned sl = atomicAdd(&S.lcount, 1u); S.list[sl] = key; }
+            }
+            __syncthreads();
+            if (tid < (int)cnt) {
+                const unsigned long long xk = S.list[tid];
+                unsigned less = 0;
+                for (unsigned q = 0; q < cnt; ++q) { const unsigned long long yk = S.list[q]; less += (yk < xk || (yk == xk && q < (unsigned)tid)) ? 1u : 0u; }
+                if (less == rank) S.v0 = __longlong_as_double((long long)xk);
+            }
+            __syncthreads();
+            return;
+        }
+        // narrow to the bin: its members' smallest and largest keys become the new interval
+        unsigned long long lo2 = ~0ull, hi2 = 0ull;
+        for (int k = tid; k < m; k += CMB_THREADS) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(err[k]);
+            if (key >= ka && key <= kb && cmb_bin(err[k], a, scale) == bin) { lo2 = min(lo2, key); hi2 = max(hi2, key); }
+        }
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) { lo2 = min(lo2, __shfl_xor_sync(GSF_FULL_MASK, lo2, ofs)); hi2 = max(hi2, __shfl_xor_sync(GSF_FULL_MASK, hi2, ofs)); }
+        if (lane == 0) { S.redk[0][warp] = lo2; S.redk[1][warp] = hi2; }
+        __syncthreads();
+        lo2 = S.redk[0][lane]; hi2 = S.redk[1][lane];
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) { lo2 = min(lo2, __shfl_xor_sync(GSF_FULL_MASK, lo2, ofs)); hi2 = max(hi2, __shfl_xor_sync(GSF_FULL_MASK, hi2, ofs)); }
+        ka = lo2; kb = hi2;
+        __syncthreads();
+    }
+    if (tid == 0) S.v0 = __longlong_as_double((long long)ka);           // not reached: 12 levels of 1024 bins exceed 2^64 keys
+    __syncthreads();
+}
+__global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const CombineArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int m = (int)A.hdr[3];
+    double* const cs = reinterpret_cast<double*>(smem_raw);              // candidates [m,3], x-sorted
+    double* const err = cs + 3 * (size_t)m;                              // errors [m], candidate order
+    double* const hg = err + m;                                          // skip bound [m]
+    unsigned short* const yp = reinterpret_cast<unsigned short*>(hg + m);          // y order -> x-rank [m]
+    unsigned short* const yr = yp + ((m + 3) & ~3);                      // x-rank -> position in y order, 0xFFFF: scan in x order
+    __shared__ CmbShared S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long total_slots = (long long)((A.nq + CMB_GROUP - 1) / CMB_GROUP) * CMB_GROUP * A.Kz * A.Kr;
+    const bool dead = (A.status[0] & GRID_FATAL) || (int)A.hdr[4] != m || m == 0;
+    if (!dead) {
+        for (int k = tid; k < 3 * m; k += CMB_THREADS) cs[k] = A.cand[k];
+        for (int k = tid; k < m; k += CMB_THREADS) { hg[k] = A.hgap[k]; yp[k] = A.yperm[k]; yr[k] = A.yrank[k]; }
+    }
+    __syncthreads();
+    const int nxy = A.nq * A.Kr;
+    for (long long slot = blockIdx.x; slot < total_slots; slot += gridDim.x) {
+        // slot -> (q_xy, q_z, r): groups of CMB_GROUP q_xy values outermost, then q_z, then r, q_xy within the group innermost
+        const long long per_group = (long long)CMB_GROUP * A.Kz * A.Kr;
+        const int g = (int)(slot / per_group);
+        const int sg = (int)(slot - (long long)g * per_group);
+        const int iql = g * CMB_GROUP + sg % CMB_GROUP;                  // q_xy index relative to iq0
+        const int ir = (sg / CMB_GROUP) % A.Kr, iz = sg / (CMB_GROUP * A.Kr);
+        if (iql >= A.nq) continue;
+        const long long h = ((long long)(A.iq0 + iql) * A.Kz + iz) * A.Kr + ir;
+        if (h < A.h_first || h >= A.h_first + A.h_count || iz < A.iz0 || iz >= A.iz0 + A.nz) continue;
+        double* const o = A.stats + 4 * (size_t)(h - A.h_first);
+        if (dead) { if (tid == 0) { o[0] = o[1] = o[2] = nan(""); o[3] = 0.0; } continue; }
+        const double* __restrict__ tx = A.tracks + (size_t)(iql * A.Kr + ir) * A.npad;
+        const double* __restrict__ ty = A.tracks + (size_t)(nxy + iql * A.Kr + ir) * A.npad;
+        const double* __restrict__ tz = A.tracks + (size_t)(2 * nxy + (iz - A.iz0) * A.Kr + ir) * A.npad;
+        // ---- phase 1: nearest-neighbour error of every evaluated pose (:1028-1031), exact and pruned; queries in candidate order
+        double se = 0.0, se2 = 0.0;
+        unsigned long long klo = ~0ull, khi = 0ull;
+        for (int k = tid; k < m; k += CMB_THREADS) {
+            const double x0 = __ldg(tx + k), x1 = __ldg(ty + k), x2 = __ldg(tz + k);
+            double dx = x0 - cs[3 * k], dy = x1 - cs[3 * k + 1], dz = x2 - cs[3 * k + 2];
+            double best = dist2_rn(dx, dy, dz);
+            if (!(best < hg[k])) {                                       // another candidate may be nearer than the own measurement
+                const int jr = yr[k];
+                if (jr == 0xFFFF) {                                      // scan outwards in x order while the 1-D gap alone can still win
+                    for (int c = k - 1; c >= 0; --c) {
+                        dx = x0 - cs[3 * c];
+                        if (dx > 0.0 && dx * dx >= best) break;
+                        dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
+                        best = fmin(best, dist2_rn(dx, dy, dz));
+                    }
+                    for (int c = k + 1; c < m; ++c) {
+                        dx = cs[3 * c] - x0;
+                        if (dx > 0.0 && dx * dx >= best) break;
+                        dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
+                        best = fmin(best, dist2_rn(dx, dy, dz));
+                    }
+                } else {                                                 // the track runs along y here: the same in y order
+                    for (int j = jr - 1; j >= 0; --j) {
+                        const int c = yp[j];
+                        dy = x1 - cs[3 * c + 1];
+                        if (dy > 0.0 && dy * dy >= best) break;
+                        dx = x0 - cs[3 * c]; dz = x2 - cs[3 * c + 2];
+                        best = fmin(best, dist2_rn(dx, dy, dz));
+                    }
+                    for (int j = jr + 1; j < m; ++j) {
+                        const int c = yp[j];
+                        dy = cs[3 * c + 1] - x1;
+                        if (dy > 0.0 && dy * dy >= best) break;
+                        dx = x0 - cs[3 * c]; dz = x2 - cs[3 * c + 2];
+                        best = fmin(best, dist2_rn(dx, dy, dz));
+                    }
+                }
+            }
+            const double e = sqrt(best);
+            err[k] = e;
+            se += e; se2 += e * e;
+            const unsigned long long key = (unsigned long long)__double_as_longlong(e);      // e >= 0 or NaN: patterns order like the values
+            klo = min(klo, key); khi = max(khi, key);
+        }
+        // fixed-order block reduction (lane tree, then warp tree)
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            se += __shfl_xor_sync(GSF_FULL_MASK, se, ofs); se2 += __shfl_xor_sync(GSF_FULL_MASK, se2, ofs);
+            klo = min(klo, __shfl_xor_sync(GSF_FULL_MASK, klo, ofs)); khi = max(khi, __shfl_xor_sync(GSF_FULL_MASK, khi, ofs));
+        }
+        if (lane == 0) { S.red[0][warp] = se; S.red[1][warp] = se2; S.redk[0][warp] = klo; S.redk[1][warp] = khi; }
+        __syncthreads();
+        if (warp == 0) {
+            double a = S.red[0][lane], b = S.red[1][lane];
+            unsigned long long lo = S.redk[0][lane], hi = S.redk[1][lane];
+#pragma unroll
+            for (int ofs = 16; ofs > 0; ofs >>= 1) {
+                a += __shfl_xor_sync(GSF_FULL_MASK, a, ofs); b += __shfl_xor_sync(GSF_FULL_MASK, b, ofs);
+                lo = min(lo, __shfl_xor_sync(GSF_FULL_MASK, lo, ofs)); hi = max(hi, __shfl_xor_sync(GSF_FULL_MASK, hi, ofs));
+            }
+            if (lane == 0) { S.fin[0] = a; S.fin[1] = b; S.lo = __longlong_as_double((long long)lo); S.hi = __longlong_as_double((long long)hi); }
+        }
+        __syncthreads();
+        // ---- phase 2: exact median (np.median: mean of the two middle order statistics for an even count)
+        const bool has_nan = S.fin[0] != S.fin[0];
+        double med = nan("");
+        if (!has_nan) {
+            cmb_select(S, err, m, (unsigned)((m - 1) / 2), tid, lane, warp);
+            const double v0 = S.v0;
+            med = v0;
+            if (!(m & 1)) {
+                // rank m/2: v0 again if enough elements are <= v0, else the smallest element above it
+                unsigned le = 0; unsigned long long ab = ~0ull;
+                const unsigned long long k0 = (unsigned long long)__double_as_longlong(v0);
+                for (int k = tid; k < m; k += CMB_THREADS) {
+                    const unsigned long long key = (unsigned long long)__double_as_longlong(err[k]);
+                    if (key <= k0) ++le; else ab = min(ab, key);
+                }
+#pragma unroll
+                for (int ofs = 16; ofs > 0; ofs >>= 1) { le += __shfl_xor_sync(GSF_FULL_MASK, le, ofs); ab = min(ab, __shfl_xor_sync(GSF_FULL_MASK, ab, ofs)); }
+                if (lane == 0) { S.wtot[warp] = le; S.redk[0][warp] = ab; }
+                __syncthreads();
+                if (warp == 0) {
+                    le = S.wtot[lane]; ab = S.redk[0][lane];
+#pragma unroll
+                    for (int ofs = 16; ofs > 0; ofs >>= 1) { le += __shfl_xor_sync(GSF_FULL_MASK, le, ofs); ab = min(ab, __shfl_xor_sync(GSF_FULL_MASK, ab, ofs)); }
+                    if (lane == 0) S.v1 = le > (unsigned)(m / 2) ? v0 : __longlong_as_double((long long)ab);
+                }
+                __syncthreads();
+                med = 0.5 * (v0 + S.v1);
+            }
+        }
+        if (tid == 0) { o[0] = S.fin[0] / m; o[1] = med; o[2] = sqrt(S.fin[1] / m); o[3] = (double)m; }
+        __syncthreads();
+    }
+}
+
+// work layout (doubles): the header block of the per-hypothesis path (hdr, R t s, offsets2, status, rec, cand, Umeyama tiles,
+// mask), own (n ints), hgap (n), then the track table [tracks][npad].
+static void noise_grid_ranges(int Kz, int Kr, long long h_first, long long h_count, int& iq0, int& nq, int& iz0, int& nz) {
+    const long long slab = (long long)Kz * Kr;
+    iq0 = (int)(h_first / slab);
+    const int iq1 = (int)((h_first + h_count - 1) / slab);
+    nq = iq1 - iq0 + 1;
+    if (nq == 1) { iz0 = (int)((h_first % slab) / Kr); nz = (int)(((h_first + h_count - 1) % slab) / Kr) - iz0 + 1; }
+    else { iz0 = 0; nz = Kz; }
+}
+static long long noise_grid_head_doubles(long long n) {
+    return 16 + 16 + 2 + 2 + 8 * n + 3 * n + (long long)sim3_tiles_for(n) * 20 + (n + 7) / 8 + 4 + (n + 1) / 2 + n + 2 * ((n + 3) / 4) + 8;
+}
+long long noise_grid_work_doubles(long long n, int Kq, int Kz, int Kr, long long h_first, long long h_count) {
+    (void)Kq;
+    int iq0, nq, iz0, nz;
+    noise_grid_ranges(Kz, Kr, h_first, h_count, iq0, nq, iz0, nz);
+    const long long npad = (n + 31) / 32 * 32;
+    return noise_grid_head_doubles(n) + (2ll * nq + nz) * Kr * npad + 4;
+}
+cudaError_t launch_noise_grid(const double* ts, const double* pos, const double* quat, const double* z, long long n,
+                              const FuseParams* base, const double* qxy, const double* qz, const double* rr, int Kq, int Kz, int Kr,
+                              long long h_first, long long h_count, double* work, double* stats, double* sim3_out, int* status_out,
+                              int max_smem, int num_sms, cudaStream_t stream) {
+    (void)Kq;
+    double* hdr = work;
+    double* R = work + 16; double* t = R + 9; double* s = t + 3;
+    long long* offsets2 = reinterpret_cast<long long*>(work + 32);
+    int* st = reinterpret_cast<int*>(work + 34);
+    double* rec = work + 36;
+    double* cand = rec + 8 * n;
+    double* uwork = cand + 3 * n;
+    unsigned char* mask = reinterpret_cast<unsigned char*>(uwork + (size_t)sim3_tiles_for(n) * 20);
+    double* after = reinterpret_cast<double*>(mask) + (n + 7) / 8 + 4;
+    int* own = reinterpret_cast<int*>(after);
+    double* hgap = after + (n + 1) / 2;
+    unsigned short* yperm = reinterpret_cast<unsigned short*>(hgap + n);
+    unsigned short* yrank = yperm + 4 * ((n + 3) / 4);
+    double* tracks = work + noise_grid_head_doubles(n);
+    tracks = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(tracks) + 31) & ~(uintptr_t)31);
+    const long long npad = (n + 31) / 32 * 32;
+    int iq0, nq, iz0, nz;
+    noise_grid_ranges(Kz, Kr, h_first, h_count, iq0, nq, iz0, nz);
+    const int cap2 = pow2_at_least(n);
+    const size_t smem_prep = (size_t)cap2 * 12;
+    const size_t smem_cmb = (size_t)n * 44 + 64;                           // candidates 24 + errors 8 + skip bound 8 + y order 4 per pose
+    if (smem_prep > (size_t)max_smem || smem_cmb > (size_t)max_smem || (size_t)n * 8 > (size_t)max_smem || n > 65535) return cudaErrorInvalidValue;
+    grid_prep_select_kernel<<<1, 1024, 0, stream>>>(ts, z, (int)n, base, mask, offsets2, st);
+    cudaError_t e = launch_umeyama(pos, z, offsets2, mask, 1, n, uwork, R, t, s, st + 1, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(grid_prep_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
+    if (e != cudaSuccess) return e;
+    grid_prep_records_kernel<<<1, 1024, smem_prep, stream>>>(ts, pos, quat, z, (int)n, base, R, t, s, rec, cand, hdr, st, cap2);
+    grid_prep_order_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(rec, cand, hdr, (int)n, own, hgap, st);
+    e = cudaFuncSetAttribute(grid_prep_ysort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
+    if (e != cudaSuccess) return e;
+    grid_prep_ysort_kernel<<<1, 1024, smem_prep, stream>>>(cand, z, hdr, (int)n, own, yperm, yrank, st, cap2);
+    const int NT = (2 * nq + nz) * Kr;
+    grid_tracks_kernel<<<(NT + TRK_THREADS - 1) / TRK_THREADS, TRK_THREADS, 0, stream>>>(rec, hdr, (int)n, base, qxy, qz, rr, Kr, iq0, nq, iz0, nz,
+                                                                                         tracks, npad, st);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(grid_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8));
+    if (e != cudaSuccess) return e;
+    grid_permute_kernel<<<NT, 256, (size_t)n * 8, stream>>>(tracks, npad, (int)n, own, hdr, st);
+    CombineArgs ca;
+    ca.cand = cand; ca.hgap = hgap; ca.hdr = hdr; ca.tracks = tracks; ca.npad = npad; ca.yperm = yperm; ca.yrank = yrank;
+    ca.n = (int)n; ca.Kz = Kz; ca.Kr = Kr; ca.iq0 = iq0; ca.nq = nq; ca.iz0 = iz0; ca.nz = nz;
+    ca.h_first = h_first; ca.h_count = h_count; ca.stats = stats; ca.status = st;
+    e = cudaFuncSetAttribute(grid_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cmb);
+    if (e != cudaSuccess) return e;
+    long long blocks = h_count < num_sms ? h_count : num_sms;
+    grid_combine_kernel<<<(unsigned)blocks, CMB_THREADS, smem_cmb, stream>>>(ca);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (sim3_out) { e = cudaMemcpyAsync(sim3_out, R, 13 * sizeof(double), cudaMemcpyDeviceToDevice, stream); if (e != cudaSuccess) return e; }
+    if (status_out) e = cudaMemcpyAsync(status_out, st, sizeof(int), cudaMemcpyDeviceToDevice, stream);
+    return e;
 }
 
 // One block per SM (the candidate set fills most of the shared memory) and a block takes about the same time whatever

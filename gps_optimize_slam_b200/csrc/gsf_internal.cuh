@@ -33,6 +33,10 @@ cudaError_t launch_ekf_strict(const double*, const double*, const double*, const
 long long grid_work_doubles(long long n, int H);
 cudaError_t launch_hypothesis_grid(const double*, const double*, const double*, const double*, long long, const FuseParams*, int,
                                    double*, double*, double*, int*, int, int, cudaStream_t);
+long long noise_grid_work_doubles(long long n, int Kq, int Kz, int Kr, long long h_first, long long h_count);
+cudaError_t launch_noise_grid(const double*, const double*, const double*, const double*, long long, const FuseParams*, const double*,
+                              const double*, const double*, int, int, int, long long, long long, double*, double*, double*, int*, int, int,
+                              cudaStream_t);
 cudaError_t launch_ekf_step(int, const double*, const double*, const double*, const double*, const double*, const double*, const double*,
                             const double*, const double*, int, double*, double*, double*, double*, int*, cudaStream_t);
 cudaError_t launch_rts_segment(const double*, const double*, const double*, const double*, const long long*, int, double*, double*, cudaStream_t);

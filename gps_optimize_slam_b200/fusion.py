@@ -161,6 +161,34 @@ def hypothesis_grid(ts, pos, quat, z, params, stream=None):
     return stats, sim3, status
 
 
+def noise_grid(ts, pos, quat, z, base_params, q_xy, q_z, r, h_first=0, h_count=None, work=None, stats=None, stream=None):
+    """One trajectory x a product grid of noise hypotheses (gsf_ekf_noise_grid_dev): hypothesis
+    h = (iq * Kz + iz) * Kr + ir uses process noise (q_xy[iq], q_xy[iq], q_z[iz]) and measurement noise r[ir]; everything
+    else comes from ``base_params`` (uint8 [184]).  Scores [h_first, h_first + h_count).
+    Returns (stats [h_count,4] = mean, median, RMSE, count; sim3 [13]; status [1]); asynchronous."""
+    lib = _lib.load()
+    _require_cuda(ts, pos, quat, z, base_params, q_xy, q_z, r)
+    n = int(ts.numel())
+    Kq, Kz, Kr = int(q_xy.numel()), int(q_z.numel()), int(r.numel())
+    if h_count is None:
+        h_count = Kq * Kz * Kr - h_first
+    dev = ts.device
+    need = lib.gsf_noise_grid_work_doubles(n, Kq, Kz, Kr, int(h_first), int(h_count))
+    if need <= 0:
+        raise ValueError("noise_grid: empty or out-of-range hypothesis range")
+    if work is None or work.numel() < need:
+        work = torch.empty((need,), dtype=torch.float64, device=dev)
+    if stats is None:
+        stats = torch.empty((h_count, 4), dtype=torch.float64, device=dev)
+    sim3 = torch.empty((13,), dtype=torch.float64, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    rc = lib.gsf_ekf_noise_grid_dev(_ptr(ts), _ptr(pos), _ptr(quat), _ptr(z), n, _ptr(base_params), _ptr(q_xy), _ptr(q_z), _ptr(r),
+                                    Kq, Kz, Kr, int(h_first), int(h_count), _ptr(work), _ptr(stats), _ptr(sim3), _ptr(status),
+                                    _stream_ptr(stream))
+    _lib.check(rc, "gsf_ekf_noise_grid_dev")
+    return stats, sim3, status
+
+
 def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, params_per_traj=False, stream=None):
     """Literal step-by-step EKF recursion, one thread per trajectory (gsf_ekf_strict_batched_dev)."""
     lib = _lib.load()

@@ -97,6 +97,21 @@ int gsf_ekf_hypothesis_grid_dev(const double* ts, const double* pos, const doubl
                                 const gsf_fuse_params* params, int32_t H, double* work, double* stats,
                                 double* sim3_out, int32_t* status, void* stream);
 
+/* ---- the same for a PRODUCT grid of noise hypotheses (BASELINE config 5: 64 x 64 x 64 over q_xy, q_z, r): hypothesis
+ *      h = (iq * Kz + iz) * Kr + ir runs ExtendedKalmanFilter (:679-772) with process_noise_diag[0:2] = q_xy[iq],
+ *      process_noise_diag[2] = q_z[iz], meas_noise_diag = r[ir] (x3) and everything else from `base` (one record).
+ *      P0 / Q / R are diagonal (:684-686), so the x / y tracks depend on (q_xy, r) only and the z track on (q_z, r)
+ *      only: Kq*Kr + Kq*Kr + Kz*Kr scalar filter runs (bit-identical to the components the per-hypothesis entry above
+ *      computes) and one nearest-neighbour evaluation (:1021-1033) per hypothesis.  The call scores the hypotheses
+ *      [h_first, h_first + h_count) (a rank's shard); stats [h_count,4]: mean, median, RMSE, count.  q_xy [Kq],
+ *      q_z [Kz], r [Kr] device fp64.  work: gsf_noise_grid_work_doubles() doubles.  Same restriction and status as
+ *      gsf_ekf_hypothesis_grid_dev. */
+int64_t gsf_noise_grid_work_doubles(int64_t n, int32_t Kq, int32_t Kz, int32_t Kr, int64_t h_first, int64_t h_count);
+int gsf_ekf_noise_grid_dev(const double* ts, const double* pos, const double* quat, const double* z, int64_t n,
+                           const gsf_fuse_params* base, const double* q_xy, const double* q_z, const double* r,
+                           int32_t Kq, int32_t Kz, int32_t Kr, int64_t h_first, int64_t h_count,
+                           double* work, double* stats, double* sim3_out, int32_t* status, void* stream);
+
 /* ---- apply_ekf_correction (:831-935), literal step-by-step recursion, one thread per
  *      trajectory (general path; keeps the zero-motion fallback of :84-86). */
 int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,

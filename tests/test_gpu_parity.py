@@ -553,6 +553,52 @@ def test_hypothesis_grid_matches_oracle(gsf, n, dt):
     assert int(st2.cpu()[0]) & _lib.ST_GRID_NEEDS_ALL_VALID and np.isnan(stats2.cpu().numpy()[:, :3]).all()
 
 
+@pytest.mark.parametrize("n,k", [(300, (5, 4, 6)), (4541, (3, 3, 4))])
+def test_noise_grid_matches_per_hypothesis_kernel_and_oracle(gsf, n, k):
+    """gsf_ekf_noise_grid_dev (product grid, factored into scalar x/y and z tracks + a combine kernel) against
+    gsf_ekf_hypothesis_grid_dev on the same hypotheses (same per-step arithmetic: medians bit-identical, sums to
+    rounding) and against the oracle (EKFGPSSLAM.py:679-772, :1021-1033); a shard [h_first, h_first + h_count) that
+    starts and ends inside a q_xy slab equals the same rows of the full run bit for bit."""
+    from gps_optimize_slam_b200 import synth
+    from gps_optimize_slam_b200.config import pack_fuse_params, pack_noise_grid
+    from oracle import fusion_oracle as fo
+    tr = synth.make_loop_trajectory(7, n=n) if n > 1000 else synth.make_trajectory(43, n=n, dt=0.104, speed=9.0)
+    Kq, Kz, Kr = k
+    qxy = np.logspace(-3, 1, Kq); qz = np.logspace(-2.5, 0.5, Kz); rr = np.logspace(-2, 1, Kr)
+    grid = np.stack(np.meshgrid(qxy, qz, rr, indexing="ij"), axis=-1).reshape(-1, 3)
+    H = len(grid)
+    args = [dev(tr[key]) for key in ("ts", "pos", "quat", "gps")]
+    base = dev(pack_fuse_params(), torch.uint8)
+    stats, sim3, st = gsf.noise_grid(*args, base, dev(qxy), dev(qz), dev(rr))
+    assert int(st.cpu()[0]) == 0
+    ref, sim3b, stb = gsf.hypothesis_grid(*args, dev(pack_noise_grid(grid), torch.uint8))
+    stats, ref = stats.cpu().numpy(), ref.cpu().numpy()
+    np.testing.assert_array_equal(stats[:, 1], ref[:, 1])                  # medians: order statistics of identical errors
+    np.testing.assert_array_equal(stats[:, 3], ref[:, 3])
+    np.testing.assert_allclose(stats[:, [0, 2]], ref[:, [0, 2]], rtol=1e-13, atol=0)
+    np.testing.assert_array_equal(sim3.cpu().numpy(), sim3b.cpu().numpy())
+    # shard inside the grid
+    h0, hc = Kz * Kr + 3, H - 2 * Kz * Kr - 5 if Kq > 3 else H - Kz * Kr - 7
+    part, _, _ = gsf.noise_grid(*args, base, dev(qxy), dev(qz), dev(rr), h_first=h0, h_count=hc)
+    np.testing.assert_array_equal(part.cpu().numpy(), stats[h0:h0 + hc])
+    one, _, _ = gsf.noise_grid(*args, base, dev(qxy), dev(qz), dev(rr), h_first=5, h_count=2)   # inside one (q_xy, q_z) row
+    np.testing.assert_array_equal(one.cpu().numpy(), stats[5:7])
+    # oracle, a few hypotheses
+    valid = np.ones(n, dtype=bool)
+    ev = fo.evaluation_indices(tr["ts"], valid)
+    for h in ([0, H // 2, H - 1] if n > 1000 else range(0, H, 7)):
+        cfg = fo.default_config()
+        cfg["ekf"].update(process_noise_diag=[grid[h, 0], grid[h, 0], grid[h, 1]] + [0.01] * 4, meas_noise_diag=[grid[h, 2]] * 3)
+        o = oracle_pipeline(tr, cfg)
+        want = fo.error_stats(fo.nn_errors(o["pos"], tr["gps"], ev))
+        np.testing.assert_allclose(stats[h, :3], want, rtol=0, atol=POS_ATOL)
+        assert stats[h, 3] == len(ev)
+    bad = tr["gps"].copy(); bad[50] = np.nan
+    s2, _, st2 = gsf.noise_grid(args[0], args[1], args[2], dev(bad), base, dev(qxy), dev(qz), dev(rr))
+    from gps_optimize_slam_b200 import _lib
+    assert int(st2.cpu()[0]) & _lib.ST_GRID_NEEDS_ALL_VALID and np.isnan(s2.cpu().numpy()[:, :3]).all()
+
+
 def test_bit_reproducible_and_shard_invariant(gsf):
     """Same inputs -> same bits; an N-way shard (separate launches over trajectory ranges)
     equals the unsharded run bit for bit (multi-GPU without a cluster)."""

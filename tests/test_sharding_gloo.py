@@ -26,6 +26,9 @@ def _worker(rank, world, port, total, out_dir):
     b = torch.arange(lo, hi, dtype=torch.float64)
     local = torch.stack([b, 2 * b, 3 * b, torch.full_like(b, rank)], dim=1)
     full = sharding.gather_stats(local, total_rows=total)
+    counts = [sharding.shard_range(total, r, world)[1] - sharding.shard_range(total, r, world)[0] for r in range(world)]
+    full2 = sharding.gather_stats(local, total_rows=total, counts=counts)     # one collective, no height exchange
+    assert torch.equal(full, full2)
     t = sharding.max_over_ranks(10.0 + rank, "cpu")
     torch.save({"full": full, "t": t, "range": (lo, hi)}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
