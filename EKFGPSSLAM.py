@@ -410,15 +410,34 @@ def apply_ekf_correction(slam_data_in, gps_data_in, sim3_pos_initial, sim3_quat_
 
 
 def fuse_trajectory(slam_data, aligned, config=CONFIG):
-    """Whole device path for one trajectory with associated measurements: Sim3 selection +
-    Umeyama + EKF in ONE kernel launch -> dict(R, t, s, pos, quat, status)."""
+    """Whole device path for one trajectory with associated measurements (NaN row = no GNSS): Sim3 selection +
+    Umeyama + EKF in ONE kernel launch -> dict(R, t, s, pos, quat, status, sim3_path).
+    The fused kernel fits ALL selected points; that equals compute_sim3_transform_robust (EKFGPSSLAM.py:389-426)
+    whenever RANSAC's best trial keeps every point.  When a residual of the all-points fit reaches the threshold
+    (status bit 16, GSF_ST_RANSAC_OUTLIERS) the reference would have refitted on an inlier subset, so this function
+    re-runs the explicit route -- device RANSAC, transform of pose 0, EKF seeded with it -- like main_process does."""
     ts = np.asarray(slam_data["timestamps"], float)
     n = len(ts)
-    p, q, sim3, st = fusion.fuse_batched(_dev(ts), _dev(slam_data["positions"]), _dev(slam_data["quaternions"]),
-                                         _dev(aligned), _one(n), n, fusion.params_tensor(config))
+    args = (_dev(ts), _dev(slam_data["positions"]), _dev(slam_data["quaternions"]), _dev(aligned), _one(n))
+    prm = fusion.params_tensor(config)
+    p, q, sim3, st = fusion.fuse_batched(*args, n, prm)
     s3 = sim3[0].cpu().numpy()
-    return {"R": s3[:9].reshape(3, 3), "t": s3[9:12], "s": float(s3[12]), "n_selected": int(s3[13]),
-            "pos": p.cpu().numpy(), "quat": q.cpu().numpy(), "status": int(st.cpu()[0])}
+    status = int(st.cpu()[0])
+    out = {"R": s3[:9].reshape(3, 3), "t": s3[9:12], "s": float(s3[12]), "n_selected": int(s3[13]),
+           "pos": p.cpu().numpy(), "quat": q.cpu().numpy(), "status": status, "sim3_path": "fused all-points fit"}
+    if status & _lib.ST_RANSAC_OUTLIERS:
+        valid = ~np.isnan(np.asarray(aligned)).any(axis=1)
+        sel = select_sim3_indices(ts, valid, config)
+        rc = config["sim3_ransac"]
+        R, t, s = compute_sim3_transform_robust(np.asarray(slam_data["positions"])[sel], np.asarray(aligned)[sel], rc["min_samples"],
+                                                rc["residual_threshold"], rc["max_trials"], rc["min_inliers_needed"])
+        if R is None:
+            raise RuntimeError("Sim3 global transform failed")
+        p0, q0 = transform_trajectory(np.asarray(slam_data["positions"])[:1], np.asarray(slam_data["quaternions"])[:1], R, t, s)
+        p, q, _, st2 = fusion.fuse_batched(*args, n, prm, init_pos=_dev(p0), init_quat=_dev(q0))
+        out.update(R=R, t=np.asarray(t), s=float(s), n_selected=len(sel), pos=p.cpu().numpy(), quat=q.cpu().numpy(),
+                   status=int(st2.cpu()[0]) | _lib.ST_RANSAC_OUTLIERS, sim3_path="RANSAC refit (outliers in the Sim3 window)")
+    return out
 
 
 # ----------------------------------------------------------------------------- evaluation + orchestration

@@ -196,7 +196,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
     ap.add_argument("--with-ate", action="store_true", help="also run the NN-ATE kernel at N=1 (always on for N>1, with the NCCL gather)")
-    ap.add_argument("--ate-trajectories", type=int, default=65536, help="trajectories per rank scored by the NN-ATE kernel")
+    ap.add_argument("--ate-trajectories", type=int, default=0, help="trajectories per rank scored by the NN-ATE kernel (0 = the whole shard)")
+    ap.add_argument("--outage-prob", type=float, default=0.0, help="fraction of trajectories with a GNSS outage (general kernel + RTS) in the main workload")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the mixed fast / general-path records (10 % and 50 % outage trajectories)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config 5 sub-record appended to the default line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload in ("config4", "config5"):
@@ -236,7 +239,8 @@ def main():
     while B_res * n * BYTES_PER_POSE + B_res * 256 > 0.92 * free:        # does not fit: process the shard in equal resident slabs
         passes += 1
         B_res = -(-B // passes)
-    ts, pos, quat, z = fusion.synth_generate(B_res, n, wl["dt"], wl["speed"], seed=20261018, first_traj=lo, device=dev)
+    ts, pos, quat, z = fusion.synth_generate(B_res, n, wl["dt"], wl["speed"], seed=20261018, first_traj=lo, device=dev,
+                                             outage_prob=args.outage_prob, outage_max_len=60 if args.outage_prob > 0 else 0)
     off = fusion.equal_offsets(B_res, n, device=dev)
     prm = fusion.params_tensor(device=dev)
     out_pos = torch.empty_like(pos); out_quat = torch.empty_like(quat)
@@ -318,32 +322,100 @@ def main():
         e2e_s = time.perf_counter() - t0
         e2e_s = sharding.max_over_ranks(e2e_s, dev)
         e2e_ok = bool(torch.equal(hop, out_pos[: Be * n].cpu())) if passes == 1 else True
-        e2e = {"value": world * Be * (n - 1) * e2e_steps / e2e_s, "unit": "pose-updates/s",
+        # host copy ceiling: the same bytes, the same pinned buffers, copies only (H2D on one stream, D2H on another,
+        # all ranks at once) -- what the host memory system / PCIe allow with no kernel in the way
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        d_in = [ts[: Be * n], pos[: Be * n], quat[: Be * n], z[: Be * n]]
+
+        def copy_step():
+            with torch.cuda.stream(s_in):
+                for d_, h_ in zip(d_in, (hts, hpos, hquat, hz)):
+                    d_.copy_(h_, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hop.copy_(out_pos[: Be * n], non_blocking=True); hoq.copy_(out_quat[: Be * n], non_blocking=True)
+
+        copy_step(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copy_step()
+        torch.cuda.synchronize(dev)
+        copy_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e_value = world * Be * (n - 1) * e2e_steps / e2e_s
+        ceiling = world * Be * (n - 1) * e2e_steps / copy_s
+        e2e = {"value": e2e_value, "unit": "pose-updates/s",
                "h2d_bytes_per_step": Be * n * 88 + (Be + 1) * 8 + 184, "d2h_bytes_per_step": Be * n * 56 + Be * 132,
                "sample": f"{Be} trajectories x {n} poses per rank per step, pinned host buffers, {e2e_steps} steps",
-               "matches_device_path": e2e_ok}
+               "matches_device_path": e2e_ok,
+               "host_copy_ceiling": {"value": ceiling, "unit": "pose-updates/s", "frac_of_ceiling": e2e_value / ceiling,
+                                     "gb_per_s_per_rank": Be * n * 144 * e2e_steps / copy_s / 1e9,
+                                     "how": "same pinned buffers and byte counts, concurrent H2D + D2H copies only, all ranks at once"}}
+        del d_in
 
-    # ---- ATE statistics (EKFGPSSLAM.py:1021-1033): per-rank NN-ATE kernel on a bounded slab of the
-    #      fused output, then the only collective of the path: gather of the per-trajectory stats
-    #      (NCCL all_gather over NVLink).  Outside the timed region; the exact O(n^2) nearest-neighbour
-    #      kernel is FP64-bound (about 20x the fused kernel per trajectory at n = 1000).
+    # ---- ATE statistics (EKFGPSSLAM.py:1021-1033) of the WHOLE shard: exact pruned nearest-neighbour kernel over the fused
+    #      output (56 B/pose read: trajectory 24 + candidates 24 + stamps 8), then the only collective of the path: the
+    #      full [B, 4] table gathered with one NCCL all_gather over NVLink.  Device-timed (CUDA events), max over ranks.
     ate = None
-    if args.with_ate or world > 1:
-        Ba = min(B_res, args.ate_trajectories)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
+    if True:
+        Ba = B_res if args.ate_trajectories <= 0 else min(B_res, args.ate_trajectories)
+        counts = None
+        if world > 1 and Ba == B_res and passes == 1:
+            counts = [sharding.shard_range(B_total, r, world)[1] - sharding.shard_range(B_total, r, world)[0] for r in range(world)]
+        for _ in range(2):                                                       # warm the kernel and the communicator
+            stats = fusion.ate_nn_batched(out_pos[: Ba * n], z[: Ba * n], ts[: Ba * n], off[: Ba + 1], n, 5.0)
+            table = sharding.gather_stats(stats, counts=counts)
+        barrier()
+        ea = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ea[0].record()
         stats = fusion.ate_nn_batched(out_pos[: Ba * n], z[: Ba * n], ts[: Ba * n], off[: Ba + 1], n, 5.0)
+        ea[1].record()
+        table = sharding.gather_stats(stats, counts=counts)
+        ea[2].record()
         torch.cuda.synchronize(dev)
-        ate_s = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        table = sharding.gather_stats(stats, total_rows=Ba * world if world > 1 else None)
-        torch.cuda.synchronize(dev)
-        gather_s = time.perf_counter() - t0
+        ate_ms = sharding.max_over_ranks(ea[0].elapsed_time(ea[1]), dev)
+        gather_ms = sharding.max_over_ranks(ea[1].elapsed_time(ea[2]), dev)
         s_ = table.cpu()
-        ate = {"trajectories": int(s_.shape[0]), "per_rank": Ba, "mean_rmse_m": float(s_[:, 2].mean()),
-               "mean_median_m": float(s_[:, 1].mean()), "mean_of_means_m": float(s_[:, 0].mean()),
-               "kernel_seconds_per_rank": ate_s, "gather_seconds": gather_s,
-               "gathered_with": "nccl all_gather" if world > 1 else "single rank (no collective)"}
+        ok = torch.isfinite(s_[:, 2])
+        ate_gbs = Ba * n * 56 / (ate_ms * 1e-3) / 1e9
+        ate = {"trajectories": int(s_.shape[0]), "per_rank": Ba, "mean_rmse_m": float(s_[ok, 2].mean()),
+               "mean_median_m": float(s_[ok, 1].mean()), "mean_of_means_m": float(s_[ok, 0].mean()),
+               "kernel_ms_per_rank": ate_ms, "gather_ms": gather_ms, "kernel_seconds_per_rank": ate_ms * 1e-3, "gather_seconds": gather_ms * 1e-3,
+               "poses_per_s": world * Ba * n / (ate_ms * 1e-3),
+               "roofline": {"bound": "hbm", "achieved": ate_gbs, "peak": peak, "unit": "GB/s", "frac": ate_gbs / peak,
+                            "kernel": "ate_nn_kernel", "algorithmic_bytes_per_launch": Ba * n * 56, "launch_ms": ate_ms},
+               "ms_relative_to_fused_step": ate_ms / launch_ms * (B_res / Ba),
+               "gathered_with": "nccl all_gather_into_tensor" if world > 1 else "single rank (no collective)"}
+        del stats, table
+
+    # ---- the general path at scale (outages -> general kernel + closed-form RTS, EKFGPSSLAM.py:875-928): the first slab of the
+    #      resident buffers is regenerated with 10 % / 50 % of the trajectories carrying a GNSS outage and re-timed
+    mixed = None
+    if not args.no_mixed and args.workload == "config3":
+        mixed = []
+        Bm = min(B_res, 131072)
+        sl = [x[: Bm * n] for x in (ts, pos, quat, z)]
+        for prob in (0.1, 0.5):
+            fusion.synth_generate(Bm, n, wl["dt"], wl["speed"], seed=20261018, first_traj=lo, device=dev, outage_prob=prob, outage_max_len=60, out=sl)
+            with_outage = int(torch.isnan(sl[3][:, 0]).reshape(Bm, n).any(dim=1).sum().cpu())
+
+            def mstep():
+                fusion.fuse_batched(sl[0], sl[1], sl[2], sl[3], off[: Bm + 1], n, prm, out_pos=out_pos[: Bm * n], out_quat=out_quat[: Bm * n],
+                                    sim3_out=sim3[:Bm], status=status[:Bm])
+            for _ in range(3):
+                mstep()
+            barrier()
+            em = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            em[0].record()
+            for _ in range(5):
+                mstep()
+            em[1].record()
+            torch.cuda.synchronize(dev)
+            mms = sharding.max_over_ranks(em[0].elapsed_time(em[1]), dev) / 5
+            gbs = Bm * n * BYTES_PER_POSE / (mms * 1e-3) / 1e9
+            mixed.append({"outage_prob": prob, "trajectories_per_rank": Bm, "with_outage": with_outage, "ms_per_step": mms,
+                          "pose_updates_per_s": world * Bm * (n - 1) / (mms * 1e-3), "roofline_frac": gbs / peak,
+                          "nonzero_status": int((status[:Bm] != 0).sum().cpu()),
+                          "kernels": "fuse_fast_kernel, then fuse_traj_kernel over the deferred (outage) trajectories"})
+        del sl
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample
     cpu = None
@@ -353,8 +425,26 @@ def main():
         h = [x.cpu().numpy() for x in (ts[: k * n], pos[: k * n], quat[: k * n], z[: k * n])]
         sample = [(h[0][i * n:(i + 1) * n], h[1][i * n:(i + 1) * n], h[2][i * n:(i + 1) * n], h[3][i * n:(i + 1) * n]) for i in range(k)]
         v, ms, used = cpu_reference_run(sample, steps=3, warmup=1, cores=cores)
+        from oracle import bench_worker
+        bench_worker.warm()
+        t0 = time.perf_counter()
+        upd1 = bench_worker.run_trajectories(sample[:2])[0]
+        one_core = upd1 / (time.perf_counter() - t0)
         cpu = {"value": v, "unit": "pose-updates/s", "cores": used, "kind": "port",
-               "sample": f"first {k} trajectories x {n} poses of the same device-generated batch, {used} processes, 3 timed passes"}
+               "sample": f"first {k} trajectories x {n} poses of the same device-generated batch, {used} processes, 3 timed passes",
+               "one_core": {"value": one_core, "unit": "pose-updates/s", "cores": 1, "sample": f"first 2 trajectories x {n} poses, this process"}}
+
+    # ---- config 5 (one KITTI-00-length trajectory x 64^3 noise-grid hypotheses, hypotheses sharded over the ranks, NCCL
+    #      gather of the statistics inside its timed step) as a sub-record, so that the driver's scaling run carries it
+    config5 = None
+    if not args.no_config5 and args.workload == "config3":
+        del ts, pos, quat, z, out_pos, out_quat, sim3, status
+        torch.cuda.empty_cache()
+        import bench_workloads as bw
+        try:
+            config5 = bw.measure_config5(args, rank, local_rank, world, ClockSampler, with_cpu=False, with_e2e=False, steps=5, warmup=3)
+        except Exception as exc:                                         # never lose the headline line to the sub-record
+            config5 = {"error": f"{type(exc).__name__}: {exc}"}
 
     if world > 1:
         dist.barrier()
@@ -367,10 +457,11 @@ def main():
                        "trajectories_per_gpu": B, "resident_per_gpu": B_res, "passes_per_step": passes,
                        "parallelism": f"trajectory-sharded x{world}, no data-path collective",
                        "l2": "inputs (88 B/pose x resident poses) far exceed the 126 MB L2; no flush needed",
-                       "sim3": "selection + Umeyama + residual check inside the same kernel", "nonzero_status": bad},
+                       "sim3": "selection + Umeyama + residual check inside the same kernel", "nonzero_status": bad,
+                       "outage_prob": args.outage_prob},
             "sim3_aligned_points_per_s": sim3_pts,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 2 * args.steps * passes, "ate": ate,
+            "gpu_launches": 2 * args.steps * passes, "ate": ate, "general_path": mixed, "config5": config5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -33,6 +33,7 @@ constexpr int FLAG_VALID = 1;
 constexpr int FLAG_SELECTED = 2;
 constexpr int FLAG_RECOVERY = 4;
 constexpr int FLAG_NO_RTS = 8;
+constexpr int FLAG_SHARP_STEP = 16;     // outage step (pose i-1 -> i, both without GNSS) whose yaw rate exceeds the sharp-turn threshold
 
 // ----------------------------------------------------------------------------- scan operators
 // 2x2 Moebius matrices for the three position axes, row-major [a b; c d] per axis.  Entries

@@ -224,15 +224,39 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
         GSF_STAMP(2);
         int st = ST_OK;
 
-        // ------------------------------------------------------------------ GNSS recoveries (:879-894), rare: sharp-turn gate
+        // ------------------------------------------------------------------ GNSS recoveries (:879-894): sharp-turn gate
+        // is_sharp_turn_in_segment (:808-826) over the outage [s .. i-1] is a maximum of per-step yaw rates, and every step
+        // costs nine transcendental calls (two as_euler('zyx') yaws, the wrap): the steps of all outages of the trajectory are
+        // spread over the whole block (one thread walking a 60-pose outage alone held the block for ~100k cycles), each
+        // leaves one flag bit, and the thread that owns the recovery pose ORs the bits of its outage.
         if (iscr[14]) {
+            const double thr = prm.yaw_rate_thresh;
+            const double* __restrict__ gq = A.quat + 4 * e0;
+            for (int a = 1 + tid; a < n; a += THREADS) {
+                if (!(flg[a] & FLAG_VALID) && !(flg[a - 1] & FLAG_VALID)) {
+                    const double t1 = tsS[a - 1], t2 = tsS[a];
+                    if (t2 <= t1) continue;
+                    const double2 l1 = __ldg(reinterpret_cast<const double2*>(gq + 4 * (a - 1))), h1 = __ldg(reinterpret_cast<const double2*>(gq + 4 * (a - 1)) + 1);
+                    const double2 l2 = __ldg(reinterpret_cast<const double2*>(gq + 4 * a)), h2 = __ldg(reinterpret_cast<const double2*>(gq + 4 * a) + 1);
+                    const Quat q1{l1.x, l1.y, h1.x, h1.y}, q2{l2.x, l2.y, h2.x, h2.y};
+                    bool sharp;
+                    if (qnorm2(q1) == 0.0 || qnorm2(q2) == 0.0) sharp = true;          // scipy ValueError -> True (:821)
+                    else {
+                        const double y1 = yaw_zyx(q1), y2 = yaw_zyx(q2);
+                        const double d = atan2(sin(y2 - y1), cos(y2 - y1));
+                        sharp = fabs(d / (t2 - t1)) > thr;
+                    }
+                    if (sharp) flg[a] = (unsigned char)(flg[a] | FLAG_SHARP_STEP);     // bit 0 is unchanged: concurrent neighbour reads stay valid
+                }
+            }
+            __syncthreads();
             for (int i = s0; i < c1; ++i) {
                 const int f = flg[i];
                 if ((f & FLAG_VALID) && !(flg[i - 1] & FLAG_VALID)) {
-                    int s = i - 1;
-                    while (s > 0 && !(flg[s - 1] & FLAG_VALID)) --s;
+                    int s = i - 1, sharp = 0;
+                    while (s > 0 && !(flg[s - 1] & FLAG_VALID)) { sharp |= flg[s] & FLAG_SHARP_STEP; --s; }
                     int nf = f | FLAG_RECOVERY;
-                    if (sharp_turn_ool(A.ts + e0, A.quat + 4 * e0, s, i - 1, prm.yaw_rate_thresh)) nf |= FLAG_NO_RTS;
+                    if (sharp) nf |= FLAG_NO_RTS;
                     flg[i] = (unsigned char)nf;             // bit 0 is unchanged: concurrent neighbour reads stay valid
                     iscr[9] = 1;
                 }

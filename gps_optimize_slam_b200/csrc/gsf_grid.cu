@@ -517,6 +517,9 @@ __global__ void __launch_bounds__(256) grid_permute_kernel(double* __restrict__ 
     for (int k = threadIdx.x; k < m; k += blockDim.x) g[k] = row[own[k]];
 }
 
+#ifdef GSF_GRID_CLK
+__device__ unsigned long long g_grid_clk[8];
+#endif
 constexpr int CMB_THREADS = 1024;
 constexpr int CMB_GROUP = 8;          // q_xy values per loop group: their 2 x 8 x Kr x/y rows stay L2-resident across the q_z loop
 constexpr int CMB_BINS = 1024;        // linear bins of the median selection (one per thread)
@@ -644,6 +647,9 @@ __global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const Comb
         const double* __restrict__ tx = A.tracks + (size_t)(iql * A.Kr + ir) * A.npad;
         const double* __restrict__ ty = A.tracks + (size_t)(nxy + iql * A.Kr + ir) * A.npad;
         const double* __restrict__ tz = A.tracks + (size_t)(2 * nxy + (iz - A.iz0) * A.Kr + ir) * A.npad;
+#ifdef GSF_GRID_CLK
+        long long c0 = clock64();
+#endif
         // ---- phase 1: nearest-neighbour error of every evaluated pose (:1028-1031), exact and pruned; queries in candidate order
         double se = 0.0, se2 = 0.0;
         unsigned long long klo = ~0ull, khi = 0ull;
@@ -689,6 +695,9 @@ __global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const Comb
             const unsigned long long key = (unsigned long long)__double_as_longlong(e);      // e >= 0 or NaN: patterns order like the values
             klo = min(klo, key); khi = max(khi, key);
         }
+#ifdef GSF_GRID_CLK
+        long long c1 = clock64();
+#endif
         // fixed-order block reduction (lane tree, then warp tree)
 #pragma unroll
         for (int ofs = 16; ofs > 0; ofs >>= 1) {
@@ -708,6 +717,9 @@ __global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const Comb
             if (lane == 0) { S.fin[0] = a; S.fin[1] = b; S.lo = __longlong_as_double((long long)lo); S.hi = __longlong_as_double((long long)hi); }
         }
         __syncthreads();
+#ifdef GSF_GRID_CLK
+        long long c2 = clock64();
+#endif
         // ---- phase 2: exact median (np.median: mean of the two middle order statistics for an even count)
         const bool has_nan = S.fin[0] != S.fin[0];
         double med = nan("");
@@ -739,6 +751,15 @@ __global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const Comb
         }
         if (tid == 0) { o[0] = S.fin[0] / m; o[1] = med; o[2] = sqrt(S.fin[1] / m); o[3] = (double)m; }
         __syncthreads();
+#ifdef GSF_GRID_CLK
+        if (blockIdx.x == 0 && (tid & 31) == 0) {       // own phase-1 time per warp, wait at the barrier, median (warp 0)
+            const long long c3 = clock64();
+            atomicAdd(&g_grid_clk[0], (unsigned long long)(c1 - c0));
+            atomicAdd(&g_grid_clk[1], (unsigned long long)(c2 - c1));
+            if (tid == 0) { atomicAdd(&g_grid_clk[2], (unsigned long long)(c3 - c2)); atomicAdd(&g_grid_clk[3], (unsigned long long)(c3 - c0)); atomicAdd(&g_grid_clk[4], 1ull); }
+            atomicMax(&g_grid_clk[5], (unsigned long long)(c1 - c0));
+        }
+#endif
     }
 }
 
@@ -817,6 +838,18 @@ cudaError_t launch_noise_grid(const double* ts, const double* pos, const double*
     grid_combine_kernel<<<(unsigned)blocks, CMB_THREADS, smem_cmb, stream>>>(ca);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+#ifdef GSF_GRID_CLK
+    {
+        unsigned long long hc[8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpyFromSymbol(hc, g_grid_clk, sizeof(hc));
+        const double nh = (double)(hc[4] ? hc[4] : 1);
+        fprintf(stderr, "[grid clk] block 0, %llu hypotheses: per hypothesis -- phase 1 own time, mean over warps %.0f; wait+reduce %.0f; median %.0f; total %.0f cycles; longest phase 1 of any warp %llu\n",
+                hc[4], hc[0] / nh / 32.0, hc[1] / nh / 32.0, hc[2] / nh, hc[3] / nh, hc[5]);
+        unsigned long long zero[8] = {0};
+        cudaMemcpyToSymbol(g_grid_clk, zero, sizeof(zero));
+    }
+#endif
     if (sim3_out) { e = cudaMemcpyAsync(sim3_out, R, 13 * sizeof(double), cudaMemcpyDeviceToDevice, stream); if (e != cudaSuccess) return e; }
     if (status_out) e = cudaMemcpyAsync(status_out, st, sizeof(int), cudaMemcpyDeviceToDevice, stream);
     return e;

@@ -69,6 +69,10 @@ int gsf_device_sm_count(void);
  *      init_pos/init_quat: NULL, or [B,3]/[B,4] to skip the Sim3 stage and start the filter
  *      from a given pose (the stand-alone apply_ekf_correction contract).
  *      sim3_out [B,16]: R(9, row-major) t(3) s n_selected n_valid n_residual_violators; may be NULL.
+ *      Sim3 here is the all-points Umeyama fit.  It equals compute_sim3_transform_robust (:389-426) whenever RANSAC's
+ *      best trial keeps every selected point; status bit GSF_ST_RANSAC_OUTLIERS (and n_residual_violators > 0) marks a
+ *      trajectory where a residual reaches residual_threshold, i.e. where the reference would have refitted on an
+ *      inlier subset: run gsf_sim3_ransac_dev + gsf_sim3_apply_dev and call again with init_pos / init_quat for it.
  *      max_len: largest trajectory length in the batch (sizes the shared-memory staging).  Any length is
  *      accepted: trajectories beyond the shared-memory staging (about 4000 poses) are streamed through
  *      shared memory in tiles by a third kernel (csrc/gsf_long.cu) behind the other two.

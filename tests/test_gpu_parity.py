@@ -4,6 +4,8 @@ Run on a B200:  python -m pytest tests -m gpu -x -q
 Tolerances (north_star: 1e-9 relative in fp64).  UTM-scale coordinates are ~5.4e6 m, where
 one fp64 ulp is 9.3e-10 m; positions are compared with an absolute tolerance of 2e-7 m
 (4e-14 relative), quaternions / rotations with 1e-9 absolute."""
+import os
+
 import numpy as np
 import pytest
 
@@ -270,6 +272,25 @@ def test_utm_kernels(gsf):
         assert int(z[2]) == zone and bool(z[3]) == south
         e, n = gsf.utm_forward(dev(raw[:, 2]), dev(raw[:, 1]), zone, south)
         np.testing.assert_allclose(np.column_stack((e.cpu().numpy(), n.cpu().numpy())), g["gps_utm"][:, :2], rtol=0, atol=2e-8)
+
+
+def test_utm_kernels_match_40_digit_fixture(gsf):
+    """K1 forward / inverse against tests/golden/utm_mp.npz: the projection's definition evaluated with mpmath at 40
+    digits (oracle/utm_mp.py; no coefficient table involved) on a +-3.5 deg x +-84 deg lattice in zones 1 / 32 / 39 / 60,
+    both hemispheres.  Tolerance: 3 ulp of the output coordinate (1 ulp = 1.9e-9 m at a 9.3e6 m northing)."""
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "utm_mp.npz"))
+    P = d["points"]
+    for zone in np.unique(P[:, 2]):
+        for south in (0.0, 1.0):
+            m = (P[:, 2] == zone) & (P[:, 3] == south)
+            if not m.any():
+                continue
+            e, n = gsf.utm_forward(dev(P[m, 0]), dev(P[m, 1]), int(zone), bool(south))
+            np.testing.assert_allclose(e.cpu().numpy(), P[m, 4], rtol=0, atol=6e-9)
+            np.testing.assert_allclose(n.cpu().numpy(), P[m, 5], rtol=0, atol=6e-9)
+            lon, lat = gsf.utm_inverse(dev(P[m, 4]), dev(P[m, 5]), int(zone), bool(south))
+            np.testing.assert_allclose(lon.cpu().numpy(), P[m, 0], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(lat.cpu().numpy(), P[m, 1], rtol=0, atol=1e-12)
 
 
 def test_fused_gnss_ingest_matches_loader_and_oracle(gsf):
@@ -639,6 +660,40 @@ def test_full_size_properties(gsf):
         assert float(err_f.cpu()) < float(err_s.cpu())
         ps, qs, _ = gsf.ekf_strict_batched(ts, pos, quat, z, off, prm, sp.reshape(B, n, 3)[:, 0].contiguous(), sq.reshape(B, n, 4)[:, 0].contiguous())
         assert float((ps - p).abs().max().cpu()) < POS_ATOL and float((qs - q).abs().max().cpu()) < ROT_ATOL
+
+
+def test_fuse_trajectory_falls_back_to_ransac_on_outliers(gsf):
+    """The single-launch path fits all selected points; with gross GNSS outliers in the Sim3 window the reference's
+    compute_sim3_transform_robust (EKFGPSSLAM.py:389-426) refits on an inlier subset.  fuse_trajectory must notice
+    (status bit 16) and take the explicit RANSAC route, so that it returns what main_process / the reference return:
+    compared with the oracle's RANSAC (same numpy seed -> same sample indices, :408) + EKF seeded with its pose 0."""
+    import EKFGPSSLAM as E
+    from gps_optimize_slam_b200 import _lib, synth
+    from oracle import fusion_oracle as fo
+    tr = synth.make_trajectory(77, n=271)
+    clean = E.fuse_trajectory({"timestamps": tr["ts"], "positions": tr["pos"], "quaternions": tr["quat"]}, tr["gps"])
+    assert clean["status"] == 0 and clean["sim3_path"].startswith("fused")
+    z = tr["gps"].copy()
+    for i in (20, 90, 150, 151, 230):
+        z[i] += np.array([35.0, -28.0, 12.0])
+    slam = {"timestamps": tr["ts"], "positions": tr["pos"], "quaternions": tr["quat"]}
+    np.random.seed(11)
+    out = E.fuse_trajectory(slam, z)
+    assert out["status"] & _lib.ST_RANSAC_OUTLIERS and out["sim3_path"].startswith("RANSAC")
+    cfg = fo.default_config(); rc = cfg["sim3_ransac"]
+    valid = np.ones(271, dtype=bool)
+    sel = fo.sim3_point_selection(tr["ts"], valid)
+    np.random.seed(11)
+    R, t, s = fo.sim3_ransac(tr["pos"][sel], z[sel], rc["min_samples"], rc["residual_threshold"], rc["max_trials"], rc["min_inliers_needed"])
+    sp, sq = fo.sim3_apply(tr["pos"], tr["quat"], R, t, s)
+    fp, fq = fo.ekf_fuse(tr["ts"], tr["pos"], tr["quat"], z, valid, sp[0], sq[0], cfg)
+    np.testing.assert_allclose(out["R"], R, rtol=0, atol=ROT_ATOL)
+    assert abs(out["s"] - s) < 1e-11
+    np.testing.assert_allclose(out["pos"], fp, rtol=0, atol=POS_ATOL)
+    np.testing.assert_allclose(out["quat"], fq, rtol=0, atol=ROT_ATOL)
+    # the all-points fit is visibly different here (that is what the flag protects against)
+    allpts = fo.umeyama(tr["pos"][sel], z[sel])
+    assert np.abs(allpts[1] - t).max() > 1e-3
 
 
 def test_dropin_entry_point(gsf, tmp_path):
