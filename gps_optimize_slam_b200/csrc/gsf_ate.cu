@@ -15,6 +15,7 @@
 // any length works -- the reference has no length limit either.
 #include "gsf_common.cuh"
 #include "gsf_internal.cuh"
+#include "gsf_select.cuh"
 
 namespace gsf {
 
@@ -26,7 +27,7 @@ constexpr int ATE_NB = 1024;             // bins along the dominant axis
 struct AteShared {
     int bin[ATE_NB + 1];
     int cursor[ATE_NB];
-    unsigned int hist[256];
+    SelectShared<ATE_T, 4> sel;
     double red[4 * ATE_NW];
     unsigned long long kmin, kmax, above;
     unsigned int rank, le_count;
@@ -187,61 +188,12 @@ __global__ void __launch_bounds__(ATE_T) ate_nn_kernel(const AteArgs A) {
         if (lane == 0) { atomicMin(&S.kmin, kmn); atomicMax(&S.kmax, kmx); }
         __syncthreads();
 
-        // ---- median: radix selection of rank (m - 1) / 2, then its upper neighbour for an even count
+        // ---- median: exact selection of rank (m - 1) / 2 and, for an even count, its upper neighbour (gsf_select.cuh)
         double med = nan("");
         if (!S.any_nan) {
-            const unsigned long long diff = S.kmin ^ S.kmax;
-            const int first = diff ? (__clzll((long long)diff) >> 3) : 8;      // bytes above `first` are common to every key
-            if (tid == 0) { S.prefix = first == 0 ? 0ull : (S.kmin & (~0ull << (64 - 8 * first))); S.rank = (unsigned)((m - 1) / 2); }
-            __syncthreads();
-            for (int d = first; d < 8; ++d) {
-                const int shift = 56 - 8 * d;
-                S.hist[tid] = 0u;
-                __syncthreads();
-                const unsigned long long himask = d == 0 ? 0ull : (~0ull << (64 - 8 * d));
-                const unsigned long long pf = S.prefix;
-                for (int k = tid; k < m; k += ATE_T) {
-                    const unsigned long long key = ate_key(err[k]);
-                    if ((key & himask) == pf) atomicAdd(&S.hist[(unsigned)(key >> shift) & 255u], 1u);
-                }
-                __syncthreads();
-                if (warp == 0) {                                           // 8 bins per lane, shuffle scan, owner lane walks its bins
-                    unsigned c8[8], tot = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { c8[k] = S.hist[8 * lane + k]; tot += c8[k]; }
-                    const unsigned r = S.rank;
-                    unsigned inc = tot;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) { const unsigned y = __shfl_up_sync(GSF_FULL_MASK, inc, off); if (lane >= off) inc += y; }
-                    const unsigned exc = inc - tot;
-                    if ((r >= exc && r < inc) || (lane == 31 && r >= inc)) {
-                        unsigned acc = exc; int bin = 0;
-                        for (; bin < 7; ++bin) { if (acc + c8[bin] > r) break; acc += c8[bin]; }
-                        S.rank = r - acc;
-                        S.prefix = pf | ((unsigned long long)(8 * lane + bin) << shift);
-                    }
-                }
-                __syncthreads();
-            }
-            const unsigned long long klo = S.prefix;
-            const double lo_v = __longlong_as_double((long long)klo);
-            med = lo_v;
-            if (!(m & 1)) {
-                // rank m/2 = rank (m-1)/2 + 1: the same value if it is repeated often enough, else the smallest key above it
-                unsigned le = 0; unsigned long long ab = ~0ull;
-                for (int k = tid; k < m; k += ATE_T) {
-                    const unsigned long long key = ate_key(err[k]);
-                    if (key <= klo) ++le; else ab = min(ab, key);
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    le += __shfl_xor_sync(GSF_FULL_MASK, le, off); ab = min(ab, __shfl_xor_sync(GSF_FULL_MASK, ab, off));
-                }
-                if (lane == 0) { atomicAdd(&S.le_count, le); atomicMin(&S.above, ab); }
-                __syncthreads();
-                const double hi_v = (S.le_count >= (unsigned)(m / 2 + 1)) ? lo_v : __longlong_as_double((long long)S.above);
-                med = 0.5 * (lo_v + hi_v);
-            }
+            const double mu = v2[0] / m, var = v2[1] / m - mu * mu, sg = var > 0.0 ? sqrt(var) : 0.0;
+            block_select<ATE_T, 4>(S.sel, err, m, (unsigned)((m - 1) / 2), !(m & 1), S.kmin, S.kmax, mu - sg, mu + sg);
+            med = (m & 1) ? S.sel.v0 : 0.5 * (S.sel.v0 + S.sel.v1);
         }
         if (tid == 0) {
             o[0] = v2[0] / m; o[1] = med; o[2] = sqrt(v2[1] / m); o[3] = (double)m;

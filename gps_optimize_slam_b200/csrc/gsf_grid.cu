@@ -22,6 +22,7 @@
 #include "gsf_common.cuh"
 #include "gsf_ptx.cuh"
 #include "gsf_internal.cuh"
+#include "gsf_select.cuh"
 
 namespace gsf {
 
@@ -432,12 +433,14 @@ __global__ void __launch_bounds__(TRK_THREADS) grid_tracks_kernel(const double* 
     }
 }
 
-// Candidate order for the combine kernel: own[k] = pose of the k-th candidate (x order), hgap[k] = a quarter of the
-// squared distance from candidate k to its nearest other candidate.  Triangle inequality: a query closer than half that
-// distance to its own measurement cannot have another candidate nearer, so the scan is skipped for it.
+// Candidate order for the combine kernel: own[k] = pose of the k-th candidate (x order); hgap[2k], hgap[2k+1] = a quarter of
+// the squared distance from candidate k to its nearest / third nearest other candidate; near2[2k..] = its two nearest.
+// Triangle inequality: a query at distance e from its own measurement z_k can only be beaten by candidates
+// within 2e of z_k -- none if e is under half the nearest distance, at most the two nearest if under half the third.
 __global__ void __launch_bounds__(256) grid_prep_order_kernel(const double* __restrict__ rec, const double* __restrict__ cand,
                                                               const double* __restrict__ hdr, int n, int* __restrict__ own,
-                                                              double* __restrict__ hgap, const int* __restrict__ status) {
+                                                              float* __restrict__ hgap, unsigned short* __restrict__ near2,
+                                                              const int* __restrict__ status) {
     if (status[0] & GRID_FATAL) return;
     const int m = (int)hdr[3];
     if ((int)hdr[4] != m) return;
@@ -446,21 +449,23 @@ __global__ void __launch_bounds__(256) grid_prep_order_kernel(const double* __re
         if (r >= 0) own[r] = i;
     }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+        // the three nearest other candidates of candidate k (pruned scan in x order)
         const double x0 = cand[3 * k], x1 = cand[3 * k + 1], x2 = cand[3 * k + 2];
-        double best = INFINITY;
-        for (int c = k - 1; c >= 0; --c) {
-            const double dx = x0 - cand[3 * c];
-            if (dx * dx >= best) break;
-            const double dy = x1 - cand[3 * c + 1], dz = x2 - cand[3 * c + 2];
-            best = fmin(best, dist2_rn(dx, dy, dz));
-        }
-        for (int c = k + 1; c < m; ++c) {
-            const double dx = cand[3 * c] - x0;
-            if (dx * dx >= best) break;
-            const double dy = x1 - cand[3 * c + 1], dz = x2 - cand[3 * c + 2];
-            best = fmin(best, dist2_rn(dx, dy, dz));
-        }
-        hgap[k] = best < INFINITY ? 0.25 * best * (1.0 - 1e-12) : 0.0;        // rounding margin; one candidate only: never skip (harmless)
+        double b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+        int i1 = k, i2 = k;
+        auto take = [&](int c) {
+            const double d = dist2_rn(x0 - cand[3 * c], x1 - cand[3 * c + 1], x2 - cand[3 * c + 2]);
+            if (d < b1) { b3 = b2; b2 = b1; i2 = i1; b1 = d; i1 = c; }
+            else if (d < b2) { b3 = b2; b2 = d; i2 = c; }
+            else if (d < b3) b3 = d;
+        };
+        for (int c = k - 1; c >= 0; --c) { const double dx = x0 - cand[3 * c]; if (dx * dx >= b3) break; take(c); }
+        for (int c = k + 1; c < m; ++c) { const double dx = cand[3 * c] - x0; if (dx * dx >= b3) break; take(c); }
+        // skip bounds, rounded down: a query within half the distance to the nearest other candidate keeps its own measurement;
+        // within half the distance to the third nearest, only the two nearest need a look
+        hgap[2 * k] = b1 < INFINITY ? __double2float_rd(0.25 * b1 * (1.0 - 1e-6)) : 0.0f;
+        hgap[2 * k + 1] = b3 < INFINITY ? __double2float_rd(0.25 * b3 * (1.0 - 1e-6)) : 0.0f;
+        near2[2 * k] = (unsigned short)i1; near2[2 * k + 1] = (unsigned short)i2;
     }
 }
 // Second scan order for the combine kernel.  The 1-D pruning of an x-sorted scan degenerates where the track runs along y
@@ -522,9 +527,8 @@ __device__ unsigned long long g_grid_clk[8];
 #endif
 constexpr int CMB_THREADS = 1024;
 constexpr int CMB_GROUP = 8;          // q_xy values per loop group: their 2 x 8 x Kr x/y rows stay L2-resident across the q_z loop
-constexpr int CMB_BINS = 1024;        // linear bins of the median selection (one per thread)
 struct CombineArgs {
-    const double* cand; const double* hgap; const double* hdr; const double* tracks; long long npad;
+    const double* cand; const float* hgap; const unsigned short* near2; const double* hdr; const double* tracks; long long npad;
     const unsigned short* yperm; const unsigned short* yrank;
     int n, Kz, Kr, iq0, nq, iz0, nz;
     long long h_first, h_count;
@@ -533,112 +537,78 @@ struct CombineArgs {
 struct CmbShared {
     double red[2][32];
     unsigned long long redk[2][32];
-    unsigned int hist[CMB_BINS];
-    unsigned int wtot[32];
-    unsigned long long list[64];
-    double fin[2], lo, hi, sel_lo, sel_w, v0, v1;
-    unsigned int rank, lcount, below, cnt, level, done, le_count;
-    unsigned long long above;
+    double fin[2];
+    unsigned long long klo, khi;
+    SelectShared<CMB_THREADS, 1> sel;
 };
-// value of 0-based rank `r` among err[0..m): linear bins between the running bounds, narrowed level by level; the bin index
-// is a monotone function of the value, so order statistics are exact.  Leaves S.v0 (the value) and S.le_count
-// (how many elements are <= it) / S.above (smallest key above it) for the caller.
-__device__ __forceinline__ int cmb_bin(double e, double lo, double scale) {
-    const double t = (e - lo) * scale;
-    return t < (double)(CMB_BINS - 1) ? (t > 0.0 ? (int)t : 0) : CMB_BINS - 1;
-}
-__device__ void cmb_select(CmbShared& S, const double* __restrict__ err, int m, unsigned r, int tid, int lane, int warp) {
-    // level state: elements with value in [lo_cur, hi_cur] by bin chain; here the chain is kept as an explicit value interval
-    // [a, b] of *keys* (bit patterns), which is exact: after choosing a bin we take the min / max keys of its members.
-    unsigned long long ka = __double_as_longlong(S.lo), kb = __double_as_longlong(S.hi);
-    unsigned rank = r;
-    for (int level = 0; level < 12; ++level) {
-        const double a = __longlong_as_double((long long)ka), b = __longlong_as_double((long long)kb);
-        if (ka == kb) { if (tid == 0) S.v0 = a; __syncthreads(); return; }
-        const double scale = (double)CMB_BINS / (b - a);
-        S.hist[tid] = 0u;
-        if (tid == 0) { S.lcount = 0u; }
-        __syncthreads();
-        for (int k = tid; k < m; k += CMB_THREADS) {
-            const unsigned long long key = (unsigned long long)__double_as_longlong(err[k]);
-            if (key >= ka && key <= kb) atomicAdd(&S.hist[cmb_bin(err[k], a, scale)], 1u);
+// Exact pruned nearest-neighbour scan around candidate k: outwards in x order (or in y order where the track runs along y)
+// while the 1-D gap alone can still beat the best squared distance.
+__device__ __forceinline__ double full_scan(const double* __restrict__ cs, const unsigned short* __restrict__ yp,
+                                            const unsigned short* __restrict__ yr, int m, int k, double x0, double x1, double x2, double best) {
+    double dx, dy, dz;
+    const int jr = yr[k];
+    if (jr == 0xFFFF) {
+        for (int c = k - 1; c >= 0; --c) {
+            dx = x0 - cs[3 * c];
+            if (dx > 0.0 && dx * dx >= best) break;
+            dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
+            best = fmin(best, dist2_rn(dx, dy, dz));
         }
-        __syncthreads();
-        // exclusive scan over the 1024 bins (one per thread)
-        const unsigned c = S.hist[tid];
-        unsigned inc = c;
-#pragma unroll
-        for (int ofs = 1; ofs < 32; ofs <<= 1) { const unsigned y = __shfl_up_sync(GSF_FULL_MASK, inc, ofs); if (lane >= ofs) inc += y; }
-        if (lane == 31) S.wtot[warp] = inc;
-        __syncthreads();
-        unsigned pre = 0;
-        for (int w = 0; w < warp; ++w) pre += S.wtot[w];
-        const unsigned exc = pre + inc - c;
-        if (c > 0 && rank >= exc && rank < exc + c) { S.rank = rank - exc; S.cnt = c; S.level = (unsigned)tid; }
-        __syncthreads();
-        const int bin = (int)S.level;
-        const unsigned cnt = S.cnt;
-        rank = S.rank;
-        if (cnt <= 64u) {
-            // gather the members of the bin and pick the rank by counting
-            for (int k = tid; k < m; k += CMB_THREADS) {
-                const unsigned long long key = (unsigned long long)__double_as_longlong(err[k]);
-                if (key >= ka && key <= kb && cmb_bin(err[k], a, scale) == bin) { const unsigned sl = atomicAdd(&S.lcount, 1u); S.list[sl] = key; }
-            }
-            __syncthreads();
-            if (tid < (int)cnt) {
-                const unsigned long long xk = S.list[tid];
-                unsigned less = 0;
-                for (unsigned q = 0; q < cnt; ++q) { const unsigned long long yk = S.list[q]; less += (yk < xk || (yk == xk && q < (unsigned)tid)) ? 1u : 0u; }
-                if (less == rank) S.v0 = __longlong_as_double((long long)xk);
-            }
-            __syncthreads();
-            return;
+        for (int c = k + 1; c < m; ++c) {
+            dx = cs[3 * c] - x0;
+            if (dx > 0.0 && dx * dx >= best) break;
+            dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
+            best = fmin(best, dist2_rn(dx, dy, dz));
         }
-        // narrow to the bin: its members' smallest and largest keys become the new interval
-        unsigned long long lo2 = ~0ull, hi2 = 0ull;
-        for (int k = tid; k < m; k += CMB_THREADS) {
-            const unsigned long long key = (unsigned long long)__double_as_longlong(err[k]);
-            if (key >= ka && key <= kb && cmb_bin(err[k], a, scale) == bin) { lo2 = min(lo2, key); hi2 = max(hi2, key); }
+    } else {
+        for (int j = jr - 1; j >= 0; --j) {
+            const int c = yp[j];
+            dy = x1 - cs[3 * c + 1];
+            if (dy > 0.0 && dy * dy >= best) break;
+            dx = x0 - cs[3 * c]; dz = x2 - cs[3 * c + 2];
+            best = fmin(best, dist2_rn(dx, dy, dz));
         }
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) { lo2 = min(lo2, __shfl_xor_sync(GSF_FULL_MASK, lo2, ofs)); hi2 = max(hi2, __shfl_xor_sync(GSF_FULL_MASK, hi2, ofs)); }
-        if (lane == 0) { S.redk[0][warp] = lo2; S.redk[1][warp] = hi2; }
-        __syncthreads();
-        lo2 = S.redk[0][lane]; hi2 = S.redk[1][lane];
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) { lo2 = min(lo2, __shfl_xor_sync(GSF_FULL_MASK, lo2, ofs)); hi2 = max(hi2, __shfl_xor_sync(GSF_FULL_MASK, hi2, ofs)); }
-        ka = lo2; kb = hi2;
-        __syncthreads();
+        for (int j = jr + 1; j < m; ++j) {
+            const int c = yp[j];
+            dy = cs[3 * c + 1] - x1;
+            if (dy > 0.0 && dy * dy >= best) break;
+            dx = x0 - cs[3 * c]; dz = x2 - cs[3 * c + 2];
+            best = fmin(best, dist2_rn(dx, dy, dz));
+        }
     }
-    if (tid == 0) S.v0 = __longlong_as_double((long long)ka);           // not reached: 12 levels of 1024 bins exceed 2^64 keys
-    __syncthreads();
+    return best;
 }
 __global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const CombineArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = (int)A.hdr[3];
+    __shared__ CmbShared S;
     double* const cs = reinterpret_cast<double*>(smem_raw);              // candidates [m,3], x-sorted
     double* const err = cs + 3 * (size_t)m;                              // errors [m], candidate order
-    double* const hg = err + m;                                          // skip bound [m]
-    unsigned short* const yp = reinterpret_cast<unsigned short*>(hg + m);          // y order -> x-rank [m]
+    float* const hg = reinterpret_cast<float*>(err + m);                 // skip bounds [m,2]
+    unsigned short* const nn = reinterpret_cast<unsigned short*>(hg + 2 * (size_t)m);      // two nearest other candidates [m,2]
+    unsigned short* const yp = nn + 2 * (size_t)m + ((2 * m) & 1 ? 1 : 0);         // y order -> x-rank [m]
     unsigned short* const yr = yp + ((m + 3) & ~3);                      // x-rank -> position in y order, 0xFFFF: scan in x order
-    __shared__ CmbShared S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long total_slots = (long long)((A.nq + CMB_GROUP - 1) / CMB_GROUP) * CMB_GROUP * A.Kz * A.Kr;
     const bool dead = (A.status[0] & GRID_FATAL) || (int)A.hdr[4] != m || m == 0;
     if (!dead) {
         for (int k = tid; k < 3 * m; k += CMB_THREADS) cs[k] = A.cand[k];
-        for (int k = tid; k < m; k += CMB_THREADS) { hg[k] = A.hgap[k]; yp[k] = A.yperm[k]; yr[k] = A.yrank[k]; }
+        for (int k = tid; k < m; k += CMB_THREADS) {
+            hg[2 * k] = A.hgap[2 * k]; hg[2 * k + 1] = A.hgap[2 * k + 1]; nn[2 * k] = A.near2[2 * k]; nn[2 * k + 1] = A.near2[2 * k + 1];
+            yp[k] = A.yperm[k]; yr[k] = A.yrank[k];
+        }
     }
     __syncthreads();
     const int nxy = A.nq * A.Kr;
     for (long long slot = blockIdx.x; slot < total_slots; slot += gridDim.x) {
         // slot -> (q_xy, q_z, r): groups of CMB_GROUP q_xy values outermost, then q_z, then r, q_xy within the group innermost
-        const long long per_group = (long long)CMB_GROUP * A.Kz * A.Kr;
-        const int g = (int)(slot / per_group);
-        const int sg = (int)(slot - (long long)g * per_group);
-        const int iql = g * CMB_GROUP + sg % CMB_GROUP;                  // q_xy index relative to iq0
-        const int ir = (sg / CMB_GROUP) % A.Kr, iz = sg / (CMB_GROUP * A.Kr);
+        // (32-bit arithmetic: the launcher refuses grids beyond 2^31 slots)
+        const unsigned per_group = (unsigned)(CMB_GROUP * A.Kz * A.Kr);
+        const unsigned us = (unsigned)slot;
+        const int g = (int)(us / per_group);
+        const unsigned sg = us - (unsigned)g * per_group;
+        const int iql = g * CMB_GROUP + (int)(sg % CMB_GROUP);           // q_xy index relative to iq0
+        const int ir = (int)((sg / CMB_GROUP) % (unsigned)A.Kr), iz = (int)(sg / (unsigned)(CMB_GROUP * A.Kr));
         if (iql >= A.nq) continue;
         const long long h = ((long long)(A.iq0 + iql) * A.Kz + iz) * A.Kr + ir;
         if (h < A.h_first || h >= A.h_first + A.h_count || iz < A.iz0 || iz >= A.iz0 + A.nz) continue;
@@ -650,54 +620,36 @@ __global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const Comb
 #ifdef GSF_GRID_CLK
         long long c0 = clock64();
 #endif
-        // ---- phase 1: nearest-neighbour error of every evaluated pose (:1028-1031), exact and pruned; queries in candidate order
+        // ---- phase 1: nearest-neighbour error of every evaluated pose (:1028-1031), exact and pruned; queries in candidate order.
+        // Three tiers by the triangle inequality: own measurement only / the two nearest of z_k / a full pruned scan.
+        // (Queueing the rare full scans for a second, dense pass -- a single one stalls its warp -- measured slower than
+        // leaving them in place: 26.0 vs 23.4 ms; the extra sweeps over err[] cost more than the divergence.)
         double se = 0.0, se2 = 0.0;
         unsigned long long klo = ~0ull, khi = 0ull;
-        for (int k = tid; k < m; k += CMB_THREADS) {
-            const double x0 = __ldg(tx + k), x1 = __ldg(ty + k), x2 = __ldg(tz + k);
-            double dx = x0 - cs[3 * k], dy = x1 - cs[3 * k + 1], dz = x2 - cs[3 * k + 2];
-            double best = dist2_rn(dx, dy, dz);
-            if (!(best < hg[k])) {                                       // another candidate may be nearer than the own measurement
-                const int jr = yr[k];
-                if (jr == 0xFFFF) {                                      // scan outwards in x order while the 1-D gap alone can still win
-                    for (int c = k - 1; c >= 0; --c) {
-                        dx = x0 - cs[3 * c];
-                        if (dx > 0.0 && dx * dx >= best) break;
-                        dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
-                        best = fmin(best, dist2_rn(dx, dy, dz));
-                    }
-                    for (int c = k + 1; c < m; ++c) {
-                        dx = cs[3 * c] - x0;
-                        if (dx > 0.0 && dx * dx >= best) break;
-                        dy = x1 - cs[3 * c + 1]; dz = x2 - cs[3 * c + 2];
-                        best = fmin(best, dist2_rn(dx, dy, dz));
-                    }
-                } else {                                                 // the track runs along y here: the same in y order
-                    for (int j = jr - 1; j >= 0; --j) {
-                        const int c = yp[j];
-                        dy = x1 - cs[3 * c + 1];
-                        if (dy > 0.0 && dy * dy >= best) break;
-                        dx = x0 - cs[3 * c]; dz = x2 - cs[3 * c + 2];
-                        best = fmin(best, dist2_rn(dx, dy, dz));
-                    }
-                    for (int j = jr + 1; j < m; ++j) {
-                        const int c = yp[j];
-                        dy = cs[3 * c + 1] - x1;
-                        if (dy > 0.0 && dy * dy >= best) break;
-                        dx = x0 - cs[3 * c]; dz = x2 - cs[3 * c + 2];
-                        best = fmin(best, dist2_rn(dx, dy, dz));
-                    }
+        {
+            int k = tid;
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+            if (k < m) { x0 = __ldg(tx + k); x1 = __ldg(ty + k); x2 = __ldg(tz + k); }
+            while (k < m) {
+                const int kn = k + CMB_THREADS;
+                double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+                if (kn < m) { n0 = __ldg(tx + kn); n1 = __ldg(ty + kn); n2 = __ldg(tz + kn); }      // next query's track values (L2 latency)
+                double best = dist2_rn(x0 - cs[3 * k], x1 - cs[3 * k + 1], x2 - cs[3 * k + 2]);
+                if (!(best < (double)hg[2 * k])) {                       // another candidate may be nearer than the own measurement
+                    if (best < (double)hg[2 * k + 1]) {                  // ... but only one of the two nearest of z_k
+                        const int c1 = nn[2 * k], c2 = nn[2 * k + 1];
+                        best = fmin(best, dist2_rn(x0 - cs[3 * c1], x1 - cs[3 * c1 + 1], x2 - cs[3 * c1 + 2]));
+                        best = fmin(best, dist2_rn(x0 - cs[3 * c2], x1 - cs[3 * c2 + 1], x2 - cs[3 * c2 + 2]));
+                    } else best = full_scan(cs, yp, yr, m, k, x0, x1, x2, best);
                 }
+                const double e = sqrt(best);
+                err[k] = e;
+                se += e; se2 += e * e;
+                const unsigned long long key = (unsigned long long)__double_as_longlong(e);      // e >= 0 or NaN: patterns order like the values
+                klo = min(klo, key); khi = max(khi, key);
+                k = kn; x0 = n0; x1 = n1; x2 = n2;
             }
-            const double e = sqrt(best);
-            err[k] = e;
-            se += e; se2 += e * e;
-            const unsigned long long key = (unsigned long long)__double_as_longlong(e);      // e >= 0 or NaN: patterns order like the values
-            klo = min(klo, key); khi = max(khi, key);
         }
-#ifdef GSF_GRID_CLK
-        long long c1 = clock64();
-#endif
         // fixed-order block reduction (lane tree, then warp tree)
 #pragma unroll
         for (int ofs = 16; ofs > 0; ofs >>= 1) {
@@ -714,40 +666,20 @@ __global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const Comb
                 a += __shfl_xor_sync(GSF_FULL_MASK, a, ofs); b += __shfl_xor_sync(GSF_FULL_MASK, b, ofs);
                 lo = min(lo, __shfl_xor_sync(GSF_FULL_MASK, lo, ofs)); hi = max(hi, __shfl_xor_sync(GSF_FULL_MASK, hi, ofs));
             }
-            if (lane == 0) { S.fin[0] = a; S.fin[1] = b; S.lo = __longlong_as_double((long long)lo); S.hi = __longlong_as_double((long long)hi); }
+            if (lane == 0) { S.fin[0] = a; S.fin[1] = b; S.klo = lo; S.khi = hi; }
         }
         __syncthreads();
 #ifdef GSF_GRID_CLK
         long long c2 = clock64();
 #endif
-        // ---- phase 2: exact median (np.median: mean of the two middle order statistics for an even count)
+        // ---- phase 2: exact median (np.median: mean of the two middle order statistics for an even count); the median of any
+        //      sample lies within one standard deviation of its mean, which brackets the first level of the selection
         const bool has_nan = S.fin[0] != S.fin[0];
         double med = nan("");
         if (!has_nan) {
-            cmb_select(S, err, m, (unsigned)((m - 1) / 2), tid, lane, warp);
-            const double v0 = S.v0;
-            med = v0;
-            if (!(m & 1)) {
-                // rank m/2: v0 again if enough elements are <= v0, else the smallest element above it
-                unsigned le = 0; unsigned long long ab = ~0ull;
-                const unsigned long long k0 = (unsigned long long)__double_as_longlong(v0);
-                for (int k = tid; k < m; k += CMB_THREADS) {
-                    const unsigned long long key = (unsigned long long)__double_as_longlong(err[k]);
-                    if (key <= k0) ++le; else ab = min(ab, key);
-                }
-#pragma unroll
-                for (int ofs = 16; ofs > 0; ofs >>= 1) { le += __shfl_xor_sync(GSF_FULL_MASK, le, ofs); ab = min(ab, __shfl_xor_sync(GSF_FULL_MASK, ab, ofs)); }
-                if (lane == 0) { S.wtot[warp] = le; S.redk[0][warp] = ab; }
-                __syncthreads();
-                if (warp == 0) {
-                    le = S.wtot[lane]; ab = S.redk[0][lane];
-#pragma unroll
-                    for (int ofs = 16; ofs > 0; ofs >>= 1) { le += __shfl_xor_sync(GSF_FULL_MASK, le, ofs); ab = min(ab, __shfl_xor_sync(GSF_FULL_MASK, ab, ofs)); }
-                    if (lane == 0) S.v1 = le > (unsigned)(m / 2) ? v0 : __longlong_as_double((long long)ab);
-                }
-                __syncthreads();
-                med = 0.5 * (v0 + S.v1);
-            }
+            const double mu = S.fin[0] / m, var = S.fin[1] / m - mu * mu, sg = var > 0.0 ? sqrt(var) : 0.0;
+            block_select<CMB_THREADS, 1>(S.sel, err, m, (unsigned)((m - 1) / 2), !(m & 1), S.klo, S.khi, mu - sg, mu + sg);
+            med = (m & 1) ? S.sel.v0 : 0.5 * (S.sel.v0 + S.sel.v1);
         }
         if (tid == 0) { o[0] = S.fin[0] / m; o[1] = med; o[2] = sqrt(S.fin[1] / m); o[3] = (double)m; }
         __syncthreads();
@@ -774,7 +706,7 @@ static void noise_grid_ranges(int Kz, int Kr, long long h_first, long long h_cou
     else { iz0 = 0; nz = Kz; }
 }
 static long long noise_grid_head_doubles(long long n) {
-    return 16 + 16 + 2 + 2 + 8 * n + 3 * n + (long long)sim3_tiles_for(n) * 20 + (n + 7) / 8 + 4 + (n + 1) / 2 + n + 2 * ((n + 3) / 4) + 8;
+    return 16 + 16 + 2 + 2 + 8 * n + 3 * n + (long long)sim3_tiles_for(n) * 20 + (n + 7) / 8 + 4 + (n + 1) / 2 + n + (n + 1) / 2 + 2 * ((n + 3) / 4) + 8;
 }
 long long noise_grid_work_doubles(long long n, int Kq, int Kz, int Kr, long long h_first, long long h_count) {
     (void)Kq;
@@ -798,8 +730,9 @@ cudaError_t launch_noise_grid(const double* ts, const double* pos, const double*
     unsigned char* mask = reinterpret_cast<unsigned char*>(uwork + (size_t)sim3_tiles_for(n) * 20);
     double* after = reinterpret_cast<double*>(mask) + (n + 7) / 8 + 4;
     int* own = reinterpret_cast<int*>(after);
-    double* hgap = after + (n + 1) / 2;
-    unsigned short* yperm = reinterpret_cast<unsigned short*>(hgap + n);
+    float* hgap = reinterpret_cast<float*>(after + (n + 1) / 2);                   // [n,2] floats = n doubles
+    unsigned short* near2 = reinterpret_cast<unsigned short*>(after + (n + 1) / 2 + n);      // [n,2] = (n + 1) / 2 doubles
+    unsigned short* yperm = near2 + 4 * ((n + 1) / 2);
     unsigned short* yrank = yperm + 4 * ((n + 3) / 4);
     double* tracks = work + noise_grid_head_doubles(n);
     tracks = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(tracks) + 31) & ~(uintptr_t)31);
@@ -808,15 +741,16 @@ cudaError_t launch_noise_grid(const double* ts, const double* pos, const double*
     noise_grid_ranges(Kz, Kr, h_first, h_count, iq0, nq, iz0, nz);
     const int cap2 = pow2_at_least(n);
     const size_t smem_prep = (size_t)cap2 * 12;
-    const size_t smem_cmb = (size_t)n * 44 + 64;                           // candidates 24 + errors 8 + skip bound 8 + y order 4 per pose
-    if (smem_prep > (size_t)max_smem || smem_cmb > (size_t)max_smem || (size_t)n * 8 > (size_t)max_smem || n > 65535) return cudaErrorInvalidValue;
+    const size_t smem_cmb = (size_t)n * 48 + 64;                           // candidates 24 + errors 8 + skip bounds 8 + two nearest 4 + y order 4 per pose
+    if (smem_prep > (size_t)max_smem || smem_cmb > (size_t)max_smem || (size_t)n * 8 > (size_t)max_smem || n > 65535 ||
+        (long long)((nq + CMB_GROUP - 1) / CMB_GROUP) * CMB_GROUP * Kz * Kr > 0x7fffffffll) return cudaErrorInvalidValue;
     grid_prep_select_kernel<<<1, 1024, 0, stream>>>(ts, z, (int)n, base, mask, offsets2, st);
     cudaError_t e = launch_umeyama(pos, z, offsets2, mask, 1, n, uwork, R, t, s, st + 1, stream);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(grid_prep_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
     if (e != cudaSuccess) return e;
     grid_prep_records_kernel<<<1, 1024, smem_prep, stream>>>(ts, pos, quat, z, (int)n, base, R, t, s, rec, cand, hdr, st, cap2);
-    grid_prep_order_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(rec, cand, hdr, (int)n, own, hgap, st);
+    grid_prep_order_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(rec, cand, hdr, (int)n, own, hgap, near2, st);
     e = cudaFuncSetAttribute(grid_prep_ysort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
     if (e != cudaSuccess) return e;
     grid_prep_ysort_kernel<<<1, 1024, smem_prep, stream>>>(cand, z, hdr, (int)n, own, yperm, yrank, st, cap2);
@@ -829,7 +763,7 @@ cudaError_t launch_noise_grid(const double* ts, const double* pos, const double*
     if (e != cudaSuccess) return e;
     grid_permute_kernel<<<NT, 256, (size_t)n * 8, stream>>>(tracks, npad, (int)n, own, hdr, st);
     CombineArgs ca;
-    ca.cand = cand; ca.hgap = hgap; ca.hdr = hdr; ca.tracks = tracks; ca.npad = npad; ca.yperm = yperm; ca.yrank = yrank;
+    ca.cand = cand; ca.hgap = hgap; ca.near2 = near2; ca.hdr = hdr; ca.tracks = tracks; ca.npad = npad; ca.yperm = yperm; ca.yrank = yrank;
     ca.n = (int)n; ca.Kz = Kz; ca.Kr = Kr; ca.iq0 = iq0; ca.nq = nq; ca.iz0 = iz0; ca.nz = nz;
     ca.h_first = h_first; ca.h_count = h_count; ca.stats = stats; ca.status = st;
     e = cudaFuncSetAttribute(grid_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cmb);
