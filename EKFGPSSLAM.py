@@ -204,31 +204,48 @@ def auto_utm_projection(lons: np.ndarray, lats: np.ndarray) -> Tuple[int, str]:
     return int(out[2]), (" +south" if out[3] else "")
 
 
+def _window_inliers_device(t_dev, pos_dev, idx, config):
+    """One window of EKFGPSSLAM.py:204-219 on the device: per axis one gsf_poly_ransac_dev fit (sklearn's RANSACRegressor
+    loop).  The sample indices are drawn here exactly as sklearn draws them -- sample_without_replacement(n_window,
+    min_samples) per trial from numpy's global RNG (RANSACRegressor(random_state=None)) -- and after each fit the RNG is
+    rewound and advanced by the number of trials the fit really consumed, so that a seeded run of the reference and this
+    function see the same random stream.  Raises ValueError where sklearn would (no consensus set)."""
+    from sklearn.utils.random import sample_without_replacement
+    rng = np.random.mtrand._rand
+    nw, ms, max_trials = len(idx), int(config["min_samples"]), int(config["max_trials"])
+    widx = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int32)).to("cuda")
+    off = torch.tensor([0, nw], dtype=torch.int64, device="cuda")
+    dyn = torch.from_numpy(fusion.dynamic_max_trials_table(nw, ms, max_trials)).to("cuda")
+    dyn_off = torch.zeros(1, dtype=torch.int64, device="cuda")
+    keep = np.ones(nw, dtype=bool)
+    for axis in range(pos_dev.shape[1]):
+        state = rng.get_state()
+        samples = np.stack([sample_without_replacement(nw, ms, random_state=rng) for _ in range(max_trials)]).astype(np.int32)
+        mask, n_trials, status = fusion.poly_ransac(t_dev, pos_dev, widx, off, torch.tensor([axis], dtype=torch.int32, device="cuda"),
+                                                    torch.from_numpy(samples).to("cuda"), dyn, dyn_off, ms,
+                                                    int(config["polynomial_degree"]), max_trials, float(config["residual_threshold_meters"]))
+        used = int(n_trials.cpu()[0])
+        rng.set_state(state)
+        for _ in range(used):
+            sample_without_replacement(nw, ms, random_state=rng)
+        if int(status.cpu()[0]):
+            raise ValueError("RANSAC could not find a valid consensus set")
+        keep &= mask.cpu().numpy().astype(bool)
+    return keep
+
+
 def filter_gps_outliers_ransac(times, positions, config):
-    """EKFGPSSLAM.py:136-247.  Host-side and unseeded in the reference (sklearn RANSACRegressor);
-    outside the kernel scope (SURVEY 2, row "GPS outlier RANSAC").  Same windowing, same
-    sklearn estimators, when sklearn is importable."""
+    """EKFGPSSLAM.py:136-247: sliding-window (or global) polynomial RANSAC per axis; a point survives if it is an
+    inlier on all axes in at least one processed window.  The fits run on the device (gsf_poly_ransac_dev); the window
+    enumeration below is the reference's loop (index bookkeeping)."""
     if not config.get("enabled", False) or len(times) < config["min_samples"]:
         return times, positions
-    from sklearn.linear_model import RANSACRegressor
-    from sklearn.pipeline import make_pipeline
-    from sklearn.preprocessing import PolynomialFeatures
-
-    def inliers(t, xyz):
-        masks = []
-        for axis in range(xyz.shape[1]):
-            model = make_pipeline(PolynomialFeatures(degree=config["polynomial_degree"]),
-                                  RANSACRegressor(min_samples=config["min_samples"],
-                                                  residual_threshold=config["residual_threshold_meters"],
-                                                  max_trials=config["max_trials"]))
-            model.fit(t.reshape(-1, 1), xyz[:, axis])
-            masks.append(model[-1].inlier_mask_)
-        return np.logical_and.reduce(masks)
-
+    times = np.asarray(times, dtype=np.float64); positions = np.asarray(positions, dtype=np.float64)
+    t_dev, pos_dev = _dev(times), _dev(positions)
     if not config.get("use_sliding_window", False):
         try:
-            keep = inliers(times, positions)
-        except Exception:
+            keep = _window_inliers_device(t_dev, pos_dev, np.arange(len(times)), config)
+        except ValueError:
             return times, positions
         return times[keep], positions[keep]
     width = config["window_duration_seconds"]
@@ -240,8 +257,8 @@ def filter_gps_outliers_ransac(times, positions, config):
         idx = np.where((times >= start) & (times < stop))[0]
         if len(idx) >= config["min_samples"]:
             try:
-                keep[idx[inliers(times[idx], positions[idx])]] = True
-            except Exception:
+                keep[idx[_window_inliers_device(t_dev, pos_dev, idx, config)]] = True
+            except ValueError:
                 pass
         if step <= 1e-6:
             later = np.where(times > start)[0]

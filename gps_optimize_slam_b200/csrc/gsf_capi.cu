@@ -190,6 +190,23 @@ int gsf_ekf_noise_grid_dev(const double* ts, const double* pos, const double* qu
     return 0;
 }
 
+int gsf_poly_ransac_dev(const double* t, const double* y, int32_t y_stride, const int32_t* window_idx, const int64_t* fit_offsets,
+                        const int32_t* fit_axis, const int32_t* samples, const int32_t* dyn_trials, const int64_t* dyn_offsets,
+                        int32_t F, int32_t min_samples, int32_t degree, int32_t max_trials, double residual_threshold,
+                        uint8_t* inlier_mask, int32_t* n_trials, int32_t* status, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (F == 0) return 0;
+    if (F < 0 || !t || !y || y_stride < 1 || !window_idx || !fit_offsets || !fit_axis || !samples || !dyn_trials || !dyn_offsets ||
+        !inlier_mask || !n_trials || !status || max_trials < 1 || degree < 0 || degree > 3 || min_samples < degree + 1)
+        return fail(GSF_E_INVALID, "gsf_poly_ransac_dev: null pointer or bad size (degree <= 3, min_samples > degree)");
+    cudaError_t e = gsf::launch_poly_ransac(t, y, y_stride, window_idx, reinterpret_cast<const long long*>(fit_offsets), fit_axis, samples,
+                                            dyn_trials, reinterpret_cast<const long long*>(dyn_offsets), F, min_samples, degree, max_trials,
+                                            residual_threshold, inlier_mask, n_trials, status, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_poly_ransac_dev");
+    return 0;
+}
+
 int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,
                                const int64_t* offsets, int32_t B,
                                const gsf_fuse_params* params, int32_t params_per_traj,

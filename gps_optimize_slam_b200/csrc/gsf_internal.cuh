@@ -70,6 +70,8 @@ struct AteArgs {
 size_t ate_smem_bytes(int cap);
 int ate_smem_capacity(int max_smem);
 cudaError_t launch_ate(const AteArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_poly_ransac(const double*, const double*, int, const int*, const long long*, const int*, const int*, const int*,
+                               const long long*, int, int, int, int, double, unsigned char*, int*, int*, cudaStream_t);
 struct SynthArgs {
     double* ts; double* pos; double* quat; double* z;
     long long traj0; int B; int n; double dt; double speed; unsigned long long seed;

@@ -189,6 +189,46 @@ def noise_grid(ts, pos, quat, z, base_params, q_xy, q_z, r, h_first=0, h_count=N
     return stats, sim3, status
 
 
+def poly_ransac(t, y, window_idx, fit_offsets, fit_axis, samples, dyn_trials, dyn_offsets, min_samples, degree, max_trials,
+                residual_threshold, stream=None):
+    """Per-window polynomial RANSAC of the GNSS pre-filter (gsf_poly_ransac_dev, EKFGPSSLAM.py:136-247) for F fits.
+    t [N], y [N,C] device fp64; window_idx int32, fit_offsets int64 [F+1], fit_axis int32 [F], samples int32
+    [F, max_trials, min_samples], dyn_trials int32, dyn_offsets int64 [F] (all device).
+    Returns (inlier_mask uint8 [len(window_idx)], n_trials int32 [F], status int32 [F]); asynchronous."""
+    lib = _lib.load()
+    _require_cuda(t, y, window_idx, fit_offsets, fit_axis, samples, dyn_trials, dyn_offsets)
+    F = int(fit_axis.numel())
+    dev = t.device
+    mask = torch.empty((int(window_idx.numel()),), dtype=torch.uint8, device=dev)
+    n_trials = torch.empty((F,), dtype=torch.int32, device=dev)
+    status = torch.empty((F,), dtype=torch.int32, device=dev)
+    rc = lib.gsf_poly_ransac_dev(_ptr(t), _ptr(y), int(y.shape[1]) if y.dim() > 1 else 1, _ptr(window_idx), _ptr(fit_offsets), _ptr(fit_axis),
+                                 _ptr(samples), _ptr(dyn_trials), _ptr(dyn_offsets), F, int(min_samples), int(degree), int(max_trials),
+                                 float(residual_threshold), _ptr(mask), _ptr(n_trials), _ptr(status), _stream_ptr(stream))
+    _lib.check(rc, "gsf_poly_ransac_dev")
+    return mask, n_trials, status
+
+
+def dynamic_max_trials_table(n_window: int, min_samples: int, max_trials: int, probability: float = 0.99):
+    """sklearn's _dynamic_max_trials(n_inliers, n_window, min_samples, probability) for n_inliers = 0..n_window
+    (linear_model/_ransac.py), clipped to max_trials; int32 numpy array."""
+    import numpy as np
+    eps = np.spacing(1)
+    out = np.empty(n_window + 1, dtype=np.int32)
+    for k in range(n_window + 1):
+        ratio = k / float(n_window)
+        nom = max(eps, 1 - probability)
+        denom = max(eps, 1 - ratio ** min_samples)
+        if nom == 1:
+            v = 0.0
+        elif denom == 1:
+            v = float("inf")
+        else:
+            v = abs(float(np.ceil(np.log(nom) / np.log(denom))))
+        out[k] = int(min(v, max_trials))
+    return out
+
+
 def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, params_per_traj=False, stream=None):
     """Literal step-by-step EKF recursion, one thread per trajectory (gsf_ekf_strict_batched_dev)."""
     lib = _lib.load()

@@ -116,6 +116,21 @@ int gsf_ekf_noise_grid_dev(const double* ts, const double* pos, const double* qu
                            int32_t Kq, int32_t Kz, int32_t Kr, int64_t h_first, int64_t h_count,
                            double* work, double* stats, double* sim3_out, int32_t* status, void* stream);
 
+/* ---- GNSS outlier pre-filter: the per-window, per-axis polynomial RANSAC of filter_gps_outliers_ransac (:136-247), i.e.
+ *      sklearn's RANSACRegressor over PolynomialFeatures(degree) + LinearRegression (absolute loss, `<=` threshold, skip on
+ *      fewer inliers, R^2 tie-break, dynamic max_trials), for F independent fits in one launch.  Fit f covers the points
+ *      window_idx[fit_offsets[f] .. fit_offsets[f+1]) (indices into t / y) and the column fit_axis[f] of y (row stride
+ *      y_stride doubles).  samples [F, max_trials, min_samples]: HOST-SUPPLIED sample indices into the fit's window (what
+ *      sklearn draws with sample_without_replacement per trial); dyn_trials[dyn_offsets[f] + k] = sklearn's
+ *      _dynamic_max_trials(k, n_window, min_samples, 0.99) for k = 0..n_window, so the loop stops exactly where sklearn's
+ *      does.  Outputs: inlier_mask [fit_offsets[F]] (the best trial's), n_trials [F] (draws consumed), status [F]
+ *      (1: no consensus set, sklearn's ValueError -> the reference skips the window, :228).  The window enumeration
+ *      (:203-238), the AND over the axes and the OR over the windows (:216-219) are index bookkeeping of the caller. */
+int gsf_poly_ransac_dev(const double* t, const double* y, int32_t y_stride, const int32_t* window_idx, const int64_t* fit_offsets,
+                        const int32_t* fit_axis, const int32_t* samples, const int32_t* dyn_trials, const int64_t* dyn_offsets,
+                        int32_t F, int32_t min_samples, int32_t degree, int32_t max_trials, double residual_threshold,
+                        uint8_t* inlier_mask, int32_t* n_trials, int32_t* status, void* stream);
+
 /* ---- apply_ekf_correction (:831-935), literal step-by-step recursion, one thread per
  *      trajectory (general path; keeps the zero-motion fallback of :84-86). */
 int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,

@@ -36,6 +36,10 @@ DEFAULT_CONFIG = {
         "min_inliers_needed": 4,
         "max_initial_duration": 180.0,
     },
+    "gps_filtering_ransac": {            # EKFGPSSLAM.py:39-48
+        "enabled": True, "use_sliding_window": True, "window_duration_seconds": 15.0, "window_step_factor": 0.5,
+        "polynomial_degree": 2, "min_samples": 6, "residual_threshold_meters": 10.0, "max_trials": 50,
+    },
     "time_alignment": {"max_samples_for_corr": 500, "max_gps_gap_threshold": 5.0},
     "rts_decision": {
         "sharp_turn_yaw_rate_threshold_deg_per_sec": 45.0,
@@ -208,6 +212,101 @@ def sim3_ransac(src, dst, min_samples, residual_threshold, max_trials, min_inlie
     if best < min_inliers:
         return None, None, None
     return umeyama(src[best_mask], dst[best_mask])
+
+
+def _dynamic_max_trials(n_inliers, n_samples, min_samples, probability=0.99):
+    """sklearn/linear_model/_ransac.py:_dynamic_max_trials."""
+    eps = np.spacing(1)
+    ratio = n_inliers / float(n_samples)
+    nom = max(eps, 1 - probability)
+    denom = max(eps, 1 - ratio ** min_samples)
+    if nom == 1:
+        return 0
+    if denom == 1:
+        return float("inf")
+    return abs(float(np.ceil(np.log(nom) / np.log(denom))))
+
+
+def poly_ransac_fit(t, y, degree, min_samples, residual_threshold, max_trials, rng=None):
+    """One RANSACRegressor fit of the GNSS pre-filter (EKFGPSSLAM.py:206-216: PolynomialFeatures(degree) +
+    RANSACRegressor(min_samples, residual_threshold, max_trials)), sklearn's loop restated in numpy: absolute loss,
+    inliers = residual <= threshold, skip on fewer inliers, R^2 tie-break, dynamic max_trials.  The polynomial is fitted
+    in centred, scaled time (same polynomial space as sklearn's Vandermonde columns).  Draws the samples like sklearn:
+    sample_without_replacement from numpy's global RNG (``rng`` None).  Returns (inlier_mask, n_trials); raises
+    ValueError when no trial has an inlier (sklearn does)."""
+    from sklearn.utils.random import sample_without_replacement
+    rs = np.random.mtrand._rand if rng is None else rng
+    n = len(t)
+    n_best, score_best, mask_best = 1, -np.inf, None
+    trials, limit = 0, max_trials
+    while trials < limit:
+        trials += 1
+        pick = sample_without_replacement(n, min_samples, random_state=rs)
+        tm = t[pick].mean()
+        sc = np.abs(t[pick] - tm).max() or 1.0
+        u = (t[pick] - tm) / sc
+        V = np.vander(u, degree + 1, increasing=True)
+        coef, *_ = np.linalg.lstsq(V, y[pick] - y[pick][0], rcond=None)
+        pred = np.vander((t - tm) / sc, degree + 1, increasing=True) @ coef + y[pick][0]
+        mask = np.abs(y - pred) <= residual_threshold
+        cnt = int(mask.sum())
+        if cnt < n_best:
+            continue
+        yi = y[mask]
+        sst = ((yi - yi.mean()) ** 2).sum()
+        ssr = ((yi - pred[mask]) ** 2).sum()
+        score = 1.0 - ssr / sst if sst > 0 else (1.0 if ssr == 0 else 0.0)
+        if cnt == n_best and score < score_best:
+            continue
+        n_best, score_best, mask_best = cnt, score, mask
+        limit = min(limit, _dynamic_max_trials(n_best, n, min_samples))
+    if mask_best is None:
+        raise ValueError("RANSAC could not find a valid consensus set")
+    return mask_best, trials
+
+
+def gps_filter_ransac(times, positions, cfg, rng=None):
+    """filter_gps_outliers_ransac (EKFGPSSLAM.py:136-247): windows, per-axis fits, AND over the axes, OR over the
+    windows.  -> kept indices."""
+    n = len(times)
+    if not cfg.get("enabled", False) or n < cfg["min_samples"]:
+        return np.arange(n)
+
+    def inliers(idx):
+        keep = np.ones(len(idx), dtype=bool)
+        for axis in range(positions.shape[1]):
+            m, _ = poly_ransac_fit(times[idx], positions[idx, axis], cfg["polynomial_degree"], cfg["min_samples"],
+                                   cfg["residual_threshold_meters"], cfg["max_trials"], rng)
+            keep &= m
+        return keep
+
+    if not cfg.get("use_sliding_window", False):
+        try:
+            return np.flatnonzero(inliers(np.arange(n)))
+        except ValueError:
+            return np.arange(n)
+    width = cfg["window_duration_seconds"]
+    step = width * cfg["window_step_factor"]
+    keep = np.zeros(n, dtype=bool)
+    start, t_end = times[0], times[-1]
+    while start < t_end:
+        stop = start + width
+        idx = np.where((times >= start) & (times < stop))[0]
+        if len(idx) >= cfg["min_samples"]:
+            try:
+                keep[idx[inliers(idx)]] = True
+            except ValueError:
+                pass
+        if step <= 1e-6:
+            later = np.where(times > start)[0]
+            if len(later) == 0:
+                break
+            start = times[later[0]]
+        else:
+            start += step
+        if start >= t_end and times[-1] >= stop:
+            start = max(times[0], times[-1] - width + 1e-6)
+    return np.flatnonzero(keep)
 
 
 def sim3_apply(pos, quat, R, t, s):

@@ -696,6 +696,58 @@ def test_fuse_trajectory_falls_back_to_ransac_on_outliers(gsf):
     assert np.abs(allpts[1] - t).max() > 1e-3
 
 
+@pytest.mark.parametrize("case", ["gpsfilter_sliding", "gpsfilter_sparse", "gpsfilter_global", "gpsfilter_clean"])
+def test_gps_prefilter_matches_seeded_reference(gsf, case):
+    """N3: the drop-in's filter_gps_outliers_ransac (per-window, per-axis polynomial RANSAC on the device,
+    gsf_poly_ransac_dev) against the UNMODIFIED reference's (EKFGPSSLAM.py:136-247, sklearn RANSACRegressor) run with the
+    same numpy seed (tests/golden/gpsfilter_*.npz, oracle/make_golden_gpsfilter.py): the same points survive and numpy's
+    global RNG ends in the same state, i.e. every fit stopped after the same number of trials."""
+    import EKFGPSSLAM as E
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case + ".npz"))
+    cfg = dict(E.CONFIG["gps_filtering_ransac"])
+    cfg["enabled"] = True
+    cfg["use_sliding_window"] = bool(g["sliding"])
+    np.random.seed(int(g["seed"]))
+    tf, pf = E.filter_gps_outliers_ransac(g["t"], g["pos"], cfg)
+    np.testing.assert_array_equal(tf, g["t"][g["kept"]])
+    np.testing.assert_array_equal(pf, g["pos"][g["kept"]])
+    assert np.random.random() == float(g["rng_after"])
+
+
+def test_poly_ransac_batched_matches_oracle(gsf):
+    """gsf_poly_ransac_dev, many fits in one launch (windows x axes of several tracks), against the numpy restatement of
+    sklearn's loop (oracle.poly_ransac_fit) fed the same sample indices; degree 1..3, ragged windows, a window whose
+    samples never reach an inlier count of 1 is impossible (the sample itself fits), so status stays 0."""
+    from sklearn.utils.random import sample_without_replacement
+    from oracle import fusion_oracle as fo
+    from oracle.make_golden_gpsfilter import make_track
+    rng = np.random.default_rng(5)
+    ms, max_trials, thr = 6, 50, 10.0
+    for degree in (1, 2, 3):
+        ts, ys, widx, off, axes, samples, dyn, dyn_off, want = [], [], [], [0], [], [], [], [], []
+        base = 0
+        for k in range(6):
+            t, pos, _ = make_track(40 + k, n=int(rng.integers(30, 200)), dt=0.1, outlier_frac=0.08, borderline_frac=0.02)
+            for axis in range(3):
+                nw = len(t)
+                rs_dev, rs_ref = np.random.RandomState(1000 * degree + 10 * k + axis), np.random.RandomState(1000 * degree + 10 * k + axis)
+                samples.append(np.stack([sample_without_replacement(nw, ms, random_state=rs_dev) for _ in range(max_trials)]))
+                mask, used = fo.poly_ransac_fit(t, pos[:, axis], degree, ms, thr, max_trials, rng=rs_ref)
+                want.append((mask, used))
+                widx.append(base + np.arange(nw)); off.append(off[-1] + nw); axes.append(axis)
+                dyn_off.append(sum(len(d) for d in dyn)); dyn.append(gsf.dynamic_max_trials_table(nw, ms, max_trials))
+            ts.append(t); ys.append(pos); base += len(t)
+        mask, n_trials, status = gsf.poly_ransac(dev(np.concatenate(ts)), dev(np.concatenate(ys)), dev(np.concatenate(widx), torch.int32),
+                                                 dev(np.array(off), torch.int64), dev(np.array(axes), torch.int32),
+                                                 dev(np.stack(samples), torch.int32), dev(np.concatenate(dyn), torch.int32),
+                                                 dev(np.array(dyn_off), torch.int64), ms, degree, max_trials, thr)
+        mask, n_trials, status = mask.cpu().numpy().astype(bool), n_trials.cpu().numpy(), status.cpu().numpy()
+        assert (status == 0).all()
+        for f, (m_ref, used) in enumerate(want):
+            np.testing.assert_array_equal(mask[off[f]:off[f + 1]], m_ref, err_msg=f"degree {degree} fit {f}")
+            assert n_trials[f] == used
+
+
 def test_dropin_entry_point(gsf, tmp_path):
     """The drop-in module reproduces the reference's run on the shipped pair A (from the
     golden fixture; the reference's files do not travel to the GPU box)."""

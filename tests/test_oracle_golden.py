@@ -92,3 +92,19 @@ def test_sim3_ransac_matches_seeded_reference(case):
     np.testing.assert_allclose(R, g["R"], rtol=0, atol=1e-15)
     np.testing.assert_allclose(t, g["t"], rtol=1e-15)
     assert abs(s - float(g["s"])) <= 1e-15
+
+
+@pytest.mark.parametrize("case", ["gpsfilter_sliding", "gpsfilter_sparse", "gpsfilter_global", "gpsfilter_clean"])
+def test_gps_filter_oracle_matches_seeded_reference(case):
+    """oracle.gps_filter_ransac (sklearn's RANSACRegressor loop restated in numpy) against the UNMODIFIED reference's
+    filter_gps_outliers_ransac (EKFGPSSLAM.py:136-247) run with the same numpy seed: same surviving points, and numpy's
+    global RNG left in the same state (i.e. every fit consumed the same number of trials)."""
+    import os
+    from oracle import fusion_oracle as fo
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case + ".npz"))
+    cfg = dict(fo.default_config()["gps_filtering_ransac"])
+    cfg["use_sliding_window"] = bool(g["sliding"])
+    np.random.seed(int(g["seed"]))
+    kept = fo.gps_filter_ransac(g["t"], g["pos"], cfg)
+    np.testing.assert_array_equal(kept, g["kept"])
+    assert np.random.random() == float(g["rng_after"])
