@@ -164,10 +164,31 @@ class ExtendedKalmanFilter:
 
 
 # ----------------------------------------------------------------------------- loading
+def _loadtxt_device(path: str, delimiter=None) -> np.ndarray:
+    """np.loadtxt(path[, delimiter=...]) with the parsing on the device (gsf_parse_table_dev): the file's bytes go to the
+    GPU as they are; comments, blank lines, field splitting and the decimal -> double conversion (correctly rounded, like
+    strtod) run there.  Raises what numpy raises: FileNotFoundError, ValueError for a non-numeric / empty field or ragged rows."""
+    raw = np.fromfile(path, dtype=np.uint8)                                   # FileNotFoundError like np.loadtxt
+    if raw.size == 0:
+        return np.empty((0,), dtype=np.float64)
+    first = next((ln for ln in bytes(raw[:65536]).split(b"\n") if ln.split(b"#")[0].strip()), b"")
+    body = first.split(b"#")[0].strip()
+    ncols = len(body.split() if delimiter is None else body.split(delimiter.encode())) or 1
+    table, status = fusion.parse_table(torch.from_numpy(raw).to("cuda"), 0 if delimiter is None else ord(delimiter), max_cols=ncols)
+    if status & 1:
+        raise ValueError("could not convert string to float")
+    if status & (2 | 16):
+        raise ValueError("Wrong number of columns")
+    if status & 4:
+        raise ValueError("a field has more than 19 significant digits with an ambiguous rounding")
+    out = table.cpu().numpy()
+    return out[0] if out.shape[0] == 1 else out                               # numpy squeezes a single row
+
+
 def load_slam_trajectory(txt_path: str) -> Dict[str, np.ndarray]:
     """TUM file ``ts x y z qx qy qz qw`` (EKFGPSSLAM.py:110-125)."""
     try:
-        table = np.loadtxt(txt_path)
+        table = _loadtxt_device(txt_path)
         if table.ndim == 1:
             table = table.reshape(1, -1)
         if table.shape[1] != 8:
@@ -277,9 +298,9 @@ def load_gps_data(txt_path: str, data_label: str = "GPS",
     """GNSS rows ``ts lat lon alt ...`` -> UTM (EKFGPSSLAM.py:249-289)."""
     try:
         try:
-            raw = np.loadtxt(txt_path, delimiter=" ")
+            raw = _loadtxt_device(txt_path, delimiter=" ")
         except ValueError:
-            raw = np.loadtxt(txt_path, delimiter=",")
+            raw = _loadtxt_device(txt_path, delimiter=",")
         if raw.ndim == 1:
             raw = raw.reshape(1, -1)
         if raw.shape[1] < 4:
@@ -469,16 +490,17 @@ def evaluate_errors(traj_xyz, aligned, slam_timestamps, skip_seconds: float = EV
 
 
 def save_results(slam_path, out_path_utm, timestamps, corrected_pos, corrected_quat, projector):
-    """Writers of EKFGPSSLAM.py:1087-1102 (same formats, headers and file naming)."""
-    np.savetxt(out_path_utm, np.column_stack((timestamps, corrected_pos, corrected_quat)),
-               fmt=["%.6f"] + ["%.6f"] * 3 + ["%.8f"] * 4, header="timestamp x y z qx qy qz qw (UTM)", comments="")
+    """Writers of EKFGPSSLAM.py:1087-1102 (same formats, headers and file naming); the text is produced on the device
+    (gsf_write_pose_rows_dev: exact "%.Df" formatting) and written to disk as one block."""
+    ts_d, q_d = _dev(timestamps), _dev(corrected_quat)
+    utm_text = fusion.write_pose_rows(ts_d, _dev(corrected_pos), q_d, [6, 6, 6, 6, 8, 8, 8, 8], "timestamp x y z qx qy qz qw (UTM)\n")
+    utm_text.cpu().numpy().tofile(out_path_utm)
     wgs = utm_to_wgs84(corrected_pos, projector)
     out_wgs = out_path_utm.replace("_utm.txt", "_wgs84.txt")
     if out_wgs == out_path_utm:
         out_wgs = out_path_utm.replace(".txt", "_wgs84.txt") if ".txt" in out_path_utm else out_path_utm + "_wgs84.txt"
-    np.savetxt(out_wgs, np.column_stack((timestamps, wgs, corrected_quat)),
-               fmt=["%.6f"] + ["%.8f", "%.8f", "%.3f"] + ["%.8f"] * 4,
-               header="timestamp lon lat alt qx qy qz qw (WGS84)", comments="")
+    wgs_text = fusion.write_pose_rows(ts_d, _dev(wgs), q_d, [6, 8, 8, 3, 8, 8, 8, 8], "timestamp lon lat alt qx qy qz qw (WGS84)\n")
+    wgs_text.cpu().numpy().tofile(out_wgs)
     return out_path_utm, out_wgs
 
 

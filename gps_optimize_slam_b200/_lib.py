@@ -27,6 +27,11 @@ SIGNATURES = {
     "gsf_noise_grid_work_doubles": (c_int64, [c_int64, c_int32, c_int32, c_int32, c_int64, c_int64]),
     "gsf_ekf_noise_grid_dev": (c_int32, [c_void_p] * 4 + [c_int64] + [c_void_p] * 4 + [c_int32] * 3 + [c_int64] * 2 + [c_void_p] * 5),
     "gsf_poly_ransac_dev": (c_int32, [c_void_p, c_void_p, c_int32] + [c_void_p] * 6 + [c_int32] * 4 + [c_double] + [c_void_p] * 4),
+    "gsf_parse_table_work_bytes": (c_int64, [c_int64]),
+    "gsf_parse_table_dev": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gsf_write_rows_work_bytes": (c_int64, [c_int64]),
+    "gsf_write_pose_rows_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_char_p, c_int32, c_void_p, c_int64,
+                                          c_void_p, c_void_p, c_void_p]),
     "gsf_ekf_step_dev": (c_int32, [c_int32] + [c_void_p] * 9 + [c_int32] + [c_void_p] * 6),
     "gsf_rts_segment_dev": (c_int32, [c_void_p] * 5 + [c_int32] + [c_void_p] * 3),
     "gsf_quat_nlerp_dev": (c_int32, [c_void_p] * 3 + [c_int64, c_void_p, c_void_p]),

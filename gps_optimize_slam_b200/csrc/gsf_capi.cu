@@ -207,6 +207,32 @@ int gsf_poly_ransac_dev(const double* t, const double* y, int32_t y_stride, cons
     return 0;
 }
 
+int64_t gsf_parse_table_work_bytes(int64_t nbytes) { return gsf::parse_table_work_bytes(nbytes < 0 ? 0 : nbytes); }
+int gsf_parse_table_dev(const char* text, int64_t nbytes, int32_t delimiter, int32_t max_cols, double* out, int64_t max_rows,
+                        void* work, int64_t* info, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (nbytes < 0 || max_cols < 1 || max_rows < 0 || (nbytes > 0 && !text) || !out || !work || !info || delimiter < 0 || delimiter > 127)
+        return fail(GSF_E_INVALID, "gsf_parse_table_dev: null pointer or bad size");
+    cudaError_t e = gsf::launch_parse_table(text, nbytes, delimiter, max_cols, out, max_rows, work, reinterpret_cast<long long*>(info), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_parse_table_dev");
+    return 0;
+}
+int64_t gsf_write_rows_work_bytes(int64_t n) { return gsf::write_rows_work_bytes(n < 0 ? 0 : n); }
+int gsf_write_pose_rows_dev(const double* ts, const double* xyz, const double* quat, int64_t n, const int32_t* decimals,
+                            const char* header, int32_t header_bytes, char* out, int64_t capacity, void* work, int64_t* out_info,
+                            void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (n < 0 || !ts || !xyz || !quat || !decimals || !out || !work || !out_info || header_bytes < 0 || (header_bytes > 0 && !header))
+        return fail(GSF_E_INVALID, "gsf_write_pose_rows_dev: null pointer or bad size");
+    cudaError_t e = gsf::launch_write_pose_rows(ts, xyz, quat, n, decimals, header, header_bytes, out, capacity, work,
+                                                reinterpret_cast<long long*>(out_info), (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(GSF_E_INVALID, "gsf_write_pose_rows_dev: decimals must be 0..9 and the header must fit"); }
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_write_pose_rows_dev");
+    return 0;
+}
+
 int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,
                                const int64_t* offsets, int32_t B,
                                const gsf_fuse_params* params, int32_t params_per_traj,

@@ -72,6 +72,11 @@ int ate_smem_capacity(int max_smem);
 cudaError_t launch_ate(const AteArgs& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_poly_ransac(const double*, const double*, int, const int*, const long long*, const int*, const int*, const int*,
                                const long long*, int, int, int, int, double, unsigned char*, int*, int*, cudaStream_t);
+long long parse_table_work_bytes(long long nbytes);
+cudaError_t launch_parse_table(const char*, long long, int, int, double*, long long, void*, long long*, cudaStream_t);
+long long write_rows_work_bytes(long long n);
+cudaError_t launch_write_pose_rows(const double*, const double*, const double*, long long, const int*, const char*, int, char*, long long,
+                                   void*, long long*, cudaStream_t);
 struct SynthArgs {
     double* ts; double* pos; double* quat; double* z;
     long long traj0; int B; int n; double dt; double speed; unsigned long long seed;

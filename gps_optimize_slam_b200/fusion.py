@@ -229,6 +229,54 @@ def dynamic_max_trials_table(n_window: int, min_samples: int, max_trials: int, p
     return out
 
 
+def parse_table(text, delimiter: int = 0, max_cols: int = 16, max_rows=None, stream=None):
+    """np.loadtxt of a numeric text table on the device (gsf_parse_table_dev).  text: uint8 CUDA tensor with the file's
+    bytes; delimiter 0 = whitespace runs, else ord(char).  Returns (table [rows, cols] float64 CUDA, status bits)
+    -- synchronous (the row count comes back to the host)."""
+    lib = _lib.load()
+    _require_cuda(text)
+    nbytes = int(text.numel())
+    dev = text.device
+    if max_rows is None:
+        max_rows = nbytes // 2 + 1                   # a row needs a digit and a newline
+    out = torch.empty((max_rows, max_cols), dtype=torch.float64, device=dev)
+    work = torch.empty((lib.gsf_parse_table_work_bytes(nbytes),), dtype=torch.uint8, device=dev)
+    info = torch.zeros((4,), dtype=torch.int64, device=dev)
+    rc = lib.gsf_parse_table_dev(_ptr(text), nbytes, int(delimiter), int(max_cols), _ptr(out), int(max_rows), _ptr(work), _ptr(info),
+                                 _stream_ptr(stream))
+    _lib.check(rc, "gsf_parse_table_dev")
+    rows, cmin, cmax, status = [int(v) for v in info.cpu()]
+    if rows > 0 and cmin != cmax:
+        status |= 16                                 # ragged rows: numpy's "Wrong number of columns"
+    cols = min(cmax, max_cols) if rows > 0 else 0
+    return out[:min(rows, max_rows), :cols], status
+
+
+def write_pose_rows(ts, xyz, quat, decimals, header: str = "", stream=None):
+    """np.savetxt of rows ``ts a b c qx qy qz qw`` with "%.Df" per column (gsf_write_pose_rows_dev, EKFGPSSLAM.py:1087-1102).
+    Returns the file's bytes as a uint8 CUDA tensor -- synchronous (the length comes back to the host)."""
+    import numpy as np
+    lib = _lib.load()
+    _require_cuda(ts, xyz, quat)
+    n = int(ts.numel())
+    dev = ts.device
+    hdr = header.encode()
+    dec = np.ascontiguousarray(decimals, dtype=np.int32)
+    if dec.shape != (8,):
+        raise ValueError("decimals must have 8 entries")
+    cap = len(hdr) + n * (8 * 31) + 16
+    out = torch.empty((cap,), dtype=torch.uint8, device=dev)
+    work = torch.empty((lib.gsf_write_rows_work_bytes(n),), dtype=torch.uint8, device=dev)
+    info = torch.zeros((2,), dtype=torch.int64, device=dev)
+    rc = lib.gsf_write_pose_rows_dev(_ptr(ts), _ptr(xyz), _ptr(quat), n, ctypes.c_void_p(dec.ctypes.data), hdr, len(hdr), _ptr(out), cap,
+                                     _ptr(work), _ptr(info), _stream_ptr(stream))
+    _lib.check(rc, "gsf_write_pose_rows_dev")
+    nbytes, bad = [int(v) for v in info.cpu()]
+    if bad:
+        raise _lib.GsfError("write_pose_rows: a value is outside the fixed-point formatter's range (|x| >= 2^63)")
+    return out[:nbytes]
+
+
 def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, params_per_traj=False, stream=None):
     """Literal step-by-step EKF recursion, one thread per trajectory (gsf_ekf_strict_batched_dev)."""
     lib = _lib.load()

@@ -131,6 +131,26 @@ int gsf_poly_ransac_dev(const double* t, const double* y, int32_t y_stride, cons
                         int32_t F, int32_t min_samples, int32_t degree, int32_t max_trials, double residual_threshold,
                         uint8_t* inlier_mask, int32_t* n_trials, int32_t* status, void* stream);
 
+/* ---- file formats on the device.
+ *      gsf_parse_table_dev: np.loadtxt of a numeric text table already in device memory (load_slam_trajectory :110-125,
+ *      load_gps_data :252-258): '#' comments, blank lines skipped, delimiter 0 = runs of whitespace, else exactly that
+ *      character (the reference tries ' ' then ',', :252-253).  Every field is converted like strtod (correctly rounded:
+ *      the doubles equal numpy's).  out [max_rows, max_cols] row-major, rows in file order.  info [4] (device):
+ *      rows, min columns, max columns, status bits (1 unparsable / empty field = numpy's ValueError, 2 a row has more
+ *      than max_cols columns, 4 a field has more than 19 significant digits and its rounding is ambiguous, 8 more rows
+ *      than max_rows).  Synchronises the stream once (the line count sizes the second half).
+ *      gsf_write_pose_rows_dev: the np.savetxt calls of :1087-1102 -- header (host string, written verbatim, may be
+ *      NULL), then n rows "ts a b c qx qy qz qw\n" with column k printed as "%.{decimals[k]}f" exactly as printf does
+ *      (decimals: host int32 [8]; UTM file 6,6,6,6,8,8,8,8; WGS84 file 6,8,8,3,8,8,8,8).  out_info [2] (device): bytes
+ *      written, 1 if a value was outside the formatter's range (|x| >= 2^63). */
+int64_t gsf_parse_table_work_bytes(int64_t nbytes);
+int gsf_parse_table_dev(const char* text, int64_t nbytes, int32_t delimiter, int32_t max_cols, double* out, int64_t max_rows,
+                        void* work, int64_t* info, void* stream);
+int64_t gsf_write_rows_work_bytes(int64_t n);
+int gsf_write_pose_rows_dev(const double* ts, const double* xyz, const double* quat, int64_t n, const int32_t* decimals,
+                            const char* header, int32_t header_bytes, char* out, int64_t capacity, void* work, int64_t* out_info,
+                            void* stream);
+
 /* ---- apply_ekf_correction (:831-935), literal step-by-step recursion, one thread per
  *      trajectory (general path; keeps the zero-motion fallback of :84-86). */
 int gsf_ekf_strict_batched_dev(const double* ts, const double* pos, const double* quat, const double* z,

@@ -21,3 +21,9 @@ int hm_ekf_strict(long n, const double* ts, const double* pos, const double* qua
     return gsf::ekf_strict_trajectory(n, ts, pos, quat, z, init_pos, init_quat, *prm, out_pos, out_quat);
 }
 }
+
+#include "../../gps_optimize_slam_b200/csrc/gsf_text.cuh"
+extern "C" {
+int hm_parse_double(const char* s, int n, double* out, int* inexact) { return gsf::parse_double(s, s + n, out, inexact); }
+int hm_format_fixed(double x, int D, char* buf, int* bad) { return gsf::format_fixed(x, D, buf, bad); }
+}

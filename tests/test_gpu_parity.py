@@ -748,6 +748,44 @@ def test_poly_ransac_batched_matches_oracle(gsf):
             assert n_trials[f] == used
 
 
+def test_text_parser_and_writer_match_numpy(gsf, tmp_path):
+    """N4: gsf_parse_table_dev against np.loadtxt (EKFGPSSLAM.py:110-125, :252-258) -- bit-identical doubles on whitespace-,
+    space- and comma-delimited tables with comments, blank lines, exponents, 16-19 digit fields, CRLF, a missing final
+    newline -- and gsf_write_pose_rows_dev against np.savetxt with the reference's formats (:1087-1102), byte for byte."""
+    import io
+    rng = np.random.default_rng(12)
+    n = 20011
+    tab = np.column_stack([1317384506.0 + np.arange(n) * 0.1037, rng.normal(0, 300, (n, 3)), rng.normal(0, 1, (n, 4))])
+    tab[5, 2] = 0.0; tab[6, 3] = -0.0; tab[7, 1] = 1e-12; tab[8, 1] = 123456789012.125
+    cases = []
+    buf = io.StringIO(); np.savetxt(buf, tab, fmt="%.6f"); cases.append((buf.getvalue(), None))
+    buf = io.StringIO(); np.savetxt(buf, tab); cases.append(("# ts x y z qx qy qz qw\n\n" + buf.getvalue().replace("\n", "\r\n", 50), None))      # %.18e
+    buf = io.StringIO(); np.savetxt(buf, tab[:300], fmt="%.9f", delimiter=","); cases.append((buf.getvalue().rstrip("\n"), ","))
+    buf = io.StringIO(); np.savetxt(buf, tab[:300], fmt="%.12g", delimiter=" "); cases.append((buf.getvalue() + "# tail comment\n", " "))
+    cases.append(("1 2 3 # c\n4 5 6\n", None)); cases.append(("7.5\n", None)); cases.append(("1e400 -1e-400 nan -inf 0x\n".replace(" 0x", ""), None))
+    for text, delim in cases:
+        want = np.loadtxt(io.StringIO(text), delimiter=delim, ndmin=2)
+        raw = torch.from_numpy(np.frombuffer(text.encode(), dtype=np.uint8).copy()).cuda()
+        got, status = gsf.parse_table(raw, 0 if delim is None else ord(delim), max_cols=want.shape[1])
+        assert status == 0, status
+        got = got.cpu().numpy()
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)) or np.array_equal(got, want, equal_nan=True)
+    # errors numpy raises as ValueError
+    for text, delim, bit in (("1 2\n3 x\n", None, 1), ("1 2\n3\n", None, 16), ("1  2\n", " ", 1), ("1,2,\n", ",", 1)):
+        raw = torch.from_numpy(np.frombuffer(text.encode(), dtype=np.uint8).copy()).cuda()
+        _, status = gsf.parse_table(raw, 0 if delim is None else ord(delim), max_cols=4)
+        assert status & bit, (text, status)
+    # writers
+    ts = tab[:, 0]; xyz = tab[:, 1:4] + np.array([455779.0, 5431368.0, 112.0]); quat = tab[:, 4:8]
+    xyz[11] = [0.0000005, -0.0000005, 2.5e-7]; xyz[12] = [1.0000005, 2.00000050000001, 0.9999995]; quat[13] = [0.5, -0.125, 1e-9, -1e-9]
+    for dec, hdr in (([6, 6, 6, 6, 8, 8, 8, 8], "timestamp x y z qx qy qz qw (UTM)"), ([6, 8, 8, 3, 8, 8, 8, 8], "timestamp lon lat alt qx qy qz qw (WGS84)")):
+        ref = io.StringIO()
+        np.savetxt(ref, np.column_stack((ts, xyz, quat)), fmt=["%%.%df" % d for d in dec], header=hdr, comments="")
+        got = bytes(gsf.write_pose_rows(dev(ts), dev(xyz), dev(quat), dec, hdr + "\n").cpu().numpy())
+        assert got == ref.getvalue().encode()
+
+
 def test_dropin_entry_point(gsf, tmp_path):
     """The drop-in module reproduces the reference's run on the shipped pair A (from the
     golden fixture; the reference's files do not travel to the GPU box)."""

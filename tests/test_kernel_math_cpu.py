@@ -146,3 +146,50 @@ def test_kernel_formulation_matches_oracle(name, threads):
     np.testing.assert_allclose(m["R"], R, atol=1e-12)
     np.testing.assert_allclose(m["pos"], fp, rtol=0, atol=5e-8)
     np.testing.assert_allclose(m["quat"], fq, rtol=0, atol=1e-13)
+
+
+def test_text_conversions_match_python(hostmath):
+    """gsf_text.cuh compiled for the host: parse_double against Python's float() (strtod-quality: Clinger fast path +
+    Eisel-Lemire) and format_fixed against printf's "%.Df" -- the conversions behind gsf_parse_table_dev /
+    gsf_write_pose_rows_dev (np.loadtxt / np.savetxt of EKFGPSSLAM.py:110-125, :252-258, :1087-1102)."""
+    import ctypes
+    import random
+    hostmath.hm_parse_double.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
+    hostmath.hm_format_fixed.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
+    rnd = random.Random(3)
+    out, flag = ctypes.c_double(), ctypes.c_int(0)
+    for i in range(30000):
+        k = rnd.random()
+        if k < 0.3:
+            s = "%.6f" % rnd.uniform(-2e9, 2e9)
+        elif k < 0.55:
+            s = repr(rnd.uniform(-1, 1) * 10 ** rnd.randint(-30, 30))
+        elif k < 0.8:
+            s = "%.18e" % (rnd.uniform(-1, 1) * 10 ** rnd.randint(-300, 300))
+        else:
+            s = str(rnd.getrandbits(63)) + "e" + str(rnd.randint(-330, 290))
+        flag.value = 0
+        used = hostmath.hm_parse_double(s.encode(), len(s), ctypes.byref(out), ctypes.byref(flag))
+        assert used == len(s) and flag.value == 0 and out.value == float(s), s
+    for s, want in (("nan", None), ("-inf", -np.inf), ("Infinity", np.inf), ("1e400", np.inf), ("5e-324", 5e-324), ("-0", -0.0), ("+.5e1", 5.0)):
+        used = hostmath.hm_parse_double(s.encode(), len(s), ctypes.byref(out), ctypes.byref(flag))
+        assert used == len(s) and (np.isnan(out.value) if want is None else out.value == want)
+    assert hostmath.hm_parse_double(b"abc", 3, ctypes.byref(out), ctypes.byref(flag)) == 0
+    buf = ctypes.create_string_buffer(64)
+    for i in range(30000):
+        k = rnd.random()
+        if k < 0.4:
+            x = rnd.uniform(-2e9, 2e9)
+        elif k < 0.6:
+            x = rnd.uniform(-1, 1) * 10 ** rnd.randint(-12, 3)
+        elif k < 0.8:
+            x = round(rnd.uniform(-1e7, 1e7), rnd.choice([3, 6, 8])) + rnd.choice([0, 5e-4, 5e-7, 5e-9, -5e-9])
+        else:
+            x = rnd.randint(-10 ** 9, 10 ** 9) / rnd.choice([2, 4, 8, 16, 1024, 2 ** 20, 2 ** 30])
+        D = rnd.choice([3, 6, 8])
+        flag.value = 0
+        n = hostmath.hm_format_fixed(x, D, buf, ctypes.byref(flag))
+        assert buf.raw[:n].decode() == ("%." + str(D) + "f") % x and flag.value == 0, x
+    for x in (0.0, -0.0, float("nan"), float("inf"), -float("inf"), 0.5, 1.5, 2.5, 9.9999999999, 999999.9999995):
+        n = hostmath.hm_format_fixed(x, 6, buf, ctypes.byref(flag))
+        assert buf.raw[:n].decode() == "%.6f" % x
