@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("GSF_LIB") or os.path.join(PKG_DIR, "libgsf.so")     #
 
 GSF_E_INVALID, GSF_E_CUDA, GSF_E_NO_DEVICE, GSF_E_TOO_LARGE = -1, -2, -3, -4
 ST_OK, ST_TOO_FEW_POINTS, ST_DEGENERATE, ST_BAD_QUATERNION = 0, 1, 2, 4
-ST_EMPTY, ST_RANSAC_OUTLIERS, ST_TOO_LONG, ST_GRID_NEEDS_ALL_VALID = 8, 16, 32, 64
+ST_EMPTY, ST_RANSAC_OUTLIERS, ST_TOO_LONG, ST_GRID_NEEDS_ALL_VALID, ST_NEEDS_FP64 = 8, 16, 32, 64, 128
 GEO_PARTS = 1024
 
 # name -> (restype, argtypes); the CPU test-suite checks that every symbol declared in
@@ -32,6 +32,9 @@ SIGNATURES = {
     "gsf_write_rows_work_bytes": (c_int64, [c_int64]),
     "gsf_write_pose_rows_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_char_p, c_int32, c_void_p, c_int64,
                                           c_void_p, c_void_p, c_void_p]),
+    "gsf_to_local_f32_dev": (c_int32, [c_void_p] * 5 + [c_int32] + [c_void_p] * 6),
+    "gsf_from_local_f32_dev": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gsf_fuse_batched_f32_dev": (c_int32, [c_void_p] * 6 + [c_int32, c_void_p, c_int32] + [c_void_p] * 5),
     "gsf_ekf_step_dev": (c_int32, [c_int32] + [c_void_p] * 9 + [c_int32] + [c_void_p] * 6),
     "gsf_rts_segment_dev": (c_int32, [c_void_p] * 5 + [c_int32] + [c_void_p] * 3),
     "gsf_quat_nlerp_dev": (c_int32, [c_void_p] * 3 + [c_int64, c_void_p, c_void_p]),

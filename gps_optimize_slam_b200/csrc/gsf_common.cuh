@@ -35,6 +35,7 @@ enum : int {
                                // unseeded RANSAC could pick a different inlier set here
     ST_TOO_LONG = 32,          // trajectory does not fit the shared-memory staging buffer
     ST_GRID_NEEDS_ALL_VALID = 64,  // hypothesis grid: the trajectory has poses without GNSS (outage/RTS unsupported there)
+    ST_NEEDS_FP64 = 128,       // fp32 mode: the trajectory needs the general machinery (outage / gap / window / ...): use the fp64 path
     ST_DEFERRED = 1 << 30,     // internal: left by the fast kernel for the general kernel (never returned)
 };
 

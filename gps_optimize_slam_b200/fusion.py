@@ -277,6 +277,49 @@ def write_pose_rows(ts, xyz, quat, decimals, header: str = "", stream=None):
     return out[:nbytes]
 
 
+def to_local_f32(ts, pos, quat, z, offsets, stream=None):
+    """fp64 absolute arrays -> the fp32 mode's storage (gsf_to_local_f32_dev): (ts32, pos32, quat32, z32, origins [B,7])."""
+    lib = _lib.load()
+    _require_cuda(ts, pos, quat, z, offsets)
+    B = offsets.numel() - 1
+    dev = ts.device
+    ts32 = torch.empty(ts.shape, dtype=torch.float32, device=dev); pos32 = torch.empty(pos.shape, dtype=torch.float32, device=dev)
+    quat32 = torch.empty(quat.shape, dtype=torch.float32, device=dev); z32 = torch.empty(z.shape, dtype=torch.float32, device=dev)
+    origins = torch.empty((B, 7), dtype=torch.float64, device=dev)
+    rc = lib.gsf_to_local_f32_dev(_ptr(ts), _ptr(pos), _ptr(quat), _ptr(z), _ptr(offsets), B, _ptr(ts32), _ptr(pos32), _ptr(quat32), _ptr(z32),
+                                  _ptr(origins), _stream_ptr(stream))
+    _lib.check(rc, "gsf_to_local_f32_dev")
+    return ts32, pos32, quat32, z32, origins
+
+
+def from_local_f32(pos32, offsets, origins, stream=None):
+    """fused positions of the fp32 mode back to fp64 absolute coordinates (gsf_from_local_f32_dev)."""
+    lib = _lib.load()
+    _require_cuda(pos32, offsets, origins)
+    out = torch.empty(pos32.shape, dtype=torch.float64, device=pos32.device)
+    rc = lib.gsf_from_local_f32_dev(_ptr(pos32), _ptr(offsets), offsets.numel() - 1, _ptr(origins), _ptr(out), _stream_ptr(stream))
+    _lib.check(rc, "gsf_from_local_f32_dev")
+    return out
+
+
+def fuse_batched_f32(ts32, pos32, quat32, z32, origins, offsets, params, params_per_traj=False, out_pos=None, out_quat=None,
+                     sim3_out=None, status=None, stream=None):
+    """Optional fp32 mode of the fused path (gsf_fuse_batched_f32_dev).  Returns (out_pos32, out_quat32, sim3 [B,16], status)."""
+    lib = _lib.load()
+    _require_cuda(ts32, pos32, quat32, z32, origins, offsets, params)
+    B = offsets.numel() - 1
+    dev = ts32.device
+    out_pos = torch.empty_like(pos32) if out_pos is None else out_pos
+    out_quat = torch.empty_like(quat32) if out_quat is None else out_quat
+    sim3_out = torch.empty((B, 16), dtype=torch.float64, device=dev) if sim3_out is None else sim3_out
+    status = torch.empty((B,), dtype=torch.int32, device=dev) if status is None else status
+    rc = lib.gsf_fuse_batched_f32_dev(_ptr(ts32), _ptr(pos32), _ptr(quat32), _ptr(z32), _ptr(origins), _ptr(offsets), B, _ptr(params),
+                                      int(bool(params_per_traj)), _ptr(out_pos), _ptr(out_quat), _ptr(sim3_out), _ptr(status),
+                                      _stream_ptr(stream))
+    _lib.check(rc, "gsf_fuse_batched_f32_dev")
+    return out_pos, out_quat, sim3_out, status
+
+
 def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, params_per_traj=False, stream=None):
     """Literal step-by-step EKF recursion, one thread per trajectory (gsf_ekf_strict_batched_dev)."""
     lib = _lib.load()

@@ -42,6 +42,7 @@ extern "C" {
 #define GSF_ST_RANSAC_OUTLIERS 16   /* all-points fit has residuals >= threshold (:411) */
 #define GSF_ST_TOO_LONG        32
 #define GSF_ST_GRID_NEEDS_ALL_VALID 64 /* hypothesis grid: a pose without GNSS (use gsf_fuse_batched_dev) */
+#define GSF_ST_NEEDS_FP64     128   /* fp32 mode: outage / gap / Sim3 window / too few points: use gsf_fuse_batched_dev */
 
 /* Flattened CONFIG (EKFGPSSLAM.py:22-71); 184 bytes, layout fixed. */
 typedef struct gsf_fuse_params {
@@ -150,6 +151,24 @@ int64_t gsf_write_rows_work_bytes(int64_t n);
 int gsf_write_pose_rows_dev(const double* ts, const double* xyz, const double* quat, int64_t n, const int32_t* decimals,
                             const char* header, int32_t header_bytes, char* out, int64_t capacity, void* work, int64_t* out_info,
                             void* stream);
+
+/* ---- optional fp32 mode of the fused path (same stages as gsf_fuse_batched_dev; target 1e-4 m).  Storage is fp32 relative
+ *      to per-trajectory fp64 origins: origins [B,7] = t0, SLAM origin (3), UTM origin (3); ts32 = ts - t0,
+ *      pos32 = pos - SLAM origin, z32 = z - UTM origin (NaN row = no GNSS), quat32; outputs out_pos32 (fused position - UTM
+ *      origin) and out_quat32.  44 B in + 28 B out per pose instead of 88 + 56.  Reductions (Umeyama sums), the SVD and
+ *      pose 0 are fp64; the filter runs in fp32 in innovation form (state minus measurement), so its rounding is 1e-7 of
+ *      metres, and the result is limited by the fp32 storage of the relative coordinates (6e-5 m at 1 km from the origin).
+ *      sim3_out [B,16] as in gsf_fuse_batched_dev, t in the absolute frames.  One thread per trajectory; trajectory offsets
+ *      that are multiples of 4 poses get 128-bit loads.  Trajectories that need the general machinery (a pose without GNSS,
+ *      a GNSS gap, the Sim3 window, a step <= 1e-6 s, too few points, a zero first quaternion) return GSF_ST_NEEDS_FP64 and
+ *      NaN rows.  gsf_to_local_f32_dev / gsf_from_local_f32_dev convert fp64 absolute arrays to the format and fused
+ *      positions back (origin: the middle pose). */
+int gsf_to_local_f32_dev(const double* ts, const double* pos, const double* quat, const double* z, const int64_t* offsets, int32_t B,
+                         float* ts32, float* pos32, float* quat32, float* z32, double* origins, void* stream);
+int gsf_from_local_f32_dev(const float* pos32, const int64_t* offsets, int32_t B, const double* origins, double* pos, void* stream);
+int gsf_fuse_batched_f32_dev(const float* ts32, const float* pos32, const float* quat32, const float* z32, const double* origins,
+                             const int64_t* offsets, int32_t B, const gsf_fuse_params* params, int32_t params_per_traj,
+                             float* out_pos32, float* out_quat32, double* sim3_out, int32_t* status, void* stream);
 
 /* ---- apply_ekf_correction (:831-935), literal step-by-step recursion, one thread per
  *      trajectory (general path; keeps the zero-motion fallback of :84-86). */

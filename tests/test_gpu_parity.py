@@ -786,6 +786,38 @@ def test_text_parser_and_writer_match_numpy(gsf, tmp_path):
         assert got == ref.getvalue().encode()
 
 
+def test_fp32_mode_within_1e_4_m(gsf):
+    """Optional fp32 mode (gsf_fuse_batched_f32_dev: fp32 storage relative to fp64 origins, fp64 reductions and SVD, fp32
+    filter in innovation form) against the fp64 oracle on the ORIGINAL data: positions within 1e-4 m (north star), rotation
+    and quaternions at fp32 rounding; ragged batch (aligned and unaligned offsets); a trajectory with an outage is
+    handed back with GSF_ST_NEEDS_FP64; the fp64 fused kernel on the same batch agrees to the same tolerance."""
+    from gps_optimize_slam_b200 import _lib, synth
+    from oracle import fusion_oracle as fo
+    trajs = [synth.make_trajectory(300 + k, n=n) for k, n in enumerate((271, 272, 1000, 63, 517, 1000, 8, 271))]
+    trajs[4] = synth.make_trajectory(304, n=517, outages=[(100, 140)])
+    ts, pos, quat, z, off, offs, maxlen = pack(trajs)
+    prm = gsf.params_tensor()
+    ts32, pos32, quat32, z32, origins = gsf.to_local_f32(ts, pos, quat, z, off)
+    p32, q32, sim3, st = gsf.fuse_batched_f32(ts32, pos32, quat32, z32, origins, off, prm)
+    p = gsf.from_local_f32(p32, off, origins).cpu().numpy()
+    q32, sim3, st = q32.cpu().numpy().astype(np.float64), sim3.cpu().numpy(), st.cpu().numpy()
+    p64, q64, sim64, st64 = gsf.fuse_batched(ts, pos, quat, z, off, maxlen, prm)
+    p64 = p64.cpu().numpy()
+    cfg = fo.default_config()
+    for b, tr in enumerate(trajs):
+        sl = slice(offs[b], offs[b + 1])
+        if b == 4:
+            assert st[b] == _lib.ST_NEEDS_FP64 and np.isnan(p[sl]).all()
+            continue
+        assert st[b] == 0, (b, st[b])
+        o = oracle_pipeline(tr, cfg)
+        assert np.abs(p[sl] - o["pos"]).max() < 1e-4, (b, np.abs(p[sl] - o["pos"]).max())
+        assert np.abs(p[sl] - p64[sl]).max() < 1e-4
+        assert np.abs(q32[sl] - o["quat"]).max() < 2e-6
+        np.testing.assert_allclose(sim3[b, :9].reshape(3, 3), o["R"], rtol=0, atol=2e-6)
+        assert abs(sim3[b, 12] - o["s"]) < 2e-6 and np.abs(sim3[b, 9:12] - o["t"]).max() < 2e-2      # t amplifies the rotation's fp32-input rounding by |origin|
+
+
 def test_dropin_entry_point(gsf, tmp_path):
     """The drop-in module reproduces the reference's run on the shipped pair A (from the
     golden fixture; the reference's files do not travel to the GPU box)."""
