@@ -364,8 +364,12 @@ def dynamic_time_alignment(slam_data, gps_data_source, time_align_config):
         return aligned, valid
     if len(tu) < len(t):
         t, p = tu, p[first]
-    a, v = fusion.associate_spline(_dev(t), _dev(p), _one(len(t)), _dev(slam_t), _one(n),
-                                   gap=float(time_align_config["max_gps_gap_threshold"]))
+    gap = float(time_align_config["max_gps_gap_threshold"])
+    if len(t) > 8192:                                       # long tracks: local-halo spline solve, parallel over the knots
+        a, v, st = fusion.associate_spline_long(_dev(t), _dev(p), _dev(slam_t), gap)
+        if int(st.cpu()[0]) == 0:
+            return a.cpu().numpy(), v.cpu().numpy().astype(bool)
+    a, v = fusion.associate_spline(_dev(t), _dev(p), _one(len(t)), _dev(slam_t), _one(n), gap=gap)
     return a.cpu().numpy(), v.cpu().numpy().astype(bool)
 
 

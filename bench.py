@@ -446,6 +446,39 @@ def main():
         except Exception as exc:                                         # never lose the headline line to the sub-record
             config5 = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- optional fp32 mode (gsf_fuse_batched_f32_dev) on a slab of the same generator: fp32 storage relative to fp64 origins
+    fp32 = None
+    if not args.no_config5 and args.workload == "config3":
+        try:
+            Bf = min(B, 262144)
+            t64 = fusion.synth_generate(Bf, n, wl["dt"], wl["speed"], seed=20261018, first_traj=lo, device=dev)
+            offf = fusion.equal_offsets(Bf, n, device=dev)
+            prm2 = fusion.params_tensor(device=dev)
+            f32 = fusion.to_local_f32(*t64, offf)
+            ref_p, _, _, _ = fusion.fuse_batched(*t64, offf, n, prm2)
+            del t64
+            op32 = torch.empty_like(f32[1]); oq32 = torch.empty_like(f32[2])
+            s32 = torch.empty((Bf, 16), dtype=torch.float64, device=dev); st32 = torch.empty((Bf,), dtype=torch.int32, device=dev)
+            for _ in range(3):
+                fusion.fuse_batched_f32(*f32, offf, prm2, out_pos=op32, out_quat=oq32, sim3_out=s32, status=st32)
+            barrier()
+            ef = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ef[0].record()
+            for _ in range(5):
+                fusion.fuse_batched_f32(*f32, offf, prm2, out_pos=op32, out_quat=oq32, sim3_out=s32, status=st32)
+            ef[1].record()
+            torch.cuda.synchronize(dev)
+            fms = sharding.max_over_ranks(ef[0].elapsed_time(ef[1]), dev) / 5
+            err = float((fusion.from_local_f32(op32, offf, f32[4]) - ref_p).abs().max().cpu())
+            fp32 = {"trajectories_per_rank": Bf, "ms_per_step": fms, "pose_updates_per_s": world * Bf * (n - 1) / (fms * 1e-3),
+                    "bytes_per_pose": 72, "achieved_gb_s": Bf * n * 72 / (fms * 1e-3) / 1e9, "frac_of_hbm_peak": Bf * n * 72 / (fms * 1e-3) / 1e9 / peak,
+                    "max_abs_diff_vs_fp64_kernel_m": err, "nonzero_status": int((st32 != 0).sum().cpu()),
+                    "kernel": "fuse_f32_kernel (one thread per trajectory; fp64 sums + SVD, fp32 filter in innovation form)"}
+            del f32, op32, oq32, ref_p
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            fp32 = {"error": f"{type(exc).__name__}: {exc}"}
+
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -461,7 +494,7 @@ def main():
                        "outage_prob": args.outage_prob},
             "sim3_aligned_points_per_s": sim3_pts,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 2 * args.steps * passes, "ate": ate, "general_path": mixed, "config5": config5,
+            "gpu_launches": 2 * args.steps * passes, "ate": ate, "general_path": mixed, "config5": config5, "fp32_mode": fp32,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -12,7 +12,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("GSF_LIB_OUT") or os.path.join(PKG_DIR, "libgsf.so")   # GSF_LIB_OUT: A/B builds (with GSF_NVCC_EXTRA)
-SOURCES = ["gsf_fused.cu", "gsf_fast.cu", "gsf_long.cu", "gsf_ate.cu", "gsf_kernels.cu", "gsf_ransac.cu", "gsf_grid.cu", "gsf_ekf_api.cu", "gsf_synth.cu", "gsf_gpsfilter.cu", "gsf_text.cu", "gsf_f32.cu", "gsf_capi.cu"]
+SOURCES = ["gsf_fused.cu", "gsf_fast.cu", "gsf_long.cu", "gsf_ate.cu", "gsf_kernels.cu", "gsf_ransac.cu", "gsf_grid.cu", "gsf_ekf_api.cu", "gsf_synth.cu", "gsf_gpsfilter.cu", "gsf_text.cu", "gsf_f32.cu", "gsf_assoc_long.cu", "gsf_capi.cu"]
 EXTRA = os.environ.get("GSF_NVCC_EXTRA", "").split()
 PER_FILE = {}                     # per-source extra flags (tuning hook)
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -474,6 +474,17 @@ int gsf_associate_spline_dev(const double* gps_t, const double* gps_xyz, const i
     return 0;
 }
 
+int gsf_associate_spline_long_dev(const double* gps_t, const double* gps_xyz, int64_t M, const double* slam_t, int64_t N, double gap,
+                                  double* work, double* aligned, uint8_t* valid, int32_t* status, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (M < 0 || N < 0 || (M > 0 && (!gps_t || !gps_xyz)) || (N > 0 && (!slam_t || !aligned || !valid)) || !work)
+        return fail(GSF_E_INVALID, "gsf_associate_spline_long_dev: null pointer or negative size");
+    cudaError_t e = gsf::launch_associate_long(gps_t, gps_xyz, M, slam_t, N, gap, work, aligned, valid, status, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_associate_spline_long_dev");
+    return 0;
+}
+
 int gsf_synth_generate_dev(double* ts, double* pos, double* quat, double* z, int64_t first_traj,
                            int32_t B, int32_t n, double dt, double speed, uint64_t seed,
                            double outage_prob, int32_t outage_max_len, void* stream) {

@@ -54,6 +54,8 @@ struct AssocArgs {
     double gap; double* aligned; unsigned char* valid; double* work; int B;
 };
 cudaError_t launch_associate(const AssocArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_associate_long(const double*, const double*, long long, const double*, long long, double, double*, double*, unsigned char*, int*,
+                                  cudaStream_t);
 int sim3_tiles_for(long long max_len);
 cudaError_t launch_umeyama(const double*, const double*, const long long*, const unsigned char*, int, long long, double*,
                            double*, double*, double*, int*, cudaStream_t);

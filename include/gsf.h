@@ -260,6 +260,15 @@ int gsf_associate_spline_dev(const double* gps_t, const double* gps_xyz, const i
                              const double* slam_t, const int64_t* slam_offsets, int32_t B, double gap,
                              double* work, double* aligned, uint8_t* valid, void* stream);
 
+/* ---- the same for ONE trajectory of any size (BASELINE config 4: 1e8 samples): the not-a-knot system is solved locally --
+ *      32-knot chunks with a 32-knot halo, natural ends where the halo cuts a segment, the true end rows where the segment
+ *      ends inside it; the cut decays like 0.268^32 = 5e-19, below fp64 rounding -- and the evaluation is one thread per
+ *      SLAM stamp.  gps_t [M] sorted and unique, gps_xyz [M,3], slam_t [N] (any order).  work: 3 M + 1 doubles.
+ *      status [1] (may be NULL): 1 if two consecutive GNSS stamps differ by <= 1e-9 s inside a segment (the reference
+ *      drops such a segment, :356-359; use gsf_associate_spline_dev for that data). */
+int gsf_associate_spline_long_dev(const double* gps_t, const double* gps_xyz, int64_t M, const double* slam_t, int64_t N, double gap,
+                                  double* work, double* aligned, uint8_t* valid, int32_t* status, void* stream);
+
 /* ---- synthetic batch generator for the large bench configs (equal lengths n). */
 int gsf_synth_generate_dev(double* ts, double* pos, double* quat, double* z, int64_t first_traj,
                            int32_t B, int32_t n, double dt, double speed, uint64_t seed,

@@ -330,6 +330,42 @@ def test_association_kernel_matches_reference_golden(gsf, case):
     np.testing.assert_allclose(a[v], g["aligned"][v], rtol=0, atol=POS_ATOL)
 
 
+def test_association_long_trajectory_local_halo(gsf):
+    """gsf_associate_spline_long_dev (local-halo solve, one thread per 32-knot chunk) against scipy's interp1d per segment
+    (what dynamic_time_alignment calls, EKFGPSSLAM.py:351-380) and against the serial per-trajectory kernel: irregular
+    knot spacing, gaps that cut segments of 1, 2, 3, 4, 5, 31, 32, 33, 64, 65 and thousands of knots, stamps exactly on
+    knots / segment ends / inside gaps / outside the track; plus the golden cases (271 knots)."""
+    from oracle import fusion_oracle as fo
+    rng = np.random.default_rng(21)
+    lens = [1, 2, 3, 4, 5, 31, 32, 33, 64, 65, 97, 3000, 1, 7000, 4, 20000]
+    ts, t0 = [], 100.0
+    for m in lens:
+        steps = rng.uniform(0.02, 0.4, m) * rng.choice([1.0, 1.0, 5.0], m)
+        steps = np.minimum(steps, 4.0)
+        seg = t0 + np.cumsum(steps)
+        ts.append(seg); t0 = seg[-1] + rng.uniform(5.5, 9.0)
+    gt = np.concatenate(ts)
+    M = len(gt)
+    gy = np.column_stack([455779.0 + 8.0 * (gt - 100.0) + 30 * np.sin(gt / 7.0), 5431368.0 + 50 * np.cos(gt / 11.0) + 3.0 * (gt - 100.0),
+                          112.0 + np.sin(gt / 3.0)]) + rng.normal(0, 0.3, (M, 3))
+    st = np.concatenate([rng.uniform(gt[0] - 3, gt[-1] + 3, 40000), gt[::7], gt[[0, -1]], [ts[3][0], ts[3][-1], ts[5][-1], ts[11][0]],
+                         [ts[1][0] + 1e-7, ts[0][0]]])
+    want, want_valid = fo.associate(st, gt, gy, 5.0)
+    a, v, status = gsf.associate_spline_long(dev(gt), dev(gy), dev(st), 5.0)
+    assert int(status.cpu()[0]) == 0
+    a, v = a.cpu().numpy(), v.cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(v, want_valid)
+    np.testing.assert_allclose(a[v], want[v], rtol=0, atol=POS_ATOL)
+    a2, v2 = gsf.associate_spline(dev(gt), dev(gy), dev(np.array([0, M]), torch.int64), dev(st), dev(np.array([0, len(st)]), torch.int64), gap=5.0)
+    np.testing.assert_array_equal(v2.cpu().numpy().astype(bool), v)
+    np.testing.assert_allclose(a[v], a2.cpu().numpy()[v], rtol=0, atol=2e-8)
+    for case in GOLDEN_CASES:
+        g = load_golden(case)
+        a, v, _ = gsf.associate_spline_long(dev(g["gps_ts"]), dev(g["gps_utm"]), dev(g["slam_ts"]), 5.0)
+        np.testing.assert_array_equal(v.cpu().numpy().astype(bool), g["valid"])
+        np.testing.assert_allclose(a.cpu().numpy()[g["valid"]], g["aligned"][g["valid"]], rtol=0, atol=POS_ATOL)
+
+
 def test_association_short_segments(gsf):
     """2-3 knot segments are linear, 1-knot segments are skipped (EKFGPSSLAM.py:361-362)."""
     from oracle import fusion_oracle as fo
