@@ -15,6 +15,7 @@
 // any length works -- the reference has no length limit either.
 #include "gsf_common.cuh"
 #include "gsf_internal.cuh"
+#include "gsf_ptx.cuh"
 #include "gsf_select.cuh"
 
 namespace gsf {
@@ -54,6 +55,15 @@ __global__ void __launch_bounds__(ATE_T) ate_nn_kernel(const AteArgs A) {
         double* const cs = GLOBAL_WORK ? A.work + 4 * e0 : smem_arr;          // bucketed candidates [m,3]
         double* const err = GLOBAL_WORK ? A.work + 4 * e0 + 3 * (size_t)n : smem_arr + 3 * (size_t)A.cap;   // errors [m]
         __syncthreads();
+        // the next trajectory of this block into L2 now: its four sweeps (bounding box, histogram, scatter, queries) then read
+        // L2 instead of waiting for HBM with a handful of loads in flight per thread
+        if (tid == 0 && b + (int)gridDim.x < A.B) {
+            const long long f0 = A.offsets[b + gridDim.x] & ~1ll, f1 = A.offsets[b + gridDim.x + 1] & ~1ll;      // even pose index: 16-byte aligned rows
+            if (f1 > f0 && f1 - f0 < (1ll << 24)) {
+                bulk_prefetch_l2(A.cand + 3 * f0, (uint32_t)((f1 - f0) * 24)); bulk_prefetch_l2(A.traj + 3 * f0, (uint32_t)((f1 - f0) * 24));
+                bulk_prefetch_l2(A.ts + f0, (uint32_t)((f1 - f0) * 8));
+            }
+        }
         if (n <= 0) { if (tid == 0) { o[0] = o[1] = o[2] = nan(""); o[3] = 0.0; } continue; }
         const double t0 = gts[0] + A.skip;
 

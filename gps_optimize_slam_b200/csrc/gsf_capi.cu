@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <mutex>
 #include <algorithm>
 
 #include "../../include/gsf.h"
@@ -132,18 +133,23 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
     const char* impl = getenv("GSF_FUSE_IMPL");
     const bool want_fast = !(impl && strcmp(impl, "general") == 0);
     cudaError_t e;
+    int counter_slot = -1;
     if (want_fast && a.use_tma && !init_pos && gsf::fast_fuse_supported(cap, d.max_smem)) {
-        e = gsf::defer_counter(&a.defer_count);
-        if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter)");
-        a.work_counter = a.defer_count + 1;
-        e = cudaMemsetAsync(a.defer_count, 0, 2 * sizeof(int), (cudaStream_t)stream);
-        if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter reset)");
-        e = gsf::launch_fuse_fast(a, d.sms, (cudaStream_t)stream);
-        if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (fast kernel)");
-        a.only_deferred = 1;
+        e = gsf::defer_counter(&a.defer_count, &counter_slot);
+        if (e == cudaErrorNotReady) { a.defer_count = nullptr; counter_slot = -1; }      // every counter slot busy: general kernel for the whole batch
+        else if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter)");
+        else {
+            a.work_counter = a.defer_count + 1;
+            e = cudaMemsetAsync(a.defer_count, 0, 2 * sizeof(int), (cudaStream_t)stream);
+            if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter reset)");
+            e = gsf::launch_fuse_fast(a, d.sms, (cudaStream_t)stream);
+            if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (fast kernel)");
+            a.only_deferred = 1;
+        }
     }
     e = gsf::launch_fuse(a, pick_threads(cap, d.max_smem), d.sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev");
+    if (counter_slot >= 0) gsf::defer_counter_release(counter_slot, (cudaStream_t)stream);
     if (need_long) {
         e = gsf::launch_fuse_long(a, d.sms, (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (long-trajectory kernel)");
@@ -516,6 +522,7 @@ struct Slot {
 };
 Slot g_slots[2];
 int g_slot_device = -1;
+std::mutex g_slot_mutex;          // the workspace is process-global: concurrent callers of the host entry are serialised
 
 void slot_free(Slot& s) {
     cudaFree(s.ts); cudaFree(s.pos); cudaFree(s.quat); cudaFree(s.z); cudaFree(s.opos); cudaFree(s.oquat);
@@ -556,8 +563,10 @@ cudaError_t slot_reserve(Slot& s, size_t poses, size_t trajs) {
 }
 }  // namespace
 
+static void host_workspace_free_locked() { slot_free(g_slots[0]); slot_free(g_slots[1]); g_slot_device = -1; }
 void gsf_host_workspace_free(void) {
-    slot_free(g_slots[0]); slot_free(g_slots[1]); g_slot_device = -1;
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    host_workspace_free_locked();
 }
 
 int gsf_fuse_batched_host(const double* ts, const double* pos, const double* quat, const double* z,
@@ -572,8 +581,9 @@ int gsf_fuse_batched_host(const double* ts, const double* pos, const double* qua
         return fail(GSF_E_INVALID, "gsf_fuse_batched_host: null pointer or negative size");
     if ((init_pos == nullptr) != (init_quat == nullptr))
         return fail(GSF_E_INVALID, "gsf_fuse_batched_host: init_pos and init_quat must be given together");
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
     int dev = 0; cudaGetDevice(&dev);
-    if (g_slot_device != dev) { gsf_host_workspace_free(); g_slot_device = dev; }
+    if (g_slot_device != dev) { host_workspace_free_locked(); g_slot_device = dev; }
 
     // chunk the batch: ~2M poses (176 MB in / 112 MB out) per chunk, two chunks in flight
     const int64_t CHUNK_POSES = 2 << 20;
@@ -593,7 +603,7 @@ int gsf_fuse_batched_host(const double* ts, const double* pos, const double* qua
     }
     for (int k = 0; k < 2; ++k) {
         cudaError_t e = slot_reserve(g_slots[k], max_poses, max_trajs);
-        if (e != cudaSuccess) { gsf_host_workspace_free(); return cuda_fail(e, "gsf_fuse_batched_host(workspace)"); }
+        if (e != cudaSuccess) { host_workspace_free_locked(); return cuda_fail(e, "gsf_fuse_batched_host(workspace)"); }
     }
     int rc = 0;
     for (size_t c = 0; c + 1 < cuts.size() && rc == 0; ++c) {
@@ -603,28 +613,31 @@ int gsf_fuse_batched_host(const double* ts, const double* pos, const double* qua
         const int32_t b0 = cuts[c], nb = cuts[c + 1] - cuts[c];
         const int64_t p0 = offsets[b0], np = offsets[b0 + nb] - p0;
         for (int32_t i = 0; i <= nb; ++i) s.off_host[i] = offsets[b0 + i] - p0;
-        cudaMemcpyAsync(s.off, s.off_host, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s.stream);
-        cudaMemcpyAsync(s.ts, ts + p0, (size_t)np * 8, cudaMemcpyHostToDevice, s.stream);
-        cudaMemcpyAsync(s.pos, pos + 3 * p0, (size_t)np * 24, cudaMemcpyHostToDevice, s.stream);
-        cudaMemcpyAsync(s.quat, quat + 4 * p0, (size_t)np * 32, cudaMemcpyHostToDevice, s.stream);
-        cudaMemcpyAsync(s.z, z + 3 * p0, (size_t)np * 24, cudaMemcpyHostToDevice, s.stream);
-        cudaMemcpyAsync(s.params, params + (params_per_traj ? b0 : 0), (params_per_traj ? (size_t)nb : 1) * sizeof(gsf_fuse_params),
-                        cudaMemcpyHostToDevice, s.stream);
+        cudaError_t ce = cudaSuccess;
+        auto copy = [&](void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, kind, s.stream);
+        };
+        copy(s.off, s.off_host, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice);
+        copy(s.ts, ts + p0, (size_t)np * 8, cudaMemcpyHostToDevice);
+        copy(s.pos, pos + 3 * p0, (size_t)np * 24, cudaMemcpyHostToDevice);
+        copy(s.quat, quat + 4 * p0, (size_t)np * 32, cudaMemcpyHostToDevice);
+        copy(s.z, z + 3 * p0, (size_t)np * 24, cudaMemcpyHostToDevice);
+        copy(s.params, params + (params_per_traj ? b0 : 0), (params_per_traj ? (size_t)nb : 1) * sizeof(gsf_fuse_params), cudaMemcpyHostToDevice);
         if (init_pos) {
-            cudaMemcpyAsync(s.ipos, init_pos + 3 * (size_t)b0, (size_t)nb * 24, cudaMemcpyHostToDevice, s.stream);
-            cudaMemcpyAsync(s.iquat, init_quat + 4 * (size_t)b0, (size_t)nb * 32, cudaMemcpyHostToDevice, s.stream);
+            copy(s.ipos, init_pos + 3 * (size_t)b0, (size_t)nb * 24, cudaMemcpyHostToDevice);
+            copy(s.iquat, init_quat + 4 * (size_t)b0, (size_t)nb * 32, cudaMemcpyHostToDevice);
         }
+        if (ce != cudaSuccess) { rc = cuda_fail(ce, "gsf_fuse_batched_host(H2D copy)"); break; }
         rc = gsf_fuse_batched_dev(s.ts, s.pos, s.quat, s.z, reinterpret_cast<const int64_t*>(s.off), nb, max_len,
                                   reinterpret_cast<const gsf_fuse_params*>(s.params), params_per_traj,
                                   init_pos ? s.ipos : nullptr, init_pos ? s.iquat : nullptr,
                                   s.opos, s.oquat, s.sim3, s.status, s.stream);
         if (rc != 0) break;
-        cudaMemcpyAsync(out_pos + 3 * p0, s.opos, (size_t)np * 24, cudaMemcpyDeviceToHost, s.stream);
-        cudaMemcpyAsync(out_quat + 4 * p0, s.oquat, (size_t)np * 32, cudaMemcpyDeviceToHost, s.stream);
-        if (sim3_out) cudaMemcpyAsync(sim3_out + 16 * (size_t)b0, s.sim3, (size_t)nb * 128, cudaMemcpyDeviceToHost, s.stream);
-        cudaMemcpyAsync(status + b0, s.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, s.stream);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) rc = cuda_fail(e, "gsf_fuse_batched_host(copy)");
+        copy(out_pos + 3 * p0, s.opos, (size_t)np * 24, cudaMemcpyDeviceToHost);
+        copy(out_quat + 4 * p0, s.oquat, (size_t)np * 32, cudaMemcpyDeviceToHost);
+        if (sim3_out) copy(sim3_out + 16 * (size_t)b0, s.sim3, (size_t)nb * 128, cudaMemcpyDeviceToHost);
+        copy(status + b0, s.status, (size_t)nb * 4, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) rc = cuda_fail(ce, "gsf_fuse_batched_host(D2H copy)");
     }
     for (int k = 0; k < 2; ++k) {
         if (!g_slots[k].stream) continue;

@@ -117,9 +117,15 @@ __global__ void __launch_bounds__(F32_T) fuse_f32_kernel(const F32Args A) {
     {
         const float gap = (float)prm.gap_threshold, tlim = t_first + (float)prm.max_duration;
         float tprev = t_first;
+        float tn[4], pn[12], zn[12];
+        load_group<1>(ts, 0, n, vec, tn); load_group<3>(pos, 0, n, vec, pn); load_group<3>(z, 0, n, vec, zn);
         for (int i0 = 0; i0 < n; i0 += 4) {
             float tv[4], pv[12], zv[12];
-            load_group<1>(ts, i0, n, vec, tv); load_group<3>(pos, i0, n, vec, pv); load_group<3>(z, i0, n, vec, zv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tv[k] = tn[k];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) { pv[k] = pn[k]; zv[k] = zn[k]; }
+            if (i0 + 4 < n) { load_group<1>(ts, i0 + 4, n, vec, tn); load_group<3>(pos, i0 + 4, n, vec, pn); load_group<3>(z, i0 + 4, n, vec, zn); }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (i0 + k < n) {
@@ -188,9 +194,17 @@ __global__ void __launch_bounds__(F32_T) fuse_f32_kernel(const F32Args A) {
         for (int a = 0; a < 3; ++a) { zp[a] = __ldg(z + a); pp[a] = __ldg(pos + a); e[a] = (float)(xd[a] - (double)zp[a]); y[a] = e[a]; }
     }
     int nviol = 0, bad = 0;
+    float tn[4], pn[12], zn[12], qn[16];                    // the next group's inputs are requested before the current group is processed
+    load_group<1>(ts, 0, n, vec, tn); load_group<3>(pos, 0, n, vec, pn); load_group<3>(z, 0, n, vec, zn); load_group<4>(quat, 0, n, vec, qn);
     for (int i0 = 0; i0 < n; i0 += 4) {
         float tv[4], pv[12], zv[12], qv[16], ov[12], oqv[16];
-        load_group<1>(ts, i0, n, vec, tv); load_group<3>(pos, i0, n, vec, pv); load_group<3>(z, i0, n, vec, zv); load_group<4>(quat, i0, n, vec, qv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tv[k] = tn[k];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { pv[k] = pn[k]; zv[k] = zn[k]; }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) qv[k] = qn[k];
+        if (i0 + 4 < n) { load_group<1>(ts, i0 + 4, n, vec, tn); load_group<3>(pos, i0 + 4, n, vec, pn); load_group<3>(z, i0 + 4, n, vec, zn); load_group<4>(quat, i0 + 4, n, vec, qn); }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int i = i0 + k;

@@ -899,13 +899,35 @@ __global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel
 // Deferred-trajectory counters (one per in-flight call, recycled round-robin): module-level device
 // memory, so the *_dev entry point needs no workspace argument and allocates nothing.
 __device__ int g_defer_count[128];          // pairs: [deferred count, work counter]
-cudaError_t defer_counter(int** out) {
-    static std::atomic<unsigned> ticket{0};
+// One slot per in-flight call, handed out round-robin.  A slot is released by an event recorded behind the call's last
+// kernel (defer_counter_release); a call that draws a slot whose previous user has not finished (more than 64 calls in
+// flight on different streams, or overlapping replays of a captured graph) gets cudaErrorNotReady and the caller falls
+// back to the general kernel, which needs no counters -- never a shared counter.
+static cudaEvent_t g_defer_event[64];
+static bool g_defer_event_ok[64];
+static std::atomic<unsigned> g_defer_ticket{0};
+cudaError_t defer_counter(int** out, int* slot_out) {
     int* base = nullptr;
     cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_defer_count);
     if (e != cudaSuccess) return e;
-    *out = base + 2 * (ticket.fetch_add(1) & 63u);
+    const unsigned slot = g_defer_ticket.fetch_add(1) & 63u;
+    if (g_defer_event_ok[slot]) {
+        const cudaError_t q = cudaEventQuery(g_defer_event[slot]);
+        if (q == cudaErrorNotReady) return cudaErrorNotReady;
+        if (q != cudaSuccess) { cudaGetLastError(); }
+    }
+    *out = base + 2 * slot;
+    *slot_out = (int)slot;
     return cudaSuccess;
+}
+void defer_counter_release(int slot, cudaStream_t stream) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }   // inside a graph capture: no host-side tracking
+    if (!g_defer_event_ok[slot]) {
+        if (cudaEventCreateWithFlags(&g_defer_event[slot], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+        g_defer_event_ok[slot] = true;
+    }
+    if (cudaEventRecord(g_defer_event[slot], stream) != cudaSuccess) cudaGetLastError();
 }
 
 template <int CT, int LCH>
@@ -913,14 +935,22 @@ static cudaError_t launch_fast_t(const FuseArgs& a, int num_sms, cudaStream_t st
     size_t smem = fast_smem_bytes(a.cap, CT);
     if (const char* pad = getenv("GSF_FAST_PAD_SMEM")) smem += (size_t)atoi(pad);      // tuning hook: fewer blocks per SM
     auto kern = fuse_fast_kernel<CT, LCH>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
+    // function attributes and occupancy are fixed per (instantiation, shared-memory size): looked up once, not per call
+    static std::atomic<long long> cached_smem{-1};
+    static std::atomic<int> cached_per_sm{0};
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CT + 64, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    if (cached_smem.load(std::memory_order_acquire) == (long long)smem) per_sm = cached_per_sm.load(std::memory_order_relaxed);
+    else {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CT + 64, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        cached_per_sm.store(per_sm, std::memory_order_relaxed);
+        cached_smem.store((long long)smem, std::memory_order_release);
+    }
     long long grid = (long long)num_sms * per_sm;
     if (grid > a.B) grid = a.B;
     kern<<<(unsigned)grid, CT + 64, smem, stream>>>(a);

@@ -27,7 +27,8 @@ cudaError_t launch_fuse_long(const FuseArgs& a, int num_sms, cudaStream_t stream
 // Warp-specialised fast kernel (gsf_fast.cu); fast_fuse_supported: an instantiation covers `cap`.
 bool fast_fuse_supported(int cap, int max_smem);
 cudaError_t launch_fuse_fast(const FuseArgs& a, int num_sms, cudaStream_t stream);
-cudaError_t defer_counter(int** out);
+cudaError_t defer_counter(int** out, int* slot_out);
+void defer_counter_release(int slot, cudaStream_t stream);
 cudaError_t launch_ekf_strict(const double*, const double*, const double*, const double*, const long long*,
                               const FuseParams*, int, const double*, const double*, double*, double*, int*, int, cudaStream_t);
 long long grid_work_doubles(long long n, int H);
