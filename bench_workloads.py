@@ -40,8 +40,15 @@ def measure_config5(args, rank, local_rank, world, ClockSampler, with_cpu=False,
     lo, hi = sharding.shard_range(H_total, rank, world)
     counts = [sharding.shard_range(H_total, r, world)[1] - sharding.shard_range(H_total, r, world)[0] for r in range(world)]
     tr = synth.make_loop_trajectory(2026, n=n)
-    grid = synth.noise_grid(k)
-    axes_h = [torch.from_numpy(a).pin_memory() for a in (np.logspace(-3, 1, k), np.logspace(-3, 1, k), np.logspace(-2, 1, k))]
+    # The grid is a SET of hypotheses; the q_xy axis (slowest index, the one the ranks' contiguous shards cut) is listed in a
+    # strided order, so that every shard holds small and large q_xy alike: slow filters (small q_xy) have large errors and
+    # need more full nearest-neighbour scans, and in sorted order rank 0 would get all of them.
+    stride = 8 if k % 8 == 0 else 1
+    perm = np.arange(k).reshape(k // stride, stride).T.reshape(-1)
+    qxy_axis = np.logspace(-3, 1, k)[perm]
+    qz_axis, r_axis = np.logspace(-3, 1, k), np.logspace(-2, 1, k)
+    grid = np.stack(np.meshgrid(qxy_axis, qz_axis, r_axis, indexing="ij"), axis=-1).reshape(-1, 3)
+    axes_h = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (qxy_axis, qz_axis, r_axis)]
     host = [torch.from_numpy(np.ascontiguousarray(tr[key])).pin_memory() for key in ("ts", "pos", "quat", "gps")]
     ts, pos, quat, z = [h.to(dev) for h in host]
     H = hi - lo
