@@ -41,6 +41,9 @@ namespace gsf {
 #ifndef GSF_A_EARLY
 #define GSF_A_EARLY 0               // 0: warp A starts trajectory j+2 when trajectory j releases its slot; 1 / 2: when trajectory j has finished pass B / pass C
 #endif
+#ifndef GSF_SUMS_SPLIT
+#define GSF_SUMS_SPLIT 0            // 1: the scan warp sums the last quarter of the pose pairs (see sums_share_b; measured neutral)
+#endif
 #ifndef GSF_QUAT2
 #define GSF_QUAT2 0                 // quaternion pass: poses per thread and iteration - 1
 #endif
@@ -138,7 +141,7 @@ constexpr int MB_FULL = 0, MB_QUAT = 1, MB_QUAT0 = 2, MB_TSB = 7;
 constexpr int NB_AUXRDY = 2, NB_FREE_A = 4, NB_FREE_B = 6, NB_SUMS = 8, NB_MID = 10;
 
 __host__ __device__ constexpr size_t fast_smem_bytes(int cap, int ct) {
-    return (size_t)((cap + 3) & ~1) * 64 + (size_t)(FS_PST + 6 * ct) * 8;
+    return (size_t)((cap + 3) & ~1) * 64 + (size_t)(FS_PST + 6 * ct + 16) * 8;      // ... + 16: the scan warp's partial sums
 }
 
 // 16 accumulators x 32 lanes -> lane L (bit 0 clear) ends with the warp total of value idx(L):
@@ -662,6 +665,64 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
 #endif
 }
 
+// Pivot-shifted Umeyama sums of the pose pairs [pair_lo, pair_hi) of one trajectory, streamed from global memory by one
+// warp (lane-strided pairs, NP pairs in flight per lane, fixed order -> bit-reproducible).
+template <int NP>
+__device__ __forceinline__ void stream_pose_sums(const double* __restrict__ gp, const double* __restrict__ gz, long long e0, int n,
+                                                 int pair_lo, int pair_hi, int lane, double* v,
+                                                 double ps0, double ps1, double ps2, double pz0, double pz1, double pz2) {
+    if (!(e0 & 1)) {
+        const double2* __restrict__ gp2 = reinterpret_cast<const double2*>(gp);
+        const double2* __restrict__ gz2 = reinterpret_cast<const double2*>(gz);
+#pragma unroll 1
+        for (int p = pair_lo + lane; p < pair_hi; p += 32 * NP) {
+            // NP pose pairs per round: 6 NP 128-bit loads in flight
+            double2 a[NP][3], c[NP][3];
+#pragma unroll
+            for (int h = 0; h < NP; ++h) {
+                const int pp = p + 32 * h;
+                if (pp < pair_hi && 2 * pp + 1 < n) {
+                    // plain read-only loads: the lines were requested with evict_last by the bulk prefetch, and a per-load
+                    // cache-policy operand costs two uniform-register moves per load in this loop
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { a[h][q] = __ldg(gp2 + 3 * pp + q); c[h][q] = __ldg(gz2 + 3 * pp + q); }
+                } else if (pp < pair_hi && 2 * pp < n) {        // last pose of an odd-length trajectory
+                    a[h][0] = make_double2(gp[6 * pp], gp[6 * pp + 1]); a[h][1] = make_double2(gp[6 * pp + 2], 0.0);
+                    c[h][0] = make_double2(gz[6 * pp], gz[6 * pp + 1]); c[h][1] = make_double2(gz[6 * pp + 2], 0.0);
+                    a[h][2] = make_double2(0.0, 0.0); c[h][2] = make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < NP; ++h) {
+                const int pp = p + 32 * h;
+                if (pp < pair_hi && 2 * pp < n) umeyama_accumulate(v, a[h][0].x, a[h][0].y, a[h][1].x, c[h][0].x, c[h][0].y, c[h][1].x, ps0, ps1, ps2, pz0, pz1, pz2);
+                if (pp < pair_hi && 2 * pp + 1 < n) umeyama_accumulate(v, a[h][1].y, a[h][2].x, a[h][2].y, c[h][1].y, c[h][2].x, c[h][2].y, ps0, ps1, ps2, pz0, pz1, pz2);
+            }
+        }
+    } else {
+        // odd pose offset: rows are only 8-byte aligned; same pose order, 64-bit loads
+#pragma unroll 1
+        for (int p = pair_lo + lane; p < pair_hi; p += 32) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = 2 * p + h;
+                if (i < n) umeyama_accumulate(v, gp[3 * i], gp[3 * i + 1], gp[3 * i + 2], gz[3 * i], gz[3 * i + 1], gz[3 * i + 2], ps0, ps1, ps2, pz0, pz1, pz2);
+            }
+        }
+    }
+}
+// Pose pairs (the LAST ones of the trajectory, whole 64-pair rounds) that the scan warp sums itself while it would otherwise
+// wait for the sums warp: the look-ahead chain is sums -> SVD, and the sums are its longer half (14.8 k of 23.6 k cycles at
+// 1000 poses) -- with a quarter of them on warp B, which idles ~6 k cycles per trajectory between its covariance scan and
+// the SVD, both warps finish together.  Long trajectories only (two compute warps).  Measured (round 2): warp A's streaming
+// drops from 14.8 k to 11.8 k cycles and the chain gets ~1 k cycles of slack, but the block's period stays at 23 k (31.5 vs
+// 30.8 ms per 2^20 x 1000 poses): the compute warps are as long, and every phase stretches when another shrinks -- the SM's
+// FP64 issue capacity is what the three blocks share.  Off by default.
+template <int CT>
+__device__ __forceinline__ int sums_share_b(int npairs) {
+    return (GSF_SUMS_SPLIT && CT > 32) ? ((npairs / 4 + 32) & ~63) : 0;
+}
+
 template <int CT, int LCH>
 __device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
     // (pointers are derived from the shared array here so that the accesses compile to LDS/STS, not generic loads)
@@ -707,45 +768,7 @@ __device__ __forceinline__ void fast_sums_role(const FuseArgs& A) {
         for (int q = 0; q < 16; ++q) v[q] = 0.0;
         constexpr int NP = CT <= 32 ? 1 : 2;                // pose pairs in flight per lane (short trajectories, 5 blocks per SM: one measured 4 % faster)
         const int npairs = (n + 1) >> 1;
-        if (!(e0 & 1)) {
-            const double2* __restrict__ gp2 = reinterpret_cast<const double2*>(gp);
-            const double2* __restrict__ gz2 = reinterpret_cast<const double2*>(gz);
-#pragma unroll 1
-            for (int p = lane; p < npairs; p += 32 * NP) {
-                // NP pose pairs per round: 6 NP 128-bit loads in flight
-                double2 a[NP][3], c[NP][3];
-#pragma unroll
-                for (int h = 0; h < NP; ++h) {
-                    const int pp = p + 32 * h;
-                    if (2 * pp + 1 < n) {
-#pragma unroll
-                                                // plain read-only loads: the lines were requested with evict_last by the bulk prefetch above, and a
-                        // per-load cache-policy operand costs two uniform-register moves per load in this loop
-                        for (int q = 0; q < 3; ++q) { a[h][q] = __ldg(gp2 + 3 * pp + q); c[h][q] = __ldg(gz2 + 3 * pp + q); }
-                    } else if (2 * pp < n) {                    // last pose of an odd-length trajectory
-                        a[h][0] = make_double2(gp[6 * pp], gp[6 * pp + 1]); a[h][1] = make_double2(gp[6 * pp + 2], 0.0);
-                        c[h][0] = make_double2(gz[6 * pp], gz[6 * pp + 1]); c[h][1] = make_double2(gz[6 * pp + 2], 0.0);
-                        a[h][2] = make_double2(0.0, 0.0); c[h][2] = make_double2(0.0, 0.0);
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < NP; ++h) {
-                    const int pp = p + 32 * h;
-                    if (2 * pp < n) umeyama_accumulate(v, a[h][0].x, a[h][0].y, a[h][1].x, c[h][0].x, c[h][0].y, c[h][1].x, ps0, ps1, ps2, pz0, pz1, pz2);
-                    if (2 * pp + 1 < n) umeyama_accumulate(v, a[h][1].y, a[h][2].x, a[h][2].y, c[h][1].y, c[h][2].x, c[h][2].y, ps0, ps1, ps2, pz0, pz1, pz2);
-                }
-            }
-        } else {
-            // odd pose offset: rows are only 8-byte aligned; same pose order, 64-bit loads
-#pragma unroll 1
-            for (int p = lane; p < npairs; p += 32) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int i = 2 * p + h;
-                    if (i < n) umeyama_accumulate(v, gp[3 * i], gp[3 * i + 1], gp[3 * i + 2], gz[3 * i], gz[3 * i + 1], gz[3 * i + 2], ps0, ps1, ps2, pz0, pz1, pz2);
-                }
-            }
-        }
+        stream_pose_sums<NP>(gp, gz, e0, n, 0, npairs - sums_share_b<CT>(npairs), lane, v, ps0, ps1, ps2, pz0, pz1, pz2);
         GSF_FSTAMP(18);
         const double total = butterfly16(v, lane);
         double* sums = sd + FS_SUMS + 24 * slot;
@@ -824,13 +847,27 @@ __device__ __forceinline__ void fast_scan_svd_role(const FuseArgs& A) {
             if (nx.b < A.B) issue_ts_load(A, nx.e0, nx.n, tsb, mbar + MB_TSB);
         }
         GSF_FSTAMP(26);
+        // this warp's share of the Umeyama sums (the last pose pairs), while warp A streams the rest
+        double* const sums_b = sd + FS_PST + 6 * CT + cap2;
+        const int npairs = (n + 1) >> 1, share = sums_share_b<CT>(npairs);
+        if (share > 0) {
+            const double* __restrict__ gp = A.pos + 3 * e0;
+            const double* __restrict__ gz = A.z + 3 * e0;
+            double vb[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) vb[q] = 0.0;
+            stream_pose_sums<2>(gp, gz, e0, n, npairs - share, npairs, lane, vb, gp[0], gp[1], gp[2], gz[0], gz[1], gz[2]);
+            const double tb = butterfly16(vb, lane);
+            if (!(lane & 1)) sums_b[butterfly16_index(lane)] = tb;
+            __syncwarp();
+        }
         named_sync(NB_SUMS + slot, 64);
         __threadfence_block();
         GSF_FSTAMP(27);
         const double* sums = sd + FS_SUMS + 24 * slot;
         double v[16], chk = 0.0;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { v[q] = sums[q]; chk += v[q]; }
+        for (int q = 0; q < 16; ++q) { v[q] = share > 0 ? sums[q] + sums_b[q] : sums[q]; chk += v[q]; }
         if (!(fabs(chk) <= 1.7976931348623157e308)) general = 1;       // NaN row (no GNSS) or non-finite input
         if (n < 3 || n < gprm->min_samples) general = 1;
         const Quat q0{__shfl_sync(GSF_FULL_MASK, q0c, 0), __shfl_sync(GSF_FULL_MASK, q0c, 1), __shfl_sync(GSF_FULL_MASK, q0c, 2),
