@@ -882,6 +882,30 @@ def test_dropin_entry_point(gsf, tmp_path):
     np.testing.assert_allclose(dp, dpo, atol=1e-12); np.testing.assert_allclose(dq, dqo, atol=1e-12)
 
 
+def test_relative_pose_many_pairs(gsf):
+    """calculate_relative_pose (EKFGPSSLAM.py:77-92) through the drop-in on many random pose pairs -- unnormalised
+    quaternions (scipy normalises on construction), large UTM-scale positions, a half-turn -- and the zero-quaternion
+    fallback (:84-86: zero motion, identity rotation) against the oracle (scipy Rotation)."""
+    import EKFGPSSLAM as E
+    from oracle import fusion_oracle as fo
+    rng = np.random.default_rng(31)
+    for k in range(60):
+        q1 = rng.normal(size=4) * rng.choice([1.0, 0.3, 7.0]); q2 = rng.normal(size=4) * rng.choice([1.0, 2.0])
+        if k == 7:
+            q2 = -q1.copy()                                  # same rotation, opposite sign
+        if k == 8:
+            q1 = np.array([0.0, 0.0, 1.0, 0.0]); q2 = np.array([0.0, 0.0, 0.0, 1.0])       # half-turn about z
+        p1 = rng.normal(size=3) * rng.choice([1.0, 5e6]); p2 = p1 + rng.normal(size=3) * rng.choice([0.01, 1.0, 50.0])
+        dp, dq = E.calculate_relative_pose(p1, q1, p2, q2)
+        dpo, dqo = fo.relative_pose(p1, q1, p2, q2)
+        np.testing.assert_allclose(dp, dpo, rtol=0, atol=1e-9 * max(1.0, np.abs(p2 - p1).max()))
+        assert min(np.abs(dq - dqo).max(), np.abs(dq + dqo).max()) < 1e-12 and np.abs(dq - dqo).max() < 1e-12
+    for q1, q2 in ((np.zeros(4), np.array([0.0, 0.0, 0.0, 1.0])), (np.array([0.1, 0.2, 0.3, 0.9]), np.zeros(4))):
+        dp, dq = E.calculate_relative_pose(np.zeros(3), q1, np.ones(3), q2)
+        dpo, dqo = fo.relative_pose(np.zeros(3), q1, np.ones(3), q2)
+        np.testing.assert_array_equal(dp, dpo); np.testing.assert_array_equal(dq, dqo)
+
+
 # ----------------------------------------------------------------------------- long trajectories (no length limit)
 def _nn_errors_chunked(traj, cand):
     """cdist(...).min(axis=1) of EKFGPSSLAM.py:1030-1031 in row blocks (the full matrix of a 20 000-pose
