@@ -383,44 +383,116 @@ __global__ void __launch_bounds__(256) grid_median_kernel(const double* __restri
 // are diagonal (EKFGPSSLAM.py:684-686) and H = [I3 0], so the x / y / z components of the filter are three independent
 // scalar filters: the x and y tracks depend on (q_xy, r) only, the z track on (q_z, r) only.  Kq Kr x/y tracks and
 // Kz Kr z tracks (2 x 64^2 + 64^2 = 12 288 scalar filter runs) replace the 3 x 64^3 = 786 432 the per-hypothesis
-// kernel above executes -- same arithmetic per step, so every track is bit-identical to the corresponding component
-// of ekf_grid_kernel -- and a combine kernel scores every (q_xy, q_z, r) triple against the candidate set.
-//   grid_tracks_kernel   one thread per scalar track, the whole recursion in registers; 32 x 32 tiles are transposed
-//                        through shared memory so that the table [track][pose] is written in 256-byte rows;
+// kernel above executes -- same arithmetic per step, so every track equals the corresponding component of ekf_grid_kernel
+// to rounding -- and a combine kernel scores every (q_xy, q_z, r) triple against the candidate set.
+//   tracks_*_kernel      the scalar filter runs, parallel in time (see below); 32 x 32 tiles are transposed through shared
+//                        memory so that the table [track][pose] is written in 256-byte rows;
 //   grid_combine_kernel  one block per hypothesis at a time (threads over poses -- the tracks make the poses of a
 //                        hypothesis independent, so the evaluation is parallel in time): coalesced reads of the three
 //                        track rows (L2-resident by the loop order), exact pruned nearest neighbour in the x-sorted
 //                        candidate set (shared memory), errors kept in shared memory, mean / RMSE by a fixed-order block
 //                        reduction, median by radix selection in shared memory.  No [poses, hypotheses] error table.
 static int pow2_at_least(long long n);
+// Tracks, parallel in time.  A scalar filter run is a 4541-step recursion; one thread per track makes the launch one long
+// dependent chain (0.79 ms, whatever the number of tracks -- the part of a rank's step that sharding over 8 GPUs does not
+// shrink).  The recursion is two scans: the covariance map p -> r(p + q dt)/(p + q dt + r) is a Moebius map (2x2 step
+// matrix [1 qa; g g qa + 1], g = 1/r), the state map x -> (1 - k)(x + u) + k z is affine.  Three launches over
+// (track, chunk of TRK_CHUNK steps):
+//   A  composite Moebius matrix of every chunk;
+//   B  covariance at the chunk start (product of the chunks before it, applied to P0), then the exact per-step recursion of
+//      ekf_grid_kernel through the chunk, composing the chunk's affine state map;
+//   C  state at the chunk start (composition of the chunks before it, applied to x0), the recursion once more with the
+//      state, 32 x 32 tiles transposed through shared memory into the [track][pose] table.
+// Inside a chunk every step is the arithmetic of ekf_grid_kernel; only the chunk-start values come from the scans, and the
+// covariance recursion is a contraction, so the tracks agree with the serial ones to a few 1e-16 relative.
 constexpr int TRK_THREADS = 128;
-__global__ void __launch_bounds__(TRK_THREADS) grid_tracks_kernel(const double* __restrict__ rec, const double* __restrict__ hdr, int n,
-                                                                  const FuseParams* __restrict__ base, const double* __restrict__ qxy,
-                                                                  const double* __restrict__ qz, const double* __restrict__ rr, int Kr,
-                                                                  int iq0, int nq, int iz0, int nz, double* __restrict__ tracks,
-                                                                  long long npad, const int* __restrict__ status) {
-    __shared__ double tile[TRK_THREADS / 32][32][33];
-    if (status[0] & GRID_FATAL) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nxy = nq * Kr, NT = 2 * nxy + nz * Kr;
-    const int t = blockIdx.x * TRK_THREADS + threadIdx.x;
-    const int tw0 = t - lane;                                            // first track of this warp
-    if (tw0 >= NT) return;
-    const bool live = t < NT;
-    const int tt = live ? t : NT - 1;
+constexpr int TRK_CHUNK = 128;        // steps per chunk (a multiple of 32)
+
+struct TrackSet {
+    const double* rec; const double* hdr; const FuseParams* base; const double* qxy; const double* qz; const double* rr;
+    int n, Kr, iq0, nq, iz0, nz, nchunks;
+    const int* status;
+};
+__device__ __forceinline__ void track_params(const TrackSet& T, int t, int& axis, double& q, double& r) {
+    const int nxy = T.nq * T.Kr;
+    if (t < 2 * nxy) { axis = t / nxy; const int rem = t - axis * nxy; q = T.qxy[T.iq0 + rem / T.Kr]; r = T.rr[rem % T.Kr]; }
+    else { axis = 2; const int rem = t - 2 * nxy; q = T.qz[T.iz0 + rem / T.Kr]; r = T.rr[rem % T.Kr]; }
+}
+__device__ __forceinline__ void moeb2_rescale(double* m) {
+    const int hi = max(max(__double2hiint(m[0]), __double2hiint(m[1])), max(__double2hiint(m[2]), __double2hiint(m[3])));
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const double sc = __hiloint2double((1023 - e) << 20, 0);
+    m[0] *= sc; m[1] *= sc; m[2] *= sc; m[3] *= sc;
+}
+// thread (track, chunk); layout of the chunk arrays: [chunk][track] (coalesced over the tracks of a warp)
+__global__ void __launch_bounds__(TRK_THREADS) tracks_moebius_kernel(const TrackSet T, int NT, double* __restrict__ mo) {
+    if (T.status[0] & GRID_FATAL) return;
+    const int t = blockIdx.x * TRK_THREADS + threadIdx.x, c = blockIdx.y;
+    if (t >= NT) return;
     int axis; double q, r;
-    if (tt < 2 * nxy) { axis = tt / nxy; const int rem = tt - axis * nxy; q = qxy[iq0 + rem / Kr]; r = rr[rem % Kr]; }
-    else { axis = 2; const int rem = tt - 2 * nxy; q = qz[iz0 + rem / Kr]; r = rr[rem % Kr]; }
-    double P = base->p0[axis], x = hdr[axis];
-    for (int i0 = 0; i0 < n; i0 += 32) {
-        const int cnt = min(32, n - i0);
-#pragma unroll 4
+    track_params(T, t, axis, q, r);
+    const double g = 1.0 / r;
+    double m[4] = {1.0, 0.0, 0.0, 1.0};
+    const int i0 = max(c * TRK_CHUNK, 1), i1 = min((c + 1) * TRK_CHUNK, T.n);
+    for (int i = i0; i < i1; ++i) {
+        const double qa = q * T.rec[(size_t)GRID_REC * i];
+        m[0] = fma(qa, m[2], m[0]); m[1] = fma(qa, m[3], m[1]);       // [1 qa; 0 1] * m
+        m[2] = fma(g, m[0], m[2]); m[3] = fma(g, m[1], m[3]);         // [1 0; g 1] * that
+        if (((i - i0) & 15) == 15) moeb2_rescale(m);
+    }
+    moeb2_rescale(m);
+    double* o = mo + ((size_t)c * NT + t) * 4;
+    o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = m[3];
+}
+__device__ __forceinline__ double tracks_chunk_start_cov(const TrackSet& T, int NT, const double* __restrict__ mo, int t, int c, double P0) {
+    double P = P0;
+    for (int k = 0; k < c; ++k) {                                     // the chunks before this one, in order
+        const double* m = mo + ((size_t)k * NT + t) * 4;
+        P = (m[0] * P + m[1]) * rcp_(m[2] * P + m[3]);
+    }
+    return P;
+}
+__global__ void __launch_bounds__(TRK_THREADS) tracks_affine_kernel(const TrackSet T, int NT, const double* __restrict__ mo,
+                                                                     double* __restrict__ pstart, double* __restrict__ aff) {
+    if (T.status[0] & GRID_FATAL) return;
+    const int t = blockIdx.x * TRK_THREADS + threadIdx.x, c = blockIdx.y;
+    if (t >= NT) return;
+    int axis; double q, r;
+    track_params(T, t, axis, q, r);
+    double P = tracks_chunk_start_cov(T, NT, mo, t, c, T.base->p0[axis]);
+    pstart[(size_t)c * NT + t] = P;
+    double A = 1.0, B = 0.0;
+    const int i0 = max(c * TRK_CHUNK, 1), i1 = min((c + 1) * TRK_CHUNK, T.n);
+    for (int i = i0; i < i1; ++i) {
+        const double* rc = T.rec + (size_t)GRID_REC * i;
+        const double pp = P + q * rc[0], kk = pp * rcp_(pp + r), om = 1.0 - kk;
+        P = om * pp * om + kk * r * kk;
+        B = om * (B + rc[1 + axis]) + kk * rc[4 + axis]; A *= om;
+    }
+    aff[((size_t)c * NT + t) * 2] = A; aff[((size_t)c * NT + t) * 2 + 1] = B;
+}
+__global__ void __launch_bounds__(TRK_THREADS) tracks_write_kernel(const TrackSet T, int NT, const double* __restrict__ pstart,
+                                                                    const double* __restrict__ aff, double* __restrict__ tracks, long long npad) {
+    __shared__ double tile[TRK_THREADS / 32][32][33];
+    if (T.status[0] & GRID_FATAL) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * TRK_THREADS + threadIdx.x, c = blockIdx.y;
+    const int tw0 = t - lane;
+    if (tw0 >= NT) return;
+    const int tt = t < NT ? t : NT - 1;
+    int axis; double q, r;
+    track_params(T, tt, axis, q, r);
+    double x = T.hdr[axis];
+    for (int k = 0; k < c; ++k) x = aff[((size_t)k * NT + tt) * 2] * x + aff[((size_t)k * NT + tt) * 2 + 1];
+    double P = pstart[(size_t)c * NT + tt];
+    const int c0 = c * TRK_CHUNK, c1 = min((c + 1) * TRK_CHUNK, T.n);
+    for (int i0 = c0; i0 < c1; i0 += 32) {
+        const int cnt = min(32, c1 - i0);
         for (int k = 0; k < cnt; ++k) {
             const int i = i0 + k;
             if (i > 0) {
-                const double* rc = rec + (size_t)GRID_REC * i;
-                const double dt = rc[0];
-                const double pp = P + q * dt, kk = pp * rcp_(pp + r), om = 1.0 - kk;     // the step of ekf_grid_kernel, verbatim
+                const double* rc = T.rec + (size_t)GRID_REC * i;
+                const double pp = P + q * rc[0], kk = pp * rcp_(pp + r), om = 1.0 - kk;     // the step of ekf_grid_kernel, verbatim
                 P = om * pp * om + kk * r * kk; x = om * (x + rc[1 + axis]) + kk * rc[4 + axis];
             }
             tile[warp][k][lane] = x;
@@ -532,7 +604,7 @@ struct CombineArgs {
     const unsigned short* yperm; const unsigned short* yrank;
     int n, Kz, Kr, iq0, nq, iz0, nz;
     long long h_first, h_count;
-    double* stats; const int* status;
+    double* stats; const int* status; unsigned long long* slot_counter;
 };
 struct CmbShared {
     double red[2][32];
@@ -600,7 +672,15 @@ __global__ void __launch_bounds__(CMB_THREADS, 1) grid_combine_kernel(const Comb
     }
     __syncthreads();
     const int nxy = A.nq * A.Kr;
-    for (long long slot = blockIdx.x; slot < total_slots; slot += gridDim.x) {
+    // hypotheses differ a lot in cost (slow filters have large errors and need full scans): slots are handed out by a counter,
+    // not by a static stride
+    __shared__ long long s_slot;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_slot = (long long)atomicAdd(A.slot_counter, 1ull);
+        __syncthreads();
+        const long long slot = s_slot;
+        if (slot >= total_slots) break;
         // slot -> (q_xy, q_z, r): groups of CMB_GROUP q_xy values outermost, then q_z, then r, q_xy within the group innermost
         // (32-bit arithmetic: the launcher refuses grids beyond 2^31 slots)
         const unsigned per_group = (unsigned)(CMB_GROUP * A.Kz * A.Kr);
@@ -713,7 +793,8 @@ long long noise_grid_work_doubles(long long n, int Kq, int Kz, int Kr, long long
     int iq0, nq, iz0, nz;
     noise_grid_ranges(Kz, Kr, h_first, h_count, iq0, nq, iz0, nz);
     const long long npad = (n + 31) / 32 * 32;
-    return noise_grid_head_doubles(n) + (2ll * nq + nz) * Kr * npad + 4;
+    const long long NT = (2ll * nq + nz) * Kr, nchunks = (n + 127) / 128;
+    return noise_grid_head_doubles(n) + NT * npad + 4 + 7 * nchunks * NT + 8;        // table + chunk scratch (Moebius 4, covariance 1, affine 2)
 }
 cudaError_t launch_noise_grid(const double* ts, const double* pos, const double* quat, const double* z, long long n,
                               const FuseParams* base, const double* qxy, const double* qz, const double* rr, int Kq, int Kz, int Kr,
@@ -739,6 +820,7 @@ cudaError_t launch_noise_grid(const double* ts, const double* pos, const double*
     const long long npad = (n + 31) / 32 * 32;
     int iq0, nq, iz0, nz;
     noise_grid_ranges(Kz, Kr, h_first, h_count, iq0, nq, iz0, nz);
+    double* tracks_scratch = tracks + (size_t)(2 * nq + nz) * Kr * npad + 4;
     const int cap2 = pow2_at_least(n);
     const size_t smem_prep = (size_t)cap2 * 12;
     const size_t smem_cmb = (size_t)n * 48 + 64;                           // candidates 24 + errors 8 + skip bounds 8 + two nearest 4 + y order 4 per pose
@@ -755,8 +837,18 @@ cudaError_t launch_noise_grid(const double* ts, const double* pos, const double*
     if (e != cudaSuccess) return e;
     grid_prep_ysort_kernel<<<1, 1024, smem_prep, stream>>>(cand, z, hdr, (int)n, own, yperm, yrank, st, cap2);
     const int NT = (2 * nq + nz) * Kr;
-    grid_tracks_kernel<<<(NT + TRK_THREADS - 1) / TRK_THREADS, TRK_THREADS, 0, stream>>>(rec, hdr, (int)n, base, qxy, qz, rr, Kr, iq0, nq, iz0, nz,
-                                                                                         tracks, npad, st);
+    {
+        TrackSet T;
+        T.rec = rec; T.hdr = hdr; T.base = base; T.qxy = qxy; T.qz = qz; T.rr = rr; T.n = (int)n; T.Kr = Kr; T.iq0 = iq0; T.nq = nq; T.iz0 = iz0; T.nz = nz;
+        T.nchunks = (int)((n + TRK_CHUNK - 1) / TRK_CHUNK); T.status = st;
+        double* mo = tracks_scratch;                                  // [nchunks][NT][4]
+        double* pstart = mo + (size_t)T.nchunks * NT * 4;             // [nchunks][NT]
+        double* aff = pstart + (size_t)T.nchunks * NT;                // [nchunks][NT][2]
+        const dim3 tg((NT + TRK_THREADS - 1) / TRK_THREADS, T.nchunks);
+        tracks_moebius_kernel<<<tg, TRK_THREADS, 0, stream>>>(T, NT, mo);
+        tracks_affine_kernel<<<tg, TRK_THREADS, 0, stream>>>(T, NT, mo, pstart, aff);
+        tracks_write_kernel<<<tg, TRK_THREADS, 0, stream>>>(T, NT, pstart, aff, tracks, npad);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(grid_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n * 8));
@@ -766,6 +858,9 @@ cudaError_t launch_noise_grid(const double* ts, const double* pos, const double*
     ca.cand = cand; ca.hgap = hgap; ca.near2 = near2; ca.hdr = hdr; ca.tracks = tracks; ca.npad = npad; ca.yperm = yperm; ca.yrank = yrank;
     ca.n = (int)n; ca.Kz = Kz; ca.Kr = Kr; ca.iq0 = iq0; ca.nq = nq; ca.iz0 = iz0; ca.nz = nz;
     ca.h_first = h_first; ca.h_count = h_count; ca.stats = stats; ca.status = st;
+    ca.slot_counter = reinterpret_cast<unsigned long long*>(hdr + 12);           // hdr[12]: free header slot
+    e = cudaMemsetAsync(ca.slot_counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(grid_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cmb);
     if (e != cudaSuccess) return e;
     long long blocks = h_count < num_sms ? h_count : num_sms;

@@ -106,8 +106,8 @@ int gsf_ekf_hypothesis_grid_dev(const double* ts, const double* pos, const doubl
  *      h = (iq * Kz + iz) * Kr + ir runs ExtendedKalmanFilter (:679-772) with process_noise_diag[0:2] = q_xy[iq],
  *      process_noise_diag[2] = q_z[iz], meas_noise_diag = r[ir] (x3) and everything else from `base` (one record).
  *      P0 / Q / R are diagonal (:684-686), so the x / y tracks depend on (q_xy, r) only and the z track on (q_z, r)
- *      only: Kq*Kr + Kq*Kr + Kz*Kr scalar filter runs (bit-identical to the components the per-hypothesis entry above
- *      computes) and one nearest-neighbour evaluation (:1021-1033) per hypothesis.  The call scores the hypotheses
+ *      only: Kq*Kr + Kq*Kr + Kz*Kr scalar filter runs (the components the per-hypothesis entry above computes, evaluated
+ *      parallel in time: equal to rounding) and one nearest-neighbour evaluation (:1021-1033) per hypothesis.  The call scores the hypotheses
  *      [h_first, h_first + h_count) (a rank's shard); stats [h_count,4]: mean, median, RMSE, count.  q_xy [Kq],
  *      q_z [Kz], r [Kr] device fp64.  work: gsf_noise_grid_work_doubles() doubles.  Same restriction and status as
  *      gsf_ekf_hypothesis_grid_dev. */

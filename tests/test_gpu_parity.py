@@ -613,7 +613,7 @@ def test_hypothesis_grid_matches_oracle(gsf, n, dt):
 @pytest.mark.parametrize("n,k", [(300, (5, 4, 6)), (4541, (3, 3, 4))])
 def test_noise_grid_matches_per_hypothesis_kernel_and_oracle(gsf, n, k):
     """gsf_ekf_noise_grid_dev (product grid, factored into scalar x/y and z tracks + a combine kernel) against
-    gsf_ekf_hypothesis_grid_dev on the same hypotheses (same per-step arithmetic: medians bit-identical, sums to
+    gsf_ekf_hypothesis_grid_dev on the same hypotheses (same per-step arithmetic, tracks parallel in time: equal to
     rounding) and against the oracle (EKFGPSSLAM.py:679-772, :1021-1033); a shard [h_first, h_first + h_count) that
     starts and ends inside a q_xy slab equals the same rows of the full run bit for bit."""
     from gps_optimize_slam_b200 import synth
@@ -630,9 +630,10 @@ def test_noise_grid_matches_per_hypothesis_kernel_and_oracle(gsf, n, k):
     assert int(st.cpu()[0]) == 0
     ref, sim3b, stb = gsf.hypothesis_grid(*args, dev(pack_noise_grid(grid), torch.uint8))
     stats, ref = stats.cpu().numpy(), ref.cpu().numpy()
-    np.testing.assert_array_equal(stats[:, 1], ref[:, 1])                  # medians: order statistics of identical errors
+    # same per-step arithmetic; the tracks are computed parallel in time (chunk-start values from Moebius / affine scans), so they
+    # agree with the per-hypothesis kernel's serial recursion to a few 1e-16 relative of the UTM-scale coordinates
     np.testing.assert_array_equal(stats[:, 3], ref[:, 3])
-    np.testing.assert_allclose(stats[:, [0, 2]], ref[:, [0, 2]], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(stats[:, :3], ref[:, :3], rtol=0, atol=2e-8)
     np.testing.assert_array_equal(sim3.cpu().numpy(), sim3b.cpu().numpy())
     # shard inside the grid
     h0, hc = Kz * Kr + 3, H - 2 * Kz * Kr - 5 if Kq > 3 else H - Kz * Kr - 7
