@@ -261,8 +261,9 @@ int gsf_associate_spline_dev(const double* gps_t, const double* gps_xyz, const i
                              double* work, double* aligned, uint8_t* valid, void* stream);
 
 /* ---- the same for ONE trajectory of any size (BASELINE config 4: 1e8 samples): the not-a-knot system is solved locally --
- *      32-knot chunks with a 32-knot halo, natural ends where the halo cuts a segment, the true end rows where the segment
- *      ends inside it; the cut decays like 0.268^32 = 5e-19, below fp64 rounding -- and the evaluation is one thread per
+ *      64-knot chunks with a 20-knot halo, natural ends where the halo cuts a segment, the true end rows where the segment
+ *      ends inside it; the cut decays like 0.268^20 = 4e-12 of a centimetre-sized curvature term, below fp64 rounding of the
+ *      coordinates -- and the evaluation is one thread per
  *      SLAM stamp.  gps_t [M] sorted and unique, gps_xyz [M,3], slam_t [N] (any order).  work: 3 M + 1 doubles.
  *      status [1] (may be NULL): 1 if two consecutive GNSS stamps differ by <= 1e-9 s inside a segment (the reference
  *      drops such a segment, :356-359; use gsf_associate_spline_dev for that data). */
