@@ -863,7 +863,8 @@ def test_dropin_entry_point(gsf, tmp_path):
     slam_file, gps_file = tmp_path / "slam.txt", tmp_path / "gnss.txt"
     np.savetxt(slam_file, np.column_stack((g["slam_ts"], g["slam_pos"], g["slam_quat"])))
     np.savetxt(gps_file, g["gnss_raw"], fmt="%.12f")
-    E.CONFIG["gps_filtering_ransac"]["enabled"] = False          # sklearn filter: host-only, unseeded
+    E.CONFIG["gps_filtering_ransac"]["enabled"] = True           # the shipped CONFIG: the device pre-filter runs (and removes nothing here)
+    np.random.seed(0)
     out = E.main_process(str(slam_file), str(gps_file), save_path=str(tmp_path / "slam_corrected_utm.txt"))
     assert out["utm_zone"] == "39N"
     assert abs(out["s"] - float(g["s"])) < 1e-9
@@ -1042,7 +1043,7 @@ def test_dropin_main_process_pair_b(gsf, tmp_path):
     slam_file, gps_file = tmp_path / "slam.txt", tmp_path / "gnss.txt"
     np.savetxt(slam_file, np.column_stack((g["slam_ts"], g["slam_pos"], g["slam_quat"])), fmt="%.18e")
     np.savetxt(gps_file, g["gnss_raw"], fmt="%.18e")
-    E.CONFIG["gps_filtering_ransac"]["enabled"] = False          # sklearn filter: unseeded in the reference, removes nothing here
+    E.CONFIG["gps_filtering_ransac"]["enabled"] = True           # the shipped CONFIG: the device pre-filter runs (and removes nothing here)
     np.random.seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         out = E.main_process(str(slam_file), str(gps_file))
