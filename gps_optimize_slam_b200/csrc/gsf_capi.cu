@@ -239,38 +239,42 @@ int gsf_write_pose_rows_dev(const double* ts, const double* xyz, const double* q
     return 0;
 }
 
-int gsf_to_local_f32_dev(const double* ts, const double* pos, const double* quat, const double* z, const int64_t* offsets, int32_t B,
-                         float* ts32, float* pos32, float* quat32, float* z32, double* origins, void* stream) {
+int gsf_to_local_f32_dev(const double* ts, const double* pos, const double* quat, const double* z, const int64_t* offsets,
+                         const int64_t* group_offsets, int32_t B, float* ts32, float* pos32, float* quat32, float* z32, double* origins,
+                         void* stream) {
     DeviceInfo& d = device_info();
     if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
     if (B == 0) return 0;
-    if (B < 0 || !ts || !pos || !quat || !z || !offsets || !ts32 || !pos32 || !quat32 || !z32 || !origins)
+    if (B < 0 || !ts || !pos || !quat || !z || !offsets || !group_offsets || !ts32 || !pos32 || !quat32 || !z32 || !origins)
         return fail(GSF_E_INVALID, "gsf_to_local_f32_dev: null pointer or negative size");
-    cudaError_t e = gsf::launch_to_local_f32(ts, pos, quat, z, reinterpret_cast<const long long*>(offsets), B, ts32, pos32, quat32, z32, origins,
+    cudaError_t e = gsf::launch_to_local_f32(ts, pos, quat, z, reinterpret_cast<const long long*>(offsets),
+                                             reinterpret_cast<const long long*>(group_offsets), B, ts32, pos32, quat32, z32, origins,
                                              d.sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gsf_to_local_f32_dev");
     return 0;
 }
-int gsf_from_local_f32_dev(const float* pos32, const int64_t* offsets, int32_t B, const double* origins, double* pos, void* stream) {
+int gsf_from_local_f32_dev(const float* pos32, const float* quat32, const int64_t* offsets, const int64_t* group_offsets, int32_t B,
+                           const double* origins, double* pos, double* quat, void* stream) {
     DeviceInfo& d = device_info();
     if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
     if (B == 0) return 0;
-    if (B < 0 || !pos32 || !offsets || !origins || !pos) return fail(GSF_E_INVALID, "gsf_from_local_f32_dev: null pointer or negative size");
-    cudaError_t e = gsf::launch_from_local_f32(pos32, reinterpret_cast<const long long*>(offsets), B, origins, pos, d.sms, (cudaStream_t)stream);
+    if (B < 0 || !pos32 || !offsets || !group_offsets || !origins || (!pos && !quat) || (quat && !quat32))
+        return fail(GSF_E_INVALID, "gsf_from_local_f32_dev: null pointer or negative size");
+    cudaError_t e = gsf::launch_from_local_f32(pos32, quat32, reinterpret_cast<const long long*>(offsets),
+                                               reinterpret_cast<const long long*>(group_offsets), B, origins, pos, quat, d.sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gsf_from_local_f32_dev");
     return 0;
 }
 int gsf_fuse_batched_f32_dev(const float* ts32, const float* pos32, const float* quat32, const float* z32, const double* origins,
-                             const int64_t* offsets, int32_t B, const gsf_fuse_params* params, int32_t params_per_traj,
-                             float* out_pos32, float* out_quat32, double* sim3_out, int32_t* status, void* stream) {
+                             const int64_t* offsets, const int64_t* group_offsets, int32_t B, const gsf_fuse_params* params,
+                             int32_t params_per_traj, float* out_pos32, float* out_quat32, double* sim3_out, int32_t* status, void* stream) {
     DeviceInfo& d = device_info();
     if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
     if (B == 0) return 0;
-    if (B < 0 || !ts32 || !pos32 || !quat32 || !z32 || !origins || !offsets || !params || !out_pos32 || !out_quat32 || !status)
+    if (B < 0 || !ts32 || !pos32 || !quat32 || !z32 || !origins || !offsets || !group_offsets || !params || !out_pos32 || !out_quat32 || !status)
         return fail(GSF_E_INVALID, "gsf_fuse_batched_f32_dev: null pointer or negative size");
-    if (!aligned16(ts32) || !aligned16(pos32) || !aligned16(quat32) || !aligned16(z32) || !aligned16(out_pos32) || !aligned16(out_quat32))
-        return fail(GSF_E_INVALID, "gsf_fuse_batched_f32_dev: arrays must be 16-byte aligned");
-    cudaError_t e = gsf::launch_fuse_f32(ts32, pos32, quat32, z32, origins, reinterpret_cast<const long long*>(offsets), B,
+    cudaError_t e = gsf::launch_fuse_f32(ts32, pos32, quat32, z32, origins, reinterpret_cast<const long long*>(offsets),
+                                         reinterpret_cast<const long long*>(group_offsets), B,
                                          reinterpret_cast<const gsf::FuseParams*>(params), params_per_traj, out_pos32, out_quat32, sim3_out,
                                          status, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_f32_dev");

@@ -80,11 +80,11 @@ cudaError_t launch_parse_table(const char*, long long, int, int, double*, long l
 long long write_rows_work_bytes(long long n);
 cudaError_t launch_write_pose_rows(const double*, const double*, const double*, long long, const int*, const char*, int, char*, long long,
                                    void*, long long*, cudaStream_t);
-cudaError_t launch_to_local_f32(const double*, const double*, const double*, const double*, const long long*, int, float*, float*, float*, float*,
-                                double*, int, cudaStream_t);
-cudaError_t launch_from_local_f32(const float*, const long long*, int, const double*, double*, int, cudaStream_t);
-cudaError_t launch_fuse_f32(const float*, const float*, const float*, const float*, const double*, const long long*, int, const FuseParams*, int,
-                            float*, float*, double*, int*, cudaStream_t);
+cudaError_t launch_to_local_f32(const double*, const double*, const double*, const double*, const long long*, const long long*, int, float*, float*,
+                                float*, float*, double*, int, cudaStream_t);
+cudaError_t launch_from_local_f32(const float*, const float*, const long long*, const long long*, int, const double*, double*, double*, int, cudaStream_t);
+cudaError_t launch_fuse_f32(const float*, const float*, const float*, const float*, const double*, const long long*, const long long*, int,
+                            const FuseParams*, int, float*, float*, double*, int*, cudaStream_t);
 struct SynthArgs {
     double* ts; double* pos; double* quat; double* z;
     long long traj0; int B; int n; double dt; double speed; unsigned long long seed;

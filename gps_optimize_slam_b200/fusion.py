@@ -277,64 +277,76 @@ def write_pose_rows(ts, xyz, quat, decimals, header: str = "", stream=None):
     return out[:nbytes]
 
 
+class F32Batch:
+    """The fp32 mode's storage of a batch (see include/gsf.h: fp32 relative to fp64 origins, interleaved by 32 trajectories)."""
+
+    def __init__(self, ts32, pos32, quat32, z32, origins, offsets, group_offsets):
+        self.ts32, self.pos32, self.quat32, self.z32 = ts32, pos32, quat32, z32
+        self.origins, self.offsets, self.group_offsets = origins, offsets, group_offsets
+
+    @property
+    def B(self):
+        return self.offsets.numel() - 1
+
+
+def f32_group_offsets(offsets):
+    """offsets [B+1] (device int64) -> group_offsets [ceil(B/32)+1]: running sum of every 32-trajectory group's longest length."""
+    lengths = offsets[1:] - offsets[:-1]
+    B = lengths.numel()
+    G = (B + 31) // 32
+    padded = torch.zeros((G * 32,), dtype=torch.int64, device=offsets.device)
+    padded[:B] = lengths
+    Lg = padded.reshape(G, 32).max(dim=1).values
+    return torch.cat([torch.zeros((1,), dtype=torch.int64, device=offsets.device), torch.cumsum(Lg, 0)])
+
+
 def to_local_f32(ts, pos, quat, z, offsets, stream=None):
-    """fp64 absolute arrays -> the fp32 mode's storage (gsf_to_local_f32_dev): (ts32, pos32, quat32, z32, origins [B,7])."""
+    """fp64 AoS arrays -> the fp32 mode's storage (gsf_to_local_f32_dev).  Returns an F32Batch (one host sync: the padded size)."""
     lib = _lib.load()
     _require_cuda(ts, pos, quat, z, offsets)
     B = offsets.numel() - 1
     dev = ts.device
-    ts32 = torch.empty(ts.shape, dtype=torch.float32, device=dev); pos32 = torch.empty(pos.shape, dtype=torch.float32, device=dev)
-    quat32 = torch.empty(quat.shape, dtype=torch.float32, device=dev); z32 = torch.empty(z.shape, dtype=torch.float32, device=dev)
-    origins = torch.empty((B, 7), dtype=torch.float64, device=dev)
-    rc = lib.gsf_to_local_f32_dev(_ptr(ts), _ptr(pos), _ptr(quat), _ptr(z), _ptr(offsets), B, _ptr(ts32), _ptr(pos32), _ptr(quat32), _ptr(z32),
-                                  _ptr(origins), _stream_ptr(stream))
+    go = f32_group_offsets(offsets)
+    rows = int(go[-1].item())
+    ts32 = torch.empty((rows * 32,), dtype=torch.float32, device=dev); pos32 = torch.empty((rows * 96,), dtype=torch.float32, device=dev)
+    quat32 = torch.empty((rows * 128,), dtype=torch.float32, device=dev); z32 = torch.empty((rows * 96,), dtype=torch.float32, device=dev)
+    origins = torch.zeros((B, 7), dtype=torch.float64, device=dev)
+    rc = lib.gsf_to_local_f32_dev(_ptr(ts), _ptr(pos), _ptr(quat), _ptr(z), _ptr(offsets), _ptr(go), B, _ptr(ts32), _ptr(pos32), _ptr(quat32),
+                                  _ptr(z32), _ptr(origins), _stream_ptr(stream))
     _lib.check(rc, "gsf_to_local_f32_dev")
-    return ts32, pos32, quat32, z32, origins
+    return F32Batch(ts32, pos32, quat32, z32, origins, offsets, go)
 
 
-def from_local_f32(pos32, offsets, origins, stream=None):
-    """fused positions of the fp32 mode back to fp64 absolute coordinates (gsf_from_local_f32_dev)."""
+def from_local_f32(batch, pos32, quat32=None, stream=None):
+    """fused positions (and quaternions) of the fp32 mode back to fp64 AoS arrays (gsf_from_local_f32_dev)."""
     lib = _lib.load()
-    _require_cuda(pos32, offsets, origins)
-    out = torch.empty(pos32.shape, dtype=torch.float64, device=pos32.device)
-    rc = lib.gsf_from_local_f32_dev(_ptr(pos32), _ptr(offsets), offsets.numel() - 1, _ptr(origins), _ptr(out), _stream_ptr(stream))
+    _require_cuda(pos32)
+    P = int(batch.offsets[-1].item())
+    dev = pos32.device
+    out_p = torch.empty((P, 3), dtype=torch.float64, device=dev)
+    out_q = torch.empty((P, 4), dtype=torch.float64, device=dev) if quat32 is not None else None
+    rc = lib.gsf_from_local_f32_dev(_ptr(pos32), _ptr(quat32), _ptr(batch.offsets), _ptr(batch.group_offsets), batch.B, _ptr(batch.origins),
+                                    _ptr(out_p), _ptr(out_q), _stream_ptr(stream))
     _lib.check(rc, "gsf_from_local_f32_dev")
-    return out
+    return out_p if quat32 is None else (out_p, out_q)
 
 
-def fuse_batched_f32(ts32, pos32, quat32, z32, origins, offsets, params, params_per_traj=False, out_pos=None, out_quat=None,
-                     sim3_out=None, status=None, stream=None):
-    """Optional fp32 mode of the fused path (gsf_fuse_batched_f32_dev).  Returns (out_pos32, out_quat32, sim3 [B,16], status)."""
+def fuse_batched_f32(batch, params, params_per_traj=False, out_pos=None, out_quat=None, sim3_out=None, status=None, stream=None):
+    """Optional fp32 mode of the fused path (gsf_fuse_batched_f32_dev) on an F32Batch.
+    Returns (out_pos32, out_quat32 in the batch's interleaved layout, sim3 [B,16], status [B]); asynchronous."""
     lib = _lib.load()
-    _require_cuda(ts32, pos32, quat32, z32, origins, offsets, params)
-    B = offsets.numel() - 1
-    dev = ts32.device
-    out_pos = torch.empty_like(pos32) if out_pos is None else out_pos
-    out_quat = torch.empty_like(quat32) if out_quat is None else out_quat
+    _require_cuda(batch.ts32, params)
+    B = batch.B
+    dev = batch.ts32.device
+    out_pos = torch.empty_like(batch.pos32) if out_pos is None else out_pos
+    out_quat = torch.empty_like(batch.quat32) if out_quat is None else out_quat
     sim3_out = torch.empty((B, 16), dtype=torch.float64, device=dev) if sim3_out is None else sim3_out
     status = torch.empty((B,), dtype=torch.int32, device=dev) if status is None else status
-    rc = lib.gsf_fuse_batched_f32_dev(_ptr(ts32), _ptr(pos32), _ptr(quat32), _ptr(z32), _ptr(origins), _ptr(offsets), B, _ptr(params),
-                                      int(bool(params_per_traj)), _ptr(out_pos), _ptr(out_quat), _ptr(sim3_out), _ptr(status),
-                                      _stream_ptr(stream))
+    rc = lib.gsf_fuse_batched_f32_dev(_ptr(batch.ts32), _ptr(batch.pos32), _ptr(batch.quat32), _ptr(batch.z32), _ptr(batch.origins),
+                                      _ptr(batch.offsets), _ptr(batch.group_offsets), B, _ptr(params), int(bool(params_per_traj)),
+                                      _ptr(out_pos), _ptr(out_quat), _ptr(sim3_out), _ptr(status), _stream_ptr(stream))
     _lib.check(rc, "gsf_fuse_batched_f32_dev")
     return out_pos, out_quat, sim3_out, status
-
-
-def associate_spline_long(gps_t, gps_xyz, slam_t, gap, stream=None):
-    """dynamic_time_alignment for one trajectory of any size (gsf_associate_spline_long_dev): local-halo spline solve.
-    Returns (aligned [N,3], valid [N] uint8, status [1] int32); asynchronous."""
-    lib = _lib.load()
-    _require_cuda(gps_t, gps_xyz, slam_t)
-    M, N = int(gps_t.numel()), int(slam_t.numel())
-    dev = gps_t.device
-    work = torch.empty((3 * M + 2,), dtype=torch.float64, device=dev)
-    aligned = torch.empty((N, 3), dtype=torch.float64, device=dev)
-    valid = torch.empty((N,), dtype=torch.uint8, device=dev)
-    status = torch.zeros((1,), dtype=torch.int32, device=dev)
-    rc = lib.gsf_associate_spline_long_dev(_ptr(gps_t), _ptr(gps_xyz), M, _ptr(slam_t), N, float(gap), _ptr(work), _ptr(aligned), _ptr(valid),
-                                           _ptr(status), _stream_ptr(stream))
-    _lib.check(rc, "gsf_associate_spline_long_dev")
-    return aligned, valid, status
 
 
 def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, params_per_traj=False, stream=None):

@@ -153,22 +153,27 @@ int gsf_write_pose_rows_dev(const double* ts, const double* xyz, const double* q
                             void* stream);
 
 /* ---- optional fp32 mode of the fused path (same stages as gsf_fuse_batched_dev; target 1e-4 m).  Storage is fp32 relative
- *      to per-trajectory fp64 origins: origins [B,7] = t0, SLAM origin (3), UTM origin (3); ts32 = ts - t0,
- *      pos32 = pos - SLAM origin, z32 = z - UTM origin (NaN row = no GNSS), quat32; outputs out_pos32 (fused position - UTM
- *      origin) and out_quat32.  44 B in + 28 B out per pose instead of 88 + 56.  Reductions (Umeyama sums), the SVD and
- *      pose 0 are fp64; the filter runs in fp32 in innovation form (state minus measurement), so its rounding is 1e-7 of
- *      metres, and the result is limited by the fp32 storage of the relative coordinates (6e-5 m at 1 km from the origin).
- *      sim3_out [B,16] as in gsf_fuse_batched_dev, t in the absolute frames.  One thread per trajectory; trajectory offsets
- *      that are multiples of 4 poses get 128-bit loads.  Trajectories that need the general machinery (a pose without GNSS,
- *      a GNSS gap, the Sim3 window, a step <= 1e-6 s, too few points, a zero first quaternion) return GSF_ST_NEEDS_FP64 and
- *      NaN rows.  gsf_to_local_f32_dev / gsf_from_local_f32_dev convert fp64 absolute arrays to the format and fused
- *      positions back (origin: the middle pose). */
-int gsf_to_local_f32_dev(const double* ts, const double* pos, const double* quat, const double* z, const int64_t* offsets, int32_t B,
-                         float* ts32, float* pos32, float* quat32, float* z32, double* origins, void* stream);
-int gsf_from_local_f32_dev(const float* pos32, const int64_t* offsets, int32_t B, const double* origins, double* pos, void* stream);
+ *      to per-trajectory fp64 origins -- origins [B,7] = t0, SLAM origin (3), UTM origin (3); ts32 = ts - t0,
+ *      pos32 = pos - SLAM origin, z32 = z - UTM origin (NaN = no GNSS), quat32; outputs out_pos32 (fused position - UTM
+ *      origin), out_quat32 -- and INTERLEAVED BY 32 TRAJECTORIES: trajectories 32 g .. 32 g + 31 form group g, padded to
+ *      its longest member; group_offsets [ceil(B/32) + 1] (int64) = running sum of the padded lengths; element (pose i,
+ *      component c, member l) of a W-component array lives at ((group_offsets[g] + i) * W + c) * 32 + l.  A warp is a
+ *      group, so every access is one 128-byte line.  44 B in + 28 B out per pose instead of 88 + 56.
+ *      Reductions (Umeyama sums), the SVD and pose 0 are fp64; the filter runs in fp32 in innovation form (state minus
+ *      measurement), so its rounding is 1e-7 of metres and the result is limited by the fp32 storage of the relative
+ *      coordinates (6e-5 m at 1 km from the origin).  sim3_out [B,16] as in gsf_fuse_batched_dev, t in the absolute
+ *      frames.  One thread per trajectory.  Trajectories that need the general machinery (a pose without GNSS, a GNSS gap,
+ *      the Sim3 window, a step <= 1e-6 s, too few points, a zero first quaternion) return GSF_ST_NEEDS_FP64 and NaN rows.
+ *      gsf_to_local_f32_dev / gsf_from_local_f32_dev convert fp64 AoS arrays (offsets [B+1]) to the format and the fused
+ *      positions / quaternions back (origin: the middle pose; `pos` or `quat` may be NULL in the second). */
+int gsf_to_local_f32_dev(const double* ts, const double* pos, const double* quat, const double* z, const int64_t* offsets,
+                         const int64_t* group_offsets, int32_t B, float* ts32, float* pos32, float* quat32, float* z32, double* origins,
+                         void* stream);
+int gsf_from_local_f32_dev(const float* pos32, const float* quat32, const int64_t* offsets, const int64_t* group_offsets, int32_t B,
+                           const double* origins, double* pos, double* quat, void* stream);
 int gsf_fuse_batched_f32_dev(const float* ts32, const float* pos32, const float* quat32, const float* z32, const double* origins,
-                             const int64_t* offsets, int32_t B, const gsf_fuse_params* params, int32_t params_per_traj,
-                             float* out_pos32, float* out_quat32, double* sim3_out, int32_t* status, void* stream);
+                             const int64_t* offsets, const int64_t* group_offsets, int32_t B, const gsf_fuse_params* params,
+                             int32_t params_per_traj, float* out_pos32, float* out_quat32, double* sim3_out, int32_t* status, void* stream);
 
 /* ---- apply_ekf_correction (:831-935), literal step-by-step recursion, one thread per
  *      trajectory (general path; keeps the zero-motion fallback of :84-86). */

@@ -824,9 +824,9 @@ def test_text_parser_and_writer_match_numpy(gsf, tmp_path):
 
 
 def test_fp32_mode_within_1e_4_m(gsf):
-    """Optional fp32 mode (gsf_fuse_batched_f32_dev: fp32 storage relative to fp64 origins, fp64 reductions and SVD, fp32
-    filter in innovation form) against the fp64 oracle on the ORIGINAL data: positions within 1e-4 m (north star), rotation
-    and quaternions at fp32 rounding; ragged batch (aligned and unaligned offsets); a trajectory with an outage is
+    """Optional fp32 mode (gsf_fuse_batched_f32_dev: fp32 storage relative to fp64 origins and interleaved by 32
+    trajectories, fp64 reductions and SVD, fp32 filter in innovation form) against the fp64 oracle on the ORIGINAL data: positions within 1e-4 m (north star), rotation
+    and quaternions at fp32 rounding; ragged batch (a partly filled group of 32, lengths 8 .. 1000); a trajectory with an outage is
     handed back with GSF_ST_NEEDS_FP64; the fp64 fused kernel on the same batch agrees to the same tolerance."""
     from gps_optimize_slam_b200 import _lib, synth
     from oracle import fusion_oracle as fo
@@ -834,10 +834,10 @@ def test_fp32_mode_within_1e_4_m(gsf):
     trajs[4] = synth.make_trajectory(304, n=517, outages=[(100, 140)])
     ts, pos, quat, z, off, offs, maxlen = pack(trajs)
     prm = gsf.params_tensor()
-    ts32, pos32, quat32, z32, origins = gsf.to_local_f32(ts, pos, quat, z, off)
-    p32, q32, sim3, st = gsf.fuse_batched_f32(ts32, pos32, quat32, z32, origins, off, prm)
-    p = gsf.from_local_f32(p32, off, origins).cpu().numpy()
-    q32, sim3, st = q32.cpu().numpy().astype(np.float64), sim3.cpu().numpy(), st.cpu().numpy()
+    batch = gsf.to_local_f32(ts, pos, quat, z, off)
+    p32, q32, sim3, st = gsf.fuse_batched_f32(batch, prm)
+    p, q32 = gsf.from_local_f32(batch, p32, q32)
+    p, q32, sim3, st = p.cpu().numpy(), q32.cpu().numpy(), sim3.cpu().numpy(), st.cpu().numpy()
     p64, q64, sim64, st64 = gsf.fuse_batched(ts, pos, quat, z, off, maxlen, prm)
     p64 = p64.cpu().numpy()
     cfg = fo.default_config()
