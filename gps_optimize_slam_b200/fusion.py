@@ -349,6 +349,23 @@ def fuse_batched_f32(batch, params, params_per_traj=False, out_pos=None, out_qua
     return out_pos, out_quat, sim3_out, status
 
 
+def associate_spline_long(gps_t, gps_xyz, slam_t, gap, stream=None):
+    """dynamic_time_alignment for one trajectory of any size (gsf_associate_spline_long_dev): local-halo spline solve.
+    Returns (aligned [N,3], valid [N] uint8, status [1] int32); asynchronous."""
+    lib = _lib.load()
+    _require_cuda(gps_t, gps_xyz, slam_t)
+    M, N = int(gps_t.numel()), int(slam_t.numel())
+    dev = gps_t.device
+    work = torch.empty((3 * M + 2,), dtype=torch.float64, device=dev)
+    aligned = torch.empty((N, 3), dtype=torch.float64, device=dev)
+    valid = torch.empty((N,), dtype=torch.uint8, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    rc = lib.gsf_associate_spline_long_dev(_ptr(gps_t), _ptr(gps_xyz), M, _ptr(slam_t), N, float(gap), _ptr(work), _ptr(aligned), _ptr(valid),
+                                           _ptr(status), _stream_ptr(stream))
+    _lib.check(rc, "gsf_associate_spline_long_dev")
+    return aligned, valid, status
+
+
 def ekf_strict_batched(ts, pos, quat, z, offsets, params, init_pos, init_quat, params_per_traj=False, stream=None):
     """Literal step-by-step EKF recursion, one thread per trajectory (gsf_ekf_strict_batched_dev)."""
     lib = _lib.load()

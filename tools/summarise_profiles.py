@@ -24,7 +24,8 @@ def raw(path):
 
 def summarise(name, kernel, what, units=None, bytes_per_unit=None, unit_name="pose"):
     rp = f"gpurun_out/p_{name}_raw.csv"
-    if not os.path.exists(rp):
+    if not os.path.exists(rp) or sum(1 for _ in open(rp)) < 3:
+        print("no capture for", name)
         return None
     m = raw(rp)
     num = lambda k: float(m[k][1].replace(",", ""))
