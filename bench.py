@@ -2,7 +2,7 @@
 """Benchmark of the fused GPS/SLAM path (BASELINE.json: "EKF pose-updates/s + Sim3 aligned
 pts/s at 1/2/4/8 B200; % HBM roofline").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config3|config2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config3|config2|config4|config5]
 
 Workload (default ``config3``): 2^20 synthetic trajectories x 1000 poses (BASELINE.json
 configs[2]), generated on the device, resident in HBM, sharded by trajectory across the N
@@ -11,6 +11,10 @@ the rank's shard (two kernel launches: the warp-specialised fast kernel, then th
 kernel over whatever the fast one deferred): Sim3 point selection + Umeyama + all-points residual check + EKF/RTS for
 every trajectory (N-1 pose updates and N Sim3-aligned points per trajectory).
 Prints one JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
+After the timed loop the same line gets: ``e2e`` (host-buffer entry, pinned memory, with the host copy ceiling beside it),
+``ate`` (NN-ATE of the whole shard + NCCL gather of the statistics, device-timed), ``general_path`` (10 % / 50 % outage
+trajectories), ``cpu_baseline`` (oracle port, all cores and one core), ``config5`` (noise-grid workload as a sub-record,
+hypotheses sharded over the ranks) and ``fp32_mode``.
 """
 from __future__ import annotations
 
@@ -195,7 +199,7 @@ def main():
     ap.add_argument("--e2e-trajectories", type=int, default=0, help="host-buffer sample per rank (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
-    ap.add_argument("--with-ate", action="store_true", help="also run the NN-ATE kernel at N=1 (always on for N>1, with the NCCL gather)")
+    ap.add_argument("--with-ate", action="store_true", help="(kept for compatibility: the NN-ATE of the shard and the gather of its statistics always run)")
     ap.add_argument("--ate-trajectories", type=int, default=0, help="trajectories per rank scored by the NN-ATE kernel (0 = the whole shard)")
     ap.add_argument("--outage-prob", type=float, default=0.0, help="fraction of trajectories with a GNSS outage (general kernel + RTS) in the main workload")
     ap.add_argument("--no-mixed", action="store_true", help="skip the mixed fast / general-path records (10 % and 50 % outage trajectories)")
@@ -355,36 +359,35 @@ def main():
     #      output (56 B/pose read: trajectory 24 + candidates 24 + stamps 8), then the only collective of the path: the
     #      full [B, 4] table gathered with one NCCL all_gather over NVLink.  Device-timed (CUDA events), max over ranks.
     ate = None
-    if True:
-        Ba = B_res if args.ate_trajectories <= 0 else min(B_res, args.ate_trajectories)
-        counts = None
-        if world > 1 and Ba == B_res and passes == 1:
-            counts = [sharding.shard_range(B_total, r, world)[1] - sharding.shard_range(B_total, r, world)[0] for r in range(world)]
-        for _ in range(2):                                                       # warm the kernel and the communicator
-            stats = fusion.ate_nn_batched(out_pos[: Ba * n], z[: Ba * n], ts[: Ba * n], off[: Ba + 1], n, 5.0)
-            table = sharding.gather_stats(stats, counts=counts)
-        barrier()
-        ea = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        ea[0].record()
+    Ba = B_res if args.ate_trajectories <= 0 else min(B_res, args.ate_trajectories)
+    counts = None
+    if world > 1 and Ba == B_res and passes == 1:
+        counts = [sharding.shard_range(B_total, r, world)[1] - sharding.shard_range(B_total, r, world)[0] for r in range(world)]
+    for _ in range(2):                                                       # warm the kernel and the communicator
         stats = fusion.ate_nn_batched(out_pos[: Ba * n], z[: Ba * n], ts[: Ba * n], off[: Ba + 1], n, 5.0)
-        ea[1].record()
         table = sharding.gather_stats(stats, counts=counts)
-        ea[2].record()
-        torch.cuda.synchronize(dev)
-        ate_ms = sharding.max_over_ranks(ea[0].elapsed_time(ea[1]), dev)
-        gather_ms = sharding.max_over_ranks(ea[1].elapsed_time(ea[2]), dev)
-        s_ = table.cpu()
-        ok = torch.isfinite(s_[:, 2])
-        ate_gbs = Ba * n * 56 / (ate_ms * 1e-3) / 1e9
-        ate = {"trajectories": int(s_.shape[0]), "per_rank": Ba, "mean_rmse_m": float(s_[ok, 2].mean()),
-               "mean_median_m": float(s_[ok, 1].mean()), "mean_of_means_m": float(s_[ok, 0].mean()),
-               "kernel_ms_per_rank": ate_ms, "gather_ms": gather_ms, "kernel_seconds_per_rank": ate_ms * 1e-3, "gather_seconds": gather_ms * 1e-3,
-               "poses_per_s": world * Ba * n / (ate_ms * 1e-3),
-               "roofline": {"bound": "hbm", "achieved": ate_gbs, "peak": peak, "unit": "GB/s", "frac": ate_gbs / peak,
-                            "kernel": "ate_nn_kernel", "algorithmic_bytes_per_launch": Ba * n * 56, "launch_ms": ate_ms},
-               "ms_relative_to_fused_step": ate_ms / launch_ms * (B_res / Ba),
-               "gathered_with": "nccl all_gather_into_tensor" if world > 1 else "single rank (no collective)"}
-        del stats, table
+    barrier()
+    ea = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ea[0].record()
+    stats = fusion.ate_nn_batched(out_pos[: Ba * n], z[: Ba * n], ts[: Ba * n], off[: Ba + 1], n, 5.0)
+    ea[1].record()
+    table = sharding.gather_stats(stats, counts=counts)
+    ea[2].record()
+    torch.cuda.synchronize(dev)
+    ate_ms = sharding.max_over_ranks(ea[0].elapsed_time(ea[1]), dev)
+    gather_ms = sharding.max_over_ranks(ea[1].elapsed_time(ea[2]), dev)
+    s_ = table.cpu()
+    ok = torch.isfinite(s_[:, 2])
+    ate_gbs = Ba * n * 56 / (ate_ms * 1e-3) / 1e9
+    ate = {"trajectories": int(s_.shape[0]), "per_rank": Ba, "mean_rmse_m": float(s_[ok, 2].mean()),
+           "mean_median_m": float(s_[ok, 1].mean()), "mean_of_means_m": float(s_[ok, 0].mean()),
+           "kernel_ms_per_rank": ate_ms, "gather_ms": gather_ms, "kernel_seconds_per_rank": ate_ms * 1e-3, "gather_seconds": gather_ms * 1e-3,
+           "poses_per_s": world * Ba * n / (ate_ms * 1e-3),
+           "roofline": {"bound": "hbm", "achieved": ate_gbs, "peak": peak, "unit": "GB/s", "frac": ate_gbs / peak,
+                        "kernel": "ate_nn_kernel", "algorithmic_bytes_per_launch": Ba * n * 56, "launch_ms": ate_ms},
+           "ms_relative_to_fused_step": ate_ms / launch_ms * (B_res / Ba),
+           "gathered_with": "nccl all_gather_into_tensor" if world > 1 else "single rank (no collective)"}
+    del stats, table
 
     # ---- the general path at scale (outages -> general kernel + closed-form RTS, EKFGPSSLAM.py:875-928): the first slab of the
     #      resident buffers is regenerated with 10 % / 50 % of the trajectories carrying a GNSS outage and re-timed
