@@ -449,6 +449,19 @@ def main():
         except Exception as exc:                                         # never lose the headline line to the sub-record
             config5 = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- config 4 (one 1e8-sample trajectory: ingest + spline association + Umeyama reduction + transform) as a sub-record:
+    #      specified for one GPU (replicas only), so rank 0 runs it while the others wait
+    config4 = None
+    if not args.no_config5 and args.workload == "config3":
+        if rank == 0:
+            try:
+                a4 = argparse.Namespace(poses=0, steps=3, warmup=3)
+                config4 = bw.measure_config4(a4, local_rank, ClockSampler, read_peak, with_cpu=False)
+            except Exception as exc:
+                config4 = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+        barrier()
+
     # ---- optional fp32 mode (gsf_fuse_batched_f32_dev) on a slab of the same generator: fp32 storage relative to fp64 origins
     fp32 = None
     if not args.no_config5 and args.workload == "config3":
@@ -497,7 +510,7 @@ def main():
                        "outage_prob": args.outage_prob},
             "sim3_aligned_points_per_s": sim3_pts,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 2 * args.steps * passes, "ate": ate, "general_path": mixed, "config5": config5, "fp32_mode": fp32,
+            "gpu_launches": 2 * args.steps * passes, "ate": ate, "general_path": mixed, "config5": config5, "config4": config4, "fp32_mode": fp32,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -206,13 +206,21 @@ def cpu_baseline_config5(tr, grid, cores, per_core=2):
 
 def run_config4(args, rank, local_rank, world, ClockSampler, read_peak):
     """Replicas only: the single long trajectory is specified for one GPU."""
+    if rank != 0:
+        return
+    line = measure_config4(args, local_rank, ClockSampler, read_peak, with_cpu=not args.no_cpu_baseline)
+    print(json.dumps(line), flush=True)
+
+
+def measure_config4(args, local_rank, ClockSampler, read_peak, with_cpu=False, steps=None, warmup=None):
+    """config 4 on one GPU -> the record (dict)."""
     import torch
     from gps_optimize_slam_b200 import fusion
 
-    if rank != 0:
-        return
     dev = torch.device("cuda", local_rank)
-    n = args.poses or 100_000_000
+    n = getattr(args, "poses", 0) or 100_000_000
+    steps = steps or args.steps
+    warmup = max(3, warmup or args.warmup)
     g = torch.Generator(device=dev); g.manual_seed(4)
     # GNSS rows (ts, lat, lon, alt) of a long drive inside one UTM zone; SLAM positions = the ENU track in a
     # Sim3-related frame + noise; quaternions about z.  GNSS stamps = SLAM stamps (association = identity, stated).
@@ -254,13 +262,13 @@ def run_config4(args, rank, local_rank, world, ClockSampler, read_peak):
         if ev: ev[4].record()
         return R, t, s, st
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize(dev)
     sampler = ClockSampler(local_rank); sampler.start()
     stage = [[], [], [], []]
     t_all = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         ev = _events(torch, 5)
         ev[0].record()
         R, t, s, st = step(ev)
@@ -283,10 +291,10 @@ def run_config4(args, rank, local_rank, world, ClockSampler, read_peak):
                                  {"ms": ms_assoc, "GB/s": n * 113 / (ms_assoc * 1e-3) / 1e9, "pts_per_s": n / (ms_assoc * 1e-3)},
                                  "sim3_apply_kernel (112 B/pt)": {"ms": ms_apply, "GB/s": n * 112 / (ms_apply * 1e-3) / 1e9}}}
     cpu = None
-    if not args.no_cpu_baseline:
+    if with_cpu:
         cpu = cpu_baseline_config4(rows[:2_000_000].cpu().numpy(), pos[:2_000_000].cpu().numpy(), quat[:2_000_000].cpu().numpy())
     line = {"metric": "Sim3 aligned pts/s (GNSS ingest + spline association + Umeyama reduction + transform, single trajectory)", "value": n / (ms * 1e-3),
-            "unit": "pts/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "unit": "pts/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"config4: single {n}-pose trajectory: ENU conversion + Sim3 alignment",
                        "stages_ms": {"gnss_ingest_utm": ms_ingest, "spline_association": ms_assoc, "umeyama_reduce": ms_reduce, "transform_apply": ms_apply},
@@ -296,8 +304,8 @@ def run_config4(args, rank, local_rank, world, ClockSampler, read_peak):
                        "ingest_pts_per_s": n / (ms_ingest * 1e-3), "parallelism": "single GPU (replicas only)",
                        "l2": "arrays of 0.8-3.2 GB each: far beyond L2, no flush needed",
                        "recovered_scale_error": scale_err, "status": int(st.cpu()[0]), "zone": int(zone.cpu()[2])},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": 10 * args.steps}
-    print(json.dumps(line), flush=True)
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": 10 * steps}
+    return line
 
 
 def cpu_baseline_config4(rows, pos, quat):
