@@ -570,27 +570,45 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 zS[3 * i] = x0; zS[3 * i + 1] = x1; zS[3 * i + 2] = x2;
             }
         }
-        // ------------------------------------------------------------------ closed-form RTS over recovered outages (rare)
+        // ------------------------------------------------------------------ closed-form RTS over recovered outages
+        // x_s[k] = x_f[k] + P_f[k] / P_pred[i] (x_f[i] - x_pred[i]) for the poses k of an outage recovered at i (:785-799 collapsed,
+        // see the header).  Two block-wide steps instead of the recovery thread patching its whole outage alone: (1) the owner
+        // of a recovery pose i leaves g = (x_f[i] - x_pred[i]) / P_pred[i] in the covariance row of pose i (free after pass C:
+        // RTS reads the covariance rows of outage poses only); (2) every thread patches the outage poses of its own chunk,
+        // walking it backwards with the g of the recovery that follows (found by a short look-ahead for the chunk's last run).
         if (iscr[9]) {
             __syncthreads();
             for (int i = s0; i < c1; ++i) {
                 const int f = flg[i];
                 if ((f & FLAG_RECOVERY) && !(f & FLAG_NO_RTS)) {
-                    int s = i - 1;
-                    while (s > 0 && !(flg[s - 1] & FLAG_VALID)) --s;
                     const double dt = fmax(1e-6, tsS[i] - tsS[i - 1]);
                     const double* gp = A.pos + 3 * (e0 + i);
                     double u[3];
                     mat_vec(bc, gp[0] - gp[-3], gp[1] - gp[-2], gp[2] - gp[-1], u[0], u[1], u[2]);
-                    double ratio_den[3], delta[3];
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        ratio_den[a] = posS[3 * (i - 1) + a] + prm.q[a] * dt;         // P_pred[i]
-                        delta[a] = zS[3 * i + a] - (zS[3 * (i - 1) + a] + u[a]);       // x_f[i] - x_pred[i]
+                        const double ratio_den = posS[3 * (i - 1) + a] + prm.q[a] * dt;          // P_pred[i]
+                        const double delta = zS[3 * i + a] - (zS[3 * (i - 1) + a] + u[a]);        // x_f[i] - x_pred[i]
+                        posS[3 * i + a] = delta / ratio_den;
                     }
-                    for (int k = s; k < i; ++k) {
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) zS[3 * k + a] += (posS[3 * k + a] / ratio_den[a]) * delta[a];
+                }
+            }
+            __syncthreads();
+            if (c0 < c1) {
+                bool active = false;
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+                if (!(flg[c1 - 1] & FLAG_VALID)) {                     // the chunk ends inside an outage: its recovery lies ahead
+                    int j = c1;
+                    while (j < n && !(flg[j] & FLAG_VALID)) ++j;
+                    if (j < n && (flg[j] & FLAG_RECOVERY) && !(flg[j] & FLAG_NO_RTS)) { active = true; g0 = posS[3 * j]; g1 = posS[3 * j + 1]; g2 = posS[3 * j + 2]; }
+                }
+                for (int k = c1 - 1; k >= c0; --k) {
+                    const int f = flg[k];
+                    if (f & FLAG_VALID) {
+                        active = (f & FLAG_RECOVERY) && !(f & FLAG_NO_RTS);
+                        if (active) { g0 = posS[3 * k]; g1 = posS[3 * k + 1]; g2 = posS[3 * k + 2]; }
+                    } else if (active) {
+                        zS[3 * k] += posS[3 * k] * g0; zS[3 * k + 1] += posS[3 * k + 1] * g1; zS[3 * k + 2] += posS[3 * k + 2] * g2;
                     }
                 }
             }
