@@ -14,132 +14,225 @@
 // The evaluation is one thread per SLAM stamp: binary search for its knot interval, segment membership from the gaps
 // around it, cubic in moment form / linear / NaN (scipy: NaN outside [seg start, seg end], :377-379).
 #include "gsf_common.cuh"
+#include "gsf_fuse_shared.cuh"
 #include "gsf_internal.cuh"
 
 namespace gsf {
 
-constexpr int AL_CH = 64;
-constexpr int AL_H = 20;
-constexpr int AL_MAX = AL_CH + 2 * AL_H + 2;
+constexpr int AL_CH = 15;                         // knots per thread (odd: conflict-free shared-memory strides of 15 and 45 doubles)
+constexpr int AL_H = 20;                          // halo
+constexpr int AL_NT = 128;
+constexpr int AL_TILE = AL_CH * AL_NT;            // knots per block
+constexpr int AL_PADW = AL_H + 2;                 // window margin (even, so that the window starts on a 16-byte boundary)
+constexpr int AL_W = AL_TILE + 2 * AL_PADW;
+constexpr size_t AL_SMEM = (size_t)AL_W * 32 + 16;
 
-__global__ void __launch_bounds__(128) assoc_long_moments_kernel(const double* __restrict__ gt, const double* __restrict__ gy, long long M, double gap,
-                                                                 double* __restrict__ mom, int* __restrict__ bad_steps) {
-    const long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long j0 = chunk * AL_CH;
-    if (j0 >= M) return;
-    const long long j1 = min(j0 + AL_CH, M) - 1;
-    double cp[AL_MAX], dd[3][AL_MAX];
-    long long cur = j0;
-    while (cur <= j1) {
+__global__ void __launch_bounds__(AL_NT, 3) assoc_long_moments_kernel(const double* __restrict__ gt, const double* __restrict__ gy, long long M, double gap,
+                                                                      double* __restrict__ mom, int* __restrict__ bad_steps, int use_tma) {
+    extern __shared__ __align__(16) double al_sm[];
+    double* Yv = al_sm;                           // [AL_W][3]
+    double* T = al_sm + 3 * AL_W;                 // [AL_W]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(T + AL_W);
+    const int tid = threadIdx.x;
+    const long long K0 = (long long)blockIdx.x * AL_TILE, base = K0 - AL_PADW;
+    // ---- the block's window of knots -> shared memory (every knot is read from DRAM once; the halo twice)
+    if (use_tma && base >= 0 && base + AL_W <= M) {
+        if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(mbar, (uint32_t)AL_W * 32u);
+            bulk_g2s(T, gt + base, (uint32_t)AL_W * 8u, mbar);
+            bulk_g2s(Yv, gy + 3 * base, (uint32_t)AL_W * 24u, mbar);
+        }
+        mbar_wait(mbar, 0);
+    } else {
+        const long long jlo = max(base, 0ll), jhi = min(base + AL_W, M);
+        for (long long j = jlo + tid; j < jhi; j += AL_NT) T[j - base] = gt[j];
+        for (long long f = 3 * jlo + tid; f < 3 * jhi; f += AL_NT) Yv[f - 3 * base] = gy[f];
+        __syncthreads();
+    }
+    const int kfirst = base <= 0 ? (int)(-base) : -1;                          // local index of knot 0 / knot M-1 when inside the window
+    const int klast = (M - 1 - base < AL_W) ? (int)(M - 1 - base) : (1 << 30);
+    const int kc0 = AL_PADW + AL_CH * tid;                                    // the thread's chunk, local indices
+    const int kj1 = min(kc0 + AL_CH - 1, klast);
+    double cpR[AL_CH], dR[3][AL_CH];
+#pragma unroll
+    for (int L = 0; L < AL_CH; ++L) { cpR[L] = 0.0; dR[0][L] = 0.0; dR[1][L] = 0.0; dR[2][L] = 0.0; }
+    // stamps that do not increase by more than 1e-9 inside a segment: the reference drops the segment (:356-359)
+    for (int k = kc0; k <= kj1 && k < klast; ++k) {
+        const double st = T[k + 1] - T[k];
+        if (!(st > gap) && !(st > 1e-9)) *bad_steps = 1;
+    }
+    int cur = kc0;
+    while (cur <= kj1) {
         // segment extent around `cur`, limited to the halo
-        long long a = cur; bool left_true = false;
+        int a = cur; bool lt = false;
         for (;;) {
-            if (a == 0) { left_true = true; break; }
-            const double st = gt[a] - gt[a - 1];
-            if (st > gap) { left_true = true; break; }
-            if (!(st > 1e-9)) *bad_steps = 1;              // not strictly increasing by > 1e-9: the reference drops the segment (:356-359)
-            if (cur - a >= AL_H + (cur - j0)) break;
+            if (a == kfirst) { lt = true; break; }
+            if (T[a] - T[a - 1] > gap) { lt = true; break; }
+            if (a <= kc0 - AL_H) break;
             --a;
         }
-        long long b = cur; bool right_true = false;
+        int b = cur; bool rt = false;
         for (;;) {
-            if (b == M - 1) { right_true = true; break; }
-            const double st = gt[b + 1] - gt[b];
-            if (st > gap) { right_true = true; break; }
-            if (!(st > 1e-9)) *bad_steps = 1;
-            if (b - j1 >= AL_H) break;
+            if (b == klast) { rt = true; break; }
+            if (T[b + 1] - T[b] > gap) { rt = true; break; }
+            if (b - kj1 >= AL_H) break;
             ++b;
         }
-        const long long w0 = max(a, j0), w1 = min(b, j1);   // knots of this chunk in the segment
-        const int m = (int)(b - a + 1);
-        if (m < 4 && left_true && right_true) {
-            for (long long j = w0; j <= w1; ++j) { mom[3 * j] = 0.0; mom[3 * j + 1] = 0.0; mom[3 * j + 2] = 0.0; }
-        } else {
-            auto h = [&](long long j) { return gt[j + 1] - gt[j]; };
-            // Thomas forward sweep over the interior unknowns a+1 .. b-1 (local index j - a); knot times, spacings and
-            // slopes are carried from step to step: one new knot (t, x, y, z) is loaded per step
+        const int w1 = min(b, kj1);
+        // interior unknowns U0 .. U1 (the end moments follow from the not-a-knot rows at evaluation time); this chunk's: R0 .. R1
+        const int U0 = a + 1, U1 = b - 1;
+        const int R0 = max(max(a, kc0), U0), R1 = min(w1, U1);
+        if (b - a + 1 >= 4 && R0 <= R1) {          // fewer than 4 knots (both ends true then): linear, no moments (:362)
+            const double e_h0 = T[a + 1] - T[a], e_h1 = T[a + 2] - T[a + 1], e_ha = T[b - 1] - T[b - 2], e_hb = T[b] - T[b - 1];
+            const double l_di = lt ? e_h0 * (e_h0 + e_h1) / e_h1 : 0.0, l_up = lt ? e_h0 * e_h0 / e_h1 : 0.0;     // not-a-knot rows at true ends
+            const double r_di = rt ? e_hb * (e_ha + e_hb) / e_ha : 0.0, r_lo = rt ? e_hb * e_hb / e_ha : 0.0;     // (natural where the halo cuts)
+            // ---- forward elimination U0 .. R1: knot times, spacings and slopes carried from row to row
             double pcp = 0.0, pd[3] = {0.0, 0.0, 0.0};
-            double tj = gt[a + 1], hp = tj - gt[a];                         // t_j, h(j-1)
-            double yj[3] = {gy[3 * (a + 1)], gy[3 * (a + 1) + 1], gy[3 * (a + 1) + 2]};
-            double sp[3] = {(yj[0] - gy[3 * a]) / hp, (yj[1] - gy[3 * a + 1]) / hp, (yj[2] - gy[3 * a + 2]) / hp};      // slope of interval j-1
-            const double e_h0 = hp, e_h1 = gt[a + 2] - gt[a + 1];           // first two spacings (not-a-knot row at a true left end)
-            const double e_ha = gt[b - 1] - gt[b - 2], e_hb = gt[b] - gt[b - 1];
-            for (long long j = a + 1; j <= b - 1; ++j) {
-                const double tn = gt[j + 1], hc = tn - tj;                 // h(j)
+            double tj = T[a + 1], hp = e_h0;
+            double yj[3], sp[3];
+            {
+                const double rh = fast_rcp(hp);
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) { yj[ax] = Yv[3 * (a + 1) + ax]; sp[ax] = (yj[ax] - Yv[3 * a + ax]) * rh; }
+            }
+            auto fstep = [&](int j, double& c_out, double* d_out) {
+                const double tn = T[j + 1], hc = tn - tj;
                 double lo = hp, di = 2.0 * (hp + hc), up = hc;
-                if (j == a + 1) {
-                    if (left_true) { di += e_h0 * (e_h0 + e_h1) / e_h1; up -= e_h0 * e_h0 / e_h1; }
-                    lo = 0.0;
-                }
-                if (j == b - 1) {
-                    if (right_true) { di += e_hb * (e_ha + e_hb) / e_ha; lo -= e_hb * e_hb / e_ha; }
-                    up = 0.0;
-                }
-                const double den = di - lo * pcp;
-                const double c = up / den;
-                const int L = (int)(j - a);
-                cp[L] = c;
+                if (j == U0) { di += l_di; up -= l_up; lo = 0.0; }
+                if (j == U1) { di += r_di; lo -= r_lo; up = 0.0; }
+                const double r = fast_rcp(di - lo * pcp), rh = fast_rcp(hc);
+                c_out = up * r;
 #pragma unroll
                 for (int ax = 0; ax < 3; ++ax) {
-                    const double yn = gy[3 * (j + 1) + ax];
-                    const double sn = (yn - yj[ax]) / hc;
-                    const double d = (6.0 * (sn - sp[ax]) - lo * pd[ax]) / den;
-                    dd[ax][L] = d; pd[ax] = d;
-                    yj[ax] = yn; sp[ax] = sn;
+                    const double yn = Yv[3 * (j + 1) + ax];
+                    const double sn = (yn - yj[ax]) * rh;
+                    const double d = (6.0 * (sn - sp[ax]) - lo * pd[ax]) * r;
+                    d_out[ax] = d; pd[ax] = d; yj[ax] = yn; sp[ax] = sn;
                 }
-                pcp = c; tj = tn; hp = hc;
-            }
-            for (long long j = b - 2; j >= a + 1; --j) {
-                const int L = (int)(j - a);
+                pcp = c_out; tj = tn; hp = hc;
+            };
+            for (int j = U0; j < kc0; ++j) { double c, d[3]; fstep(j, c, d); }
 #pragma unroll
-                for (int ax = 0; ax < 3; ++ax) dd[ax][L] -= cp[L] * dd[ax][L + 1];
+            for (int L = 0; L < AL_CH; ++L) {
+                const int j = kc0 + L;
+                if (j >= R0 && j <= R1) { double c, d[3]; fstep(j, c, d); cpR[L] = c; dR[0][L] = d[0]; dR[1][L] = d[1]; dR[2][L] = d[2]; }
             }
+            // ---- elimination from the right end U1 .. R1 + 1 (nothing stored), then the 2 x 2 system that joins the two at row R1
+            double pbp = 0.0, pe[3] = {0.0, 0.0, 0.0};
+            if (U1 > R1) {
+                double tb = T[b - 1], hn = e_hb;
+                double yb[3], sn[3];
+                {
+                    const double rh = fast_rcp(hn);
 #pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {
-                if (left_true) { const double h0 = h(a), h1 = h(a + 1); dd[ax][0] = ((h0 + h1) * dd[ax][1] - h0 * dd[ax][2]) / h1; }
-                else dd[ax][0] = 0.0;
-                const int Lb = (int)(b - a);
-                if (right_true) { const double ha = h(b - 2), hb = h(b - 1); dd[ax][Lb] = ((ha + hb) * dd[ax][Lb - 1] - hb * dd[ax][Lb - 2]) / ha; }
-                else dd[ax][Lb] = 0.0;
+                    for (int ax = 0; ax < 3; ++ax) { yb[ax] = Yv[3 * (b - 1) + ax]; sn[ax] = (Yv[3 * b + ax] - yb[ax]) * rh; }
+                }
+                for (int j = U1; j > R1; --j) {
+                    const double tp = T[j - 1], hq = tb - tp;
+                    double lo = hq, di = 2.0 * (hq + hn), up = hn;
+                    if (j == U1) { di += r_di; lo -= r_lo; up = 0.0; }
+                    const double r = fast_rcp(di - up * pbp), rh = fast_rcp(hq);
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const double yp = Yv[3 * (j - 1) + ax];
+                        const double sq = (yb[ax] - yp) * rh;
+                        const double e = (6.0 * (sn[ax] - sq) - up * pe[ax]) * r;
+                        pe[ax] = e; yb[ax] = yp; sn[ax] = sq;
+                    }
+                    pbp = lo * r; tb = tp; hn = hq;
+                }
             }
-            for (long long j = w0; j <= w1; ++j) {
-                const int L = (int)(j - a);
-                mom[3 * j] = dd[0][L]; mom[3 * j + 1] = dd[1][L]; mom[3 * j + 2] = dd[2][L];
+            double mn[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int L = AL_CH - 1; L >= 0; --L) {
+                const int j = kc0 + L;
+                if (j >= R0 && j <= R1) {
+                    if (j == R1) {
+                        const double inv = U1 > R1 ? fast_rcp(1.0 - cpR[L] * pbp) : 1.0;
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) mn[ax] = (dR[ax][L] - cpR[L] * pe[ax]) * inv;
+                    } else {
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) mn[ax] = dR[ax][L] - cpR[L] * mn[ax];
+                    }
+                    dR[0][L] = mn[0]; dR[1][L] = mn[1]; dR[2][L] = mn[2];
+                }
             }
         }
         cur = w1 + 1;
     }
+    // ---- moments -> shared memory (over the y window, which nobody reads any more) -> coalesced store
+    __syncthreads();
+#pragma unroll
+    for (int L = 0; L < AL_CH; ++L) { Yv[3 * (kc0 + L)] = dR[0][L]; Yv[3 * (kc0 + L) + 1] = dR[1][L]; Yv[3 * (kc0 + L) + 2] = dR[2][L]; }
+    __syncthreads();
+    const long long cnt = 3 * min((long long)AL_TILE, M - K0);
+    for (long long f = tid; f < cnt; f += AL_NT) mom[3 * K0 + f] = Yv[3 * AL_PADW + f];
 }
 
-__global__ void __launch_bounds__(256) assoc_long_eval_kernel(const double* __restrict__ gt, const double* __restrict__ gy, const double* __restrict__ mom,
-                                                              long long M, const double* __restrict__ st, long long N, double gap,
-                                                              double* __restrict__ out, unsigned char* __restrict__ val) {
-    // The stamps of a block are usually close together (SLAM stamps are sorted): two threads bracket the block's smallest
-    // and largest stamp in the whole knot array (27 dependent loads for 1e8 knots), every other thread searches inside that
-    // bracket only (a few hundred knots, cached).
-    __shared__ double s_lo[8], s_hi[8];
+// largest j with gt[j] <= q (0 if none) and the smallest bracket end above it, found by one warp probing 32 knots per round
+// (6 dependent rounds for 1e8 knots instead of the 27 of a bisection)
+__device__ __forceinline__ void warp_bracket(const double* __restrict__ gt, long long M, double q, int lane, long long& l_out, long long& r_out) {
+    long long l = 0, r = M - 1;
+    while (r - l > 1) {
+        const long long pos = l + ((r - l) * (lane + 1)) / 33;
+        const bool le = pos == l || gt[pos] <= q;
+        const int n = __popc(__ballot_sync(GSF_FULL_MASK, le));             // the knots are sorted: the lanes with le come first
+        const long long nl = __shfl_sync(GSF_FULL_MASK, pos, max(n - 1, 0)), nr = __shfl_sync(GSF_FULL_MASK, pos, min(n, 31));
+        if (n < 32) r = nr;
+        if (n > 0) l = nl;
+    }
+    l_out = l; r_out = r;
+}
+
+constexpr int EV_NT = 256;
+constexpr int EV_CAP = 1536;                     // knots of the block's bracket staged in shared memory
+
+__global__ void __launch_bounds__(EV_NT) assoc_long_eval_kernel(const double* __restrict__ gt, const double* __restrict__ gy, const double* __restrict__ mom,
+                                                                long long M, const double* __restrict__ st, long long N, double gap,
+                                                                double* __restrict__ out, unsigned char* __restrict__ val) {
+    // The stamps of a block are usually close together (SLAM stamps are sorted): two warps bracket the block's smallest
+    // and largest stamp in the whole knot array, the knot times of the bracket go to shared memory (when it is small enough)
+    // and every thread searches there.
+    __shared__ double s_lo[EV_NT / 32], s_hi[EV_NT / 32];
     __shared__ long long b_l, b_r;
+    __shared__ double s_t[EV_CAP];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double t = i < N ? st[i] : nan("");
     {
         double mn = (t == t) ? t : INFINITY, mx = (t == t) ? t : -INFINITY;
         for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(GSF_FULL_MASK, mn, o)); mx = fmax(mx, __shfl_xor_sync(GSF_FULL_MASK, mx, o)); }
-        if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = mn; s_hi[threadIdx.x >> 5] = mx; }
+        if (lane == 0) { s_lo[warp] = mn; s_hi[warp] = mx; }
         __syncthreads();
-        if (threadIdx.x < 2 && M >= 2) {
-            double q = threadIdx.x == 0 ? INFINITY : -INFINITY;
-            for (int w = 0; w < 8; ++w) q = threadIdx.x == 0 ? fmin(q, s_lo[w]) : fmax(q, s_hi[w]);
-            long long l = 0, r = M - 1;                       // largest j with gt[j] <= q (0 if none), then widened by one
-            while (r - l > 1) { const long long mid = (l + r) >> 1; if (gt[mid] <= q) l = mid; else r = mid; }
-            if (threadIdx.x == 0) b_l = l; else b_r = r;
+        if (warp < 2 && M >= 2) {
+            double q = warp == 0 ? INFINITY : -INFINITY;
+            for (int w = 0; w < EV_NT / 32; ++w) q = warp == 0 ? fmin(q, s_lo[w]) : fmax(q, s_hi[w]);
+            long long l, r;
+            warp_bracket(gt, M, q, lane, l, r);
+            if (lane == 0) { if (warp == 0) b_l = l; else b_r = r; }
         }
+        __syncthreads();
+    }
+    const long long bl = M >= 2 ? b_l : 0, br = M >= 2 ? b_r : 0;
+    const bool staged = M >= 2 && br >= bl && br - bl < EV_CAP;
+    if (staged) {
+        for (long long k = bl + threadIdx.x; k <= br; k += EV_NT) s_t[k - bl] = gt[k];
         __syncthreads();
     }
     if (i >= N) return;
     double v0 = nan(""), v1 = v0, v2 = v0;
     if (M >= 2 && t >= gt[0] && t <= gt[M - 1]) {
-        long long l = b_l, r = b_r;                           // largest j with gt[j] <= t: gt[b_l] <= t (or b_l = 0), gt[b_r] >= t (or b_r = M - 1)
-        while (r - l > 1) { const long long mid = (l + r) >> 1; if (gt[mid] <= t) l = mid; else r = mid; }
+        long long l = bl, r = br;                             // largest j with gt[j] <= t: gt[b_l] <= t (or b_l = 0), gt[b_r] >= t (or b_r = M - 1)
+        if (staged) {
+            int li = 0, ri = (int)(br - bl);
+            while (ri - li > 1) { const int mid = (li + ri) >> 1; if (s_t[mid] <= t) li = mid; else ri = mid; }
+            l = bl + li; r = bl + ri;
+        } else {
+            while (r - l > 1) { const long long mid = (l + r) >> 1; if (gt[mid] <= t) l = mid; else r = mid; }
+        }
         long long j = (gt[r] <= t) ? r : l;
         // interval [j, j+1] unless t sits exactly on the last knot of a segment: then [j-1, j]
         bool ok = true;
@@ -147,20 +240,24 @@ __global__ void __launch_bounds__(256) assoc_long_eval_kernel(const double* __re
             if (t == gt[j] && j > 0 && !(gt[j] - gt[j - 1] > gap)) --j; else ok = false;        // inside a gap (or an isolated knot): no segment
         }
         if (ok) {
-            // knots of the segment around the interval, up to 4 (decides cubic / linear, :362)
-            int cnt = 2;
-            if (j >= 1 && !(gt[j] - gt[j - 1] > gap)) { ++cnt; if (j >= 2 && !(gt[j - 1] - gt[j - 2] > gap)) ++cnt; }
-            if (j + 2 <= M - 1 && !(gt[j + 2] - gt[j + 1] > gap)) { ++cnt; if (j + 3 <= M - 1 && !(gt[j + 3] - gt[j + 2] > gap)) ++cnt; }
-            const double hh = gt[j + 1] - gt[j];
-            const double wa = (gt[j + 1] - t) / hh, wb = (t - gt[j]) / hh;
+            // knots of the segment around the interval, up to 2 on each side (decides cubic / linear, :362, and which moments are end moments)
+            const double tj = gt[j], tn = gt[j + 1];
+            double hl = 0.0, hr = 0.0;                         // spacing of the neighbouring intervals when they belong to the segment
+            int nl = 0, nr = 0;
+            if (j >= 1) { hl = tj - gt[j - 1]; if (!(hl > gap)) { nl = 1; if (j >= 2 && !(gt[j - 1] - gt[j - 2] > gap)) nl = 2; } }
+            if (j + 2 <= M - 1) { hr = gt[j + 2] - tn; if (!(hr > gap)) { nr = 1; if (j + 3 <= M - 1 && !(gt[j + 3] - gt[j + 2] > gap)) nr = 2; } }
+            const double hh = tn - tj;
+            const double wa = (tn - t) / hh, wb = (t - tj) / hh;
             double v[3];
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
                 const double y0 = gy[3 * j + ax], y1 = gy[3 * (j + 1) + ax];
-                if (cnt >= 4) {
-                    const double m0 = mom[3 * j + ax], m1 = mom[3 * (j + 1) + ax];
+                if (2 + nl + nr >= 4) {
+                    // the moments kernel leaves the interior moments; the two end moments of a segment come from its not-a-knot rows
+                    const double m0 = nl ? mom[3 * j + ax] : ((hh + hr) * mom[3 * (j + 1) + ax] - hh * mom[3 * (j + 2) + ax]) / hr;
+                    const double m1 = nr ? mom[3 * (j + 1) + ax] : ((hl + hh) * mom[3 * j + ax] - hh * mom[3 * (j - 1) + ax]) / hl;
                     v[ax] = wa * y0 + wb * y1 + ((wa * wa * wa - wa) * m0 + (wb * wb * wb - wb) * m1) * (hh * hh) / 6.0;
-                } else v[ax] = (y1 - y0) / hh * (t - gt[j]) + y0;
+                } else v[ax] = (y1 - y0) / hh * (t - tj) + y0;
             }
             v0 = v[0]; v1 = v[1]; v2 = v[2];
         }
@@ -176,10 +273,16 @@ cudaError_t launch_associate_long(const double* gps_t, const double* gps_xyz, lo
     cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
     if (M >= 2) {
-        const long long chunks = (M + AL_CH - 1) / AL_CH;
-        assoc_long_moments_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, stream>>>(gps_t, gps_xyz, M, gap, work, bad);
+        static bool attr_done = false;
+        if (!attr_done) {
+            e = cudaFuncSetAttribute(assoc_long_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AL_SMEM);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        const int use_tma = ((reinterpret_cast<uintptr_t>(gps_t) | reinterpret_cast<uintptr_t>(gps_xyz)) & 15) == 0;
+        assoc_long_moments_kernel<<<(unsigned)((M + AL_TILE - 1) / AL_TILE), AL_NT, AL_SMEM, stream>>>(gps_t, gps_xyz, M, gap, work, bad, use_tma);
     }
-    if (N > 0) assoc_long_eval_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(gps_t, gps_xyz, work, M, slam_t, N, gap, aligned, valid);
+    if (N > 0) assoc_long_eval_kernel<<<(unsigned)((N + EV_NT - 1) / EV_NT), EV_NT, 0, stream>>>(gps_t, gps_xyz, work, M, slam_t, N, gap, aligned, valid);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (status) e = cudaMemcpyAsync(status, bad, sizeof(int), cudaMemcpyDeviceToDevice, stream);
