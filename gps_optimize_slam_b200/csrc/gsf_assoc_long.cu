@@ -188,82 +188,104 @@ __device__ __forceinline__ void warp_bracket(const double* __restrict__ gt, long
 }
 
 constexpr int EV_NT = 256;
-constexpr int EV_CAP = 1536;                     // knots of the block's bracket staged in shared memory
+constexpr int EV_PER = 8;                        // stamps per thread: one bracket search serves EV_NT * EV_PER stamps
+constexpr int EV_TILE = EV_NT * EV_PER;
+constexpr int EV_CAP = 3072;                     // knot times of the block's bracket staged in shared memory
+constexpr int EV_MARGIN = 3;                     // knots around the bracket that the segment tests read
+
+// One stamp.  G(j): knot time j (shared memory when the bracket is staged).
+template <class TimeOf>
+__device__ __forceinline__ void eval_stamp(double t, long long bl, long long br, TimeOf G, const double* __restrict__ gy, const double* __restrict__ mom,
+                                           long long M, double gap, double t_first, double t_last, double& v0, double& v1, double& v2) {
+    v0 = v1 = v2 = nan("");
+    if (!(t >= t_first && t <= t_last)) return;
+    long long l = bl, r = br;                                 // largest j with gt[j] <= t: gt[b_l] <= t (or b_l = 0), gt[b_r] >= t (or b_r = M - 1)
+    while (r - l > 1) { const long long mid = (l + r) >> 1; if (G(mid) <= t) l = mid; else r = mid; }
+    long long j = (G(r) <= t) ? r : l;
+    // interval [j, j+1] unless t sits exactly on the last knot of a segment: then [j-1, j]
+    double tj = G(j);
+    if (j == M - 1 || G(j + 1) - tj > gap) {
+        if (t == tj && j > 0 && !(tj - G(j - 1) > gap)) { --j; tj = G(j); } else return;        // inside a gap (or an isolated knot): no segment
+    }
+    // knots of the segment around the interval, up to 2 on each side (decides cubic / linear, :362, and which moments are end moments)
+    const double tn = G(j + 1);
+    double hl = 0.0, hr = 0.0;                                // spacing of the neighbouring intervals when they belong to the segment
+    int nl = 0, nr = 0;
+    if (j >= 1) { const double tp = G(j - 1); hl = tj - tp; if (!(hl > gap)) { nl = 1; if (j >= 2 && !(tp - G(j - 2) > gap)) nl = 2; } }
+    if (j + 2 <= M - 1) { const double tq = G(j + 2); hr = tq - tn; if (!(hr > gap)) { nr = 1; if (j + 3 <= M - 1 && !(G(j + 3) - tq > gap)) nr = 2; } }
+    const double hh = tn - tj;
+    const double wa = (tn - t) / hh, wb = (t - tj) / hh;
+    double v[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const double y0 = gy[3 * j + ax], y1 = gy[3 * (j + 1) + ax];
+        if (2 + nl + nr >= 4) {
+            // the moments kernel leaves the interior moments; the two end moments of a segment come from its not-a-knot rows
+            const double m0 = nl ? mom[3 * j + ax] : ((hh + hr) * mom[3 * (j + 1) + ax] - hh * mom[3 * (j + 2) + ax]) / hr;
+            const double m1 = nr ? mom[3 * (j + 1) + ax] : ((hl + hh) * mom[3 * j + ax] - hh * mom[3 * (j - 1) + ax]) / hl;
+            v[ax] = wa * y0 + wb * y1 + ((wa * wa * wa - wa) * m0 + (wb * wb * wb - wb) * m1) * (hh * hh) / 6.0;
+        } else v[ax] = (y1 - y0) / hh * (t - tj) + y0;
+    }
+    v0 = v[0]; v1 = v[1]; v2 = v[2];
+}
 
 __global__ void __launch_bounds__(EV_NT) assoc_long_eval_kernel(const double* __restrict__ gt, const double* __restrict__ gy, const double* __restrict__ mom,
                                                                 long long M, const double* __restrict__ st, long long N, double gap,
                                                                 double* __restrict__ out, unsigned char* __restrict__ val) {
     // The stamps of a block are usually close together (SLAM stamps are sorted): two warps bracket the block's smallest
     // and largest stamp in the whole knot array, the knot times of the bracket go to shared memory (when it is small enough)
-    // and every thread searches there.
+    // and every thread searches there.  The bracket search is a chain of dependent DRAM reads: it is paid once per 2048 stamps
+    // and overlaps with the evaluation of the other resident blocks.
     __shared__ double s_lo[EV_NT / 32], s_hi[EV_NT / 32];
     __shared__ long long b_l, b_r;
     __shared__ double s_t[EV_CAP];
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i0 = (long long)blockIdx.x * EV_TILE + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double t = i < N ? st[i] : nan("");
-    {
-        double mn = (t == t) ? t : INFINITY, mx = (t == t) ? t : -INFINITY;
-        for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(GSF_FULL_MASK, mn, o)); mx = fmax(mx, __shfl_xor_sync(GSF_FULL_MASK, mx, o)); }
-        if (lane == 0) { s_lo[warp] = mn; s_hi[warp] = mx; }
-        __syncthreads();
-        if (warp < 2 && M >= 2) {
-            double q = warp == 0 ? INFINITY : -INFINITY;
-            for (int w = 0; w < EV_NT / 32; ++w) q = warp == 0 ? fmin(q, s_lo[w]) : fmax(q, s_hi[w]);
-            long long l, r;
-            warp_bracket(gt, M, q, lane, l, r);
-            if (lane == 0) { if (warp == 0) b_l = l; else b_r = r; }
-        }
-        __syncthreads();
-    }
-    const long long bl = M >= 2 ? b_l : 0, br = M >= 2 ? b_r : 0;
-    const bool staged = M >= 2 && br >= bl && br - bl < EV_CAP;
-    if (staged) {
-        for (long long k = bl + threadIdx.x; k <= br; k += EV_NT) s_t[k - bl] = gt[k];
-        __syncthreads();
-    }
-    if (i >= N) return;
-    double v0 = nan(""), v1 = v0, v2 = v0;
-    if (M >= 2 && t >= gt[0] && t <= gt[M - 1]) {
-        long long l = bl, r = br;                             // largest j with gt[j] <= t: gt[b_l] <= t (or b_l = 0), gt[b_r] >= t (or b_r = M - 1)
-        if (staged) {
-            int li = 0, ri = (int)(br - bl);
-            while (ri - li > 1) { const int mid = (li + ri) >> 1; if (s_t[mid] <= t) li = mid; else ri = mid; }
-            l = bl + li; r = bl + ri;
-        } else {
-            while (r - l > 1) { const long long mid = (l + r) >> 1; if (gt[mid] <= t) l = mid; else r = mid; }
-        }
-        long long j = (gt[r] <= t) ? r : l;
-        // interval [j, j+1] unless t sits exactly on the last knot of a segment: then [j-1, j]
-        bool ok = true;
-        if (j == M - 1 || gt[j + 1] - gt[j] > gap) {
-            if (t == gt[j] && j > 0 && !(gt[j] - gt[j - 1] > gap)) --j; else ok = false;        // inside a gap (or an isolated knot): no segment
-        }
-        if (ok) {
-            // knots of the segment around the interval, up to 2 on each side (decides cubic / linear, :362, and which moments are end moments)
-            const double tj = gt[j], tn = gt[j + 1];
-            double hl = 0.0, hr = 0.0;                         // spacing of the neighbouring intervals when they belong to the segment
-            int nl = 0, nr = 0;
-            if (j >= 1) { hl = tj - gt[j - 1]; if (!(hl > gap)) { nl = 1; if (j >= 2 && !(gt[j - 1] - gt[j - 2] > gap)) nl = 2; } }
-            if (j + 2 <= M - 1) { hr = gt[j + 2] - tn; if (!(hr > gap)) { nr = 1; if (j + 3 <= M - 1 && !(gt[j + 3] - gt[j + 2] > gap)) nr = 2; } }
-            const double hh = tn - tj;
-            const double wa = (tn - t) / hh, wb = (t - tj) / hh;
-            double v[3];
+    double mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {
-                const double y0 = gy[3 * j + ax], y1 = gy[3 * (j + 1) + ax];
-                if (2 + nl + nr >= 4) {
-                    // the moments kernel leaves the interior moments; the two end moments of a segment come from its not-a-knot rows
-                    const double m0 = nl ? mom[3 * j + ax] : ((hh + hr) * mom[3 * (j + 1) + ax] - hh * mom[3 * (j + 2) + ax]) / hr;
-                    const double m1 = nr ? mom[3 * (j + 1) + ax] : ((hl + hh) * mom[3 * j + ax] - hh * mom[3 * (j - 1) + ax]) / hl;
-                    v[ax] = wa * y0 + wb * y1 + ((wa * wa * wa - wa) * m0 + (wb * wb * wb - wb) * m1) * (hh * hh) / 6.0;
-                } else v[ax] = (y1 - y0) / hh * (t - tj) + y0;
-            }
-            v0 = v[0]; v1 = v[1]; v2 = v[2];
-        }
+    for (int u = 0; u < EV_PER; ++u) {
+        const long long i = i0 + (long long)u * EV_NT;
+        const double t = i < N ? st[i] : nan("");
+        if (t == t) { mn = fmin(mn, t); mx = fmax(mx, t); }
     }
-    out[3 * i] = v0; out[3 * i + 1] = v1; out[3 * i + 2] = v2;
-    val[i] = !row_has_nan(v0, v1, v2);
+    for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(GSF_FULL_MASK, mn, o)); mx = fmax(mx, __shfl_xor_sync(GSF_FULL_MASK, mx, o)); }
+    if (lane == 0) { s_lo[warp] = mn; s_hi[warp] = mx; }
+    __syncthreads();
+    if (warp < 2 && M >= 2) {
+        double q = warp == 0 ? INFINITY : -INFINITY;
+        for (int w = 0; w < EV_NT / 32; ++w) q = warp == 0 ? fmin(q, s_lo[w]) : fmax(q, s_hi[w]);
+        long long l, r;
+        warp_bracket(gt, M, q, lane, l, r);
+        if (lane == 0) { if (warp == 0) b_l = l; else b_r = r; }
+    }
+    __syncthreads();
+    if (M < 2) {
+#pragma unroll
+        for (int u = 0; u < EV_PER; ++u) {
+            const long long i = i0 + (long long)u * EV_NT;
+            if (i < N) { out[3 * i] = nan(""); out[3 * i + 1] = nan(""); out[3 * i + 2] = nan(""); val[i] = 0; }
+        }
+        return;
+    }
+    const long long bl = b_l, br = b_r;
+    const long long s0 = max(bl - EV_MARGIN, 0ll), s1 = min(br + EV_MARGIN, M - 1);
+    const bool staged = br >= bl && s1 - s0 < EV_CAP;
+    if (staged) {
+        for (long long k = s0 + threadIdx.x; k <= s1; k += EV_NT) s_t[k - s0] = gt[k];
+        __syncthreads();
+    }
+    const double t_first = gt[0], t_last = gt[M - 1];
+#pragma unroll 2
+    for (int u = 0; u < EV_PER; ++u) {
+        const long long i = i0 + (long long)u * EV_NT;
+        if (i >= N) break;
+        const double t = st[i];                               // second read: L1 / L2
+        double v0, v1, v2;
+        if (staged) eval_stamp(t, bl, br, [&](long long j) { return s_t[j - s0]; }, gy, mom, M, gap, t_first, t_last, v0, v1, v2);
+        else eval_stamp(t, bl, br, [&](long long j) { return gt[j]; }, gy, mom, M, gap, t_first, t_last, v0, v1, v2);
+        out[3 * i] = v0; out[3 * i + 1] = v1; out[3 * i + 2] = v2;
+        val[i] = !row_has_nan(v0, v1, v2);
+    }
 }
 
 // work: 3 M doubles (moments) + 1 int
@@ -282,7 +304,7 @@ cudaError_t launch_associate_long(const double* gps_t, const double* gps_xyz, lo
         const int use_tma = ((reinterpret_cast<uintptr_t>(gps_t) | reinterpret_cast<uintptr_t>(gps_xyz)) & 15) == 0;
         assoc_long_moments_kernel<<<(unsigned)((M + AL_TILE - 1) / AL_TILE), AL_NT, AL_SMEM, stream>>>(gps_t, gps_xyz, M, gap, work, bad, use_tma);
     }
-    if (N > 0) assoc_long_eval_kernel<<<(unsigned)((N + EV_NT - 1) / EV_NT), EV_NT, 0, stream>>>(gps_t, gps_xyz, work, M, slam_t, N, gap, aligned, valid);
+    if (N > 0) assoc_long_eval_kernel<<<(unsigned)((N + EV_TILE - 1) / EV_TILE), EV_NT, 0, stream>>>(gps_t, gps_xyz, work, M, slam_t, N, gap, aligned, valid);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (status) e = cudaMemcpyAsync(status, bad, sizeof(int), cudaMemcpyDeviceToDevice, stream);
