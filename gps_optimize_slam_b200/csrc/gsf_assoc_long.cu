@@ -58,27 +58,37 @@ __global__ void __launch_bounds__(AL_NT, 3) assoc_long_moments_kernel(const doub
     double cpR[AL_CH], dR[3][AL_CH];
 #pragma unroll
     for (int L = 0; L < AL_CH; ++L) { cpR[L] = 0.0; dR[0][L] = 0.0; dR[1][L] = 0.0; dR[2][L] = 0.0; }
-    // stamps that do not increase by more than 1e-9 inside a segment: the reference drops the segment (:356-359)
+    // stamps that do not increase by more than 1e-9 inside a segment: the reference drops the segment (:356-359); and one
+    // block-wide test for the usual case -- no gap and no end of the track anywhere in the window -- which spares every
+    // thread the walk to its segment's ends
+    int gap_seen = (kfirst >= 0) || (klast < AL_W);
     for (int k = kc0; k <= kj1 && k < klast; ++k) {
         const double st = T[k + 1] - T[k];
-        if (!(st > gap) && !(st > 1e-9)) *bad_steps = 1;
+        if (st > gap) gap_seen = 1; else if (!(st > 1e-9)) *bad_steps = 1;
     }
+    if (!gap_seen && tid < 2 * AL_PADW - 1) {                 // the margins of the window
+        const int k = tid < AL_PADW ? tid : AL_TILE + tid;
+        if (T[k + 1] - T[k] > gap) gap_seen = 1;
+    }
+    const bool plain = !__syncthreads_or(gap_seen);
     int cur = kc0;
     while (cur <= kj1) {
         // segment extent around `cur`, limited to the halo
-        int a = cur; bool lt = false;
-        for (;;) {
-            if (a == kfirst) { lt = true; break; }
-            if (T[a] - T[a - 1] > gap) { lt = true; break; }
-            if (a <= kc0 - AL_H) break;
-            --a;
-        }
-        int b = cur; bool rt = false;
-        for (;;) {
-            if (b == klast) { rt = true; break; }
-            if (T[b + 1] - T[b] > gap) { rt = true; break; }
-            if (b - kj1 >= AL_H) break;
-            ++b;
+        int a = cur, b = cur; bool lt = false, rt = false;
+        if (plain) { a = kc0 - AL_H; b = kj1 + AL_H; }
+        else {
+            for (;;) {
+                if (a == kfirst) { lt = true; break; }
+                if (T[a] - T[a - 1] > gap) { lt = true; break; }
+                if (a <= kc0 - AL_H) break;
+                --a;
+            }
+            for (;;) {
+                if (b == klast) { rt = true; break; }
+                if (T[b + 1] - T[b] > gap) { rt = true; break; }
+                if (b - kj1 >= AL_H) break;
+                ++b;
+            }
         }
         const int w1 = min(b, kj1);
         // interior unknowns U0 .. U1 (the end moments follow from the not-a-knot rows at evaluation time); this chunk's: R0 .. R1
@@ -113,6 +123,7 @@ __global__ void __launch_bounds__(AL_NT, 3) assoc_long_moments_kernel(const doub
                 }
                 pcp = c_out; tj = tn; hp = hc;
             };
+#pragma unroll 4
             for (int j = U0; j < kc0; ++j) { double c, d[3]; fstep(j, c, d); }
 #pragma unroll
             for (int L = 0; L < AL_CH; ++L) {
@@ -129,6 +140,7 @@ __global__ void __launch_bounds__(AL_NT, 3) assoc_long_moments_kernel(const doub
 #pragma unroll
                     for (int ax = 0; ax < 3; ++ax) { yb[ax] = Yv[3 * (b - 1) + ax]; sn[ax] = (Yv[3 * b + ax] - yb[ax]) * rh; }
                 }
+#pragma unroll 4
                 for (int j = U1; j > R1; --j) {
                     const double tp = T[j - 1], hq = tb - tp;
                     double lo = hq, di = 2.0 * (hq + hn), up = hn;
@@ -199,9 +211,16 @@ __device__ __forceinline__ void eval_stamp(double t, long long bl, long long br,
                                            long long M, double gap, double t_first, double t_last, double& v0, double& v1, double& v2) {
     v0 = v1 = v2 = nan("");
     if (!(t >= t_first && t <= t_last)) return;
-    long long l = bl, r = br;                                 // largest j with gt[j] <= t: gt[b_l] <= t (or b_l = 0), gt[b_r] >= t (or b_r = M - 1)
-    while (r - l > 1) { const long long mid = (l + r) >> 1; if (G(mid) <= t) l = mid; else r = mid; }
-    long long j = (G(r) <= t) ? r : l;
+    long long j;                                              // largest j with gt[j] <= t: gt[b_l] <= t (or b_l = 0), gt[b_r] >= t (or b_r = M - 1)
+    if (br - bl < (1ll << 30)) {
+        int li = 0, ri = (int)(br - bl);
+        while (ri - li > 1) { const int mid = (li + ri) >> 1; if (G(bl + mid) <= t) li = mid; else ri = mid; }
+        j = bl + ((G(bl + ri) <= t) ? ri : li);
+    } else {
+        long long l = bl, r = br;
+        while (r - l > 1) { const long long mid = (l + r) >> 1; if (G(mid) <= t) l = mid; else r = mid; }
+        j = (G(r) <= t) ? r : l;
+    }
     // interval [j, j+1] unless t sits exactly on the last knot of a segment: then [j-1, j]
     double tj = G(j);
     if (j == M - 1 || G(j + 1) - tj > gap) {
@@ -229,7 +248,7 @@ __device__ __forceinline__ void eval_stamp(double t, long long bl, long long br,
     v0 = v[0]; v1 = v[1]; v2 = v[2];
 }
 
-__global__ void __launch_bounds__(EV_NT) assoc_long_eval_kernel(const double* __restrict__ gt, const double* __restrict__ gy, const double* __restrict__ mom,
+__global__ void __launch_bounds__(EV_NT, 4) assoc_long_eval_kernel(const double* __restrict__ gt, const double* __restrict__ gy, const double* __restrict__ mom,
                                                                 long long M, const double* __restrict__ st, long long N, double gap,
                                                                 double* __restrict__ out, unsigned char* __restrict__ val) {
     // The stamps of a block are usually close together (SLAM stamps are sorted): two warps bracket the block's smallest
@@ -281,7 +300,7 @@ __global__ void __launch_bounds__(EV_NT) assoc_long_eval_kernel(const double* __
         if (i >= N) break;
         const double t = st[i];                               // second read: L1 / L2
         double v0, v1, v2;
-        if (staged) eval_stamp(t, bl, br, [&](long long j) { return s_t[j - s0]; }, gy, mom, M, gap, t_first, t_last, v0, v1, v2);
+        if (staged) eval_stamp(t, bl, br, [&](long long j) { return s_t[(int)(j - s0)]; }, gy, mom, M, gap, t_first, t_last, v0, v1, v2);
         else eval_stamp(t, bl, br, [&](long long j) { return gt[j]; }, gy, mom, M, gap, t_first, t_last, v0, v1, v2);
         out[3 * i] = v0; out[3 * i + 1] = v1; out[3 * i + 2] = v2;
         val[i] = !row_has_nan(v0, v1, v2);
