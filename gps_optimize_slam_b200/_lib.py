@@ -35,6 +35,7 @@ SIGNATURES = {
     "gsf_to_local_f32_dev": (c_int32, [c_void_p] * 6 + [c_int32] + [c_void_p] * 6),
     "gsf_from_local_f32_dev": (c_int32, [c_void_p] * 4 + [c_int32] + [c_void_p] * 4),
     "gsf_fuse_batched_f32_dev": (c_int32, [c_void_p] * 7 + [c_int32, c_void_p, c_int32] + [c_void_p] * 5),
+    "gsf_associate_spline_long_work_doubles": (c_int64, [c_int64, c_int64]),
     "gsf_associate_spline_long_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_double] + [c_void_p] * 5),
     "gsf_ekf_step_dev": (c_int32, [c_int32] + [c_void_p] * 9 + [c_int32] + [c_void_p] * 6),
     "gsf_rts_segment_dev": (c_int32, [c_void_p] * 5 + [c_int32] + [c_void_p] * 3),

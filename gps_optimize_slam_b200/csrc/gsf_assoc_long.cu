@@ -3,16 +3,31 @@
 // spline of a segment with one serial Thomas sweep per axis -- fine for 271 knots, hopeless for 1e8.  Here the solve is
 // LOCAL: the spline's tridiagonal system is diagonally dominant (|off-diagonal| <= diagonal / 2 for any knot spacing), so the
 // influence of a boundary value on the moment k knots away decays at least like (2 - sqrt 3)^k = 0.268^k.  Every thread
-// owns a chunk of AL_CH = 64 consecutive knots and solves the system on the chunk widened by a halo of AL_H = 20 knots on both
-// sides, with a natural end (m = 0) where the halo cuts the segment and the true not-a-knot rows where the segment really
-// ends inside the halo; only the chunk's own moments are kept.  The cut moment is wrong by its own size, and 0.268^20 =
-// 3.7e-12 of that reaches the chunk: for GNSS noise of 0.3 m at 10 Hz (second differences of 30 m/s^2, a curvature term of
+// owns AL_CH = 15 consecutive knots and solves the system on its chunk widened by a halo of AL_H = 20 knots on both sides,
+// with a natural end (m = 0) where the halo cuts the segment and the true not-a-knot rows where the segment really ends
+// inside the halo; only the chunk's own moments are kept.  The cut moment is wrong by its own size, and 0.268^20 = 3.7e-12
+// of that reaches the chunk: for GNSS noise of 0.3 m at 10 Hz (second differences of 30 m/s^2, a curvature term of
 // m h^2 / 8 = 4 cm in the interpolant) that is 1.5e-13 m, far below one ulp of a UTM coordinate (9.3e-10 m) -- the values
-// equal the global solve's (the test compares with scipy and with the serial kernel).  (32-knot chunks with a
-// 32-knot halo: 12.7 ms for 1e8 knots, three times the arithmetic and the local-memory traffic per knot.)  Segments split at gaps > max_gps_gap_threshold
-// (:351-354); 2-3 knot segments are linear (:362), single knots give nothing (:361).
-// The evaluation is one thread per SLAM stamp: binary search for its knot interval, segment membership from the gaps
-// around it, cubic in moment form / linear / NaN (scipy: NaN outside [seg start, seg end], :377-379).
+// equal the global solve's (the test compares with scipy and with the serial kernel).
+//
+// Layout of the moments kernel: a block of 128 threads stages its window of 1920 + 2 x 22 knots (t and xyz, exactly as they
+// lie in global memory: 15- and 45-double strides between threads are conflict-free) with two TMA bulk copies, so every knot
+// comes from DRAM once (the halo twice).  A thread eliminates forward from the left end of its window to the last knot of its
+// chunk, keeping the eliminated rows of its own 15 knots in REGISTERS (fully unrolled, predicated on the segment limits),
+// eliminates from the right end of the window down to the knot after its chunk keeping nothing, joins the two at the chunk's
+// last row (a 2 x 2 system) and back-substitutes through its registers.  (First version: 64-knot chunks with the whole
+// widened system in local memory -- 9.8 ms for 1e8 knots, 4.2x the algorithmic DRAM traffic from local-memory spills; this one:
+// 1.9 ms.)  Only the INTERIOR moments of a segment are stored; the two end moments follow from the not-a-knot rows
+// (m_a = ((h0 + h1) m_{a+1} - h0 m_{a+2}) / h1) and are formed by the evaluation when a stamp falls into a segment's first or
+// last interval.  Segments split at gaps > max_gps_gap_threshold (:351-354); 2-3 knot segments are linear (:362), single
+// knots give nothing (:361).  A block whose window holds no gap and no end of the track (the usual case) skips the walk to
+// the segment ends.
+//
+// Evaluation: a tile of 2048 stamps per block.  assoc_long_bracket_kernel (one warp per tile) brackets the tile's smallest and
+// largest stamp in the knot array with a 32-way search (6 dependent reads for 1e8 knots); the evaluation kernel stages the
+// bracket's knot times in shared memory, finds each stamp's interval from the position equally spaced knots would give
+// (verified, else bisection of the bracket), decides segment membership from the gaps around it, and evaluates the cubic in
+// moment form / the line / NaN (scipy: NaN outside [seg start, seg end], :377-379).
 #include "gsf_common.cuh"
 #include "gsf_fuse_shared.cuh"
 #include "gsf_internal.cuh"
@@ -205,79 +220,108 @@ constexpr int EV_TILE = EV_NT * EV_PER;
 constexpr int EV_CAP = 3072;                     // knot times of the block's bracket staged in shared memory
 constexpr int EV_MARGIN = 3;                     // knots around the bracket that the segment tests read
 
-// One stamp.  G(j): knot time j (shared memory when the bracket is staged).
-template <class TimeOf>
-__device__ __forceinline__ void eval_stamp(double t, long long bl, long long br, TimeOf G, const double* __restrict__ gy, const double* __restrict__ mom,
-                                           long long M, double gap, double t_first, double t_last, double& v0, double& v1, double& v2) {
-    v0 = v1 = v2 = nan("");
-    if (!(t >= t_first && t <= t_last)) return;
-    long long j;                                              // largest j with gt[j] <= t: gt[b_l] <= t (or b_l = 0), gt[b_r] >= t (or b_r = M - 1)
-    if (br - bl < (1ll << 30)) {
-        int li = 0, ri = (int)(br - bl);
-        while (ri - li > 1) { const int mid = (li + ri) >> 1; if (G(bl + mid) <= t) li = mid; else ri = mid; }
-        j = bl + ((G(bl + ri) <= t) ? ri : li);
-    } else {
-        long long l = bl, r = br;
-        while (r - l > 1) { const long long mid = (l + r) >> 1; if (G(mid) <= t) l = mid; else r = mid; }
-        j = (G(r) <= t) ? r : l;
-    }
-    // interval [j, j+1] unless t sits exactly on the last knot of a segment: then [j-1, j]
-    double tj = G(j);
-    if (j == M - 1 || G(j + 1) - tj > gap) {
-        if (t == tj && j > 0 && !(tj - G(j - 1) > gap)) { --j; tj = G(j); } else return;        // inside a gap (or an isolated knot): no segment
-    }
-    // knots of the segment around the interval, up to 2 on each side (decides cubic / linear, :362, and which moments are end moments)
-    const double tn = G(j + 1);
-    double hl = 0.0, hr = 0.0;                                // spacing of the neighbouring intervals when they belong to the segment
-    int nl = 0, nr = 0;
-    if (j >= 1) { const double tp = G(j - 1); hl = tj - tp; if (!(hl > gap)) { nl = 1; if (j >= 2 && !(tp - G(j - 2) > gap)) nl = 2; } }
-    if (j + 2 <= M - 1) { const double tq = G(j + 2); hr = tq - tn; if (!(hr > gap)) { nr = 1; if (j + 3 <= M - 1 && !(G(j + 3) - tq > gap)) nr = 2; } }
+// Interpolant on the interval [j, j+1] (knot times tj, tn) of a segment that has nl / nr (0..2) more knots on the left / right;
+// hl, hr: the neighbouring spacings when those knots exist.
+__device__ __forceinline__ void eval_interval(double t, double tj, double tn, double hl, double hr, int nl, int nr, long long j,
+                                              const double* __restrict__ gy, const double* __restrict__ mom, double& v0, double& v1, double& v2) {
     const double hh = tn - tj;
-    const double wa = (tn - t) / hh, wb = (t - tj) / hh;
+    const double* __restrict__ y = gy + 3 * j;
     double v[3];
+    if (2 + nl + nr >= 4) {
+        const double* __restrict__ m = mom + 3 * j;
+        const double wb = (t - tj) / hh, wa = 1.0 - wb;
+        const double h26 = hh * hh * (1.0 / 6.0);
+        const double ca = (wa * wa * wa - wa) * h26, cb = (wb * wb * wb - wb) * h26;
 #pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-        const double y0 = gy[3 * j + ax], y1 = gy[3 * (j + 1) + ax];
-        if (2 + nl + nr >= 4) {
+        for (int ax = 0; ax < 3; ++ax) {
             // the moments kernel leaves the interior moments; the two end moments of a segment come from its not-a-knot rows
-            const double m0 = nl ? mom[3 * j + ax] : ((hh + hr) * mom[3 * (j + 1) + ax] - hh * mom[3 * (j + 2) + ax]) / hr;
-            const double m1 = nr ? mom[3 * (j + 1) + ax] : ((hl + hh) * mom[3 * j + ax] - hh * mom[3 * (j - 1) + ax]) / hl;
-            v[ax] = wa * y0 + wb * y1 + ((wa * wa * wa - wa) * m0 + (wb * wb * wb - wb) * m1) * (hh * hh) / 6.0;
-        } else v[ax] = (y1 - y0) / hh * (t - tj) + y0;
+            const double m0 = nl ? m[ax] : ((hh + hr) * m[3 + ax] - hh * m[6 + ax]) / hr;
+            const double m1 = nr ? m[3 + ax] : ((hl + hh) * m[ax] - hh * m[ax - 3]) / hl;
+            v[ax] = fma(wb, y[3 + ax] - y[ax], y[ax]) + (ca * m0 + cb * m1);
+        }
+    } else {
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) v[ax] = (y[3 + ax] - y[ax]) / hh * (t - tj) + y[ax];          // 2-3 knots: linear (:362)
     }
     v0 = v[0]; v1 = v[1]; v2 = v[2];
 }
 
+// One stamp against the whole knot array (brackets too wide to stage).
+__device__ __forceinline__ void eval_stamp_global(double t, long long bl, long long br, const double* __restrict__ gt, const double* __restrict__ gy,
+                                                  const double* __restrict__ mom, long long M, double gap, double t_first, double t_last,
+                                                  double& v0, double& v1, double& v2) {
+    v0 = v1 = v2 = nan("");
+    if (!(t >= t_first && t <= t_last)) return;
+    long long l = bl, r = br;                                 // largest j with gt[j] <= t: gt[b_l] <= t (or b_l = 0), gt[b_r] >= t (or b_r = M - 1)
+    while (r - l > 1) { const long long mid = (l + r) >> 1; if (gt[mid] <= t) l = mid; else r = mid; }
+    long long j = (gt[r] <= t) ? r : l;
+    // interval [j, j+1] unless t sits exactly on the last knot of a segment: then [j-1, j]
+    double tj = gt[j];
+    if (j == M - 1 || gt[j + 1] - tj > gap) {
+        if (t == tj && j > 0 && !(tj - gt[j - 1] > gap)) { --j; tj = gt[j]; } else return;        // inside a gap (or an isolated knot): no segment
+    }
+    const double tn = gt[j + 1];
+    double hl = 0.0, hr = 0.0;
+    int nl = 0, nr = 0;
+    if (j >= 1) { const double tp = gt[j - 1]; hl = tj - tp; if (!(hl > gap)) { nl = 1; if (j >= 2 && !(tp - gt[j - 2] > gap)) nl = 2; } }
+    if (j + 2 <= M - 1) { const double tq = gt[j + 2]; hr = tq - tn; if (!(hr > gap)) { nr = 1; if (j + 3 <= M - 1 && !(gt[j + 3] - tq > gap)) nr = 2; } }
+    eval_interval(t, tj, tn, hl, hr, nl, nr, j, gy, mom, v0, v1, v2);
+}
+
+// One stamp against the staged bracket: S[k] = gt[s0 + k]; lo / hi: the bracket ends; zl: 0 if s0 == 0 (knot 0 is S[0]) else a
+// negative number (every S[jl - 2] exists); ml: index of knot M - 1 if it is staged, else huge.  The search starts from the
+// position that equally spaced knots would give and falls back to the bisection of the bracket when that misses.
+__device__ __forceinline__ void eval_stamp_staged(double t, const double* __restrict__ S, int lo, int hi, double inv_span, long long s0, int zl, int ml,
+                                                  const double* __restrict__ gy, const double* __restrict__ mom, double gap, double t_first,
+                                                  double t_last, double& v0, double& v1, double& v2) {
+    v0 = v1 = v2 = nan("");
+    if (!(t >= t_first && t <= t_last)) return;
+    int g = lo + (int)((t - S[lo]) * inv_span);
+    g = max(lo, min(g, hi));
+    const int wl = max(g - 3, lo), wr = min(g + 4, hi);
+    int li = lo, ri = hi;
+    if ((wl == lo || S[wl] <= t) && (wr == hi || S[wr] > t)) { li = wl; ri = wr; }
+    while (ri - li > 1) { const int mid = (li + ri) >> 1; if (S[mid] <= t) li = mid; else ri = mid; }
+    int jl = (S[ri] <= t) ? ri : li;
+    double tj = S[jl];
+    if (jl == ml || S[jl + 1] - tj > gap) {
+        if (t == tj && jl >= 1 + zl && !(tj - S[jl - 1] > gap)) { --jl; tj = S[jl]; } else return;
+    }
+    const double tn = S[jl + 1];
+    double hl = 0.0, hr = 0.0;
+    int nl = 0, nr = 0;
+    if (jl >= 1 + zl) { const double tp = S[jl - 1]; hl = tj - tp; if (!(hl > gap)) { nl = 1; if (jl >= 2 + zl && !(tp - S[jl - 2] > gap)) nl = 2; } }
+    if (jl + 2 <= ml) { const double tq = S[jl + 2]; hr = tq - tn; if (!(hr > gap)) { nr = 1; if (jl + 3 <= ml && !(S[jl + 3] - tq > gap)) nr = 2; } }
+    eval_interval(t, tj, tn, hl, hr, nl, nr, s0 + jl, gy, mom, v0, v1, v2);
+}
+
+// One warp per tile of EV_TILE stamps: the knot interval that brackets the tile's smallest and largest stamp.  A chain of
+// dependent DRAM reads per tile -- in its own kernel, where ten thousand warps wait side by side, not in front of the evaluation.
+__global__ void __launch_bounds__(256) assoc_long_bracket_kernel(const double* __restrict__ gt, long long M, const double* __restrict__ st, long long N,
+                                                                 long long* __restrict__ brackets, long long ntiles) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= ntiles) return;
+    double mn = INFINITY, mx = -INFINITY;
+    const long long i0 = w * EV_TILE, i1 = min(i0 + EV_TILE, N);
+#pragma unroll 8
+    for (long long i = i0 + lane; i < i1; i += 32) { const double t = st[i]; if (t == t) { mn = fmin(mn, t); mx = fmax(mx, t); } }
+    for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(GSF_FULL_MASK, mn, o)); mx = fmax(mx, __shfl_xor_sync(GSF_FULL_MASK, mx, o)); }
+    long long l, r, l2, r2;
+    warp_bracket(gt, M, mn, lane, l, r);
+    warp_bracket(gt, M, mx, lane, l2, r2);
+    if (lane == 0) { brackets[2 * w] = l; brackets[2 * w + 1] = r2; }
+}
+
 __global__ void __launch_bounds__(EV_NT, 4) assoc_long_eval_kernel(const double* __restrict__ gt, const double* __restrict__ gy, const double* __restrict__ mom,
                                                                 long long M, const double* __restrict__ st, long long N, double gap,
-                                                                double* __restrict__ out, unsigned char* __restrict__ val) {
-    // The stamps of a block are usually close together (SLAM stamps are sorted): two warps bracket the block's smallest
-    // and largest stamp in the whole knot array, the knot times of the bracket go to shared memory (when it is small enough)
-    // and every thread searches there.  The bracket search is a chain of dependent DRAM reads: it is paid once per 2048 stamps
-    // and overlaps with the evaluation of the other resident blocks.
-    __shared__ double s_lo[EV_NT / 32], s_hi[EV_NT / 32];
-    __shared__ long long b_l, b_r;
+                                                                const long long* __restrict__ brackets, double* __restrict__ out,
+                                                                unsigned char* __restrict__ val) {
+    // The stamps of a block are usually close together (SLAM stamps are sorted): assoc_long_bracket_kernel has bracketed the
+    // block's smallest and largest stamp in the whole knot array; the knot times of the bracket go to shared memory (when it is
+    // small enough) and every thread searches there.
     __shared__ double s_t[EV_CAP];
     const long long i0 = (long long)blockIdx.x * EV_TILE + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < EV_PER; ++u) {
-        const long long i = i0 + (long long)u * EV_NT;
-        const double t = i < N ? st[i] : nan("");
-        if (t == t) { mn = fmin(mn, t); mx = fmax(mx, t); }
-    }
-    for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(GSF_FULL_MASK, mn, o)); mx = fmax(mx, __shfl_xor_sync(GSF_FULL_MASK, mx, o)); }
-    if (lane == 0) { s_lo[warp] = mn; s_hi[warp] = mx; }
-    __syncthreads();
-    if (warp < 2 && M >= 2) {
-        double q = warp == 0 ? INFINITY : -INFINITY;
-        for (int w = 0; w < EV_NT / 32; ++w) q = warp == 0 ? fmin(q, s_lo[w]) : fmax(q, s_hi[w]);
-        long long l, r;
-        warp_bracket(gt, M, q, lane, l, r);
-        if (lane == 0) { if (warp == 0) b_l = l; else b_r = r; }
-    }
-    __syncthreads();
     if (M < 2) {
 #pragma unroll
         for (int u = 0; u < EV_PER; ++u) {
@@ -286,7 +330,7 @@ __global__ void __launch_bounds__(EV_NT, 4) assoc_long_eval_kernel(const double*
         }
         return;
     }
-    const long long bl = b_l, br = b_r;
+    const long long bl = brackets[2 * blockIdx.x], br = brackets[2 * blockIdx.x + 1];
     const long long s0 = max(bl - EV_MARGIN, 0ll), s1 = min(br + EV_MARGIN, M - 1);
     const bool staged = br >= bl && s1 - s0 < EV_CAP;
     if (staged) {
@@ -294,23 +338,30 @@ __global__ void __launch_bounds__(EV_NT, 4) assoc_long_eval_kernel(const double*
         __syncthreads();
     }
     const double t_first = gt[0], t_last = gt[M - 1];
+    const int lo = (int)(bl - s0), hi = (int)(br - s0);
+    const int zl = s0 == 0 ? 0 : -8, ml = s1 == M - 1 ? (int)(s1 - s0) : (1 << 30);
+    double inv_span = 0.0;
+    if (staged) { const double span = s_t[hi] - s_t[lo]; inv_span = span > 0.0 ? (double)(hi - lo) / span : 0.0; }
 #pragma unroll 2
     for (int u = 0; u < EV_PER; ++u) {
         const long long i = i0 + (long long)u * EV_NT;
         if (i >= N) break;
-        const double t = st[i];                               // second read: L1 / L2
+        const double t = st[i];
         double v0, v1, v2;
-        if (staged) eval_stamp(t, bl, br, [&](long long j) { return s_t[(int)(j - s0)]; }, gy, mom, M, gap, t_first, t_last, v0, v1, v2);
-        else eval_stamp(t, bl, br, [&](long long j) { return gt[j]; }, gy, mom, M, gap, t_first, t_last, v0, v1, v2);
+        if (staged) eval_stamp_staged(t, s_t, lo, hi, inv_span, s0, zl, ml, gy, mom, gap, t_first, t_last, v0, v1, v2);
+        else eval_stamp_global(t, bl, br, gt, gy, mom, M, gap, t_first, t_last, v0, v1, v2);
         out[3 * i] = v0; out[3 * i + 1] = v1; out[3 * i + 2] = v2;
         val[i] = !row_has_nan(v0, v1, v2);
     }
 }
 
-// work: 3 M doubles (moments) + 1 int
+// work: 3 M doubles (moments), 1 int (+ padding), 2 int64 per tile of EV_TILE stamps (brackets)
+long long associate_long_work_doubles(long long M, long long N) { return 3 * M + 2 + 2 * ((N + EV_TILE - 1) / EV_TILE); }
+
 cudaError_t launch_associate_long(const double* gps_t, const double* gps_xyz, long long M, const double* slam_t, long long N, double gap,
                                   double* work, double* aligned, unsigned char* valid, int* status, cudaStream_t stream) {
     int* bad = reinterpret_cast<int*>(work + 3 * M);
+    long long* brackets = reinterpret_cast<long long*>(work + 3 * M + 2);
     cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
     if (M >= 2) {
@@ -323,7 +374,11 @@ cudaError_t launch_associate_long(const double* gps_t, const double* gps_xyz, lo
         const int use_tma = ((reinterpret_cast<uintptr_t>(gps_t) | reinterpret_cast<uintptr_t>(gps_xyz)) & 15) == 0;
         assoc_long_moments_kernel<<<(unsigned)((M + AL_TILE - 1) / AL_TILE), AL_NT, AL_SMEM, stream>>>(gps_t, gps_xyz, M, gap, work, bad, use_tma);
     }
-    if (N > 0) assoc_long_eval_kernel<<<(unsigned)((N + EV_TILE - 1) / EV_TILE), EV_NT, 0, stream>>>(gps_t, gps_xyz, work, M, slam_t, N, gap, aligned, valid);
+    if (N > 0) {
+        const long long ntiles = (N + EV_TILE - 1) / EV_TILE;
+        if (M >= 2) assoc_long_bracket_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, stream>>>(gps_t, M, slam_t, N, brackets, ntiles);
+        assoc_long_eval_kernel<<<(unsigned)ntiles, EV_NT, 0, stream>>>(gps_t, gps_xyz, work, M, slam_t, N, gap, brackets, aligned, valid);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (status) e = cudaMemcpyAsync(status, bad, sizeof(int), cudaMemcpyDeviceToDevice, stream);

@@ -484,6 +484,8 @@ int gsf_associate_spline_dev(const double* gps_t, const double* gps_xyz, const i
     return 0;
 }
 
+int64_t gsf_associate_spline_long_work_doubles(int64_t M, int64_t N) { return (M < 0 || N < 0) ? -1 : gsf::associate_long_work_doubles(M, N); }
+
 int gsf_associate_spline_long_dev(const double* gps_t, const double* gps_xyz, int64_t M, const double* slam_t, int64_t N, double gap,
                                   double* work, double* aligned, uint8_t* valid, int32_t* status, void* stream) {
     DeviceInfo& d = device_info();

@@ -55,6 +55,7 @@ struct AssocArgs {
     double gap; double* aligned; unsigned char* valid; double* work; int B;
 };
 cudaError_t launch_associate(const AssocArgs& a, int num_sms, cudaStream_t stream);
+long long associate_long_work_doubles(long long M, long long N);
 cudaError_t launch_associate_long(const double*, const double*, long long, const double*, long long, double, double*, double*, unsigned char*, int*,
                                   cudaStream_t);
 int sim3_tiles_for(long long max_len);

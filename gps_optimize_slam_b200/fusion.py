@@ -356,7 +356,7 @@ def associate_spline_long(gps_t, gps_xyz, slam_t, gap, stream=None):
     _require_cuda(gps_t, gps_xyz, slam_t)
     M, N = int(gps_t.numel()), int(slam_t.numel())
     dev = gps_t.device
-    work = torch.empty((3 * M + 2,), dtype=torch.float64, device=dev)
+    work = torch.empty((int(lib.gsf_associate_spline_long_work_doubles(M, N)),), dtype=torch.float64, device=dev)
     aligned = torch.empty((N, 3), dtype=torch.float64, device=dev)
     valid = torch.empty((N,), dtype=torch.uint8, device=dev)
     status = torch.zeros((1,), dtype=torch.int32, device=dev)

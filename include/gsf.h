@@ -266,12 +266,14 @@ int gsf_associate_spline_dev(const double* gps_t, const double* gps_xyz, const i
                              double* work, double* aligned, uint8_t* valid, void* stream);
 
 /* ---- the same for ONE trajectory of any size (BASELINE config 4: 1e8 samples): the not-a-knot system is solved locally --
- *      64-knot chunks with a 20-knot halo, natural ends where the halo cuts a segment, the true end rows where the segment
- *      ends inside it; the cut decays like 0.268^20 = 4e-12 of a centimetre-sized curvature term, below fp64 rounding of the
- *      coordinates -- and the evaluation is one thread per
- *      SLAM stamp.  gps_t [M] sorted and unique, gps_xyz [M,3], slam_t [N] (any order).  work: 3 M + 1 doubles.
+ *      15-knot chunks with a 20-knot halo on both sides, natural ends where the halo cuts a segment, the true end rows where
+ *      the segment ends inside it; the cut decays like 0.268^20 = 4e-12 of a centimetre-sized curvature term, below fp64
+ *      rounding of the coordinates -- and the evaluation searches each SLAM stamp inside the knot bracket of its tile of
+ *      2048 stamps.  gps_t [M] sorted and unique, gps_xyz [M,3], slam_t [N] (any order; sorted stamps keep the brackets
+ *      small).  work: gsf_associate_spline_long_work_doubles(M, N) doubles (3 M + 2 + 2 ceil(N / 2048)).
  *      status [1] (may be NULL): 1 if two consecutive GNSS stamps differ by <= 1e-9 s inside a segment (the reference
  *      drops such a segment, :356-359; use gsf_associate_spline_dev for that data). */
+int64_t gsf_associate_spline_long_work_doubles(int64_t M, int64_t N);
 int gsf_associate_spline_long_dev(const double* gps_t, const double* gps_xyz, int64_t M, const double* slam_t, int64_t N, double gap,
                                   double* work, double* aligned, uint8_t* valid, int32_t* status, void* stream);
 
