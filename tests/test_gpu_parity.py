@@ -331,7 +331,7 @@ def test_association_kernel_matches_reference_golden(gsf, case):
 
 
 def test_association_long_trajectory_local_halo(gsf):
-    """gsf_associate_spline_long_dev (local-halo solve, one thread per 32-knot chunk) against scipy's interp1d per segment
+    """gsf_associate_spline_long_dev (local-halo solve, 15-knot chunks in registers) against scipy's interp1d per segment
     (what dynamic_time_alignment calls, EKFGPSSLAM.py:351-380) and against the serial per-trajectory kernel: irregular
     knot spacing, gaps that cut segments of 1, 2, 3, 4, 5, 31, 32, 33, 64, 65 and thousands of knots, stamps exactly on
     knots / segment ends / inside gaps / outside the track; plus the golden cases (271 knots)."""
@@ -359,6 +359,17 @@ def test_association_long_trajectory_local_halo(gsf):
     a2, v2 = gsf.associate_spline(dev(gt), dev(gy), dev(np.array([0, M]), torch.int64), dev(st), dev(np.array([0, len(st)]), torch.int64), gap=5.0)
     np.testing.assert_array_equal(v2.cpu().numpy().astype(bool), v)
     np.testing.assert_allclose(a[v], a2.cpu().numpy()[v], rtol=0, atol=2e-8)
+    # sorted stamps: narrow brackets, the evaluation searches the knot times staged in shared memory (random order above: the
+    # whole-array search); and knot arrays that start 8 bytes off a 16-byte boundary (no TMA staging in the moments kernel)
+    order = np.argsort(st, kind="stable")
+    a3, v3, _ = gsf.associate_spline_long(dev(gt), dev(gy), dev(st[order]), 5.0)
+    np.testing.assert_array_equal(v3.cpu().numpy().astype(bool), v[order])
+    np.testing.assert_array_equal(a3.cpu().numpy()[v[order]], a[order][v[order]])
+    gt_off, gy_off = dev(np.concatenate([[0.0], gt]))[1:], dev(np.concatenate([np.zeros(3), gy.ravel()]))[3:].view(-1, 3)
+    assert gt_off.data_ptr() % 16 == 8 and gy_off.data_ptr() % 16 == 8
+    a4, v4, _ = gsf.associate_spline_long(gt_off, gy_off, dev(st[order]), 5.0)
+    np.testing.assert_array_equal(a4.cpu().numpy()[v[order]], a3.cpu().numpy()[v[order]])
+    np.testing.assert_array_equal(v4.cpu().numpy(), v3.cpu().numpy())
     for case in GOLDEN_CASES:
         g = load_golden(case)
         a, v, _ = gsf.associate_spline_long(dev(g["gps_ts"]), dev(g["gps_utm"]), dev(g["slam_ts"]), 5.0)
