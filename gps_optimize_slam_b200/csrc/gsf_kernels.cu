@@ -40,9 +40,11 @@ __device__ __forceinline__ void krueger_series(const double* coef, double xi_in,
 }
 
 // forward projection of one point (lam = lon - lon0, phi in radians) -> (xi, eta) scaled later by A k0.
-// Four transcendental calls per point (sincos phi, sincos lam, atan2, asinh): sigma = sinh(e atanh(e sin phi)) has a
-// tiny argument (e sin phi <= 0.082), so both functions are short odd series (truncation < 1e-17 relative); the
-// double-angle terms of the series follow algebraically from tau', cos lam and sin lam (no sincos(2 xi') / exp(2 eta')).
+// sigma = sinh(e atanh(e sin phi)) has a tiny argument (e sin phi <= 0.082), so both functions are short odd series
+// (truncation < 1e-17 relative) and sqrt(1 + sigma^2) is four terms; the double-angle terms of the Krueger series follow
+// algebraically from tau', cos lam and sin lam (no sincos(2 xi') / exp(2 eta')).  Inside a zone (|lam| < 0.12 rad = 6.9 deg)
+// sin lam, cos lam and asinh(sinh eta') are Taylor series too (truncation < 1e-18): two library calls per point remain
+// (sincos phi, atan2); farther from the central meridian the library functions take over.
 __device__ __forceinline__ void utm_forward_point(const UtmConst& K, double lam, double phi, double& xi, double& eta) {
     double sp, cp;
     sincos(phi, &sp, &cp);
@@ -57,14 +59,38 @@ __device__ __forceinline__ void utm_forward_point(const UtmConst& K, double lam,
     // sinh(y) = y (1 + y^2/6 + y^4/120 + y^6/5040 + y^8/362880)
     double sg = 1.0 / 362880.0;
     sg = fma(sg, y2, 1.0 / 5040.0); sg = fma(sg, y2, 1.0 / 120.0); sg = fma(sg, y2, 1.0 / 6.0); sg = fma(sg, y2, 1.0);
-    const double sigma = y * sg;
-    const double taup = tau * sqrt(1.0 + sigma * sigma) - sigma * t1;
-    double sl, cl;
-    sincos(lam, &sl, &cl);
-    const double h2 = taup * taup + cl * cl, rh2 = 1.0 / h2, rh = sqrt(rh2);
+    const double sigma = y * sg, sg2 = sigma * sigma;                  // sigma^2 <= 4.6e-5
+    // sqrt(1 + u) = 1 + u/2 - u^2/8 + u^3/16 - 5 u^4/128 (next term 6e-24)
+    const double rt = fma(fma(fma(fma(-5.0 / 128.0, sg2, 1.0 / 16.0), sg2, -0.125), sg2, 0.5), sg2, 1.0);
+    const double taup = tau * rt - sigma * t1;
+    double sl, cl, etap, v, rh2;
+    if (fabs(lam) < 0.12) {
+        const double l2 = lam * lam;
+        double ps = 1.0 / 6227020800.0;                                // sin: lam (1 - l2/3! + ... + l2^6/13!)
+        ps = fma(ps, l2, -1.0 / 39916800.0); ps = fma(ps, l2, 1.0 / 362880.0); ps = fma(ps, l2, -1.0 / 5040.0);
+        ps = fma(ps, l2, 1.0 / 120.0); ps = fma(ps, l2, -1.0 / 6.0); ps = fma(ps, l2, 1.0);
+        sl = lam * ps;
+        double pc = 1.0 / 479001600.0;                                 // cos: 1 - l2/2! + ... + l2^6/12!
+        pc = fma(pc, l2, -1.0 / 3628800.0); pc = fma(pc, l2, 1.0 / 40320.0); pc = fma(pc, l2, -1.0 / 720.0);
+        pc = fma(pc, l2, 1.0 / 24.0); pc = fma(pc, l2, -0.5); pc = fma(pc, l2, 1.0);
+        cl = pc;
+        const double rh = rsqrt(taup * taup + cl * cl);
+        rh2 = rh * rh;
+        v = sl * rh;                                                    // sinh(eta'), |v| <= tan 0.12 = 0.1206
+        const double w = v * v;
+        // asinh(v) = v (1 - w/6 + 3 w^2/40 - 5 w^3/112 + 35 w^4/1152 - 63 w^5/2816 + 231 w^6/13312 - 143 w^7/10240 + 6435 w^8/557056 - ...)
+        double pa = -12155.0 / 1245184.0;
+        pa = fma(pa, w, 6435.0 / 557056.0); pa = fma(pa, w, -143.0 / 10240.0); pa = fma(pa, w, 231.0 / 13312.0); pa = fma(pa, w, -63.0 / 2816.0);
+        pa = fma(pa, w, 35.0 / 1152.0); pa = fma(pa, w, -5.0 / 112.0); pa = fma(pa, w, 3.0 / 40.0); pa = fma(pa, w, -1.0 / 6.0); pa = fma(pa, w, 1.0);
+        etap = v * pa;
+    } else {
+        sincos(lam, &sl, &cl);
+        const double h2 = taup * taup + cl * cl;
+        rh2 = 1.0 / h2;
+        v = sl * sqrt(rh2);
+        etap = asinh(v);
+    }
     const double xip = atan2(taup, cl);
-    const double v = sl * rh;                                           // sinh(eta')
-    const double etap = asinh(v);
     const double s2 = 2.0 * taup * cl * rh2, c2 = (cl * cl - taup * taup) * rh2;
     const double sh2 = 2.0 * v * sqrt(1.0 + v * v), ch2 = 1.0 + 2.0 * v * v;
     krueger_series_sc(K.alpha, xip, etap, 1.0, s2, c2, sh2, ch2, xi, eta);

@@ -264,6 +264,12 @@ def test_utm_kernels(gsf):
         lo2, la2 = gsf.utm_inverse(e, n, 32, south)
         np.testing.assert_allclose(lo2.cpu().numpy(), lon, rtol=0, atol=1e-12)
         np.testing.assert_allclose(la2.cpu().numpy(), lat, rtol=0, atol=1e-12)
+    # far outside the zone (6.9 .. 20 deg from the central meridian): the library-function branch of the forward kernel
+    lon_far = 9.0 + rng.choice([-1.0, 1.0], 2000) * rng.uniform(6.8, 20.0, 2000); lat_far = rng.uniform(-79, 83, 2000)
+    e, n = gsf.utm_forward(dev(lon_far), dev(lat_far), 32, False)
+    eo, no = uk.utm_forward(lon_far, lat_far, 32, False)
+    np.testing.assert_allclose(e.cpu().numpy(), eo, rtol=0, atol=2e-8)
+    np.testing.assert_allclose(n.cpu().numpy(), no, rtol=0, atol=2e-8)
     for case in ("pairA", "pairB"):
         g = load_golden(case)
         raw = g["gnss_raw"]
