@@ -112,46 +112,62 @@ __global__ void utm_forward_kernel(const double* __restrict__ lon, const double*
 __device__ __forceinline__ bool gnss_row_valid(double lat, double lon) {
     return fabs(lat) <= 90.0 && fabs(lon) <= 180.0 && lat != 0.0 && lon != 0.0;
 }
-// Stage 1 of the masked means: fixed grid, fixed stride order -> part[grid][3] = sum lon, sum lat, count.
-__global__ void gnss_rows_sum_kernel(const double* __restrict__ rows, long long n, double* __restrict__ part) {
+// Zone guess from the first rows (one warp): out[2] = zone, out[3] = south flag of the mean over the valid rows among the
+// first 4096.  The projection runs with this guess while it accumulates the sums of ALL rows; a track whose overall mean
+// falls into another zone (or hemisphere) than its beginning is projected again (gnss_rows_zone_kernel raises the flag).
+__global__ void gnss_rows_guess_kernel(const double* __restrict__ rows, long long n, double* out) {
+    const double2* __restrict__ r2 = reinterpret_cast<const double2*>(rows);
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (long long i = threadIdx.x; i < n && i < 4096; i += 32) {
+        const double2 p = __ldg(r2 + 2 * i), q = __ldg(r2 + 2 * i + 1);
+        if (gnss_row_valid(p.y, q.x)) { a += q.x; b += p.y; c += 1.0; }
+    }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (threadIdx.x == 0) {
+        out[2] = c > 0.0 ? floor((a / c + 180.0) / 6.0) + 1.0 : 31.0;
+        out[3] = (c > 0.0 && b / c < 0.0) ? 1.0 : 0.0;
+    }
+}
+// Stage 2 (one thread): out = mean lon, mean lat, zone, south flag, valid count; part[0] = 1 if the zone / hemisphere
+// differ from the guess that the projection used (out[2], out[3] on entry).
+__global__ void gnss_rows_zone_kernel(double* part, int nparts, double* out) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = 0; i < nparts; ++i) { a += part[3 * i]; b += part[3 * i + 1]; c += part[3 * i + 2]; }
+    a /= c; b /= c;
+    const double zone = floor((a + 180.0) / 6.0) + 1.0;           // int((mean_lon + 180) // 6 + 1)
+    const double south = (b < 0.0) ? 1.0 : 0.0;
+    part[0] = (zone == out[2] && south == out[3]) ? 0.0 : 1.0;
+    out[0] = a; out[1] = b; out[2] = zone; out[3] = south; out[4] = c;
+}
+// Projection: one thread per row, two 128-bit loads; zone / hemisphere are read from device memory (no host
+// round trip).  Invalid rows become NaN measurements ("no GNSS at this stamp").  With `part` it also leaves the partial
+// sums of the masked means (stage 1 of the fixed-order reduction: fixed grid, fixed stride order -> part[grid][3] = sum lon,
+// sum lat, count); with `redo` it runs only if *redo != 0.
+__global__ void __launch_bounds__(256) gnss_rows_project_kernel(const double* __restrict__ rows, long long n, UtmConst K,
+                                                                const double* __restrict__ zone_dev, double* __restrict__ out_ts,
+                                                                double* __restrict__ out_xyz, double* __restrict__ part,
+                                                                const double* __restrict__ redo) {
     __shared__ double scratch[3 * 8];
+    if (redo && *redo == 0.0) return;
+    const double D2R = 0.017453292519943295769236907684886;
+    const double lon0 = (6.0 * zone_dev[2] - 183.0) * D2R, fn = zone_dev[3] != 0.0 ? 10000000.0 : 0.0;
     const double2* __restrict__ r2 = reinterpret_cast<const double2*>(rows);
     double v[3] = {0.0, 0.0, 0.0};
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double2 a = __ldg(r2 + 2 * i), b = __ldg(r2 + 2 * i + 1);       // (ts, lat), (lon, alt)
-        if (gnss_row_valid(a.y, b.x)) { v[0] += b.x; v[1] += a.y; v[2] += 1.0; }
-    }
-    block_sum<3>(v, scratch);
-    if (threadIdx.x == 0) { part[3 * blockIdx.x] = v[0]; part[3 * blockIdx.x + 1] = v[1]; part[3 * blockIdx.x + 2] = v[2]; }
-}
-// Stage 2 (one thread): out = mean lon, mean lat, zone, south flag, valid count.
-__global__ void gnss_rows_zone_kernel(const double* part, int nparts, double* out) {
-    double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = 0; i < nparts; ++i) { a += part[3 * i]; b += part[3 * i + 1]; c += part[3 * i + 2]; }
-    a /= c; b /= c;
-    out[0] = a; out[1] = b;
-    out[2] = floor((a + 180.0) / 6.0) + 1.0;           // int((mean_lon + 180) // 6 + 1)
-    out[3] = (b < 0.0) ? 1.0 : 0.0;
-    out[4] = c;
-}
-// Projection: one thread per row, two 128-bit loads; zone / hemisphere are read from device memory (no host
-// round trip).  Invalid rows become NaN measurements ("no GNSS at this stamp").
-__global__ void __launch_bounds__(256) gnss_rows_project_kernel(const double* __restrict__ rows, long long n, UtmConst K,
-                                                                const double* __restrict__ zone_dev, double* __restrict__ out_ts,
-                                                                double* __restrict__ out_xyz) {
-    const double D2R = 0.017453292519943295769236907684886;
-    const double lon0 = (6.0 * zone_dev[2] - 183.0) * D2R, fn = zone_dev[3] != 0.0 ? 10000000.0 : 0.0;
-    const double2* __restrict__ r2 = reinterpret_cast<const double2*>(rows);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double2 a = __ldg(r2 + 2 * i), b = __ldg(r2 + 2 * i + 1);       // (ts, lat), (lon, alt)
         double e = nan(""), nn = nan(""), up = nan("");
         if (gnss_row_valid(a.y, b.x)) {
+            v[0] += b.x; v[1] += a.y; v[2] += 1.0;
             double xi, eta;
             utm_forward_point(K, b.x * D2R - lon0, a.y * D2R, xi, eta);
             e = 500000.0 + K.A_k0 * eta; nn = fn + K.A_k0 * xi; up = b.y;
         }
         if (out_ts) out_ts[i] = a.x;
         out_xyz[3 * i] = e; out_xyz[3 * i + 1] = nn; out_xyz[3 * i + 2] = up;
+    }
+    if (part) {
+        block_sum<3>(v, scratch);
+        if (threadIdx.x == 0) { part[3 * blockIdx.x] = v[0]; part[3 * blockIdx.x + 1] = v[1]; part[3 * blockIdx.x + 2] = v[2]; }
     }
 }
 
@@ -504,11 +520,13 @@ cudaError_t launch_utm(bool inverse, const double* a, const double* b, long long
 cudaError_t launch_gnss_rows(const double* rows, long long n, const UtmConst& K, double* part, int nparts, double* zone_out,
                              double* out_ts, double* out_xyz, int num_sms, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    gnss_rows_sum_kernel<<<nparts, 256, 0, stream>>>(rows, n, part);
+    // one pass over the rows: projection with the zone of the track's beginning + the sums of the masked means; the zone of
+    // the whole track is known afterwards, and the (rare) track that needs another zone is projected a second time
+    gnss_rows_guess_kernel<<<1, 32, 0, stream>>>(rows, n, zone_out);
+    gnss_rows_project_kernel<<<nparts, 256, 0, stream>>>(rows, n, K, zone_out, out_ts, out_xyz, part, nullptr);
     gnss_rows_zone_kernel<<<1, 1, 0, stream>>>(part, nparts, zone_out);
-    long long blocks = (n + 255) / 256;
-    if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
-    gnss_rows_project_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rows, n, K, zone_out, out_ts, out_xyz);
+    gnss_rows_project_kernel<<<nparts, 256, 0, stream>>>(rows, n, K, zone_out, out_ts, out_xyz, nullptr, part);
+    (void)num_sms;
     return cudaGetLastError();
 }
 cudaError_t launch_geo_mean(const double* lon, const double* lat, long long n, double* part, int nparts, double* out, cudaStream_t stream) {

@@ -323,6 +323,19 @@ def test_fused_gnss_ingest_matches_loader_and_oracle(gsf):
     assert int(z[2]) == zone_o and bool(z[3]) == south_o and south_o
     assert np.isnan(xyz[~keep]).all()
     np.testing.assert_allclose(xyz[keep], np.column_stack((e, nn, rows[keep, 3])), rtol=0, atol=1e-8)
+    # a track that starts in zone 32 / north and whose overall mean lies in zone 33 / south: the projection runs with the zone
+    # of the first rows while it forms the means, and has to be repeated with the zone of the whole track (:127-134)
+    n = 20000
+    lon = np.where(np.arange(n) < 6000, 11.5, 13.5) + rng.normal(0, 0.01, n)
+    lat = np.where(np.arange(n) < 6000, 0.4, -0.4) + rng.normal(0, 0.01, n)
+    rows = np.column_stack([np.arange(n) * 0.1, lat, lon, np.full(n, 12.0)])
+    zone_o, south_o = uk.utm_zone_from_means(lon, lat)
+    assert (zone_o, south_o) == (33, True) and uk.utm_zone_from_means(lon[:4096], lat[:4096]) == (32, False)
+    e, nn = uk.utm_forward(lon, lat, zone_o, south_o)
+    _, xyz, zone = gsf.gnss_rows_to_utm(dev(rows), want_ts=False)
+    z = zone.cpu().numpy()
+    assert int(z[2]) == 33 and bool(z[3]) and int(z[4]) == n
+    np.testing.assert_allclose(xyz.cpu().numpy(), np.column_stack((e, nn, rows[:, 3])), rtol=0, atol=1e-8)
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
