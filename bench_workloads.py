@@ -285,8 +285,8 @@ def measure_config4(args, local_rank, ClockSampler, read_peak, with_cpu=False, s
                 "frac": n * 48 / (ms_reduce * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                 "kernel": "sim3_tile_stats_kernel (Umeyama reduction, 48 B/point)", "launch_ms": ms_reduce,
                 "algorithmic_bytes_per_launch": n * 48,
-                "other_stages": {"gnss_rows_project_kernel (64 B/pt incl. the zone pass; transcendental-bound)":
-                                 {"ms": ms_ingest, "GB/s": n * 88 / (ms_ingest * 1e-3) / 1e9},
+                "other_stages": {"gnss_rows_project_kernel (one pass: 32 B read, 32 B written per row, zone means in the same loop; FP64-bound)":
+                                 {"ms": ms_ingest, "GB/s": n * 64 / (ms_ingest * 1e-3) / 1e9},
                                  "assoc_long_moments_kernel (56 B/knot: t 8 + xyz 24 read, moments 24 written) + assoc_long_bracket_kernel + assoc_long_eval_kernel (89 B/stamp: stamp 8, knot t 8 + xyz 24 + moments 24 read, 24 + 1 written): 145 B/pt over the two passes":
                                  {"ms": ms_assoc, "GB/s": n * 145 / (ms_assoc * 1e-3) / 1e9, "pts_per_s": n / (ms_assoc * 1e-3)},
                                  "sim3_apply_kernel (112 B/pt)": {"ms": ms_apply, "GB/s": n * 112 / (ms_apply * 1e-3) / 1e9}}}

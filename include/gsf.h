@@ -253,7 +253,9 @@ int gsf_geo_zone_dev(const double* lon, const double* lat, int64_t n, double* pa
  *      (:127-134).  rows [n,4] = timestamp, lat, lon, alt in the loader's column order (:258), 16-byte
  *      aligned.  Rows failing the validity mask (:259) do not enter the zone means and come out as NaN
  *      measurements.  zone_out[5] = mean lon, mean lat, zone, south flag, valid rows (device; the
- *      projection reads the zone from there: no host round trip).  part: 3*GSF_GEO_PARTS doubles.
+ *      projection reads the zone from there: no host round trip; it runs once with the zone of the first
+ *      4096 rows while the means accumulate, and again only if the whole-track zone differs).
+ *      part: 3*GSF_GEO_PARTS doubles.
  *      out_ts [n] (may be NULL), out_xyz [n,3] = easting, northing, altitude. */
 int gsf_gnss_rows_to_utm_dev(const double* rows, int64_t n, double* part, double* zone_out,
                              double* out_ts, double* out_xyz, void* stream);
