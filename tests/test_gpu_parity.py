@@ -396,6 +396,33 @@ def test_association_long_trajectory_local_halo(gsf):
         np.testing.assert_allclose(a.cpu().numpy()[g["valid"]], g["aligned"][g["valid"]], rtol=0, atol=POS_ATOL)
 
 
+def test_association_long_gaps_at_chunk_and_block_edges(gsf):
+    """Segment ends placed on and next to the boundaries of the moments kernel's work split (15-knot chunks, 1920-knot blocks,
+    22-knot window margins, 20-knot halos) and next to the ends of the track, sorted stamps (staged evaluation) that include
+    every knot: against scipy per segment (oracle)."""
+    from oracle import fusion_oracle as fo
+    rng = np.random.default_rng(33)
+    M = 6000
+    edge_sets = [
+        [1919, 1920, 1921], [1905, 1935], [1898, 1899, 1900, 1941, 1942], [14, 15, 16, 29, 30, 31], [3839, 3840, 3841, 3855, 3860],
+        [1, 2, 3], [4, 5996], [5995, 5996, 5997, 5998], [1920 - 20, 1920 + 19], [1920 - 21, 1920 + 20, 1920 + 21], [3, 7, 11, 15, 19, 23, 27],
+        list(range(1900, 1960, 4)), [],
+    ]
+    for edges in edge_sets:
+        steps = rng.uniform(0.05, 0.3, M)
+        steps[np.array(edges, dtype=int)] = rng.uniform(5.5, 8.0, len(edges))       # a gap BEFORE knot k for every k in edges
+        steps[0] = 0.1
+        gt = 50.0 + np.cumsum(steps)
+        gy = np.column_stack([4.5e5 + 9.0 * gt + 20 * np.sin(gt / 5.0), 5.4e6 + 40 * np.cos(gt / 9.0), 100.0 + np.sin(gt / 2.0)]) + rng.normal(0, 0.3, (M, 3))
+        st = np.sort(np.concatenate([rng.uniform(gt[0] - 1, gt[-1] + 1, 9000), gt]))
+        want, want_valid = fo.associate(st, gt, gy, 5.0)
+        a, v, status = gsf.associate_spline_long(dev(gt), dev(gy), dev(st), 5.0)
+        assert int(status.cpu()[0]) == 0
+        a, v = a.cpu().numpy(), v.cpu().numpy().astype(bool)
+        np.testing.assert_array_equal(v, want_valid, err_msg=str(edges))
+        np.testing.assert_allclose(a[v], want[v], rtol=0, atol=POS_ATOL, err_msg=str(edges))
+
+
 def test_association_short_segments(gsf):
     """2-3 knot segments are linear, 1-knot segments are skipped (EKFGPSSLAM.py:361-362)."""
     from oracle import fusion_oracle as fo
