@@ -667,7 +667,7 @@ __device__ __forceinline__ void fast_compute_role(const FuseArgs& A) {
 
 // Pivot-shifted Umeyama sums of the pose pairs [pair_lo, pair_hi) of one trajectory, streamed from global memory by one
 // warp (lane-strided pairs, NP pairs in flight per lane, fixed order -> bit-reproducible).
-template <int NP>
+template <int NP, bool LDG = true>
 __device__ __forceinline__ void stream_pose_sums(const double* __restrict__ gp, const double* __restrict__ gz, long long e0, int n,
                                                  int pair_lo, int pair_hi, int lane, double* v,
                                                  double ps0, double ps1, double ps2, double pz0, double pz1, double pz2) {
@@ -685,7 +685,7 @@ __device__ __forceinline__ void stream_pose_sums(const double* __restrict__ gp, 
                     // plain read-only loads: the lines were requested with evict_last by the bulk prefetch, and a per-load
                     // cache-policy operand costs two uniform-register moves per load in this loop
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) { a[h][q] = __ldg(gp2 + 3 * pp + q); c[h][q] = __ldg(gz2 + 3 * pp + q); }
+                    for (int q = 0; q < 3; ++q) { a[h][q] = LDG ? __ldg(gp2 + 3 * pp + q) : gp2[3 * pp + q]; c[h][q] = LDG ? __ldg(gz2 + 3 * pp + q) : gz2[3 * pp + q]; }
                 } else if (pp < pair_hi && 2 * pp < n) {        // last pose of an odd-length trajectory
                     a[h][0] = make_double2(gp[6 * pp], gp[6 * pp + 1]); a[h][1] = make_double2(gp[6 * pp + 2], 0.0);
                     c[h][0] = make_double2(gz[6 * pp], gz[6 * pp + 1]); c[h][1] = make_double2(gz[6 * pp + 2], 0.0);
@@ -933,6 +933,269 @@ __global__ void __launch_bounds__(CT + 64, fast_min_blocks(CT)) fuse_fast_kernel
     else fast_scan_svd_role<CT, LCH>(A);
 }
 
+// ====================================================================== short trajectories: one warp per trajectory
+// Up to 32 * LCH poses.  The three roles above pay per trajectory for their hand-offs, for the second read of positions and
+// measurements and for a two-stage pipeline that has to fill -- fixed costs that a 271-pose trajectory does not amortise
+// (4096 x 271 poses: 31 % of the HBM roofline with the role kernel, its SVD warp busy 13 of every 15.8 k cycles).  Here a
+// block is ONE warp that takes a trajectory through the same steps by itself -- TMA load, covariance start scan, Umeyama
+// sums (from shared memory), SVD, pass B, warp scan, pass C, bulk store, quaternions -- with the same device functions in
+// the same order (bit-identical results), and the SM overlaps a dozen such warps at different stages instead of three
+// roles in lock step.  Work is handed out by the global counter.
+// MEASURED (round 2, tools/warp_vs_roles.py, profiles/r02_warp_kernel_*): bit-identical to the role kernel and 1.7x SLOWER
+// (262 144 x 271 poses: 5.36 vs 3.13 ms; 4096 x 271: 0.149 vs 0.102 ms).  Every warp walks the whole 72 KB of code
+// (4536 instructions) by itself, twelve warps per SM at twelve different places: instruction-cache hit rate 72 %, and
+// `no_instruction` + `branch_resolving` (the rolled shuffle scans) are the top stalls at 33 % issue utilisation -- the
+// role split is what keeps each warp inside a small loop.  Kept behind GSF_FAST_CT=1 (test_warp_kernel_matches_role_kernel).
+constexpr int WS_BC = 0, WS_SUMS = 48, WS_PRM = 72, WS_PST = 96, WS_MBAR = 192, WS_TOTAL = 200;      // doubles after the staging buffers
+__host__ __device__ constexpr size_t warp_smem_bytes(int cap) { return (size_t)((cap + 3) & ~1) * 56 + (size_t)WS_TOTAL * 8; }
+
+template <int LCH>
+__global__ void __launch_bounds__(32, 12) fuse_warp_kernel(const __grid_constant__ FuseArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cap2 = (A.cap + 3) & ~1;
+    double* const ts_s = reinterpret_cast<double*>(smem_raw);
+    double* const pos_s = ts_s + cap2;
+    double* const z_s = pos_s + 3 * (size_t)cap2;
+    double* const sd = z_s + 3 * (size_t)cap2;
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(sd + WS_MBAR);      // 0 trajectory, 1 quaternions part 1, 2 part 2
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+        mbar_init(mbar, 1); mbar_init(mbar + 1, 1); mbar_init(mbar + 2, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    uint32_t par_full = 0, par_q0 = 0, par_q1 = 0;
+    bool have_prm = false;
+    for (;;) {
+        // ---- next trajectory
+        TrajRef ref{0, 0, 0};
+        if (lane == 0) ref = traj_ref_from(A, atomicAdd(A.work_counter, 1));
+        const int b = __shfl_sync(GSF_FULL_MASK, ref.b, 0), n = __shfl_sync(GSF_FULL_MASK, ref.n, 0);
+        const long long e0 = __shfl_sync(GSF_FULL_MASK, ref.e0, 0);
+        if (b >= A.B) break;
+        const int lead = (int)(e0 & 1);
+        if (lane == 0) {
+            issue_trajectory_load_hint(A, e0, n, ts_s, pos_s, z_s, mbar);
+            const long long qn = ((long long)n * 32) & ~15ll;
+            bulk_prefetch_l2_hint(A.quat + 4 * e0, (uint32_t)qn, l2_policy_evict_last());
+        }
+        const double q0c = A.quat[4 * e0 + (lane & 3)];
+        if (lane < 23 && (A.params_per_traj || !have_prm))      // a batch-wide record is fetched once
+            sd[WS_PRM + lane] = reinterpret_cast<const double*>(A.params + (A.params_per_traj ? b : 0))[lane];
+        have_prm = true;
+        double* tsS = ts_s + lead; double* posS = pos_s + 3 * lead; double* zS = z_s + 3 * lead;
+        {
+            const int cnt = n + lead, even = cnt & ~1;
+            if ((cnt & 1) && lane < 7) {                  // odd tail element: plain copy
+                const long long g = e0 - lead + even;
+                if (lane == 0) ts_s[even] = A.ts[g];
+                else if (lane < 4) pos_s[3 * even + (lane - 1)] = A.pos[3 * g + (lane - 1)];
+                else z_s[3 * even + (lane - 4)] = A.z[3 * g + (lane - 4)];
+            }
+            if (even > 0) { mbar_wait_polite(mbar, par_full); par_full ^= 1; }
+        }
+        __syncwarp();
+        const FuseParams& prm = *reinterpret_cast<const FuseParams*>(sd + WS_PRM);
+        const bool xy_same = prm.p0[0] == prm.p0[1] && prm.q[0] == prm.q[1] && prm.r[0] == prm.r[1];
+        double* const bc = sd + WS_BC;
+        double* const pst = sd + WS_PST;
+        double* const sums = sd + WS_SUMS;
+
+        // ---- covariance start values + gap / window check (the scan warp's part 1)
+        int general = xy_same ? cov_start_scan<2, 32, LCH>(tsS, n, &prm, lane, pst, nullptr)
+                              : cov_start_scan<3, 32, LCH>(tsS, n, &prm, lane, pst, nullptr);
+        // ---- Umeyama sums from the staged tile (the sums warp), finish + SVD (the scan warp's part 2)
+        {
+            const double ps0 = posS[0], ps1 = posS[1], ps2 = posS[2], pz0 = zS[0], pz1 = zS[1], pz2 = zS[2];
+            double v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = 0.0;
+            stream_pose_sums<1, false>(posS, zS, e0, n, 0, (n + 1) >> 1, lane, v, ps0, ps1, ps2, pz0, pz1, pz2);
+            const double total = butterfly16(v, lane);
+            if (!(lane & 1)) sums[butterfly16_index(lane)] = total;
+            if (lane == 1) { sums[16] = ps0; sums[17] = ps1; sums[18] = ps2; sums[19] = pz0; sums[20] = pz1; sums[21] = pz2; }
+        }
+        __syncwarp();
+        int ust = 0;
+        {
+            double v[16], chk = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { v[q] = sums[q]; chk += v[q]; }
+            if (!(fabs(chk) <= 1.7976931348623157e308)) general = 1;       // NaN row (no GNSS) or non-finite input
+            if (n < 3 || n < prm.min_samples) general = 1;
+            const Quat q0{__shfl_sync(GSF_FULL_MASK, q0c, 0), __shfl_sync(GSF_FULL_MASK, q0c, 1), __shfl_sync(GSF_FULL_MASK, q0c, 2),
+                          __shfl_sync(GSF_FULL_MASK, q0c, 3)};
+            if (qnorm2(q0) == 0.0) general = 1;
+            if (!general) {
+                const double nn = (double)n, inv = 1.0 / nn;
+                const double ma[3] = {v[0] * inv, v[1] * inv, v[2] * inv}, mb[3] = {v[3] * inv, v[4] * inv, v[5] * inv};
+                double ms_[3], md_[3], hh[9];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { ms_[q] = sums[16 + q] + ma[q]; md_[q] = sums[19 + q] + mb[q]; }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) hh[3 * r + c] = v[6 + 3 * r + c] - nn * ma[r] * mb[c];
+                const double ss = v[15] - nn * (ma[0] * ma[0] + ma[1] * ma[1] + ma[2] * ma[2]);
+                double R[9], t[3], s = 1.0;
+                ust = umeyama_finish(n, ms_, md_, hh, ss, R, t, s);
+                if (lane == 0) {
+                    const Quat qR = quat_from_matrix(R);
+                    const Quat q0h = qunit(q0);
+                    const Quat qs0 = qunit_or_identity(qmul(qR, q0h));
+                    const Quat Cq = qmul(qs0, qconj(q0h));
+                    double M[9]; qmat(Cq, M);
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { bc[q] = M[q]; bc[20 + q] = R[q]; }
+                    bc[9] = Cq.x; bc[10] = Cq.y; bc[11] = Cq.z; bc[12] = Cq.w;
+                    double rx, ry, rz;
+                    mat_vec(R, sums[16], sums[17], sums[18], rx, ry, rz);
+                    bc[13] = s * rx + t[0]; bc[14] = s * ry + t[1]; bc[15] = s * rz + t[2];
+                    bc[16] = t[0]; bc[17] = t[1]; bc[18] = t[2]; bc[19] = s;
+                }
+            }
+        }
+        __syncwarp();
+        if (general) {
+            // needs the general machinery: leave it to the general kernel
+            if (lane == 0) { A.status[b] = ST_DEFERRED; atomicAdd(A.defer_count, 1); }
+            fence_proxy_async();
+            __syncwarp();
+            continue;
+        }
+
+        // ---- pass B: gains, affine maps, residual check (the compute warps' code with one warp)
+        const int c0 = min(lane * LCH, n), c1 = min(c0 + LCH, n);
+        const int s0 = max(c0, 1);
+        int st = ust;
+        const double thr2 = !(prm.residual_thresh > 0.0) ? -1.0 : prm.residual_thresh * prm.residual_thresh;
+        double pprev0 = 0.0, pprev1 = 0.0, pprev2 = 0.0;
+        if (c0 < n) { const int ip = max(c0 - 1, 0); pprev0 = posS[3 * ip]; pprev1 = posS[3 * ip + 1]; pprev2 = posS[3 * ip + 2]; }
+        int nviol = 0;
+        if (c0 == 0 && thr2 > 0.0) {                      // pose 0 against its Sim3 image
+            double rx, ry, rz;
+            mat_vec(bc, posS[0], posS[1], posS[2], rx, ry, rz);
+            const double d0 = bc[19] * rx + bc[16] - zS[0], d1 = bc[19] * ry + bc[17] - zS[1], d2 = bc[19] * rz + bc[18] - zS[2];
+            if (!(d0 * d0 + d1 * d1 + d2 * d2 < thr2)) ++nviol;
+        }
+        __syncwarp();                                     // neighbours' boundary poses are read before being overwritten
+        Aff3 aff;
+        if (xy_same) nviol += pass_b12<true>(tsS, posS, zS, bc, prm, pst + 3 * lane, s0, c1, thr2, pprev0, pprev1, pprev2, aff);
+        else nviol += pass_b12<false>(tsS, posS, zS, bc, prm, pst + 3 * lane, s0, c1, thr2, pprev0, pprev1, pprev2, aff);
+        const int viol_total = thr2 > 0.0 ? warp_sum_i(nviol) : 0;
+        Aff3 aex;                                         // exclusive affine prefix inside the warp
+        aff_warp_scan(aff, lane);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { aex.a[k] = __shfl_up_sync(GSF_FULL_MASK, aff.a[k], 1); aex.b[k] = __shfl_up_sync(GSF_FULL_MASK, aff.b[k], 1); }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { aex.a[k] = 1.0; aex.b[k] = 0.0; }
+        }
+        fence_proxy_async();                              // generic reads of the timestamp buffer before the TMA write below
+        __syncwarp();
+        // quaternions, part 1, into the dead timestamp buffer while pass C runs; part 2 into the position buffer after it
+        const int nq1 = min(n, (cap2 >> 2) & ~31);
+        if (lane == 0) {
+            mbar_expect_tx(mbar + 1, (uint32_t)nq1 * 32u);
+            if (nq1 > 0) bulk_g2s_hint(ts_s, A.quat + 4 * e0, (uint32_t)nq1 * 32u, mbar + 1, l2_policy_evict_first());
+        }
+        // ---- pass C: state recursion
+        {
+            double x0 = aex.a[0] * bc[13] + aex.b[0], x1 = aex.a[1] * bc[14] + aex.b[1], x2 = aex.a[2] * bc[15] + aex.b[2];
+            if (c0 == 0) { zS[0] = bc[13]; zS[1] = bc[14]; zS[2] = bc[15]; }
+#pragma unroll PASSC_UNROLL
+            for (int i = s0; i < c1; ++i) {
+                x0 = posS[3 * i] * x0 + zS[3 * i]; x1 = posS[3 * i + 1] * x1 + zS[3 * i + 1]; x2 = posS[3 * i + 2] * x2 + zS[3 * i + 2];
+                zS[3 * i] = x0; zS[3 * i + 1] = x1; zS[3 * i + 2] = x2;
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        // ---- store fused positions; stream the quaternions
+        double* gout = A.out_pos + 3 * e0;
+        if (viol_total) st |= ST_RANSAC_OUTLIERS;
+        if (lane == 0) {
+            const int m = n - lead, even = m & ~1;
+            if (even > 0) { bulk_s2g_hint(gout + 3 * lead, zS + 3 * lead, (uint32_t)even * 24u, l2_policy_evict_first()); bulk_commit(); }
+            if (lead) { gout[0] = zS[0]; gout[1] = zS[1]; gout[2] = zS[2]; }
+            if (m & 1) {
+                const int q = 3 * (lead + even);
+                gout[q] = zS[q]; gout[q + 1] = zS[q + 1]; gout[q + 2] = zS[q + 2];
+            }
+            A.status[b] = st;
+            if (A.sim3_out) {
+                double* o = A.sim3_out + 16 * (size_t)b;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) o[k] = bc[20 + k];
+                o[9] = bc[16]; o[10] = bc[17]; o[11] = bc[18]; o[12] = bc[19];
+                o[13] = (double)n; o[14] = (double)n; o[15] = (double)viol_total;
+            }
+            if (n > nq1) {
+                mbar_expect_tx(mbar + 2, (uint32_t)(n - nq1) * 32u);
+                bulk_g2s_hint(ts_s + 4 * nq1, A.quat + 4 * (e0 + nq1), (uint32_t)(n - nq1) * 32u, mbar + 2, l2_policy_evict_first());
+            }
+        }
+        int bad = 0;
+        {
+            const Quat C{bc[9], bc[10], bc[11], bc[12]};
+            const uint64_t pf = l2_policy_evict_first();
+            double2* __restrict__ qout = reinterpret_cast<double2*>(A.out_quat + 4 * e0);
+            const double2* __restrict__ q2 = reinterpret_cast<const double2*>(ts_s);
+            mbar_wait_polite(mbar + 1, par_q0); par_q0 ^= 1;
+            int i0 = 0, stop = min(n, nq1);
+#pragma unroll 1
+            for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+                for (; i0 < stop; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int ia = i < n ? i : 0;             // the tail re-reads a landed pose and stores nothing
+                    const double2 lo0 = q2[2 * ia], hi0 = q2[2 * ia + 1];
+                    const Quat qa{lo0.x, lo0.y, hi0.x, hi0.y};
+                    const double na = qnorm2(qa);
+                    if (na == 0.0) bad = 1;                   // scipy raises here (:466); output row becomes NaN
+                    const Quat rr = qscale(qmul(C, qa), fast_rsqrt(na));
+                    if (i < n) {
+                        stg2_hint(qout + 2 * i, make_double2(rr.x, rr.y), pf);
+                        stg2_hint(qout + 2 * i + 1, make_double2(rr.z, rr.w), pf);
+                    }
+                }
+                if (phase == 0 && n > nq1) { mbar_wait_polite(mbar + 2, par_q1); par_q1 ^= 1; }
+                stop = n;
+            }
+        }
+        fence_proxy_async();                                  // generic reads of the buffers before the next TMA writes
+        __syncwarp();                                         // (and lane 0's status store is ordered before the flag below)
+        if (bad) atomicOr(A.status + b, ST_BAD_QUATERNION);
+        if (lane == 0) bulk_wait_read();                      // the position store has left shared memory
+        __syncwarp();
+    }
+}
+
+template <int LCH>
+static cudaError_t launch_warp_t(const FuseArgs& a, int num_sms, cudaStream_t stream) {
+    const size_t smem = warp_smem_bytes(a.cap);
+    auto kern = fuse_warp_kernel<LCH>;
+    static std::atomic<long long> cached_smem{-1};
+    static std::atomic<int> cached_per_sm{0};
+    int per_sm = 0;
+    if (cached_smem.load(std::memory_order_acquire) == (long long)smem) per_sm = cached_per_sm.load(std::memory_order_relaxed);
+    else {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        cached_per_sm.store(per_sm, std::memory_order_relaxed);
+        cached_smem.store((long long)smem, std::memory_order_release);
+    }
+    long long grid = (long long)num_sms * per_sm;
+    if (grid > a.B) grid = a.B;
+    kern<<<(unsigned)grid, 32, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
 // Deferred-trajectory counters (one per in-flight call, recycled round-robin): module-level device
 // memory, so the *_dev entry point needs no workspace argument and allocates nothing.
 __device__ int g_defer_count[128];          // pairs: [deferred count, work counter]
@@ -1004,6 +1267,7 @@ static int fast_variant(int cap) {
     if (f == 64 && cap <= 64 * 9) return 6409;
     if (f == 64 && cap <= 64 * 17) return 6417;
     if (f == 32 && cap <= 32 * 9) return 3209;
+    if (f == 1 && cap <= 32 * 9) return 1;           // one warp per trajectory (fuse_warp_kernel): measured slower, see there
     if (cap <= 32 * 9) return 3209;
     if (cap <= 64 * 9) return 6409;
     if (cap <= 64 * 17) return 6417;                 // two compute warps x 17 poses per thread: 1 % faster than 96 x 11 at 1000 poses
@@ -1014,10 +1278,12 @@ static int fast_variant(int cap) {
 static int variant_ct(int v) { return v / 100; }
 bool fast_fuse_supported(int cap, int max_smem) {
     const int v = fast_variant(cap);
+    if (v == 1) return warp_smem_bytes(cap) <= (size_t)max_smem;
     return v > 0 && fast_smem_bytes(cap, variant_ct(v)) <= (size_t)max_smem;
 }
 cudaError_t launch_fuse_fast(const FuseArgs& a, int num_sms, cudaStream_t stream) {
     switch (fast_variant(a.cap)) {
+        case 1: return launch_warp_t<9>(a, num_sms, stream);
         case 3209: return launch_fast_t<32, 9>(a, num_sms, stream);
         case 6409: return launch_fast_t<64, 9>(a, num_sms, stream);
         case 6417: return launch_fast_t<64, 17>(a, num_sms, stream);

@@ -396,6 +396,33 @@ def test_association_long_trajectory_local_halo(gsf):
         np.testing.assert_allclose(a.cpu().numpy()[g["valid"]], g["aligned"][g["valid"]], rtol=0, atol=POS_ATOL)
 
 
+def test_warp_kernel_matches_role_kernel(gsf, monkeypatch):
+    """The one-warp-per-trajectory variant of the fast kernel (GSF_FAST_CT=1, kept as a measured alternative) runs the same
+    device functions in the same order as the role kernel: bit-identical outputs, ragged lengths and odd offsets included."""
+    lens = [271, 33, 1, 2, 288, 97, 270, 3, 64, 255] * 40
+    ts, pos, quat, z, off = _ragged_batch(gsf, lens)
+    prm = gsf.params_tensor()
+    monkeypatch.delenv("GSF_FAST_CT", raising=False)
+    a = [o.clone() for o in gsf.fuse_batched(ts, pos, quat, z, off, max(lens), prm)]
+    monkeypatch.setenv("GSF_FAST_CT", "1")
+    b = gsf.fuse_batched(ts, pos, quat, z, off, max(lens), prm)
+    for x, y in zip(a, b):            # bit patterns: the deferred 1- and 2-pose trajectories come out as NaN rows in both
+        assert torch.equal(x.view(torch.int64) if x.dtype == torch.float64 else x, y.view(torch.int64) if y.dtype == torch.float64 else y)
+    assert int((a[3] == 0).sum()) == 280          # 1, 2 and 3 poses: not enough points for the Sim3 (status set, same in both)
+
+
+def _ragged_batch(gsf, lens):
+    """Device-generated equal-length batch cut to ragged lengths (offsets into the packed arrays)."""
+    n = max(lens)
+    ts, pos, quat, z = gsf.synth_generate(len(lens), n, 0.104, 13.0, seed=11)
+    keep = torch.zeros((len(lens), n), dtype=torch.bool, device=ts.device)
+    for k, m in enumerate(lens):
+        keep[k, :m] = True
+    flat = keep.reshape(-1)
+    off = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=ts.device)
+    return ts.reshape(-1)[flat].contiguous(), pos.reshape(-1, 3)[flat].contiguous(), quat.reshape(-1, 4)[flat].contiguous(), z.reshape(-1, 3)[flat].contiguous(), off
+
+
 def test_association_long_gaps_at_chunk_and_block_edges(gsf):
     """Segment ends placed on and next to the boundaries of the moments kernel's work split (15-knot chunks, 1920-knot blocks,
     22-knot window margins, 20-knot halos) and next to the ends of the track, sorted stamps (staged evaluation) that include

@@ -15,8 +15,9 @@ ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum 
 ./tools/ncu_kernel.sh p_general fuse_traj_kernel 3 -- python tools/fast_vs_general.py 65536 1000 0.5
 ./tools/ncu_kernel.sh p_combine grid_combine_kernel 3 -- python bench.py --workload config5 $B --steps 1 --warmup 3
 ./tools/ncu_kernel.sh p_ate ate_nn_kernel 2 -- python bench.py $B --no-e2e --no-config5 --no-mixed --steps 1 --trajectories 131072
+GSF_FAST_CT=1 ./tools/ncu_kernel.sh p_warp fuse_warp_kernel 2 -- python tools/ab_short.py 65536 271 3
 ./tools/ncu_kernel.sh p_f32 fuse_f32_kernel 2 -- python tools/f32_bench.py 131072 1000
 ./tools/ncu_kernel.sh p_assoc_m assoc_long_moments_kernel 2 -- python bench.py --workload config4 $B --steps 1 --warmup 3 --poses 20000000
 ./tools/ncu_kernel.sh p_assoc_e assoc_long_eval_kernel 2 -- python bench.py --workload config4 $B --steps 1 --warmup 3 --poses 20000000
-rm -f gpurun_out/p_assoc_m.ncu-rep gpurun_out/p_assoc_e.ncu-rep gpurun_out/p_f32.ncu-rep gpurun_out/p_ate.ncu-rep
+rm -f gpurun_out/p_warp.ncu-rep gpurun_out/p_assoc_m.ncu-rep gpurun_out/p_assoc_e.ncu-rep gpurun_out/p_f32.ncu-rep gpurun_out/p_ate.ncu-rep
 ls -la gpurun_out | tail -30

@@ -57,7 +57,8 @@ summarise("combine", "grid_combine_kernel", "config 5, 262 144 hypotheses x 4541
 summarise("ate", "ate_nn_kernel", "131 072 trajectories x 1000 poses", 131072 * 1000, 56)
 summarise("f32", "fuse_f32_kernel", "fp32 mode, 131 072 trajectories x 1000 poses", 131072 * 1000, 72)
 summarise("assoc_m", "assoc_long_moments_kernel", "config 4 at 2e7 samples: local-halo spline moments", 20000000, 56, "sample")
-summarise("assoc_e", "assoc_long_eval_kernel", "config 4 at 2e7 samples: per-stamp evaluation", 20000000, 57, "sample")
+summarise("assoc_e", "assoc_long_eval_kernel", "config 4 at 2e7 samples: per-stamp evaluation", 20000000, 89, "sample")
+summarise("warp", "fuse_warp_kernel", "65 536 x 271 poses, one warp per trajectory (GSF_FAST_CT=1; measured alternative, not the default)", 65536 * 271, 144)
 for c in (2, 3, 4, 5):
     src = f"gpurun_out/p_bench_config{c}.json"
     if os.path.exists(src) and os.path.getsize(src) > 0:
