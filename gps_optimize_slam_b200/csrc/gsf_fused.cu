@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                 }
             }
             __syncthreads();
+            GSF_STAMP(10);
             for (int i = s0; i < c1; ++i) {
                 const int f = flg[i];
                 if ((f & FLAG_VALID) && !(flg[i - 1] & FLAG_VALID)) {
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             }
         }
         // ------------------------------------------------------------------ general Sim3 point selection (:972-998), rare
+        GSF_STAMP(11);
         if (!ekf_only && iscr[11]) {
             int cntv = 0; double lastT = nan("");
             for (int i = c0; i < c1; ++i) if (flg[i] & FLAG_VALID) { ++cntv; lastT = tsS[i]; }

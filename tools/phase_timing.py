@@ -4,7 +4,8 @@ sys.path.insert(0, ".")
 from gps_optimize_slam_b200 import _lib, fusion
 lib = _lib.load()
 B, n = int(sys.argv[1]), int(sys.argv[2])
-ts, pos, quat, z = fusion.synth_generate(B, n, 0.1, 10.0, seed=1)
+outage = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0            # share of trajectories with GNSS outages
+ts, pos, quat, z = fusion.synth_generate(B, n, 0.1, 10.0, seed=1, outage_prob=outage, outage_max_len=20)
 off = fusion.equal_offsets(B, n); prm = fusion.params_tensor()
 buf = torch.zeros(16, dtype=torch.int64, device="cuda")
 lib.gsf_debug_phase_clock.argtypes = [ctypes.c_void_p]; lib.gsf_debug_phase_clock.restype = None
@@ -18,4 +19,6 @@ print("n", n, "total cycles", c[6] - c[0])
 for k, nm in enumerate(names):
     print(f"  {nm:36s} {c[k+1]-c[k]:8d}")
 print("  [pass2 detail] moebius+scan", c[7]-c[2], " sums-combine", c[8]-c[7], " svd call", c[9]-c[8], " bcast+sync", c[3]-c[9])
+if c[10] and c[11]:
+    print("  [2->7 detail] sharp-turn gate", c[10]-c[2], " recovery flags", c[11]-c[10], " Sim3 selection + centred sums", c[7]-c[11])
 lib.gsf_debug_phase_clock(None)
