@@ -450,6 +450,34 @@ def test_association_long_gaps_at_chunk_and_block_edges(gsf):
         np.testing.assert_allclose(a[v], want[v], rtol=0, atol=POS_ATOL, err_msg=str(edges))
 
 
+def test_association_long_degenerate_sizes(gsf):
+    """Tracks of 1 .. 6 knots, stamp sets of 1 / 3 / 2049 / 4100 entries (tile edges of the evaluation), NaN stamps, and the
+    status flag for stamps that do not increase inside a segment (:356-359)."""
+    from oracle import fusion_oracle as fo
+    rng = np.random.default_rng(5)
+    for M in (1, 2, 3, 4, 5, 6):
+        gt = 10.0 + np.cumsum(rng.uniform(0.1, 0.5, M))
+        gy = rng.normal(0, 5.0, (M, 3)) + [4e5, 5e6, 100.0]
+        for N in (1, 3, 2049, 4100):
+            st = np.sort(rng.uniform(gt[0] - 0.5, gt[-1] + 0.5, N))
+            st[N // 2] = gt[M // 2]
+            want, want_valid = fo.associate(st, gt, gy, 5.0)
+            a, v, status = gsf.associate_spline_long(dev(gt), dev(gy), dev(st), 5.0)
+            assert int(status.cpu()[0]) == 0
+            a, v = a.cpu().numpy(), v.cpu().numpy().astype(bool)
+            np.testing.assert_array_equal(v, want_valid, err_msg=f"M={M} N={N}")
+            np.testing.assert_allclose(a[v], want[v], rtol=0, atol=POS_ATOL, err_msg=f"M={M} N={N}")
+            assert np.isnan(a[~v]).all()
+    gt = 10.0 + np.cumsum(rng.uniform(0.1, 0.5, 5000)); gy = rng.normal(0, 5.0, (5000, 3))
+    st = np.sort(rng.uniform(gt[0], gt[-1], 3000)); st[[0, 7, 2999]] = np.nan
+    a, v, status = gsf.associate_spline_long(dev(gt), dev(gy), dev(st), 5.0)
+    v = v.cpu().numpy().astype(bool)
+    assert not v[[0, 7, 2999]].any() and v.sum() == 2997 and int(status.cpu()[0]) == 0
+    gt_bad = gt.copy(); gt_bad[2500] = gt_bad[2499]                       # a repeated stamp inside a segment
+    _, _, status = gsf.associate_spline_long(dev(gt_bad), dev(gy), dev(st), 5.0)
+    assert int(status.cpu()[0]) == 1
+
+
 def test_association_short_segments(gsf):
     """2-3 knot segments are linear, 1-knot segments are skipped (EKFGPSSLAM.py:361-362)."""
     from oracle import fusion_oracle as fo
