@@ -411,6 +411,31 @@ def test_warp_kernel_matches_role_kernel(gsf, monkeypatch):
     assert int((a[3] == 0).sum()) == 280          # 1, 2 and 3 poses: not enough points for the Sim3 (status set, same in both)
 
 
+def test_fused_call_replays_from_a_cuda_graph(gsf):
+    """gsf_fuse_batched_dev inside a stream capture (its memset and both kernels become graph nodes): replays give the
+    eager call's bits, also for a batch with deferred (outage) trajectories.  bench.py times config 2 this way."""
+    B, n = 600, 271
+    ts, pos, quat, z = gsf.synth_generate(B, n, 0.104, 13.0, seed=3, outage_prob=0.3, outage_max_len=15)
+    off = gsf.equal_offsets(B, n); prm = gsf.params_tensor()
+    want = [o.clone() for o in gsf.fuse_batched(ts, pos, quat, z, off, n, prm)]
+    outs = dict(out_pos=torch.empty_like(pos), out_quat=torch.empty_like(quat), sim3_out=torch.empty((B, 16), dtype=torch.float64, device="cuda"),
+                status=torch.empty((B,), dtype=torch.int32, device="cuda"))
+    gsf.fuse_batched(ts, pos, quat, z, off, n, prm, **outs)                  # warm-up: attributes and occupancy are cached
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        gsf.fuse_batched(ts, pos, quat, z, off, n, prm, **outs)
+    for _ in range(3):
+        for t in outs.values():
+            t.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        got = (outs["out_pos"], outs["out_quat"], outs["sim3_out"], outs["status"])
+        for x, y in zip(want, got):
+            assert torch.equal(x.view(torch.int64) if x.dtype == torch.float64 else x, y.view(torch.int64) if y.dtype == torch.float64 else y)
+    assert 0 < int((want[3] == 0).sum()) <= B
+
+
 def _ragged_batch(gsf, lens):
     """Device-generated equal-length batch cut to ragged lengths (offsets into the packed arrays)."""
     n = max(lens)
