@@ -140,11 +140,12 @@ int gsf_fuse_batched_dev(const double* ts, const double* pos, const double* quat
         else if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter)");
         else {
             a.work_counter = a.defer_count + 1;
-            e = cudaMemsetAsync(a.defer_count, 0, 2 * sizeof(int), (cudaStream_t)stream);
+            e = cudaMemsetAsync(a.defer_count, 0, 4 * sizeof(int), (cudaStream_t)stream);
             if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (defer counter reset)");
             e = gsf::launch_fuse_fast(a, d.sms, (cudaStream_t)stream);
             if (e != cudaSuccess) return cuda_fail(e, "gsf_fuse_batched_dev (fast kernel)");
             a.only_deferred = 1;
+            a.work_counter = a.defer_count + 2;           // the deferred pass hands out chunks of trajectories from its own counter
         }
     }
     e = gsf::launch_fuse(a, pick_threads(cap, d.max_smem), d.sms, (cudaStream_t)stream);

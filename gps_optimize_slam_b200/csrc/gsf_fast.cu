@@ -1198,7 +1198,7 @@ static cudaError_t launch_warp_t(const FuseArgs& a, int num_sms, cudaStream_t st
 
 // Deferred-trajectory counters (one per in-flight call, recycled round-robin): module-level device
 // memory, so the *_dev entry point needs no workspace argument and allocates nothing.
-__device__ int g_defer_count[128];          // pairs: [deferred count, work counter]
+__device__ int g_defer_count[256];          // per slot: deferred count, fast kernel work counter, general kernel chunk counter, pad
 // One slot per in-flight call, handed out round-robin.  A slot is released by an event recorded behind the call's last
 // kernel (defer_counter_release); a call that draws a slot whose previous user has not finished (more than 64 calls in
 // flight on different streams, or overlapping replays of a captured graph) gets cudaErrorNotReady and the caller falls
@@ -1216,7 +1216,7 @@ cudaError_t defer_counter(int** out, int* slot_out) {
         if (q == cudaErrorNotReady) return cudaErrorNotReady;
         if (q != cudaSuccess) { cudaGetLastError(); }
     }
-    *out = base + 2 * slot;
+    *out = base + 4 * slot;
     *slot_out = (int)slot;
     return cudaSuccess;
 }

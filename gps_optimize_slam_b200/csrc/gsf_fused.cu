@@ -92,22 +92,30 @@ __device__ __forceinline__ int block_min_int(int v, int* scratch) {
     return r;
 }
 
-// Next trajectory of a block (static stride over the batch).  When only the trajectories the fast kernel deferred are
-// processed, the block's sequence is scanned ahead to the next deferred one (four independent status reads per round), so
-// that its bulk loads are in flight while the current trajectory is finished -- a load issued for the plain successor is
-// wasted whenever that one is not deferred (load wait 6.7 k -> 2 k cycles per trajectory at 50 % deferred).
-__device__ __forceinline__ int next_trajectory(const FuseArgs& A, int b, int stride) {
-    int nb = b + stride;
-    if (!A.only_deferred) return nb;
-    while (nb < A.B) {
-        int st[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const long long idx = (long long)nb + (long long)k * stride; st[k] = idx < A.B ? A.status[idx] : ST_DEFERRED; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (st[k] == ST_DEFERRED) return (int)min((long long)nb + (long long)k * stride, (long long)A.B);
-        nb += 4 * stride;
+// Next trajectory of a block.  Whole batch: static stride.  Deferred pass (only the trajectories the fast kernel left):
+// chunks of 8 consecutive indices are claimed from a global counter and the deferred ones among them are taken in order --
+// a static stride gives every block a binomial share of the deferred trajectories (+-17 % at 50 %), and a load issued for
+// the plain successor is wasted whenever that one is not deferred.  Called by thread 0 only; the cursor lives in its registers.
+constexpr int DQ_CHUNK = 8;
+struct TrajCursor { int base; unsigned mask; };
+__device__ __forceinline__ int next_trajectory(const FuseArgs& A, int b, int stride, TrajCursor& cur) {
+    if (!A.only_deferred || !A.work_counter) {
+        int nb = b + stride;
+        if (A.only_deferred) while (nb < A.B && A.status[nb] != ST_DEFERRED) nb += stride;
+        return min(nb, A.B);
     }
-    return A.B;
+    for (;;) {
+        if (cur.mask) { const int k = __ffs(cur.mask) - 1; cur.mask &= cur.mask - 1; return cur.base + k; }
+        const int c = atomicAdd(A.work_counter, DQ_CHUNK);
+        if (c >= A.B) return A.B;
+        int st[DQ_CHUNK];
+#pragma unroll
+        for (int k = 0; k < DQ_CHUNK; ++k) st[k] = c + k < A.B ? A.status[c + k] : 0;
+        unsigned m = 0;
+#pragma unroll
+        for (int k = 0; k < DQ_CHUNK; ++k) if (st[k] == ST_DEFERRED) m |= 1u << k;
+        cur.base = c; cur.mask = m;
+    }
 }
 
 // ----------------------------------------------------------------------------- shared-memory map
@@ -142,11 +150,16 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t parity = 0;
     if (A.only_deferred && *A.defer_count == 0) return;     // nothing was left by the fast kernel
-    if (tid == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-    __syncthreads();
     const int stride = (int)gridDim.x;
-    const int first = next_trajectory(A, (int)blockIdx.x - stride, stride);      // (the block's first deferred trajectory in that mode)
-    if (A.use_tma && tid == 0 && first < A.B) issue_trajectory_load(A, first, ts_s, pos_s, z_s, mbar);
+    TrajCursor cursor{0, 0u};
+    if (tid == 0) {
+        mbar_init(mbar, 1); fence_mbar_init();
+        const int f = next_trajectory(A, (int)blockIdx.x - stride, stride, cursor);      // (deferred pass: the block's first deferred trajectory)
+        iscr[15] = f;
+        if (A.use_tma && f < A.B) issue_trajectory_load(A, f, ts_s, pos_s, z_s, mbar);
+    }
+    __syncthreads();
+    const int first = iscr[15];
 
     // quaternion rounds of the previous trajectory still to do (they run in the shadow of the next SVD)
     long long dq_e0 = 0; int dq_n = 0, dq_b = -1; Quat dq_C{0.0, 0.0, 0.0, 1.0};
@@ -159,11 +172,15 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
         const int n = (int)(A.offsets[b + 1] - e0);
         const bool not_mine = A.only_deferred && A.status[b] != ST_DEFERRED;   // status[b] is only ever written by this block
         if (n <= 0 || n > A.cap || not_mine) {
-            nb = next_trajectory(A, b, stride);
+            __syncthreads();                                // (everybody has read the previous iscr[15])
             if (tid == 0) {
                 if (!not_mine) A.status[b] = n <= 0 ? ST_EMPTY : ST_TOO_LONG;
-                if (A.use_tma && nb < A.B) issue_trajectory_load(A, nb, ts_s, pos_s, z_s, mbar);
+                const int nx = next_trajectory(A, b, stride, cursor);
+                iscr[15] = nx;
+                if (A.use_tma && nx < A.B) issue_trajectory_load(A, nx, ts_s, pos_s, z_s, mbar);
             }
+            __syncthreads();
+            nb = iscr[15];
             continue;
         }
         GSF_STAMP(0);
@@ -445,7 +462,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
                     for (int k = 0; k < 13; ++k) o[k] = nan("");
                     o[13] = (double)iscr[12]; o[14] = (double)iscr[13]; o[15] = 0.0;
                 }
-                const int nx = next_trajectory(A, b, stride);
+                const int nx = next_trajectory(A, b, stride, cursor);
                 iscr[15] = nx;
                 if (A.use_tma && nx < A.B) issue_trajectory_load(A, nx, ts_s, pos_s, z_s, mbar);
             }
@@ -679,7 +696,7 @@ __global__ void __launch_bounds__(THREADS, fuse_min_blocks(THREADS)) fuse_traj_k
             const int n_now = (NW > 1 && GSF_DEFER_QUAT) ? min(n, 4 * THREADS) : n;
             int bad = quat_rounds(A.quat + 4 * e0, A.out_quat + 4 * e0, C, tid, THREADS, n_now);
             if (tid == 0) {
-                const int nx = next_trajectory(A, b, stride);
+                const int nx = next_trajectory(A, b, stride, cursor);
                 iscr[15] = nx;
                 if (A.use_tma) {
                     bulk_wait_read();                               // shared memory is free again
