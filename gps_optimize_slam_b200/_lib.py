@@ -42,6 +42,8 @@ SIGNATURES = {
     "gsf_quat_nlerp_dev": (c_int32, [c_void_p] * 3 + [c_int64, c_void_p, c_void_p]),
     "gsf_sharp_turn_dev": (c_int32, [c_void_p] * 3 + [c_int32, c_double] + [c_void_p] * 3),
     "gsf_umeyama_work_doubles": (c_int64, [c_int32, c_int64]),
+    "gsf_sim3_partial_stats_dev": (c_int32, [c_void_p] * 4 + [c_int64] + [c_void_p] * 3),
+    "gsf_sim3_from_partial_stats_dev": (c_int32, [c_void_p, c_int32] + [c_void_p] * 5),
     "gsf_sim3_umeyama_batched_dev": (c_int32, [c_void_p] * 4 + [c_int32, c_int64] + [c_void_p] * 6),
     "gsf_sim3_ransac_work_doubles": (c_int64, [c_int32, c_int64]),
     "gsf_sim3_ransac_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_double, c_int32] + [c_void_p] * 8),

@@ -365,6 +365,24 @@ int gsf_sim3_umeyama_batched_dev(const double* src, const double* dst, const int
     return 0;
 }
 
+int gsf_sim3_partial_stats_dev(const double* src, const double* dst, const int64_t* offsets2, const uint8_t* mask, int64_t n,
+                               double* work, double* stats17, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (n < 0 || !src || !dst || !offsets2 || !work || !stats17) return fail(GSF_E_INVALID, "gsf_sim3_partial_stats_dev: null pointer or negative size");
+    cudaError_t e = gsf::launch_sim3_partial_stats(src, dst, reinterpret_cast<const long long*>(offsets2), mask, n, work, stats17, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_sim3_partial_stats_dev");
+    return 0;
+}
+int gsf_sim3_from_partial_stats_dev(const double* stats, int32_t shards, double* R, double* t, double* s, int32_t* status, void* stream) {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(GSF_E_NO_DEVICE, "no sm_100 CUDA device (libgsf has no CPU fallback)");
+    if (shards <= 0 || !stats || !R || !t || !s || !status) return fail(GSF_E_INVALID, "gsf_sim3_from_partial_stats_dev: null pointer or bad shard count");
+    cudaError_t e = gsf::launch_sim3_from_partial_stats(stats, shards, R, t, s, status, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gsf_sim3_from_partial_stats_dev");
+    return 0;
+}
+
 int64_t gsf_sim3_ransac_work_doubles(int32_t trials, int64_t n) {
     return gsf::sim3_ransac_work_doubles(trials < 0 ? 0 : trials, n < 0 ? 0 : n);
 }

@@ -61,6 +61,8 @@ cudaError_t launch_associate_long(const double*, const double*, long long, const
 int sim3_tiles_for(long long max_len);
 cudaError_t launch_umeyama(const double*, const double*, const long long*, const unsigned char*, int, long long, double*,
                            double*, double*, double*, int*, cudaStream_t);
+cudaError_t launch_sim3_partial_stats(const double*, const double*, const long long*, const unsigned char*, long long, double*, double*, cudaStream_t);
+cudaError_t launch_sim3_from_partial_stats(const double*, int, double*, double*, double*, int*, cudaStream_t);
 cudaError_t launch_sim3_ransac(const double*, const double*, long long, const int*, int, int, double, int, double*, unsigned char*,
                                double*, double*, double*, int*, int*, int, cudaStream_t);
 long long sim3_ransac_work_doubles(int T, long long n);

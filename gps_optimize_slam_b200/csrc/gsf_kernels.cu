@@ -428,9 +428,11 @@ __device__ __forceinline__ void sim3_merge(double* a, const double* b) {
 
 // One warp per trajectory: every lane merges a contiguous run of tiles in tile order, then the lanes are merged
 // by a fixed in-order tree (lane L absorbs lane L + o for o = 1, 2, 4, ...) -> deterministic; lane 0 finishes.
+// stats_out != NULL: the merged statistics (SIM3_STAT doubles per trajectory) are stored and nothing else -- one shard's
+// contribution to a trajectory that is spread over several GPUs (gsf_sim3_partial_stats_dev).
 __global__ void __launch_bounds__(128) sim3_finalize_kernel(const double* __restrict__ stats, int tiles_max, int B,
                                                             double* __restrict__ Rout, double* __restrict__ tout, double* __restrict__ sout,
-                                                            int* __restrict__ status) {
+                                                            int* __restrict__ status, double* __restrict__ stats_out) {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
     double acc[17];
@@ -448,6 +450,11 @@ __global__ void __launch_bounds__(128) sim3_finalize_kernel(const double* __rest
         }
     }
     if (lane != 0) return;
+    if (stats_out) {
+#pragma unroll
+        for (int k = 0; k < SIM3_STAT; ++k) stats_out[SIM3_STAT * (size_t)b + k] = k < 17 ? acc[k] : 0.0;
+        return;
+    }
     double* R = Rout + 9 * (size_t)b; double* t = tout + 3 * (size_t)b;
     if (acc[0] < 3.0) {                                 // (None, None, None), :431
         for (int k = 0; k < 9; ++k) R[k] = nan("");
@@ -550,7 +557,22 @@ cudaError_t launch_umeyama(const double* src, const double* dst, const long long
         dim3 grid(tiles, nb);
         sim3_tile_stats_kernel<<<grid, 256, 0, stream>>>(src, dst, offsets + b0, mask, tiles, sim3_tile_len(max_len), work + (size_t)b0 * tiles * SIM3_STAT);
     }
-    sim3_finalize_kernel<<<(B + 3) / 4, 128, 0, stream>>>(work, tiles, B, R, t, s, status);
+    sim3_finalize_kernel<<<(B + 3) / 4, 128, 0, stream>>>(work, tiles, B, R, t, s, status, nullptr);
+    return cudaGetLastError();
+}
+// One trajectory spread over several GPUs: a shard's statistics (count, means, centred cross-covariance, sum |src_c|^2:
+// SIM3_STAT doubles) ...
+cudaError_t launch_sim3_partial_stats(const double* src, const double* dst, const long long* offsets2, const unsigned char* mask, long long n,
+                                      double* work, double* stats_out, cudaStream_t stream) {
+    const int tiles = sim3_tiles_for(n);
+    dim3 grid(tiles, 1);
+    sim3_tile_stats_kernel<<<grid, 256, 0, stream>>>(src, dst, offsets2, mask, tiles, sim3_tile_len(n), work);
+    sim3_finalize_kernel<<<1, 128, 0, stream>>>(work, tiles, 1, nullptr, nullptr, nullptr, nullptr, stats_out);
+    return cudaGetLastError();
+}
+// ... and R, t, s from the statistics of all shards, merged in shard order with the pairwise covariance update.
+cudaError_t launch_sim3_from_partial_stats(const double* stats, int shards, double* R, double* t, double* s, int* status, cudaStream_t stream) {
+    sim3_finalize_kernel<<<1, 128, 0, stream>>>(stats, shards, 1, R, t, s, status, nullptr);
     return cudaGetLastError();
 }
 cudaError_t launch_sim3_apply(const double* pos, const double* quat, const long long* offsets, const double* R, const double* t,

@@ -422,6 +422,40 @@ def umeyama_batched(src, dst, offsets, max_len, mask=None, stream=None):
     return R, t, s, status
 
 
+SIM3_STATS = 20        # GSF_SIM3_STATS: count, mean src, mean dst, centred H, sum |src_c|^2, padding
+
+
+def sim3_partial_stats(src, dst, mask=None, stream=None):
+    """One shard's contribution to compute_sim3_transform of a trajectory spread over several GPUs
+    (gsf_sim3_partial_stats_dev) -> [SIM3_STATS] float64."""
+    lib = _lib.load()
+    _require_cuda(src, dst, mask)
+    n = int(src.shape[0])
+    dev = src.device
+    off = torch.tensor([0, n], dtype=torch.int64, device=dev)
+    work = torch.empty((max(1, lib.gsf_umeyama_work_doubles(1, n)),), dtype=torch.float64, device=dev)
+    stats = torch.empty((SIM3_STATS,), dtype=torch.float64, device=dev)
+    rc = lib.gsf_sim3_partial_stats_dev(_ptr(src), _ptr(dst), _ptr(off), _ptr(mask), n, _ptr(work), _ptr(stats), _stream_ptr(stream))
+    _lib.check(rc, "gsf_sim3_partial_stats_dev")
+    return stats
+
+
+def sim3_from_partial_stats(stats, stream=None):
+    """R [3,3], t [3], s [1], status [1] from the statistics of all shards, [shards, SIM3_STATS] in shard order
+    (gsf_sim3_from_partial_stats_dev)."""
+    lib = _lib.load()
+    _require_cuda(stats)
+    stats = stats.contiguous()
+    dev = stats.device
+    R = torch.empty((3, 3), dtype=torch.float64, device=dev)
+    t = torch.empty((3,), dtype=torch.float64, device=dev)
+    s = torch.empty((1,), dtype=torch.float64, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    rc = lib.gsf_sim3_from_partial_stats_dev(_ptr(stats), int(stats.shape[0]), _ptr(R), _ptr(t), _ptr(s), _ptr(status), _stream_ptr(stream))
+    _lib.check(rc, "gsf_sim3_from_partial_stats_dev")
+    return R, t, s, status
+
+
 def sim3_apply_batched(pos, quat, offsets, max_len, R, t, s, stream=None):
     """transform_trajectory for B trajectories -> (pos', quat', status)."""
     lib = _lib.load()

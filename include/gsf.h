@@ -209,6 +209,17 @@ int gsf_sim3_umeyama_batched_dev(const double* src, const double* dst, const int
                                  const uint8_t* mask, int32_t B, int64_t max_len, double* work,
                                  double* R, double* t, double* s, int32_t* status, void* stream);
 
+/* ---- compute_sim3_transform (:428-459) for ONE trajectory whose points are spread over several GPUs (BASELINE config 4
+ *      sharded): every rank reduces its shard to GSF_SIM3_STATS doubles -- count, mean src [3], mean dst [3],
+ *      centred cross-covariance [9] (not / n), sum |src - mean|^2, 3 of padding -- the ranks exchange them (an all-gather
+ *      of 160 bytes each) and every rank merges them in shard order (pairwise covariance update, deterministic) and finishes.
+ *      offsets2 = {0, n} on the device; mask NULL or one byte per point; work: gsf_umeyama_work_doubles(1, n) doubles.
+ *      stats [shards, GSF_SIM3_STATS]; R [9], t [3], s [1], status [1]. */
+#define GSF_SIM3_STATS 20
+int gsf_sim3_partial_stats_dev(const double* src, const double* dst, const int64_t* offsets2, const uint8_t* mask, int64_t n,
+                               double* work, double* stats, void* stream);
+int gsf_sim3_from_partial_stats_dev(const double* stats, int32_t shards, double* R, double* t, double* s, int32_t* status, void* stream);
+
 /* ---- compute_sim3_transform_robust (:389-426) with HOST-SUPPLIED sample indices: `samples`
  *      [trials, min_samples] int32 (device) holds what the reference draws with
  *      np.random.choice(n, min_samples, replace=False) in each trial (:408), so a seeded reference

@@ -411,6 +411,28 @@ def test_warp_kernel_matches_role_kernel(gsf, monkeypatch):
     assert int((a[3] == 0).sum()) == 280          # 1, 2 and 3 poses: not enough points for the Sim3 (status set, same in both)
 
 
+def test_sim3_partial_stats_merge_equals_whole_fit(gsf):
+    """A trajectory cut into shards (gsf_sim3_partial_stats_dev per shard, gsf_sim3_from_partial_stats_dev over all) gives the
+    Umeyama fit of the whole point set (gsf_sim3_umeyama_batched_dev): masks, an empty shard and a one-point shard included."""
+    rng = np.random.default_rng(12)
+    n = 50000
+    src = np.cumsum(rng.normal(0, 1.0, (n, 3)), axis=0)
+    th = 0.7; Rg = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    dst = 1.07 * src @ Rg.T + [455000.0, 5431000.0, 110.0] + rng.normal(0, 0.3, (n, 3))
+    mask = rng.uniform(size=n) > 0.1
+    dst[~mask] = np.nan
+    R, t, s, st = gsf.umeyama_batched(dev(src), dev(dst), dev(np.array([0, n]), torch.int64), n, mask=dev(mask, torch.uint8))
+    cuts = [0, 17000, 17000, 17001, 40000, n]                       # shards of 17000, 0, 1, 22999, 10000 points
+    parts = [gsf.sim3_partial_stats(dev(src[a:b]), dev(dst[a:b]), mask=dev(mask[a:b], torch.uint8)) if b > a
+             else torch.zeros(gsf.SIM3_STATS, dtype=torch.float64, device="cuda") for a, b in zip(cuts[:-1], cuts[1:])]
+    R2, t2, s2, st2 = gsf.sim3_from_partial_stats(torch.stack(parts))
+    assert int(st.cpu()[0]) == 0 and int(st2.cpu()[0]) == 0
+    assert float(parts[0][0]) == mask[:17000].sum() and float(parts[2][0]) == float(mask[17000])
+    np.testing.assert_allclose(R2.cpu().numpy(), R.cpu().numpy()[0], rtol=0, atol=1e-10)       # (the merge order of the sums differs)
+    np.testing.assert_allclose(s2.cpu().numpy(), s.cpu().numpy(), rtol=1e-11, atol=0)
+    np.testing.assert_allclose(t2.cpu().numpy(), t.cpu().numpy()[0], rtol=0, atol=1e-6)
+
+
 def test_fused_call_replays_from_a_cuda_graph(gsf):
     """gsf_fuse_batched_dev inside a stream capture (its memset and both kernels become graph nodes): replays give the
     eager call's bits, also for a batch with deferred (outage) trajectories.  bench.py times config 2 this way."""
