@@ -125,7 +125,7 @@ def sharp_turn(ts, quat, offsets, thresh, stream=None):
     return flags, rate
 
 
-def gnss_rows_to_utm(rows, want_ts=True, stream=None):
+def gnss_rows_to_utm(rows, want_ts=True, stream=None, out_ts=None, out_xyz=None):
     """Fused GNSS ingest (gsf_gnss_rows_to_utm_dev): rows [n,4] = ts, lat, lon, alt ->
     (ts [n] or None, xyz [n,3] = E, N, alt with NaN rows where the validity mask fails,
     zone [5] = mean lon, mean lat, zone, south, valid count); asynchronous, zone stays on the device."""
@@ -135,8 +135,8 @@ def gnss_rows_to_utm(rows, want_ts=True, stream=None):
     dev = rows.device
     part = torch.empty((3 * _lib.GEO_PARTS,), dtype=torch.float64, device=dev)
     zone = torch.empty((5,), dtype=torch.float64, device=dev)
-    ts = torch.empty((n,), dtype=torch.float64, device=dev) if want_ts else None
-    xyz = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    ts = out_ts if out_ts is not None else (torch.empty((n,), dtype=torch.float64, device=dev) if want_ts else None)
+    xyz = out_xyz if out_xyz is not None else torch.empty((n, 3), dtype=torch.float64, device=dev)      # (contiguous views of a caller's buffer)
     rc = lib.gsf_gnss_rows_to_utm_dev(_ptr(rows), int(n), _ptr(part), _ptr(zone), _ptr(ts), _ptr(xyz), _stream_ptr(stream))
     _lib.check(rc, "gsf_gnss_rows_to_utm_dev")
     return ts, xyz, zone

@@ -1,7 +1,9 @@
-"""Multi-GPU plumbing of the batched path: independent trajectories (or noise hypotheses) are
-sharded by contiguous ranges, one process per GPU; there is no collective inside the data path.
-The only exchange is the final gather of per-trajectory ATE statistics (torch.distributed:
-NCCL over NVLink on the GPUs, gloo in the CPU tests)."""
+"""Multi-GPU plumbing.  Batched path: independent trajectories (or noise hypotheses) are sharded by
+contiguous ranges, one process per GPU; there is no collective inside the data path, the only
+exchange is the final gather of per-trajectory ATE statistics.  One long trajectory (config 4): the
+poses are cut into contiguous blocks and three small all-gathers carry what crosses the cuts (zone
+means, spline halo knots, Umeyama statistics).  torch.distributed: NCCL over NVLink on the GPUs,
+gloo in the CPU tests."""
 from __future__ import annotations
 
 import torch
@@ -81,8 +83,9 @@ def all_gather_rows(local: torch.Tensor) -> torch.Tensor:
 
 def global_zone(zone_local: torch.Tensor):
     """zone [5] = mean lon, mean lat, zone, south, valid count of THIS rank's rows (gsf_gnss_rows_to_utm_dev) ->
-    (zone, south) of the whole track (auto_utm_projection, EKFGPSSLAM.py:127-134, from the count-weighted means) and whether
-    this rank's projection used them.  One all-gather of 5 doubles per rank; the result comes back to the host (one sync)."""
+    (zone, south) of the whole track (auto_utm_projection, EKFGPSSLAM.py:127-134, from the count-weighted means), whether
+    this rank's projection used them, and the valid-row counts of all ranks (list).  One all-gather of 5 doubles per rank; the
+    result comes back to the host (one synchronisation)."""
     z = all_gather_rows(zone_local).cpu()
     cnt = z[:, 4]
     tot = float(cnt.sum())
@@ -95,7 +98,7 @@ def global_zone(zone_local: torch.Tensor):
     south = mean_lat < 0.0
     rank, _ = _world()
     mine_ok = (not bool(w[rank])) or (int(z[rank, 2]) == zone and bool(z[rank, 3] != 0) == south)
-    return zone, south, mine_ok
+    return zone, south, mine_ok, [int(c) for c in cnt]
 
 
 def exchange_halo(t_local: torch.Tensor, xyz_local: torch.Tensor, halo: int = ASSOC_HALO):
@@ -129,24 +132,44 @@ def long_trajectory_sharded(rows_local, slam_ts_local, slam_pos_local, slam_quat
     """GNSS ingest -> spline association -> Sim3 (Umeyama over the whole track) -> transform, for ONE trajectory whose
     poses are split into contiguous blocks over the ranks.  rows_local [m,4] = ts, lat, lon, alt (GNSS samples of this
     block, sorted), slam_* the SLAM poses of this block.  Returns (aligned [n,3], valid [n], R, t, s, out_pos, out_quat,
-    zone); R, t, s are identical on every rank."""
+    (zone, south), association status, Sim3 status); R, t, s are identical on every rank."""
     from . import fusion
     rank, world = _world()
     dev = rows_local.device
-    # 1. ingest with the zone of the whole track
-    g_ts, g_xyz, zone_local = fusion.gnss_rows_to_utm(rows_local)
-    zone, south, mine_ok = global_zone(zone_local)
+    m, h = int(rows_local.shape[0]), ASSOC_HALO
+    # 1. ingest with the zone of the whole track, written into buffers that have room for the neighbours' knots on both sides
+    t_buf = torch.empty((m + 2 * h,), dtype=torch.float64, device=dev)
+    x_buf = torch.empty((m + 2 * h, 3), dtype=torch.float64, device=dev)
+    g_ts, g_xyz = t_buf[h:h + m], x_buf[h:h + m]
+    _, _, zone_local = fusion.gnss_rows_to_utm(rows_local, out_ts=g_ts, out_xyz=g_xyz)
+    zone, south, mine_ok, counts = global_zone(zone_local)
     if not mine_ok:                                         # this block's own means point to another zone: project again
         e, nn = fusion.utm_forward(rows_local[:, 2].contiguous(), rows_local[:, 1].contiguous(), zone, south)
         bad = torch.isnan(g_xyz[:, 0])
-        g_xyz = torch.stack([e, nn, rows_local[:, 3]], dim=1)
+        g_xyz[:, 0] = e; g_xyz[:, 1] = nn
         g_xyz[bad] = float("nan")
-    keep = ~torch.isnan(g_xyz[:, 0])
-    if not bool(keep.all()):
-        g_ts, g_xyz = g_ts[keep].contiguous(), g_xyz[keep].contiguous()
-    # 2. association: the neighbours' edge knots make the local spline solve exact to its halo bound
-    t_ext, xyz_ext, _ = exchange_halo(g_ts, g_xyz)
-    aligned, valid, status = fusion.associate_spline_long(t_ext, xyz_ext, slam_ts_local, gap)
+    if counts[rank] != m:                                   # invalid rows: the spline takes the valid knots only
+        keep = ~torch.isnan(g_xyz[:, 0])
+        kt, kx = g_ts[keep], g_xyz[keep]
+        m = int(kt.shape[0])
+        t_buf = torch.empty((m + 2 * h,), dtype=torch.float64, device=dev); x_buf = torch.empty((m + 2 * h, 3), dtype=torch.float64, device=dev)
+        t_buf[h:h + m] = kt; x_buf[h:h + m] = kx
+        g_ts, g_xyz = t_buf[h:h + m], x_buf[h:h + m]
+    # 2. association: the neighbours' edge knots (one all-gather) go into the margins -- no copy of the block itself
+    k_l = min(h, counts[rank - 1]) if rank > 0 else 0
+    k_r = min(h, counts[rank + 1]) if rank < world - 1 else 0
+    if world > 1:
+        edge = torch.full((2, h, 4), float("nan"), dtype=torch.float64, device=dev)
+        k = min(h, m)
+        if k > 0:
+            edge[0, :k, 0] = g_ts[:k]; edge[0, :k, 1:] = g_xyz[:k]
+            edge[1, h - k:, 0] = g_ts[m - k:]; edge[1, h - k:, 1:] = g_xyz[m - k:]
+        alle = all_gather_rows(edge)
+        if k_l:
+            t_buf[h - k_l:h] = alle[rank - 1, 1, h - k_l:, 0]; x_buf[h - k_l:h] = alle[rank - 1, 1, h - k_l:, 1:]
+        if k_r:
+            t_buf[h + m:h + m + k_r] = alle[rank + 1, 0, :k_r, 0]; x_buf[h + m:h + m + k_r] = alle[rank + 1, 0, :k_r, 1:]
+    aligned, valid, status = fusion.associate_spline_long(t_buf[h - k_l:h + m + k_r], x_buf[h - k_l:h + m + k_r], slam_ts_local, gap)
     # 3. Umeyama: every shard's statistics, merged in rank order on every rank
     stats = all_gather_rows(fusion.sim3_partial_stats(slam_pos_local, aligned, mask=valid))
     R, t, s, st = fusion.sim3_from_partial_stats(stats)

@@ -71,7 +71,8 @@ def _halo_worker(rank, world, port, lens, out_dir):
     # zone record of this rank: mean lon, mean lat, zone, south, valid count (rank 1 of 3 has no valid row)
     zones = {0: [8.4, 49.0, 32.0, 0.0, 100.0], 1: [float("nan"), float("nan"), float("nan"), 0.0, 0.0], 2: [13.1, 49.2, 33.0, 0.0, 300.0]}
     z = torch.tensor(zones.get(rank, zones[0]), dtype=torch.float64)
-    zone, south, mine_ok = sharding.global_zone(z)
+    zone, south, mine_ok, counts = sharding.global_zone(z)
+    assert counts == [int(zones.get(r, zones[0])[4]) for r in range(world)]
     rows = sharding.all_gather_rows(torch.full((3,), float(rank), dtype=torch.float64))
     torch.save({"t": t_ext, "xyz": xyz_ext, "n_left": n_left, "zone": (zone, south, mine_ok), "rows": rows}, os.path.join(out_dir, f"h{rank}.pt"))
     dist.destroy_process_group()
