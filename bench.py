@@ -51,7 +51,8 @@ class ClockSampler:
     (an `nvidia-smi -lms` child needs longer to start than a 0.3 s timed region lasts); nvidia-smi only if NVML is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+            "applications_clocks_setting": 0x2, "sync_boost": 0x10, "hw_power_brake_slowdown": 0x80, "display_clock_setting": 0x100}
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -100,13 +101,17 @@ class ClockSampler:
                 self.thread.join(timeout=1.0)
             rows = [r for r in self.rows if r[0] >= self.t_mark]
             sm = [r[1] for r in rows]
-            reasons = {n for n in names for r in rows if r[2] & self.BITS[n]}
+            reasons = {n for n in self.BITS for r in rows if r[2] & self.BITS[n]}
+            bits = 0
+            for r in rows:
+                bits |= r[2]
             try:
                 self.nvml.nvmlShutdown()
             except Exception:
                 pass
             return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
-                    "samples": len(sm), "source": "NVML, 5 ms polling"}
+                    "samples": len(sm), "source": "NVML, 5 ms polling", "reason_bits": hex(bits & ~0x1),
+                    "sm_mhz_min": min(sm) if sm else None, "sm_mhz_max_seen": max(sm) if sm else None}
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
