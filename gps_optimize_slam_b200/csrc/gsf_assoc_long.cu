@@ -3,21 +3,21 @@
 // spline of a segment with one serial Thomas sweep per axis -- fine for 271 knots, hopeless for 1e8.  Here the solve is
 // LOCAL: the spline's tridiagonal system is diagonally dominant (|off-diagonal| <= diagonal / 2 for any knot spacing), so the
 // influence of a boundary value on the moment k knots away decays at least like (2 - sqrt 3)^k = 0.268^k.  Every thread
-// owns AL_CH = 15 consecutive knots and solves the system on its chunk widened by a halo of AL_H = 20 knots on both sides,
+// owns AL_CH = 13 consecutive knots and solves the system on its chunk widened by a halo of AL_H = 20 knots on both sides,
 // with a natural end (m = 0) where the halo cuts the segment and the true not-a-knot rows where the segment really ends
 // inside the halo; only the chunk's own moments are kept.  The cut moment is wrong by its own size, and 0.268^20 = 3.7e-12
 // of that reaches the chunk: for GNSS noise of 0.3 m at 10 Hz (second differences of 30 m/s^2, a curvature term of
 // m h^2 / 8 = 4 cm in the interpolant) that is 1.5e-13 m, far below one ulp of a UTM coordinate (9.3e-10 m) -- the values
 // equal the global solve's (the test compares with scipy and with the serial kernel).
 //
-// Layout of the moments kernel: a block of 128 threads stages its window of 1920 + 2 x 22 knots (t and xyz, exactly as they
-// lie in global memory: 15- and 45-double strides between threads are conflict-free) with two TMA bulk copies, so every knot
+// Layout of the moments kernel: a block of 128 threads stages its window of 1664 + 2 x 22 knots (t and xyz, exactly as they
+// lie in global memory: 13- and 39-double strides between threads are conflict-free) with two TMA bulk copies, so every knot
 // comes from DRAM once (the halo twice).  A thread eliminates forward from the left end of its window to the last knot of its
-// chunk, keeping the eliminated rows of its own 15 knots in REGISTERS (fully unrolled, predicated on the segment limits),
+// chunk, keeping the eliminated rows of its own 13 knots in REGISTERS (fully unrolled, predicated on the segment limits),
 // eliminates from the right end of the window down to the knot after its chunk keeping nothing, joins the two at the chunk's
 // last row (a 2 x 2 system) and back-substitutes through its registers.  (First version: 64-knot chunks with the whole
 // widened system in local memory -- 9.8 ms for 1e8 knots, 4.2x the algorithmic DRAM traffic from local-memory spills; this one:
-// 1.9 ms.)  Only the INTERIOR moments of a segment are stored; the two end moments follow from the not-a-knot rows
+// 1.7 ms.)  Only the INTERIOR moments of a segment are stored; the two end moments follow from the not-a-knot rows
 // (m_a = ((h0 + h1) m_{a+1} - h0 m_{a+2}) / h1) and are formed by the evaluation when a stamp falls into a segment's first or
 // last interval.  Segments split at gaps > max_gps_gap_threshold (:351-354); 2-3 knot segments are linear (:362), single
 // knots give nothing (:361).  A block whose window holds no gap and no end of the track (the usual case) skips the walk to
@@ -34,7 +34,19 @@
 
 namespace gsf {
 
-constexpr int AL_CH = 15;                         // knots per thread (odd: conflict-free shared-memory strides of 15 and 45 doubles)
+#ifndef GSF_AL_CH
+#define GSF_AL_CH 13                  // 13: 1.71 ms per 1e8 knots; 15: 1.87 (register spills at 168); 17 with two blocks per SM: 1.71
+#endif
+#ifndef GSF_AL_MINB
+#define GSF_AL_MINB 3
+#endif
+#ifndef GSF_EV_PER
+#define GSF_EV_PER 8
+#endif
+#ifndef GSF_EV_MINB
+#define GSF_EV_MINB 4
+#endif
+constexpr int AL_CH = GSF_AL_CH;                  // knots per thread (odd: conflict-free shared-memory strides of AL_CH and 3 AL_CH doubles)
 constexpr int AL_H = 20;                          // halo
 constexpr int AL_NT = 128;
 constexpr int AL_TILE = AL_CH * AL_NT;            // knots per block
@@ -42,7 +54,7 @@ constexpr int AL_PADW = AL_H + 2;                 // window margin (even, so tha
 constexpr int AL_W = AL_TILE + 2 * AL_PADW;
 constexpr size_t AL_SMEM = (size_t)AL_W * 32 + 16;
 
-__global__ void __launch_bounds__(AL_NT, 3) assoc_long_moments_kernel(const double* __restrict__ gt, const double* __restrict__ gy, long long M, double gap,
+__global__ void __launch_bounds__(AL_NT, GSF_AL_MINB) assoc_long_moments_kernel(const double* __restrict__ gt, const double* __restrict__ gy, long long M, double gap,
                                                                       double* __restrict__ mom, int* __restrict__ bad_steps, int use_tma) {
     extern __shared__ __align__(16) double al_sm[];
     double* Yv = al_sm;                           // [AL_W][3]
@@ -215,9 +227,9 @@ __device__ __forceinline__ void warp_bracket(const double* __restrict__ gt, long
 }
 
 constexpr int EV_NT = 256;
-constexpr int EV_PER = 8;                        // stamps per thread: one bracket search serves EV_NT * EV_PER stamps
+constexpr int EV_PER = GSF_EV_PER;                        // stamps per thread: one bracket search serves EV_NT * EV_PER stamps
 constexpr int EV_TILE = EV_NT * EV_PER;
-constexpr int EV_CAP = 3072;                     // knot times of the block's bracket staged in shared memory
+constexpr int EV_CAP = EV_TILE + EV_TILE / 2;                     // knot times of the block's bracket staged in shared memory
 constexpr int EV_MARGIN = 3;                     // knots around the bracket that the segment tests read
 
 // Interpolant on the interval [j, j+1] (knot times tj, tn) of a segment that has nl / nr (0..2) more knots on the left / right;
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(256) assoc_long_bracket_kernel(const double* _
     if (lane == 0) { brackets[2 * w] = l; brackets[2 * w + 1] = r2; }
 }
 
-__global__ void __launch_bounds__(EV_NT, 4) assoc_long_eval_kernel(const double* __restrict__ gt, const double* __restrict__ gy, const double* __restrict__ mom,
+__global__ void __launch_bounds__(EV_NT, GSF_EV_MINB) assoc_long_eval_kernel(const double* __restrict__ gt, const double* __restrict__ gy, const double* __restrict__ mom,
                                                                 long long M, const double* __restrict__ st, long long N, double gap,
                                                                 const long long* __restrict__ brackets, double* __restrict__ out,
                                                                 unsigned char* __restrict__ val) {

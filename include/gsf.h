@@ -279,7 +279,7 @@ int gsf_associate_spline_dev(const double* gps_t, const double* gps_xyz, const i
                              double* work, double* aligned, uint8_t* valid, void* stream);
 
 /* ---- the same for ONE trajectory of any size (BASELINE config 4: 1e8 samples): the not-a-knot system is solved locally --
- *      15-knot chunks with a 20-knot halo on both sides, natural ends where the halo cuts a segment, the true end rows where
+ *      13-knot chunks with a 20-knot halo on both sides, natural ends where the halo cuts a segment, the true end rows where
  *      the segment ends inside it; the cut decays like 0.268^20 = 4e-12 of a centimetre-sized curvature term, below fp64
  *      rounding of the coordinates -- and the evaluation searches each SLAM stamp inside the knot bracket of its tile of
  *      2048 stamps.  gps_t [M] sorted and unique, gps_xyz [M,3], slam_t [N] (any order; sorted stamps keep the brackets

@@ -350,7 +350,7 @@ def test_association_kernel_matches_reference_golden(gsf, case):
 
 
 def test_association_long_trajectory_local_halo(gsf):
-    """gsf_associate_spline_long_dev (local-halo solve, 15-knot chunks in registers) against scipy's interp1d per segment
+    """gsf_associate_spline_long_dev (local-halo solve, 13-knot chunks in registers) against scipy's interp1d per segment
     (what dynamic_time_alignment calls, EKFGPSSLAM.py:351-380) and against the serial per-trajectory kernel: irregular
     knot spacing, gaps that cut segments of 1, 2, 3, 4, 5, 31, 32, 33, 64, 65 and thousands of knots, stamps exactly on
     knots / segment ends / inside gaps / outside the track; plus the golden cases (271 knots)."""
@@ -471,13 +471,15 @@ def _ragged_batch(gsf, lens):
 
 
 def test_association_long_gaps_at_chunk_and_block_edges(gsf):
-    """Segment ends placed on and next to the boundaries of the moments kernel's work split (15-knot chunks, 1920-knot blocks,
+    """Segment ends placed on and next to the boundaries of the moments kernel's work split (13-knot chunks, 1664-knot blocks; the 15 / 1920 of an earlier layout stay in the list,
     22-knot window margins, 20-knot halos) and next to the ends of the track, sorted stamps (staged evaluation) that include
     every knot: against scipy per segment (oracle)."""
     from oracle import fusion_oracle as fo
     rng = np.random.default_rng(33)
     M = 6000
     edge_sets = [
+        [1663, 1664, 1665], [1651, 1677], [1642, 1643, 1644, 1685, 1686], [12, 13, 14, 25, 26, 27], [3327, 3328, 3329, 3341], [1664 - 20, 1664 + 19],
+        [1664 - 21, 1664 + 20, 1664 + 21], list(range(1640, 1700, 4)),
         [1919, 1920, 1921], [1905, 1935], [1898, 1899, 1900, 1941, 1942], [14, 15, 16, 29, 30, 31], [3839, 3840, 3841, 3855, 3860],
         [1, 2, 3], [4, 5996], [5995, 5996, 5997, 5998], [1920 - 20, 1920 + 19], [1920 - 21, 1920 + 20, 1920 + 21], [3, 7, 11, 15, 19, 23, 27],
         list(range(1900, 1960, 4)), [],
