@@ -514,16 +514,20 @@ def main():
             config5 = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- config 4 (one 1e8-sample trajectory: ingest + spline association + Umeyama reduction + transform) as a sub-record:
-    #      specified for one GPU (replicas only), so rank 0 runs it while the others wait
+    #      one GPU: the pipeline with per-stage times; several GPUs: the trajectory cut into contiguous blocks over the ranks
+    #      (three small all-gathers), so that the driver's scaling run carries it
     config4 = None
     if not args.no_config5 and args.workload == "config3":
-        if rank == 0:
-            try:
+        try:
+            if world == 1:
                 a4 = argparse.Namespace(poses=0, steps=3, warmup=3)
                 config4 = bw.measure_config4(a4, local_rank, ClockSampler, read_peak, with_cpu=False)
-            except Exception as exc:
-                config4 = {"error": f"{type(exc).__name__}: {exc}"}
-            torch.cuda.empty_cache()
+            else:
+                a4 = argparse.Namespace(poses=0, steps=10, warmup=5)
+                config4 = bw.measure_config4_sharded(a4, rank, local_rank, world, ClockSampler, read_peak)
+        except Exception as exc:
+            config4 = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
         barrier()
 
     # ---- optional fp32 mode (gsf_fuse_batched_f32_dev) on a slab of the same generator: fp32 storage relative to fp64 origins
