@@ -131,7 +131,7 @@ def exchange_halo(t_local: torch.Tensor, xyz_local: torch.Tensor, halo: int = AS
 def long_trajectory_sharded(rows_local, slam_ts_local, slam_pos_local, slam_quat_local, gap: float = 5.0):
     """GNSS ingest -> spline association -> Sim3 (Umeyama over the whole track) -> transform, for ONE trajectory whose
     poses are split into contiguous blocks over the ranks.  rows_local [m,4] = ts, lat, lon, alt (GNSS samples of this
-    block, sorted), slam_* the SLAM poses of this block.  Returns (aligned [n,3], valid [n], R, t, s, out_pos, out_quat,
+    block, sorted; at least 22 valid ones per rank), slam_* the SLAM poses of this block.  Returns (aligned [n,3], valid [n], R, t, s, out_pos, out_quat,
     (zone, south), association status, Sim3 status); R, t, s are identical on every rank."""
     from . import fusion
     rank, world = _world()
@@ -143,6 +143,8 @@ def long_trajectory_sharded(rows_local, slam_ts_local, slam_pos_local, slam_quat
     g_ts, g_xyz = t_buf[h:h + m], x_buf[h:h + m]
     _, _, zone_local = fusion.gnss_rows_to_utm(rows_local, out_ts=g_ts, out_xyz=g_xyz)
     zone, south, mine_ok, counts = global_zone(zone_local)
+    if world > 1 and min(counts) < h:                       # the halo comes from the direct neighbours only
+        raise ValueError(f"every rank needs at least {h} valid GNSS samples of the trajectory (got {counts})")
     if not mine_ok:                                         # this block's own means point to another zone: project again
         e, nn = fusion.utm_forward(rows_local[:, 2].contiguous(), rows_local[:, 1].contiguous(), zone, south)
         bad = torch.isnan(g_xyz[:, 0])
