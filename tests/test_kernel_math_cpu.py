@@ -193,3 +193,37 @@ def test_text_conversions_match_python(hostmath):
     for x in (0.0, -0.0, float("nan"), float("inf"), -float("inf"), 0.5, 1.5, 2.5, 9.9999999999, 999999.9999995):
         n = hostmath.hm_format_fixed(x, 6, buf, ctypes.byref(flag))
         assert buf.raw[:n].decode() == "%.6f" % x
+
+
+def test_local_halo_spline_solve_matches_global_solve():
+    """The algorithm of csrc/gsf_assoc_long.cu in numpy (oracle/assoc_long_model.py: 13-knot chunks, 20-knot halos, forward
+    elimination + elimination from the far end joined at the chunk's last row) against the global not-a-knot solve per
+    segment (scipy CubicSpline = the spline behind interp1d(kind='cubic'), EKFGPSSLAM.py:351-380): irregular spacing, gaps
+    that cut segments of 3, 1, 4 and hundreds of knots.  The halo bound is 0.268^20 = 3.7e-12 of the moments' size; a
+    6-knot halo shows the decay it rests on."""
+    from scipy.interpolate import CubicSpline
+    from oracle.assoc_long_model import local_halo_moments
+    rng = np.random.default_rng(3)
+    M = 700
+    steps = np.minimum(rng.uniform(0.02, 0.4, M) * rng.choice([1.0, 1.0, 5.0], M), 4.0)
+    for k in (100, 103, 104, 108, 400, 640):
+        steps[k] = rng.uniform(5.5, 8.0)
+    t = 10 + np.cumsum(steps)
+    y = 5e6 + 8 * t + 30 * np.sin(t / 7) + rng.normal(0, 0.3, M)
+    h = np.diff(t)
+    ss = np.concatenate([[0], np.nonzero(h > 5)[0] + 1]); se = np.concatenate([ss[1:] - 1, [M - 1]])
+
+    def worst(H):
+        m = local_halo_moments(t, y, gap=5.0, CH=13, H=H)
+        w = 0.0
+        for a, b in zip(ss, se):
+            if b - a + 1 < 4:
+                assert np.isnan(m[a:b + 1]).all()                      # linear / skipped segments: no moments
+                continue
+            mg = CubicSpline(t[a:b + 1], y[a:b + 1], bc_type="not-a-knot")(t[a:b + 1], 2)
+            assert np.isnan(m[a]) and np.isnan(m[b])                   # end moments are formed at evaluation time
+            w = max(w, np.abs(m[a + 1:b] - mg[1:-1]).max() / np.abs(mg).max())
+        return w
+
+    assert worst(20) < 1e-11
+    assert 1e-9 < worst(6) < 0.268 ** 6 * 4
